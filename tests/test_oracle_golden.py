@@ -1,0 +1,102 @@
+"""Pins the CPU oracle against the reference's own golden vectors: the blockhash256 values in
+lib/zosimos/tests/reference/*.crc.png (copied to tests/golden/reference_hashes.json) for the
+pipelines of lib/zosimos/tests/blend.rs and knobs.rs, run on the reference's own input images."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import refpipes as R
+
+
+def rgba_image(arr):
+    h, w, _ = arr.shape
+    return O.Image(O.srgb_rgba8(w, h), arr.reshape(h, w * 4))
+
+
+def as_rgba(img):
+    return img.data.reshape(img.desc.height, img.desc.width, 4)
+
+
+def check(golden_hashes, key, img):
+    h = O.blockhash256(as_rgba(img))
+    assert h in golden_hashes[key], (key, h, golden_hashes[key])
+
+
+def test_blockhash_of_fixture(fixtures, golden_hashes):
+    # swapped / convert_bt709 / crt all hash like the untouched background (r+g+b is preserved)
+    assert O.blockhash256(fixtures["background"]) in golden_hashes["swapped"]
+
+
+def test_composed(fixtures, golden_hashes):
+    bg, fg = rgba_image(fixtures["background"]), rgba_image(fixtures["foreground"])
+    out = O.inscribe(bg, (0, 0, fg.desc.width, fg.desc.height), fg)
+    check(golden_hashes, "composed", out)
+    # the Rectangle::normalize quirk (command.rs:3536-3543) is pinned: the strict placement hashes differently
+    strict = O.inscribe(bg, (0, 0, fg.desc.width, fg.desc.height), fg, exact_quirks=False)
+    assert O.blockhash256(as_rgba(strict)) not in golden_hashes["composed"]
+
+
+def test_affine(fixtures, golden_hashes):
+    bg, fg = rgba_image(fixtures["background"]), rgba_image(fixtures["foreground"])
+    m = R.affine_matrix_blend_rs(fg.desc.width, fg.desc.height, bg.desc.width, bg.desc.height)
+    check(golden_hashes, "affine", O.affine(bg, m, fg))
+
+
+def test_adapted(fixtures, golden_hashes):
+    check(golden_hashes, "adapted", O.chromatic_adaptation(rgba_image(fixtures["background"]), "vonkries", "D50"))
+
+
+def test_convert_bt709(fixtures, golden_hashes):
+    bg = fixtures["background"]
+    src = O.Image(O.Desc(512, 512, O.RGBA8, O.BT709_RGB), bg.reshape(512, -1))
+    check(golden_hashes, "convert_bt709", O.color_convert(src, O.SRGB, O.RGBA8))
+
+
+def test_swapped(fixtures, golden_hashes):
+    bg = rgba_image(fixtures["background"])
+    r, g = O.extract(bg, "R"), O.extract(bg, "G")
+    out = O.inject(O.inject(bg, "G", r), "R", g)
+    check(golden_hashes, "swapped", out)
+    a = as_rgba(out); b = fixtures["background"]
+    # the single-channel registers are staged (f16 texture + truncating pack): each trip may lose 1 LSB
+    d = a.astype(int) - b[..., [1, 0, 2, 3]].astype(int)
+    assert d.max() <= 0 and d.min() >= -2
+    assert np.array_equal(a[..., 3], b[..., 3])
+
+
+def lch_pipeline(color):
+    grid = O.bilinear(O.Desc(400, 400, O.RGBA8, O.SCALARS_LINEAR), R.LCH_GRID)
+    lch = O.transmute(grid, O.Desc(400, 400, O.Texel(O.B_UINT8X4, O.P_LCHA), color))
+    return O.color_convert(lch, O.SRGB, O.RGBA8)
+
+
+def test_oklab(golden_hashes):
+    check(golden_hashes, "oklab", lch_pipeline(O.OKLAB))
+
+
+def test_srlab2(golden_hashes):
+    check(golden_hashes, "srlab2", lch_pipeline(O.Color("srlab2", whitepoint="D65")))
+
+
+def test_solid(golden_hashes):
+    check(golden_hashes, "solid", O.solid(O.srgb_rgba8(400, 400), [0.5, 0.5, 1.0, 1.0]))
+
+
+@pytest.mark.parametrize("name", sorted(R.DERIVATIVES))
+def test_derivative(fixtures, golden_hashes, name):
+    out = O.derivative(rgba_image(fixtures["background"]), R.DERIVATIVES[name])
+    check(golden_hashes, "derived_" + name, out)
+
+
+@pytest.mark.parametrize("idx", range(5))
+def test_bilinear_knob(golden_hashes, idx):
+    um, uM, vm, vM = R.KNOBS[idx]
+    out = O.bilinear(O.srgb_rgba8(512, 512), (um, uM, vm, vM, [0] * 4, [0] * 4))
+    check(golden_hashes, "bilinear-knob-%d" % idx, out)
+
+
+def test_transmute_bytes(fixtures):
+    # tests/blend.rs:371-372: transmuted bytes equal the input bytes
+    bg = rgba_image(fixtures["background"])
+    la16 = O.Desc(512, 512, O.Texel(O.B_UINT16X2, O.P_LUMAA), O.SRGB)
+    assert np.array_equal(O.transmute(bg, la16).data, bg.data)
