@@ -1,0 +1,263 @@
+/* zosimos_cuda.h -- C ABI of the B200 execution backend for zosimos compositing programs.
+ *
+ * This is the drop-in boundary: the entry points a Rust `zosimos-cuda-sys` crate (or any FFI)
+ * binds in place of the reference's wgpu encoder + executor.  Reference = 197g/zosimos; every
+ * declaration cites the reference interface it replaces (paths relative to the reference root).
+ * See INTEGRATION.md for the Rust-side binding.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; every function returns zos_status (0 = ok) and never
+ *     aborts or unwinds (reference: Result<_, LaunchError|StartError|StepError>,
+ *     lib/zosimos/src/program.rs:1997-2006, lib/zosimos/src/run.rs:370-408);
+ *     zos_last_error(ctx) gives a human readable message for the last failure.
+ *   - a zos_ctx owns one CUDA device + one stream; it is NOT thread safe (like `&mut Execution`,
+ *     run.rs:1389); distinct contexts are independent (one per GPU / per host thread).
+ *   - images live in pitch-linear device buffers; rows are padded to 256 bytes exactly like
+ *     Descriptor::to_aligned (lib/zosimos/src/buffer.rs:121-134); use zos_aligned_row_stride.
+ *   - numeric codes for transfer / sample parts / sample bits are the reference's own
+ *     (lib/zosimos/src/shaders/stage.rs:74-119, lib/std/src/stage.frag:107-170).
+ *   - there is NO CPU fallback: without a CUDA device every call fails with ZOS_ERR_CUDA.
+ */
+#ifndef ZOSIMOS_CUDA_H
+#define ZOSIMOS_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZOS_ABI_VERSION 1
+
+typedef int32_t zos_status;
+enum {
+  ZOS_OK = 0,
+  ZOS_ERR_INVALID = 1,        /* bad argument / inconsistent descriptor (CommandErrorKind::BadDescriptor) */
+  ZOS_ERR_UNSUPPORTED = 2,    /* valid but not implemented texel / op (CommandError::UNIMPLEMENTED, todo!()) */
+  ZOS_ERR_CUDA = 3,           /* CUDA runtime / driver failure, or no device */
+  ZOS_ERR_TYPE = 4,           /* operand descriptors do not match (CommandError::TYPE_ERR) */
+  ZOS_ERR_STATE = 5,          /* call not valid in this state (StepError::ProgramEnd, StartError::MissingKey) */
+  ZOS_ERR_OOM = 6
+};
+
+/* ---- texel vocabulary (image-canvas, re-exported by lib/zosimos/src/buffer.rs:2-6) ---- */
+enum { /* Transfer; `as u32` discriminants, stage.frag:107-119 */
+  ZOS_TRANSFER_BT709 = 0, ZOS_TRANSFER_BT470M = 1, ZOS_TRANSFER_BT601 = 2, ZOS_TRANSFER_SMPTE240 = 3,
+  ZOS_TRANSFER_LINEAR = 4, ZOS_TRANSFER_SRGB = 5, ZOS_TRANSFER_BT2020_10BIT = 6, ZOS_TRANSFER_BT2020_12BIT = 7,
+  ZOS_TRANSFER_SMPTE2084 = 8, ZOS_TRANSFER_BT2100PQ = 9, ZOS_TRANSFER_BT2100HLG = 10, ZOS_TRANSFER_LINEAR_SCENE = 11,
+  ZOS_TRANSFER_LABLCH = 0x100 /* shaders/stage.rs:221-226 */
+};
+enum { /* SampleParts, shaders/stage.rs:74-96 */
+  ZOS_PARTS_A = 0, ZOS_PARTS_R = 1, ZOS_PARTS_G = 2, ZOS_PARTS_B = 3, ZOS_PARTS_LUMA = 4, ZOS_PARTS_LUMAA = 5,
+  ZOS_PARTS_RGB = 6, ZOS_PARTS_BGR = 7, ZOS_PARTS_RGBA = 8, ZOS_PARTS_RGBX = 9, ZOS_PARTS_BGRA = 10, ZOS_PARTS_BGRX = 11,
+  ZOS_PARTS_ARGB = 12, ZOS_PARTS_XRGB = 13, ZOS_PARTS_ABGR = 14, ZOS_PARTS_XBGR = 15, ZOS_PARTS_YUV = 16,
+  ZOS_PARTS_LAB = 17, ZOS_PARTS_LABA = 18, ZOS_PARTS_LCH = 19, ZOS_PARTS_LCHA = 20
+};
+enum { /* SampleBits, shaders/stage.rs:98-119 */
+  ZOS_BITS_UINT8 = 0, ZOS_BITS_UINT332 = 1, ZOS_BITS_UINT233 = 2, ZOS_BITS_UINT16 = 3, ZOS_BITS_UINT4X4 = 4,
+  ZOS_BITS_UINT_444 = 5, ZOS_BITS_UINT444_ = 6, ZOS_BITS_UINT565 = 7, ZOS_BITS_UINT8X2 = 8, ZOS_BITS_UINT8X3 = 9,
+  ZOS_BITS_UINT8X4 = 10, ZOS_BITS_UINT16X2 = 11, ZOS_BITS_UINT16X3 = 12, ZOS_BITS_UINT16X4 = 13,
+  ZOS_BITS_UINT2101010 = 14, ZOS_BITS_UINT1010102 = 15, /* 15 = the usual RGB10A2 (R in the low bits) */
+  ZOS_BITS_UINT101010_ = 16, ZOS_BITS_UINT_101010 = 17, ZOS_BITS_FLOAT16X4 = 18, ZOS_BITS_FLOAT32X4 = 19
+};
+enum { ZOS_COLOR_RGB = 0, ZOS_COLOR_SCALARS = 1, ZOS_COLOR_OKLAB = 2, ZOS_COLOR_SRLAB2 = 3 }; /* image_canvas::Color */
+enum { ZOS_PRIM_BT709 = 0, ZOS_PRIM_BT601_525 = 1, ZOS_PRIM_BT601_625 = 2, ZOS_PRIM_SMPTE240 = 3, ZOS_PRIM_BT2020 = 4, ZOS_PRIM_BT2100 = 5 };
+enum { ZOS_WP_A = 0, ZOS_WP_B, ZOS_WP_C, ZOS_WP_D50, ZOS_WP_D55, ZOS_WP_D65, ZOS_WP_D75, ZOS_WP_E, ZOS_WP_F2, ZOS_WP_F7, ZOS_WP_F11 };
+/* Block: the reference only lowers Block::Pixel (program.rs:794-938); the planar blocks are
+ * additions of this backend */
+enum { ZOS_BLOCK_PIXEL = 0, ZOS_BLOCK_YUV420_PLANAR = 1 /* I420: Y, U, V planes */, ZOS_BLOCK_YUV420_NV12 = 2 };
+enum { ZOS_YUV_BT601 = 0, ZOS_YUV_BT709 = 1, ZOS_YUV_BT2020 = 2 }; /* luma coefficients Kr,Kb */
+
+/* Replaces buffer::Descriptor {layout: ByteLayout, color: Color, texel: Texel}
+ * (lib/zosimos/src/buffer.rs:14-30). */
+typedef struct zos_desc {
+  uint32_t width, height;
+  uint64_t row_stride;   /* bytes between rows of plane 0 in the DEVICE buffer (256-aligned) */
+  uint32_t texel_stride; /* bytes per texel (plane 0) */
+  uint32_t block;        /* ZOS_BLOCK_* */
+  uint32_t bits;         /* ZOS_BITS_* */
+  uint32_t parts;        /* ZOS_PARTS_* */
+  uint32_t color;        /* ZOS_COLOR_* */
+  uint32_t transfer;     /* ZOS_TRANSFER_* (Color::Rgb / Color::Scalars) */
+  uint32_t primaries;    /* ZOS_PRIM_* */
+  uint32_t whitepoint;   /* ZOS_WP_* */
+  uint32_t yuv_matrix;   /* ZOS_YUV_*            (planar blocks only) */
+  uint32_t yuv_full_range;
+  uint32_t chroma_filter; /* 0 nearest, 1 bilinear chroma upsampling */
+  uint32_t reserved;
+} zos_desc;
+
+/* How a register's bytes turn into working values: the native-vs-staged decision of
+ * ImageDescriptor::new (lib/zosimos/src/program.rs:781-946) plus this backend's float texels. */
+enum { ZOS_STORAGE_STAGED = 0, ZOS_STORAGE_SRGB8 = 1, ZOS_STORAGE_UNORM8 = 2, ZOS_STORAGE_FLOAT = 3, ZOS_STORAGE_YUV420 = 4 };
+typedef struct zos_texfmt { /* = the uvec4 of XyzParameter::serialize_std140, shaders/stage.rs:53-61 */
+  uint32_t transfer, parts, bits, storage;
+} zos_texfmt;
+
+uint32_t zos_abi_version(void);
+uint32_t zos_bits_bytes(uint32_t bits);                                   /* SampleBits::bytes() */
+uint64_t zos_aligned_row_stride(uint32_t width, uint32_t texel_stride);   /* buffer.rs:121-134 */
+zos_status zos_desc_texfmt(const zos_desc* desc, zos_texfmt* out);        /* program.rs:781-946 */
+uint64_t zos_desc_device_bytes(const zos_desc* desc);                     /* all planes, buffer.rs:137-140 */
+
+/* ---- context, device memory, host <-> device (replaces Pool's Gpu + ImageData::GpuBuffer,
+ *      lib/zosimos/src/pool.rs:39-41,122-156, and Low::WriteImageToBuffer / Low::ReadBuffer,
+ *      lib/zosimos/src/run.rs:1896-2041,2160-2276) ---- */
+typedef struct zos_ctx zos_ctx;
+typedef struct zos_buf zos_buf;
+
+zos_status zos_ctx_create(int32_t device, zos_ctx** out);
+void zos_ctx_destroy(zos_ctx* ctx);
+const char* zos_last_error(const zos_ctx* ctx); /* ctx may be NULL: last error of a failed create */
+int32_t zos_ctx_device(const zos_ctx* ctx);
+void* zos_ctx_stream(const zos_ctx* ctx);       /* the cudaStream_t all launches of this ctx go to */
+zos_status zos_sync(zos_ctx* ctx);              /* SyncPoint::block_on, run.rs:3019 */
+uint64_t zos_ctx_launch_count(const zos_ctx* ctx); /* kernels launched so far (bench: gpu_launches) */
+
+zos_status zos_buf_alloc(zos_ctx* ctx, uint64_t bytes, zos_buf** out);
+void zos_buf_free(zos_ctx* ctx, zos_buf* buf);
+void* zos_buf_ptr(const zos_buf* buf);
+uint64_t zos_buf_size(const zos_buf* buf);
+/* pinned host staging memory (the map_write / map_read buffers of encoder.rs:574-616) */
+zos_status zos_host_alloc(zos_ctx* ctx, uint64_t bytes, void** out);
+void zos_host_free(zos_ctx* ctx, void* ptr);
+/* rows x row_bytes from tight/pitched host rows into the pitched device buffer and back
+ * (copy_host_to_buffer, run.rs:3282-3309; the ReadBuffer row loop, run.rs:2265-2270).
+ * Asynchronous on the ctx stream when `host` is pinned. */
+zos_status zos_buf_upload(zos_ctx* ctx, zos_buf* dst, uint64_t dst_offset, uint64_t dst_pitch, const void* host,
+                          uint64_t host_pitch, uint64_t row_bytes, uint64_t rows);
+zos_status zos_buf_download(zos_ctx* ctx, const zos_buf* src, uint64_t src_offset, uint64_t src_pitch, void* host,
+                            uint64_t host_pitch, uint64_t row_bytes, uint64_t rows);
+zos_status zos_buf_copy(zos_ctx* ctx, zos_buf* dst, uint64_t dst_offset, const zos_buf* src, uint64_t src_offset,
+                        uint64_t bytes); /* High::Copy (transmute / from_buffer), program.rs:1534-1576 */
+zos_status zos_buf_fill(zos_ctx* ctx, zos_buf* dst, uint64_t offset, uint64_t bytes, uint8_t value);
+
+/* ---- images: a descriptor + where its planes live ---- */
+typedef struct zos_image {
+  zos_desc desc;
+  void* data;            /* device pointer, plane 0 (pixels, or Y) */
+  void* plane1;          /* U (I420) or interleaved UV (NV12); NULL for ZOS_BLOCK_PIXEL */
+  void* plane2;          /* V (I420) */
+  uint64_t chroma_stride; /* bytes between chroma rows */
+  uint64_t batch_stride;  /* bytes between consecutive frames of plane 0 (0 if batch == 1) */
+  uint64_t chroma_batch_stride;
+} zos_image;
+
+/* ---- per-pixel steps fused into a kernel between unpack and pack.  Parameter layouts are the
+ *      reference's uniform blocks with matrices row-major. ---- */
+enum {
+  ZOS_STEP_MATRIX = 1,     /* linear.frag:12-17            m = 3x3                       */
+  ZOS_STEP_OKLAB_ENC = 2,  /* oklab.frag:34-47             m = rgb -> xyz                */
+  ZOS_STEP_OKLAB_DEC = 3,  /* oklab.frag:50-64             m = xyz -> rgb                */
+  ZOS_STEP_SRLAB2_ENC = 4, /* srlab2.frag:36-57            m = rgb -> xyz                */
+  ZOS_STEP_SRLAB2_DEC = 5, /* srlab2.frag:60-85            m = xyz -> rgb, v = whitepoint */
+  ZOS_STEP_REQUANT = 6,    /* store to + reload from a declared register: fmt            */
+  ZOS_STEP_INJECT = 7,     /* inject.frag:20-25 (second operand = `aux` image)  v=mix,m[0..3]=color */
+  ZOS_STEP_F16 = 8         /* round through an Rgba16Float texture                        */
+};
+typedef struct zos_step {
+  uint32_t kind;
+  zos_texfmt fmt; /* ZOS_STEP_REQUANT */
+  float m[9];
+  float v[4];
+} zos_step;
+#define ZOS_MAX_STEPS 8
+
+/* unpack(src) -> steps -> pack(dst), one pass, `batch` frames.  Replaces the decode pass, the
+ * PaintFullScreen draw(s) and the encode pass of color_convert / chromatic_adaptation / extract
+ * (command.rs:2527-2597; program.rs:1475-1533). */
+zos_status zos_pixel_chain(zos_ctx* ctx, const zos_image* src, const zos_image* dst, const zos_step* steps,
+                           uint32_t nsteps, uint32_t batch);
+
+/* ---- two-layer composition and resampling ---- */
+enum { ZOS_SAMPLE_NEAREST = 0, ZOS_SAMPLE_BILINEAR = 1 }; /* AffineSample, command.rs:339-352 */
+enum { /* how `above` texels land on the destination */
+  ZOS_MAP_RECT = 0,   /* QuadTarget::Rect: selection sel[] stretched over target tgt[] (inscribe, crop,
+                         blend; program.rs:1908-1920) -- exact rational nearest indexing */
+  ZOS_MAP_AFFINE = 1, /* QuadTarget::Absolute: inv[] = inverse of Affine.transformation (program.rs:1898-1906) */
+  ZOS_MAP_GRID8 = 2,  /* CommandBuffer::resize as the reference does it: an RGBA8 coordinate grid and a
+                         palette lookup, coordinates truncated to 8 bits (command.rs:1675-1702) */
+  ZOS_MAP_SCALE = 3   /* exact resize: tgt[] = full destination, half-pixel centres */
+};
+enum { /* what happens where `above` lands */
+  ZOS_BLEND_OVERWRITE = -1, /* blend: None (encoder.rs:1493): RGBA replaced -- inscribe / affine */
+  ZOS_BLEND_CLEAR = 0, ZOS_BLEND_SRC = 1, ZOS_BLEND_DST = 2, ZOS_BLEND_SRC_OVER = 3, ZOS_BLEND_DST_OVER = 4,
+  ZOS_BLEND_SRC_IN = 5, ZOS_BLEND_DST_IN = 6, ZOS_BLEND_SRC_OUT = 7, ZOS_BLEND_DST_OUT = 8, ZOS_BLEND_SRC_ATOP = 9,
+  ZOS_BLEND_DST_ATOP = 10, ZOS_BLEND_XOR = 11 /* Porter-Duff, linear light (Blend::Alpha = SRC_OVER) */
+};
+typedef struct zos_compose_params {
+  int32_t map;       /* ZOS_MAP_* */
+  int32_t sampling;  /* ZOS_SAMPLE_* */
+  int32_t blend;     /* ZOS_BLEND_* */
+  int32_t use_tma;   /* 0 = direct loads, 1 = stage source tiles through TMA into shared memory when possible */
+  int32_t sel[4];    /* x, y, w, h in `above` texels (ZOS_MAP_RECT) */
+  int32_t tgt[4];    /* x, y, w, h in destination pixels (ZOS_MAP_RECT / ZOS_MAP_SCALE) */
+  float inv[9];      /* row-major inverse affine (ZOS_MAP_AFFINE) */
+  uint32_t n_src_steps, n_dst_steps;
+  zos_step src_steps[ZOS_MAX_STEPS]; /* applied to every `above` tap after unpack */
+  zos_step dst_steps[ZOS_MAX_STEPS]; /* applied to the composed value before pack */
+} zos_compose_params;
+
+/* dst = pack(dst_steps(compose(unpack(below), sample(src_steps(unpack(above)))))).  `below` may be
+ * NULL (pure resample; uncovered pixels get the Target::Discard colour (0,0,1,1), program.rs:1494-1506).
+ * Replaces the two PaintToSelection passes of inscribe / affine (command.rs:2642-2740), resize's
+ * bilinear + palette passes (command.rs:1675-1702) and implements blend (command.rs:1510-1519). */
+zos_status zos_compose(zos_ctx* ctx, const zos_image* below, const zos_image* above, const zos_image* dst,
+                       const zos_compose_params* params, uint32_t batch);
+
+/* constructors (ConstructOp::{Solid,Bilinear}, command.rs:1524-1633; bilinear.frag, solid_rgb.frag):
+ * p = 24 floats u_min,u_max,v_min,v_max,uv_min,uv_max; for a solid colour put it in u_min and zero the rest */
+zos_status zos_generate_bilinear(zos_ctx* ctx, const zos_image* dst, const float* p, uint32_t batch);
+/* box3.frag:16-52 (derivative, command.rs:1493-1508): m = 3x3 weights, row-major [dy+1][dx+1] */
+zos_status zos_box3(zos_ctx* ctx, const zos_image* src, const zos_image* dst, const float* m, uint32_t batch);
+/* palette.frag:21-32 (command.rs:1442-1485): dst = pal @ (xc . idx, yc . idx) */
+zos_status zos_palette(zos_ctx* ctx, const zos_image* pal, const zos_image* idx, const zos_image* dst, const float* xc,
+                       const float* yc, uint32_t batch);
+
+/* ---- programs: the High instruction stream (lib/zosimos/src/program.rs:89-139) ---- */
+typedef struct zos_program zos_program;
+enum {
+  ZOS_OP_INPUT = 1,        /* High::Input(reg)                       dst                           */
+  ZOS_OP_OUTPUT = 2,       /* High::Output{src,dst}                  src[0]                        */
+  ZOS_OP_PIXEL = 3,        /* PushOperand + DrawInto{PaintFullScreen} src[0] -> dst, steps          */
+  ZOS_OP_COMPOSE = 4,      /* the 2x PaintToSelection pattern        src[0]=below src[1]=above      */
+  ZOS_OP_COPY = 5,         /* High::Copy (transmute)                 src[0] -> dst                  */
+  ZOS_OP_GENERATE = 6,     /* DrawInto without operands (bilinear / solid)  gen[24]                 */
+  ZOS_OP_BOX3 = 7,
+  ZOS_OP_PALETTE = 8       /* src[0]=palette src[1]=indices, compose.inv[0..7] = xc,yc              */
+};
+typedef struct zos_op {
+  uint32_t kind;
+  int32_t src[2]; /* register indices, -1 = unused */
+  int32_t dst;
+  zos_desc desc;  /* descriptor of dst (Input: of the bound image) */
+  uint32_t nsteps;
+  zos_step steps[ZOS_MAX_STEPS];
+  zos_compose_params compose;
+  float gen[24];
+  uint32_t knob; /* 0 = none, else 1-based knob id whose bytes overwrite this op's parameter block */
+} zos_op;
+enum { ZOS_FUSE_EXACT = 0 /* every declared register is quantised like the reference, in registers */,
+       ZOS_FUSE_WIDE = 1 /* fused intermediates stay f32 */,
+       ZOS_FUSE_NONE = 2 /* one kernel per op, intermediates materialised (debug / parity) */ };
+
+/* Program::lower_to (program.rs:1304-1423): plan buffers, fuse, build the kernel schedule */
+zos_status zos_program_create(zos_ctx* ctx, const zos_op* ops, uint32_t nops, uint32_t fuse_mode, uint32_t batch,
+                              zos_program** out);
+void zos_program_destroy(zos_program* prog);
+/* Environment::bind / bind_output (run.rs:1171-1244): registers of Input ops and the src of Output ops */
+zos_status zos_program_bind(zos_program* prog, int32_t reg, const zos_image* image);
+/* Environment::knob (run.rs:1292-1306) */
+zos_status zos_program_set_knob(zos_program* prog, uint32_t knob, const void* data, uint64_t len);
+/* Executable::launch + Execution::step (run.rs:1016,1389): step launches up to max_kernels kernels */
+zos_status zos_program_launch(zos_program* prog);
+zos_status zos_program_step(zos_program* prog, uint32_t max_kernels, int32_t* still_running);
+uint32_t zos_program_kernel_count(const zos_program* prog);
+/* fills descriptor + device location of a register the program allocated itself (outputs not bound) */
+zos_status zos_program_register_image(const zos_program* prog, int32_t reg, zos_image* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZOSIMOS_CUDA_H */

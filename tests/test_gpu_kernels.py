@@ -1,0 +1,416 @@
+"""GPU parity tests: the CUDA kernels, called through the C-ABI (zos_pixel_chain / zos_compose /
+...), against the CPU oracle on the same seeded inputs and the same parameters.
+
+Bars (BASELINE.json north_star): bit-exact for integer texel packing/unpacking and for nearest
+indexing; <= 1 LSB per 8-bit channel (<= 1e-5 relative for float texels) where a transcendental
+function (pow / cbrt / atan2 / sincos) sits on the path, since the SFU approximations differ from
+glibc's in the last bits."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import refpipes as R
+from tests.gpu_common import (B, ctx, gpu_image, oracle_desc, oracle_image, rand_bytes, to_oracle_color, zdesc)  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+import zosimos_b200 as Z  # noqa: E402
+from zosimos_b200 import _ffi, ops  # noqa: E402
+from zosimos_b200.buffer import Color, SampleBits, SampleParts, Texel, Transfer  # noqa: E402
+
+SRGB8 = ("rgba8", Color.SRGB)
+
+
+def run_chain(ctx, src_desc, data, dst_desc, steps):
+    src = ctx.upload(src_desc, data)
+    dst = ctx.image(dst_desc)
+    ops.pixel_chain(ctx, src, dst, steps)
+    return dst.download()
+
+
+def max_lsb(a, b):
+    return int(np.abs(a.astype(np.int64) - b.astype(np.int64)).max())
+
+
+# ---------------------------------------------------------------- texel codecs
+STAGED_LINEAR = [
+    (SampleBits.UInt8x4, SampleParts.RgbA), (SampleBits.UInt8x4, SampleParts.BgrA), (SampleBits.UInt8x4, SampleParts.ARgb),
+    (SampleBits.UInt8x4, SampleParts.ABgr), (SampleBits.UInt1010102, SampleParts.RgbA), (SampleBits.UInt2101010, SampleParts.ARgb),
+    (SampleBits.UInt565, SampleParts.Rgb), (SampleBits.UInt565, SampleParts.Bgr), (SampleBits.UInt4x4, SampleParts.RgbA),
+    (SampleBits.UInt332, SampleParts.Rgb), (SampleBits.UInt233, SampleParts.Bgr), (SampleBits.UInt8, SampleParts.Luma),
+    (SampleBits.UInt8, SampleParts.A), (SampleBits.UInt8x2, SampleParts.LumaA), (SampleBits.UInt16, SampleParts.Luma),
+    (SampleBits.UInt16x2, SampleParts.LumaA),
+]
+
+
+@pytest.mark.parametrize("bits,parts", STAGED_LINEAR)
+def test_unpack_pack_linear_bit_exact(ctx, bits, parts):
+    """Integer unpack -> f16 texture -> truncating pack, linear transfer: no transcendental on the
+    path, must be bit-exact (stage.frag demux_uint / mux_uint / parts_*)."""
+    w, h = 301, 37  # ragged width: exercises the partial 4-pixel group at the row end
+    texel = Texel(Z.Block.Pixel, bits, parts)
+    d = zdesc(w, h, texel, Color.Scalars(Transfer.Linear))
+    data = rand_bytes(h, w * bits.bytes(), seed=int(bits) * 31 + int(parts))
+    # -> RGBA8 linear scalars and back to the same format
+    mid = zdesc(w, h, Texel.new_u8(SampleParts.RgbA), Color.Scalars(Transfer.Linear))
+    got_mid = run_chain(ctx, d, data, mid, [])
+    exp_mid = O.encode(oracle_desc(mid), O.decode(oracle_image(d, data)))
+    assert np.array_equal(got_mid, exp_mid.data)
+    got = run_chain(ctx, d, data, d, [])
+    exp = O.encode(oracle_desc(d), O.decode(oracle_image(d, data)))
+    assert np.array_equal(got, exp.data)
+
+
+@pytest.mark.parametrize("transfer", [Transfer.Srgb, Transfer.Bt709, Transfer.Bt470M, Transfer.Bt601, Transfer.Smpte240,
+                                      Transfer.Bt2020_10bit, Transfer.Smpte2084, Transfer.Bt2100Pq])
+@pytest.mark.parametrize("bits", [SampleBits.UInt1010102, SampleBits.UInt8x4])
+def test_transfer_functions_within_1lsb(ctx, transfer, bits):
+    """Staged texels with a non-linear transfer (stage.frag:280-408): decode to a half-float texel
+    and encode back; pow runs on the SFU -> <= 1 LSB, and almost always equal."""
+    w, h = 256, 64
+    texel = Texel(Z.Block.Pixel, bits, SampleParts.BgrA if bits == SampleBits.UInt8x4 else SampleParts.RgbA)
+    color = Color.Rgb(Z.Primaries.Bt709, transfer)
+    d = zdesc(w, h, texel, color)
+    data = rand_bytes(h, w * 4, seed=7 + int(transfer))
+    f16 = zdesc(w, h, Texel.new_f16(), Color.Rgb(Z.Primaries.Bt709, Transfer.Linear))
+    got = run_chain(ctx, d, data, f16, []).view(np.float16).astype(np.float32)
+    exp = O.encode(oracle_desc(f16), O.decode(oracle_image(d, data))).data.view(np.float16).astype(np.float32)
+    assert np.allclose(got, exp, rtol=2e-3, atol=1e-6)  # half precision: 1 ulp = 2^-11 relative
+    assert np.mean(got == exp) > 0.98
+    back = run_chain(ctx, d, data, d, [])
+    expb = O.encode(oracle_desc(d), O.decode(oracle_image(d, data))).data
+    nb = {SampleBits.UInt1010102: (10, 10, 10, 2), SampleBits.UInt8x4: (8, 8, 8, 8)}[bits]
+    gw, ew = back.view("<u4"), expb.view("<u4")
+    sh = 0
+    for n in nb:
+        ga, ea = (gw >> sh) & ((1 << n) - 1), (ew >> sh) & ((1 << n) - 1)
+        assert max_lsb(ga, ea) <= 1
+        assert np.mean(ga == ea) > 0.99
+        sh += n
+
+
+def test_native_srgb8_roundtrip_identity(ctx):
+    """Rgba8UnormSrgb decode (exact table) + correctly rounded encode is the identity on all codes."""
+    w, h = 256, 256
+    data = np.zeros((h, w, 4), np.uint8)
+    data[..., 0] = np.arange(256)[None, :]; data[..., 1] = np.arange(256)[:, None]
+    data[..., 2] = (np.arange(256)[None, :] * 7 + np.arange(256)[:, None] * 13) % 256
+    data[..., 3] = 255 - np.arange(256)[None, :]
+    d = zdesc(w, h, Texel.new_u8(SampleParts.RgbA), Color.SRGB)
+    got = run_chain(ctx, d, data, d, [])
+    assert np.array_equal(got.reshape(h, w, 4), data)
+    bgra = zdesc(w, h, Texel.new_u8(SampleParts.BgrA), Color.SRGB)
+    got = run_chain(ctx, d, data, bgra, []).reshape(h, w, 4)
+    assert np.array_equal(got[..., [2, 1, 0, 3]], data)
+
+
+def test_srgb8_encode_correctly_rounded(ctx):
+    """float -> sRGB8 must equal the oracle's threshold search for every value, including the
+    neighbourhood of every rounding threshold."""
+    dec = np.zeros(256, np.float32); thr = np.zeros(257, np.float32)
+    O.lib().zo_srgb_tables(O._fp(dec), O._fp(thr))
+    vals = [np.linspace(-0.1, 1.1, 100000, dtype=np.float32)]
+    for k in range(1, 256):
+        t = thr[k]
+        vals.append(np.array([np.nextafter(t, -np.inf, dtype=np.float32), t, np.nextafter(t, np.inf, dtype=np.float32)], np.float32))
+    v = np.concatenate(vals)
+    n = (v.size + 255) // 256 * 256
+    v = np.concatenate([v, np.zeros(n - v.size, np.float32)])
+    tex = np.stack([v, v[::-1], v, np.clip(v, 0, 1)], -1).reshape(n // 256, 256, 4)
+    src = zdesc(256, n // 256, Texel.new_f32(), Color.Rgb(Z.Primaries.Bt709, Transfer.Linear))
+    dst = zdesc(256, n // 256, Texel.new_u8(SampleParts.RgbA), Color.SRGB)
+    got = run_chain(ctx, src, tex.view(np.uint8), dst, [])
+    exp = O.encode(oracle_desc(dst), tex).data
+    assert np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize("fmt", ["f16", "f32"])
+def test_float_texels(ctx, fmt):
+    """Ours (the reference has no 8/16-byte texels): RGBA16F / RGBA32F with an sRGB transfer."""
+    w, h = 200, 50
+    rng = np.random.default_rng(11)
+    vals = rng.random((h, w, 4), dtype=np.float32) * 1.2 - 0.1
+    texel = Texel.new_f16() if fmt == "f16" else Texel.new_f32()
+    data = vals.astype(np.float16 if fmt == "f16" else np.float32)
+    d = zdesc(w, h, texel, Color.Rgb(Z.Primaries.Bt709, Transfer.Srgb))
+    lin = zdesc(w, h, Texel.new_f32(), Color.Rgb(Z.Primaries.Bt709, Transfer.Linear))
+    got = run_chain(ctx, d, data.view(np.uint8), lin, []).view(np.float32)
+    exp = O.encode(oracle_desc(lin), O.decode(oracle_image(d, data.view(np.uint8)))).data.view(np.float32)
+    assert np.allclose(got, exp, rtol=1e-5, atol=1e-7)
+    got = run_chain(ctx, lin, exp.view(np.uint8), d, [])
+    expb = O.encode(oracle_desc(d), exp.reshape(h, w, 4)).data
+    a = got.view(np.float16 if fmt == "f16" else np.float32).astype(np.float32)
+    b = expb.view(np.float16 if fmt == "f16" else np.float32).astype(np.float32)
+    assert np.allclose(a, b, rtol=2e-3 if fmt == "f16" else 1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------- colour operators
+def test_color_matrix_bit_exact(ctx, fixtures):
+    """chromatic_adaptation (command.rs:1112-1174 -> linear.frag): table decode, 3 fma rows,
+    threshold encode: no approximation anywhere -> bit exact on the reference's own test image."""
+    bg = fixtures["background"]
+    h, w, _ = bg.shape
+    d = zdesc(w, h, Texel.new_u8(SampleParts.RgbA), Color.SRGB)
+    M = O.mul3(O.inv3(O.to_xyz("bt709", "D50")), O.mul3(O.adaptation_matrix("vonkries", "D65", "D50"), O.to_xyz("bt709", "D65")))
+    got = run_chain(ctx, d, bg, d, [ops.matrix(M)])
+    exp = O.chromatic_adaptation(oracle_image(d, bg), "vonkries", "D50")
+    assert np.array_equal(got, exp.data)
+    assert O.blockhash256(got.reshape(h, w, 4)) in R_hashes()["adapted"]
+
+
+def R_hashes():
+    import json, os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "reference_hashes.json")) as f:
+        return json.load(f)
+
+
+def lch_descs(w, h, model):
+    lch = zdesc(w, h, Texel(Z.Block.Pixel, SampleBits.UInt8x4, SampleParts.LchA), model)
+    return lch, zdesc(w, h, Texel.new_u8(SampleParts.RgbA), Color.SRGB)
+
+
+@pytest.mark.parametrize("space", ["oklab", "srlab2"])
+def test_lab_encode_decode_per_op(ctx, fixtures, space):
+    """color_convert sRGB8 -> Oklab/SrLab2 (LchA u8 register, truncating pack) and back, each op
+    checked against the oracle ON THE ORACLE'S OWN INTERMEDIATE."""
+    bg = fixtures["background"]
+    h, w, _ = bg.shape
+    model = Color.Oklab if space == "oklab" else Color.SrLab2(Z.Whitepoint.D65)
+    lch, srgb = lch_descs(w, h, model)
+    T = O.to_xyz("bt709", "D65")
+    enc = ops.step(_ffi.STEP_OKLAB_ENC if space == "oklab" else _ffi.STEP_SRLAB2_ENC, T)
+    dec = ops.step(_ffi.STEP_OKLAB_DEC if space == "oklab" else _ffi.STEP_SRLAB2_DEC, O.inv3(T), v=O.WHITEPOINTS["D65"])
+    got_lch = run_chain(ctx, srgb, bg, lch, [enc])
+    exp_lch = O.color_convert(oracle_image(srgb, bg), to_oracle_color(model), oracle_desc(lch).texel)
+    a, b = got_lch.reshape(h, w, 4), exp_lch.data.reshape(h, w, 4)
+    assert np.array_equal(a[..., 3], b[..., 3])
+    assert max_lsb(a[..., :2], b[..., :2]) <= 1
+    dh = (a[..., 2].astype(int) - b[..., 2].astype(int)) % 256  # hue is circular; it is ill-conditioned where chroma ~ 0
+    dh = np.minimum(dh, 256 - dh)
+    assert (dh[b[..., 1] >= 2] <= 1).all()
+    assert np.mean(a == b) > 0.995
+    # decode from the oracle's intermediate
+    got = run_chain(ctx, lch, exp_lch.data, srgb, [dec])
+    exp = O.color_convert(exp_lch, O.SRGB, O.RGBA8)
+    assert max_lsb(got, exp.data) <= 1
+    assert np.mean(got == exp.data) > 0.995
+
+
+@pytest.mark.parametrize("space", ["oklab", "srlab2"])
+def test_lab_golden_hash(ctx, space):
+    """tests/blend.rs run_oklab / run_srlab2 on the GPU: bilinear LCh grid -> transmute -> sRGB."""
+    w = h = 400
+    grid = zdesc(w, h, Texel.new_u8(SampleParts.RgbA), Color.Scalars(Transfer.Linear))
+    model = Color.Oklab if space == "oklab" else Color.SrLab2(Z.Whitepoint.D65)
+    lch, srgb = lch_descs(w, h, model)
+    g = ctx.image(grid)
+    ops.generate_bilinear(ctx, g, R.LCH_GRID)
+    grid_bytes = g.download()
+    exp_grid = O.bilinear(oracle_desc(grid), R.LCH_GRID)
+    assert np.array_equal(grid_bytes, exp_grid.data)  # mix() + truncating pack: exact
+    T = O.to_xyz("bt709", "D65")
+    dec = ops.step(_ffi.STEP_OKLAB_DEC if space == "oklab" else _ffi.STEP_SRLAB2_DEC, O.inv3(T), v=O.WHITEPOINTS["D65"])
+    got = run_chain(ctx, lch, grid_bytes, srgb, [dec])
+    assert O.blockhash256(got.reshape(h, w, 4)) in R_hashes()[space]
+
+
+def test_fused_c1_chain_matches_unfused(ctx, fixtures):
+    """BASELINE config 1 as ONE kernel: sRGB8 -> Oklab -> [LchA u8 register replayed in registers]
+    -> sRGB8.  Must equal the GPU's own two-kernel result exactly (same arithmetic, the register is
+    quantised identically), and track the oracle within the statistical bound of SURVEY.md 7.2."""
+    bg = fixtures["background"]
+    h, w, _ = bg.shape
+    lch, srgb = lch_descs(w, h, Color.Oklab)
+    T = O.to_xyz("bt709", "D65")
+    enc, dec = ops.step(_ffi.STEP_OKLAB_ENC, T), ops.step(_ffi.STEP_OKLAB_DEC, O.inv3(T))
+    two = run_chain(ctx, lch, run_chain(ctx, srgb, bg, lch, [enc]), srgb, [dec])
+    one = run_chain(ctx, srgb, bg, srgb, [enc, ops.requant(lch), dec])
+    assert np.array_equal(one, two)
+    exp = O.color_convert(O.color_convert(oracle_image(srgb, bg), O.OKLAB, oracle_desc(lch).texel), O.SRGB, O.RGBA8).data
+    d = np.abs(one.astype(int) - exp.astype(int))
+    assert np.mean(d > 1) < 0.01   # a flipped truncation of the 8-bit LCh register moves a few pixels by > 1
+    assert np.mean(d == 0) > 0.97
+
+
+# ---------------------------------------------------------------- composition
+def test_inscribe_golden_and_exact(ctx, fixtures):
+    bg, fg = fixtures["background"], fixtures["foreground"]
+    H, W, _ = bg.shape; fh, fw, _ = fg.shape
+    db, df = zdesc(W, H, Texel.new_u8(SampleParts.RgbA), Color.SRGB), zdesc(fw, fh, Texel.new_u8(SampleParts.RgbA), Color.SRGB)
+    below, above, dst = ctx.upload(db, bg), ctx.upload(df, fg), ctx.image(db)
+    # reference placement: Rectangle::normalize() stretches the layer to w x w (command.rs:3536-3543)
+    p = ops.compose_params(sel=(0, 0, fw, fh), tgt=(0, 0, fw, fw))
+    ops.compose(ctx, below, above, dst, p)
+    got = dst.download()
+    exp = O.inscribe(oracle_image(db, bg), (0, 0, fw, fh), oracle_image(df, fg))
+    assert np.array_equal(got, exp.data)
+    assert O.blockhash256(got.reshape(H, W, 4)) in R_hashes()["composed"]
+    # unscaled placement at a 4-aligned offset (streaming kernel) and at an odd offset (gather kernel)
+    for (tx, ty) in ((64, 33), (13, 7)):
+        ops.compose(ctx, below, above, dst, ops.compose_params(sel=(0, 0, fw, fh), tgt=(tx, ty, fw, fh)))
+        got = dst.download().reshape(H, W, 4)
+        exp = bg.copy(); exp[ty:ty + fh, tx:tx + fw] = fg
+        assert np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize("use_tma", [False, True])
+def test_affine_nearest_golden_and_exact(ctx, fixtures, use_tma):
+    bg, fg = fixtures["background"], fixtures["foreground"]
+    H, W, _ = bg.shape; fh, fw, _ = fg.shape
+    db, df = zdesc(W, H, Texel.new_u8(SampleParts.RgbA), Color.SRGB), zdesc(fw, fh, Texel.new_u8(SampleParts.RgbA), Color.SRGB)
+    m = R.affine_matrix_blend_rs(fw, fh, W, H)
+    inv = O.inv3(m.astype(np.float64)).astype(np.float32)
+    below, above, dst = ctx.upload(db, bg), ctx.upload(df, fg), ctx.image(db)
+    ops.compose(ctx, below, above, dst, ops.compose_params(map=_ffi.MAP_AFFINE, inv=inv, use_tma=use_tma))
+    got = dst.download()
+    exp = O.affine(oracle_image(db, bg), m, oracle_image(df, fg))
+    assert np.array_equal(got, exp.data)
+    assert O.blockhash256(got.reshape(H, W, 4)) in R_hashes()["affine"]
+
+
+@pytest.mark.parametrize("use_tma", [False, True])
+@pytest.mark.parametrize("angle,scale", [(30.0, 1.0), (45.0, 0.8), (-12.0, 1.7), (90.0, 1.0)])
+def test_affine_bilinear_f16(ctx, use_tma, angle, scale):
+    """BASELINE config 3 at test size: rotate + bilinear on RGBA16F (ours: the reference rejects
+    BiLinear, command.rs:1659-1665).  Only fma/sub on the path -> bit exact."""
+    W, H, w, h = 500, 333, 420, 300
+    rng = np.random.default_rng(3)
+    a = rng.random((h, w, 4), dtype=np.float32); a[rng.random((h, w)) < 0.01] *= 4.0; a[..., 3] = 1.0
+    b = rng.random((H, W, 4), dtype=np.float32)
+    t = Texel.new_f16(); c = Color.Rgb(Z.Primaries.Bt709, Transfer.Linear)
+    da, dbb = zdesc(w, h, t, c), zdesc(W, H, t, c)
+    a16, b16 = a.astype(np.float16), b.astype(np.float16)
+    m = O.shift(W / 2, H / 2) @ O.scale(scale, scale) @ O.rotate(np.deg2rad(angle)) @ O.shift(-w / 2, -h / 2)
+    m = m.astype(np.float32)
+    inv = O.inv3(m.astype(np.float64)).astype(np.float32)
+    below, above, dst = ctx.upload(dbb, b16.view(np.uint8)), ctx.upload(da, a16.view(np.uint8)), ctx.image(dbb)
+    ops.compose(ctx, below, above, dst, ops.compose_params(map=_ffi.MAP_AFFINE, sampling=_ffi.SAMPLE_BILINEAR, inv=inv, use_tma=use_tma))
+    got = dst.download().view(np.float16)
+    exp = O.affine(oracle_image(dbb, b16.view(np.uint8)), m, oracle_image(da, a16.view(np.uint8)), sampling=1).data.view(np.float16)
+    assert np.array_equal(got, exp)
+    # pure resample (no `below`): uncovered pixels get the Target::Discard colour (0,0,1,1)
+    ops.compose(ctx, None, above, dst, ops.compose_params(map=_ffi.MAP_AFFINE, sampling=_ffi.SAMPLE_BILINEAR, inv=inv, use_tma=use_tma))
+    got2 = dst.download().view(np.float16).reshape(H, W, 4)
+    tex = np.zeros((H, W, 4), np.float32); tex[..., 2:] = 1.0
+    O.paint_affine(tex, O.decode(oracle_image(da, a16.view(np.uint8))), inv.reshape(9), 1)
+    assert np.array_equal(got2, tex.astype(np.float16))
+
+
+@pytest.mark.parametrize("mode", list(range(12)))
+def test_porter_duff_bit_exact(ctx, mode):
+    """BASELINE config 2 at test size: blend two RGBA8 sRGB layers in linear light (ours; the
+    reference's blend is UNIMPLEMENTED, command.rs:1510-1519).  Table decode, fma/div, threshold
+    encode -> bit exact."""
+    W, H = 640, 97
+    bgd = rand_bytes(H, W * 4, seed=1); fgd = rand_bytes(H, W * 4, seed=2)
+    fgd.reshape(H, W, 4)[:, :40, 3] = 0; bgd.reshape(H, W, 4)[:, 20:60, 3] = 0
+    d = zdesc(W, H, Texel.new_u8(SampleParts.RgbA), Color.SRGB)
+    below, above, dst = ctx.upload(d, bgd), ctx.upload(d, fgd), ctx.image(d)
+    ops.compose(ctx, below, above, dst, ops.compose_params(blend=mode, sel=(0, 0, W, H), tgt=(0, 0, W, H)))
+    got = dst.download()
+    exp = O.blend(oracle_image(d, bgd), (0, 0, W, H), oracle_image(d, fgd), mode)
+    assert np.array_equal(got, exp.data)
+
+
+def test_blend_offset_layer_gather_path(ctx):
+    W, H, w, h = 300, 200, 120, 90
+    bgd = rand_bytes(H, W * 4, seed=5); fgd = rand_bytes(h, w * 4, seed=6)
+    db, df = zdesc(W, H, Texel.new_u8(SampleParts.RgbA), Color.SRGB), zdesc(w, h, Texel.new_u8(SampleParts.RgbA), Color.SRGB)
+    below, above, dst = ctx.upload(db, bgd), ctx.upload(df, fgd), ctx.image(db)
+    for tx, ty in ((37, 51), (40, 8)):
+        ops.compose(ctx, below, above, dst, ops.compose_params(blend=_ffi.BLEND_SRC_OVER, sel=(0, 0, w, h), tgt=(tx, ty, w, h)))
+        exp = O.blend(oracle_image(db, bgd), (tx, ty, tx + w, ty + h), oracle_image(df, fgd), 3)
+        assert np.array_equal(dst.download(), exp.data)
+
+
+# ---------------------------------------------------------------- resize
+def test_resize_reference_mode(ctx, fixtures):
+    """CommandBuffer::resize as the reference does it (command.rs:1675-1702): 8-bit coordinate grid
+    + palette lookup.  All arithmetic is exact -> bit exact, both through the fused MAP_GRID8 path and
+    through the unfused generate + palette kernels."""
+    bg = fixtures["background"]
+    H, W, _ = bg.shape
+    for (w, h) in ((400, 300), (157, 600), (1024, 768)):
+        ds, dd = zdesc(W, H, Texel.new_u8(SampleParts.RgbA), Color.SRGB), zdesc(w, h, Texel.new_u8(SampleParts.RgbA), Color.SRGB)
+        src, dst = ctx.upload(ds, bg), ctx.image(dd)
+        ops.compose(ctx, None, src, dst, ops.compose_params(map=_ffi.MAP_GRID8))
+        exp = O.resize(oracle_image(ds, bg), (w, h), "reference")
+        assert np.array_equal(dst.download(), exp.data)
+        grid = ctx.image(zdesc(w, h, Texel.new_u8(SampleParts.RgbA), Color.Scalars(Transfer.Linear)))
+        ops.generate_bilinear(ctx, grid, ([0, 0, 0, 1], [1, 0, 0, 1], [0, 0, 0, 1], [0, 1, 0, 1], [0, 0, 0, 1], [0, 0, 0, 1]))
+        ops.palette(ctx, src, grid, dst, [1, 0, 0, 0], [0, 1, 0, 0])
+        assert np.array_equal(dst.download(), exp.data)
+
+
+@pytest.mark.parametrize("use_tma", [False, True])
+@pytest.mark.parametrize("mode", ["nearest", "bilinear"])
+def test_resize_exact_modes(ctx, fixtures, mode, use_tma):
+    bg = fixtures["background"]
+    H, W, _ = bg.shape
+    ds = zdesc(W, H, Texel.new_u8(SampleParts.RgbA), Color.SRGB)
+    src = ctx.upload(ds, bg)
+    for (w, h) in ((341, 341), (1280, 720), (512, 512), (100, 37)):
+        dd = zdesc(w, h, Texel.new_u8(SampleParts.RgbA), Color.SRGB)
+        dst = ctx.image(dd)
+        ops.compose(ctx, None, src, dst, ops.compose_params(map=_ffi.MAP_SCALE, sampling=0 if mode == "nearest" else 1, use_tma=use_tma))
+        exp = O.resize(oracle_image(ds, bg), (w, h), mode)
+        assert np.array_equal(dst.download(), exp.data), (mode, w, h)
+
+
+# ---------------------------------------------------------------- neighbourhood / constructors
+@pytest.mark.parametrize("name", sorted(R.DERIVATIVES))
+def test_derivative_golden(ctx, fixtures, name):
+    bg = fixtures["background"]
+    H, W, _ = bg.shape
+    d = zdesc(W, H, Texel.new_u8(SampleParts.RgbA), Color.SRGB)
+    src, dst = ctx.upload(d, bg), ctx.image(d)
+    M = np.outer(np.asarray(R.DERIVATIVES[name], np.float32), np.asarray([0.5, 0.0, -0.5], np.float32))
+    ops.box3(ctx, src, dst, M)
+    got = dst.download()
+    exp = O.derivative(oracle_image(d, bg), R.DERIVATIVES[name])
+    assert np.array_equal(got, exp.data)
+    assert O.blockhash256(got.reshape(H, W, 4)) in R_hashes()["derived_" + name]
+
+
+@pytest.mark.parametrize("idx", range(5))
+def test_bilinear_knob_golden(ctx, idx):
+    um, uM, vm, vM = R.KNOBS[idx]
+    d = zdesc(512, 512, Texel.new_u8(SampleParts.RgbA), Color.SRGB)
+    dst = ctx.image(d)
+    ops.generate_bilinear(ctx, dst, (um, uM, vm, vM, [0] * 4, [0] * 4))
+    got = dst.download()
+    assert np.array_equal(got, O.bilinear(oracle_desc(d), (um, uM, vm, vM, [0] * 4, [0] * 4)).data)
+    assert O.blockhash256(got.reshape(512, 512, 4)) in R_hashes()["bilinear-knob-%d" % idx]
+
+
+# ---------------------------------------------------------------- planar YUV (ours)
+@pytest.mark.parametrize("nv12", [False, True])
+@pytest.mark.parametrize("chroma_filter", [0, 1])
+def test_yuv420_to_rgba8(ctx, nv12, chroma_filter):
+    w, h = 322, 130
+    rng = np.random.default_rng(4)
+    y = rng.integers(16, 236, (h, w), dtype=np.uint8)
+    u = rng.integers(16, 241, (h // 2, w // 2), dtype=np.uint8); v = rng.integers(16, 241, (h // 2, w // 2), dtype=np.uint8)
+    color = Color.Rgb(Z.Primaries.Bt709, Transfer.Bt709)
+    d = Z.yuv420_descriptor(w, h, color, Z.YuvMatrix.Bt709, False, nv12, chroma_filter)
+    planes = (y, np.stack([u, v], -1).reshape(h // 2, w) if nv12 else u, None if nv12 else v)
+    src = ctx.upload(d, planes)
+    dd = zdesc(w, h, Texel.new_u8(SampleParts.RgbA), Color.SRGB)
+    dst = ctx.image(dd)
+    ops.pixel_chain(ctx, src, dst, [])
+    got = dst.download()
+    uu = np.stack([u, v], -1).reshape(h // 2, w) if nv12 else u
+    tex = O.decode_yuv420(y, uu, uu.reshape(-1)[1:] if nv12 else v, w, h, 0.2126, 0.0722, False, nv12, chroma_filter, O.TR_BT709) \
+        if not nv12 else None
+    if nv12:
+        # the oracle takes the interleaved plane through u / v pointers one byte apart
+        flat = np.ascontiguousarray(uu)
+        tex = np.empty((h, w, 4), np.float32)
+        p = O.Yuv(0.2126, 0.0722, 0, 1, chroma_filter, O.TR_BT709)
+        import ctypes as C
+        base = flat.ctypes.data
+        O.lib().zo_decode_yuv420(C.byref(p), O._bp(y), C.c_size_t(w), C.cast(base, C.POINTER(C.c_uint8)),
+                                 C.cast(base + 1, C.POINTER(C.c_uint8)), C.c_size_t(w), w, h, O._fp(tex))
+    exp = O.encode(oracle_desc(dd), tex).data
+    assert max_lsb(got, exp) <= 1
+    assert np.mean(got == exp) > 0.99

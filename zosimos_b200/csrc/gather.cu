@@ -1,0 +1,538 @@
+// gather.cu -- destination-centric composition / resampling kernel.
+//
+//   dst(i,j) = pack( dst_steps( inside(i,j) ? blend(sample(above, map(i,j)), below(i,j)) : below(i,j) ) )
+//
+// Covers the reference's PaintToSelection draws (box.vert:43-59 + copy.frag:8-10 with the Nearest /
+// ClampToEdge sampler of encoder.rs:1533-1537) for crop / inscribe / affine
+// (command.rs:2507-2526, 2642-2740), resize (command.rs:1675-1702: bilinear.frag grid + palette.frag
+// lookup, coordinates truncated to 8 bits), and this backend's additions: bilinear sampling,
+// Porter-Duff blending, planar YUV 4:2:0 sources.
+//
+// A CTA of 256 threads produces a 32x32 destination tile, 4 consecutive pixels per thread.  The
+// footprint of the tile in the source (the bounding box of the inverse-mapped tile) is staged
+// into shared memory by ONE TMA bulk tensor copy per plane (cp.async.bulk.tensor.3d, completion on
+// an mbarrier), double buffered so the next tile's box lands while the current tile is computed;
+// out-of-image parts of the box are zero-filled by the TMA unit and never read (taps are clamped
+// to the image first).  Tiles whose footprint does not fit the box fall back to direct loads.
+#include <cuda.h>
+
+#include "colorops.cuh"
+#include "zos_internal.h"
+
+namespace zos {
+
+ZOS_DEFINE_CONSTANT_UPLOAD(upload_constants_gather)
+
+constexpr int TILE = 32;
+constexpr int THREADS = 256;
+
+struct GatherParams {
+  DevImage below, above, dst;
+  int32_t has_below, below_vec, dst_vec;
+  int32_t map, sampling, blend;
+  int32_t sel[4], tgt[4];
+  float inv[6];
+  float rx, ry;  // sel.w / tgt.w, sel.h / tgt.h (bilinear rect mapping)
+  uint32_t tiles_x, tiles_y, total_tiles;
+  FastDiv div_tx, div_ty;
+  int32_t use_tma;        // 0 direct, 1 TMA (pixel source), 2 TMA (planar YUV source)
+  int32_t box_w, box_h;   // texels, plane 0
+  int32_t cbox_w, cbox_h; // chroma box
+  int32_t ept;            // 4-byte elements per texel in the tensor map (bpp >= 4), else 0
+  StepList src_steps, dst_steps;
+};
+struct TensorMaps {
+  CUtensorMap m0, m1, m2;
+};
+
+__device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv& f) {
+  uint32_t t = __umulhi(n, f.m);
+  return f.l == 0 ? n : (t + ((n - t) >> 1)) >> (f.l - 1);
+}
+
+// ---------------- mbarrier / TMA primitives ----------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ---------------- tile geometry ----------------
+struct TileInfo {
+  uint32_t frame;
+  int x0, y0;    // destination tile origin
+  int bx, by;    // source box origin (plane 0 texels)
+  int cbx, cby;  // chroma box origin
+  bool fits;     // footprint fits the TMA box
+  bool any;      // tile intersects the covered area at all
+};
+
+__device__ __forceinline__ void map_point(const GatherParams& P, float cx, float cy, float& px, float& py) {
+  px = fmaf(P.inv[1], cy, fmaf(P.inv[0], cx, P.inv[2]));
+  py = fmaf(P.inv[4], cy, fmaf(P.inv[3], cx, P.inv[5]));
+}
+
+__device__ TileInfo tile_info(const GatherParams& P, uint32_t t) {
+  TileInfo ti;
+  uint32_t r = fastdiv(t, P.div_tx);
+  uint32_t txi = t - r * P.tiles_x;
+  ti.frame = fastdiv(r, P.div_ty);
+  uint32_t tyi = r - ti.frame * P.tiles_y;
+  ti.x0 = (int)txi * TILE;
+  ti.y0 = (int)tyi * TILE;
+  ti.fits = false; ti.any = true;
+  ti.bx = ti.by = ti.cbx = ti.cby = 0;
+  if (!P.use_tma) return ti;
+  int x1 = min(ti.x0 + TILE, P.dst.w) - 1, y1 = min(ti.y0 + TILE, P.dst.h) - 1;  // inclusive
+  float minx, maxx, miny, maxy;
+  if (P.map == ZOS_MAP_AFFINE) {
+    float px[4], py[4];
+    map_point(P, ti.x0 + 0.5f, ti.y0 + 0.5f, px[0], py[0]);
+    map_point(P, x1 + 0.5f, ti.y0 + 0.5f, px[1], py[1]);
+    map_point(P, ti.x0 + 0.5f, y1 + 0.5f, px[2], py[2]);
+    map_point(P, x1 + 0.5f, y1 + 0.5f, px[3], py[3]);
+    minx = fminf(fminf(px[0], px[1]), fminf(px[2], px[3])); maxx = fmaxf(fmaxf(px[0], px[1]), fmaxf(px[2], px[3]));
+    miny = fminf(fminf(py[0], py[1]), fminf(py[2], py[3])); maxy = fmaxf(fmaxf(py[0], py[1]), fmaxf(py[2], py[3]));
+  } else {  // ZOS_MAP_RECT (also the exact resize): separable, monotone
+    int ix0 = max(ti.x0, P.tgt[0]), ix1 = min(x1, P.tgt[0] + P.tgt[2] - 1);
+    int iy0 = max(ti.y0, P.tgt[1]), iy1 = min(y1, P.tgt[1] + P.tgt[3] - 1);
+    if (ix0 > ix1 || iy0 > iy1) { ti.any = false; return ti; }
+    minx = P.sel[0] + ((float)(ix0 - P.tgt[0]) + 0.5f) * P.rx; maxx = P.sel[0] + ((float)(ix1 - P.tgt[0]) + 0.5f) * P.rx;
+    miny = P.sel[1] + ((float)(iy0 - P.tgt[1]) + 0.5f) * P.ry; maxy = P.sel[1] + ((float)(iy1 - P.tgt[1]) + 0.5f) * P.ry;
+  }
+  // clip the footprint to the image: taps are clamped before they are fetched
+  minx = fmaxf(minx, 0.0f); miny = fmaxf(miny, 0.0f);
+  maxx = fminf(maxx, (float)P.above.w); maxy = fminf(maxy, (float)P.above.h);
+  if (minx > maxx || miny > maxy) { ti.any = false; return ti; }
+  int lox = max((int)floorf(minx) - 2, 0), hix = min((int)floorf(maxx) + 2, P.above.w - 1);
+  int loy = max((int)floorf(miny) - 2, 0), hiy = min((int)floorf(maxy) + 2, P.above.h - 1);
+  if (P.use_tma == 2) {  // chroma needs an even origin; bilinear chroma reaches one chroma texel further
+    lox = max((lox & ~1) - 2, 0); loy = max((loy & ~1) - 2, 0);
+    hix = min(hix + 2, P.above.w - 1); hiy = min(hiy + 2, P.above.h - 1);
+    ti.cbx = lox >> 1; ti.cby = loy >> 1;
+    ti.fits = ((hix >> 1) - ti.cbx + 1 <= P.cbox_w) && ((hiy >> 1) - ti.cby + 1 <= P.cbox_h);
+  } else {
+    ti.fits = true;
+  }
+  ti.bx = lox; ti.by = loy;
+  ti.fits = ti.fits && (hix - lox + 1 <= P.box_w) && (hiy - loy + 1 <= P.box_h);
+  return ti;
+}
+
+// ---------------- source fetch ----------------
+struct Stage {          // one pipeline stage in dynamic shared memory
+  const uint8_t* p0;    // plane 0 box
+  const uint8_t* p1;    // U box
+  const uint8_t* p2;    // V box
+};
+
+template <bool SMEM>
+__device__ __forceinline__ uint4 fetch_word(const GatherParams& P, const TileInfo& ti, const Stage& st, int u, int v) {
+  const int bpp = P.above.bpp;
+  const uint8_t* p;
+  if (SMEM) p = st.p0 + ((size_t)(v - ti.by) * P.box_w + (u - ti.bx)) * bpp;
+  else p = P.above.p0 + ti.frame * P.above.bstride + (uint64_t)v * P.above.pitch + (uint64_t)u * bpp;
+  uint4 w = make_uint4(0, 0, 0, 0);
+  switch (bpp) {
+    case 1: w.x = *p; break;
+    case 2: w.x = *reinterpret_cast<const uint16_t*>(p); break;
+    case 4: w.x = *reinterpret_cast<const uint32_t*>(p); break;
+    case 8: { uint2 t = *reinterpret_cast<const uint2*>(p); w.x = t.x; w.y = t.y; break; }
+    default: w = *reinterpret_cast<const uint4*>(p); break;
+  }
+  return w;
+}
+
+template <bool SMEM>
+__device__ __forceinline__ float chroma_at(const GatherParams& P, const TileInfo& ti, const uint8_t* box, const uint8_t* plane,
+                                           int cx, int cy) {
+  if (SMEM) return (float)box[(size_t)(cy - ti.cby) * P.cbox_w * (P.above.block == ZOS_BLOCK_YUV420_NV12 ? 2 : 1) +
+                              (size_t)(cx - ti.cbx) * (P.above.block == ZOS_BLOCK_YUV420_NV12 ? 2 : 1)];
+  const int step = P.above.block == ZOS_BLOCK_YUV420_NV12 ? 2 : 1;
+  return (float)plane[ti.frame * P.above.cbstride + (uint64_t)cy * P.above.cpitch + (uint64_t)cx * step];
+}
+
+// one source texel, unpacked to working values (linear light), with the src steps applied
+template <bool SMEM>
+__device__ __forceinline__ float4 fetch_texel(const GatherParams& P, const TileInfo& ti, const Stage& st, int u, int v, const Tables& T) {
+  float4 c;
+  if (P.above.block == ZOS_BLOCK_PIXEL) {
+    c = unpack_texel(P.above.fmt, fetch_word<SMEM>(P, ti, st, u, v), T);
+  } else {
+    float Y;
+    if (SMEM) Y = (float)st.p0[(size_t)(v - ti.by) * P.box_w + (u - ti.bx)];
+    else Y = (float)P.above.p0[ti.frame * P.above.bstride + (uint64_t)v * P.above.pitch + u];
+    const int cw = (P.above.w + 1) >> 1, ch = (P.above.h + 1) >> 1;
+    float U, V;
+    if (!P.above.chroma_filter) {
+      U = chroma_at<SMEM>(P, ti, st.p1, P.above.p1, u >> 1, v >> 1);
+      V = chroma_at<SMEM>(P, ti, st.p2, P.above.p2, u >> 1, v >> 1);
+    } else {
+      float fx = ((float)u + 0.5f) * 0.5f - 0.5f, fy = ((float)v + 0.5f) * 0.5f - 0.5f;
+      float x0f = floorf(fx), y0f = floorf(fy);
+      float ax = fx - x0f, ay = fy - y0f;
+      int x0 = (int)x0f, y0 = (int)y0f;
+      int x1 = min(max(x0 + 1, 0), cw - 1), y1 = min(max(y0 + 1, 0), ch - 1);
+      x0 = min(max(x0, 0), cw - 1); y0 = min(max(y0, 0), ch - 1);
+      float u00 = chroma_at<SMEM>(P, ti, st.p1, P.above.p1, x0, y0), u10 = chroma_at<SMEM>(P, ti, st.p1, P.above.p1, x1, y0);
+      float u01 = chroma_at<SMEM>(P, ti, st.p1, P.above.p1, x0, y1), u11 = chroma_at<SMEM>(P, ti, st.p1, P.above.p1, x1, y1);
+      float v00 = chroma_at<SMEM>(P, ti, st.p2, P.above.p2, x0, y0), v10 = chroma_at<SMEM>(P, ti, st.p2, P.above.p2, x1, y0);
+      float v01 = chroma_at<SMEM>(P, ti, st.p2, P.above.p2, x0, y1), v11 = chroma_at<SMEM>(P, ti, st.p2, P.above.p2, x1, y1);
+      float ut = fmaf(ax, u10 - u00, u00), ub = fmaf(ax, u11 - u01, u01);
+      float vt = fmaf(ax, v10 - v00, v00), vb = fmaf(ax, v11 - v01, v01);
+      U = fmaf(ay, ub - ut, ut); V = fmaf(ay, vb - vt, vt);
+    }
+    float y, cb, cr;
+    if (P.above.full_range) { y = Y / 255.0f; cb = (U - 128.0f) / 255.0f; cr = (V - 128.0f) / 255.0f; }
+    else { y = (Y - 16.0f) / 219.0f; cb = (U - 128.0f) / 224.0f; cr = (V - 128.0f) / 224.0f; }
+    const float kr = P.above.kr, kb = P.above.kb, kg = 1.0f - kr - kb;
+    float r = fmaf(2.0f * (1.0f - kr), cr, y);
+    float b = fmaf(2.0f * (1.0f - kb), cb, y);
+    float g = (y - kr * r - kb * b) / kg;
+    c = make_float4(eo_scalar(P.above.fmt.transfer, r), eo_scalar(P.above.fmt.transfer, g), eo_scalar(P.above.fmt.transfer, b), 1.0f);
+  }
+  apply_steps(P.src_steps, c, T);
+  return c;
+}
+
+template <bool SMEM>
+__device__ __forceinline__ float4 sample_bilinear(const GatherParams& P, const TileInfo& ti, const Stage& st, float px, float py,
+                                                  const Tables& T) {
+  float fx = px - 0.5f, fy = py - 0.5f;
+  float x0f = floorf(fx), y0f = floorf(fy);
+  float ax = fx - x0f, ay = fy - y0f;
+  int x0 = (int)x0f, y0 = (int)y0f;
+  const int sw = P.above.w, sh = P.above.h;
+  int x1 = min(max(x0 + 1, 0), sw - 1), y1 = min(max(y0 + 1, 0), sh - 1);
+  x0 = min(max(x0, 0), sw - 1); y0 = min(max(y0, 0), sh - 1);
+  float4 p00 = fetch_texel<SMEM>(P, ti, st, x0, y0, T), p10 = fetch_texel<SMEM>(P, ti, st, x1, y0, T);
+  float4 p01 = fetch_texel<SMEM>(P, ti, st, x0, y1, T), p11 = fetch_texel<SMEM>(P, ti, st, x1, y1, T);
+  float4 o;
+#define ZOS_LERP2(c) { float top = fmaf(ax, p10.c - p00.c, p00.c), bot = fmaf(ax, p11.c - p01.c, p01.c); o.c = fmaf(ay, bot - top, top); }
+  ZOS_LERP2(x) ZOS_LERP2(y) ZOS_LERP2(z) ZOS_LERP2(w)
+#undef ZOS_LERP2
+  return o;
+}
+
+__device__ __forceinline__ int rect_index(int k, int s, int t) {  // floor(((2k+1)*s) / (2t)), exact
+  if (s == t) return k;
+  return (int)(((uint64_t)(2 * (uint32_t)k + 1) * (uint32_t)s) / (2ull * (uint32_t)t));
+}
+
+// CommandBuffer::resize the way the reference does it (command.rs:1675-1702): the coordinate is
+// written to an RGBA8 linear "Scalars" register (f16 texture, truncating pack), read back, biased
+// by half a GRID texel and looked up with the nearest / clamp-to-edge sampler (palette.frag:21-32).
+__device__ __forceinline__ int grid8_index(int i, int n_dst, int n_src, const Tables& T) {
+  float u = ((float)i + 0.5f) / (float)n_dst;
+  uint32_t q = (uint32_t)(clamp01(f16r(u)) * 255.0f);
+  float c = f16r(T.unorm8[q]);
+  float pu = c + 0.5f / (float)n_dst;
+  int x = (int)floorf(pu * (float)n_src);
+  return min(max(x, 0), n_src - 1);
+}
+
+__device__ __forceinline__ uint4 load_px(const DevImage& im, uint32_t frame, int x, int y) {
+  const uint8_t* p = im.p0 + frame * im.bstride + (uint64_t)y * im.pitch + (uint64_t)x * im.bpp;
+  uint4 w = make_uint4(0, 0, 0, 0);
+  switch (im.bpp) {
+    case 1: w.x = *p; break;
+    case 2: w.x = *reinterpret_cast<const uint16_t*>(p); break;
+    case 4: w.x = __ldcs(reinterpret_cast<const uint32_t*>(p)); break;
+    case 8: { uint2 t = __ldcs(reinterpret_cast<const uint2*>(p)); w.x = t.x; w.y = t.y; break; }
+    default: w = __ldcs(reinterpret_cast<const uint4*>(p)); break;
+  }
+  return w;
+}
+__device__ __forceinline__ void store_px(const DevImage& im, uint32_t frame, int x, int y, const uint4& w) {
+  uint8_t* p = im.p0 + frame * im.bstride + (uint64_t)y * im.pitch + (uint64_t)x * im.bpp;
+  switch (im.bpp) {
+    case 1: *p = (uint8_t)w.x; break;
+    case 2: *reinterpret_cast<uint16_t*>(p) = (uint16_t)w.x; break;
+    case 4: __stcs(reinterpret_cast<uint32_t*>(p), w.x); break;
+    case 8: __stcs(reinterpret_cast<uint2*>(p), make_uint2(w.x, w.y)); break;
+    default: __stcs(reinterpret_cast<uint4*>(p), w); break;
+  }
+}
+
+// A warp owns one 32-pixel row segment of the tile per iteration: all global accesses to `below`
+// and dst are fully coalesced without per-thread vectors, for every texel size.
+template <bool SMEM>
+__device__ __forceinline__ void compute_tile(const GatherParams& P, const TileInfo& ti, const Stage& st, const Tables& T) {
+  const int i = ti.x0 + (threadIdx.x & 31);
+  if (i >= P.dst.w) return;
+#pragma unroll 1
+  for (int k = 0; k < TILE / 8; k++) {
+    const int j = ti.y0 + (threadIdx.x >> 5) + 8 * k;
+    if (j >= P.dst.h) break;
+    bool covered = false;
+    float4 v = make_float4(0.0f, 0.0f, 1.0f, 1.0f);  // Target::Discard clear colour
+    if (P.map == ZOS_MAP_AFFINE) {
+      float px, py;
+      map_point(P, (float)i + 0.5f, (float)j + 0.5f, px, py);
+      if (px >= 0.0f && px < (float)P.above.w && py >= 0.0f && py < (float)P.above.h) {
+        covered = true;
+        v = P.sampling == ZOS_SAMPLE_NEAREST ? fetch_texel<SMEM>(P, ti, st, (int)floorf(px), (int)floorf(py), T)
+                                             : sample_bilinear<SMEM>(P, ti, st, px, py, T);
+      }
+    } else if (P.map == ZOS_MAP_GRID8) {
+      covered = true;
+      v = fetch_texel<SMEM>(P, ti, st, grid8_index(i, P.dst.w, P.above.w, T), grid8_index(j, P.dst.h, P.above.h, T), T);
+    } else {
+      const int kx = i - P.tgt[0], ky = j - P.tgt[1];
+      if (kx >= 0 && kx < P.tgt[2] && ky >= 0 && ky < P.tgt[3]) {
+        covered = true;
+        if (P.sampling == ZOS_SAMPLE_NEAREST) {
+          int u = min(max(P.sel[0] + rect_index(kx, P.sel[2], P.tgt[2]), 0), P.above.w - 1);
+          int w = min(max(P.sel[1] + rect_index(ky, P.sel[3], P.tgt[3]), 0), P.above.h - 1);
+          v = fetch_texel<SMEM>(P, ti, st, u, w, T);
+        } else {
+          float px = (float)P.sel[0] + ((float)kx + 0.5f) * P.rx, py = (float)P.sel[1] + ((float)ky + 0.5f) * P.ry;
+          v = sample_bilinear<SMEM>(P, ti, st, px, py, T);
+        }
+      }
+    }
+    if (P.has_below && !(covered && P.blend == ZOS_BLEND_OVERWRITE)) {
+      float4 b = unpack_texel(P.below.fmt, load_px(P.below, ti.frame, i, j), T);
+      v = covered ? porter_duff(P.blend, v, b) : b;
+    }
+    apply_steps(P.dst_steps, v, T);
+    store_px(P.dst, ti.frame, i, j, pack_texel(P.dst.fmt, v, T));
+  }
+}
+
+__global__ void __launch_bounds__(THREADS) k_gather_direct(const __grid_constant__ GatherParams P) {
+  __shared__ Tables T;
+  load_tables(T);
+  Stage st{nullptr, nullptr, nullptr};
+  for (uint32_t t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+    TileInfo ti = tile_info(P, t);
+    compute_tile<false>(P, ti, st, T);
+  }
+}
+
+// error flag set when an mbarrier wait runs away (never expected; avoids hanging the GPU)
+__device__ int g_tma_timeout = 0;
+
+__global__ void __launch_bounds__(THREADS) k_gather_tma(const __grid_constant__ GatherParams P, const __grid_constant__ TensorMaps M) {
+  extern __shared__ __align__(128) uint8_t dyn[];
+  __shared__ Tables T;
+  __shared__ __align__(8) uint64_t bar[2];
+  load_tables(T);
+  const int bpp = P.above.bpp;
+  const uint32_t box0 = (uint32_t)P.box_w * P.box_h * bpp;
+  const uint32_t cstep = P.above.block == ZOS_BLOCK_YUV420_NV12 ? 2 : 1;
+  const uint32_t cbox = P.use_tma == 2 ? (uint32_t)P.cbox_w * P.cbox_h * cstep : 0;
+  const uint32_t box0_al = (box0 + 127) & ~127u, cbox_al = (cbox + 127) & ~127u;
+  const uint32_t nchroma = P.use_tma == 2 ? (cstep == 2 ? 1 : 2) : 0;
+  const uint32_t stage_bytes = box0_al + nchroma * cbox_al;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](uint32_t t, int s) {
+    TileInfo ti = tile_info(P, t);
+    if (!ti.fits || !ti.any) return;
+    uint8_t* base = dyn + (size_t)s * stage_bytes;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of this stage vs. the async write
+    mbar_expect_tx(&bar[s], box0 + nchroma * cbox);
+    tma_load_3d(base, &M.m0, ti.bx * (P.ept ? P.ept : 1), ti.by, (int)ti.frame, &bar[s]);
+    if (nchroma >= 1) tma_load_3d(base + box0_al, &M.m1, ti.cbx, ti.cby, (int)ti.frame, &bar[s]);
+    if (nchroma == 2) tma_load_3d(base + box0_al + cbox_al, &M.m2, ti.cbx, ti.cby, (int)ti.frame, &bar[s]);
+  };
+
+  uint32_t phase[2] = {0, 0};
+  int s = 0;
+  if (threadIdx.x == 0 && blockIdx.x < P.total_tiles) issue(blockIdx.x, 0);
+  for (uint32_t t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+    const uint32_t next = t + gridDim.x;
+    if (threadIdx.x == 0 && next < P.total_tiles) issue(next, s ^ 1);
+    TileInfo ti = tile_info(P, t);
+    if (ti.any) {
+      if (ti.fits) {
+        uint32_t spins = 0;
+        while (!mbar_try_wait(&bar[s], phase[s])) {
+          if (++spins > (1u << 24)) { g_tma_timeout = 1; break; }
+        }
+        phase[s] ^= 1;
+        uint8_t* base = dyn + (size_t)s * stage_bytes;
+        Stage st{base, base + box0_al, cstep == 2 ? base + box0_al + 1 : base + box0_al + cbox_al};
+        compute_tile<true>(P, ti, st, T);
+      } else {
+        Stage st{nullptr, nullptr, nullptr};
+        compute_tile<false>(P, ti, st, T);
+      }
+    } else {
+      Stage st{nullptr, nullptr, nullptr};
+      compute_tile<false>(P, ti, st, T);  // nothing of `above` lands here: copies `below`
+    }
+    __syncthreads();  // everyone is done with stage s before it is refilled two tiles later
+    s ^= 1;
+  }
+}
+
+// ---------------- host side ----------------
+bool gather_take_timeout_flag() {
+  int v = 0, zero = 0;
+  if (cudaMemcpyFromSymbol(&v, g_tma_timeout, sizeof v) != cudaSuccess) return false;
+  if (v) cudaMemcpyToSymbol(g_tma_timeout, &zero, sizeof zero);
+  return v != 0;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode(zos_ctx* ctx) {
+  if (!ctx->encode_tiled) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      ctx->encode_tiled = fn;
+  }
+  return (EncodeTiledFn)ctx->encode_tiled;
+}
+
+static bool make_map(zos_ctx* ctx, CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, void* base, uint64_t w_elems, uint64_t h,
+                     uint64_t pitch, uint64_t frames, uint64_t frame_stride, uint32_t box_w_elems, uint32_t box_h) {
+  EncodeTiledFn enc = get_encode(ctx);
+  if (!enc) return false;
+  if (((uintptr_t)base & 15) || (pitch & 15) || (frame_stride & 15)) return false;
+  if (box_w_elems > 256 || box_h > 256 || ((uint64_t)box_w_elems * elem_bytes) % 16) return false;
+  cuuint64_t dims[3] = {w_elems, h, frames};
+  cuuint64_t strides[2] = {pitch, frames > 1 ? frame_stride : pitch * h};
+  cuuint32_t box[3] = {box_w_elems, box_h, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, dt, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+static bool img_vec_ok(const DevImage& im) {
+  return ((uintptr_t)im.p0 % 16) == 0 && (im.pitch % 16) == 0 && (im.bstride % 16) == 0 &&
+         im.pitch >= (uint64_t)((im.w + 3) / 4) * 4 * im.bpp && (im.bpp == 4 || im.bpp == 8);
+}
+
+zos_status launch_gather(zos_ctx* ctx, const DevImage* below, const DevImage& above, const DevImage& dst,
+                         const zos_compose_params& cp, uint32_t batch) {
+  if (dst.block != ZOS_BLOCK_PIXEL) return fail(ctx, ZOS_ERR_UNSUPPORTED, "planar YUV destinations are not implemented yet");
+  if (below && below->block != ZOS_BLOCK_PIXEL) return fail(ctx, ZOS_ERR_UNSUPPORTED, "planar `below`");
+  GatherParams P;
+  memset(&P, 0, sizeof P);
+  P.above = above; P.dst = dst;
+  P.has_below = below != nullptr;
+  if (below) { P.below = *below; P.below_vec = img_vec_ok(*below); }
+  P.dst_vec = img_vec_ok(dst);
+  P.map = cp.map; P.sampling = cp.sampling; P.blend = cp.blend;
+  for (int k = 0; k < 4; k++) { P.sel[k] = cp.sel[k]; P.tgt[k] = cp.tgt[k]; }
+  if (cp.map == ZOS_MAP_SCALE || cp.map == ZOS_MAP_GRID8) {
+    P.sel[0] = P.sel[1] = 0; P.sel[2] = above.w; P.sel[3] = above.h;
+    P.tgt[0] = P.tgt[1] = 0; P.tgt[2] = dst.w; P.tgt[3] = dst.h;
+    if (cp.map == ZOS_MAP_SCALE) P.map = ZOS_MAP_RECT;
+  }
+  for (int k = 0; k < 6; k++) P.inv[k] = cp.inv[k];
+  P.rx = (float)P.sel[2] / (float)(P.tgt[2] > 0 ? P.tgt[2] : 1);
+  P.ry = (float)P.sel[3] / (float)(P.tgt[3] > 0 ? P.tgt[3] : 1);
+  P.src_steps.n = cp.n_src_steps;
+  for (uint32_t i = 0; i < cp.n_src_steps; i++) P.src_steps.s[i] = cp.src_steps[i];
+  P.dst_steps.n = cp.n_dst_steps;
+  for (uint32_t i = 0; i < cp.n_dst_steps; i++) P.dst_steps.s[i] = cp.dst_steps[i];
+  P.tiles_x = (dst.w + TILE - 1) / TILE;
+  P.tiles_y = (dst.h + TILE - 1) / TILE;
+  uint64_t total = (uint64_t)P.tiles_x * P.tiles_y * batch;
+  if (total >= (1ull << 31)) return fail(ctx, ZOS_ERR_UNSUPPORTED, "gather: too many tiles in one launch");
+  P.total_tiles = (uint32_t)total;
+  P.div_tx = make_fastdiv(P.tiles_x);
+  P.div_ty = make_fastdiv(P.tiles_y);
+
+  // ---- TMA plan: box = bounding box of a 32x32 destination tile in the source, plus margins
+  bool tma = cp.use_tma && P.map != ZOS_MAP_GRID8;
+  TensorMaps M;
+  memset(&M, 0, sizeof M);
+  size_t smem = 0;
+  if (tma) {
+    float ex, ey;
+    if (P.map == ZOS_MAP_AFFINE) {
+      ex = (TILE - 1) * (fabsf(P.inv[0]) + fabsf(P.inv[1]));
+      ey = (TILE - 1) * (fabsf(P.inv[3]) + fabsf(P.inv[4]));
+    } else {
+      ex = (TILE - 1) * P.rx; ey = (TILE - 1) * P.ry;
+    }
+    const bool yuv = above.block != ZOS_BLOCK_PIXEL;
+    int need_w = (int)ceilf(ex) + (yuv ? 12 : 6), need_h = (int)ceilf(ey) + (yuv ? 12 : 6);
+    int bpp = above.bpp;
+    int gran = bpp >= 16 ? 1 : 16 / bpp;  // box rows must be a multiple of 16 bytes
+    if (yuv) gran = 32;                   // so that the chroma box (half width) is too
+    int bw = (need_w + gran - 1) / gran * gran, bh = need_h;
+    P.ept = bpp >= 4 ? bpp / 4 : 0;
+    uint32_t bw_elems = P.ept ? bw * P.ept : bw;
+    size_t stage = ((size_t)bw * bh * bpp + 127) & ~(size_t)127;
+    int cstep = above.block == ZOS_BLOCK_YUV420_NV12 ? 2 : 1;
+    if (yuv) {
+      P.cbox_w = bw / 2; P.cbox_h = (bh + 1) / 2 + 1;
+      size_t cb = ((size_t)P.cbox_w * P.cbox_h * cstep + 127) & ~(size_t)127;
+      stage += cb * (cstep == 2 ? 1 : 2);
+    }
+    smem = 2 * stage;
+    bool ok = bw_elems <= 256 && bh <= 256 && smem <= 96 * 1024;
+    if (ok) {
+      CUtensorMapDataType dt = bpp == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : bpp == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32;
+      int eb = bpp >= 4 ? 4 : bpp;
+      uint64_t w_elems = P.ept ? (uint64_t)above.w * P.ept : (uint64_t)above.w;
+      ok = make_map(ctx, &M.m0, dt, eb, above.p0, w_elems, above.h, above.pitch, batch, above.bstride, bw_elems, bh);
+      if (ok && yuv) {
+        uint64_t cw = (above.w + 1) / 2, ch = (above.h + 1) / 2;
+        if (cstep == 2) {
+          ok = make_map(ctx, &M.m1, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, above.p1, cw, ch, above.cpitch, batch, above.cbstride, P.cbox_w, P.cbox_h);
+        } else {
+          ok = make_map(ctx, &M.m1, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, above.p1, cw, ch, above.cpitch, batch, above.cbstride, P.cbox_w, P.cbox_h) &&
+               make_map(ctx, &M.m2, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, above.p2, cw, ch, above.cpitch, batch, above.cbstride, P.cbox_w, P.cbox_h);
+        }
+      }
+    }
+    if (ok) { P.use_tma = yuv ? 2 : 1; P.box_w = bw; P.box_h = bh; } else { tma = false; P.use_tma = 0; smem = 0; }
+  }
+
+  cudaError_t e;
+  if (tma) {
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_gather_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr_set = true; }
+    int per_sm = (int)((200 * 1024) / (smem + sizeof(Tables) + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+    uint64_t cap = (uint64_t)ctx->sm_count * per_sm;
+    int grid = (int)(total < cap ? total : cap);
+    k_gather_tma<<<grid, THREADS, smem, ctx->stream>>>(P, M);
+    e = cudaGetLastError();
+  } else {
+    uint64_t cap = (uint64_t)ctx->sm_count * 8;
+    int grid = (int)(total < cap ? total : cap);
+    k_gather_direct<<<grid, THREADS, 0, ctx->stream>>>(P);
+    e = cudaGetLastError();
+  }
+  ctx->launches++;
+  return check_cuda(ctx, e, "k_gather launch");
+}
+
+}  // namespace zos

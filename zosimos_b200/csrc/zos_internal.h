@@ -1,0 +1,74 @@
+// zos_internal.h -- shared between the host runtime and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/zosimos_cuda.h"
+
+struct zos_buf {
+  void* ptr = nullptr;
+  uint64_t size = 0;
+};
+
+struct zos_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  uint64_t launches = 0;
+  std::string err;
+  void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved lazily through the runtime
+  std::vector<void*> scratch;    // device scratch owned by the ctx (tensor maps etc.)
+};
+
+namespace zos {
+
+// What a kernel needs to know about one image operand.
+struct DevImage {
+  uint8_t* p0;  // pixels / Y
+  uint8_t* p1;  // U or UV
+  uint8_t* p2;  // V
+  uint64_t pitch, cpitch;
+  uint64_t bstride, cbstride;  // per-frame strides
+  int32_t w, h;
+  int32_t bpp;      // bytes per texel of plane 0
+  uint32_t block;   // ZOS_BLOCK_*
+  zos_texfmt fmt;   // transfer of the colour for planar YUV
+  float kr, kb;
+  uint32_t full_range, chroma_filter;
+};
+
+// n / d for any 32-bit n (Granlund-Montgomery round-up method), d >= 1
+struct FastDiv {
+  uint32_t d, m, l;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  uint32_t l = 0;
+  while ((1ull << l) < d) l++;
+  f.l = l;
+  f.m = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  return f;
+}
+
+zos_status fail(zos_ctx* ctx, zos_status code, const char* fmt, ...);
+zos_status check_cuda(zos_ctx* ctx, cudaError_t e, const char* what);
+zos_status make_dev_image(zos_ctx* ctx, const zos_image* img, DevImage* out, const char* name);
+zos_status validate_steps(zos_ctx* ctx, const zos_step* steps, uint32_t n);
+int grid_for(const zos_ctx* ctx, uint64_t work_items, int threads, int ctas_per_sm);
+
+// kernel launchers (one per .cu)
+zos_status launch_rowwise(zos_ctx* ctx, const DevImage* below, const DevImage* above, const DevImage& dst,
+                          const zos_compose_params* cp, const zos_step* steps, uint32_t nsteps, uint32_t batch);
+bool rowwise_can_compose(const DevImage& below, const DevImage& above, const DevImage& dst, const zos_compose_params& cp);
+zos_status launch_gather(zos_ctx* ctx, const DevImage* below, const DevImage& above, const DevImage& dst,
+                         const zos_compose_params& cp, uint32_t batch);
+zos_status launch_generate(zos_ctx* ctx, const DevImage& dst, const float* p, uint32_t batch);
+zos_status launch_box3(zos_ctx* ctx, const DevImage& src, const DevImage& dst, const float* m, uint32_t batch);
+zos_status launch_palette(zos_ctx* ctx, const DevImage& pal, const DevImage& idx, const DevImage& dst, const float* xc,
+                          const float* yc, uint32_t batch);
+
+}  // namespace zos
