@@ -75,8 +75,9 @@ def test_transfer_functions_within_1lsb(ctx, transfer, bits):
     f16 = zdesc(w, h, Texel.new_f16(), Color.Rgb(Z.Primaries.Bt709, Transfer.Linear))
     got = run_chain(ctx, d, data, f16, []).view(np.float16).astype(np.float32)
     exp = O.encode(oracle_desc(f16), O.decode(oracle_image(d, data))).data.view(np.float16).astype(np.float32)
-    assert np.allclose(got, exp, rtol=2e-3, atol=1e-6)  # half precision: 1 ulp = 2^-11 relative
-    assert np.mean(got == exp) > 0.98
+    # (Smpte240's inverse curve is NaN between 0.0913 and 0.1115 in the reference's formula, on both sides)
+    assert np.allclose(got, exp, rtol=2e-3, atol=1e-6, equal_nan=True)  # half precision: 1 ulp = 2^-11 relative
+    assert np.mean((got == exp) | (np.isnan(got) & np.isnan(exp))) > 0.98
     back = run_chain(ctx, d, data, d, [])
     expb = O.encode(oracle_desc(d), O.decode(oracle_image(d, data))).data
     nb = {SampleBits.UInt1010102: (10, 10, 10, 2), SampleBits.UInt8x4: (8, 8, 8, 8)}[bits]

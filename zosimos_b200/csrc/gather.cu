@@ -39,6 +39,7 @@ struct GatherParams {
   int32_t box_w, box_h;   // texels, plane 0
   int32_t cbox_w, cbox_h; // chroma box
   int32_t ept;            // 4-byte elements per texel in the tensor map (bpp >= 4), else 0
+  int32_t align_x;        // box origin x is rounded down to this many texels: the TMA source address must be 16-byte aligned
   StepList src_steps, dst_steps;
 };
 struct TensorMaps {
@@ -127,11 +128,12 @@ __device__ TileInfo tile_info(const GatherParams& P, uint32_t t) {
   int lox = max((int)floorf(minx) - 2, 0), hix = min((int)floorf(maxx) + 2, P.above.w - 1);
   int loy = max((int)floorf(miny) - 2, 0), hiy = min((int)floorf(maxy) + 2, P.above.h - 1);
   if (P.use_tma == 2) {  // chroma needs an even origin; bilinear chroma reaches one chroma texel further
-    lox = max((lox & ~1) - 2, 0); loy = max((loy & ~1) - 2, 0);
+    lox = max(lox - 2, 0) & ~(P.align_x - 1); loy = max((loy & ~1) - 2, 0);
     hix = min(hix + 2, P.above.w - 1); hiy = min(hiy + 2, P.above.h - 1);
     ti.cbx = lox >> 1; ti.cby = loy >> 1;
     ti.fits = ((hix >> 1) - ti.cbx + 1 <= P.cbox_w) && ((hiy >> 1) - ti.cby + 1 <= P.cbox_h);
   } else {
+    lox &= ~(P.align_x - 1);
     ti.fits = true;
   }
   ti.bx = lox; ti.by = loy;
@@ -352,23 +354,30 @@ __global__ void __launch_bounds__(THREADS) k_gather_tma(const __grid_constant__ 
   }
   __syncthreads();
 
-  auto issue = [&](uint32_t t, int s) {
-    TileInfo ti = tile_info(P, t);
-    if (!ti.fits || !ti.any) return;
-    uint8_t* base = dyn + (size_t)s * stage_bytes;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of this stage vs. the async write
-    mbar_expect_tx(&bar[s], box0 + nchroma * cbox);
-    tma_load_3d(base, &M.m0, ti.bx * (P.ept ? P.ept : 1), ti.by, (int)ti.frame, &bar[s]);
-    if (nchroma >= 1) tma_load_3d(base + box0_al, &M.m1, ti.cbx, ti.cby, (int)ti.frame, &bar[s]);
-    if (nchroma == 2) tma_load_3d(base + box0_al + cbox_al, &M.m2, ti.cbx, ti.cby, (int)ti.frame, &bar[s]);
-  };
+  // NB: the tensor maps are read by the TMA unit through their param-space address; never let them
+  // be copied (no by-value captures / locals), a map in local memory is an illegal instruction.
+  const CUtensorMap* const m0 = &M.m0;
+  const CUtensorMap* const m1 = &M.m1;
+  const CUtensorMap* const m2 = &M.m2;
+#define ZOS_ISSUE(TILE_INDEX, STAGE)                                                                           \
+  do {                                                                                                          \
+    TileInfo ti_ = tile_info(P, (TILE_INDEX));                                                                  \
+    if (ti_.fits && ti_.any) {                                                                                  \
+      uint8_t* base_ = dyn + (size_t)(STAGE) * stage_bytes;                                                     \
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                                            \
+      mbar_expect_tx(&bar[(STAGE)], box0 + nchroma * cbox);                                                     \
+      tma_load_3d(base_, m0, ti_.bx * (P.ept ? P.ept : 1), ti_.by, (int)ti_.frame, &bar[(STAGE)]);              \
+      if (nchroma >= 1) tma_load_3d(base_ + box0_al, m1, ti_.cbx, ti_.cby, (int)ti_.frame, &bar[(STAGE)]);      \
+      if (nchroma == 2) tma_load_3d(base_ + box0_al + cbox_al, m2, ti_.cbx, ti_.cby, (int)ti_.frame, &bar[(STAGE)]); \
+    }                                                                                                           \
+  } while (0)
 
   uint32_t phase[2] = {0, 0};
   int s = 0;
-  if (threadIdx.x == 0 && blockIdx.x < P.total_tiles) issue(blockIdx.x, 0);
+  if (threadIdx.x == 0 && blockIdx.x < P.total_tiles) ZOS_ISSUE(blockIdx.x, 0);
   for (uint32_t t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
     const uint32_t next = t + gridDim.x;
-    if (threadIdx.x == 0 && next < P.total_tiles) issue(next, s ^ 1);
+    if (threadIdx.x == 0 && next < P.total_tiles) ZOS_ISSUE(next, s ^ 1);
     TileInfo ti = tile_info(P, t);
     if (ti.any) {
       if (ti.fits) {
@@ -481,10 +490,11 @@ zos_status launch_gather(zos_ctx* ctx, const DevImage* below, const DevImage& ab
       ex = (TILE - 1) * P.rx; ey = (TILE - 1) * P.ry;
     }
     const bool yuv = above.block != ZOS_BLOCK_PIXEL;
-    int need_w = (int)ceilf(ex) + (yuv ? 12 : 6), need_h = (int)ceilf(ey) + (yuv ? 12 : 6);
     int bpp = above.bpp;
-    int gran = bpp >= 16 ? 1 : 16 / bpp;  // box rows must be a multiple of 16 bytes
+    int gran = bpp >= 16 ? 1 : 16 / bpp;  // box rows must be a multiple of 16 bytes, and so must the box origin
     if (yuv) gran = 32;                   // so that the chroma box (half width) is too
+    P.align_x = gran;
+    int need_w = (int)ceilf(ex) + (yuv ? 12 : 6) + (gran - 1), need_h = (int)ceilf(ey) + (yuv ? 12 : 6);
     int bw = (need_w + gran - 1) / gran * gran, bh = need_h;
     P.ept = bpp >= 4 ? bpp / 4 : 0;
     uint32_t bw_elems = P.ept ? bw * P.ept : bw;
