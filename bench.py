@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the compositing hot path on B200 (contract: see the task brief).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+Default workload = BASELINE.json configs[1]: Porter-Duff source-over of two 3840x2160 RGBA8 sRGB
+layers composited in linear light.  One "step" = one launch of the fused kernel over a batch of
+FRAMES frame pairs resident in HBM (FRAMES * 99.5 MB touched once per step, far larger than the
+126 MB L2, so nothing is served from cache between steps).  Frames are independent: with N GPUs
+every rank owns its own batch (weak scaling, no collective on the data path).
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+  roofline     algorithmic bytes per launch / CUDA-event kernel time vs the measured HBM peak
+  cpu_baseline the CPU oracle (restatement of the reference pipeline; kind "port") on host cores
+  e2e          the same metric through host buffers: pinned H2D of the layers + kernel + D2H
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+NOMINAL_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return NOMINAL_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------ workloads
+class Workload:
+    """name, output pixels per frame, algorithmic bytes per frame, builders for GPU and CPU."""
+
+    def __init__(self, name, desc, out_px, in_px, bytes_per_frame, frames):
+        self.name, self.desc, self.out_px, self.in_px, self.bytes_per_frame, self.frames = name, desc, out_px, in_px, bytes_per_frame, frames
+
+
+def _descs():
+    import zosimos_b200 as Z
+    from zosimos_b200.buffer import ByteLayout, Color, Descriptor, SampleParts, Texel, Transfer
+
+    def d(w, h, texel, color):
+        b = texel.bits.bytes()
+        return Descriptor(ByteLayout(w, h, w * b, b), color, texel)
+    return Z, d, Color, Texel, SampleParts, Transfer
+
+
+def make_gpu_workload(name, ctx, frames, seed):
+    """Returns (workload, launch(), e2e_step() or None).  Inputs are generated on the host with the
+    seeds of SURVEY.md 8(d) and uploaded before timing."""
+    Z, d, Color, Texel, SampleParts, Transfer = _descs()
+    from oracle import oracle as O  # only for host-side parameter preparation of some workloads (matrices)
+    from zosimos_b200 import _ffi, ops
+    rng = np.random.default_rng(seed)
+    rgba8 = Texel.new_u8(SampleParts.RgbA)
+    lin = Color.Rgb(Z.Primaries.Bt709, Transfer.Linear)
+
+    def rand_u8(fr, h, rb):
+        return rng.integers(0, 256, (fr, h, rb), dtype=np.uint8)
+
+    if name in ("c2_blend", "c2_inscribe"):
+        W, H = 3840, 2160
+        desc = d(W, H, rgba8, Color.SRGB)
+        # one random frame pair, replicated on the device into `frames` distinct buffers (content does
+        # not influence the timing; generating 1.6 GB of host randomness would only slow the setup)
+        below, above, dst = ctx.image(desc, frames), ctx.image(desc, frames), ctx.image(desc, frames)
+        b0, a0 = rand_u8(1, H, W * 4), rand_u8(1, H, W * 4)
+        _replicate(ctx, below, b0); _replicate(ctx, above, a0)
+        blend = _ffi.BLEND_SRC_OVER if name == "c2_blend" else _ffi.BLEND_OVERWRITE
+        p = ops.compose_params(blend=blend, sel=(0, 0, W, H), tgt=(0, 0, W, H))
+        bpp = 12 if name == "c2_blend" else 8
+        wl = Workload(name, "Porter-Duff source-over, linear light" if name == "c2_blend" else "inscribe (full-size layer)",
+                      W * H, W * H, W * H * bpp, frames)
+
+        def launch():
+            ops.compose(ctx, below, above, dst, p)
+
+        # e2e: host layers -> device -> kernel -> host result, frame by frame through pinned memory
+        fb = W * H * 4
+        pin_in = ctx.pinned(2 * fb); pin_out = ctx.pinned(fb)
+        pin_in.array[:fb] = b0.reshape(-1); pin_in.array[fb:] = a0.reshape(-1)
+        one_b, one_a, one_d = ctx.image(desc, 1), ctx.image(desc, 1), ctx.image(desc, 1)
+        import ctypes as C
+        lib = ctx._lib
+
+        def e2e_frame():
+            ctx.check(lib.zos_buf_upload(ctx.handle, one_b.buf.handle, 0, one_b.pitch, C.c_void_p(pin_in.ptr.value), W * 4, W * 4, H))
+            ctx.check(lib.zos_buf_upload(ctx.handle, one_a.buf.handle, 0, one_a.pitch, C.c_void_p(pin_in.ptr.value + fb), W * 4, W * 4, H))
+            ops.compose(ctx, one_b, one_a, one_d, p)
+            ctx.check(lib.zos_buf_download(ctx.handle, one_d.buf.handle, 0, one_d.pitch, C.c_void_p(pin_out.ptr.value), W * 4, W * 4, H))
+        return wl, launch, (e2e_frame, 2 * fb, fb)
+
+    if name == "c1_oklab":
+        W = H = 4096
+        desc = d(W, H, rgba8, Color.SRGB)
+        lch = d(W, H, Texel(Z.Block.Pixel, Z.SampleBits.UInt8x4, SampleParts.LchA), Color.Oklab)
+        src, dst = ctx.image(desc, frames), ctx.image(desc, frames)
+        _replicate(ctx, src, rand_u8(1, H, W * 4))
+        T = O.to_xyz("bt709", "D65")
+        steps = [ops.step(_ffi.STEP_OKLAB_ENC, T), ops.requant(lch), ops.step(_ffi.STEP_OKLAB_DEC, O.inv3(T))]
+        wl = Workload(name, "sRGB8 -> Oklab (LchA u8 register) -> sRGB8, one fused kernel", W * H, W * H, W * H * 8, frames)
+        return wl, (lambda: ops.pixel_chain(ctx, src, dst, steps)), None
+
+    if name.startswith("c5_"):
+        fmt = name[3:]
+        W = H = 4096
+        M = O.mul3(O.inv3(O.to_xyz("bt709", "D65")), O.to_xyz("bt2020", "D65"))
+        if fmt == "rgba8":
+            sd = dd = d(W, H, rgba8, Color.SRGB); bpp = 8
+        elif fmt == "rgba16f":
+            sd = dd = d(W, H, Texel.new_f16(), lin); bpp = 16
+        elif fmt == "rgb10a2":
+            sd = dd = d(W, H, Texel(Z.Block.Pixel, Z.SampleBits.UInt1010102, SampleParts.RgbA), Color.Rgb(Z.Primaries.Bt709, Transfer.Srgb)); bpp = 8
+        else:
+            raise SystemExit("unknown workload " + name)
+        src, dst = ctx.image(sd, frames), ctx.image(dd, frames)
+        data = rand_u8(1, H, W * sd.layout.texel_stride)
+        if fmt == "rgba16f":
+            data = rng.random((1, H, W * 4), dtype=np.float32).astype(np.float16).view(np.uint8)
+        _replicate(ctx, src, data)
+        steps = [ops.matrix(M)]
+        wl = Workload(name, "decode -> 3x3 primaries matrix -> encode (%s)" % fmt, W * H, W * H, W * H * bpp, frames)
+        return wl, (lambda: ops.pixel_chain(ctx, src, dst, steps)), None
+
+    if name in ("c3_affine_bilinear", "c3_affine_nearest"):
+        W, H = 7680, 4320
+        desc = d(W, H, Texel.new_f16(), lin)
+        below, above, dst = ctx.image(desc, frames), ctx.image(desc, frames), ctx.image(desc, frames)
+        v = rng.random((1, 270, W * 4), dtype=np.float32)
+        v[rng.random(v.shape) < 0.01] *= 4.0
+        tile = np.tile(v.astype(np.float16), (1, H // 270, 1)).view(np.uint8)
+        _replicate(ctx, below, tile); _replicate(ctx, above, tile[:, ::-1].copy())
+        ang = np.deg2rad(30.0)
+        m = (O.shift(W / 2, H / 2) @ O.rotate(ang) @ O.shift(-W / 2, -H / 2)).astype(np.float32)
+        inv = O.inv3(m.astype(np.float64)).astype(np.float32)
+        p = ops.compose_params(map=_ffi.MAP_AFFINE, sampling=_ffi.SAMPLE_BILINEAR if name.endswith("bilinear") else _ffi.SAMPLE_NEAREST,
+                               inv=inv, use_tma=True)
+        wl = Workload(name, "affine rotate 30deg, %s, RGBA16F over RGBA16F" % name.split("_")[-1], W * H, W * H, W * H * 16, frames)
+        return wl, (lambda: ops.compose(ctx, below, above, dst, p)), None
+
+    if name == "c4_fused":
+        W, H, w, h = 1920, 1080, 1280, 720
+        yuv = Z.yuv420_descriptor(W, H, Color.Rgb(Z.Primaries.Bt2020, Transfer.Bt709), Z.YuvMatrix.Bt709, False, False, 0)
+        src = ctx.image(yuv, frames)
+        y = rng.integers(16, 236, (1, H, W), dtype=np.uint8)
+        u = rng.integers(16, 241, (1, H // 2, W // 2), dtype=np.uint8); vv = rng.integers(16, 241, (1, H // 2, W // 2), dtype=np.uint8)
+        one = ctx.image(yuv, 1); one.upload((y, u, vv))
+        for f in range(frames):
+            ctx.check(ctx._lib.zos_buf_copy(ctx.handle, src.buf.handle, f * src.frame_bytes, one.buf.handle, 0, src.frame_bytes))
+        od = d(w, h, rgba8, Color.SRGB)
+        bg = ctx.upload(od, rand_u8(1, h, w * 4)[0])  # one background shared by all frames (batch_stride 0)
+        dst = ctx.image(od, frames)
+        M = O.mul3(O.inv3(O.to_xyz("bt709", "D65")), O.to_xyz("bt2020", "D65"))
+        p = ops.compose_params(map=_ffi.MAP_SCALE, sampling=_ffi.SAMPLE_BILINEAR, blend=_ffi.BLEND_SRC_OVER, src_steps=[ops.matrix(M)], use_tma=True)
+        bpf = W * H * 3 // 2 + 2 * w * h * 4
+        wl = Workload(name, "I420 unpack -> BT.2020->709 matrix -> bilinear 1080p->720p -> over RGBA8 bg -> sRGB8 pack", w * h, W * H, bpf, frames)
+        return wl, (lambda: ops.compose(ctx, bg, src, dst, p)), None
+    raise SystemExit("unknown workload " + name)
+
+
+def _replicate(ctx, img, one_frame):
+    """Uploads one frame and copies it device-side into every frame slot of `img`."""
+    import zosimos_b200 as Z
+    tmp = ctx.image(img.desc, 1)
+    tmp.upload(one_frame)
+    for f in range(img.batch):
+        ctx.check(ctx._lib.zos_buf_copy(ctx.handle, img.buf.handle, f * img.frame_bytes, tmp.buf.handle, 0, img.frame_bytes))
+    ctx.sync()
+    tmp.free()
+
+
+# ------------------------------------------------------------------ CPU baseline (oracle = "port")
+def cpu_baseline(name, budget_s=12.0):
+    """Times the CPU oracle (pass-structured restatement of the reference pipeline, OpenMP over rows)
+    on a bounded sample of the workload.  Returns MP/s (output pixels of the same definition)."""
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    rng = np.random.default_rng(1)
+    if name in ("c2_blend", "c2_inscribe"):
+        W, H = 3840, 2160
+        od = O.srgb_rgba8(W, H)
+        a = O.Image(od, rng.integers(0, 256, (H, W * 4), dtype=np.uint8)); b = O.Image(od, rng.integers(0, 256, (H, W * 4), dtype=np.uint8))
+        fn = (lambda: O.blend(b, (0, 0, W, H), a, 3)) if name == "c2_blend" else (lambda: O.inscribe(b, (0, 0, W, H), a, exact_quirks=False))
+        px = W * H; sample = "1 frame pair 3840x2160 per repetition"
+    elif name == "c1_oklab":
+        W = H = 2048
+        od = O.srgb_rgba8(W, H)
+        a = O.Image(od, rng.integers(0, 256, (H, W * 4), dtype=np.uint8))
+        fn = lambda: O.color_convert(O.color_convert(a, O.OKLAB, O.Texel(O.B_UINT8X4, O.P_LCHA)), O.SRGB, O.RGBA8)
+        px = W * H; sample = "2048x2048 per repetition"
+    else:
+        return None
+    fn()  # warm up (page faults, tables)
+    t0 = time.perf_counter(); n = 0
+    while True:
+        fn(); n += 1
+        dt = time.perf_counter() - t0
+        if dt > budget_s or n >= 50:
+            break
+    return {"value": round(px * n / dt / 1e6, 2), "unit": "MP/s", "cores": cores, "kind": "port",
+            "sample": "%s, %d repetitions in %.1f s, oracle/zos_oracle.c with OpenMP on %d threads" % (sample, n, dt, cores)}
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0])); self.max_mhz = float(out[1])
+                for nme, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(nme)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------ main
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is Rust + wgpu
+    (no cargo, no Vulkan ICD here), so oracle/_ref does not exist; the timed code is the oracle port."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = args.workload
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    W, H = 3840, 2160
+    rng = np.random.default_rng(1)
+    od = O.srgb_rgba8(W, H)
+    a = O.Image(od, rng.integers(0, 256, (H, W * 4), dtype=np.uint8)); b = O.Image(od, rng.integers(0, 256, (H, W * 4), dtype=np.uint8))
+    if name == "c2_inscribe":
+        fn = lambda: O.inscribe(b, (0, 0, W, H), a, exact_quirks=False)
+    else:
+        name = "c2_blend"
+        fn = lambda: O.blend(b, (0, 0, W, H), a, 3)
+    for _ in range(args.warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fn()
+    dt = time.perf_counter() - t0
+    v = round(W * H * args.steps / dt / 1e6, 2)
+    sample = "each step = 1 frame pair 3840x2160 (of the %d-frame batch the GPU arm processes per step)" % args.frames
+    line = {"impl": "reference", "metric": "megapixels/sec", "value": v, "unit": "MP/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name, "width": W, "height": H, "layers": 2, "frames_per_step": 1},
+            "cpu_baseline": {"value": v, "unit": "MP/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c2_blend")
+    ap.add_argument("--frames", type=int, default=16, help="frames per step per GPU")
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import zosimos_b200 as Z
+    ctx = Z.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local)
+    wl, launch, e2e = make_gpu_workload(args.workload, ctx, args.frames, seed=1 + rank)
+
+    def barrier():
+        ctx.sync(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ctx.sync(); torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        launch()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = ctx.launch_count
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record(stream)
+    for i in range(args.steps):
+        launch()
+        ev[i + 1].record(stream)
+    barrier()
+    launches = ctx.launch_count - l0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps))
+    t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+
+    # end to end: pinned host -> device -> kernel -> host, every frame of the step
+    e2e_out = None
+    if e2e is not None:
+        fn, h2d, d2h = e2e
+        for _ in range(3):
+            fn()
+        barrier()
+        nfr = max(8, min(args.frames * 2, 32))
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record(stream)
+        for _ in range(nfr):
+            fn()
+        t1.record(stream)
+        barrier()
+        te = torch.tensor([t0.elapsed_time(t1)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_val = wl.out_px * nfr * world / (float(te.item()) * 1e-3) / 1e6
+        e2e_out = {"value": round(e2e_val, 1), "unit": "MP/s", "h2d_bytes_per_step": h2d * args.frames, "d2h_bytes_per_step": d2h * args.frames,
+                   "note": "frame by frame through pinned host buffers on one stream (PCIe bound)"}
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        ms_step = total_ms_max / args.steps
+        value = wl.out_px * wl.frames * world / (ms_step * 1e-3) / 1e6
+        med = per[len(per) // 2]
+        avg = total_ms / args.steps
+        achieved = wl.bytes_per_frame * wl.frames / (avg * 1e-3) / 1e9
+        line = {
+            "metric": "megapixels/sec", "value": round(value, 1), "unit": "MP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl.name, "what": wl.desc, "frames_per_step_per_gpu": wl.frames,
+                       "out_px_per_frame": wl.out_px, "l2": "each step touches %.0f MB once (> 126 MB L2)" % (wl.bytes_per_frame * wl.frames / 1e6),
+                       "parallelism": "frame-batch sharding over %d GPU(s), no collective" % world},
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": wl.bytes_per_frame * wl.frames,
+                         "kernel_ms_avg": round(avg, 4), "kernel_ms_median": round(med, 4)},
+            "gpu_launches": int(launches),
+            "clocks": sampler.result() if sampler else None,
+        }
+        if e2e_out:
+            line["e2e"] = e2e_out
+        if not args.no_cpu:
+            cb = cpu_baseline(wl.name)
+            if cb:
+                line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
