@@ -114,6 +114,9 @@ int32_t zos_ctx_device(const zos_ctx* ctx);
 void* zos_ctx_stream(const zos_ctx* ctx);       /* the cudaStream_t all launches of this ctx go to */
 zos_status zos_sync(zos_ctx* ctx);              /* SyncPoint::block_on, run.rs:3019 */
 uint64_t zos_ctx_launch_count(const zos_ctx* ctx); /* kernels launched so far (bench: gpu_launches) */
+/* debugging / parity switches; ZOS_CTX_NO_FAST_PATHS routes every launch through the generic kernels */
+enum { ZOS_CTX_NO_FAST_PATHS = 1 };
+zos_status zos_ctx_set_flags(zos_ctx* ctx, uint32_t flags);
 
 zos_status zos_buf_alloc(zos_ctx* ctx, uint64_t bytes, zos_buf** out);
 void zos_buf_free(zos_ctx* ctx, zos_buf* buf);

@@ -721,9 +721,10 @@ static inline void pd_blend(int mode, const float* s, const float* d, float* o) 
   pd_factors(mode, as, ad, &fa, &fb);
   float wa = as * fa, wb = ad * fb;
   float ao = wa + wb;
+  float rcp = ao > 0.0f ? 1.0f / ao : 0.0f; /* one correctly rounded reciprocal per pixel */
   for (int k = 0; k < 3; k++) {
     float pm = fmaf(wb, d[k], wa * s[k]);
-    o[k] = ao > 0.0f ? pm / ao : 0.0f;
+    o[k] = pm * rcp;
   }
   o[3] = ao;
 }

@@ -415,3 +415,53 @@ def test_yuv420_to_rgba8(ctx, nv12, chroma_filter):
     exp = O.encode(oracle_desc(dd), tex).data
     assert max_lsb(got, exp) <= 1
     assert np.mean(got == exp) > 0.99
+
+
+# ---------------------------------------------------------------- specialised kernels == generic kernels
+def test_fast_u8_kernel_equals_generic(ctx):
+    """rowwise_u8.cu must produce the bytes of the generic kernel (and of the oracle) for every
+    combination of native 8-bit storage, with a matrix step, with overwrite and with source-over."""
+    W, H = 1021, 64
+    rng = np.random.default_rng(9)
+    a = rng.integers(0, 256, (H, W * 4), dtype=np.uint8); b = rng.integers(0, 256, (H, W * 4), dtype=np.uint8)
+    a.reshape(H, W, 4)[::3, ::5, 3] = 0; a.reshape(H, W, 4)[1::3, ::7, 3] = 255; b.reshape(H, W, 4)[::4, ::3, 3] = 0
+    M = O.mul3(O.inv3(O.to_xyz("bt709", "D65")), O.to_xyz("bt2020", "D65"))
+    colors = [Color.SRGB, Color.Rgb(Z.Primaries.Bt709, Transfer.Linear)]
+    for sc in colors:
+        for dc in colors:
+            for sp, dp in ((SampleParts.RgbA, SampleParts.RgbA), (SampleParts.BgrA, SampleParts.RgbA), (SampleParts.RgbA, SampleParts.BgrA)):
+                sd, dd = zdesc(W, H, Texel.new_u8(sp), sc), zdesc(W, H, Texel.new_u8(dp), dc)
+                for steps in ([], [ops.matrix(M)], [ops.matrix(M), ops.matrix(O.inv3(M))]):
+                    res = []
+                    for flags in (0, 1):
+                        ctx.set_flags(flags)
+                        res.append(run_chain(ctx, sd, a, dd, steps))
+                    ctx.set_flags(0)
+                    assert np.array_equal(res[0], res[1]), (sc, dc, sp, dp, len(steps))
+                    tex = O.decode(oracle_image(sd, a))
+                    for s in steps:
+                        tex = O.linear(tex, np.array(list(s.m)).reshape(3, 3))
+                    assert np.array_equal(res[0], O.encode(oracle_desc(dd), tex).data)
+    d = zdesc(W, H, Texel.new_u8(SampleParts.RgbA), Color.SRGB)
+    below, above, dst = ctx.upload(d, b), ctx.upload(d, a), ctx.image(d)
+    for blend in (_ffi.BLEND_OVERWRITE, _ffi.BLEND_SRC_OVER):
+        for tgt in ((0, 0, W, H),):
+            res = []
+            for flags in (0, 1):
+                ctx.set_flags(flags)
+                ops.compose(ctx, below, above, dst, ops.compose_params(blend=blend, sel=(0, 0, W, H), tgt=tgt, dst_steps=[ops.matrix(M)]))
+                res.append(dst.download())
+            ctx.set_flags(0)
+            assert np.array_equal(res[0], res[1])
+
+
+def test_unorm8_decode_exact_all_codes(ctx):
+    """code * (1/255) + one Newton step == IEEE code / 255 for all 256 codes (rowwise_u8.cu)."""
+    w, h = 256, 4
+    data = np.zeros((h, w, 4), np.uint8)
+    for c in range(4):
+        data[..., c] = (np.arange(256)[None, :] + 37 * c) % 256
+    sd = zdesc(w, h, Texel.new_u8(SampleParts.RgbA), Color.Rgb(Z.Primaries.Bt709, Transfer.Linear))
+    dd = zdesc(w, h, Texel.new_f32(), Color.Rgb(Z.Primaries.Bt709, Transfer.Linear))
+    got = run_chain(ctx, sd, data, dd, []).view(np.float32).reshape(h, w, 4)
+    assert np.array_equal(got, data.astype(np.float32) / np.float32(255))

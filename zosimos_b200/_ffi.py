@@ -86,6 +86,7 @@ SIGNATURES = {
     "zos_ctx_device": (C.c_int32, [_P]),
     "zos_ctx_stream": (_P, [_P]),
     "zos_sync": (C.c_int32, [_P]),
+    "zos_ctx_set_flags": (C.c_int32, [_P, C.c_uint32]),
     "zos_ctx_launch_count": (C.c_uint64, [_P]),
     "zos_buf_alloc": (C.c_int32, [_P, C.c_uint64, C.POINTER(_P)]),
     "zos_buf_free": (None, [_P, _P]),

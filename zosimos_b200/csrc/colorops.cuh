@@ -128,13 +128,11 @@ __device__ __forceinline__ float4 porter_duff(int mode, const float4& s, const f
   float wa = as * fa, wb = ad * fb;
   float ao = wa + wb;
   float4 o;
-  if (ao > 0.0f) {
-    o.x = __fdiv_rn(fmaf(wb, d.x, wa * s.x), ao);
-    o.y = __fdiv_rn(fmaf(wb, d.y, wa * s.y), ao);
-    o.z = __fdiv_rn(fmaf(wb, d.z, wa * s.z), ao);
-  } else {
-    o.x = o.y = o.z = 0.0f;
-  }
+  // un-premultiply with ONE correctly rounded reciprocal (the oracle does the same: 1.0f / ao)
+  float rcp = ao > 0.0f ? __frcp_rn(ao) : 0.0f;
+  o.x = fmaf(wb, d.x, wa * s.x) * rcp;
+  o.y = fmaf(wb, d.y, wa * s.y) * rcp;
+  o.z = fmaf(wb, d.z, wa * s.z) * rcp;
   o.w = ao;
   return o;
 }

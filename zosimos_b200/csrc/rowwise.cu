@@ -7,6 +7,8 @@
 // copy.frag + box.vert) and the encode pass (stage.frag encode_*), i.e.
 // lib/zosimos/src/program.rs:1475-1533.  HBM traffic is the algorithmic minimum: every source
 // texel is read once, every destination texel written once.
+#include <stdlib.h>
+
 #include "colorops.cuh"
 #include "zos_internal.h"
 
@@ -179,6 +181,8 @@ zos_status launch_rowwise(zos_ctx* ctx, const DevImage* below, const DevImage* a
   }
   if (!vec_ok(P.below) || !vec_ok(dst))
     return fail(ctx, ZOS_ERR_INVALID, "rowwise: buffers must be 16-byte aligned with padded rows (use zos_aligned_row_stride)");
+  // native 8-bit texels with at most matrix steps: the specialised kernel (rowwise_u8.cu), same results
+  if (!(ctx->flags & ZOS_CTX_NO_FAST_PATHS) && rowwise_u8_eligible(below, above, dst, cp, steps, nsteps)) return launch_rowwise_u8(ctx, below, above, dst, cp, steps, nsteps, batch);
   uint64_t gpr = (uint64_t)(dst.w + 3) / 4;
   uint64_t total = gpr * (uint64_t)dst.h * batch;
   if (total == 0) return ZOS_OK;

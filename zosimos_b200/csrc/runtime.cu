@@ -13,6 +13,7 @@ namespace zos {
 cudaError_t upload_constants_rowwise(const TablesGlobal*, const ColorConstants*, cudaStream_t);
 cudaError_t upload_constants_gather(const TablesGlobal*, const ColorConstants*, cudaStream_t);
 cudaError_t upload_constants_misc(const TablesGlobal*, const ColorConstants*, cudaStream_t);
+cudaError_t upload_constants_rowwise_u8(const TablesGlobal*, const ColorConstants*, cudaStream_t);
 
 static thread_local std::string g_create_error;
 
@@ -231,10 +232,11 @@ zos_status zos_ctx_create(int32_t device, zos_ctx** out) {
     cudaError_t e1 = upload_constants_rowwise(t, c, ctx->stream);
     cudaError_t e2 = upload_constants_gather(t, c, ctx->stream);
     cudaError_t e3 = upload_constants_misc(t, c, ctx->stream);
+    cudaError_t e5 = upload_constants_rowwise_u8(t, c, ctx->stream);
     cudaError_t e4 = cudaStreamSynchronize(ctx->stream);
     delete t;
     delete c;
-    cudaError_t ee = e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3 != cudaSuccess ? e3 : e4;
+    cudaError_t ee = e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3 != cudaSuccess ? e3 : e5 != cudaSuccess ? e5 : e4;
     if ((st = check_cuda(ctx, ee, "constant upload")) != ZOS_OK) goto bad;
   }
   *out = ctx;
@@ -258,6 +260,11 @@ const char* zos_last_error(const zos_ctx* ctx) { return ctx ? ctx->err.c_str() :
 int32_t zos_ctx_device(const zos_ctx* ctx) { return ctx ? ctx->device : -1; }
 void* zos_ctx_stream(const zos_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 uint64_t zos_ctx_launch_count(const zos_ctx* ctx) { return ctx ? ctx->launches : 0; }
+zos_status zos_ctx_set_flags(zos_ctx* ctx, uint32_t flags) {
+  if (!ctx) return ZOS_ERR_INVALID;
+  ctx->flags = flags;
+  return ZOS_OK;
+}
 zos_status zos_sync(zos_ctx* ctx) {
   if (!ctx) return ZOS_ERR_INVALID;
   return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");

@@ -18,6 +18,7 @@ struct zos_ctx {
   cudaStream_t stream = nullptr;
   int sm_count = 148;
   uint64_t launches = 0;
+  uint32_t flags = 0;
   std::string err;
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved lazily through the runtime
   std::vector<void*> scratch;    // device scratch owned by the ctx (tensor maps etc.)
@@ -63,6 +64,10 @@ int grid_for(const zos_ctx* ctx, uint64_t work_items, int threads, int ctas_per_
 // kernel launchers (one per .cu)
 zos_status launch_rowwise(zos_ctx* ctx, const DevImage* below, const DevImage* above, const DevImage& dst,
                           const zos_compose_params* cp, const zos_step* steps, uint32_t nsteps, uint32_t batch);
+bool rowwise_u8_eligible(const DevImage* below, const DevImage* above, const DevImage& dst, const zos_compose_params* cp,
+                         const zos_step* steps, uint32_t nsteps);
+zos_status launch_rowwise_u8(zos_ctx* ctx, const DevImage* below, const DevImage* above, const DevImage& dst,
+                             const zos_compose_params* cp, const zos_step* steps, uint32_t nsteps, uint32_t batch);
 bool rowwise_can_compose(const DevImage& below, const DevImage& above, const DevImage& dst, const zos_compose_params& cp);
 zos_status launch_gather(zos_ctx* ctx, const DevImage* below, const DevImage& above, const DevImage& dst,
                          const zos_compose_params& cp, uint32_t batch);

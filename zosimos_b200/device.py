@@ -37,6 +37,10 @@ class Context:
     def launch_count(self) -> int:
         return int(self._lib.zos_ctx_launch_count(self.handle))
 
+    def set_flags(self, flags: int):
+        """ZOS_CTX_NO_FAST_PATHS = 1: route every launch through the generic kernels (parity checks)."""
+        self.check(self._lib.zos_ctx_set_flags(self.handle, int(flags)))
+
     def sync(self):
         self.check(self._lib.zos_sync(self.handle))
 
