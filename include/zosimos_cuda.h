@@ -147,6 +147,12 @@ typedef struct zos_image {
   uint64_t chroma_batch_stride;
 } zos_image;
 
+/* whole-image transfers between TIGHT host rows and a (pitched) device image, frame `frame` of a
+ * batch.  Host layout: plane 0 rows of width*texel_stride bytes; planar 4:2:0 then U and V rows
+ * (I420) or the interleaved UV rows (NV12).  Asynchronous on the ctx stream when `host` is pinned. */
+zos_status zos_image_upload(zos_ctx* ctx, const zos_image* dst, uint32_t frame, const void* host);
+zos_status zos_image_download(zos_ctx* ctx, const zos_image* src, uint32_t frame, void* host);
+
 /* ---- per-pixel steps fused into a kernel between unpack and pack.  Parameter layouts are the
  *      reference's uniform blocks with matrices row-major. ---- */
 enum {
@@ -212,6 +218,7 @@ zos_status zos_compose(zos_ctx* ctx, const zos_image* below, const zos_image* ab
 /* constructors (ConstructOp::{Solid,Bilinear}, command.rs:1524-1633; bilinear.frag, solid_rgb.frag):
  * p = 24 floats u_min,u_max,v_min,v_max,uv_min,uv_max; for a solid colour put it in u_min and zero the rest */
 zos_status zos_generate_bilinear(zos_ctx* ctx, const zos_image* dst, const float* p, uint32_t batch);
+zos_status zos_generate_solid(zos_ctx* ctx, const zos_image* dst, const float* color /* 4 floats */, uint32_t batch);
 /* box3.frag:16-52 (derivative, command.rs:1493-1508): m = 3x3 weights, row-major [dy+1][dx+1] */
 zos_status zos_box3(zos_ctx* ctx, const zos_image* src, const zos_image* dst, const float* m, uint32_t batch);
 /* palette.frag:21-32 (command.rs:1442-1485): dst = pal @ (xc . idx, yc . idx) */
@@ -240,6 +247,7 @@ typedef struct zos_op {
   zos_compose_params compose;
   float gen[24];
   uint32_t knob; /* 0 = none, else 1-based knob id whose bytes overwrite this op's parameter block */
+  int32_t reg;   /* this op's own register number (Register(idx), command.rs:31); equals dst except for Output ops */
 } zos_op;
 enum { ZOS_FUSE_EXACT = 0 /* every declared register is quantised like the reference, in registers */,
        ZOS_FUSE_WIDE = 1 /* fused intermediates stay f32 */,

@@ -1,0 +1,82 @@
+/* zosimos_host.h -- C view of the C++ host layer that mirrors the reference's operator API
+ * (`CommandBuffer` and `Linker`, lib/zosimos/src/command.rs) above the device C-ABI of
+ * zosimos_cuda.h.  A Rust maintainer keeps the reference's own CommandBuffer/Linker and binds at
+ * zos_program_create; this layer exists for C/C++/Python callers (the reference's toolchain is not
+ * available in the build image, so the parity tests drive this mirror).  Same names, argument
+ * meaning and error behaviour as the reference; every function cites the method it mirrors.
+ */
+#ifndef ZOSIMOS_HOST_H
+#define ZOSIMOS_HOST_H
+
+#include "zosimos_cuda.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* CommandErrorKind, lib/zosimos/src/command.rs:3612-3647 */
+enum {
+  ZOSH_OK = 0,
+  ZOSH_ERR_BAD_DESCRIPTOR = 1,    /* CommandErrorKind::BadDescriptor */
+  ZOSH_ERR_CONFLICTING_TYPES = 2, /* CommandErrorKind::ConflictingTypes */
+  ZOSH_ERR_TYPE = 3,              /* CommandError::TYPE_ERR (GenericTypeError) */
+  ZOSH_ERR_OTHER = 4,             /* CommandError::OTHER (also BAD_REGISTER / INVALID_CALL) */
+  ZOSH_ERR_UNIMPLEMENTED = 5,     /* CommandError::UNIMPLEMENTED / CompileError::NotYetImplemented */
+  ZOSH_ERR_CONCRETE_REQUIRED = 6  /* CommandErrorKind::ConcreteDescriptorRequired */
+};
+enum { ZOSH_ADAPT_BRADFORD_VONKRIES = 0, ZOSH_ADAPT_VONKRIES = 1, ZOSH_ADAPT_XYZ = 2, ZOSH_ADAPT_BRADFORD_NONLINEAR = 3 };
+enum { ZOSH_RESIZE_REFERENCE = 0 /* 8-bit grid + palette, command.rs:1675-1702 */, ZOSH_RESIZE_NEAREST = 1, ZOSH_RESIZE_BILINEAR = 2 };
+enum { ZOSH_DERIV_PREWITT = 0, ZOSH_DERIV_SOBEL = 1, ZOSH_DERIV_SCHARR3 = 2, ZOSH_DERIV_SCHARR3_TO_4BIT = 3, ZOSH_DERIV_SCHARR3_TO_8BIT = 4,
+       ZOSH_DERIV_ROBERTS = 5 /* NotYetImplemented, command.rs:3402-3408 */ };
+
+typedef struct zosh_cb zosh_cb;           /* command::CommandBuffer */
+typedef struct zosh_program zosh_program; /* program::Program (the linked High stream) */
+typedef struct zosh_rect { uint32_t x, y, max_x, max_y; } zosh_rect; /* command::Rectangle, command.rs:311-317 */
+
+const char* zosh_last_error(void); /* message of the last failure on this thread */
+
+/* colour science used by the op builder (image-canvas Primaries::to_xyz_row_matrix, palette
+ * TransformMatrix; call sites command.rs:1023-1073, 3281-3338).  Row-major 3x3, f32. */
+int32_t zosh_to_xyz_matrix(uint32_t primaries, uint32_t whitepoint, float out[9]);
+int32_t zosh_adaptation_matrix(uint32_t method, uint32_t src_wp, uint32_t dst_wp, float out[9]);
+int32_t zosh_whitepoint_xyz(uint32_t whitepoint, float out[3]);
+/* Affine::{new,scale,rotate,shift}: left multiplication in f32, command.rs:3421-3485 */
+void zosh_affine_identity(float m[9]);
+void zosh_affine_scale(float m[9], float x, float y);
+void zosh_affine_rotate(float m[9], float rad);
+void zosh_affine_shift(float m[9], float x, float y);
+/* Rectangle::normalize with the reference's max_y = y + width (command.rs:3536-3543) */
+zosh_rect zosh_rect_normalize(zosh_rect r);
+
+zosh_cb* zosh_cb_new(void);
+void zosh_cb_free(zosh_cb* cb);
+/* every builder returns ZOSH_OK and the new register in *reg, or an error kind */
+int32_t zosh_cb_input(zosh_cb* cb, const zos_desc* desc, int32_t* reg);                               /* command.rs:743 */
+int32_t zosh_cb_output(zosh_cb* cb, int32_t src, int32_t* reg);                                      /* command.rs:1707 */
+int32_t zosh_cb_describe(const zosh_cb* cb, int32_t reg, zos_desc* out);                             /* describe_reg */
+int32_t zosh_cb_color_convert(zosh_cb* cb, int32_t src, const zos_desc* color_and_texel, int32_t* reg); /* command.rs:986 */
+int32_t zosh_cb_chromatic_adaptation(zosh_cb* cb, int32_t src, uint32_t method, uint32_t target_wp, int32_t* reg); /* :1112 */
+int32_t zosh_cb_inscribe(zosh_cb* cb, int32_t below, zosh_rect rect, int32_t above, int32_t* reg);   /* command.rs:1177 */
+int32_t zosh_cb_crop(zosh_cb* cb, int32_t src, zosh_rect rect, int32_t* reg);                        /* command.rs:971 */
+int32_t zosh_cb_affine(zosh_cb* cb, int32_t below, const float m[9], uint32_t sampling, int32_t above, int32_t* reg); /* :1636 */
+int32_t zosh_cb_resize(zosh_cb* cb, int32_t below, uint32_t w, uint32_t h, uint32_t mode, int32_t* reg); /* command.rs:1675 */
+int32_t zosh_cb_blend(zosh_cb* cb, int32_t below, zosh_rect rect, int32_t above, int32_t mode, int32_t* reg); /* command.rs:1510 */
+int32_t zosh_cb_transmute(zosh_cb* cb, int32_t src, const zos_desc* target, int32_t* reg);            /* command.rs:1276 */
+int32_t zosh_cb_bilinear(zosh_cb* cb, const zos_desc* desc, const float p[24], int32_t* reg);         /* command.rs:1615 */
+int32_t zosh_cb_solid_rgba(zosh_cb* cb, const zos_desc* desc, const float color[4], int32_t* reg);    /* command.rs:1524 */
+int32_t zosh_cb_derivative(zosh_cb* cb, int32_t src, uint32_t method, uint32_t height_direction, int32_t* reg); /* :1493 */
+int32_t zosh_cb_palette(zosh_cb* cb, int32_t palette, int32_t indices, const float xc[4], const float yc[4], int32_t* reg); /* :1442 */
+int32_t zosh_cb_with_knob(zosh_cb* cb);  /* the NEXT operation gets a knob; returns its 1-based id (command.rs:1865-1874) */
+
+/* Linker::compile (command.rs:2069): liveness + emission of the High-like op list */
+int32_t zosh_compile(const zosh_cb* cb, zosh_program** out);
+void zosh_program_free(zosh_program* p);
+uint32_t zosh_program_num_ops(const zosh_program* p);
+const zos_op* zosh_program_ops(const zosh_program* p);
+/* Program::lower_to (program.rs:1304): hand the stream to the device planner */
+zos_status zosh_program_lower(const zosh_program* p, zos_ctx* ctx, uint32_t fuse_mode, uint32_t batch, zos_program** out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,294 @@
+"""GPU tests at the program level: the pipelines of the reference's integration tests
+(lib/zosimos/tests/blend.rs, knobs.rs, direct.rs) written against the mirror API
+(CommandBuffer -> Linker.compile -> Program.lower_to -> Executable.launch -> step -> Retire),
+checked against the reference's golden hashes and, byte for byte, against the oracle; plus the
+planner's fusion (fused == unfused in ZOS_FUSE_EXACT mode)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import refpipes as R
+from tests.gpu_common import oracle_desc, oracle_image
+
+pytestmark = pytest.mark.gpu
+
+import zosimos_b200 as Z  # noqa: E402
+from zosimos_b200 import _ffi  # noqa: E402
+from zosimos_b200.buffer import Color, Descriptor, SampleBits, SampleParts, Texel, Transfer  # noqa: E402
+from zosimos_b200.command import (Affine, AffineSample, Bilinear, Blend, ChromaticAdaptationMethod, CommandBuffer, Derivative,  # noqa: E402
+                                  DerivativeMethod, Linker, Palette, Rectangle, RegisterKnob, ResizeMode)
+from zosimos_b200.program import Capabilities, Pool, StartError, StepError  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def pool():
+    p = Pool()
+    p.request_device(0)
+    yield p
+    for c in p.iter_devices():
+        c.close()
+
+
+def run_once_with_output(commands, pool, binds, out_reg, fuse_mode=_ffi.FUSE_EXACT, knobs=()):
+    """tests/util.rs:62-117."""
+    plan = Linker.from_included().compile(commands)
+    caps = Capabilities.from_device(next(pool.iter_devices()), fuse_mode)
+    executable = plan.lower_to(caps)
+    return run_executable_with_output(executable, pool, binds, out_reg, knobs)
+
+
+def run_executable_with_output(executable, pool, binds, out_reg, knobs=()):
+    env = executable.from_pool(pool)
+    for knob, data in knobs:
+        env.knob(knob, data)
+    for reg, key in binds:
+        env.bind(reg, key)
+    env.recover_buffers()
+    execution = executable.launch(env)
+    pool.clear_cache()
+    n = 0
+    while execution.is_running():
+        execution.step().block_on()
+        n += 1
+    retire = execution.retire_gracefully(pool)
+    img = retire.output(out_reg)
+    retire.retire_buffers()
+    retire.finish()
+    return img, n
+
+
+def hashes():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "reference_hashes.json")) as f:
+        return json.load(f)
+
+
+def rgba(img):
+    d = img.descriptor()
+    return img.as_bytes().reshape(d.layout.height, d.layout.width, 4)
+
+
+@pytest.fixture(scope="module")
+def images(pool, fixtures):
+    bg = pool.insert_srgb(fixtures["background"])
+    fg = pool.insert_srgb(fixtures["foreground"])
+    return bg, fg
+
+
+def test_run_blending(pool, images, fixtures):  # tests/blend.rs:81-116
+    bg, fg = images
+    c = CommandBuffer()
+    background, foreground = c.input(bg.descriptor()), c.input(fg.descriptor())
+    placement = Rectangle(0, 0, fg.layout().width, fg.layout().height)
+    result = c.inscribe(background, placement, foreground)
+    output, _ = c.output(result)
+    img, n = run_once_with_output(c, pool, [(background, bg.key()), (foreground, fg.key())], output)
+    assert n == 1  # the reference needs 2 draws + staging copies; here: one kernel
+    assert O.blockhash256(rgba(img)) in hashes()["composed"]
+    exp = O.inscribe(oracle_image(bg.descriptor(), fixtures["background"]), (0, 0, 157, 151), oracle_image(fg.descriptor(), fixtures["foreground"]))
+    assert np.array_equal(img.as_bytes(), exp.data.reshape(-1))
+
+
+def test_run_affine(pool, images, fixtures):  # tests/blend.rs:118-166
+    bg, fg = images
+    fw, fh, W, H = fg.layout().width, fg.layout().height, bg.layout().width, bg.layout().height
+    affine = Affine.new(AffineSample.Nearest).shift(-float(fw // 2), -float(fh // 2)).rotate(np.float32(np.pi) / np.float32(4)).shift(float(W // 2), float(H // 2))
+    c = CommandBuffer()
+    background, foreground = c.input(bg.descriptor()), c.input(fg.descriptor())
+    output, _ = c.output(c.affine(background, affine, foreground))
+    img, _ = run_once_with_output(c, pool, [(background, bg.key()), (foreground, fg.key())], output)
+    assert O.blockhash256(rgba(img)) in hashes()["affine"]
+    exp = O.affine(oracle_image(bg.descriptor(), fixtures["background"]), np.array(affine.transformation, np.float32).reshape(3, 3),
+                   oracle_image(fg.descriptor(), fixtures["foreground"]))
+    assert np.array_equal(img.as_bytes(), exp.data.reshape(-1))
+
+
+def test_run_adaptation(pool, images, fixtures):  # tests/blend.rs:168-195
+    bg, _ = images
+    c = CommandBuffer()
+    background = c.input(bg.descriptor())
+    output, fmt = c.output(c.chromatic_adaptation(background, ChromaticAdaptationMethod.VonKries, Z.Whitepoint.D50))
+    assert fmt.color.whitepoint == Z.Whitepoint.D50
+    img, _ = run_once_with_output(c, pool, [(background, bg.key())], output)
+    assert O.blockhash256(rgba(img)) in hashes()["adapted"]
+    exp = O.chromatic_adaptation(oracle_image(bg.descriptor(), fixtures["background"]), "vonkries", "D50")
+    assert np.array_equal(img.as_bytes(), exp.data.reshape(-1))
+
+
+def test_run_conversion(pool, images, fixtures):  # tests/blend.rs:197-224
+    bg, _ = images
+    bt = pool.allocate_like(bg.key())
+    bt.set_color(Color.BT709_RGB)
+    c = CommandBuffer()
+    inp = c.input(bt.descriptor())
+    output, _ = c.output(c.color_convert(inp, bg.descriptor().color, bg.descriptor().texel))
+    img, _ = run_once_with_output(c, pool, [(inp, bt.key())], output)
+    assert O.blockhash256(rgba(img)) in hashes()["convert_bt709"]
+    exp = O.color_convert(oracle_image(bt.descriptor(), fixtures["background"]), O.SRGB, O.RGBA8)
+    d = np.abs(img.as_bytes().astype(int) - exp.data.reshape(-1).astype(int))
+    assert d.max() <= 1 and np.mean(d == 0) > 0.99
+
+
+@pytest.mark.parametrize("space", ["oklab", "srlab2"])
+@pytest.mark.parametrize("fuse", [_ffi.FUSE_EXACT, _ffi.FUSE_NONE])
+def test_run_oklab_srlab2(pool, space, fuse):  # tests/blend.rs:449-580
+    c = CommandBuffer()
+    color_descriptor = Descriptor.with_srgb_image("rgba8", 400, 400)
+    distribution_layout = color_descriptor.with_color(Color.Scalars(Transfer.Linear))
+    model = Color.Oklab if space == "oklab" else Color.SrLab2(Z.Whitepoint.D65)
+    lab_texel = Descriptor(distribution_layout.layout, model, Texel(Z.Block.Pixel, SampleBits.UInt8x4, SampleParts.LchA))
+    g = R.LCH_GRID
+    grid = c.bilinear(distribution_layout, Bilinear(g[0], g[1], g[2], g[3], g[4], g[5]))
+    lch = c.transmute(grid, lab_texel)
+    converted = c.color_convert(lch, color_descriptor.color, color_descriptor.texel)
+    output, _ = c.output(converted)
+    img, n = run_once_with_output(c, pool, [], output, fuse)
+    assert n == 3
+    assert O.blockhash256(rgba(img)) in hashes()[space]
+
+
+def test_run_solid(pool):  # tests/blend.rs:623-644
+    c = CommandBuffer()
+    output, _ = c.output(c.solid_rgba(Descriptor.with_srgb_image("rgba8", 400, 400), [0.5, 0.5, 1.0, 1.0]))
+    img, _ = run_once_with_output(c, pool, [], output)
+    assert O.blockhash256(rgba(img)) in hashes()["solid"]
+    assert np.array_equal(img.as_bytes(), O.solid(O.srgb_rgba8(400, 400), [0.5, 0.5, 1.0, 1.0]).data.reshape(-1))
+
+
+@pytest.mark.parametrize("method", ["Scharr3", "Scharr3To4Bit", "Scharr3To8Bit", "Prewitt", "Sobel"])
+def test_run_derivative(pool, images, method):  # tests/blend.rs:582-621
+    bg, _ = images
+    c = CommandBuffer()
+    background = c.input(bg.descriptor())
+    output, _ = c.output(c.derivative(background, Derivative(DerivativeMethod[method])))
+    img, _ = run_once_with_output(c, pool, [(background, bg.key())], output)
+    assert O.blockhash256(rgba(img)) in hashes()["derived_" + method]
+
+
+def test_run_transmute_bytes_equal(pool, images, fixtures):  # tests/blend.rs:340-375
+    bg, _ = images
+    c = CommandBuffer()
+    inp = c.input(bg.descriptor())
+    output, fmt = c.output(c.transmute(inp, Descriptor.with_srgb_image("luma_a16", 512, 512)))
+    img, _ = run_once_with_output(c, pool, [(inp, bg.key())], output)
+    assert fmt.texel.bits == SampleBits.UInt16x2
+    assert np.array_equal(img.as_bytes(), fixtures["background"].reshape(-1))
+
+
+def test_run_palette(pool, images, fixtures):  # tests/blend.rs:377-424 (goldens differ per device; checked against the oracle)
+    bg, _ = images
+    c = CommandBuffer()
+    inp = c.input(bg.descriptor())
+    ramp = c.bilinear(Descriptor.with_srgb_image("rgba8", 400, 400),
+                      Bilinear([0, 0, 0, 1], [0.7, 0, 0, 1], [0, 0, 0, 1], [0, 0.7, 0, 1], [0, 0, 0, 1], [0.3, 0.3, 0, 1]))
+    sampled = c.palette(inp, Palette(Z.ColorChannel.R, Z.ColorChannel.G), ramp)
+    output, _ = c.output(sampled)
+    img, _ = run_once_with_output(c, pool, [(inp, bg.key())], output)
+    od = O.srgb_rgba8(400, 400)
+    oramp = O.bilinear(od, ([0, 0, 0, 1], [0.7, 0, 0, 1], [0, 0, 0, 1], [0, 0.7, 0, 1], [0, 0, 0, 1], [0.3, 0.3, 0, 1]))
+    exp = O.palette(oracle_image(bg.descriptor(), fixtures["background"]), oramp, [1, 0, 0, 0], [0, 1, 0, 0])
+    got = rgba(img)
+    assert np.mean(np.all(got == exp.data.reshape(400, 400, 4), axis=-1)) > 0.99  # pow in the ramp's sRGB pack: a few coordinates flip
+
+
+def test_bilinear_knobs(pool):  # tests/knobs.rs: one Executable, five launches with a patched parameter block
+    c = CommandBuffer()
+    like = Descriptor.with_srgb_image("rgba8", 512, 512)
+    result = c.with_knob().bilinear(like, Bilinear([0, 0, 1, 1], [1, 1, 1, 1], [0, 0, 1, 1], [1, 1, 1, 1]))
+    output, _ = c.output(result)
+    executable = Linker.from_included().compile(c).lower_to(Capabilities.from_device(next(pool.iter_devices())))
+    knob = executable.query_knob(RegisterKnob(0, result))
+    assert knob is not None
+    for idx, (um, uM, vm, vM) in enumerate(R.KNOBS):
+        data = Bilinear(um, uM, vm, vM).into_std430()
+        img, _ = run_executable_with_output(executable, pool, [], output, [(knob, data)])
+        assert O.blockhash256(rgba(img)) in hashes()["bilinear-knob-%d" % idx]
+
+
+def test_errors_at_launch_and_step(pool, images):
+    bg, fg = images
+    c = CommandBuffer()
+    background = c.input(bg.descriptor())
+    output, _ = c.output(c.chromatic_adaptation(background, ChromaticAdaptationMethod.VonKries, Z.Whitepoint.D50))
+    executable = Linker.from_included().compile(c).lower_to(Capabilities.from_device(next(pool.iter_devices())))
+    env = executable.from_pool(pool)
+    with pytest.raises(StartError):  # MismatchedDescriptor (run.rs:376-380)
+        env.bind(background, fg.key())
+    with pytest.raises(StartError):  # launching with an unbound input: StartError::MissingKey
+        executable.launch(executable.from_pool(pool))
+    env.bind(background, bg.key())
+    ex = executable.launch(env)
+    while ex.is_running():
+        ex.step()
+    with pytest.raises(StepError):  # StepError::ProgramEnd (run.rs:395-408)
+        ex.step()
+    ex.retire_gracefully(pool).finish()
+
+
+# ---------------------------------------------------------------- planner: fusion keeps the bytes
+def chain_c1(c, inp):
+    lch = c.color_convert(inp, Color.Oklab, Texel(Z.Block.Pixel, SampleBits.UInt8x4, SampleParts.LchA))
+    return c.color_convert(lch, Color.SRGB, Texel.new_u8(SampleParts.RgbA))
+
+
+def test_fusion_c1_chain(pool, images, fixtures):
+    """BASELINE config 1: sRGB8 -> Oklab (declared LchA u8 register) -> sRGB8.  Fused: one kernel; the
+    LCh register is quantised in registers; bytes equal the unfused two-kernel run."""
+    bg, _ = images
+    res = {}
+    for fuse in (_ffi.FUSE_EXACT, _ffi.FUSE_NONE, _ffi.FUSE_WIDE):
+        c = CommandBuffer()
+        inp = c.input(bg.descriptor())
+        output, _ = c.output(chain_c1(c, inp))
+        res[fuse] = run_once_with_output(c, pool, [(inp, bg.key())], output, fuse)
+    assert res[_ffi.FUSE_EXACT][1] == 1 and res[_ffi.FUSE_NONE][1] == 2 and res[_ffi.FUSE_WIDE][1] == 1
+    assert np.array_equal(res[_ffi.FUSE_EXACT][0].as_bytes(), res[_ffi.FUSE_NONE][0].as_bytes())
+    # WIDE skips the 8-bit LCh quantisation: closer to the source image than the exact chain
+    src = fixtures["background"].reshape(-1).astype(int)
+    e_exact = np.abs(res[_ffi.FUSE_EXACT][0].as_bytes().astype(int) - src).mean()
+    e_wide = np.abs(res[_ffi.FUSE_WIDE][0].as_bytes().astype(int) - src).mean()
+    assert e_wide < 0.1 < e_exact
+
+
+def test_fusion_into_composition(pool, images, fixtures):
+    """convert(above) -> blend over convert(below) -> convert(result): the producer of `above` becomes
+    source-side steps, the consumer becomes destination-side steps; same bytes as one kernel per op."""
+    bg, fg = images
+    res = {}
+    for fuse in (_ffi.FUSE_EXACT, _ffi.FUSE_NONE):
+        c = CommandBuffer()
+        background, foreground = c.input(bg.descriptor()), c.input(fg.descriptor())
+        a = c.color_convert(foreground, Color.Rgb(Z.Primaries.Bt2020, Transfer.Srgb), Texel.new_u8(SampleParts.RgbA))
+        b = c.color_convert(background, Color.Rgb(Z.Primaries.Bt2020, Transfer.Srgb), Texel.new_u8(SampleParts.RgbA))
+        blended = c.blend(b, Rectangle(100, 60, 257, 211), a, Blend.Alpha)
+        back = c.color_convert(blended, Color.SRGB, Texel.new_u8(SampleParts.RgbA))
+        output, _ = c.output(back)
+        res[fuse] = run_once_with_output(c, pool, [(background, bg.key()), (foreground, fg.key())], output, fuse)
+    assert res[_ffi.FUSE_NONE][1] == 4
+    assert res[_ffi.FUSE_EXACT][1] == 2  # `below` must exist in memory: its producer stays a kernel
+    assert np.array_equal(res[_ffi.FUSE_EXACT][0].as_bytes(), res[_ffi.FUSE_NONE][0].as_bytes())
+
+
+def test_resize_modes_program(pool, images, fixtures):
+    bg, _ = images
+    for mode, omode in ((ResizeMode.Reference, "reference"), (ResizeMode.Nearest, "nearest"), (ResizeMode.Bilinear, "bilinear")):
+        c = CommandBuffer()
+        inp = c.input(bg.descriptor())
+        output, fmt = c.output(c.resize(inp, (300, 200), mode))
+        assert fmt.size() == (300, 200)
+        img, n = run_once_with_output(c, pool, [(inp, bg.key())], output)
+        assert n == 1
+        exp = O.resize(oracle_image(bg.descriptor(), fixtures["background"]), (300, 200), omode)
+        assert np.array_equal(img.as_bytes(), exp.data.reshape(-1))
+
+
+def test_crop_quirk(pool, images, fixtures):  # command.rs:971-978: output keeps the source size
+    bg, _ = images
+    c = CommandBuffer()
+    inp = c.input(bg.descriptor())
+    output, fmt = c.output(c.crop(inp, Rectangle(100, 50, 356, 306)))
+    assert fmt.size() == (512, 512)
+    img, _ = run_once_with_output(c, pool, [(inp, bg.key())], output)
+    exp = O.crop(oracle_image(bg.descriptor(), fixtures["background"]), (100, 50, 356, 306))
+    assert np.array_equal(img.as_bytes(), exp.data.reshape(-1))

@@ -1,0 +1,171 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every symbol the headers declare,
+and the C++ host mirror of the op builder (CommandBuffer / Linker) behaves like the reference:
+same checks, same error kinds (lib/zosimos/src/command.rs), same parameter matrices as the oracle."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import zosimos_b200 as Z
+from oracle import oracle as O
+from zosimos_b200 import _ffi, command
+from zosimos_b200.buffer import Color, Descriptor, SampleBits, SampleParts, Texel, Transfer
+from zosimos_b200.command import (Affine, AffineSample, Bilinear, Blend, ChromaticAdaptationMethod, CommandBuffer, CommandError,
+                                  CommandErrorKind, Derivative, DerivativeMethod, Linker, Rectangle, ResizeMode)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(zosh?_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _ffi.lib()
+    names = declared("zosimos_cuda.h") + declared("zosimos_host.h")
+    assert len(names) > 60
+    for n in names:
+        assert hasattr(lib, n), n
+    # and the ctypes table covers the device header completely
+    assert set(declared("zosimos_cuda.h")) == set(_ffi.SIGNATURES)
+    assert lib.zos_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    """Without a device the product refuses to run (this container has no GPU)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(_ffi.ZosError) as e:
+        Z.Context(0)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_layout_helpers():
+    lib = _ffi.lib()
+    assert lib.zos_aligned_row_stride(157, 4) == 768 and lib.zos_aligned_row_stride(3840, 4) == 15360  # buffer.rs:121-134
+    assert [lib.zos_bits_bytes(int(b)) for b in SampleBits] == [b.bytes() for b in SampleBits]
+    d = Descriptor.with_srgb_image("rgba8", 10, 10).to_ffi()
+    f = _ffi.ZosTexFmt()
+    assert lib.zos_desc_texfmt(d, f) == 0 and f.storage == 1  # native Rgba8UnormSrgb (program.rs:794-805)
+    d.transfer = int(Transfer.Bt709)
+    assert lib.zos_desc_texfmt(d, f) == 0 and f.storage == 0  # staged
+    d.bits = int(SampleBits.UInt8x3); d.texel_stride = 3
+    assert lib.zos_desc_texfmt(d, f) == _ffi.ERR_UNSUPPORTED  # 3-byte texels: stage.rs:63-72
+    d = Descriptor.with_srgb_image("rgba8", 10, 10).with_color(Color.Oklab).to_ffi()
+    d.parts = int(SampleParts.LchA)
+    assert lib.zos_desc_texfmt(d, f) == 0 and f.transfer == 0x100 and f.parts == int(SampleParts.LchA)  # program.rs:882-890
+
+
+def test_color_matrices_match_oracle_bit_for_bit():
+    for prim, name in ((Z.Primaries.Bt709, "bt709"), (Z.Primaries.Bt2020, "bt2020"), (Z.Primaries.Bt601_625, "bt601_625")):
+        for wp in (Z.Whitepoint.D65, Z.Whitepoint.D50, Z.Whitepoint.E):
+            got = command.to_xyz_matrix(prim, wp)
+            assert np.array_equal(got, O.to_xyz(name, wp.name).astype(np.float32))
+    for m, name in ((ChromaticAdaptationMethod.VonKries, "vonkries"), (ChromaticAdaptationMethod.BradfordVonKries, "bradford"),
+                    (ChromaticAdaptationMethod.Xyz, "xyz")):
+        got = command.adaptation_matrix(m, Z.Whitepoint.D65, Z.Whitepoint.D50)
+        assert np.array_equal(got, O.adaptation_matrix(name, "D65", "D50").astype(np.float32))
+    with pytest.raises(CommandError) as e:
+        command.adaptation_matrix(ChromaticAdaptationMethod.BradfordNonLinear, Z.Whitepoint.D65, Z.Whitepoint.D50)
+    assert e.value.kind == CommandErrorKind.Unimplemented  # command.rs:3327-3331
+
+
+def test_rectangles():  # command.rs:3649-3658 + the normalize quirk (3536-3543)
+    small, large = Rectangle.with_width_height(2, 2), Rectangle.with_width_height(4, 4)
+    assert large == large.join(small) and small == large.meet(small)
+    assert large.contains(small) and not small.contains(large)
+    assert Rectangle(0, 0, 157, 151).normalize() == Rectangle(0, 0, 157, 157)
+
+
+def test_affine_left_multiplication():
+    from tests import refpipes as R
+    a = Affine.new(AffineSample.Nearest).shift(-(157 // 2), -(151 // 2)).rotate(np.float32(np.pi) / np.float32(4)).shift(256, 256)
+    assert np.allclose(np.array(a.transformation).reshape(3, 3), R.affine_matrix_blend_rs(157, 151, 512, 512), rtol=0, atol=1e-5)
+
+
+def srgb(w, h):
+    return Descriptor.with_srgb_image("rgba8", w, h)
+
+
+def test_simple_program_compiles():  # command.rs:3660-3698
+    cb = CommandBuffer()
+    bg, fg = cb.input(srgb(512, 512)), cb.input(srgb(157, 151))
+    r = cb.inscribe(bg, Rectangle(0, 0, 157, 151), fg)
+    _, fmt = cb.output(r)
+    assert fmt.layout == srgb(512, 512).layout
+    prog = Linker.from_included().compile(cb)
+    kinds = [o.kind for o in prog.ops()]
+    assert kinds == [_ffi.OP_INPUT, _ffi.OP_INPUT, _ffi.OP_COMPOSE, _ffi.OP_OUTPUT]
+    c = prog.ops()[2].compose
+    assert list(c.tgt) == [0, 0, 157, 157] and list(c.sel) == [0, 0, 157, 151]  # the quirk reaches the kernel parameters
+
+
+def test_builder_errors_match_reference():
+    cb = CommandBuffer()
+    bg, fg = cb.input(srgb(512, 512)), cb.input(srgb(157, 151))
+    with pytest.raises(CommandError) as e:  # rect != layout of above: command.rs:1196-1198 -> OTHER
+        cb.inscribe(bg, Rectangle(0, 0, 100, 100), fg)
+    assert e.value.kind == CommandErrorKind.Other
+    with pytest.raises(CommandError) as e:  # not contained: command.rs:1202-1206
+        cb.inscribe(fg, Rectangle(0, 0, 512, 512), bg)
+    assert e.value.kind == CommandErrorKind.Other
+    other = cb.input(Descriptor.with_srgb_image("rgba16", 157, 151))
+    with pytest.raises(CommandError) as e:  # chroma mismatch: command.rs:1186-1190
+        cb.inscribe(bg, Rectangle(0, 0, 157, 151), other)
+    assert e.value.kind == CommandErrorKind.ConflictingTypes and e.value.is_type_err()
+    with pytest.raises(CommandError) as e:  # affine chroma mismatch -> TYPE_ERR (command.rs:1646-1648)
+        cb.affine(bg, Affine.new(AffineSample.Nearest), other)
+    assert e.value.kind == CommandErrorKind.GenericTypeError
+    with pytest.raises(CommandError) as e:  # singular matrix (command.rs:1650-1657)
+        cb.affine(bg, Affine(AffineSample.Nearest, [1, 0, 0, 2, 0, 0, 0, 0, 1]), fg)
+    assert e.value.kind == CommandErrorKind.Other
+    with pytest.raises(CommandError) as e:  # inconsistent input (command.rs:744-748)
+        cb.input(Descriptor(Z.ByteLayout(4, 4, 16, 3), Color.SRGB, Texel.new_u8(SampleParts.RgbA)))
+    assert e.value.kind == CommandErrorKind.BadDescriptor
+    with pytest.raises(CommandError) as e:  # no conversion between different whitepoints (command.rs:1021, 1077-1084)
+        cb.color_convert(bg, Color.Rgb(Z.Primaries.Bt709, Transfer.Srgb, Z.Whitepoint.D50), Texel.new_u8(SampleParts.RgbA))
+    assert e.value.kind == CommandErrorKind.BadDescriptor
+    with pytest.raises(CommandError) as e:  # transmute to another texel size (command.rs:1329-1336)
+        cb.transmute(bg, Descriptor.with_srgb_image("rgba16", 512, 512))
+    assert e.value.kind == CommandErrorKind.ConflictingTypes
+    with pytest.raises(CommandError) as e:
+        cb.transmute(bg, Descriptor.with_srgb_image("luma_a16", 256, 512))
+    assert e.value.kind == CommandErrorKind.BadDescriptor
+    with pytest.raises(CommandError) as e:  # Roberts & co: CompileError::NotYetImplemented (command.rs:3402-3408)
+        cb.derivative(bg, Derivative(DerivativeMethod.Roberts))
+    assert e.value.kind == CommandErrorKind.Unimplemented
+    with pytest.raises(CommandError):
+        cb.output(command.Register(99))
+    # blend is implemented here (the reference returns UNIMPLEMENTED, command.rs:1510-1519)
+    r = cb.blend(bg, Rectangle(10, 10, 167, 161), fg, Blend.Alpha)
+    assert cb.describe_reg(r) == cb.describe_reg(bg)
+
+
+def test_liveness_drops_dead_operations():  # command.rs:2216-2291
+    cb = CommandBuffer()
+    a = cb.input(srgb(64, 64))
+    dead = cb.chromatic_adaptation(a, ChromaticAdaptationMethod.VonKries, Z.Whitepoint.D50)
+    live = cb.resize(a, (32, 32), ResizeMode.Bilinear)
+    cb.output(live)
+    ops = Linker.from_included().compile(cb).ops()
+    assert [o.reg for o in ops] == [a.index, live.index, live.index + 1] and dead.index not in [o.reg for o in ops]
+
+
+def test_color_convert_parameters():
+    cb = CommandBuffer()
+    a = cb.input(srgb(8, 8))
+    lch = cb.color_convert(a, Color.Oklab, Texel(Z.Block.Pixel, SampleBits.UInt8x4, SampleParts.LchA))
+    back = cb.color_convert(lch, Color.SRGB, Texel.new_u8(SampleParts.RgbA))
+    cb.output(back)
+    ops = Linker.from_included().compile(cb).ops()
+    enc, dec = ops[1], ops[2]
+    assert enc.steps[0].kind == _ffi.STEP_OKLAB_ENC and dec.steps[0].kind == _ffi.STEP_OKLAB_DEC
+    T = O.to_xyz("bt709", "D65")
+    assert np.array_equal(np.array(list(enc.steps[0].m), np.float32), T.astype(np.float32).reshape(9))
+    assert np.array_equal(np.array(list(dec.steps[0].m), np.float32), O.inv3(T).astype(np.float32).reshape(9))
+    d = cb.describe_reg(lch)
+    assert d.texel.parts == SampleParts.LchA and d.color.model == Z.ColorModel.Oklab and d.size() == (8, 8)

@@ -62,7 +62,7 @@ class ZosComposeParams(C.Structure):
 class ZosOp(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("src", C.c_int32 * 2), ("dst", C.c_int32), ("desc", ZosDesc),
                 ("nsteps", C.c_uint32), ("steps", ZosStep * ZOS_MAX_STEPS), ("compose", ZosComposeParams),
-                ("gen", C.c_float * 24), ("knob", C.c_uint32)]
+                ("gen", C.c_float * 24), ("knob", C.c_uint32), ("reg", C.c_int32)]
 
 
 class ZosError(RuntimeError):
@@ -98,9 +98,12 @@ SIGNATURES = {
     "zos_buf_download": (C.c_int32, [_P, _P, C.c_uint64, C.c_uint64, _P, C.c_uint64, C.c_uint64, C.c_uint64]),
     "zos_buf_copy": (C.c_int32, [_P, _P, C.c_uint64, _P, C.c_uint64, C.c_uint64]),
     "zos_buf_fill": (C.c_int32, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint8]),
+    "zos_image_upload": (C.c_int32, [_P, C.POINTER(ZosImage), C.c_uint32, _P]),
+    "zos_image_download": (C.c_int32, [_P, C.POINTER(ZosImage), C.c_uint32, _P]),
     "zos_pixel_chain": (C.c_int32, [_P, C.POINTER(ZosImage), C.POINTER(ZosImage), C.POINTER(ZosStep), C.c_uint32, C.c_uint32]),
     "zos_compose": (C.c_int32, [_P, C.POINTER(ZosImage), C.POINTER(ZosImage), C.POINTER(ZosImage), C.POINTER(ZosComposeParams), C.c_uint32]),
     "zos_generate_bilinear": (C.c_int32, [_P, C.POINTER(ZosImage), C.POINTER(C.c_float), C.c_uint32]),
+    "zos_generate_solid": (C.c_int32, [_P, C.POINTER(ZosImage), C.POINTER(C.c_float), C.c_uint32]),
     "zos_box3": (C.c_int32, [_P, C.POINTER(ZosImage), C.POINTER(ZosImage), C.POINTER(C.c_float), C.c_uint32]),
     "zos_palette": (C.c_int32, [_P, C.POINTER(ZosImage), C.POINTER(ZosImage), C.POINTER(ZosImage), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_uint32]),
     "zos_program_create": (C.c_int32, [_P, C.POINTER(ZosOp), C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(_P)]),

@@ -1,0 +1,404 @@
+"""command -- the typed op builder, mirroring /root/reference/lib/zosimos/src/command.rs.
+
+`CommandBuffer` has the reference's method names, argument meaning and error behaviour
+(`CommandError` with the reference's kinds).  The checks and the parameter preparation run in the
+C++ host layer (zosimos_b200/csrc/host.cpp, C view include/zosimos_host.h); this module is the
+ctypes veneer the parity tests drive, so they read like lib/zosimos/tests/blend.rs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _ffi
+from .buffer import (Block, ByteLayout, Color, ColorChannel, ColorModel, Descriptor, Primaries, SampleBits, SampleParts, Texel,
+                     Transfer, Whitepoint, YuvMatrix)
+
+
+class CommandErrorKind(enum.IntEnum):  # command.rs:3612-3647
+    BadDescriptor = 1
+    ConflictingTypes = 2
+    GenericTypeError = 3
+    Other = 4
+    Unimplemented = 5
+    ConcreteDescriptorRequired = 6
+
+
+class CommandError(Exception):
+    def __init__(self, kind: int, message: str):
+        super().__init__("%s: %s" % (CommandErrorKind(kind).name, message))
+        self.kind = CommandErrorKind(kind)
+
+    def is_type_err(self) -> bool:  # command.rs:3637-3646
+        return self.kind in (CommandErrorKind.GenericTypeError, CommandErrorKind.ConflictingTypes, CommandErrorKind.BadDescriptor)
+
+
+class ZoshRect(C.Structure):
+    _fields_ = [("x", C.c_uint32), ("y", C.c_uint32), ("max_x", C.c_uint32), ("max_y", C.c_uint32)]
+
+
+_P = C.c_void_p
+_F9 = C.c_float * 9
+_HOST_SIGNATURES = {
+    "zosh_last_error": (C.c_char_p, []),
+    "zosh_to_xyz_matrix": (C.c_int32, [C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]),
+    "zosh_adaptation_matrix": (C.c_int32, [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]),
+    "zosh_whitepoint_xyz": (C.c_int32, [C.c_uint32, C.POINTER(C.c_float)]),
+    "zosh_affine_identity": (None, [C.POINTER(C.c_float)]),
+    "zosh_affine_scale": (None, [C.POINTER(C.c_float), C.c_float, C.c_float]),
+    "zosh_affine_rotate": (None, [C.POINTER(C.c_float), C.c_float]),
+    "zosh_affine_shift": (None, [C.POINTER(C.c_float), C.c_float, C.c_float]),
+    "zosh_rect_normalize": (ZoshRect, [ZoshRect]),
+    "zosh_cb_new": (_P, []),
+    "zosh_cb_free": (None, [_P]),
+    "zosh_cb_input": (C.c_int32, [_P, C.POINTER(_ffi.ZosDesc), C.POINTER(C.c_int32)]),
+    "zosh_cb_output": (C.c_int32, [_P, C.c_int32, C.POINTER(C.c_int32)]),
+    "zosh_cb_describe": (C.c_int32, [_P, C.c_int32, C.POINTER(_ffi.ZosDesc)]),
+    "zosh_cb_color_convert": (C.c_int32, [_P, C.c_int32, C.POINTER(_ffi.ZosDesc), C.POINTER(C.c_int32)]),
+    "zosh_cb_chromatic_adaptation": (C.c_int32, [_P, C.c_int32, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32)]),
+    "zosh_cb_inscribe": (C.c_int32, [_P, C.c_int32, ZoshRect, C.c_int32, C.POINTER(C.c_int32)]),
+    "zosh_cb_crop": (C.c_int32, [_P, C.c_int32, ZoshRect, C.POINTER(C.c_int32)]),
+    "zosh_cb_affine": (C.c_int32, [_P, C.c_int32, C.POINTER(C.c_float), C.c_uint32, C.c_int32, C.POINTER(C.c_int32)]),
+    "zosh_cb_resize": (C.c_int32, [_P, C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32)]),
+    "zosh_cb_blend": (C.c_int32, [_P, C.c_int32, ZoshRect, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
+    "zosh_cb_transmute": (C.c_int32, [_P, C.c_int32, C.POINTER(_ffi.ZosDesc), C.POINTER(C.c_int32)]),
+    "zosh_cb_bilinear": (C.c_int32, [_P, C.POINTER(_ffi.ZosDesc), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "zosh_cb_solid_rgba": (C.c_int32, [_P, C.POINTER(_ffi.ZosDesc), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "zosh_cb_derivative": (C.c_int32, [_P, C.c_int32, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32)]),
+    "zosh_cb_palette": (C.c_int32, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "zosh_cb_with_knob": (C.c_int32, [_P]),
+    "zosh_compile": (C.c_int32, [_P, C.POINTER(_P)]),
+    "zosh_program_free": (None, [_P]),
+    "zosh_program_num_ops": (C.c_uint32, [_P]),
+    "zosh_program_ops": (C.POINTER(_ffi.ZosOp), [_P]),
+    "zosh_program_lower": (C.c_int32, [_P, _P, C.c_uint32, C.c_uint32, C.POINTER(_P)]),
+}
+_host = None
+
+
+def host_lib():
+    global _host
+    if _host is None:
+        l = _ffi.lib()
+        for name, (res, args) in _HOST_SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _host = l
+    return _host
+
+
+def _check(st: int):
+    if st != 0:
+        raise CommandError(st, (host_lib().zosh_last_error() or b"").decode())
+
+
+@dataclass(frozen=True)
+class Register:  # command.rs:31-32
+    index: int
+
+
+@dataclass(frozen=True)
+class Rectangle:  # command.rs:311-317
+    x: int
+    y: int
+    max_x: int
+    max_y: int
+
+    @staticmethod
+    def with_width_height(width: int, height: int) -> "Rectangle":
+        return Rectangle(0, 0, width, height)
+
+    @staticmethod
+    def with_layout(layout: ByteLayout) -> "Rectangle":
+        return Rectangle(0, 0, layout.width, layout.height)
+
+    def width(self) -> int:
+        return max(self.max_x - self.x, 0)
+
+    def height(self) -> int:
+        return max(self.max_y - self.y, 0)
+
+    def contains(self, o: "Rectangle") -> bool:
+        return self.x <= o.x and self.y <= o.y and self.width() - (o.x - self.x) >= o.width() and self.height() - (o.y - self.y) >= o.height()
+
+    def normalize(self) -> "Rectangle":
+        """With the reference's `max_y = y + width()` (command.rs:3536-3543)."""
+        r = host_lib().zosh_rect_normalize(self._ffi())
+        return Rectangle(r.x, r.y, r.max_x, r.max_y)
+
+    def meet(self, o: "Rectangle") -> "Rectangle":
+        return Rectangle(max(self.x, o.x), max(self.y, o.y), min(self.max_x, o.max_x), min(self.max_y, o.max_y))
+
+    def join(self, o: "Rectangle") -> "Rectangle":
+        return Rectangle(min(self.x, o.x), min(self.y, o.y), max(self.max_x, o.max_x), max(self.max_y, o.max_y))
+
+    def _ffi(self) -> ZoshRect:
+        return ZoshRect(self.x, self.y, self.max_x, self.max_y)
+
+
+class AffineSample(enum.IntEnum):  # command.rs:339-352
+    Nearest = 0
+    BiLinear = 1
+
+
+class Affine:
+    """command.rs:326-337, 3421-3485: row-major homogeneous matrix mapping `above` pixel coordinates to
+    `below` pixel coordinates; scale / rotate / shift multiply from the LEFT, in f32."""
+
+    def __init__(self, sampling: AffineSample = AffineSample.Nearest, transformation: Optional[Sequence[float]] = None):
+        self.sampling = AffineSample(sampling)
+        self._m = _F9()
+        if transformation is None:
+            host_lib().zosh_affine_identity(self._m)
+        else:
+            for i, v in enumerate(np.asarray(transformation, dtype=np.float32).reshape(9)):
+                self._m[i] = float(v)
+
+    @staticmethod
+    def new(sampling: AffineSample) -> "Affine":
+        return Affine(sampling)
+
+    @property
+    def transformation(self) -> List[float]:
+        return list(self._m)
+
+    def _copy(self) -> "Affine":
+        return Affine(self.sampling, list(self._m))
+
+    def scale(self, x: float, y: float) -> "Affine":
+        a = self._copy(); host_lib().zosh_affine_scale(a._m, x, y); return a
+
+    def rotate(self, rad: float) -> "Affine":
+        a = self._copy(); host_lib().zosh_affine_rotate(a._m, rad); return a
+
+    def shift(self, x: float, y: float) -> "Affine":
+        a = self._copy(); host_lib().zosh_affine_shift(a._m, x, y); return a
+
+
+class ChromaticAdaptationMethod(enum.IntEnum):
+    BradfordVonKries = 0
+    VonKries = 1
+    Xyz = 2
+    BradfordNonLinear = 3
+
+
+class Blend(enum.IntEnum):
+    """command.rs:319-323 has only `Alpha`; the other Porter-Duff operators are this backend's."""
+    Clear = 0
+    Src = 1
+    Dst = 2
+    Alpha = 3  # source-over
+    DstOver = 4
+    SrcIn = 5
+    DstIn = 6
+    SrcOut = 7
+    DstOut = 8
+    SrcAtop = 9
+    DstAtop = 10
+    Xor = 11
+
+
+class ResizeMode(enum.IntEnum):
+    Reference = 0  # 8-bit coordinate grid + palette, exactly what CommandBuffer::resize lowers to
+    Nearest = 1
+    Bilinear = 2
+
+
+class DerivativeMethod(enum.IntEnum):
+    Prewitt = 0
+    Sobel = 1
+    Scharr3 = 2
+    Scharr3To4Bit = 3
+    Scharr3To8Bit = 4
+    Roberts = 5
+
+
+class Direction(enum.IntEnum):
+    Width = 0
+    Height = 1
+
+
+@dataclass(frozen=True)
+class Derivative:
+    method: DerivativeMethod
+    direction: Direction = Direction.Width
+
+
+@dataclass(frozen=True)
+class Bilinear:  # shaders/bilinear.rs:9-32
+    u_min: Sequence[float]
+    u_max: Sequence[float]
+    v_min: Sequence[float]
+    v_max: Sequence[float]
+    uv_min: Sequence[float] = (0.0, 0.0, 0.0, 0.0)
+    uv_max: Sequence[float] = (0.0, 0.0, 0.0, 0.0)
+
+    def flat(self) -> List[float]:
+        return [float(x) for v in (self.u_min, self.u_max, self.v_min, self.v_max, self.uv_min, self.uv_max) for x in v]
+
+    def into_std430(self) -> bytes:
+        return np.asarray(self.flat(), dtype=np.float32).tobytes()
+
+
+@dataclass(frozen=True)
+class Palette:  # command.rs:566-580
+    width: Optional[ColorChannel] = None
+    height: Optional[ColorChannel] = None
+    width_base: int = 0
+    height_base: int = 0
+
+
+@dataclass(frozen=True)
+class RegisterKnob:
+    link_idx: int
+    register: Register
+
+
+def descriptor_from_ffi(d: _ffi.ZosDesc) -> Descriptor:
+    texel = Texel(Block(d.block), SampleBits(d.bits), SampleParts(d.parts))
+    color = Color(ColorModel(d.color), Transfer(d.transfer) if d.transfer < 0x100 else Transfer.Linear, Primaries(d.primaries), Whitepoint(d.whitepoint))
+    ts = int(d.texel_stride)
+    return Descriptor(ByteLayout(int(d.width), int(d.height), int(d.width) * ts, ts), color, texel, YuvMatrix(d.yuv_matrix),
+                      bool(d.yuv_full_range), int(d.chroma_filter))
+
+
+class CommandBuffer:
+    """command.rs:634-705.  Every method pushes one operation and returns its `Register`."""
+
+    def __init__(self):
+        self._h = host_lib().zosh_cb_new()
+        self._knobs = {}  # register index -> knob id
+
+    def __del__(self):
+        try:
+            if self._h:
+                host_lib().zosh_cb_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # -- plumbing
+    def _reg(self, st: int, out: C.c_int32) -> Register:
+        _check(st)
+        r = Register(int(out.value))
+        if self._pending_knob:
+            self._knobs[r.index] = self._pending_knob
+            self._pending_knob = 0
+        return r
+
+    _pending_knob = 0
+
+    def describe_reg(self, reg: Register) -> Descriptor:
+        d = _ffi.ZosDesc()
+        _check(host_lib().zosh_cb_describe(self._h, reg.index, C.byref(d)))
+        return descriptor_from_ffi(d)
+
+    def with_knob(self) -> "CommandBuffer":
+        """command.rs:1865-1874: the next operation's parameter block can be overridden at run time."""
+        self._pending_knob = int(host_lib().zosh_cb_with_knob(self._h))
+        return self
+
+    # -- operations
+    def input(self, desc: Descriptor) -> Register:
+        out = C.c_int32(); d = desc.to_ffi()
+        return self._reg(host_lib().zosh_cb_input(self._h, C.byref(d), C.byref(out)), out)
+
+    def output(self, src: Register) -> Tuple[Register, Descriptor]:
+        out = C.c_int32()
+        r = self._reg(host_lib().zosh_cb_output(self._h, src.index, C.byref(out)), out)
+        return r, self.describe_reg(src)
+
+    def color_convert(self, src: Register, color: Color, texel: Texel) -> Register:
+        out = C.c_int32()
+        b = texel.bits.bytes()
+        d = Descriptor(ByteLayout(1, 1, b, b), color, texel).to_ffi()
+        return self._reg(host_lib().zosh_cb_color_convert(self._h, src.index, C.byref(d), C.byref(out)), out)
+
+    def chromatic_adaptation(self, src: Register, method: ChromaticAdaptationMethod, target: Whitepoint) -> Register:
+        out = C.c_int32()
+        return self._reg(host_lib().zosh_cb_chromatic_adaptation(self._h, src.index, int(method), int(target), C.byref(out)), out)
+
+    def inscribe(self, below: Register, rect: Rectangle, above: Register) -> Register:
+        out = C.c_int32()
+        return self._reg(host_lib().zosh_cb_inscribe(self._h, below.index, rect._ffi(), above.index, C.byref(out)), out)
+
+    def blend(self, below: Register, rect: Rectangle, above: Register, blend: Blend = Blend.Alpha) -> Register:
+        out = C.c_int32()
+        return self._reg(host_lib().zosh_cb_blend(self._h, below.index, rect._ffi(), above.index, int(blend), C.byref(out)), out)
+
+    def crop(self, src: Register, rect: Rectangle) -> Register:
+        out = C.c_int32()
+        return self._reg(host_lib().zosh_cb_crop(self._h, src.index, rect._ffi(), C.byref(out)), out)
+
+    def affine(self, below: Register, affine: Affine, above: Register) -> Register:
+        out = C.c_int32()
+        return self._reg(host_lib().zosh_cb_affine(self._h, below.index, affine._m, int(affine.sampling), above.index, C.byref(out)), out)
+
+    def resize(self, below: Register, upper: Tuple[int, int], mode: ResizeMode = ResizeMode.Reference) -> Register:
+        out = C.c_int32()
+        return self._reg(host_lib().zosh_cb_resize(self._h, below.index, int(upper[0]), int(upper[1]), int(mode), C.byref(out)), out)
+
+    def transmute(self, src: Register, target: Descriptor) -> Register:
+        out = C.c_int32(); d = target.to_ffi()
+        return self._reg(host_lib().zosh_cb_transmute(self._h, src.index, C.byref(d), C.byref(out)), out)
+
+    def bilinear(self, describe: Descriptor, distribution: Bilinear) -> Register:
+        out = C.c_int32(); d = describe.to_ffi()
+        p = (C.c_float * 24)(*distribution.flat())
+        return self._reg(host_lib().zosh_cb_bilinear(self._h, C.byref(d), p, C.byref(out)), out)
+
+    def solid_rgba(self, describe: Descriptor, color: Sequence[float]) -> Register:
+        out = C.c_int32(); d = describe.to_ffi()
+        c = (C.c_float * 4)(*[float(x) for x in color])
+        return self._reg(host_lib().zosh_cb_solid_rgba(self._h, C.byref(d), c, C.byref(out)), out)
+
+    def derivative(self, image: Register, config: Derivative) -> Register:
+        out = C.c_int32()
+        return self._reg(host_lib().zosh_cb_derivative(self._h, image.index, int(config.method), int(config.direction), C.byref(out)), out)
+
+    def palette(self, palette: Register, config: Palette, indices: Register) -> Register:
+        pos = {ColorChannel.R: [1, 0, 0, 0], ColorChannel.G: [0, 1, 0, 0], ColorChannel.B: [0, 0, 1, 0]}
+        if (config.width is not None and config.width not in pos) or (config.height is not None and config.height not in pos):
+            raise CommandError(CommandErrorKind.GenericTypeError, "palette: channel position")  # command.rs:1453-1463
+        xc = (C.c_float * 4)(*[float(v) for v in (pos[config.width] if config.width else [0, 0, 0, 0])])
+        yc = (C.c_float * 4)(*[float(v) for v in (pos[config.height] if config.height else [0, 0, 0, 0])])
+        out = C.c_int32()
+        return self._reg(host_lib().zosh_cb_palette(self._h, palette.index, indices.index, xc, yc, C.byref(out)), out)
+
+    def extract(self, src: Register, channel: ColorChannel) -> Register:
+        raise CommandError(CommandErrorKind.Unimplemented, "extract: scheduled next (SURVEY.md 8f-2)")
+
+    def inject(self, below: Register, channel: ColorChannel, above: Register) -> Register:
+        raise CommandError(CommandErrorKind.Unimplemented, "inject: scheduled next (SURVEY.md 8f-2)")
+
+
+class Linker:
+    """command.rs:38-41, 2069: the reference's Linker carries the SPIR-V blobs; this one needs nothing
+    (the kernels live in libzosimos_cuda.so)."""
+
+    @staticmethod
+    def from_included() -> "Linker":
+        return Linker()
+
+    def compile(self, commands: CommandBuffer) -> "Program":
+        from .program import Program
+        h = _P()
+        _check(host_lib().zosh_compile(commands._h, C.byref(h)))
+        return Program(h, dict(commands._knobs))
+
+
+def to_xyz_matrix(primaries: Primaries, whitepoint: Whitepoint) -> np.ndarray:
+    m = _F9()
+    _check(host_lib().zosh_to_xyz_matrix(int(primaries), int(whitepoint), m))
+    return np.array(list(m), dtype=np.float32).reshape(3, 3)
+
+
+def adaptation_matrix(method: ChromaticAdaptationMethod, src: Whitepoint, dst: Whitepoint) -> np.ndarray:
+    m = _F9()
+    _check(host_lib().zosh_adaptation_matrix(int(method), int(src), int(dst), m))
+    return np.array(list(m), dtype=np.float32).reshape(3, 3)

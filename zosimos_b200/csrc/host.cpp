@@ -1,0 +1,457 @@
+// host.cpp -- C++ mirror of the reference's operator API above the device C-ABI:
+// command::CommandBuffer (typed SSA op builder with the reference's checks and error kinds,
+// lib/zosimos/src/command.rs:743-1740), Linker::compile (liveness + High emission,
+// command.rs:2069-2893) and the colour science its builders call (image-canvas / palette; see
+// zosimos_host.h).  Everything here is host arithmetic; the output is a zos_op[] stream for
+// zos_program_create.
+#include <math.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/zosimos_host.h"
+
+namespace {
+
+thread_local std::string g_err;
+int32_t err(int32_t kind, const char* msg) { g_err = msg; return kind; }
+
+// ---- 3x3 algebra in double, fixed evaluation order (the oracle mirrors these formulas) ----
+void inv3(const double* m, double* o) {
+  double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
+  double A = e * i - f * h, B = -(d * i - f * g), C = d * h - e * g;
+  double det = a * A + b * B + c * C;
+  o[0] = A / det; o[1] = -(b * i - c * h) / det; o[2] = (b * f - c * e) / det;
+  o[3] = B / det; o[4] = (a * i - c * g) / det; o[5] = -(a * f - c * d) / det;
+  o[6] = C / det; o[7] = -(a * h - b * g) / det; o[8] = (a * e - b * d) / det;
+}
+void mul3(const double* a, const double* b, double* o) {
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) o[3 * r + c] = a[3 * r] * b[c] + a[3 * r + 1] * b[3 + c] + a[3 * r + 2] * b[6 + c];
+}
+void to_f32(const double* m, float* o, int n = 9) { for (int i = 0; i < n; i++) o[i] = (float)m[i]; }
+
+// CIE xy chromaticities of the primaries (ITU-R BT.601/709/2020, SMPTE 240M), image-canvas `Primaries`
+const double PRIM[6][6] = {
+    {0.64, 0.33, 0.30, 0.60, 0.15, 0.06},      // Bt709
+    {0.630, 0.340, 0.310, 0.595, 0.155, 0.070},  // Bt601_525
+    {0.64, 0.33, 0.29, 0.60, 0.15, 0.06},      // Bt601_625
+    {0.630, 0.340, 0.310, 0.595, 0.155, 0.070},  // Smpte240
+    {0.708, 0.292, 0.170, 0.797, 0.131, 0.046},  // Bt2020
+    {0.708, 0.292, 0.170, 0.797, 0.131, 0.046},  // Bt2100
+};
+// white points, XYZ with Y = 1 (ASTM E308, 2 degree observer; palette::white_point)
+const double WP[11][3] = {
+    {1.09850, 1.0, 0.35585}, {0.99072, 1.0, 0.85223}, {0.98074, 1.0, 1.18232}, {0.96422, 1.0, 0.82521},
+    {0.95682, 1.0, 0.92149}, {0.95047, 1.0, 1.08883}, {0.94972, 1.0, 1.22638}, {1.0, 1.0, 1.0},
+    {0.99186, 1.0, 0.67393}, {0.95041, 1.0, 1.08747}, {1.00962, 1.0, 0.64350}};
+const double CONE[3][9] = {
+    {0.8951, 0.2664, -0.1614, -0.7502, 1.7135, 0.0367, 0.0389, -0.0685, 1.0296},  // Bradford
+    {0.40024, 0.7076, -0.08081, -0.2263, 1.16532, 0.0457, 0.0, 0.0, 0.91822},      // VonKries (HPE)
+    {1, 0, 0, 0, 1, 0, 0, 0, 1}};                                                   // XyzScaling
+
+bool to_xyz_d(uint32_t prim, uint32_t wp, double* o) {
+  if (prim > 5 || wp > 10) return false;
+  const double* p = PRIM[prim];
+  double xr = p[0], yr = p[1], xg = p[2], yg = p[3], xb = p[4], yb = p[5];
+  double P[9] = {xr / yr, xg / yg, xb / yb, 1.0, 1.0, 1.0, (1 - xr - yr) / yr, (1 - xg - yg) / yg, (1 - xb - yb) / yb};
+  double Pi[9];
+  inv3(P, Pi);
+  const double* w = WP[wp];
+  double S[3];
+  for (int r = 0; r < 3; r++) S[r] = Pi[3 * r] * w[0] + Pi[3 * r + 1] * w[1] + Pi[3 * r + 2] * w[2];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) o[3 * r + c] = P[3 * r + c] * S[c];
+  return true;
+}
+bool adaptation_d(uint32_t method, uint32_t src, uint32_t dst, double* o) {
+  if (src > 10 || dst > 10) return false;
+  int mi = method == ZOSH_ADAPT_BRADFORD_VONKRIES ? 0 : method == ZOSH_ADAPT_VONKRIES ? 1 : method == ZOSH_ADAPT_XYZ ? 2 : -1;
+  if (mi < 0) return false;
+  const double* Mc = CONE[mi];
+  double cs[3], cd[3];
+  for (int r = 0; r < 3; r++) {
+    cs[r] = Mc[3 * r] * WP[src][0] + Mc[3 * r + 1] * WP[src][1] + Mc[3 * r + 2] * WP[src][2];
+    cd[r] = Mc[3 * r] * WP[dst][0] + Mc[3 * r + 1] * WP[dst][1] + Mc[3 * r + 2] * WP[dst][2];
+  }
+  double D[9] = {cd[0] / cs[0], 0, 0, 0, cd[1] / cs[1], 0, 0, 0, cd[2] / cs[2]};
+  double Mi[9], t[9];
+  inv3(Mc, Mi);
+  mul3(D, Mc, t);
+  mul3(Mi, t, o);
+  return true;
+}
+
+// RowMatrix::multiply_right in f32: dot products left to right (color_matrix.rs:124-144)
+void mul3_f32(const float* a, const float* b, float* o) {
+  float t[9];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) t[3 * r + c] = (a[3 * r] * b[c] + a[3 * r + 1] * b[3 + c]) + a[3 * r + 2] * b[6 + c];
+  memcpy(o, t, sizeof t);
+}
+
+bool same_chroma(const zos_desc& a, const zos_desc& b) {
+  return a.block == b.block && a.bits == b.bits && a.parts == b.parts && a.color == b.color && a.transfer == b.transfer &&
+         a.primaries == b.primaries && a.whitepoint == b.whitepoint;
+}
+void fix_layout(zos_desc& d) {
+  d.texel_stride = d.block == ZOS_BLOCK_PIXEL ? zos_bits_bytes(d.bits) : 1;
+  d.row_stride = zos_aligned_row_stride(d.width, d.texel_stride);
+}
+zos_step make_step(uint32_t kind, const double* m, const double* v = nullptr) {
+  zos_step s;
+  memset(&s, 0, sizeof s);
+  s.kind = kind;
+  if (m) to_f32(m, s.m);
+  if (v) for (int i = 0; i < 3; i++) s.v[i] = (float)v[i];
+  return s;
+}
+
+}  // namespace
+
+struct zosh_cb {
+  std::vector<zos_op> ops;  // op i defines register i (outputs define a register too, like the reference)
+  uint32_t next_knob = 0, pending_knob = 0;
+};
+struct zosh_program {
+  std::vector<zos_op> ops;
+};
+
+namespace {
+bool valid_reg(const zosh_cb* cb, int32_t r) { return r >= 0 && (size_t)r < cb->ops.size() && cb->ops[r].kind != ZOS_OP_OUTPUT; }
+zos_op new_op(zosh_cb* cb, uint32_t kind, int32_t s0, int32_t s1, const zos_desc& d) {
+  zos_op op;
+  memset(&op, 0, sizeof op);
+  op.kind = kind;
+  op.src[0] = s0; op.src[1] = s1;
+  op.dst = (int32_t)cb->ops.size();
+  op.reg = op.dst;
+  op.desc = d;
+  op.knob = cb->pending_knob;
+  cb->pending_knob = 0;
+  return op;
+}
+int32_t push(zosh_cb* cb, const zos_op& op, int32_t* reg) {
+  cb->ops.push_back(op);
+  if (reg) *reg = op.dst;
+  return ZOSH_OK;
+}
+}  // namespace
+
+extern "C" {
+
+const char* zosh_last_error(void) { return g_err.c_str(); }
+
+int32_t zosh_to_xyz_matrix(uint32_t primaries, uint32_t whitepoint, float out[9]) {
+  double m[9];
+  if (!to_xyz_d(primaries, whitepoint, m)) return err(ZOSH_ERR_OTHER, "unknown primaries / whitepoint");
+  to_f32(m, out);
+  return ZOSH_OK;
+}
+int32_t zosh_adaptation_matrix(uint32_t method, uint32_t s, uint32_t d, float out[9]) {
+  double m[9];
+  if (method == ZOSH_ADAPT_BRADFORD_NONLINEAR) return err(ZOSH_ERR_UNIMPLEMENTED, "BradfordNonLinear (command.rs:3327-3331)");
+  if (!adaptation_d(method, s, d, m)) return err(ZOSH_ERR_OTHER, "unknown adaptation method / whitepoint");
+  to_f32(m, out);
+  return ZOSH_OK;
+}
+int32_t zosh_whitepoint_xyz(uint32_t wp, float out[3]) {
+  if (wp > 10) return err(ZOSH_ERR_OTHER, "unknown whitepoint");
+  for (int i = 0; i < 3; i++) out[i] = (float)WP[wp][i];
+  return ZOSH_OK;
+}
+void zosh_affine_identity(float m[9]) { const float id[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}; memcpy(m, id, sizeof id); }
+void zosh_affine_scale(float m[9], float x, float y) { const float p[9] = {x, 0, 0, 0, y, 0, 0, 0, 1}; mul3_f32(p, m, m); }
+void zosh_affine_rotate(float m[9], float rad) {
+  const float c = cosf(rad), s = sinf(rad);
+  const float p[9] = {c, s, 0, -s, c, 0, 0, 0, 1};
+  mul3_f32(p, m, m);
+}
+void zosh_affine_shift(float m[9], float x, float y) { const float p[9] = {1, 0, x, 0, 1, y, 0, 0, 1}; mul3_f32(p, m, m); }
+zosh_rect zosh_rect_normalize(zosh_rect r) {
+  uint32_t w = r.max_x > r.x ? r.max_x - r.x : 0;
+  return zosh_rect{r.x, r.y, r.x + w, r.y + w};  // sic: max_y = y + width(), command.rs:3536-3543
+}
+
+zosh_cb* zosh_cb_new(void) { return new zosh_cb(); }
+void zosh_cb_free(zosh_cb* cb) { delete cb; }
+
+int32_t zosh_cb_with_knob(zosh_cb* cb) {
+  if (!cb) return 0;
+  cb->pending_knob = ++cb->next_knob;
+  return (int32_t)cb->pending_knob;
+}
+
+int32_t zosh_cb_describe(const zosh_cb* cb, int32_t reg, zos_desc* out) {
+  if (!cb || !out || !valid_reg(cb, reg)) return err(ZOSH_ERR_OTHER, "bad register");
+  *out = cb->ops[reg].desc;
+  return ZOSH_OK;
+}
+
+int32_t zosh_cb_input(zosh_cb* cb, const zos_desc* desc, int32_t* reg) {
+  if (!cb || !desc) return err(ZOSH_ERR_OTHER, "null argument");
+  zos_desc d = *desc;
+  if (d.block == ZOS_BLOCK_PIXEL && d.texel_stride != zos_bits_bytes(d.bits))
+    return err(ZOSH_ERR_BAD_DESCRIPTOR, "inconsistent input declared");  // command.rs:744-748
+  if (d.width == 0 || d.height == 0) return err(ZOSH_ERR_BAD_DESCRIPTOR, "empty input declared");
+  fix_layout(d);
+  return push(cb, new_op(cb, ZOS_OP_INPUT, -1, -1, d), reg);
+}
+
+int32_t zosh_cb_output(zosh_cb* cb, int32_t src, int32_t* reg) {
+  if (!cb || !valid_reg(cb, src)) return err(ZOSH_ERR_OTHER, "bad register");
+  zos_op op = new_op(cb, ZOS_OP_OUTPUT, src, -1, cb->ops[src].desc);
+  if (reg) *reg = op.dst;
+  op.dst = -1;
+  cb->ops.push_back(op);
+  return ZOSH_OK;
+}
+
+int32_t zosh_cb_color_convert(zosh_cb* cb, int32_t src, const zos_desc* target, int32_t* reg) {
+  if (!cb || !target || !valid_reg(cb, src)) return err(ZOSH_ERR_OTHER, "bad register");
+  const zos_desc& s = cb->ops[src].desc;
+  zos_desc d = *target;
+  d.width = s.width; d.height = s.height; d.block = ZOS_BLOCK_PIXEL;
+  fix_layout(d);
+  double T[9], Ti[9];
+  zos_step st;
+  if (s.color == ZOS_COLOR_RGB && d.color == ZOS_COLOR_RGB && s.whitepoint == d.whitepoint) {
+    // command.rs:1022-1025 names the matrices the wrong way round and to_shader (3223-3228) then
+    // computes to_xyz(dst) * inv(to_xyz(src)); reproduced as is (identity when primaries match)
+    double A[9], B[9], M[9];
+    if (!to_xyz_d(d.primaries, d.whitepoint, A) || !to_xyz_d(s.primaries, s.whitepoint, B)) return err(ZOSH_ERR_OTHER, "unknown primaries");
+    inv3(B, Ti);
+    mul3(A, Ti, M);
+    st = make_step(ZOS_STEP_MATRIX, M);
+  } else if (s.color == ZOS_COLOR_RGB && d.color == ZOS_COLOR_OKLAB && s.whitepoint == ZOS_WP_D65) {
+    to_xyz_d(s.primaries, ZOS_WP_D65, T);
+    st = make_step(ZOS_STEP_OKLAB_ENC, T);
+  } else if (s.color == ZOS_COLOR_OKLAB && d.color == ZOS_COLOR_RGB && d.whitepoint == ZOS_WP_D65) {
+    to_xyz_d(d.primaries, ZOS_WP_D65, T);
+    inv3(T, Ti);
+    st = make_step(ZOS_STEP_OKLAB_DEC, Ti);
+  } else if (s.color == ZOS_COLOR_RGB && d.color == ZOS_COLOR_SRLAB2) {
+    to_xyz_d(s.primaries, s.whitepoint, T);
+    st = make_step(ZOS_STEP_SRLAB2_ENC, T);
+  } else if (s.color == ZOS_COLOR_SRLAB2 && d.color == ZOS_COLOR_RGB) {
+    to_xyz_d(d.primaries, d.whitepoint, T);
+    inv3(T, Ti);
+    if (s.whitepoint > 10) return err(ZOSH_ERR_OTHER, "unknown whitepoint");
+    st = make_step(ZOS_STEP_SRLAB2_DEC, Ti, WP[s.whitepoint]);
+  } else {
+    return err(ZOSH_ERR_BAD_DESCRIPTOR, "No conversion");  // command.rs:1077-1084
+  }
+  zos_op op = new_op(cb, ZOS_OP_PIXEL, src, -1, d);
+  op.nsteps = 1;
+  op.steps[0] = st;
+  return push(cb, op, reg);
+}
+
+int32_t zosh_cb_chromatic_adaptation(zosh_cb* cb, int32_t src, uint32_t method, uint32_t target, int32_t* reg) {
+  if (!cb || !valid_reg(cb, src)) return err(ZOSH_ERR_OTHER, "bad register");
+  const zos_desc& s = cb->ops[src].desc;
+  if (s.color != ZOS_COLOR_RGB) return err(ZOSH_ERR_BAD_DESCRIPTOR, "non-rgb chromatic adaptation");  // command.rs:1149-1157
+  if (method == ZOSH_ADAPT_BRADFORD_NONLINEAR) return err(ZOSH_ERR_UNIMPLEMENTED, "BradfordNonLinear");
+  double to[9], from[9], fi[9], ad[9], t[9], M[9];
+  if (!to_xyz_d(s.primaries, s.whitepoint, to) || !to_xyz_d(s.primaries, target, from) || !adaptation_d(method, s.whitepoint, target, ad))
+    return err(ZOSH_ERR_UNIMPLEMENTED, "whitepoint / method");
+  inv3(from, fi);
+  mul3(ad, to, t);
+  mul3(fi, t, M);  // from_xyz(target) * adapt * to_xyz(source), command.rs:2527-2531
+  zos_desc d = s;
+  d.whitepoint = target;
+  zos_op op = new_op(cb, ZOS_OP_PIXEL, src, -1, d);
+  op.nsteps = 1;
+  op.steps[0] = make_step(ZOS_STEP_MATRIX, M);
+  return push(cb, op, reg);
+}
+
+static void compose_defaults(zos_compose_params& p) {
+  memset(&p, 0, sizeof p);
+  p.map = ZOS_MAP_RECT; p.sampling = ZOS_SAMPLE_NEAREST; p.blend = ZOS_BLEND_OVERWRITE; p.use_tma = 1;
+}
+
+int32_t zosh_cb_inscribe(zosh_cb* cb, int32_t below, zosh_rect rect, int32_t above, int32_t* reg) {
+  if (!cb || !valid_reg(cb, below) || !valid_reg(cb, above)) return err(ZOSH_ERR_OTHER, "bad register");
+  const zos_desc& b = cb->ops[below].desc;
+  const zos_desc& a = cb->ops[above].desc;
+  if (!same_chroma(a, b)) return err(ZOSH_ERR_CONFLICTING_TYPES, "inscribe: texel / colour of the layers differ");  // :1186-1190
+  if (rect.x != 0 || rect.y != 0 || rect.max_x != a.width || rect.max_y != a.height) return err(ZOSH_ERR_OTHER, "inscribe: rect must be the layout of `above`");  // :1196-1198
+  if (rect.max_x > b.width || rect.max_y > b.height) return err(ZOSH_ERR_OTHER, "inscribe: not contained in `below`");  // :1202-1206
+  zosh_rect pl = zosh_rect_normalize(rect);
+  zos_op op = new_op(cb, ZOS_OP_COMPOSE, below, above, b);
+  compose_defaults(op.compose);
+  op.compose.sel[2] = (int32_t)a.width; op.compose.sel[3] = (int32_t)a.height;
+  op.compose.tgt[0] = (int32_t)pl.x; op.compose.tgt[1] = (int32_t)pl.y;
+  op.compose.tgt[2] = (int32_t)(pl.max_x - pl.x); op.compose.tgt[3] = (int32_t)(pl.max_y - pl.y);
+  return push(cb, op, reg);
+}
+
+int32_t zosh_cb_blend(zosh_cb* cb, int32_t below, zosh_rect rect, int32_t above, int32_t mode, int32_t* reg) {
+  // The reference returns UNIMPLEMENTED here (command.rs:1510-1519); semantics: DESIGN.md section 3.
+  if (!cb || !valid_reg(cb, below) || !valid_reg(cb, above)) return err(ZOSH_ERR_OTHER, "bad register");
+  const zos_desc& b = cb->ops[below].desc;
+  const zos_desc& a = cb->ops[above].desc;
+  if (!same_chroma(a, b)) return err(ZOSH_ERR_CONFLICTING_TYPES, "blend: texel / colour of the layers differ");
+  if (mode < ZOS_BLEND_CLEAR || mode > ZOS_BLEND_XOR) return err(ZOSH_ERR_OTHER, "blend: unknown mode");
+  if (rect.max_x < rect.x || rect.max_y < rect.y || rect.max_x - rect.x != a.width || rect.max_y - rect.y != a.height)
+    return err(ZOSH_ERR_OTHER, "blend: rect must have the size of `above`");
+  if (rect.max_x > b.width || rect.max_y > b.height) return err(ZOSH_ERR_OTHER, "blend: not contained in `below`");
+  if (a.color != ZOS_COLOR_RGB && a.color != ZOS_COLOR_SCALARS) return err(ZOSH_ERR_BAD_DESCRIPTOR, "blend: needs an RGB-ish colour");
+  zos_op op = new_op(cb, ZOS_OP_COMPOSE, below, above, b);
+  compose_defaults(op.compose);
+  op.compose.blend = mode;
+  op.compose.sel[2] = (int32_t)a.width; op.compose.sel[3] = (int32_t)a.height;
+  op.compose.tgt[0] = (int32_t)rect.x; op.compose.tgt[1] = (int32_t)rect.y;
+  op.compose.tgt[2] = (int32_t)a.width; op.compose.tgt[3] = (int32_t)a.height;
+  return push(cb, op, reg);
+}
+
+int32_t zosh_cb_crop(zosh_cb* cb, int32_t src, zosh_rect rect, int32_t* reg) {
+  if (!cb || !valid_reg(cb, src)) return err(ZOSH_ERR_OTHER, "bad register");
+  const zos_desc& s = cb->ops[src].desc;
+  if (rect.max_x <= rect.x || rect.max_y <= rect.y) return err(ZOSH_ERR_OTHER, "crop: empty rectangle");
+  // the output keeps the source descriptor and the selection is stretched over it (command.rs:971-978, 2507-2526)
+  zos_op op = new_op(cb, ZOS_OP_COMPOSE, -1, src, s);
+  compose_defaults(op.compose);
+  op.compose.sel[0] = (int32_t)rect.x; op.compose.sel[1] = (int32_t)rect.y;
+  op.compose.sel[2] = (int32_t)(rect.max_x - rect.x); op.compose.sel[3] = (int32_t)(rect.max_y - rect.y);
+  op.compose.tgt[2] = (int32_t)s.width; op.compose.tgt[3] = (int32_t)s.height;
+  return push(cb, op, reg);
+}
+
+int32_t zosh_cb_affine(zosh_cb* cb, int32_t below, const float m[9], uint32_t sampling, int32_t above, int32_t* reg) {
+  if (!cb || !m || !valid_reg(cb, below) || !valid_reg(cb, above)) return err(ZOSH_ERR_OTHER, "bad register");
+  const zos_desc& b = cb->ops[below].desc;
+  const zos_desc& a = cb->ops[above].desc;
+  if (!same_chroma(a, b)) return err(ZOSH_ERR_TYPE, "affine: texel / colour of the layers differ");  // command.rs:1646-1648
+  // RowMatrix::det in f32 (color_matrix.rs:31-39), rejected below f32::EPSILON (command.rs:1650-1657)
+  float det = m[0] * (m[4] * m[8] - m[7] * m[5]) - m[3] * (m[1] * m[8] - m[7] * m[2]) + m[6] * (m[1] * m[5] - m[4] * m[2]);
+  if (!(fabsf(det) >= 1.1920929e-07f)) return err(ZOSH_ERR_OTHER, "affine: singular transformation");
+  if (sampling > ZOS_SAMPLE_BILINEAR) return err(ZOSH_ERR_OTHER, "affine: unknown sampling");
+  // AffineSample::BiLinear is UNIMPLEMENTED in the reference (command.rs:1659-1665); implemented here.
+  if (sampling == ZOS_SAMPLE_BILINEAR && a.color != ZOS_COLOR_RGB && a.color != ZOS_COLOR_SCALARS)
+    return err(ZOSH_ERR_BAD_DESCRIPTOR, "affine: bilinear sampling needs an RGB-ish colour");
+  double md[9], inv[9];
+  for (int i = 0; i < 9; i++) md[i] = (double)m[i];
+  inv3(md, inv);
+  zos_op op = new_op(cb, ZOS_OP_COMPOSE, below, above, b);
+  compose_defaults(op.compose);
+  op.compose.map = ZOS_MAP_AFFINE;
+  op.compose.sampling = (int32_t)sampling;
+  to_f32(inv, op.compose.inv);
+  return push(cb, op, reg);
+}
+
+int32_t zosh_cb_resize(zosh_cb* cb, int32_t below, uint32_t w, uint32_t h, uint32_t mode, int32_t* reg) {
+  if (!cb || !valid_reg(cb, below)) return err(ZOSH_ERR_OTHER, "bad register");
+  if (w == 0 || h == 0 || mode > ZOSH_RESIZE_BILINEAR) return err(ZOSH_ERR_OTHER, "resize: bad size / mode");
+  zos_desc d = cb->ops[below].desc;
+  if (d.block != ZOS_BLOCK_PIXEL) {  // a planar source resizes into its R'G'B' interpretation: caller converts first
+    return err(ZOSH_ERR_BAD_DESCRIPTOR, "resize: planar source, convert it first");
+  }
+  d.width = w; d.height = h;
+  fix_layout(d);
+  zos_op op = new_op(cb, ZOS_OP_COMPOSE, -1, below, d);
+  compose_defaults(op.compose);
+  op.compose.map = mode == ZOSH_RESIZE_REFERENCE ? ZOS_MAP_GRID8 : ZOS_MAP_SCALE;
+  op.compose.sampling = mode == ZOSH_RESIZE_BILINEAR ? ZOS_SAMPLE_BILINEAR : ZOS_SAMPLE_NEAREST;
+  return push(cb, op, reg);
+}
+
+int32_t zosh_cb_transmute(zosh_cb* cb, int32_t src, const zos_desc* target, int32_t* reg) {
+  if (!cb || !target || !valid_reg(cb, src)) return err(ZOSH_ERR_OTHER, "bad register");
+  const zos_desc& s = cb->ops[src].desc;
+  zos_desc d = *target;
+  if (d.width != s.width || d.height != s.height) return err(ZOSH_ERR_BAD_DESCRIPTOR, "invalid transmute with mismatched size");  // :1305-1313
+  if (d.block != ZOS_BLOCK_PIXEL || s.block != ZOS_BLOCK_PIXEL || zos_bits_bytes(d.bits) != zos_bits_bytes(s.bits))
+    return err(ZOSH_ERR_CONFLICTING_TYPES, "transmute between texels of different size");  // :1329-1336
+  if (d.texel_stride != zos_bits_bytes(d.bits)) return err(ZOSH_ERR_BAD_DESCRIPTOR, "invalid transmute with inconsistent result");
+  fix_layout(d);
+  return push(cb, new_op(cb, ZOS_OP_COPY, src, -1, d), reg);
+}
+
+int32_t zosh_cb_bilinear(zosh_cb* cb, const zos_desc* desc, const float p[24], int32_t* reg) {
+  if (!cb || !desc || !p) return err(ZOSH_ERR_OTHER, "null argument");
+  zos_desc d = *desc;
+  if (d.block != ZOS_BLOCK_PIXEL || d.texel_stride != zos_bits_bytes(d.bits) || d.width == 0 || d.height == 0)
+    return err(ZOSH_ERR_BAD_DESCRIPTOR, "inconsistent descriptor for bilinear");
+  fix_layout(d);
+  zos_op op = new_op(cb, ZOS_OP_GENERATE, -1, -1, d);
+  memcpy(op.gen, p, sizeof op.gen);
+  return push(cb, op, reg);
+}
+
+int32_t zosh_cb_solid_rgba(zosh_cb* cb, const zos_desc* desc, const float color[4], int32_t* reg) {
+  if (!cb || !desc || !color) return err(ZOSH_ERR_OTHER, "null argument");
+  zos_desc d = *desc;
+  if (d.block != ZOS_BLOCK_PIXEL || d.texel_stride != zos_bits_bytes(d.bits) || d.width == 0 || d.height == 0)
+    return err(ZOSH_ERR_BAD_DESCRIPTOR, "inconsistent constant color image created");
+  fix_layout(d);
+  zos_op op = new_op(cb, ZOS_OP_GENERATE, -1, -1, d);
+  memcpy(op.gen, color, 16);
+  op.compose.map = 1;  // solid: the colour is written as is (solid_rgb.frag), not through mix()
+  return push(cb, op, reg);
+}
+
+int32_t zosh_cb_derivative(zosh_cb* cb, int32_t src, uint32_t method, uint32_t height_direction, int32_t* reg) {
+  if (!cb || !valid_reg(cb, src)) return err(ZOSH_ERR_OTHER, "bad register");
+  float sm[3];
+  switch (method) {  // command.rs:3343-3409
+    case ZOSH_DERIV_PREWITT: sm[0] = sm[1] = sm[2] = 1.0f / 3.0f; break;
+    case ZOSH_DERIV_SOBEL: sm[0] = 0.25f; sm[1] = 0.5f; sm[2] = 0.25f; break;
+    case ZOSH_DERIV_SCHARR3: sm[0] = sm[2] = (float)(46.84 / 256.0); sm[1] = (float)(162.32 / 256.0); break;
+    case ZOSH_DERIV_SCHARR3_TO_4BIT: sm[0] = sm[2] = 3.0f / 16.0f; sm[1] = 10.0f / 16.0f; break;
+    case ZOSH_DERIV_SCHARR3_TO_8BIT: sm[0] = sm[2] = 47.0f / 256.0f; sm[1] = 162.0f / 256.0f; break;
+    default: return err(ZOSH_ERR_UNIMPLEMENTED, "derivative method (CompileError::NotYetImplemented)");
+  }
+  const float dd[3] = {0.5f, 0.0f, -0.5f};
+  zos_op op = new_op(cb, ZOS_OP_BOX3, src, -1, cb->ops[src].desc);
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) {
+      float v = sm[r] * dd[c];  // RowMatrix::with_outer_product
+      op.gen[height_direction ? 3 * c + r : 3 * r + c] = v;
+    }
+  return push(cb, op, reg);
+}
+
+int32_t zosh_cb_palette(zosh_cb* cb, int32_t palette, int32_t indices, const float xc[4], const float yc[4], int32_t* reg) {
+  if (!cb || !xc || !yc || !valid_reg(cb, palette) || !valid_reg(cb, indices)) return err(ZOSH_ERR_OTHER, "bad register");
+  const zos_desc& p = cb->ops[palette].desc;
+  zos_desc d = cb->ops[indices].desc;  // layout of the indices, chroma of the palette (command.rs:1467-1471)
+  d.bits = p.bits; d.parts = p.parts; d.color = p.color; d.transfer = p.transfer; d.primaries = p.primaries; d.whitepoint = p.whitepoint;
+  d.block = p.block;
+  fix_layout(d);
+  zos_op op = new_op(cb, ZOS_OP_PALETTE, palette, indices, d);
+  memcpy(op.compose.inv, xc, 16);
+  memcpy(op.compose.inv + 4, yc, 16);
+  return push(cb, op, reg);
+}
+
+int32_t zosh_compile(const zosh_cb* cb, zosh_program** out) {
+  if (!cb || !out) return err(ZOSH_ERR_OTHER, "null argument");
+  // liveness (command.rs:2216-2291): only operations that reach an output are emitted
+  std::vector<char> live(cb->ops.size(), 0);
+  for (size_t i = cb->ops.size(); i-- > 0;) {
+    const zos_op& op = cb->ops[i];
+    if (op.kind == ZOS_OP_OUTPUT || op.kind == ZOS_OP_INPUT) live[i] = 1;
+    if (!live[i]) continue;
+    for (int s = 0; s < 2; s++)
+      if (op.src[s] >= 0) live[op.src[s]] = 1;
+  }
+  zosh_program* p = new zosh_program();
+  for (size_t i = 0; i < cb->ops.size(); i++)
+    if (live[i]) p->ops.push_back(cb->ops[i]);
+  *out = p;
+  return ZOSH_OK;
+}
+void zosh_program_free(zosh_program* p) { delete p; }
+uint32_t zosh_program_num_ops(const zosh_program* p) { return p ? (uint32_t)p->ops.size() : 0; }
+const zos_op* zosh_program_ops(const zosh_program* p) { return p && !p->ops.empty() ? p->ops.data() : nullptr; }
+zos_status zosh_program_lower(const zosh_program* p, zos_ctx* ctx, uint32_t fuse_mode, uint32_t batch, zos_program** out) {
+  if (!p) return ZOS_ERR_INVALID;
+  return zos_program_create(ctx, p->ops.data(), (uint32_t)p->ops.size(), fuse_mode, batch, out);
+}
+
+}  // extern "C"

@@ -33,7 +33,7 @@ __device__ __forceinline__ void store_word(const DevImage& im, uint32_t frame, i
   }
 }
 
-struct GenParams { DevImage dst; float p[24]; uint32_t total; };
+struct GenParams { DevImage dst; float p[24]; uint32_t total; uint32_t solid; };
 __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ GenParams P) {
   __shared__ Tables T;
   load_tables(T);
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ GenPar
       float a = P.p[k] * (1.0f - u) + P.p[4 + k] * u;
       float b = P.p[8 + k] * (1.0f - v) + P.p[12 + k] * v;
       float d = P.p[16 + k] * (1.0f - uv) + P.p[20 + k] * uv;
-      c[k] = a + b + d;
+      c[k] = P.solid ? P.p[k] : a + b + d;  // solid_rgb.frag writes the colour as is
     }
     store_word(P.dst, frame, i, j, pack_texel(P.dst.fmt, make_float4(c[0], c[1], c[2], c[3]), T));
   }
@@ -101,9 +101,10 @@ static zos_status total_px(zos_ctx* ctx, const DevImage& d, uint32_t batch, uint
   return ZOS_OK;
 }
 
-zos_status launch_generate(zos_ctx* ctx, const DevImage& dst, const float* p, uint32_t batch) {
+zos_status launch_generate(zos_ctx* ctx, const DevImage& dst, const float* p, uint32_t batch, bool solid) {
   GenParams P;
   P.dst = dst;
+  P.solid = solid ? 1u : 0u;
   memcpy(P.p, p, sizeof P.p);
   zos_status st = total_px(ctx, dst, batch, &P.total);
   if (st != ZOS_OK) return st;

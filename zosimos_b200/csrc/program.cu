@@ -245,6 +245,8 @@ zos_status plan(zos_program* p, const zos_op* ops, uint32_t nops) {
         if ((st = alloc_reg(p, op.dst)) != ZOS_OK) return st;
         Kernel k;
         k.kind = K_GENERATE; k.dst = op.dst; k.knob = op.knob;
+        memset(&k.cp, 0, sizeof k.cp);
+        k.cp.map = op.compose.map;  // 1 = solid colour
         memcpy(k.gen, op.gen, sizeof k.gen);
         p->schedule.push_back(k);
         break;
@@ -288,7 +290,7 @@ zos_status run_kernel(zos_program* p, const Kernel& k) {
   switch (k.kind) {
     case K_PIXEL: return zos_pixel_chain(ctx, img(k.src0), img(k.dst), k.steps, k.nsteps, p->batch);
     case K_COMPOSE: return zos_compose(ctx, img(k.src0), img(k.src1), img(k.dst), &k.cp, p->batch);
-    case K_GENERATE: return zos_generate_bilinear(ctx, img(k.dst), k.gen, p->batch);
+    case K_GENERATE: return k.cp.map ? zos_generate_solid(ctx, img(k.dst), k.gen, p->batch) : zos_generate_bilinear(ctx, img(k.dst), k.gen, p->batch);
     case K_BOX3: return zos_box3(ctx, img(k.src0), img(k.dst), k.gen, p->batch);
     case K_PALETTE: return zos_palette(ctx, img(k.src0), img(k.src1), img(k.dst), k.cp.inv, k.cp.inv + 4, p->batch);
     case K_COPY: {

@@ -333,6 +333,28 @@ zos_status zos_buf_fill(zos_ctx* ctx, zos_buf* dst, uint64_t off, uint64_t bytes
   return check_cuda(ctx, cudaMemsetAsync((uint8_t*)dst->ptr + off, value, bytes, ctx->stream), "fill");
 }
 
+static zos_status image_xfer(zos_ctx* ctx, const zos_image* img, uint32_t frame, void* host, bool up) {
+  if (!ctx || !img || !img->data || !host) return ZOS_ERR_INVALID;
+  const zos_desc& d = img->desc;
+  cudaSetDevice(ctx->device);
+  auto copy = [&](uint8_t* dev, uint64_t dpitch, uint8_t* h, uint64_t row, uint64_t rows) {
+    cudaError_t e = up ? cudaMemcpy2DAsync(dev, dpitch, h, row, row, rows, cudaMemcpyHostToDevice, ctx->stream)
+                       : cudaMemcpy2DAsync(h, row, dev, dpitch, row, rows, cudaMemcpyDeviceToHost, ctx->stream);
+    return check_cuda(ctx, e, up ? "image upload" : "image download");
+  };
+  uint8_t* h = (uint8_t*)host;
+  uint64_t row = (uint64_t)d.width * (d.block == ZOS_BLOCK_PIXEL ? d.texel_stride : 1);
+  zos_status st = copy((uint8_t*)img->data + (uint64_t)frame * img->batch_stride, d.row_stride, h, row, d.height);
+  if (st != ZOS_OK || d.block == ZOS_BLOCK_PIXEL) return st;
+  uint64_t cw = (d.width + 1) / 2, ch = (d.height + 1) / 2;
+  h += row * d.height;
+  if (d.block == ZOS_BLOCK_YUV420_NV12) return copy((uint8_t*)img->plane1 + (uint64_t)frame * img->chroma_batch_stride, img->chroma_stride, h, 2 * cw, ch);
+  if ((st = copy((uint8_t*)img->plane1 + (uint64_t)frame * img->chroma_batch_stride, img->chroma_stride, h, cw, ch)) != ZOS_OK) return st;
+  return copy((uint8_t*)img->plane2 + (uint64_t)frame * img->chroma_batch_stride, img->chroma_stride, h + cw * ch, cw, ch);
+}
+zos_status zos_image_upload(zos_ctx* ctx, const zos_image* dst, uint32_t frame, const void* host) { return image_xfer(ctx, dst, frame, (void*)host, true); }
+zos_status zos_image_download(zos_ctx* ctx, const zos_image* src, uint32_t frame, void* host) { return image_xfer(ctx, src, frame, host, false); }
+
 zos_status zos_pixel_chain(zos_ctx* ctx, const zos_image* src, const zos_image* dst, const zos_step* steps, uint32_t nsteps, uint32_t batch) {
   if (!ctx) return ZOS_ERR_INVALID;
   DevImage s, d;
@@ -386,7 +408,18 @@ zos_status zos_generate_bilinear(zos_ctx* ctx, const zos_image* dst, const float
   if ((st = make_dev_image(ctx, dst, &d, "dst")) != ZOS_OK) return st;
   if (d.block != ZOS_BLOCK_PIXEL) return fail(ctx, ZOS_ERR_UNSUPPORTED, "generate: planar destination");
   cudaSetDevice(ctx->device);
-  return batch ? launch_generate(ctx, d, p, batch) : ZOS_OK;
+  return batch ? launch_generate(ctx, d, p, batch, false) : ZOS_OK;
+}
+zos_status zos_generate_solid(zos_ctx* ctx, const zos_image* dst, const float* color, uint32_t batch) {
+  if (!ctx || !color) return ZOS_ERR_INVALID;
+  DevImage d;
+  zos_status st;
+  if ((st = make_dev_image(ctx, dst, &d, "dst")) != ZOS_OK) return st;
+  if (d.block != ZOS_BLOCK_PIXEL) return fail(ctx, ZOS_ERR_UNSUPPORTED, "generate: planar destination");
+  float p[24] = {0};
+  memcpy(p, color, 16);
+  cudaSetDevice(ctx->device);
+  return batch ? launch_generate(ctx, d, p, batch, true) : ZOS_OK;
 }
 zos_status zos_box3(zos_ctx* ctx, const zos_image* src, const zos_image* dst, const float* m, uint32_t batch) {
   if (!ctx || !m) return ZOS_ERR_INVALID;
