@@ -203,6 +203,11 @@ typedef struct zos_compose_params {
   int32_t sel[4];    /* x, y, w, h in `above` texels (ZOS_MAP_RECT) */
   int32_t tgt[4];    /* x, y, w, h in destination pixels (ZOS_MAP_RECT / ZOS_MAP_SCALE) */
   float inv[9];      /* row-major inverse affine (ZOS_MAP_AFFINE) */
+  /* sharding one large image over GPUs by row bands / tiles (all zero = whole images): dst is the window of
+   * the full destination starting at dst_origin, `above` the window of the full src_full[0] x src_full[1]
+   * source starting at src_origin.  sel / tgt / inv stay in FULL-image coordinates, so a windowed launch
+   * writes exactly the bytes of the whole-image launch. */
+  int32_t dst_origin[2], src_origin[2], src_full[2];
   uint32_t n_src_steps, n_dst_steps;
   zos_step src_steps[ZOS_MAX_STEPS]; /* applied to every `above` tap after unpack */
   zos_step dst_steps[ZOS_MAX_STEPS]; /* applied to the composed value before pack */

@@ -240,6 +240,15 @@ def paint_affine(dst_tex, src_tex, inv, sampling=0):
     return dst_tex
 
 
+def paint_affine_window(dst_rows, dst_y0, src_rows, src_y0, src_full_h, inv, sampling=0):
+    """Row-band form: dst_rows = rows [dst_y0, ...) of the destination, src_rows = rows [src_y0, ...) of the
+    full source (height src_full_h); coordinates are those of the full images."""
+    src_rows = _f32(src_rows); m = _f32(inv)
+    lib().zo_paint_affine_window(_fp(src_rows), src_rows.shape[1], int(src_full_h), int(src_y0), _fp(m), int(sampling), _fp(dst_rows),
+                                 dst_rows.shape[1], dst_rows.shape[0], int(dst_y0))
+    return dst_rows
+
+
 def gen_bilinear(params: Sequence[Sequence[float]], w: int, h: int):
     p = _f32(np.asarray(params, dtype=np.float32).reshape(24))
     out = np.empty((h, w, 4), np.float32)

@@ -583,36 +583,47 @@ static inline void affine_point(const float* inv, float cx, float cy, float* px,
   *px = fmaf(inv[1], cy, fmaf(inv[0], cx, inv[2]));
   *py = fmaf(inv[4], cy, fmaf(inv[3], cx, inv[5]));
 }
-static inline void bilinear_tap(const float* src, int sw, int sh, float px, float py, float* o) {
+/* `src` holds rows [yoff, ...) of an image of sw x sh texels (yoff = 0: the whole image) */
+static inline void bilinear_tap_win(const float* src, int sw, int sh, int yoff, float px, float py, float* o) {
   float fx = px - 0.5f, fy = py - 0.5f;
   float x0f = floorf(fx), y0f = floorf(fy);
   float ax = fx - x0f, ay = fy - y0f;
   int x0 = (int)x0f, y0 = (int)y0f, x1 = x0 + 1, y1 = y0 + 1;
   if (x0 < 0) x0 = 0; if (x1 < 0) x1 = 0; if (x0 > sw - 1) x0 = sw - 1; if (x1 > sw - 1) x1 = sw - 1;
   if (y0 < 0) y0 = 0; if (y1 < 0) y1 = 0; if (y0 > sh - 1) y0 = sh - 1; if (y1 > sh - 1) y1 = sh - 1;
-  const float* p00 = src + ((size_t)y0 * sw + x0) * 4; const float* p10 = src + ((size_t)y0 * sw + x1) * 4;
-  const float* p01 = src + ((size_t)y1 * sw + x0) * 4; const float* p11 = src + ((size_t)y1 * sw + x1) * 4;
+  const float* p00 = src + ((size_t)(y0 - yoff) * sw + x0) * 4; const float* p10 = src + ((size_t)(y0 - yoff) * sw + x1) * 4;
+  const float* p01 = src + ((size_t)(y1 - yoff) * sw + x0) * 4; const float* p11 = src + ((size_t)(y1 - yoff) * sw + x1) * 4;
   for (int k = 0; k < 4; k++) {
     float top = fmaf(ax, p10[k] - p00[k], p00[k]);
     float bot = fmaf(ax, p11[k] - p01[k], p01[k]);
     o[k] = fmaf(ay, bot - top, top);
   }
 }
-ZO_API void zo_paint_affine(const float* src, int sw, int sh, const float* inv, int sampling, float* dst, int dw, int dh) {
+static inline void bilinear_tap(const float* src, int sw, int sh, float px, float py, float* o) {
+  bilinear_tap_win(src, sw, sh, 0, px, py, o);
+}
+/* Windowed form (row-band sharding): `dst` holds rows [dst_y0, dst_y0 + dh) of the full
+ * destination and `src` rows [src_y0, ...) of the full sw x sh source; coordinates are the FULL image's,
+ * so a banded run yields exactly the bytes of the whole-image run. */
+ZO_API void zo_paint_affine_window(const float* src, int sw, int sh, int src_y0, const float* inv, int sampling, float* dst,
+                                   int dw, int dh, int dst_y0) {
 #pragma omp parallel for schedule(static)
   for (int j = 0; j < dh; j++)
     for (int i = 0; i < dw; i++) {
       float px, py;
-      affine_point(inv, (float)i + 0.5f, (float)j + 0.5f, &px, &py);
+      affine_point(inv, (float)i + 0.5f, (float)(j + dst_y0) + 0.5f, &px, &py);
       if (!(px >= 0.0f && px < (float)sw && py >= 0.0f && py < (float)sh)) continue;
       float* o = dst + ((size_t)j * dw + i) * 4;
       if (sampling == 0) {
         int u = (int)floorf(px), v = (int)floorf(py);
-        memcpy(o, src + ((size_t)v * sw + u) * 4, 16);
+        memcpy(o, src + ((size_t)(v - src_y0) * sw + u) * 4, 16);
       } else {
-        bilinear_tap(src, sw, sh, px, py, o);
+        bilinear_tap_win(src, sw, sh, src_y0, px, py, o);
       }
     }
+}
+ZO_API void zo_paint_affine(const float* src, int sw, int sh, const float* inv, int sampling, float* dst, int dw, int dh) {
+  zo_paint_affine_window(src, sw, sh, 0, inv, sampling, dst, dw, dh, 0);
 }
 
 /* bilinear.frag:14-20; mix(a,b,t) = a*(1-t) + b*t; uv = pixel centre / size */

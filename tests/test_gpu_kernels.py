@@ -465,3 +465,34 @@ def test_unorm8_decode_exact_all_codes(ctx):
     dd = zdesc(w, h, Texel.new_f32(), Color.Rgb(Z.Primaries.Bt709, Transfer.Linear))
     got = run_chain(ctx, sd, data, dd, []).view(np.float32).reshape(h, w, 4)
     assert np.array_equal(got, data.astype(np.float32) / np.float32(255))
+
+
+# ---------------------------------------------------------------- row-band sharding of one large image
+@pytest.mark.parametrize("sampling", [0, 1])
+@pytest.mark.parametrize("use_tma", [False, True])
+def test_row_bands_equal_whole_image(ctx, sampling, use_tma):
+    """a huge image is split into row bands, one per GPU; every band reads only the source
+    rows its footprint needs.  Windowed launches keep full-image coordinates, so the concatenated bands
+    are byte-identical to the whole-image launch."""
+    from zosimos_b200 import shard
+    W, H, w, h = 700, 512, 640, 480
+    rng = np.random.default_rng(21)
+    t = Texel.new_f16(); c = Color.Rgb(Z.Primaries.Bt709, Transfer.Linear)
+    a16 = rng.random((h, w, 4), dtype=np.float32).astype(np.float16); b16 = rng.random((H, W, 4), dtype=np.float32).astype(np.float16)
+    m = (O.shift(W / 2, H / 2) @ O.scale(1.1, 0.9) @ O.rotate(np.deg2rad(27.0)) @ O.shift(-w / 2, -h / 2)).astype(np.float32)
+    inv = O.inv3(m.astype(np.float64)).astype(np.float32)
+    da, dbb = zdesc(w, h, t, c), zdesc(W, H, t, c)
+    below, above, dst = ctx.upload(dbb, b16.view(np.uint8)), ctx.upload(da, a16.view(np.uint8)), ctx.image(dbb)
+    ops.compose(ctx, below, above, dst, ops.compose_params(map=_ffi.MAP_AFFINE, sampling=sampling, inv=inv, use_tma=use_tma))
+    whole = dst.download().reshape(H, -1)
+    bands = shard.row_bands(H, 4, align=32)
+    parts = []
+    for (y0, y1) in bands:
+        s0, s1 = shard.band_source_rows(inv.reshape(9), (y0, y1), W, h)
+        s1 = max(s1, s0 + 1)
+        db_band, da_band = zdesc(W, y1 - y0, t, c), zdesc(w, s1 - s0, t, c)
+        bb = ctx.upload(db_band, b16[y0:y1].view(np.uint8)); ab = ctx.upload(da_band, a16[s0:s1].view(np.uint8)); out = ctx.image(db_band)
+        ops.compose(ctx, bb, ab, out, ops.compose_params(map=_ffi.MAP_AFFINE, sampling=sampling, inv=inv, use_tma=use_tma,
+                                                         dst_origin=(0, y0), src_origin=(0, s0), src_full=(w, h)))
+        parts.append(out.download().reshape(y1 - y0, -1))
+    assert np.array_equal(np.concatenate(parts), whole)

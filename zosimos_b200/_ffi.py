@@ -55,6 +55,7 @@ class ZosStep(C.Structure):
 class ZosComposeParams(C.Structure):
     _fields_ = [("map", C.c_int32), ("sampling", C.c_int32), ("blend", C.c_int32), ("use_tma", C.c_int32),
                 ("sel", C.c_int32 * 4), ("tgt", C.c_int32 * 4), ("inv", C.c_float * 9),
+                ("dst_origin", C.c_int32 * 2), ("src_origin", C.c_int32 * 2), ("src_full", C.c_int32 * 2),
                 ("n_src_steps", C.c_uint32), ("n_dst_steps", C.c_uint32),
                 ("src_steps", ZosStep * ZOS_MAX_STEPS), ("dst_steps", ZosStep * ZOS_MAX_STEPS)]
 

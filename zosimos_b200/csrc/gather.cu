@@ -33,6 +33,10 @@ struct GatherParams {
   int32_t sel[4], tgt[4];
   float inv[6];
   float rx, ry;  // sel.w / tgt.w, sel.h / tgt.h (bilinear rect mapping)
+  // row-band / tile sharding: dst holds the window of the full destination that starts
+  // at (dox, doy); `above` holds the window of the full sfw x sfh source that starts at (sox, soy).
+  // All mapping arithmetic uses FULL-image coordinates, so a windowed run gives the whole run's bytes.
+  int32_t dox, doy, sox, soy, sfw, sfh;
   uint32_t tiles_x, tiles_y, total_tiles;
   FastDiv div_tx, div_ty;
   int32_t use_tma;        // 0 direct, 1 TMA (pixel source), 2 TMA (planar YUV source)
@@ -108,25 +112,29 @@ __device__ TileInfo tile_info(const GatherParams& P, uint32_t t) {
   float minx, maxx, miny, maxy;
   if (P.map == ZOS_MAP_AFFINE) {
     float px[4], py[4];
-    map_point(P, ti.x0 + 0.5f, ti.y0 + 0.5f, px[0], py[0]);
-    map_point(P, x1 + 0.5f, ti.y0 + 0.5f, px[1], py[1]);
-    map_point(P, ti.x0 + 0.5f, y1 + 0.5f, px[2], py[2]);
-    map_point(P, x1 + 0.5f, y1 + 0.5f, px[3], py[3]);
+    const float gx0 = (float)(ti.x0 + P.dox) + 0.5f, gx1 = (float)(x1 + P.dox) + 0.5f;
+    const float gy0 = (float)(ti.y0 + P.doy) + 0.5f, gy1 = (float)(y1 + P.doy) + 0.5f;
+    map_point(P, gx0, gy0, px[0], py[0]);
+    map_point(P, gx1, gy0, px[1], py[1]);
+    map_point(P, gx0, gy1, px[2], py[2]);
+    map_point(P, gx1, gy1, px[3], py[3]);
     minx = fminf(fminf(px[0], px[1]), fminf(px[2], px[3])); maxx = fmaxf(fmaxf(px[0], px[1]), fmaxf(px[2], px[3]));
     miny = fminf(fminf(py[0], py[1]), fminf(py[2], py[3])); maxy = fmaxf(fmaxf(py[0], py[1]), fmaxf(py[2], py[3]));
   } else {  // ZOS_MAP_RECT (also the exact resize): separable, monotone
-    int ix0 = max(ti.x0, P.tgt[0]), ix1 = min(x1, P.tgt[0] + P.tgt[2] - 1);
-    int iy0 = max(ti.y0, P.tgt[1]), iy1 = min(y1, P.tgt[1] + P.tgt[3] - 1);
+    int ix0 = max(ti.x0 + P.dox, P.tgt[0]), ix1 = min(x1 + P.dox, P.tgt[0] + P.tgt[2] - 1);
+    int iy0 = max(ti.y0 + P.doy, P.tgt[1]), iy1 = min(y1 + P.doy, P.tgt[1] + P.tgt[3] - 1);
     if (ix0 > ix1 || iy0 > iy1) { ti.any = false; return ti; }
     minx = P.sel[0] + ((float)(ix0 - P.tgt[0]) + 0.5f) * P.rx; maxx = P.sel[0] + ((float)(ix1 - P.tgt[0]) + 0.5f) * P.rx;
     miny = P.sel[1] + ((float)(iy0 - P.tgt[1]) + 0.5f) * P.ry; maxy = P.sel[1] + ((float)(iy1 - P.tgt[1]) + 0.5f) * P.ry;
   }
   // clip the footprint to the image: taps are clamped before they are fetched
   minx = fmaxf(minx, 0.0f); miny = fmaxf(miny, 0.0f);
-  maxx = fminf(maxx, (float)P.above.w); maxy = fminf(maxy, (float)P.above.h);
+  maxx = fminf(maxx, (float)P.sfw); maxy = fminf(maxy, (float)P.sfh);
   if (minx > maxx || miny > maxy) { ti.any = false; return ti; }
-  int lox = max((int)floorf(minx) - 2, 0), hix = min((int)floorf(maxx) + 2, P.above.w - 1);
-  int loy = max((int)floorf(miny) - 2, 0), hiy = min((int)floorf(maxy) + 2, P.above.h - 1);
+  // from here on in the coordinates of the window of the source that `above` holds
+  int lox = max((int)floorf(minx) - 2 - P.sox, 0), hix = min((int)floorf(maxx) + 2 - P.sox, P.above.w - 1);
+  int loy = max((int)floorf(miny) - 2 - P.soy, 0), hiy = min((int)floorf(maxy) + 2 - P.soy, P.above.h - 1);
+  if (lox > hix || loy > hiy) { ti.any = false; return ti; }
   if (P.use_tma == 2) {  // chroma needs an even origin; bilinear chroma reaches one chroma texel further
     lox = max(lox - 2, 0) & ~(P.align_x - 1); loy = max((loy & ~1) - 2, 0);
     hix = min(hix + 2, P.above.w - 1); hiy = min(hiy + 2, P.above.h - 1);
@@ -152,6 +160,7 @@ template <bool SMEM>
 __device__ __forceinline__ uint4 fetch_word(const GatherParams& P, const TileInfo& ti, const Stage& st, int u, int v) {
   const int bpp = P.above.bpp;
   const uint8_t* p;
+  u -= P.sox; v -= P.soy;  // full-image coordinates -> the window `above` holds
   if (SMEM) p = st.p0 + ((size_t)(v - ti.by) * P.box_w + (u - ti.bx)) * bpp;
   else p = P.above.p0 + ti.frame * P.above.bstride + (uint64_t)v * P.above.pitch + (uint64_t)u * bpp;
   uint4 w = make_uint4(0, 0, 0, 0);
@@ -181,7 +190,7 @@ __device__ __forceinline__ float4 fetch_texel(const GatherParams& P, const TileI
   if (P.above.block == ZOS_BLOCK_PIXEL) {
     c = unpack_texel(P.above.fmt, fetch_word<SMEM>(P, ti, st, u, v), T);
   } else {
-    float Y;
+    float Y;  // (planar sources are never windowed: sox = soy = 0)
     if (SMEM) Y = (float)st.p0[(size_t)(v - ti.by) * P.box_w + (u - ti.bx)];
     else Y = (float)P.above.p0[ti.frame * P.above.bstride + (uint64_t)v * P.above.pitch + u];
     const int cw = (P.above.w + 1) >> 1, ch = (P.above.h + 1) >> 1;
@@ -224,7 +233,7 @@ __device__ __forceinline__ float4 sample_bilinear(const GatherParams& P, const T
   float x0f = floorf(fx), y0f = floorf(fy);
   float ax = fx - x0f, ay = fy - y0f;
   int x0 = (int)x0f, y0 = (int)y0f;
-  const int sw = P.above.w, sh = P.above.h;
+  const int sw = P.sfw, sh = P.sfh;
   int x1 = min(max(x0 + 1, 0), sw - 1), y1 = min(max(y0 + 1, 0), sh - 1);
   x0 = min(max(x0, 0), sw - 1); y0 = min(max(y0, 0), sh - 1);
   float4 p00 = fetch_texel<SMEM>(P, ti, st, x0, y0, T), p10 = fetch_texel<SMEM>(P, ti, st, x1, y0, T);
@@ -290,8 +299,8 @@ __device__ __forceinline__ void compute_tile(const GatherParams& P, const TileIn
     float4 v = make_float4(0.0f, 0.0f, 1.0f, 1.0f);  // Target::Discard clear colour
     if (P.map == ZOS_MAP_AFFINE) {
       float px, py;
-      map_point(P, (float)i + 0.5f, (float)j + 0.5f, px, py);
-      if (px >= 0.0f && px < (float)P.above.w && py >= 0.0f && py < (float)P.above.h) {
+      map_point(P, (float)(i + P.dox) + 0.5f, (float)(j + P.doy) + 0.5f, px, py);
+      if (px >= 0.0f && px < (float)P.sfw && py >= 0.0f && py < (float)P.sfh) {
         covered = true;
         v = P.sampling == ZOS_SAMPLE_NEAREST ? fetch_texel<SMEM>(P, ti, st, (int)floorf(px), (int)floorf(py), T)
                                              : sample_bilinear<SMEM>(P, ti, st, px, py, T);
@@ -300,12 +309,12 @@ __device__ __forceinline__ void compute_tile(const GatherParams& P, const TileIn
       covered = true;
       v = fetch_texel<SMEM>(P, ti, st, grid8_index(i, P.dst.w, P.above.w, T), grid8_index(j, P.dst.h, P.above.h, T), T);
     } else {
-      const int kx = i - P.tgt[0], ky = j - P.tgt[1];
+      const int kx = i + P.dox - P.tgt[0], ky = j + P.doy - P.tgt[1];
       if (kx >= 0 && kx < P.tgt[2] && ky >= 0 && ky < P.tgt[3]) {
         covered = true;
         if (P.sampling == ZOS_SAMPLE_NEAREST) {
-          int u = min(max(P.sel[0] + rect_index(kx, P.sel[2], P.tgt[2]), 0), P.above.w - 1);
-          int w = min(max(P.sel[1] + rect_index(ky, P.sel[3], P.tgt[3]), 0), P.above.h - 1);
+          int u = min(max(P.sel[0] + rect_index(kx, P.sel[2], P.tgt[2]), 0), P.sfw - 1);
+          int w = min(max(P.sel[1] + rect_index(ky, P.sel[3], P.tgt[3]), 0), P.sfh - 1);
           v = fetch_texel<SMEM>(P, ti, st, u, w, T);
         } else {
           float px = (float)P.sel[0] + ((float)kx + 0.5f) * P.rx, py = (float)P.sel[1] + ((float)ky + 0.5f) * P.ry;
@@ -462,6 +471,13 @@ zos_status launch_gather(zos_ctx* ctx, const DevImage* below, const DevImage& ab
     if (cp.map == ZOS_MAP_SCALE) P.map = ZOS_MAP_RECT;
   }
   for (int k = 0; k < 6; k++) P.inv[k] = cp.inv[k];
+  P.dox = cp.dst_origin[0]; P.doy = cp.dst_origin[1]; P.sox = cp.src_origin[0]; P.soy = cp.src_origin[1];
+  P.sfw = cp.src_full[0] > 0 ? cp.src_full[0] : above.w; P.sfh = cp.src_full[1] > 0 ? cp.src_full[1] : above.h;
+  const bool windowed = P.dox || P.doy || P.sox || P.soy || P.sfw != above.w || P.sfh != above.h;
+  if (windowed && (cp.map == ZOS_MAP_GRID8 || cp.map == ZOS_MAP_SCALE || above.block != ZOS_BLOCK_PIXEL))
+    return fail(ctx, ZOS_ERR_UNSUPPORTED, "windowed (sharded) launches support ZOS_MAP_RECT / ZOS_MAP_AFFINE on pixel sources");
+  if (P.dox < 0 || P.doy < 0 || P.sox < 0 || P.soy < 0 || P.sox + above.w > P.sfw || P.soy + above.h > P.sfh)
+    return fail(ctx, ZOS_ERR_INVALID, "window outside of the full image");
   P.rx = (float)P.sel[2] / (float)(P.tgt[2] > 0 ? P.tgt[2] : 1);
   P.ry = (float)P.sel[3] / (float)(P.tgt[3] > 0 ? P.tgt[3] : 1);
   P.src_steps.n = cp.n_src_steps;

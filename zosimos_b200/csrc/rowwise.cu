@@ -148,6 +148,7 @@ static bool vec_ok(const DevImage& im) {
 
 bool rowwise_can_compose(const DevImage& below, const DevImage& above, const DevImage& dst, const zos_compose_params& cp) {
   if (cp.map != ZOS_MAP_RECT || cp.sampling != ZOS_SAMPLE_NEAREST) return false;
+  if (cp.dst_origin[0] || cp.dst_origin[1] || cp.src_origin[0] || cp.src_origin[1] || cp.src_full[0] || cp.src_full[1]) return false;
   if (below.block != ZOS_BLOCK_PIXEL || above.block != ZOS_BLOCK_PIXEL || dst.block != ZOS_BLOCK_PIXEL) return false;
   // unscaled: the selection is the whole layer and the target has its size
   if (cp.sel[0] != 0 || cp.sel[1] != 0 || cp.sel[2] != above.w || cp.sel[3] != above.h) return false;

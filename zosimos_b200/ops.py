@@ -60,11 +60,14 @@ def pixel_chain(ctx: Context, src: DeviceImage, dst: DeviceImage, steps: Sequenc
 
 
 def compose_params(map: int = _ffi.MAP_RECT, sampling: int = _ffi.SAMPLE_NEAREST, blend: int = _ffi.BLEND_OVERWRITE,
-                   sel=(0, 0, 0, 0), tgt=(0, 0, 0, 0), inv=None, src_steps=(), dst_steps=(), use_tma: bool = True) -> _ffi.ZosComposeParams:
+                   sel=(0, 0, 0, 0), tgt=(0, 0, 0, 0), inv=None, src_steps=(), dst_steps=(), use_tma: bool = True,
+                   dst_origin=(0, 0), src_origin=(0, 0), src_full=(0, 0)) -> _ffi.ZosComposeParams:
     p = _ffi.ZosComposeParams()
     p.map, p.sampling, p.blend, p.use_tma = map, sampling, blend, int(use_tma)
     for i in range(4):
         p.sel[i] = int(sel[i]); p.tgt[i] = int(tgt[i])
+    for i in range(2):
+        p.dst_origin[i] = int(dst_origin[i]); p.src_origin[i] = int(src_origin[i]); p.src_full[i] = int(src_full[i])
     if inv is not None:
         iv = np.asarray(inv, dtype=np.float32).reshape(9)
         for i in range(9):
