@@ -496,3 +496,18 @@ def test_row_bands_equal_whole_image(ctx, sampling, use_tma):
                                                          dst_origin=(0, y0), src_origin=(0, s0), src_full=(w, h)))
         parts.append(out.download().reshape(y1 - y0, -1))
     assert np.array_equal(np.concatenate(parts), whole)
+
+
+def test_source_over_all_alpha_pairs(ctx):
+    """Every (alpha_above, alpha_below) pair: the specialised kernel's reciprocal (SFU + one Newton step)
+    must equal the oracle's IEEE 1/ao for all 65536 possible ao."""
+    W = H = 256
+    a = np.zeros((H, W, 4), np.uint8); b = np.zeros((H, W, 4), np.uint8)
+    rng = np.random.default_rng(5)
+    a[..., :3] = rng.integers(0, 256, (H, W, 3)); b[..., :3] = rng.integers(0, 256, (H, W, 3))
+    a[..., 3] = np.arange(256)[None, :]; b[..., 3] = np.arange(256)[:, None]
+    d = zdesc(W, H, Texel.new_u8(SampleParts.RgbA), Color.SRGB)
+    below, above, dst = ctx.upload(d, b), ctx.upload(d, a), ctx.image(d)
+    ops.compose(ctx, below, above, dst, ops.compose_params(blend=_ffi.BLEND_SRC_OVER, sel=(0, 0, W, H), tgt=(0, 0, W, H)))
+    exp = O.blend(oracle_image(d, b), (0, 0, W, H), oracle_image(d, a), 3)
+    assert np.array_equal(dst.download(), exp.data)
