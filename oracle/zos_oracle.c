@@ -764,14 +764,17 @@ typedef struct zo_yuv {
   uint32_t full_range, nv12, chroma_filter, transfer;
 } zo_yuv;
 static inline void yuv_to_rgb(const zo_yuv* p, float Y, float U, float V, float* o) {
-  float y, cb, cr;
-  if (p->full_range) { y = Y / 255.0f; cb = (U - 128.0f) / 255.0f; cr = (V - 128.0f) / 255.0f; }
-  else { y = (Y - 16.0f) / 219.0f; cb = (U - 128.0f) / 224.0f; cr = (V - 128.0f) / 224.0f; }
-  float kg = 1.0f - p->kr - p->kb;
-  float r = fmaf(2.0f * (1.0f - p->kr), cr, y);
-  float b = fmaf(2.0f * (1.0f - p->kb), cb, y);
-  float g = (y - p->kr * r - p->kb * b) / kg;
-  o[0] = r; o[1] = g; o[2] = b;
+  /* range scaling by f32 reciprocals, then the standard matrix form; the four coefficients are
+   * evaluated in double and rounded once (the kernels get the same four floats from the host) */
+  const float yoff = p->full_range ? 0.0f : 16.0f;
+  const float ysc = p->full_range ? 1.0f / 255.0f : 1.0f / 219.0f, csc = p->full_range ? 1.0f / 255.0f : 1.0f / 224.0f;
+  const double kr = (double)p->kr, kb = (double)p->kb, kg = 1.0 - kr - kb;
+  const float r_cr = (float)(2.0 * (1.0 - kr)), b_cb = (float)(2.0 * (1.0 - kb));
+  const float g_cr = (float)(2.0 * kr * (1.0 - kr) / kg), g_cb = (float)(2.0 * kb * (1.0 - kb) / kg);
+  float y = (Y - yoff) * ysc, cb = (U - 128.0f) * csc, cr = (V - 128.0f) * csc;
+  o[0] = fmaf(r_cr, cr, y);
+  o[1] = fmaf(-g_cb, cb, fmaf(-g_cr, cr, y));
+  o[2] = fmaf(b_cb, cb, y);
 }
 static inline float chroma_sample(const uint8_t* plane, size_t pitch, int step, int cw, int ch, int x, int y, int filter) {
   if (!filter) return (float)plane[(size_t)(y >> 1) * pitch + (size_t)(x >> 1) * step];

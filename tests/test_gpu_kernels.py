@@ -511,3 +511,49 @@ def test_source_over_all_alpha_pairs(ctx):
     ops.compose(ctx, below, above, dst, ops.compose_params(blend=_ffi.BLEND_SRC_OVER, sel=(0, 0, W, H), tgt=(0, 0, W, H)))
     exp = O.blend(oracle_image(d, b), (0, 0, W, H), oracle_image(d, a), 3)
     assert np.array_equal(dst.download(), exp.data)
+
+
+# ---------------------------------------------------------------- BASELINE config 4 at test size
+@pytest.mark.parametrize("nv12", [False, True])
+@pytest.mark.parametrize("chroma_filter", [0, 1])
+def test_fused_frame_pipeline(ctx, nv12, chroma_filter):
+    """I420/NV12 unpack -> BT.2020->BT.709 3x3 -> bilinear 1.5x downscale -> source-over onto an RGBA8
+    sRGB background -> sRGB8 pack, 3 frames, ONE kernel (two-phase tiles: the TMA-staged YUV footprint is
+    converted once into shared memory, then sampled).  Checked against the oracle's pass sequence and
+    against the direct-load path of the same kernel."""
+    W, H, w, h, N = 480, 270, 320, 180, 3
+    rng = np.random.default_rng(8)
+    color = Color.Rgb(Z.Primaries.Bt2020, Transfer.Bt709)
+    d = Z.yuv420_descriptor(W, H, color, Z.YuvMatrix.Bt709, False, nv12, chroma_filter)
+    ys = rng.integers(16, 236, (N, H, W), dtype=np.uint8)
+    us = rng.integers(16, 241, (N, H // 2, W // 2), dtype=np.uint8); vs = rng.integers(16, 241, (N, H // 2, W // 2), dtype=np.uint8)
+    uv = np.stack([us, vs], -1).reshape(N, H // 2, W)
+    src = ctx.image(d, N)
+    src.upload((ys, uv if nv12 else us, None if nv12 else vs))
+    od = zdesc(w, h, Texel.new_u8(SampleParts.RgbA), Color.SRGB)
+    bgd = rng.integers(0, 256, (h, w * 4), dtype=np.uint8)
+    bg = ctx.upload(od, bgd)
+    M = O.mul3(O.inv3(O.to_xyz("bt709", "D65")), O.to_xyz("bt2020", "D65"))
+    outs = []
+    for use_tma in (True, False):
+        dst = ctx.image(od, N)
+        p = ops.compose_params(map=_ffi.MAP_SCALE, sampling=_ffi.SAMPLE_BILINEAR, blend=_ffi.BLEND_SRC_OVER, src_steps=[ops.matrix(M)], use_tma=use_tma)
+        ops.compose(ctx, bg, src, dst, p)
+        outs.append(dst.download())
+    assert np.array_equal(outs[0], outs[1])  # two-phase TMA tiles == direct loads, bit for bit
+    for f in range(N):
+        if nv12:
+            flat = np.ascontiguousarray(uv[f]); tex = np.empty((H, W, 4), np.float32)
+            import ctypes as C
+            pp = O.Yuv(0.2126, 0.0722, 0, 1, chroma_filter, O.TR_BT709)
+            O.lib().zo_decode_yuv420(C.byref(pp), O._bp(ys[f]), C.c_size_t(W), C.cast(flat.ctypes.data, C.POINTER(C.c_uint8)),
+                                     C.cast(flat.ctypes.data + 1, C.POINTER(C.c_uint8)), C.c_size_t(W), W, H, O._fp(tex))
+        else:
+            tex = O.decode_yuv420(ys[f], us[f], vs[f], W, H, 0.2126, 0.0722, False, False, chroma_filter, O.TR_BT709)
+        tex = O.linear(tex, M)
+        small = O.resize_pass(tex, w, h, 1)
+        canvas = O.decode(oracle_image(od, bgd)).copy()
+        O.blend_pass(canvas, small, 0, 0, 3)
+        exp = O.encode(oracle_desc(od), canvas).data
+        assert max_lsb(outs[0][f], exp) <= 1
+        assert np.mean(outs[0][f] == exp) > 0.99

@@ -43,6 +43,7 @@ struct GatherParams {
   int32_t box_w, box_h;   // texels, plane 0
   int32_t cbox_w, cbox_h; // chroma box
   int32_t ept;            // 4-byte elements per texel in the tensor map (bpp >= 4), else 0
+  int32_t conv_w, conv_h; // FAST=2: size of the converted-footprint buffer (texels)
   int32_t align_x;        // box origin x is rounded down to this many texels: the TMA source address must be 16-byte aligned
   StepList src_steps, dst_steps;
 };
@@ -88,6 +89,7 @@ struct TileInfo {
   int x0, y0;    // destination tile origin
   int bx, by;    // source box origin (plane 0 texels)
   int cbx, cby;  // chroma box origin
+  int fx0, fy0;  // FAST=2: origin (source texels) of the tile's tap footprint
   bool fits;     // footprint fits the TMA box
   bool any;      // tile intersects the covered area at all
 };
@@ -107,6 +109,7 @@ __device__ TileInfo tile_info(const GatherParams& P, uint32_t t) {
   ti.y0 = (int)tyi * TILE;
   ti.fits = false; ti.any = true;
   ti.bx = ti.by = ti.cbx = ti.cby = 0;
+  ti.fx0 = ti.fy0 = 0;
   if (!P.use_tma) return ti;
   int x1 = min(ti.x0 + TILE, P.dst.w) - 1, y1 = min(ti.y0 + TILE, P.dst.h) - 1;  // inclusive
   float minx, maxx, miny, maxy;
@@ -127,6 +130,8 @@ __device__ TileInfo tile_info(const GatherParams& P, uint32_t t) {
     minx = P.sel[0] + ((float)(ix0 - P.tgt[0]) + 0.5f) * P.rx; maxx = P.sel[0] + ((float)(ix1 - P.tgt[0]) + 0.5f) * P.rx;
     miny = P.sel[1] + ((float)(iy0 - P.tgt[1]) + 0.5f) * P.ry; maxy = P.sel[1] + ((float)(iy1 - P.tgt[1]) + 0.5f) * P.ry;
   }
+  ti.fx0 = min(max((int)floorf(minx - 0.5f), 0), P.sfw - 1);
+  ti.fy0 = min(max((int)floorf(miny - 0.5f), 0), P.sfh - 1);
   // clip the footprint to the image: taps are clamped before they are fetched
   minx = fmaxf(minx, 0.0f); miny = fmaxf(miny, 0.0f);
   maxx = fminf(maxx, (float)P.sfw); maxy = fminf(maxy, (float)P.sfh);
@@ -154,6 +159,7 @@ struct Stage {          // one pipeline stage in dynamic shared memory
   const uint8_t* p0;    // plane 0 box
   const uint8_t* p1;    // U box
   const uint8_t* p2;    // V box
+  const float4* conv;   // FAST=2: the tile's footprint converted to working values, [conv_h][conv_w]
 };
 
 template <bool SMEM>
@@ -184,8 +190,38 @@ __device__ __forceinline__ float chroma_at(const GatherParams& P, const TileInfo
 }
 
 // one source texel, unpacked to working values (linear light), with the src steps applied
-template <bool SMEM>
+// EOTF applied to video samples: the BT.709 family (by far the common case) inline on the SFU with
+// reciprocal multiplies, everything else through the generic curves of texel.cuh.
+__device__ __forceinline__ float yuv_eotf(uint32_t tr, float v) {
+  if (tr == ZOS_TRANSFER_BT709 || tr == ZOS_TRANSFER_BT2020_10BIT || tr == ZOS_TRANSFER_BT2020_12BIT) {
+    float lin = v * (1.0f / 4.5f);
+    float l2, pw;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"((v + 0.099f) * (1.0f / 1.099f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pw) : "f"(l2 * (1.0f / 0.45f)));
+    return v >= 0.0812428582f ? pw : lin;
+  }
+  if (tr == ZOS_TRANSFER_LINEAR) return v;
+  return eo_scalar(tr, v);
+}
+
+__device__ __forceinline__ float4 half4_to_float4(const uint2& w) {
+  float2 a = __half22float2(*reinterpret_cast<const __half2*>(&w.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// FAST = 1: `above`, `below` and dst are all plain linear RGBA16F and there are no steps (BASELINE
+// config 3): texels are 8-byte loads and two conversions, none of the generic codec is instantiated.
+template <bool SMEM, int FAST>
 __device__ __forceinline__ float4 fetch_texel(const GatherParams& P, const TileInfo& ti, const Stage& st, int u, int v, const Tables& T) {
+  if (FAST == 1) {
+    u -= P.sox; v -= P.soy;
+    const uint8_t* p = SMEM ? st.p0 + ((size_t)(v - ti.by) * P.box_w + (u - ti.bx)) * 8
+                            : P.above.p0 + ti.frame * P.above.bstride + (uint64_t)v * P.above.pitch + (uint64_t)u * 8;
+    return half4_to_float4(*reinterpret_cast<const uint2*>(p));
+  }
+  if (FAST == 2 && SMEM) {  // already unpacked, converted and run through the src steps (phase 1 of the tile)
+    return st.conv[(v - ti.fy0) * P.conv_w + (u - ti.fx0)];
+  }
   float4 c;
   if (P.above.block == ZOS_BLOCK_PIXEL) {
     c = unpack_texel(P.above.fmt, fetch_word<SMEM>(P, ti, st, u, v), T);
@@ -213,20 +249,17 @@ __device__ __forceinline__ float4 fetch_texel(const GatherParams& P, const TileI
       float vt = fmaf(ax, v10 - v00, v00), vb = fmaf(ax, v11 - v01, v01);
       U = fmaf(ay, ub - ut, ut); V = fmaf(ay, vb - vt, vt);
     }
-    float y, cb, cr;
-    if (P.above.full_range) { y = Y / 255.0f; cb = (U - 128.0f) / 255.0f; cr = (V - 128.0f) / 255.0f; }
-    else { y = (Y - 16.0f) / 219.0f; cb = (U - 128.0f) / 224.0f; cr = (V - 128.0f) / 224.0f; }
-    const float kr = P.above.kr, kb = P.above.kb, kg = 1.0f - kr - kb;
-    float r = fmaf(2.0f * (1.0f - kr), cr, y);
-    float b = fmaf(2.0f * (1.0f - kb), cb, y);
-    float g = (y - kr * r - kb * b) / kg;
-    c = make_float4(eo_scalar(P.above.fmt.transfer, r), eo_scalar(P.above.fmt.transfer, g), eo_scalar(P.above.fmt.transfer, b), 1.0f);
+    // R'G'B' = matrix * (range-scaled Y'CbCr), then the colour's EOTF (semantics: DESIGN.md section 3)
+    const DevImage& A = P.above;
+    const float y = (Y - A.yoff) * A.ysc, cb = (U - 128.0f) * A.csc, cr = (V - 128.0f) * A.csc;
+    const float r = fmaf(A.r_cr, cr, y), g = fmaf(-A.g_cb, cb, fmaf(-A.g_cr, cr, y)), b = fmaf(A.b_cb, cb, y);
+    c = make_float4(yuv_eotf(A.fmt.transfer, r), yuv_eotf(A.fmt.transfer, g), yuv_eotf(A.fmt.transfer, b), 1.0f);
   }
   apply_steps(P.src_steps, c, T);
   return c;
 }
 
-template <bool SMEM>
+template <bool SMEM, int FAST>
 __device__ __forceinline__ float4 sample_bilinear(const GatherParams& P, const TileInfo& ti, const Stage& st, float px, float py,
                                                   const Tables& T) {
   float fx = px - 0.5f, fy = py - 0.5f;
@@ -236,8 +269,31 @@ __device__ __forceinline__ float4 sample_bilinear(const GatherParams& P, const T
   const int sw = P.sfw, sh = P.sfh;
   int x1 = min(max(x0 + 1, 0), sw - 1), y1 = min(max(y0 + 1, 0), sh - 1);
   x0 = min(max(x0, 0), sw - 1); y0 = min(max(y0, 0), sh - 1);
-  float4 p00 = fetch_texel<SMEM>(P, ti, st, x0, y0, T), p10 = fetch_texel<SMEM>(P, ti, st, x1, y0, T);
-  float4 p01 = fetch_texel<SMEM>(P, ti, st, x0, y1, T), p11 = fetch_texel<SMEM>(P, ti, st, x1, y1, T);
+  float4 p00, p10, p01, p11;
+  if (FAST == 1) {
+    // one base address, the three neighbours are at +8 bytes / +one row (or 0 where a tap was clamped)
+    const int dx = (x1 - x0) * 8;
+    if (SMEM) {  // 32-bit shared addresses, LDS.64
+      const uint32_t a = smem_u32(st.p0) + (uint32_t)(((y0 - P.soy - ti.by) * P.box_w + (x0 - P.sox - ti.bx)) * 8);
+      const uint32_t dy = (uint32_t)((y1 - y0) * P.box_w * 8);
+      uint2 w00, w10, w01, w11;
+      asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w00.x), "=r"(w00.y) : "r"(a));
+      asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w10.x), "=r"(w10.y) : "r"(a + dx));
+      asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w01.x), "=r"(w01.y) : "r"(a + dy));
+      asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w11.x), "=r"(w11.y) : "r"(a + dy + dx));
+      p00 = half4_to_float4(w00); p10 = half4_to_float4(w10); p01 = half4_to_float4(w01); p11 = half4_to_float4(w11);
+    } else {
+      const uint8_t* p = P.above.p0 + ti.frame * P.above.bstride + (uint64_t)(y0 - P.soy) * P.above.pitch + (uint64_t)(x0 - P.sox) * 8;
+      const int64_t dy = (int64_t)(y1 - y0) * (int64_t)P.above.pitch;
+      p00 = half4_to_float4(*reinterpret_cast<const uint2*>(p));
+      p10 = half4_to_float4(*reinterpret_cast<const uint2*>(p + dx));
+      p01 = half4_to_float4(*reinterpret_cast<const uint2*>(p + dy));
+      p11 = half4_to_float4(*reinterpret_cast<const uint2*>(p + dy + dx));
+    }
+  } else {
+    p00 = fetch_texel<SMEM, FAST>(P, ti, st, x0, y0, T); p10 = fetch_texel<SMEM, FAST>(P, ti, st, x1, y0, T);
+    p01 = fetch_texel<SMEM, FAST>(P, ti, st, x0, y1, T); p11 = fetch_texel<SMEM, FAST>(P, ti, st, x1, y1, T);
+  }
   float4 o;
 #define ZOS_LERP2(c) { float top = fmaf(ax, p10.c - p00.c, p00.c), bot = fmaf(ax, p11.c - p01.c, p01.c); o.c = fmaf(ay, bot - top, top); }
   ZOS_LERP2(x) ZOS_LERP2(y) ZOS_LERP2(z) ZOS_LERP2(w)
@@ -287,7 +343,7 @@ __device__ __forceinline__ void store_px(const DevImage& im, uint32_t frame, int
 
 // A warp owns one 32-pixel row segment of the tile per iteration: all global accesses to `below`
 // and dst are fully coalesced without per-thread vectors, for every texel size.
-template <bool SMEM>
+template <bool SMEM, int FAST>
 __device__ __forceinline__ void compute_tile(const GatherParams& P, const TileInfo& ti, const Stage& st, const Tables& T) {
   const int i = ti.x0 + (threadIdx.x & 31);
   if (i >= P.dst.w) return;
@@ -302,12 +358,12 @@ __device__ __forceinline__ void compute_tile(const GatherParams& P, const TileIn
       map_point(P, (float)(i + P.dox) + 0.5f, (float)(j + P.doy) + 0.5f, px, py);
       if (px >= 0.0f && px < (float)P.sfw && py >= 0.0f && py < (float)P.sfh) {
         covered = true;
-        v = P.sampling == ZOS_SAMPLE_NEAREST ? fetch_texel<SMEM>(P, ti, st, (int)floorf(px), (int)floorf(py), T)
-                                             : sample_bilinear<SMEM>(P, ti, st, px, py, T);
+        v = P.sampling == ZOS_SAMPLE_NEAREST ? fetch_texel<SMEM, FAST>(P, ti, st, (int)floorf(px), (int)floorf(py), T)
+                                             : sample_bilinear<SMEM, FAST>(P, ti, st, px, py, T);
       }
     } else if (P.map == ZOS_MAP_GRID8) {
       covered = true;
-      v = fetch_texel<SMEM>(P, ti, st, grid8_index(i, P.dst.w, P.above.w, T), grid8_index(j, P.dst.h, P.above.h, T), T);
+      v = fetch_texel<SMEM, FAST>(P, ti, st, grid8_index(i, P.dst.w, P.above.w, T), grid8_index(j, P.dst.h, P.above.h, T), T);
     } else {
       const int kx = i + P.dox - P.tgt[0], ky = j + P.doy - P.tgt[1];
       if (kx >= 0 && kx < P.tgt[2] && ky >= 0 && ky < P.tgt[3]) {
@@ -315,12 +371,39 @@ __device__ __forceinline__ void compute_tile(const GatherParams& P, const TileIn
         if (P.sampling == ZOS_SAMPLE_NEAREST) {
           int u = min(max(P.sel[0] + rect_index(kx, P.sel[2], P.tgt[2]), 0), P.sfw - 1);
           int w = min(max(P.sel[1] + rect_index(ky, P.sel[3], P.tgt[3]), 0), P.sfh - 1);
-          v = fetch_texel<SMEM>(P, ti, st, u, w, T);
+          v = fetch_texel<SMEM, FAST>(P, ti, st, u, w, T);
         } else {
           float px = (float)P.sel[0] + ((float)kx + 0.5f) * P.rx, py = (float)P.sel[1] + ((float)ky + 0.5f) * P.ry;
-          v = sample_bilinear<SMEM>(P, ti, st, px, py, T);
+          v = sample_bilinear<SMEM, FAST>(P, ti, st, px, py, T);
         }
       }
+    }
+    if (FAST == 1) {
+      if (P.has_below && !(covered && P.blend == ZOS_BLEND_OVERWRITE)) {
+        const uint2 w = __ldcs(reinterpret_cast<const uint2*>(P.below.p0 + ti.frame * P.below.bstride + (uint64_t)j * P.below.pitch + (uint64_t)i * 8));
+        float4 b = half4_to_float4(w);
+        v = covered ? porter_duff(P.blend, v, b) : b;
+      }
+      __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+      __stcs(reinterpret_cast<uint2*>(P.dst.p0 + ti.frame * P.dst.bstride + (uint64_t)j * P.dst.pitch + (uint64_t)i * 8),
+             make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi)));
+      continue;
+    }
+    if (FAST == 2) {
+      // `below` and dst are native 8-bit texels, blend is overwrite or source-over, no dst steps
+      if (P.has_below && !(covered && P.blend == ZOS_BLEND_OVERWRITE)) {
+        const uint32_t w = __ldcs(reinterpret_cast<const uint32_t*>(P.below.p0 + ti.frame * P.below.bstride + (uint64_t)j * P.below.pitch + (uint64_t)i * 4));
+        const float4 b = unpack_texel(P.below.fmt, make_uint4(w, 0, 0, 0), T);
+        if (covered) {  // porter_duff(ZOS_BLEND_SRC_OVER, v, b) written out
+          const float wb = b.w * (1.0f - v.w), ao = v.w + wb;
+          const float rcp = ao > 0.0f ? __frcp_rn(ao) : 0.0f;
+          v = make_float4(fmaf(wb, b.x, v.w * v.x) * rcp, fmaf(wb, b.y, v.w * v.y) * rcp, fmaf(wb, b.z, v.w * v.z) * rcp, ao);
+        } else {
+          v = b;
+        }
+      }
+      __stcs(reinterpret_cast<uint32_t*>(P.dst.p0 + ti.frame * P.dst.bstride + (uint64_t)j * P.dst.pitch + (uint64_t)i * 4), pack_texel(P.dst.fmt, v, T).x);
+      continue;
     }
     if (P.has_below && !(covered && P.blend == ZOS_BLEND_OVERWRITE)) {
       float4 b = unpack_texel(P.below.fmt, load_px(P.below, ti.frame, i, j), T);
@@ -331,19 +414,21 @@ __device__ __forceinline__ void compute_tile(const GatherParams& P, const TileIn
   }
 }
 
+template <int FAST>
 __global__ void __launch_bounds__(THREADS) k_gather_direct(const __grid_constant__ GatherParams P) {
   __shared__ Tables T;
   load_tables(T);
-  Stage st{nullptr, nullptr, nullptr};
+  Stage st{nullptr, nullptr, nullptr, nullptr};
   for (uint32_t t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
     TileInfo ti = tile_info(P, t);
-    compute_tile<false>(P, ti, st, T);
+    compute_tile<false, FAST>(P, ti, st, T);
   }
 }
 
 // error flag set when an mbarrier wait runs away (never expected; avoids hanging the GPU)
 __device__ int g_tma_timeout = 0;
 
+template <int FAST>
 __global__ void __launch_bounds__(THREADS) k_gather_tma(const __grid_constant__ GatherParams P, const __grid_constant__ TensorMaps M) {
   extern __shared__ __align__(128) uint8_t dyn[];
   __shared__ Tables T;
@@ -396,15 +481,27 @@ __global__ void __launch_bounds__(THREADS) k_gather_tma(const __grid_constant__ 
         }
         phase[s] ^= 1;
         uint8_t* base = dyn + (size_t)s * stage_bytes;
-        Stage st{base, base + box0_al, cstep == 2 ? base + box0_al + 1 : base + box0_al + cbox_al};
-        compute_tile<true>(P, ti, st, T);
+        float4* conv = reinterpret_cast<float4*>(dyn + 2 * (size_t)stage_bytes);
+        Stage st{base, base + box0_al, cstep == 2 ? base + box0_al + 1 : base + box0_al + cbox_al, conv};
+        if (FAST == 2) {
+          // phase 1: every source texel of the tile's tap footprint is unpacked / converted / stepped ONCE
+          // (a bilinear tap pattern would otherwise convert each of them ~4 / scale^2 times)
+          const int n = P.conv_w * P.conv_h;
+          for (int idx = threadIdx.x; idx < n; idx += THREADS) {
+            const int ry = idx / P.conv_w, rx = idx - ry * P.conv_w;
+            const int u = min(ti.fx0 + rx, P.sfw - 1), v = min(ti.fy0 + ry, P.sfh - 1);
+            conv[idx] = fetch_texel<true, 0>(P, ti, st, u, v, T);
+          }
+          __syncthreads();
+        }
+        compute_tile<true, FAST>(P, ti, st, T);
       } else {
-        Stage st{nullptr, nullptr, nullptr};
-        compute_tile<false>(P, ti, st, T);
+        Stage st{nullptr, nullptr, nullptr, nullptr};
+        compute_tile<false, FAST>(P, ti, st, T);
       }
     } else {
-      Stage st{nullptr, nullptr, nullptr};
-      compute_tile<false>(P, ti, st, T);  // nothing of `above` lands here: copies `below`
+      Stage st{nullptr, nullptr, nullptr, nullptr};
+      compute_tile<false, FAST>(P, ti, st, T);  // nothing of `above` lands here: copies `below`
     }
     __syncthreads();  // everyone is done with stage s before it is refilled two tiles later
     s ^= 1;
@@ -494,6 +591,7 @@ zos_status launch_gather(zos_ctx* ctx, const DevImage* below, const DevImage& ab
 
   // ---- TMA plan: box = bounding box of a 32x32 destination tile in the source, plus margins
   bool tma = cp.use_tma && P.map != ZOS_MAP_GRID8;
+  bool two_phase = false;
   TensorMaps M;
   memset(&M, 0, sizeof M);
   size_t smem = 0;
@@ -538,23 +636,50 @@ zos_status launch_gather(zos_ctx* ctx, const DevImage* below, const DevImage& ab
         }
       }
     }
-    if (ok) { P.use_tma = yuv ? 2 : 1; P.box_w = bw; P.box_h = bh; } else { tma = false; P.use_tma = 0; smem = 0; }
+    // FAST=2 (two-phase tiles): planar source, separable mapping; the converted footprint lives behind the stages
+    auto native8 = [](const DevImage& im) {
+      return im.block == ZOS_BLOCK_PIXEL && im.bpp == 4 && (im.fmt.storage == ZOS_STORAGE_SRGB8 || im.fmt.storage == ZOS_STORAGE_UNORM8) &&
+             ((uintptr_t)im.p0 % 4) == 0 && (im.pitch % 4) == 0 && (im.bstride % 4) == 0;
+    };
+    two_phase = ok && yuv && P.map == ZOS_MAP_RECT && !(ctx->flags & ZOS_CTX_NO_FAST_PATHS) && cp.n_dst_steps == 0 &&
+                (cp.blend == ZOS_BLEND_OVERWRITE || cp.blend == ZOS_BLEND_SRC_OVER) && native8(dst) && (!below || native8(*below));
+    if (two_phase) {
+      P.conv_w = (int)ceilf(ex) + 4; P.conv_h = (int)ceilf(ey) + 4;
+      size_t conv_bytes = (size_t)P.conv_w * P.conv_h * sizeof(float4);
+      if (smem + conv_bytes <= 150 * 1024) smem += conv_bytes; else two_phase = false;
+    }
+    if (ok) { P.use_tma = yuv ? 2 : 1; P.box_w = bw; P.box_h = bh; } else { tma = false; P.use_tma = 0; smem = 0; two_phase = false; }
   }
 
+  auto plain_f16 = [](const DevImage& im) {
+    return im.block == ZOS_BLOCK_PIXEL && im.fmt.storage == ZOS_STORAGE_FLOAT && im.fmt.bits == ZOS_BITS_FLOAT16X4 &&
+           im.fmt.transfer == ZOS_TRANSFER_LINEAR && (im.fmt.parts == ZOS_PARTS_RGBA || im.fmt.parts == ZOS_PARTS_LCHA || im.fmt.parts == ZOS_PARTS_LABA) &&
+           ((uintptr_t)im.p0 % 8) == 0 && (im.pitch % 8) == 0 && (im.bstride % 8) == 0;
+  };
+  const bool fast = !(ctx->flags & ZOS_CTX_NO_FAST_PATHS) && P.map != ZOS_MAP_GRID8 && cp.n_src_steps == 0 && cp.n_dst_steps == 0 &&
+                    plain_f16(above) && plain_f16(dst) && (!below || plain_f16(*below));
   cudaError_t e;
   if (tma) {
     static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_gather_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr_set = true; }
+    if (!attr_set) {
+      cudaFuncSetAttribute(k_gather_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      cudaFuncSetAttribute(k_gather_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      cudaFuncSetAttribute(k_gather_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024);
+      attr_set = true;
+    }
     int per_sm = (int)((200 * 1024) / (smem + sizeof(Tables) + 1024));
     per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
     uint64_t cap = (uint64_t)ctx->sm_count * per_sm;
     int grid = (int)(total < cap ? total : cap);
-    k_gather_tma<<<grid, THREADS, smem, ctx->stream>>>(P, M);
+    if (two_phase) k_gather_tma<2><<<grid, THREADS, smem, ctx->stream>>>(P, M);
+    else if (fast) k_gather_tma<1><<<grid, THREADS, smem, ctx->stream>>>(P, M);
+    else k_gather_tma<0><<<grid, THREADS, smem, ctx->stream>>>(P, M);
     e = cudaGetLastError();
   } else {
     uint64_t cap = (uint64_t)ctx->sm_count * 8;
     int grid = (int)(total < cap ? total : cap);
-    k_gather_direct<<<grid, THREADS, 0, ctx->stream>>>(P);
+    if (fast) k_gather_direct<1><<<grid, THREADS, 0, ctx->stream>>>(P);
+    else k_gather_direct<0><<<grid, THREADS, 0, ctx->stream>>>(P);
     e = cudaGetLastError();
   }
   ctx->launches++;

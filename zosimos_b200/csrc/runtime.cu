@@ -123,6 +123,14 @@ zos_status make_dev_image(zos_ctx* ctx, const zos_image* img, DevImage* out, con
     out->bpp = 1;
     out->kr = YUV_K[d.yuv_matrix][0];
     out->kb = YUV_K[d.yuv_matrix][1];
+    {  // the same four matrix coefficients the oracle uses: evaluated in double, rounded once
+      const double kr = (double)out->kr, kb = (double)out->kb, kg = 1.0 - kr - kb;
+      out->yoff = d.yuv_full_range ? 0.0f : 16.0f;
+      out->ysc = d.yuv_full_range ? 1.0f / 255.0f : 1.0f / 219.0f;
+      out->csc = d.yuv_full_range ? 1.0f / 255.0f : 1.0f / 224.0f;
+      out->r_cr = (float)(2.0 * (1.0 - kr)); out->b_cb = (float)(2.0 * (1.0 - kb));
+      out->g_cr = (float)(2.0 * kr * (1.0 - kr) / kg); out->g_cb = (float)(2.0 * kb * (1.0 - kb) / kg);
+    }
     out->full_range = d.yuv_full_range;
     out->chroma_filter = d.chroma_filter;
     if (d.block == ZOS_BLOCK_YUV420_NV12) out->p2 = out->p1 + 1;

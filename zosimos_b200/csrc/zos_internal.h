@@ -38,6 +38,7 @@ struct DevImage {
   uint32_t block;   // ZOS_BLOCK_*
   zos_texfmt fmt;   // transfer of the colour for planar YUV
   float kr, kb;
+  float yoff, ysc, csc, r_cr, b_cb, g_cr, g_cb;  // planar YUV: range scaling and matrix, prepared on the host
   uint32_t full_range, chroma_filter;
 };
 
