@@ -1,0 +1,344 @@
+// frame_pipeline.cu -- the fused video-frame pipeline of BASELINE config 4 as ONE kernel:
+//
+//   planar YUV 4:2:0 (I420 / NV12) unpack -> Y'CbCr -> R'G'B' -> EOTF -> [3x3 primaries matrix]
+//   -> nearest / bilinear resize (axis-aligned placement) -> [source-over onto an 8-bit background]
+//   -> sRGB8 / unorm8 pack,
+//
+// for a whole batch of frames per launch.  Same arithmetic, bit for bit, as the general gather
+// kernel (gather.cu) that also serves this case; this file is the lean version of it:
+//
+//   * a CTA produces 32x32 destination tiles (persistent, grid-stride over tiles x frames);
+//   * the Y and chroma footprints of the NEXT tile are fetched by TMA bulk tensor copies
+//     (cp.async.bulk.tensor.3d + mbarrier) while the current tile is computed (double buffered);
+//   * phase 1 converts the staged footprint to linear-light RGB exactly once per source texel, one
+//     thread per 2x2 luma block (the block shares its chroma sample and all index arithmetic), into
+//     a float4 tile in shared memory;
+//   * phase 2 samples that tile (4 LDS.128 + 3 lerps per channel for bilinear), composites over the
+//     background and packs; global accesses of a warp are 32 consecutive pixels of one row;
+//   * tile geometry is computed by one thread for the next tile and broadcast through shared memory.
+//
+// None of this exists in the reference (no planar texels, no bilinear, no blend: SURVEY.md 0.2);
+// semantics are DESIGN.md section 3, the oracle is oracle/zos_oracle.c (zo_decode_yuv420, zo_linear,
+// zo_resize, zo_blend, zo_encode).
+#include "colorops.cuh"
+#include "tma.cuh"
+#include "zos_internal.h"
+
+namespace zos {
+
+ZOS_DEFINE_CONSTANT_UPLOAD(upload_constants_frame)
+
+namespace {
+constexpr int TILE = 32;
+constexpr int THREADS = 256;
+
+struct FrameParams {
+  int32_t sw, sh, nv12;
+  float yoff, ysc, csc, r_cr, b_cb, g_cr, g_cb;
+  uint32_t transfer;
+  int32_t nmat;
+  float m[9];
+  int32_t sel[4], tgt[4];
+  float rx, ry;
+  int32_t sampling, blend;
+  const uint8_t* below;
+  uint64_t below_pitch, below_bstride;
+  int32_t has_below;
+  zos_texfmt below_fmt, dst_fmt;
+  uint8_t* dst;
+  uint64_t dst_pitch, dst_bstride;
+  int32_t dw, dh;
+  uint32_t tiles_x, tiles_y, total_tiles;
+  FastDiv div_tx, div_ty;
+  int32_t box_w, box_h, cbox_w, cbox_h, conv_w, conv_h;
+};
+
+struct TileGeo {
+  int32_t frame, x0, y0;  // destination tile
+  int32_t bx, by;         // luma box origin (multiple of 32 / even), chroma box origin is half of it
+  int32_t fx0, fy0;       // origin of the converted footprint (even)
+  int32_t any;            // does the placement of the frame touch this tile at all
+};
+
+__device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv& f) {
+  uint32_t t = __umulhi(n, f.m);
+  return f.l == 0 ? n : (t + ((n - t) >> 1)) >> (f.l - 1);
+}
+
+__device__ void tile_geometry(const FrameParams& P, uint32_t t, TileGeo& g) {
+  uint32_t r = fastdiv(t, P.div_tx);
+  uint32_t txi = t - r * P.tiles_x;
+  uint32_t fr = fastdiv(r, P.div_ty);
+  uint32_t tyi = r - fr * P.tiles_y;
+  g.frame = (int)fr; g.x0 = (int)txi * TILE; g.y0 = (int)tyi * TILE;
+  g.bx = g.by = g.fx0 = g.fy0 = 0; g.any = 0;
+  const int x1 = min(g.x0 + TILE, P.dw) - 1, y1 = min(g.y0 + TILE, P.dh) - 1;
+  const int ix0 = max(g.x0, P.tgt[0]), ix1 = min(x1, P.tgt[0] + P.tgt[2] - 1);
+  const int iy0 = max(g.y0, P.tgt[1]), iy1 = min(y1, P.tgt[1] + P.tgt[3] - 1);
+  if (ix0 > ix1 || iy0 > iy1) return;
+  const float minx = (float)P.sel[0] + ((float)(ix0 - P.tgt[0]) + 0.5f) * P.rx;
+  const float miny = (float)P.sel[1] + ((float)(iy0 - P.tgt[1]) + 0.5f) * P.ry;
+  g.fx0 = min(max((int)floorf(minx - 0.5f), 0), P.sw - 1) & ~1;
+  g.fy0 = min(max((int)floorf(miny - 0.5f), 0), P.sh - 1) & ~1;
+  g.bx = g.fx0 & ~31;  // 16-byte aligned TMA source address for the luma AND the (half width) chroma planes
+  g.by = g.fy0;
+  g.any = 1;
+}
+
+// EOTF of video samples (same code as gather.cu's yuv_eotf)
+__device__ __forceinline__ float eotf(uint32_t tr, float v) {
+  if (tr == ZOS_TRANSFER_BT709 || tr == ZOS_TRANSFER_BT2020_10BIT || tr == ZOS_TRANSFER_BT2020_12BIT) {
+    float lin = v * (1.0f / 4.5f);
+    float l2, pw;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"((v + 0.099f) * (1.0f / 1.099f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pw) : "f"(l2 * (1.0f / 0.45f)));
+    return v >= 0.0812428582f ? pw : lin;
+  }
+  if (tr == ZOS_TRANSFER_LINEAR) return v;
+  return eo_scalar(tr, v);
+}
+
+__device__ __forceinline__ float4 convert(const FrameParams& P, float Y, float cb, float cr) {
+  const float y = (Y - P.yoff) * P.ysc;
+  float r = fmaf(P.r_cr, cr, y), g = fmaf(-P.g_cb, cb, fmaf(-P.g_cr, cr, y)), b = fmaf(P.b_cb, cb, y);
+  r = eotf(P.transfer, r); g = eotf(P.transfer, g); b = eotf(P.transfer, b);
+  if (P.nmat) {
+    float3 t = mat3_mul(P.m, r, g, b);
+    r = t.x; g = t.y; b = t.z;
+  }
+  return make_float4(r, g, b, 1.0f);
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+
+__device__ __forceinline__ int rect_index(int k, int s, int t) {  // floor(((2k+1)*s) / (2t)), exact
+  if (s == t) return k;
+  return (int)(((uint64_t)(2 * (uint32_t)k + 1) * (uint32_t)s) / (2ull * (uint32_t)t));
+}
+
+__global__ void __launch_bounds__(THREADS, 3) k_frame_pipeline(const __grid_constant__ FrameParams P, const __grid_constant__ TensorMaps M) {
+  extern __shared__ __align__(128) uint8_t dyn[];
+  __shared__ Tables T;
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ TileGeo geo[2];
+  load_tables(T);
+  const uint32_t cstep = P.nv12 ? 2 : 1;
+  const uint32_t ybox = (uint32_t)P.box_w * P.box_h, cbox = (uint32_t)P.cbox_w * P.cbox_h * cstep;
+  const uint32_t ybox_al = (ybox + 127) & ~127u, cbox_al = (cbox + 127) & ~127u;
+  const uint32_t nchroma = P.nv12 ? 1 : 2;
+  const uint32_t stage_bytes = ybox_al + nchroma * cbox_al;
+  const uint32_t conv_base = smem_u32(dyn + 2 * (size_t)stage_bytes);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const CUtensorMap* const m0 = &M.m0;
+  const CUtensorMap* const m1 = &M.m1;
+  const CUtensorMap* const m2 = &M.m2;
+#define ZOS_FRAME_ISSUE(TILE_INDEX, STAGE)                                                                 \
+  do {                                                                                                      \
+    TileGeo g_;                                                                                             \
+    tile_geometry(P, (TILE_INDEX), g_);                                                                     \
+    geo[(STAGE)] = g_;                                                                                      \
+    if (g_.any) {                                                                                           \
+      uint8_t* base_ = dyn + (size_t)(STAGE) * stage_bytes;                                                 \
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                                        \
+      mbar_expect_tx(&bar[(STAGE)], ybox + nchroma * cbox);                                                 \
+      tma_load_3d(base_, m0, g_.bx, g_.by, g_.frame, &bar[(STAGE)]);                                        \
+      tma_load_3d(base_ + ybox_al, m1, g_.bx >> 1, g_.by >> 1, g_.frame, &bar[(STAGE)]);                    \
+      if (nchroma == 2) tma_load_3d(base_ + ybox_al + cbox_al, m2, g_.bx >> 1, g_.by >> 1, g_.frame, &bar[(STAGE)]); \
+    }                                                                                                       \
+  } while (0)
+
+  if (threadIdx.x == 0 && blockIdx.x < P.total_tiles) ZOS_FRAME_ISSUE(blockIdx.x, 0);
+  __syncthreads();
+  uint32_t phase[2] = {0, 0};
+  int s = 0;
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  for (uint32_t t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+    const uint32_t next = t + gridDim.x;
+    if (threadIdx.x == 0 && next < P.total_tiles) ZOS_FRAME_ISSUE(next, s ^ 1);
+    const TileGeo g = geo[s];
+    if (g.any) {
+      uint32_t spins = 0;
+      while (!mbar_try_wait(&bar[s], phase[s])) {
+        if (++spins > (1u << 24)) break;
+      }
+      phase[s] ^= 1;
+      // ---- phase 1: the footprint, one 2x2 luma block per thread
+      const uint32_t ybase = smem_u32(dyn + (size_t)s * stage_bytes);
+      const uint32_t ubase = ybase + ybox_al, vbase = P.nv12 ? ubase + 1 : ubase + cbox_al;
+      const int offx = g.fx0 - g.bx, offy = g.fy0 - g.by;  // both even
+      const int cbw = P.conv_w >> 1, cbh = P.conv_h >> 1;
+      if (lx < cbw) {
+        for (int byi = ly; byi < cbh; byi += THREADS / 32) {
+          const uint32_t ya = ybase + (uint32_t)((offy + 2 * byi) * P.box_w + offx + 2 * lx);
+          const uint32_t ca = (uint32_t)(((offy >> 1) + byi) * P.cbox_w + (offx >> 1) + lx) * cstep;
+          uint32_t y01, y23, u8, v8;
+          asm("ld.shared.u16 %0, [%1];" : "=r"(y01) : "r"(ya));
+          asm("ld.shared.u16 %0, [%1];" : "=r"(y23) : "r"(ya + (uint32_t)P.box_w));
+          asm("ld.shared.u8 %0, [%1];" : "=r"(u8) : "r"(ubase + ca));
+          asm("ld.shared.u8 %0, [%1];" : "=r"(v8) : "r"(vbase + ca));
+          const float cb = ((float)u8 - 128.0f) * P.csc, cr = ((float)v8 - 128.0f) * P.csc;
+          const uint32_t o = conv_base + (uint32_t)((2 * byi) * P.conv_w + 2 * lx) * 16u;
+          const float4 c00 = convert(P, (float)(y01 & 255u), cb, cr), c10 = convert(P, (float)(y01 >> 8), cb, cr);
+          const float4 c01 = convert(P, (float)(y23 & 255u), cb, cr), c11 = convert(P, (float)(y23 >> 8), cb, cr);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(o), "f"(c00.x), "f"(c00.y), "f"(c00.z), "f"(c00.w) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(o + 16u), "f"(c10.x), "f"(c10.y), "f"(c10.z), "f"(c10.w) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(o + (uint32_t)P.conv_w * 16u), "f"(c01.x), "f"(c01.y), "f"(c01.z), "f"(c01.w) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(o + (uint32_t)P.conv_w * 16u + 16u), "f"(c11.x), "f"(c11.y), "f"(c11.z), "f"(c11.w) : "memory");
+        }
+      }
+      __syncthreads();
+    }
+    // ---- phase 2: sample, composite, pack
+    const int i = g.x0 + lx;
+    if (i < P.dw) {
+      const int kx = i - P.tgt[0];
+      const bool col_in = g.any && kx >= 0 && kx < P.tgt[2];
+      // horizontal taps are the same for the 4 rows this thread produces
+      int xa = 0, xb = 0;
+      float ax = 0.0f;
+      if (col_in) {
+        if (P.sampling == ZOS_SAMPLE_NEAREST) {
+          xa = xb = min(max(P.sel[0] + rect_index(kx, P.sel[2], P.tgt[2]), 0), P.sw - 1);
+        } else {
+          const float px = (float)P.sel[0] + ((float)kx + 0.5f) * P.rx;
+          const float fx = px - 0.5f, x0f = floorf(fx);
+          ax = fx - x0f;
+          const int x0 = (int)x0f;
+          xb = min(max(x0 + 1, 0), P.sw - 1);
+          xa = min(max(x0, 0), P.sw - 1);
+        }
+        xa -= g.fx0; xb -= g.fx0;
+      }
+#pragma unroll 1
+      for (int k = 0; k < TILE / 8; k++) {
+        const int j = g.y0 + ly + 8 * k;
+        if (j >= P.dh) break;
+        const int ky = j - P.tgt[1];
+        const bool covered = col_in && ky >= 0 && ky < P.tgt[3];
+        float4 v = make_float4(0.0f, 0.0f, 1.0f, 1.0f);  // Target::Discard clear colour
+        if (covered) {
+          if (P.sampling == ZOS_SAMPLE_NEAREST) {
+            const int w = min(max(P.sel[1] + rect_index(ky, P.sel[3], P.tgt[3]), 0), P.sh - 1) - g.fy0;
+            v = lds128(conv_base + (uint32_t)(w * P.conv_w + xa) * 16u);
+          } else {
+            const float py = (float)P.sel[1] + ((float)ky + 0.5f) * P.ry;
+            const float fy = py - 0.5f, y0f = floorf(fy);
+            const float ay = fy - y0f;
+            const int y0 = (int)y0f;
+            const int yb = min(max(y0 + 1, 0), P.sh - 1) - g.fy0, ya = min(max(y0, 0), P.sh - 1) - g.fy0;
+            const uint32_t ra = conv_base + (uint32_t)(ya * P.conv_w) * 16u, rb = conv_base + (uint32_t)(yb * P.conv_w) * 16u;
+            const float4 p00 = lds128(ra + xa * 16u), p10 = lds128(ra + xb * 16u), p01 = lds128(rb + xa * 16u), p11 = lds128(rb + xb * 16u);
+#define ZOS_LERP2(c) { float top = fmaf(ax, p10.c - p00.c, p00.c), bot = fmaf(ax, p11.c - p01.c, p01.c); v.c = fmaf(ay, bot - top, top); }
+            ZOS_LERP2(x) ZOS_LERP2(y) ZOS_LERP2(z) ZOS_LERP2(w)
+#undef ZOS_LERP2
+          }
+        }
+        if (P.has_below && !(covered && P.blend == ZOS_BLEND_OVERWRITE)) {
+          const uint32_t w = __ldcs(reinterpret_cast<const uint32_t*>(P.below + (uint64_t)g.frame * P.below_bstride + (uint64_t)j * P.below_pitch + (uint64_t)i * 4));
+          const float4 b = unpack_texel(P.below_fmt, make_uint4(w, 0, 0, 0), T);
+          if (covered) {  // porter_duff(ZOS_BLEND_SRC_OVER, v, b) written out
+            const float wb = b.w * (1.0f - v.w), ao = v.w + wb;
+            const float rcp = ao > 0.0f ? __frcp_rn(ao) : 0.0f;
+            v = make_float4(fmaf(wb, b.x, v.w * v.x) * rcp, fmaf(wb, b.y, v.w * v.y) * rcp, fmaf(wb, b.z, v.w * v.z) * rcp, ao);
+          } else {
+            v = b;
+          }
+        }
+        __stcs(reinterpret_cast<uint32_t*>(P.dst + (uint64_t)g.frame * P.dst_bstride + (uint64_t)j * P.dst_pitch + (uint64_t)i * 4),
+               pack_texel(P.dst_fmt, v, T).x);
+      }
+    }
+    __syncthreads();  // conv and stage s are free again; geo[s ^ 1] (written by thread 0 above) is visible
+    s ^= 1;
+  }
+}
+
+bool native8(const DevImage& im) {
+  return im.block == ZOS_BLOCK_PIXEL && im.bpp == 4 && (im.fmt.storage == ZOS_STORAGE_SRGB8 || im.fmt.storage == ZOS_STORAGE_UNORM8) &&
+         ((uintptr_t)im.p0 % 4) == 0 && (im.pitch % 4) == 0 && (im.bstride % 4) == 0;
+}
+}  // namespace
+
+// The dedicated kernel serves: planar 4:2:0 source with nearest chroma, axis-aligned placement (RECT / SCALE),
+// at most one matrix step on the source side, overwrite or source-over onto native 8-bit images.
+bool frame_pipeline_eligible(zos_ctx* ctx, const DevImage* below, const DevImage& above, const DevImage& dst, const zos_compose_params& cp) {
+  if (ctx->flags & ZOS_CTX_NO_FAST_PATHS) return false;
+  if (!cp.use_tma) return false;
+  if (above.block == ZOS_BLOCK_PIXEL || above.chroma_filter != 0) return false;
+  if (cp.map != ZOS_MAP_RECT && cp.map != ZOS_MAP_SCALE) return false;
+  if (cp.blend != ZOS_BLEND_OVERWRITE && cp.blend != ZOS_BLEND_SRC_OVER) return false;
+  if (cp.n_dst_steps != 0 || cp.n_src_steps > 1 || (cp.n_src_steps == 1 && cp.src_steps[0].kind != ZOS_STEP_MATRIX)) return false;
+  if (cp.dst_origin[0] || cp.dst_origin[1] || cp.src_origin[0] || cp.src_origin[1] || cp.src_full[0] || cp.src_full[1]) return false;
+  if (!native8(dst) || (below && !native8(*below))) return false;
+  if ((above.w & 1) || (above.h & 1)) return false;  // 2x2 blocks: even frame sizes (all video formats)
+  return true;
+}
+
+zos_status launch_frame_pipeline(zos_ctx* ctx, const DevImage* below, const DevImage& above, const DevImage& dst,
+                                 const zos_compose_params& cp, uint32_t batch, bool* handled) {
+  *handled = false;
+  FrameParams P;
+  memset(&P, 0, sizeof P);
+  P.sw = above.w; P.sh = above.h; P.nv12 = above.block == ZOS_BLOCK_YUV420_NV12;
+  P.yoff = above.yoff; P.ysc = above.ysc; P.csc = above.csc; P.r_cr = above.r_cr; P.b_cb = above.b_cb; P.g_cr = above.g_cr; P.g_cb = above.g_cb;
+  P.transfer = above.fmt.transfer;
+  P.nmat = (int32_t)cp.n_src_steps;
+  if (P.nmat) memcpy(P.m, cp.src_steps[0].m, sizeof P.m);
+  for (int k = 0; k < 4; k++) { P.sel[k] = cp.sel[k]; P.tgt[k] = cp.tgt[k]; }
+  if (cp.map == ZOS_MAP_SCALE) {
+    P.sel[0] = P.sel[1] = 0; P.sel[2] = above.w; P.sel[3] = above.h;
+    P.tgt[0] = P.tgt[1] = 0; P.tgt[2] = dst.w; P.tgt[3] = dst.h;
+  }
+  P.rx = (float)P.sel[2] / (float)(P.tgt[2] > 0 ? P.tgt[2] : 1);
+  P.ry = (float)P.sel[3] / (float)(P.tgt[3] > 0 ? P.tgt[3] : 1);
+  P.sampling = cp.sampling; P.blend = cp.blend;
+  P.has_below = below != nullptr;
+  if (below) { P.below = below->p0; P.below_pitch = below->pitch; P.below_bstride = below->bstride; P.below_fmt = below->fmt; }
+  P.dst = dst.p0; P.dst_pitch = dst.pitch; P.dst_bstride = dst.bstride; P.dst_fmt = dst.fmt; P.dw = dst.w; P.dh = dst.h;
+  P.tiles_x = (dst.w + TILE - 1) / TILE; P.tiles_y = (dst.h + TILE - 1) / TILE;
+  uint64_t total = (uint64_t)P.tiles_x * P.tiles_y * batch;
+  if (total == 0 || total >= (1ull << 31)) return ZOS_OK;
+  P.total_tiles = (uint32_t)total;
+  P.div_tx = make_fastdiv(P.tiles_x); P.div_ty = make_fastdiv(P.tiles_y);
+  // footprint of a 32-pixel run: taps from floor(min - 0.5) (rounded down to even) to floor(max - 0.5) + 1
+  P.conv_w = ((int)ceilf((TILE - 1) * P.rx) + 6) & ~1;
+  P.conv_h = ((int)ceilf((TILE - 1) * P.ry) + 6) & ~1;
+  if (P.conv_w > 64 || P.conv_h > 96) return ZOS_OK;  // strong minification: the general kernel
+  P.box_w = (P.conv_w + 31 + 31) & ~31;
+  P.box_h = P.conv_h;
+  P.cbox_w = P.box_w / 2; P.cbox_h = P.box_h / 2;
+  const int cstep = P.nv12 ? 2 : 1;
+  size_t ybox_al = ((size_t)P.box_w * P.box_h + 127) & ~(size_t)127, cbox_al = ((size_t)P.cbox_w * P.cbox_h * cstep + 127) & ~(size_t)127;
+  size_t stage = ybox_al + (P.nv12 ? 1 : 2) * cbox_al;
+  size_t smem = 2 * stage + (size_t)P.conv_w * P.conv_h * 16;
+  if (smem > 160 * 1024) return ZOS_OK;
+  TensorMaps M;
+  memset(&M, 0, sizeof M);
+  const uint64_t cw = (above.w + 1) / 2, ch = (above.h + 1) / 2;
+  bool ok = make_map(ctx, &M.m0, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, above.p0, above.w, above.h, above.pitch, batch, above.bstride, P.box_w, P.box_h);
+  if (ok && P.nv12) ok = make_map(ctx, &M.m1, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, above.p1, cw, ch, above.cpitch, batch, above.cbstride, P.cbox_w, P.cbox_h);
+  if (ok && !P.nv12)
+    ok = make_map(ctx, &M.m1, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, above.p1, cw, ch, above.cpitch, batch, above.cbstride, P.cbox_w, P.cbox_h) &&
+         make_map(ctx, &M.m2, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, above.p2, cw, ch, above.cpitch, batch, above.cbstride, P.cbox_w, P.cbox_h);
+  if (!ok) return ZOS_OK;
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(k_frame_pipeline, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr_set = true; }
+  int per_sm = (int)((220 * 1024) / (smem + sizeof(Tables) + 2048));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 3 ? 3 : per_sm);
+  uint64_t cap = (uint64_t)ctx->sm_count * per_sm;
+  int grid = (int)(total < cap ? total : cap);
+  k_frame_pipeline<<<grid, THREADS, smem, ctx->stream>>>(P, M);
+  ctx->launches++;
+  *handled = true;
+  return check_cuda(ctx, cudaGetLastError(), "k_frame_pipeline launch");
+}
+
+}  // namespace zos

@@ -14,9 +14,8 @@
 // an mbarrier), double buffered so the next tile's box lands while the current tile is computed;
 // out-of-image parts of the box are zero-filled by the TMA unit and never read (taps are clamped
 // to the image first).  Tiles whose footprint does not fit the box fall back to direct loads.
-#include <cuda.h>
-
 #include "colorops.cuh"
+#include "tma.cuh"
 #include "zos_internal.h"
 
 namespace zos {
@@ -47,40 +46,10 @@ struct GatherParams {
   int32_t align_x;        // box origin x is rounded down to this many texels: the TMA source address must be 16-byte aligned
   StepList src_steps, dst_steps;
 };
-struct TensorMaps {
-  CUtensorMap m0, m1, m2;
-};
 
 __device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv& f) {
   uint32_t t = __umulhi(n, f.m);
   return f.l == 0 ? n : (t + ((n - t) >> 1)) >> (f.l - 1);
-}
-
-// ---------------- mbarrier / TMA primitives ----------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
-      : "memory");
 }
 
 // ---------------- tile geometry ----------------
@@ -516,35 +485,6 @@ bool gather_take_timeout_flag() {
   return v != 0;
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode(zos_ctx* ctx) {
-  if (!ctx->encode_tiled) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      ctx->encode_tiled = fn;
-  }
-  return (EncodeTiledFn)ctx->encode_tiled;
-}
-
-static bool make_map(zos_ctx* ctx, CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, void* base, uint64_t w_elems, uint64_t h,
-                     uint64_t pitch, uint64_t frames, uint64_t frame_stride, uint32_t box_w_elems, uint32_t box_h) {
-  EncodeTiledFn enc = get_encode(ctx);
-  if (!enc) return false;
-  if (((uintptr_t)base & 15) || (pitch & 15) || (frame_stride & 15)) return false;
-  if (box_w_elems > 256 || box_h > 256 || ((uint64_t)box_w_elems * elem_bytes) % 16) return false;
-  cuuint64_t dims[3] = {w_elems, h, frames};
-  cuuint64_t strides[2] = {pitch, frames > 1 ? frame_stride : pitch * h};
-  cuuint32_t box[3] = {box_w_elems, box_h, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(m, dt, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
-}
-
 static bool img_vec_ok(const DevImage& im) {
   return ((uintptr_t)im.p0 % 16) == 0 && (im.pitch % 16) == 0 && (im.bstride % 16) == 0 &&
          im.pitch >= (uint64_t)((im.w + 3) / 4) * 4 * im.bpp && (im.bpp == 4 || im.bpp == 8);
@@ -553,6 +493,11 @@ static bool img_vec_ok(const DevImage& im) {
 zos_status launch_gather(zos_ctx* ctx, const DevImage* below, const DevImage& above, const DevImage& dst,
                          const zos_compose_params& cp, uint32_t batch) {
   if (dst.block != ZOS_BLOCK_PIXEL) return fail(ctx, ZOS_ERR_UNSUPPORTED, "planar YUV destinations are not implemented yet");
+  if (frame_pipeline_eligible(ctx, below, above, dst, cp)) {  // the dedicated video-frame kernel (frame_pipeline.cu)
+    bool handled = false;
+    zos_status st = launch_frame_pipeline(ctx, below, above, dst, cp, batch, &handled);
+    if (handled || st != ZOS_OK) return st;
+  }
   if (below && below->block != ZOS_BLOCK_PIXEL) return fail(ctx, ZOS_ERR_UNSUPPORTED, "planar `below`");
   GatherParams P;
   memset(&P, 0, sizeof P);

@@ -72,6 +72,9 @@ zos_status launch_rowwise_u8(zos_ctx* ctx, const DevImage* below, const DevImage
 bool rowwise_can_compose(const DevImage& below, const DevImage& above, const DevImage& dst, const zos_compose_params& cp);
 zos_status launch_gather(zos_ctx* ctx, const DevImage* below, const DevImage& above, const DevImage& dst,
                          const zos_compose_params& cp, uint32_t batch);
+bool frame_pipeline_eligible(zos_ctx* ctx, const DevImage* below, const DevImage& above, const DevImage& dst, const zos_compose_params& cp);
+zos_status launch_frame_pipeline(zos_ctx* ctx, const DevImage* below, const DevImage& above, const DevImage& dst,
+                                 const zos_compose_params& cp, uint32_t batch, bool* handled);
 zos_status launch_generate(zos_ctx* ctx, const DevImage& dst, const float* p, uint32_t batch, bool solid);
 zos_status launch_box3(zos_ctx* ctx, const DevImage& src, const DevImage& dst, const float* m, uint32_t batch);
 zos_status launch_palette(zos_ctx* ctx, const DevImage& pal, const DevImage& idx, const DevImage& dst, const float* xc,
