@@ -193,7 +193,8 @@ enum { /* what happens where `above` lands */
   ZOS_BLEND_OVERWRITE = -1, /* blend: None (encoder.rs:1493): RGBA replaced -- inscribe / affine */
   ZOS_BLEND_CLEAR = 0, ZOS_BLEND_SRC = 1, ZOS_BLEND_DST = 2, ZOS_BLEND_SRC_OVER = 3, ZOS_BLEND_DST_OVER = 4,
   ZOS_BLEND_SRC_IN = 5, ZOS_BLEND_DST_IN = 6, ZOS_BLEND_SRC_OUT = 7, ZOS_BLEND_DST_OUT = 8, ZOS_BLEND_SRC_ATOP = 9,
-  ZOS_BLEND_DST_ATOP = 10, ZOS_BLEND_XOR = 11 /* Porter-Duff, linear light (Blend::Alpha = SRC_OVER) */
+  ZOS_BLEND_DST_ATOP = 10, ZOS_BLEND_XOR = 11, /* Porter-Duff, linear light (Blend::Alpha = SRC_OVER) */
+  ZOS_BLEND_INJECT = 12 /* inject.frag:20-25: mix(below, vec4(dot(above, inject_color)), inject_mix) */
 };
 typedef struct zos_compose_params {
   int32_t map;       /* ZOS_MAP_* */
@@ -208,6 +209,7 @@ typedef struct zos_compose_params {
    * source starting at src_origin.  sel / tgt / inv stay in FULL-image coordinates, so a windowed launch
    * writes exactly the bytes of the whole-image launch. */
   int32_t dst_origin[2], src_origin[2], src_full[2];
+  float inject_mix[4], inject_color[4]; /* ZOS_BLEND_INJECT (shaders/inject.rs:28-31) */
   uint32_t n_src_steps, n_dst_steps;
   zos_step src_steps[ZOS_MAX_STEPS]; /* applied to every `above` tap after unpack */
   zos_step dst_steps[ZOS_MAX_STEPS]; /* applied to the composed value before pack */

@@ -66,6 +66,9 @@ int32_t zosh_cb_bilinear(zosh_cb* cb, const zos_desc* desc, const float p[24], i
 int32_t zosh_cb_solid_rgba(zosh_cb* cb, const zos_desc* desc, const float color[4], int32_t* reg);    /* command.rs:1524 */
 int32_t zosh_cb_derivative(zosh_cb* cb, int32_t src, uint32_t method, uint32_t height_direction, int32_t* reg); /* :1493 */
 int32_t zosh_cb_palette(zosh_cb* cb, int32_t palette, int32_t indices, const float xc[4], const float yc[4], int32_t* reg); /* :1442 */
+/* channel: 0 R, 1 G, 2 B, 3 Alpha (ColorChannel); extract = full copy whose destination texel keeps one channel */
+int32_t zosh_cb_extract(zosh_cb* cb, int32_t src, uint32_t channel, int32_t* reg);                       /* command.rs:1221 */
+int32_t zosh_cb_inject(zosh_cb* cb, int32_t below, uint32_t channel, int32_t above, int32_t* reg);      /* command.rs:1360 */
 int32_t zosh_cb_with_knob(zosh_cb* cb);  /* the NEXT operation gets a knob; returns its 1-based id (command.rs:1865-1874) */
 
 /* Linker::compile (command.rs:2069): liveness + emission of the High-like op list */

@@ -292,3 +292,24 @@ def test_crop_quirk(pool, images, fixtures):  # command.rs:971-978: output keeps
     img, _ = run_once_with_output(c, pool, [(inp, bg.key())], output)
     exp = O.crop(oracle_image(bg.descriptor(), fixtures["background"]), (100, 50, 356, 306))
     assert np.array_equal(img.as_bytes(), exp.data.reshape(-1))
+
+
+def test_run_swap(pool, images, fixtures):  # tests/blend.rs:426-447: extract R and G, inject them swapped
+    bg, _ = images
+    c = CommandBuffer()
+    inp = c.input(bg.descriptor())
+    channel_r = c.extract(inp, Z.ColorChannel.R)
+    channel_g = c.extract(inp, Z.ColorChannel.G)
+    assert c.describe_reg(channel_r).texel.parts == SampleParts.R and c.describe_reg(channel_r).texel.bits == SampleBits.UInt8
+    intermediate = c.inject(inp, Z.ColorChannel.G, channel_r)
+    swapped = c.inject(intermediate, Z.ColorChannel.R, channel_g)
+    output, _ = c.output(swapped)
+    img, _ = run_once_with_output(c, pool, [(inp, bg.key())], output)
+    assert O.blockhash256(rgba(img)) in hashes()["swapped"]
+    ob = oracle_image(bg.descriptor(), fixtures["background"])
+    exp = O.inject(O.inject(ob, "G", O.extract(ob, "R")), "R", O.extract(ob, "G"))
+    d = np.abs(img.as_bytes().astype(int) - exp.data.reshape(-1).astype(int))
+    assert d.max() <= 1 and np.mean(d == 0) > 0.99  # the single-channel registers pack through pow (sRGB OETF)
+    from zosimos_b200.command import CommandError
+    with pytest.raises(CommandError):  # `above` must be a single-channel image of the matching texel
+        c.inject(inp, Z.ColorChannel.R, inp)

@@ -25,6 +25,7 @@ MAP_RECT, MAP_AFFINE, MAP_GRID8, MAP_SCALE = 0, 1, 2, 3
 BLEND_OVERWRITE = -1
 (BLEND_CLEAR, BLEND_SRC, BLEND_DST, BLEND_SRC_OVER, BLEND_DST_OVER, BLEND_SRC_IN, BLEND_DST_IN, BLEND_SRC_OUT,
  BLEND_DST_OUT, BLEND_SRC_ATOP, BLEND_DST_ATOP, BLEND_XOR) = range(12)
+BLEND_INJECT = 12
 # program ops
 OP_INPUT, OP_OUTPUT, OP_PIXEL, OP_COMPOSE, OP_COPY, OP_GENERATE, OP_BOX3, OP_PALETTE = range(1, 9)
 FUSE_EXACT, FUSE_WIDE, FUSE_NONE = 0, 1, 2
@@ -56,6 +57,7 @@ class ZosComposeParams(C.Structure):
     _fields_ = [("map", C.c_int32), ("sampling", C.c_int32), ("blend", C.c_int32), ("use_tma", C.c_int32),
                 ("sel", C.c_int32 * 4), ("tgt", C.c_int32 * 4), ("inv", C.c_float * 9),
                 ("dst_origin", C.c_int32 * 2), ("src_origin", C.c_int32 * 2), ("src_full", C.c_int32 * 2),
+                ("inject_mix", C.c_float * 4), ("inject_color", C.c_float * 4),
                 ("n_src_steps", C.c_uint32), ("n_dst_steps", C.c_uint32),
                 ("src_steps", ZosStep * ZOS_MAX_STEPS), ("dst_steps", ZosStep * ZOS_MAX_STEPS)]
 

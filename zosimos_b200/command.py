@@ -71,6 +71,8 @@ _HOST_SIGNATURES = {
     "zosh_cb_solid_rgba": (C.c_int32, [_P, C.POINTER(_ffi.ZosDesc), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "zosh_cb_derivative": (C.c_int32, [_P, C.c_int32, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32)]),
     "zosh_cb_palette": (C.c_int32, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "zosh_cb_extract": (C.c_int32, [_P, C.c_int32, C.c_uint32, C.POINTER(C.c_int32)]),
+    "zosh_cb_inject": (C.c_int32, [_P, C.c_int32, C.c_uint32, C.c_int32, C.POINTER(C.c_int32)]),
     "zosh_cb_with_knob": (C.c_int32, [_P]),
     "zosh_compile": (C.c_int32, [_P, C.POINTER(_P)]),
     "zosh_program_free": (None, [_P]),
@@ -370,11 +372,19 @@ class CommandBuffer:
         out = C.c_int32()
         return self._reg(host_lib().zosh_cb_palette(self._h, palette.index, indices.index, xc, yc, C.byref(out)), out)
 
+    _CHANNEL = {ColorChannel.R: 0, ColorChannel.G: 1, ColorChannel.B: 2, ColorChannel.Alpha: 3}
+
     def extract(self, src: Register, channel: ColorChannel) -> Register:
-        raise CommandError(CommandErrorKind.Unimplemented, "extract: scheduled next (SURVEY.md 8f-2)")
+        if channel not in self._CHANNEL:
+            raise CommandError(CommandErrorKind.Other, "extract: channel")
+        out = C.c_int32()
+        return self._reg(host_lib().zosh_cb_extract(self._h, src.index, self._CHANNEL[channel], C.byref(out)), out)
 
     def inject(self, below: Register, channel: ColorChannel, above: Register) -> Register:
-        raise CommandError(CommandErrorKind.Unimplemented, "inject: scheduled next (SURVEY.md 8f-2)")
+        if channel not in self._CHANNEL:
+            raise CommandError(CommandErrorKind.Other, "inject: channel")
+        out = C.c_int32()
+        return self._reg(host_lib().zosh_cb_inject(self._h, below.index, self._CHANNEL[channel], above.index, C.byref(out)), out)
 
 
 class Linker:

@@ -137,4 +137,11 @@ __device__ __forceinline__ float4 porter_duff(int mode, const float4& s, const f
   return o;
 }
 
+// inject.frag:20-25: mix(bg, vec4(dot(fg, color)), select); mix(a, b, t) = a*(1-t) + b*t
+__device__ __forceinline__ float4 inject_blend(const float* inj, const float4& fg, const float4& bg) {
+  const float d = fg.x * inj[4] + fg.y * inj[5] + fg.z * inj[6] + fg.w * inj[7];
+  return make_float4(bg.x * (1.0f - inj[0]) + d * inj[0], bg.y * (1.0f - inj[1]) + d * inj[1], bg.z * (1.0f - inj[2]) + d * inj[2],
+                     bg.w * (1.0f - inj[3]) + d * inj[3]);
+}
+
 }  // namespace zos

@@ -32,6 +32,7 @@ struct GatherParams {
   int32_t sel[4], tgt[4];
   float inv[6];
   float rx, ry;  // sel.w / tgt.w, sel.h / tgt.h (bilinear rect mapping)
+  float inj[8];  // ZOS_BLEND_INJECT: mix, color
   // row-band / tile sharding: dst holds the window of the full destination that starts
   // at (dox, doy); `above` holds the window of the full sfw x sfh source that starts at (sox, soy).
   // All mapping arithmetic uses FULL-image coordinates, so a windowed run gives the whole run's bytes.
@@ -376,7 +377,7 @@ __device__ __forceinline__ void compute_tile(const GatherParams& P, const TileIn
     }
     if (P.has_below && !(covered && P.blend == ZOS_BLEND_OVERWRITE)) {
       float4 b = unpack_texel(P.below.fmt, load_px(P.below, ti.frame, i, j), T);
-      v = covered ? porter_duff(P.blend, v, b) : b;
+      v = !covered ? b : P.blend == ZOS_BLEND_INJECT ? inject_blend(P.inj, v, b) : porter_duff(P.blend, v, b);
     }
     apply_steps(P.dst_steps, v, T);
     store_px(P.dst, ti.frame, i, j, pack_texel(P.dst.fmt, v, T));
@@ -513,6 +514,7 @@ zos_status launch_gather(zos_ctx* ctx, const DevImage* below, const DevImage& ab
     if (cp.map == ZOS_MAP_SCALE) P.map = ZOS_MAP_RECT;
   }
   for (int k = 0; k < 6; k++) P.inv[k] = cp.inv[k];
+  memcpy(P.inj, cp.inject_mix, 16); memcpy(P.inj + 4, cp.inject_color, 16);
   P.dox = cp.dst_origin[0]; P.doy = cp.dst_origin[1]; P.sox = cp.src_origin[0]; P.soy = cp.src_origin[1];
   P.sfw = cp.src_full[0] > 0 ? cp.src_full[0] : above.w; P.sfh = cp.src_full[1] > 0 ? cp.src_full[1] : above.h;
   const bool windowed = P.dox || P.doy || P.sox || P.soy || P.sfw != above.w || P.sfh != above.h;
@@ -601,7 +603,7 @@ zos_status launch_gather(zos_ctx* ctx, const DevImage* below, const DevImage& ab
            im.fmt.transfer == ZOS_TRANSFER_LINEAR && (im.fmt.parts == ZOS_PARTS_RGBA || im.fmt.parts == ZOS_PARTS_LCHA || im.fmt.parts == ZOS_PARTS_LABA) &&
            ((uintptr_t)im.p0 % 8) == 0 && (im.pitch % 8) == 0 && (im.bstride % 8) == 0;
   };
-  const bool fast = !(ctx->flags & ZOS_CTX_NO_FAST_PATHS) && P.map != ZOS_MAP_GRID8 && cp.n_src_steps == 0 && cp.n_dst_steps == 0 &&
+  const bool fast = !(ctx->flags & ZOS_CTX_NO_FAST_PATHS) && P.map != ZOS_MAP_GRID8 && cp.blend != ZOS_BLEND_INJECT && cp.n_src_steps == 0 && cp.n_dst_steps == 0 &&
                     plain_f16(above) && plain_f16(dst) && (!below || plain_f16(*below));
   cudaError_t e;
   if (tma) {

@@ -429,6 +429,63 @@ int32_t zosh_cb_palette(zosh_cb* cb, int32_t palette, int32_t indices, const flo
   return push(cb, op, reg);
 }
 
+// TexelExt::channel_texel (buffer.rs:57-62): same bit depth per channel, parts = the single channel
+static bool channel_texel(const zos_desc& s, uint32_t channel, zos_desc& d) {
+  d = s;
+  switch (s.bits) {
+    case ZOS_BITS_UINT8X4: case ZOS_BITS_UINT8X3: case ZOS_BITS_UINT8X2: d.bits = ZOS_BITS_UINT8; break;
+    case ZOS_BITS_UINT16X4: case ZOS_BITS_UINT16X3: case ZOS_BITS_UINT16X2: d.bits = ZOS_BITS_UINT16; break;
+    default: return false;
+  }
+  switch (channel) {
+    case 0: d.parts = ZOS_PARTS_R; break;
+    case 1: d.parts = ZOS_PARTS_G; break;
+    case 2: d.parts = ZOS_PARTS_B; break;
+    case 3: d.parts = ZOS_PARTS_A; break;
+    default: return false;
+  }
+  fix_layout(d);
+  return true;
+}
+
+int32_t zosh_cb_extract(zosh_cb* cb, int32_t src, uint32_t channel, int32_t* reg) {
+  if (!cb || !valid_reg(cb, src)) return err(ZOSH_ERR_OTHER, "bad register");
+  zos_desc d;
+  if (cb->ops[src].desc.block != ZOS_BLOCK_PIXEL || !channel_texel(cb->ops[src].desc, channel, d)) return err(ZOSH_ERR_OTHER, "extract: no such channel texel");  // :1232-1235
+  if (channel > 2) return err(ZOSH_ERR_OTHER, "extract: channel position");  // ChannelPosition::new knows R, G, B only (buffer.rs:186-194)
+  // a full copy; the channel is picked when the result is packed into the single-channel texel (command.rs:2578-2597)
+  return push(cb, new_op(cb, ZOS_OP_PIXEL, src, -1, d), reg);
+}
+
+int32_t zosh_cb_inject(zosh_cb* cb, int32_t below, uint32_t channel, int32_t above, int32_t* reg) {
+  if (!cb || !valid_reg(cb, below) || !valid_reg(cb, above)) return err(ZOSH_ERR_OTHER, "bad register");
+  const zos_desc& b = cb->ops[below].desc;
+  const zos_desc& a = cb->ops[above].desc;
+  zos_desc expect;
+  if (b.block != ZOS_BLOCK_PIXEL || !channel_texel(b, channel, expect)) return err(ZOSH_ERR_OTHER, "inject: no such channel texel");  // :1392-1394
+  if (channel > 2) return err(ZOSH_ERR_OTHER, "inject: channel position");
+  float color[4] = {0, 0, 0, 0};
+  switch (a.parts) {  // TexelExt::channel_weight_vec4, buffer.rs:64-81
+    case ZOS_PARTS_R: case ZOS_PARTS_LUMA: color[0] = 1; break;
+    case ZOS_PARTS_G: color[1] = 1; break;
+    case ZOS_PARTS_B: color[2] = 1; break;
+    case ZOS_PARTS_A: color[3] = 1; break;
+    default: return err(ZOSH_ERR_CONFLICTING_TYPES, "inject: `above` must be a single-channel image");  // :1396-1405, 1414-1416
+  }
+  // everything but the sample parts must match the expected channel texel (command.rs:1407-1427)
+  if (a.bits != expect.bits || a.color != expect.color || a.transfer != expect.transfer || a.primaries != expect.primaries ||
+      a.whitepoint != expect.whitepoint || a.width != b.width || a.height != b.height)
+    return err(ZOSH_ERR_CONFLICTING_TYPES, "inject: `above` does not match the channel texel of `below`");
+  zos_op op = new_op(cb, ZOS_OP_COMPOSE, below, above, b);
+  compose_defaults(op.compose);
+  op.compose.blend = ZOS_BLEND_INJECT;
+  op.compose.sel[2] = (int32_t)a.width; op.compose.sel[3] = (int32_t)a.height;
+  op.compose.tgt[2] = (int32_t)a.width; op.compose.tgt[3] = (int32_t)a.height;
+  op.compose.inject_mix[channel] = 1.0f;
+  memcpy(op.compose.inject_color, color, sizeof color);
+  return push(cb, op, reg);
+}
+
 int32_t zosh_compile(const zosh_cb* cb, zosh_program** out) {
   if (!cb || !out) return err(ZOSH_ERR_OTHER, "null argument");
   // liveness (command.rs:2216-2291): only operations that reach an output are emitted

@@ -23,6 +23,7 @@ struct RowParams {
   int32_t has_below, has_above;
   int32_t tx, ty, aw, ah;  // placement of `above` on the destination
   int32_t blend;           // ZOS_BLEND_*
+  float inj[8];            // ZOS_BLEND_INJECT: mix, color
   uint32_t groups_per_row;
   uint32_t total_groups;   // groups_per_row * h * batch
   FastDiv div_gpr, div_h;
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(256) k_rowwise(const __grid_constant__ RowPara
         if (i < ncov) {
           float4 a = unpack_texel(P.above.fmt, w[i], T);
           apply_steps(P.src_steps, a, T);
-          v[i] = P.blend == ZOS_BLEND_OVERWRITE ? a : porter_duff(P.blend, a, v[i]);
+          v[i] = P.blend == ZOS_BLEND_OVERWRITE ? a : P.blend == ZOS_BLEND_INJECT ? inject_blend(P.inj, a, v[i]) : porter_duff(P.blend, a, v[i]);
         }
       }
     }
@@ -171,6 +172,7 @@ zos_status launch_rowwise(zos_ctx* ctx, const DevImage* below, const DevImage* a
   if (cp) {
     P.tx = cp->tgt[0]; P.ty = cp->tgt[1]; P.aw = cp->tgt[2]; P.ah = cp->tgt[3];
     P.blend = cp->blend;
+    memcpy(P.inj, cp->inject_mix, 16); memcpy(P.inj + 4, cp->inject_color, 16);
     P.src_steps.n = cp->n_src_steps;
     for (uint32_t i = 0; i < cp->n_src_steps; i++) P.src_steps.s[i] = cp->src_steps[i];
     P.dst_steps.n = cp->n_dst_steps;

@@ -401,7 +401,7 @@ zos_status zos_compose(zos_ctx* ctx, const zos_image* below, const zos_image* ab
   if (below && (b.w != d.w || b.h != d.h)) return fail(ctx, ZOS_ERR_TYPE, "compose: `below` and dst differ in size");
   if (cp->map < ZOS_MAP_RECT || cp->map > ZOS_MAP_SCALE) return fail(ctx, ZOS_ERR_INVALID, "compose: bad map %d", cp->map);
   if (cp->sampling != ZOS_SAMPLE_NEAREST && cp->sampling != ZOS_SAMPLE_BILINEAR) return fail(ctx, ZOS_ERR_INVALID, "compose: bad sampling");
-  if (cp->blend < ZOS_BLEND_OVERWRITE || cp->blend > ZOS_BLEND_XOR) return fail(ctx, ZOS_ERR_INVALID, "compose: bad blend mode");
+  if (cp->blend < ZOS_BLEND_OVERWRITE || cp->blend > ZOS_BLEND_INJECT) return fail(ctx, ZOS_ERR_INVALID, "compose: bad blend mode");
   if (cp->blend != ZOS_BLEND_OVERWRITE && !below) return fail(ctx, ZOS_ERR_INVALID, "compose: blending needs `below`");
   if (cp->map == ZOS_MAP_RECT && (cp->sel[2] <= 0 || cp->sel[3] <= 0 || cp->tgt[2] <= 0 || cp->tgt[3] <= 0))
     return fail(ctx, ZOS_ERR_INVALID, "compose: empty selection / target");
