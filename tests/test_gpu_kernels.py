@@ -557,3 +557,26 @@ def test_fused_frame_pipeline(ctx, nv12, chroma_filter):
         exp = O.encode(oracle_desc(od), canvas).data
         assert max_lsb(outs[0][f], exp) <= 1
         assert np.mean(outs[0][f] == exp) > 0.99
+
+
+@pytest.mark.parametrize("bits,parts,n", [(SampleBits.UInt16, SampleParts.Luma, 16), (SampleBits.UInt1010102, SampleParts.RgbA, 10),
+                                         (SampleBits.UInt565, SampleParts.Rgb, 6), (SampleBits.UInt4x4, SampleParts.RgbA, 4)])
+def test_field_division_exact_all_codes(ctx, bits, parts, n):
+    """value / (2^n - 1) is computed as reciprocal multiply + one Newton step on the device; it must equal
+    the oracle's IEEE division for EVERY code of the field (all 65536 for 16-bit)."""
+    count = 1 << n
+    w, h = 256, max(count // 256, 1)
+    codes = np.arange(w * h, dtype=np.uint32) % count
+    if bits == SampleBits.UInt16:
+        data = codes.astype("<u2").view(np.uint8).reshape(h, w * 2)
+    elif bits == SampleBits.UInt1010102:
+        data = (codes | (codes << 10) | (codes << 20) | ((codes & 3) << 30)).astype("<u4").view(np.uint8).reshape(h, w * 4)
+    elif bits == SampleBits.UInt565:
+        data = ((codes & 31) | ((codes & 63) << 5) | ((codes & 31) << 11)).astype("<u2").view(np.uint8).reshape(h, w * 2)
+    else:
+        data = ((codes & 15) * 0x1111).astype("<u2").view(np.uint8).reshape(h, w * 2)
+    d = zdesc(w, h, Texel(Z.Block.Pixel, bits, parts), Color.Scalars(Transfer.Linear))
+    f32 = zdesc(w, h, Texel.new_f32(), Color.Scalars(Transfer.Linear))
+    got = run_chain(ctx, d, data, f32, []).view(np.float32)
+    exp = O.encode(oracle_desc(f32), O.decode(oracle_image(d, data))).data.view(np.float32)
+    assert np.array_equal(got, exp)

@@ -42,7 +42,7 @@ __device__ __forceinline__ float sr_nl_inv(float v) {
   return vp * vp * vp;
 }
 
-static __device__ __noinline__ float4 apply_step_slow(const zos_step* sp, float4 v, const Tables* Tp) {
+static __device__ ZOS_SLOW_ATTR float4 apply_step_slow(const zos_step* sp, float4 v, const Tables* Tp) {
   const zos_step& s = *sp;
   const Tables& T = *Tp;
   switch (s.kind) {

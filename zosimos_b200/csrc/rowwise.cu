@@ -9,6 +9,8 @@
 // texel is read once, every destination texel written once.
 #include <stdlib.h>
 
+// the generic codec is inlined here (one pixel per thread and iteration keeps the code size in check)
+#define ZOS_SLOW_ATTR __forceinline__
 #include "colorops.cuh"
 #include "zos_internal.h"
 
@@ -35,54 +37,26 @@ __device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv& f) {
   return f.l == 0 ? n : (t + ((n - t) >> 1)) >> (f.l - 1);
 }
 
-// 4 consecutive texels starting at a (4*BPP)-aligned address
-__device__ __forceinline__ void load4(const int BPP, const uint8_t* p, uint4 (&w)[4]) {
-  if (BPP == 1) {
-    uint32_t u = __ldcs(reinterpret_cast<const uint32_t*>(p));
-#pragma unroll
-    for (int i = 0; i < 4; i++) w[i] = make_uint4((u >> (8 * i)) & 255u, 0, 0, 0);
-  } else if (BPP == 2) {
-    uint2 u = __ldcs(reinterpret_cast<const uint2*>(p));
-    w[0] = make_uint4(u.x & 65535u, 0, 0, 0); w[1] = make_uint4(u.x >> 16, 0, 0, 0);
-    w[2] = make_uint4(u.y & 65535u, 0, 0, 0); w[3] = make_uint4(u.y >> 16, 0, 0, 0);
-  } else if (BPP == 4) {
-    uint4 u = __ldcs(reinterpret_cast<const uint4*>(p));
-    w[0] = make_uint4(u.x, 0, 0, 0); w[1] = make_uint4(u.y, 0, 0, 0);
-    w[2] = make_uint4(u.z, 0, 0, 0); w[3] = make_uint4(u.w, 0, 0, 0);
-  } else if (BPP == 8) {
-    uint4 a = __ldcs(reinterpret_cast<const uint4*>(p)), b = __ldcs(reinterpret_cast<const uint4*>(p) + 1);
-    w[0] = make_uint4(a.x, a.y, 0, 0); w[1] = make_uint4(a.z, a.w, 0, 0);
-    w[2] = make_uint4(b.x, b.y, 0, 0); w[3] = make_uint4(b.z, b.w, 0, 0);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; i++) w[i] = __ldcs(reinterpret_cast<const uint4*>(p) + i);
-  }
+__device__ __forceinline__ uint4 load1(const int BPP, const uint8_t* p) {
+  uint4 w = make_uint4(0, 0, 0, 0);
+  if (BPP == 1) w.x = *p;
+  else if (BPP == 2) w.x = *reinterpret_cast<const uint16_t*>(p);
+  else if (BPP == 4) w.x = __ldcs(reinterpret_cast<const uint32_t*>(p));
+  else if (BPP == 8) { uint2 t = __ldcs(reinterpret_cast<const uint2*>(p)); w.x = t.x; w.y = t.y; }
+  else w = __ldcs(reinterpret_cast<const uint4*>(p));
+  return w;
 }
 __device__ __forceinline__ void store1(const int BPP, uint8_t* p, const uint4& w) {
   if (BPP == 1) *p = (uint8_t)w.x;
   else if (BPP == 2) *reinterpret_cast<uint16_t*>(p) = (uint16_t)w.x;
-  else if (BPP == 4) *reinterpret_cast<uint32_t*>(p) = w.x;
-  else if (BPP == 8) *reinterpret_cast<uint2*>(p) = make_uint2(w.x, w.y);
-  else *reinterpret_cast<uint4*>(p) = w;
-}
-__device__ __forceinline__ void store4(const int BPP, uint8_t* p, const uint4 (&w)[4]) {
-  if (BPP == 1) {
-    __stcs(reinterpret_cast<uint32_t*>(p), (w[0].x & 255u) | ((w[1].x & 255u) << 8) | ((w[2].x & 255u) << 16) | (w[3].x << 24));
-  } else if (BPP == 2) {
-    __stcs(reinterpret_cast<uint2*>(p), make_uint2((w[0].x & 65535u) | (w[1].x << 16), (w[2].x & 65535u) | (w[3].x << 16)));
-  } else if (BPP == 4) {
-    __stcs(reinterpret_cast<uint4*>(p), make_uint4(w[0].x, w[1].x, w[2].x, w[3].x));
-  } else if (BPP == 8) {
-    __stcs(reinterpret_cast<uint4*>(p), make_uint4(w[0].x, w[0].y, w[1].x, w[1].y));
-    __stcs(reinterpret_cast<uint4*>(p) + 1, make_uint4(w[2].x, w[2].y, w[3].x, w[3].y));
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; i++) __stcs(reinterpret_cast<uint4*>(p) + i, w[i]);
-  }
+  else if (BPP == 4) __stcs(reinterpret_cast<uint32_t*>(p), w.x);
+  else if (BPP == 8) __stcs(reinterpret_cast<uint2*>(p), make_uint2(w.x, w.y));
+  else __stcs(reinterpret_cast<uint4*>(p), w);
 }
 
-// Texel sizes are kernel-uniform run-time values (one binary for all formats); the branches on
-// them are warp-uniform.
+// The general streaming kernel: any texel pair, any step chain.  One pixel per thread and iteration: a
+// warp touches 32 consecutive texels of a row (coalesced for every texel size) and the whole generic
+// codec / step interpreter is inlined exactly once.  Texel sizes are kernel-uniform run-time values.
 __global__ void __launch_bounds__(256) k_rowwise(const __grid_constant__ RowParams P) {
   __shared__ Tables T;
   load_tables(T);
@@ -90,54 +64,21 @@ __global__ void __launch_bounds__(256) k_rowwise(const __grid_constant__ RowPara
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < P.total_groups; idx += stride) {
     uint32_t rowid = fastdiv(idx, P.div_gpr);
-    uint32_t g = idx - rowid * P.groups_per_row;
+    int x = (int)(idx - rowid * P.groups_per_row);
     uint32_t frame = fastdiv(rowid, P.div_h);
     int y = (int)(rowid - frame * (uint32_t)P.dst.h);
-    int x0 = (int)g * 4;
-    int npx = min(4, P.dst.w - x0);
-
-    // does `above` cover this group?  (tx is a multiple of 4, so a group is covered from its start)
-    int ax0 = x0 - P.tx, ay = y - P.ty;
-    bool row_in = P.has_above && ay >= 0 && ay < P.ah && ax0 >= 0 && ax0 < P.aw;
-    int ncov = row_in ? min(npx, P.aw - ax0) : 0;
-
-    float4 v[4];
-    const bool need_below = P.has_below && !(ncov == npx && P.blend == ZOS_BLEND_OVERWRITE);
-    if (need_below) {
-      uint4 w[4];
-      load4(SB, P.below.p0 + frame * P.below.bstride + (uint64_t)y * P.below.pitch + (uint64_t)x0 * SB, w);
-#pragma unroll
-      for (int i = 0; i < 4; i++) v[i] = unpack_texel(P.below.fmt, w[i], T);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; i++) v[i] = make_float4(0.0f, 0.0f, 1.0f, 1.0f);
+    const int ax = x - P.tx, ay = y - P.ty;
+    const bool covered = P.has_above && ay >= 0 && ay < P.ah && ax >= 0 && ax < P.aw;
+    float4 v = make_float4(0.0f, 0.0f, 1.0f, 1.0f);
+    if (P.has_below && !(covered && P.blend == ZOS_BLEND_OVERWRITE))
+      v = unpack_texel(P.below.fmt, load1(SB, P.below.p0 + frame * P.below.bstride + (uint64_t)y * P.below.pitch + (uint64_t)x * SB), T);
+    if (covered) {
+      float4 a = unpack_texel(P.above.fmt, load1(SB, P.above.p0 + frame * P.above.bstride + (uint64_t)ay * P.above.pitch + (uint64_t)ax * SB), T);
+      apply_steps(P.src_steps, a, T);
+      v = P.blend == ZOS_BLEND_OVERWRITE ? a : P.blend == ZOS_BLEND_INJECT ? inject_blend(P.inj, a, v) : porter_duff(P.blend, a, v);
     }
-    if (ncov > 0) {
-      uint4 w[4];
-      load4(SB, P.above.p0 + frame * P.above.bstride + (uint64_t)ay * P.above.pitch + (uint64_t)ax0 * SB, w);
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        if (i < ncov) {
-          float4 a = unpack_texel(P.above.fmt, w[i], T);
-          apply_steps(P.src_steps, a, T);
-          v[i] = P.blend == ZOS_BLEND_OVERWRITE ? a : P.blend == ZOS_BLEND_INJECT ? inject_blend(P.inj, a, v[i]) : porter_duff(P.blend, a, v[i]);
-        }
-      }
-    }
-    uint4 o[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      apply_steps(P.dst_steps, v[i], T);
-      o[i] = pack_texel(P.dst.fmt, v[i], T);
-    }
-    uint8_t* dp = P.dst.p0 + frame * P.dst.bstride + (uint64_t)y * P.dst.pitch + (uint64_t)x0 * DB;
-    if (npx == 4) {
-      store4(DB, dp, o);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 3; i++)
-        if (i < npx) store1(DB, dp + i * DB, o[i]);
-    }
+    apply_steps(P.dst_steps, v, T);
+    store1(DB, P.dst.p0 + frame * P.dst.bstride + (uint64_t)y * P.dst.pitch + (uint64_t)x * DB, pack_texel(P.dst.fmt, v, T));
   }
 }
 
@@ -186,10 +127,10 @@ zos_status launch_rowwise(zos_ctx* ctx, const DevImage* below, const DevImage* a
     return fail(ctx, ZOS_ERR_INVALID, "rowwise: buffers must be 16-byte aligned with padded rows (use zos_aligned_row_stride)");
   // native 8-bit texels with at most matrix steps: the specialised kernel (rowwise_u8.cu), same results
   if (!(ctx->flags & ZOS_CTX_NO_FAST_PATHS) && rowwise_u8_eligible(below, above, dst, cp, steps, nsteps)) return launch_rowwise_u8(ctx, below, above, dst, cp, steps, nsteps, batch);
-  uint64_t gpr = (uint64_t)(dst.w + 3) / 4;
+  uint64_t gpr = (uint64_t)dst.w;  // one pixel per work item
   uint64_t total = gpr * (uint64_t)dst.h * batch;
   if (total == 0) return ZOS_OK;
-  if (total >= (1ull << 32)) return fail(ctx, ZOS_ERR_UNSUPPORTED, "rowwise: more than 2^34 pixels in one launch");
+  if (total >= (1ull << 32)) return fail(ctx, ZOS_ERR_UNSUPPORTED, "rowwise: more than 2^32 pixels in one launch");
   P.groups_per_row = (uint32_t)gpr;
   P.total_groups = (uint32_t)total;
   P.div_gpr = make_fastdiv((uint32_t)gpr);

@@ -44,25 +44,30 @@ __device__ __forceinline__ float f16r(float x) { return __half2float(__float2hal
 __device__ __forceinline__ float clamp01(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
 
 // pow for the transfer curves: exp2(y*log2(x)) on the SFU, the same construction GLSL's pow has.
-__device__ __forceinline__ float pow_fast(float x, float y) { return exp2f(y * __log2f(x)); }
+__device__ __forceinline__ float pow_fast(float x, float y) {
+  float l, r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y * l));
+  return r;
+}
 
 // ---- transfer functions, stage.frag:280-408 ----
 __device__ __forceinline__ float oe_bt709(float v) { return v >= 0.018f ? 1.099f * pow_fast(v, 0.45f) - 0.099f : 4.5f * v; }
 __device__ __forceinline__ float eo_bt709(float v) {
   const float thr = 0.0812428582f;  // oe_bt709(0.018)
-  return v >= thr ? pow_fast((v + 0.099f) / 1.099f, 1.0f / 0.45f) : v / 4.5f;
+  return v >= thr ? pow_fast((v + 0.099f) * (1.0f / 1.099f), 1.0f / 0.45f) : v * (1.0f / 4.5f);
 }
 __device__ __forceinline__ float oe_smpte240(float v) { return v < 0.0228f ? 4.0f * v : 1.1115f * pow_fast(v, 0.45f) - 0.1115f; }
-__device__ __forceinline__ float eo_smpte240(float v) { return v < 0.0913f ? v / 4.0f : pow_fast((v - 0.1115f) / 1.1115f, 1.0f / 0.45f); }
+__device__ __forceinline__ float eo_smpte240(float v) { return v < 0.0913f ? v * 0.25f : pow_fast((v - 0.1115f) * (1.0f / 1.1115f), 1.0f / 0.45f); }
 __device__ __forceinline__ float oe_srgb(float v) {
   if (v < -0.0031308f) return -1.055f * pow_fast(-v, 1.0f / 2.4f) + 0.055f;
   if (v <= 0.0031308f) return v * 12.92f;
   return 1.055f * pow_fast(v, 1.0f / 2.4f) - 0.055f;
 }
 __device__ __forceinline__ float eo_srgb(float v) {
-  if (v < -0.04045f) return -pow_fast((-v + 0.055f) / 1.055f, 2.4f);
-  if (v <= 0.04045f) return v / 12.92f;
-  return pow_fast((v + 0.055f) / 1.055f, 2.4f);
+  if (v < -0.04045f) return -pow_fast((-v + 0.055f) * (1.0f / 1.055f), 2.4f);
+  if (v <= 0.04045f) return v * (1.0f / 12.92f);
+  return pow_fast((v + 0.055f) * (1.0f / 1.055f), 2.4f);
 }
 #define ZOS_PQ_M1 (2610.0f / 16384.0f)
 #define ZOS_PQ_M2 (2523.0f / 4096.0f)
@@ -128,7 +133,14 @@ __device__ __forceinline__ void transfer_decode(uint32_t tr, float4& c) {
 }
 
 // ---- bit fields, stage.frag:533-641 ----
-__device__ __forceinline__ float fld(uint32_t v, float d) { return __fdiv_rn((float)v, d); }
+// v / d for an integer field value: reciprocal multiply plus one Newton step == the IEEE quotient for every
+// field width the formats use (3, 7, 15, 31, 63, 255, 1023, 65535 checked exhaustively; tests/ cover it on device)
+__device__ __forceinline__ float fld(uint32_t v, float d) {
+  const float r = 1.0f / d;
+  const float c = (float)v;
+  const float q = c * r;
+  return fmaf(fmaf(-q, d, c), r, q);
+}
 __device__ __forceinline__ float4 demux(uint32_t n, uint32_t kind, const Tables& T) {
   switch (kind) {
     case ZOS_BITS_UINT8X4: return make_float4(T.unorm8[n & 255], T.unorm8[(n >> 8) & 255], T.unorm8[(n >> 16) & 255], T.unorm8[n >> 24]);
@@ -224,7 +236,10 @@ __device__ __forceinline__ uint32_t srgb8_encode(float x, const Tables& T) {
 __device__ __forceinline__ uint32_t unorm8_rne(float x) { return (uint32_t)__float2int_rn(clamp01(x) * 255.0f); }
 
 // ---- whole texels.  A texel travels as a uint4 (only .x for <= 4 bytes, .x/.y for 8 bytes) ----
-static __device__ __noinline__ float4 unpack_slow(zos_texfmt f, uint4 w, const Tables* Tp) {
+#ifndef ZOS_SLOW_ATTR
+#define ZOS_SLOW_ATTR __noinline__
+#endif
+static __device__ ZOS_SLOW_ATTR float4 unpack_slow(zos_texfmt f, uint4 w, const Tables* Tp) {
   const Tables& T = *Tp;
   switch (f.storage) {
     case ZOS_STORAGE_SRGB8: {
@@ -257,7 +272,7 @@ static __device__ __noinline__ float4 unpack_slow(zos_texfmt f, uint4 w, const T
     }
   }
 }
-static __device__ __noinline__ uint4 pack_slow(zos_texfmt f, float4 v, const Tables* Tp) {
+static __device__ ZOS_SLOW_ATTR uint4 pack_slow(zos_texfmt f, float4 v, const Tables* Tp) {
   const Tables& T = *Tp;
   uint4 w = make_uint4(0, 0, 0, 0);
   switch (f.storage) {
