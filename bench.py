@@ -385,6 +385,13 @@ def main():
         med = per[len(per) // 2]
         avg = total_ms / args.steps
         achieved = wl.bytes_per_frame * wl.frames / (avg * 1e-3) / 1e9
+        traffic = None  # from the committed ncu capture of this very command (profiles/traffic.json)
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wl.name)
+            if tj and tj["frames"] == wl.frames:
+                traffic = tj["bytes"]
+        except Exception:
+            pass
         line = {
             "metric": "megapixels/sec", "value": round(value, 1), "unit": "MP/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
@@ -393,7 +400,7 @@ def main():
                        "out_px_per_frame": wl.out_px, "l2": "each step touches %.0f MB once (> 126 MB L2)" % (wl.bytes_per_frame * wl.frames / 1e6),
                        "parallelism": "frame-batch sharding over %d GPU(s), no collective" % world},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": wl.bytes_per_frame * wl.frames,
+                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": wl.bytes_per_frame * wl.frames,
                          "kernel_ms_avg": round(avg, 4), "kernel_ms_median": round(med, 4)},
             "gpu_launches": int(launches),
             "clocks": sampler.result() if sampler else None,
