@@ -1,0 +1,284 @@
+// rowwise_lut.cu -- the streaming kernel for native 8-bit texels on both sides (Rgba8Unorm[Srgb],
+// Bgra8Unorm[Srgb]; lib/zosimos/src/program.rs:794-838): BASELINE config 2 (inscribe / blend of two
+// RGBA8 sRGB layers) and the RGBA8 row of config 5.  Bit for bit the results of the generic kernel
+// (rowwise.cu) and of the oracle; the work per pixel is cut to ~55 instructions by turning both
+// codecs into ONE shared-memory look-up per channel:
+//
+//   * decode: a 64 KB table with one 256-byte row per code: 32 lane-private copies of the exact
+//     sRGB EOTF value followed by 32 copies of code/255.  The address of a look-up is ONE byte
+//     permute, (code << 8) | (lane * 4), and no two lanes of a warp ever share a bank;
+//   * sRGB encode, correctly rounded, without transcendental: the f32 bit pattern of x in [2^-13, 1]
+//     is cut into 1665 buckets (sign/exponent/7 mantissa bits).  No bucket holds more than one of the
+//     255 rounding thresholds, so   code = base[bucket] + (low16(x) >= low16(threshold[bucket])).
+//     Both facts are folded into one 32-bit entry e = (base << 16) + (0x10000 - t16) - (top16 << 16):
+//     (e + bits(x)) >> 16 is the code: one integer max (values below 2^-13 encode to 0), a shift,
+//     a mask-or, the look-up and an add per channel.  The table is replicated 16x;
+//   * 4 pixels per thread and iteration with 16-byte accesses, the next group's loads issued before
+//     the current group is processed; a fully linear addressing mode when all layers share one
+//     geometry (the blend workload); one 1024-thread CTA per SM owning ~171 KB of tables.
+//
+// The arithmetic between decode and encode is exactly the generic kernel's (source-over with one
+// reciprocal, mat3_mul's fmaf order), so this is an optimisation of instruction count only.
+#include "colorops.cuh"
+#include "zos_internal.h"
+#include "rowwise_params.cuh"
+
+#include <vector>
+
+namespace zos {
+
+constexpr int LUT_THREADS = 1024;
+constexpr int ENC_B0 = 0x3900;                   // top 16 bits of 2^-13
+constexpr int ENC_N = 0x3f80 - ENC_B0 + 1;       // buckets up to and including the one of 1.0
+constexpr int ER = 16;                           // replication of the encode table
+constexpr uint32_t DEC_BYTES = 256u * 256u;      // [code][0..31] sRGB EOTF, [code][32..63] code/255
+constexpr uint32_t ENC_BYTES = (uint32_t)ENC_N * ER * 4u;
+constexpr uint32_t ENC_SHIFT = 16 - 6;           // bits >> 16 is the bucket, entries are ER*4 = 64 bytes apart
+constexpr uint32_t ENC_MASK = 0x7ffu * (ER * 4u);  // the low 11 bits of the bucket are unique over [ENC_B0, 0x3f80]
+constexpr uint32_t ENC_VOFF = (ENC_B0 & 0x7ff) * (ER * 4u);  // masked offset of the first bucket
+
+static __device__ uint32_t g_srgb_enc[ENC_N];
+
+ZOS_DEFINE_CONSTANT_UPLOAD(upload_constants_rowwise_lut_base)
+
+// the bucket table from the rounding thresholds (thr[k] = smallest f32 whose code is >= k)
+cudaError_t upload_constants_rowwise_lut(const TablesGlobal* t, const ColorConstants* c, cudaStream_t stream) {
+  cudaError_t e = upload_constants_rowwise_lut_base(t, c, stream);
+  if (e != cudaSuccess) return e;
+  static std::vector<uint32_t> enc;  // static: the async copy reads it after we return
+  enc.assign(ENC_N, 0);
+  auto bits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
+  for (int b = 0; b < ENC_N; b++) {
+    const uint32_t top = (uint32_t)(ENC_B0 + b), start = top << 16;
+    uint32_t base = 0;
+    while (base < 255 && bits(t->srgb_thr[base + 1]) <= start) base++;
+    uint32_t t16 = 0x10000u;
+    if (base < 255 && (bits(t->srgb_thr[base + 1]) >> 16) == top) {
+      t16 = bits(t->srgb_thr[base + 1]) & 0xffffu;
+      if (base + 2 <= 255 && (bits(t->srgb_thr[base + 2]) >> 16) == top) return cudaErrorInvalidValue;  // two thresholds in one bucket
+    }
+    enc[b] = (base << 16) + (0x10000u - t16) - (top << 16);
+  }
+  return cudaMemcpyToSymbolAsync(g_srgb_enc, enc.data(), sizeof(uint32_t) * ENC_N, 0, cudaMemcpyHostToDevice, stream);
+}
+
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+struct LutCtx {
+  uint32_t dec;      // shared address of the decode table
+  uint32_t enc;      // shared address of the encode table minus ENC_VOFF
+  uint32_t lane4;    // (lane & 31) * 4, upper bytes zero: byte 0 of every decode address
+  uint32_t lane_er;  // (lane & (ER-1)) * 4
+  uint32_t sr, sg, sb, sa;  // byte-permute selectors building (code << 8) | lane4 for R, G, B, A of a source word
+  uint32_t spack;           // final selector of the destination word (RGBA / BGRA)
+};
+
+struct Px { float r, g, b, a; };
+
+template <int SK>
+__device__ __forceinline__ Px decode8(uint32_t w, const LutCtx& c) {
+  constexpr uint32_t col = SK == K_SRGB8 ? 0u : 128u;
+  Px p;
+  p.r = lds_f32(__byte_perm(w, c.lane4, c.sr) + c.dec + col);
+  p.g = lds_f32(__byte_perm(w, c.lane4, c.sg) + c.dec + col);
+  p.b = lds_f32(__byte_perm(w, c.lane4, c.sb) + c.dec + col);
+  p.a = lds_f32(__byte_perm(w, c.lane4, c.sa) + c.dec + 128u);
+  return p;
+}
+
+// correctly rounded sRGB8 code of x (x <= 1 up to one rounding), in byte 2 of the result
+__device__ __forceinline__ uint32_t srgb_code_b2(float x, const LutCtx& c) {
+  const int idx = max(__float_as_int(x), ENC_B0 << 16);
+  const uint32_t a = (((uint32_t)idx >> ENC_SHIFT) & ENC_MASK) | c.lane_er;
+  return lds_u32(a + c.enc) + (uint32_t)idx;
+}
+
+template <int DK, bool CLAMP>
+__device__ __forceinline__ uint32_t encode8(const Px& p, const LutCtx& c) {
+  float v[4] = {p.r, p.g, p.b, p.a};
+  if (CLAMP) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) v[i] = fminf(fmaxf(v[i], 0.0f), 1.0f);
+  }
+  const uint32_t ca = __float_as_uint(v[3] * 255.0f + 8388608.0f);  // code in byte 0
+  uint32_t t1, t2;
+  if constexpr (DK == K_SRGB8) {
+    t1 = __byte_perm(srgb_code_b2(v[0], c), srgb_code_b2(v[1], c), 0x0062);
+    t2 = __byte_perm(srgb_code_b2(v[2], c), ca, 0x0042);
+  } else {
+    t1 = __byte_perm(__float_as_uint(v[0] * 255.0f + 8388608.0f), __float_as_uint(v[1] * 255.0f + 8388608.0f), 0x0040);
+    t2 = __byte_perm(__float_as_uint(v[2] * 255.0f + 8388608.0f), ca, 0x0040);
+  }
+  return __byte_perm(t1, t2, c.spack);
+}
+
+// One pixel.  MODE 0: `b` only; 2: `a` over `b` (source-over on straight alpha in linear light, the
+// oracle's pd_blend mode 3: identical operation order).
+template <int SK, int DK, int MODE, int NMAT>
+__device__ __forceinline__ uint32_t pixel8(const FastParams& P, uint32_t b, uint32_t a, const LutCtx& c) {
+  Px v = decode8<SK>(b, c);
+  if (MODE == 2) {
+    Px s = decode8<SK>(a, c);
+    float wbk = v.a * (1.0f - s.a);
+    float ao = s.a + wbk;
+    // ao is 0 or in [1/255, 1]: SFU reciprocal + one Newton step is the correctly rounded 1/ao there
+    // (tested for all alpha pairs).  ao == 0 has a zero numerator: any finite reciprocal gives the
+    // oracle's 0, so the guard is a max with a tiny normal number instead of a select.
+    float aos = fmaxf(ao, 1e-30f);
+    float r0;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(aos));
+    float rcp = fmaf(r0, -fmaf(aos, r0, -1.0f), r0);
+    v.r = fmaf(wbk, v.r, s.a * s.r) * rcp;
+    v.g = fmaf(wbk, v.g, s.a * s.g) * rcp;
+    v.b = fmaf(wbk, v.b, s.a * s.b) * rcp;
+    v.a = ao;
+  }
+#pragma unroll
+  for (int k = 0; k < NMAT; k++) {
+    float3 t = mat3_mul(P.m[k], v.r, v.g, v.b);
+    v.r = t.x; v.g = t.y; v.b = t.z;
+  }
+  return encode8<DK, (NMAT > 0)>(v, c);
+}
+
+struct Loc {
+  uint64_t ob, oa, od;  // byte offsets of the 4-texel group in below / above / dst
+  int npx, ncov;        // valid texels of the group, of which covered by `above` (from the left)
+};
+
+template <int MODE>
+__device__ __forceinline__ Loc locate(const FastParams& P, uint32_t idx) {
+  Loc L;
+  if (P.linear) {  // one geometry everywhere, rows and frames contiguous: plain streams
+    L.ob = L.oa = L.od = (uint64_t)idx * 16u;
+    L.npx = 4; L.ncov = MODE ? 4 : 0;
+    return L;
+  }
+  uint32_t rowid = fastdiv(idx, P.div_gpr);
+  uint32_t g = idx - rowid * P.groups_per_row;
+  uint32_t frame = fastdiv(rowid, P.div_h);
+  int y = (int)(rowid - frame * (uint32_t)P.h);
+  int x0 = (int)g * 4;
+  L.npx = min(4, P.w - x0);
+  L.ncov = 0; L.oa = 0;
+  if (MODE != 0) {
+    int ax0 = x0 - P.tx, ay = y - P.ty;
+    bool row_in = ay >= 0 && ay < P.ah && ax0 >= 0 && ax0 < P.aw;
+    L.ncov = row_in ? min(L.npx, P.aw - ax0) : 0;
+    if (row_in) L.oa = frame * P.above_bstride + (uint64_t)ay * P.above_pitch + (uint64_t)ax0 * 4u;
+  }
+  L.ob = frame * P.below_bstride + (uint64_t)y * P.below_pitch + (uint64_t)x0 * 4u;
+  L.od = frame * P.dst_bstride + (uint64_t)y * P.dst_pitch + (uint64_t)x0 * 4u;
+  return L;
+}
+
+template <int SK, int DK, int MODE, int NMAT>
+__global__ void __launch_bounds__(LUT_THREADS, 1) k_rowwise_lut(const __grid_constant__ FastParams P) {
+  extern __shared__ __align__(256) uint8_t smem[];
+  float* dec = reinterpret_cast<float*>(smem);
+  uint32_t* enc = reinterpret_cast<uint32_t*>(smem + DEC_BYTES);
+#pragma unroll 4
+  for (int i = threadIdx.x; i < 256 * 64; i += LUT_THREADS) dec[i] = (i & 32) ? g_tables.unorm8[i >> 6] : g_tables.srgb_dec[i >> 6];
+  if (DK == K_SRGB8) {
+#pragma unroll 4
+    for (int i = threadIdx.x; i < ENC_N * ER; i += LUT_THREADS) enc[i] = g_srgb_enc[i / ER];
+  }
+  __syncthreads();
+
+  LutCtx c;
+  c.dec = (uint32_t)__cvta_generic_to_shared(dec);
+  c.enc = (uint32_t)__cvta_generic_to_shared(enc) - ENC_VOFF;
+  c.lane4 = (threadIdx.x & 31u) * 4u;
+  c.lane_er = (threadIdx.x & (ER - 1u)) * 4u;
+  // selector nibbles: byte 0 <- lane4.byte0 (4), byte 1 <- word byte k, bytes 2, 3 <- lane4's zero bytes (6, 7)
+  const uint32_t kr = P.src_bgra ? 2u : 0u, kb = P.src_bgra ? 0u : 2u;
+  c.sr = 0x7604u | (kr << 4); c.sg = 0x7614u; c.sb = 0x7604u | (kb << 4); c.sa = 0x7634u;
+  c.spack = P.dst_bgra ? 0x5014u : 0x5410u;
+
+  const uint32_t stride = gridDim.x * LUT_THREADS;
+  uint32_t idx = blockIdx.x * LUT_THREADS + threadIdx.x;
+  if (idx >= P.total_groups) return;
+  Loc L = locate<MODE>(P, idx);
+  uint4 rb = __ldcs(reinterpret_cast<const uint4*>(P.below + L.ob));
+  uint4 ra = make_uint4(0, 0, 0, 0);
+  if (MODE != 0 && L.ncov > 0) ra = __ldcs(reinterpret_cast<const uint4*>(P.above + L.oa));
+  for (;;) {
+    const uint32_t nidx = idx + stride;
+    const bool more = nidx < P.total_groups;
+    Loc NL = L;
+    uint4 nb = rb, na = ra;
+    if (more) {  // the next group's loads are in flight while this one is computed
+      NL = locate<MODE>(P, nidx);
+      nb = __ldcs(reinterpret_cast<const uint4*>(P.below + NL.ob));
+      na = make_uint4(0, 0, 0, 0);
+      if (MODE != 0 && NL.ncov > 0) na = __ldcs(reinterpret_cast<const uint4*>(P.above + NL.oa));
+    }
+    const uint32_t wb[4] = {rb.x, rb.y, rb.z, rb.w}, wa[4] = {ra.x, ra.y, ra.z, ra.w};
+    uint32_t o[4];
+    if (MODE == 0 || L.ncov == 4) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) o[i] = pixel8<SK, DK, MODE, NMAT>(P, wb[i], wa[i], c);
+    } else {
+      // a group outside of / straddling the edge of `above`: covered pixels first, then the rest
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        o[i] = i < L.ncov ? pixel8<SK, DK, MODE, NMAT>(P, wb[i], wa[i], c) : pixel8<SK, DK, 0, NMAT>(P, wb[i], wa[i], c);
+    }
+    uint8_t* dp = P.dst + L.od;
+    if (L.npx == 4) {
+      __stcs(reinterpret_cast<uint4*>(dp), make_uint4(o[0], o[1], o[2], o[3]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+        if (i < L.npx) reinterpret_cast<uint32_t*>(dp)[i] = o[i];
+    }
+    if (!more) break;
+    L = NL; rb = nb; ra = na; idx = nidx;
+  }
+}
+
+template <int SK, int DK, int MODE, int NMAT>
+static cudaError_t launch_one(zos_ctx* ctx, const FastParams& P) {
+  static bool configured[16] = {};  // per device: opt in to > 48 KB of dynamic shared memory once
+  const uint32_t bytes = DEC_BYTES + (DK == K_SRGB8 ? ENC_BYTES : 0u);
+  auto kern = k_rowwise_lut<SK, DK, MODE, NMAT>;
+  if (ctx->device < 0 || ctx->device >= 16 || !configured[ctx->device]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DEC_BYTES + ENC_BYTES));
+    if (e != cudaSuccess) return e;
+    if (ctx->device >= 0 && ctx->device < 16) configured[ctx->device] = true;
+  }
+  const uint64_t ctas = (P.total_groups + LUT_THREADS - 1) / LUT_THREADS;
+  const int grid = (int)(ctas < (uint64_t)ctx->sm_count ? ctas : (uint64_t)ctx->sm_count);
+  kern<<<grid, LUT_THREADS, bytes, ctx->stream>>>(P);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rowwise_lut(zos_ctx* ctx, FastParams& P, int sk, int dk, int mode, int nmat) {
+  // linear addressing: every layer has the destination's geometry, rows and frames back to back
+  const uint64_t row = (uint64_t)P.w * 4u;
+  const bool full = mode == 0 || (P.tx == 0 && P.ty == 0 && P.aw == P.w && P.ah == P.h && P.above_pitch == row && P.above_bstride == row * P.h);
+  P.linear = (P.w % 4 == 0) && full && P.below_pitch == row && P.dst_pitch == row && P.below_bstride == row * P.h && P.dst_bstride == row * P.h;
+#define ZOS_LUT(SK_, DK_)                                                 \
+  if (sk == SK_ && dk == DK_) {                                           \
+    if (mode == 0 && nmat == 0) return launch_one<SK_, DK_, 0, 0>(ctx, P); \
+    if (mode == 0 && nmat == 1) return launch_one<SK_, DK_, 0, 1>(ctx, P); \
+    if (mode == 0) return launch_one<SK_, DK_, 0, 2>(ctx, P);              \
+    if (nmat == 0) return launch_one<SK_, DK_, 2, 0>(ctx, P);              \
+    if (nmat == 1) return launch_one<SK_, DK_, 2, 1>(ctx, P);              \
+    return launch_one<SK_, DK_, 2, 2>(ctx, P);                             \
+  }
+  ZOS_LUT(K_SRGB8, K_SRGB8) ZOS_LUT(K_SRGB8, K_UNORM8) ZOS_LUT(K_UNORM8, K_SRGB8) ZOS_LUT(K_UNORM8, K_UNORM8)
+#undef ZOS_LUT
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace zos

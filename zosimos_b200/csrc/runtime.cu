@@ -15,6 +15,7 @@ cudaError_t upload_constants_gather(const TablesGlobal*, const ColorConstants*, 
 cudaError_t upload_constants_misc(const TablesGlobal*, const ColorConstants*, cudaStream_t);
 cudaError_t upload_constants_rowwise_u8(const TablesGlobal*, const ColorConstants*, cudaStream_t);
 cudaError_t upload_constants_frame(const TablesGlobal*, const ColorConstants*, cudaStream_t);
+cudaError_t upload_constants_rowwise_lut(const TablesGlobal*, const ColorConstants*, cudaStream_t);
 
 static thread_local std::string g_create_error;
 
@@ -243,6 +244,7 @@ zos_status zos_ctx_create(int32_t device, zos_ctx** out) {
     cudaError_t e3 = upload_constants_misc(t, c, ctx->stream);
     cudaError_t e5 = upload_constants_rowwise_u8(t, c, ctx->stream);
     if (e5 == cudaSuccess) e5 = upload_constants_frame(t, c, ctx->stream);
+    if (e5 == cudaSuccess) e5 = upload_constants_rowwise_lut(t, c, ctx->stream);
     cudaError_t e4 = cudaStreamSynchronize(ctx->stream);
     delete t;
     delete c;
