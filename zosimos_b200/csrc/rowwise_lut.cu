@@ -84,39 +84,43 @@ struct LutCtx {
 
 struct Px { float r, g, b, a; };
 
-template <int SK>
+template <int SK, bool WITH_ALPHA = true>
 __device__ __forceinline__ Px decode8(uint32_t w, const LutCtx& c) {
   constexpr uint32_t col = SK == K_SRGB8 ? 0u : 128u;
   Px p;
   p.r = lds_f32(__byte_perm(w, c.lane4, c.sr) + c.dec + col);
   p.g = lds_f32(__byte_perm(w, c.lane4, c.sg) + c.dec + col);
   p.b = lds_f32(__byte_perm(w, c.lane4, c.sb) + c.dec + col);
-  p.a = lds_f32(__byte_perm(w, c.lane4, c.sa) + c.dec + 128u);
+  p.a = WITH_ALPHA ? lds_f32(__byte_perm(w, c.lane4, c.sa) + c.dec + 128u) : 1.0f;
   return p;
 }
 
 // correctly rounded sRGB8 code of x (x <= 1 up to one rounding), in byte 2 of the result
 __device__ __forceinline__ uint32_t srgb_code_b2(float x, const LutCtx& c) {
   const int idx = max(__float_as_int(x), ENC_B0 << 16);
-  const uint32_t a = (((uint32_t)idx >> ENC_SHIFT) & ENC_MASK) | c.lane_er;
+  uint32_t a;  // ((idx >> SHIFT) & MASK) | lane column, as ONE logic op
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(a) : "r"((uint32_t)idx >> ENC_SHIFT), "r"(ENC_MASK), "r"(c.lane_er));
   return lds_u32(a + c.enc) + (uint32_t)idx;
 }
 
-template <int DK, bool CLAMP>
-__device__ __forceinline__ uint32_t encode8(const Px& p, const LutCtx& c) {
+// RAW_ALPHA: alpha was not touched between decode and encode (no blend; matrix steps act on colour
+// only) and code -> code/255 -> code is the identity, so byte 3 of the source word `w` is the result.
+template <int DK, bool CLAMP, bool RAW_ALPHA>
+__device__ __forceinline__ uint32_t encode8(const Px& p, const LutCtx& c, uint32_t w) {
   float v[4] = {p.r, p.g, p.b, p.a};
   if (CLAMP) {
 #pragma unroll
-    for (int i = 0; i < 4; i++) v[i] = fminf(fmaxf(v[i], 0.0f), 1.0f);
+    for (int i = 0; i < 3; i++) v[i] = fminf(fmaxf(v[i], 0.0f), 1.0f);
   }
-  const uint32_t ca = __float_as_uint(v[3] * 255.0f + 8388608.0f);  // code in byte 0
+  uint32_t ca = w;  // code in byte 3
+  if (!RAW_ALPHA) ca = __float_as_uint(v[3] * 255.0f + 8388608.0f);  // code in byte 0 (blended alpha is in [0, 1])
   uint32_t t1, t2;
   if constexpr (DK == K_SRGB8) {
     t1 = __byte_perm(srgb_code_b2(v[0], c), srgb_code_b2(v[1], c), 0x0062);
-    t2 = __byte_perm(srgb_code_b2(v[2], c), ca, 0x0042);
+    t2 = __byte_perm(srgb_code_b2(v[2], c), ca, RAW_ALPHA ? 0x0072 : 0x0042);
   } else {
     t1 = __byte_perm(__float_as_uint(v[0] * 255.0f + 8388608.0f), __float_as_uint(v[1] * 255.0f + 8388608.0f), 0x0040);
-    t2 = __byte_perm(__float_as_uint(v[2] * 255.0f + 8388608.0f), ca, 0x0040);
+    t2 = __byte_perm(__float_as_uint(v[2] * 255.0f + 8388608.0f), ca, RAW_ALPHA ? 0x0070 : 0x0040);
   }
   return __byte_perm(t1, t2, c.spack);
 }
@@ -125,7 +129,7 @@ __device__ __forceinline__ uint32_t encode8(const Px& p, const LutCtx& c) {
 // oracle's pd_blend mode 3: identical operation order).
 template <int SK, int DK, int MODE, int NMAT>
 __device__ __forceinline__ uint32_t pixel8(const FastParams& P, uint32_t b, uint32_t a, const LutCtx& c) {
-  Px v = decode8<SK>(b, c);
+  Px v = decode8<SK, MODE != 0>(b, c);
   if (MODE == 2) {
     Px s = decode8<SK>(a, c);
     float wbk = v.a * (1.0f - s.a);
@@ -147,7 +151,7 @@ __device__ __forceinline__ uint32_t pixel8(const FastParams& P, uint32_t b, uint
     float3 t = mat3_mul(P.m[k], v.r, v.g, v.b);
     v.r = t.x; v.g = t.y; v.b = t.z;
   }
-  return encode8<DK, (NMAT > 0)>(v, c);
+  return encode8<DK, (NMAT > 0), MODE == 0>(v, c, b);
 }
 
 struct Loc {
@@ -158,11 +162,6 @@ struct Loc {
 template <int MODE>
 __device__ __forceinline__ Loc locate(const FastParams& P, uint32_t idx) {
   Loc L;
-  if (P.linear) {  // one geometry everywhere, rows and frames contiguous: plain streams
-    L.ob = L.oa = L.od = (uint64_t)idx * 16u;
-    L.npx = 4; L.ncov = MODE ? 4 : 0;
-    return L;
-  }
   uint32_t rowid = fastdiv(idx, P.div_gpr);
   uint32_t g = idx - rowid * P.groups_per_row;
   uint32_t frame = fastdiv(rowid, P.div_h);
@@ -181,7 +180,10 @@ __device__ __forceinline__ Loc locate(const FastParams& P, uint32_t idx) {
   return L;
 }
 
-template <int SK, int DK, int MODE, int NMAT>
+// LINEAR: every layer has the destination's geometry with rows and frames back to back, so the images
+// are plain streams of 16-byte groups (the blend / convert workloads).  Two groups are in flight per
+// thread, ping-pong, so that no register rotation is needed.
+template <int SK, int DK, int MODE, int NMAT, bool LINEAR>
 __global__ void __launch_bounds__(LUT_THREADS, 1) k_rowwise_lut(const __grid_constant__ FastParams P) {
   extern __shared__ __align__(256) uint8_t smem[];
   float* dec = reinterpret_cast<float*>(smem);
@@ -207,13 +209,39 @@ __global__ void __launch_bounds__(LUT_THREADS, 1) k_rowwise_lut(const __grid_con
   const uint32_t stride = gridDim.x * LUT_THREADS;
   uint32_t idx = blockIdx.x * LUT_THREADS + threadIdx.x;
   if (idx >= P.total_groups) return;
+
+  if constexpr (LINEAR) {
+    const uint4* pb = reinterpret_cast<const uint4*>(P.below) + idx;
+    const uint4* pa = reinterpret_cast<const uint4*>(MODE ? P.above : P.below) + idx;
+    uint4* pd = reinterpret_cast<uint4*>(P.dst) + idx;
+    const uint32_t total = P.total_groups;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    uint4 b0 = __ldcs(pb), a0 = MODE ? __ldcs(pa) : z, b1 = z, a1 = z;
+#define ZOS_LUT_GROUP(B, A, OUT)                                                        \
+    __stcs(OUT, make_uint4(pixel8<SK, DK, MODE, NMAT>(P, B.x, A.x, c), pixel8<SK, DK, MODE, NMAT>(P, B.y, A.y, c), \
+                           pixel8<SK, DK, MODE, NMAT>(P, B.z, A.z, c), pixel8<SK, DK, MODE, NMAT>(P, B.w, A.w, c)))
+    for (;;) {
+      const bool more1 = idx + stride < total && idx + stride >= stride;
+      if (more1) { b1 = __ldcs(pb + stride); if (MODE) a1 = __ldcs(pa + stride); }
+      ZOS_LUT_GROUP(b0, a0, pd);
+      if (!more1) break;
+      const uint32_t i2 = idx + 2u * stride;
+      const bool more0 = i2 < total && i2 >= 2u * stride;
+      if (more0) { b0 = __ldcs(pb + 2u * (size_t)stride); if (MODE) a0 = __ldcs(pa + 2u * (size_t)stride); }
+      ZOS_LUT_GROUP(b1, a1, pd + stride);
+      if (!more0) break;
+      idx = i2; pb += 2u * (size_t)stride; pa += 2u * (size_t)stride; pd += 2u * (size_t)stride;
+    }
+#undef ZOS_LUT_GROUP
+    return;
+  } else {
   Loc L = locate<MODE>(P, idx);
   uint4 rb = __ldcs(reinterpret_cast<const uint4*>(P.below + L.ob));
   uint4 ra = make_uint4(0, 0, 0, 0);
   if (MODE != 0 && L.ncov > 0) ra = __ldcs(reinterpret_cast<const uint4*>(P.above + L.oa));
   for (;;) {
     const uint32_t nidx = idx + stride;
-    const bool more = nidx < P.total_groups;
+    const bool more = nidx < P.total_groups && nidx >= stride;
     Loc NL = L;
     uint4 nb = rb, na = ra;
     if (more) {  // the next group's loads are in flight while this one is computed
@@ -244,21 +272,25 @@ __global__ void __launch_bounds__(LUT_THREADS, 1) k_rowwise_lut(const __grid_con
     if (!more) break;
     L = NL; rb = nb; ra = na; idx = nidx;
   }
+  }
 }
 
 template <int SK, int DK, int MODE, int NMAT>
 static cudaError_t launch_one(zos_ctx* ctx, const FastParams& P) {
   static bool configured[16] = {};  // per device: opt in to > 48 KB of dynamic shared memory once
   const uint32_t bytes = DEC_BYTES + (DK == K_SRGB8 ? ENC_BYTES : 0u);
-  auto kern = k_rowwise_lut<SK, DK, MODE, NMAT>;
+  auto kern = k_rowwise_lut<SK, DK, MODE, NMAT, false>;
+  auto kern_lin = k_rowwise_lut<SK, DK, MODE, NMAT, true>;
   if (ctx->device < 0 || ctx->device >= 16 || !configured[ctx->device]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DEC_BYTES + ENC_BYTES));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_lin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DEC_BYTES + ENC_BYTES));
     if (e != cudaSuccess) return e;
     if (ctx->device >= 0 && ctx->device < 16) configured[ctx->device] = true;
   }
   const uint64_t ctas = (P.total_groups + LUT_THREADS - 1) / LUT_THREADS;
   const int grid = (int)(ctas < (uint64_t)ctx->sm_count ? ctas : (uint64_t)ctx->sm_count);
-  kern<<<grid, LUT_THREADS, bytes, ctx->stream>>>(P);
+  if (P.linear) kern_lin<<<grid, LUT_THREADS, bytes, ctx->stream>>>(P);
+  else kern<<<grid, LUT_THREADS, bytes, ctx->stream>>>(P);
   return cudaGetLastError();
 }
 
