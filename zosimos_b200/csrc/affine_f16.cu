@@ -1,0 +1,283 @@
+// affine_f16.cu -- the resampling kernel of BASELINE config 3: `affine(below, M, above)` with nearest or
+// bilinear sampling where all three images are plain linear RGBA16F (command.rs:1636-1673; the
+// quad rasterisation it replaces is program.rs:1897-1935 + box.vert + copy.frag, bilinear is ours).
+// Same results, bit for bit, as the general gather kernel (gather.cu) and the oracle
+// (zo_paint_affine_window): identical coordinate arithmetic (fmaf order of map_point), identical
+// tap clamping and lerp order.  What is different is the instruction count per pixel:
+//
+//   * a CTA produces 32x32 destination tiles (persistent, grid-stride); the source bounding box of
+//     the NEXT tile is fetched by one TMA bulk tensor copy while the current tile is computed;
+//   * tile geometry (4 corner mappings, box origin, alignment) is computed by ONE thread and
+//     broadcast through shared memory instead of by all 256;
+//   * the x half of the inverse mapping is hoisted out of the 4-row loop of a thread, coverage of a
+//     covered pixel bounds its taps so each clamp is one instruction, taps are LDS.64 at 32-bit
+//     shared addresses, rows of a thread are fully unrolled so their 16 loads are in flight together.
+#include <cuda_fp16.h>
+
+#include "colorops.cuh"
+#include "tma.cuh"
+#include "zos_internal.h"
+
+namespace zos {
+
+ZOS_DEFINE_CONSTANT_UPLOAD(upload_constants_affine)
+
+namespace {
+constexpr int TILE = 32;
+constexpr int THREADS = 256;
+constexpr int ROWS = TILE / (THREADS / 32);  // rows of a tile per thread
+
+struct AffParams {
+  const uint8_t* above;
+  const uint8_t* below;
+  uint8_t* dst;
+  uint64_t above_pitch, above_bstride, below_pitch, below_bstride, dst_pitch, dst_bstride;
+  int32_t aw, ah;  // size of the window of the source that `above` holds
+  int32_t dw, dh;
+  int32_t has_below, blend;
+  float inv[6];
+  int32_t dox, doy, sox, soy, sfw, sfh;
+  uint32_t tiles_x, tiles_y, total_tiles;
+  FastDiv div_tx, div_ty;
+  int32_t box_w, box_h;
+  int* fault;  // mapped host word set when an mbarrier wait runs away
+};
+
+struct Geo {
+  int32_t frame, x0, y0;  // destination tile
+  int32_t bx, by;         // box origin in the window `above` holds
+  int32_t fits, any;
+};
+
+__device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv& f) {
+  uint32_t t = __umulhi(n, f.m);
+  return f.l == 0 ? n : (t + ((n - t) >> 1)) >> (f.l - 1);
+}
+__device__ __forceinline__ void map_point(const AffParams& P, float cx, float cy, float& px, float& py) {
+  px = fmaf(P.inv[1], cy, fmaf(P.inv[0], cx, P.inv[2]));
+  py = fmaf(P.inv[4], cy, fmaf(P.inv[3], cx, P.inv[5]));
+}
+
+// the bounding box of the tile's taps (the same construction as gather.cu's tile_info)
+__device__ void tile_geometry(const AffParams& P, uint32_t t, Geo& g) {
+  uint32_t r = fastdiv(t, P.div_tx);
+  uint32_t txi = t - r * P.tiles_x;
+  uint32_t fr = fastdiv(r, P.div_ty);
+  uint32_t tyi = r - fr * P.tiles_y;
+  g.frame = (int)fr; g.x0 = (int)txi * TILE; g.y0 = (int)tyi * TILE;
+  g.bx = g.by = 0; g.fits = 0; g.any = 0;
+  const int x1 = min(g.x0 + TILE, P.dw) - 1, y1 = min(g.y0 + TILE, P.dh) - 1;
+  float px[4], py[4];
+  const float gx0 = (float)(g.x0 + P.dox) + 0.5f, gx1 = (float)(x1 + P.dox) + 0.5f;
+  const float gy0 = (float)(g.y0 + P.doy) + 0.5f, gy1 = (float)(y1 + P.doy) + 0.5f;
+  map_point(P, gx0, gy0, px[0], py[0]);
+  map_point(P, gx1, gy0, px[1], py[1]);
+  map_point(P, gx0, gy1, px[2], py[2]);
+  map_point(P, gx1, gy1, px[3], py[3]);
+  float minx = fminf(fminf(px[0], px[1]), fminf(px[2], px[3])), maxx = fmaxf(fmaxf(px[0], px[1]), fmaxf(px[2], px[3]));
+  float miny = fminf(fminf(py[0], py[1]), fminf(py[2], py[3])), maxy = fmaxf(fmaxf(py[0], py[1]), fmaxf(py[2], py[3]));
+  minx = fmaxf(minx, 0.0f); miny = fmaxf(miny, 0.0f);
+  maxx = fminf(maxx, (float)P.sfw); maxy = fminf(maxy, (float)P.sfh);
+  if (minx > maxx || miny > maxy) return;
+  int lox = max((int)floorf(minx) - 2 - P.sox, 0), hix = min((int)floorf(maxx) + 2 - P.sox, P.aw - 1);
+  int loy = max((int)floorf(miny) - 2 - P.soy, 0), hiy = min((int)floorf(maxy) + 2 - P.soy, P.ah - 1);
+  if (lox > hix || loy > hiy) return;
+  lox &= ~1;  // 8-byte texels: a 16-byte aligned TMA source address
+  g.any = 1;
+  g.bx = lox; g.by = loy;
+  g.fits = (hix - lox + 1 <= P.box_w) && (hiy - loy + 1 <= P.box_h);
+}
+
+__device__ __forceinline__ float4 half4_to_float4(const uint2& w) {
+  float2 a = __half22float2(*reinterpret_cast<const __half2*>(&w.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+  uint2 w;
+  asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "r"(a));
+  return w;
+}
+
+// The taps of one covered pixel.  SMEM: `base` is the shared address of texel (0, 0) of the FULL source
+// (i.e. the stage address minus the box / window origin), `rowb` the bytes of a box row.  Otherwise
+// `gbase` points at texel (0, 0) of the full source in global memory and `rowb` is the pitch.
+template <bool BILINEAR, bool SMEM>
+__device__ __forceinline__ float4 sample(const AffParams& P, float px, float py, uint32_t base, const uint8_t* gbase, uint32_t rowb) {
+  if (!BILINEAR) {
+    const int u = (int)floorf(px), w = (int)floorf(py);
+    if (SMEM) return half4_to_float4(lds64(base + (uint32_t)w * rowb + (uint32_t)u * 8u));
+    return half4_to_float4(*reinterpret_cast<const uint2*>(gbase + (int64_t)w * rowb + (int64_t)u * 8));
+  }
+  const float fx = px - 0.5f, fy = py - 0.5f;
+  const float x0f = floorf(fx), y0f = floorf(fy);
+  const float ax = fx - x0f, ay = fy - y0f;
+  // covered: px in [0, sfw) so x0 in [-1, sfw-1]: clamp(x0) = max(x0, 0), clamp(x0 + 1) = min(x0 + 1, sfw - 1)
+  const int x0 = (int)x0f, y0 = (int)y0f;
+  const int xa = max(x0, 0), xb = min(x0 + 1, P.sfw - 1), ya = max(y0, 0), yb = min(y0 + 1, P.sfh - 1);
+  uint2 w00, w10, w01, w11;
+  if (SMEM) {
+    const uint32_t ra = base + (uint32_t)ya * rowb, rb = base + (uint32_t)yb * rowb;
+    w00 = lds64(ra + (uint32_t)xa * 8u); w10 = lds64(ra + (uint32_t)xb * 8u);
+    w01 = lds64(rb + (uint32_t)xa * 8u); w11 = lds64(rb + (uint32_t)xb * 8u);
+  } else {
+    const uint8_t* ra = gbase + (int64_t)ya * rowb;
+    const uint8_t* rb = gbase + (int64_t)yb * rowb;
+    w00 = *reinterpret_cast<const uint2*>(ra + (int64_t)xa * 8); w10 = *reinterpret_cast<const uint2*>(ra + (int64_t)xb * 8);
+    w01 = *reinterpret_cast<const uint2*>(rb + (int64_t)xa * 8); w11 = *reinterpret_cast<const uint2*>(rb + (int64_t)xb * 8);
+  }
+  const float4 p00 = half4_to_float4(w00), p10 = half4_to_float4(w10), p01 = half4_to_float4(w01), p11 = half4_to_float4(w11);
+  float4 o;
+#define ZOS_LERP2(c) { float top = fmaf(ax, p10.c - p00.c, p00.c), bot = fmaf(ax, p11.c - p01.c, p01.c); o.c = fmaf(ay, bot - top, top); }
+  ZOS_LERP2(x) ZOS_LERP2(y) ZOS_LERP2(z) ZOS_LERP2(w)
+#undef ZOS_LERP2
+  return o;
+}
+
+template <bool BILINEAR, bool SMEM>
+__device__ __forceinline__ void compute_tile(const AffParams& P, const Geo& g, uint32_t stage_addr) {
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int i = g.x0 + lx;
+  if (i >= P.dw) return;
+  const float cx = (float)(i + P.dox) + 0.5f;
+  const float tx = fmaf(P.inv[0], cx, P.inv[2]), ty = fmaf(P.inv[3], cx, P.inv[5]);
+  const float sfw = (float)P.sfw, sfh = (float)P.sfh;
+  const uint32_t rowb = SMEM ? (uint32_t)P.box_w * 8u : (uint32_t)P.above_pitch;
+  // address of texel (0, 0) of the full source: window origin and box origin folded in once per tile
+  const uint32_t base = stage_addr - (uint32_t)(g.by + P.soy) * rowb - (uint32_t)(g.bx + P.sox) * 8u;
+  const uint8_t* gbase = P.above + (uint64_t)g.frame * P.above_bstride - (int64_t)P.soy * (int64_t)P.above_pitch - (int64_t)P.sox * 8;
+  const uint64_t off0 = (uint64_t)g.frame * P.dst_bstride + (uint64_t)(g.y0 + ly) * P.dst_pitch + (uint64_t)i * 8u;
+  const uint64_t boff0 = (uint64_t)g.frame * P.below_bstride + (uint64_t)(g.y0 + ly) * P.below_pitch + (uint64_t)i * 8u;
+#pragma unroll
+  for (int k = 0; k < ROWS; k++) {
+    const int j = g.y0 + ly + (THREADS / 32) * k;
+    if (j < P.dh) {
+      const float cy = (float)(j + P.doy) + 0.5f;
+      const float px = fmaf(P.inv[1], cy, tx), py = fmaf(P.inv[4], cy, ty);
+      const bool covered = px >= 0.0f && px < sfw && py >= 0.0f && py < sfh;
+      float4 v = make_float4(0.0f, 0.0f, 1.0f, 1.0f);  // Target::Discard clear colour
+      if (covered) v = sample<BILINEAR, SMEM>(P, px, py, base, gbase, rowb);
+      if (P.has_below && !(covered && P.blend == ZOS_BLEND_OVERWRITE)) {
+        const uint2 w = __ldcs(reinterpret_cast<const uint2*>(P.below + boff0 + (uint64_t)((THREADS / 32) * k) * P.below_pitch));
+        const float4 b = half4_to_float4(w);
+        v = covered ? porter_duff(P.blend, v, b) : b;
+      }
+      __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+      __stcs(reinterpret_cast<uint2*>(P.dst + off0 + (uint64_t)((THREADS / 32) * k) * P.dst_pitch),
+             make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi)));
+    }
+  }
+}
+
+template <bool BILINEAR>
+__global__ void __launch_bounds__(THREADS, 4) k_affine_f16(const __grid_constant__ AffParams P, const __grid_constant__ TensorMaps M) {
+  extern __shared__ __align__(128) uint8_t dyn[];
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ Geo geo[2];
+  const uint32_t box_bytes = (uint32_t)P.box_w * P.box_h * 8u;
+  const uint32_t stage_bytes = (box_bytes + 127u) & ~127u;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const CUtensorMap* const m0 = &M.m0;  // stays in param space (see gather.cu)
+#define ZOS_AFF_ISSUE(TILE_INDEX, STAGE)                                                         \
+  do {                                                                                            \
+    Geo g_;                                                                                       \
+    tile_geometry(P, (TILE_INDEX), g_);                                                           \
+    geo[(STAGE)] = g_;                                                                            \
+    if (g_.any && g_.fits) {                                                                      \
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                              \
+      mbar_expect_tx(&bar[(STAGE)], box_bytes);                                                   \
+      tma_load_3d(dyn + (size_t)(STAGE) * stage_bytes, m0, g_.bx * 2, g_.by, g_.frame, &bar[(STAGE)]); \
+    }                                                                                             \
+  } while (0)
+  if (threadIdx.x == 0 && blockIdx.x < P.total_tiles) ZOS_AFF_ISSUE(blockIdx.x, 0);
+  __syncthreads();
+  uint32_t phase[2] = {0, 0};
+  int s = 0;
+  for (uint32_t t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+    const uint32_t next = t + gridDim.x;
+    if (threadIdx.x == 0 && next < P.total_tiles) ZOS_AFF_ISSUE(next, s ^ 1);
+    const Geo g = geo[s];
+    if (g.any && g.fits) {
+      uint32_t spins = 0;
+      while (!mbar_try_wait(&bar[s], phase[s])) {
+        if (++spins > (1u << 24)) { if (P.fault) *reinterpret_cast<volatile int*>(P.fault) = 1; break; }
+      }
+      phase[s] ^= 1;
+      compute_tile<BILINEAR, true>(P, g, smem_u32(dyn + (size_t)s * stage_bytes));
+    } else {
+      // no covered pixel (copies `below`), or a footprint larger than the box (strong minification): global taps
+      compute_tile<BILINEAR, false>(P, g, 0u);
+    }
+    __syncthreads();  // stage s is free again; geo[s ^ 1] (written by thread 0 above) is visible
+    s ^= 1;
+  }
+#undef ZOS_AFF_ISSUE
+}
+
+bool plain_f16(const DevImage& im) {
+  return im.block == ZOS_BLOCK_PIXEL && im.fmt.storage == ZOS_STORAGE_FLOAT && im.fmt.bits == ZOS_BITS_FLOAT16X4 &&
+         im.fmt.transfer == ZOS_TRANSFER_LINEAR && (im.fmt.parts == ZOS_PARTS_RGBA || im.fmt.parts == ZOS_PARTS_LCHA || im.fmt.parts == ZOS_PARTS_LABA) &&
+         ((uintptr_t)im.p0 % 16) == 0 && (im.pitch % 16) == 0 && (im.bstride % 16) == 0;
+}
+}  // namespace
+
+// Serves: ZOS_MAP_AFFINE, nearest / bilinear, all images plain linear RGBA16F, no steps, any
+// Porter-Duff mode or overwrite.  *handled stays false when the launch is left to gather.cu.
+zos_status launch_affine_f16(zos_ctx* ctx, const DevImage* below, const DevImage& above, const DevImage& dst,
+                             const zos_compose_params& cp, uint32_t batch, bool* handled) {
+  *handled = false;
+  if ((ctx->flags & ZOS_CTX_NO_FAST_PATHS) || !cp.use_tma || cp.map != ZOS_MAP_AFFINE) return ZOS_OK;
+  if (cp.blend == ZOS_BLEND_INJECT || cp.n_src_steps || cp.n_dst_steps) return ZOS_OK;
+  if (cp.sampling != ZOS_SAMPLE_NEAREST && cp.sampling != ZOS_SAMPLE_BILINEAR) return ZOS_OK;
+  if (!plain_f16(above) || !plain_f16(dst) || (below && !plain_f16(*below))) return ZOS_OK;
+  AffParams P;
+  memset(&P, 0, sizeof P);
+  P.fault = ctx->fault_dev;
+  P.above = above.p0; P.above_pitch = above.pitch; P.above_bstride = above.bstride; P.aw = above.w; P.ah = above.h;
+  if (below) { P.below = below->p0; P.below_pitch = below->pitch; P.below_bstride = below->bstride; }
+  P.has_below = below != nullptr;
+  P.dst = dst.p0; P.dst_pitch = dst.pitch; P.dst_bstride = dst.bstride; P.dw = dst.w; P.dh = dst.h;
+  P.blend = cp.blend;
+  for (int k = 0; k < 6; k++) P.inv[k] = cp.inv[k];
+  P.dox = cp.dst_origin[0]; P.doy = cp.dst_origin[1]; P.sox = cp.src_origin[0]; P.soy = cp.src_origin[1];
+  P.sfw = cp.src_full[0] > 0 ? cp.src_full[0] : above.w; P.sfh = cp.src_full[1] > 0 ? cp.src_full[1] : above.h;
+  if (P.dox < 0 || P.doy < 0 || P.sox < 0 || P.soy < 0 || P.sox + above.w > P.sfw || P.soy + above.h > P.sfh) return ZOS_OK;  // gather.cu reports it
+  if (above.pitch >= (1ull << 31)) return ZOS_OK;
+  P.tiles_x = (dst.w + TILE - 1) / TILE; P.tiles_y = (dst.h + TILE - 1) / TILE;
+  const uint64_t total = (uint64_t)P.tiles_x * P.tiles_y * batch;
+  if (total == 0 || total >= (1ull << 31)) return ZOS_OK;
+  P.total_tiles = (uint32_t)total;
+  P.div_tx = make_fastdiv(P.tiles_x); P.div_ty = make_fastdiv(P.tiles_y);
+  const float ex = (TILE - 1) * (fabsf(P.inv[0]) + fabsf(P.inv[1])), ey = (TILE - 1) * (fabsf(P.inv[3]) + fabsf(P.inv[4]));
+  if (!(ex < 200.0f) || !(ey < 200.0f)) return ZOS_OK;
+  P.box_w = ((int)ceilf(ex) + 6 + 1 + 1) & ~1;
+  P.box_h = (int)ceilf(ey) + 6;
+  const size_t stage = ((size_t)P.box_w * P.box_h * 8 + 127) & ~(size_t)127;
+  const size_t smem = 2 * stage;
+  if (P.box_w * 2 > 256 || P.box_h > 256 || smem > 96 * 1024) return ZOS_OK;
+  TensorMaps M;
+  memset(&M, 0, sizeof M);
+  if (!make_map(ctx, &M.m0, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, above.p0, (uint64_t)above.w * 2, above.h, above.pitch, batch, above.bstride,
+                (uint32_t)P.box_w * 2, (uint32_t)P.box_h))
+    return ZOS_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_affine_f16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(k_affine_f16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_set = true;
+  }
+  int per_sm = (int)((220 * 1024) / (smem + 2048));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+  const uint64_t cap = (uint64_t)ctx->sm_count * per_sm;
+  const int grid = (int)(total < cap ? total : cap);
+  if (cp.sampling == ZOS_SAMPLE_BILINEAR) k_affine_f16<true><<<grid, THREADS, smem, ctx->stream>>>(P, M);
+  else k_affine_f16<false><<<grid, THREADS, smem, ctx->stream>>>(P, M);
+  ctx->launches++;
+  *handled = true;
+  return check_cuda(ctx, cudaGetLastError(), "k_affine_f16 launch");
+}
+
+}  // namespace zos

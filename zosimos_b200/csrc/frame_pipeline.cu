@@ -51,6 +51,7 @@ struct FrameParams {
   uint32_t tiles_x, tiles_y, total_tiles;
   FastDiv div_tx, div_ty;
   int32_t box_w, box_h, cbox_w, cbox_h, conv_w, conv_h;
+  int* fault;  // mapped host word set when an mbarrier wait runs away
 };
 
 struct TileGeo {
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(THREADS, 3) k_frame_pipeline(const __grid_cons
     if (g.any) {
       uint32_t spins = 0;
       while (!mbar_try_wait(&bar[s], phase[s])) {
-        if (++spins > (1u << 24)) break;
+        if (++spins > (1u << 24)) { if (P.fault) *reinterpret_cast<volatile int*>(P.fault) = 1; break; }
       }
       phase[s] ^= 1;
       // ---- phase 1: the footprint, one 2x2 luma block per thread
@@ -287,6 +288,7 @@ zos_status launch_frame_pipeline(zos_ctx* ctx, const DevImage* below, const DevI
   *handled = false;
   FrameParams P;
   memset(&P, 0, sizeof P);
+  P.fault = ctx->fault_dev;
   P.sw = above.w; P.sh = above.h; P.nv12 = above.block == ZOS_BLOCK_YUV420_NV12;
   P.yoff = above.yoff; P.ysc = above.ysc; P.csc = above.csc; P.r_cr = above.r_cr; P.b_cb = above.b_cb; P.g_cr = above.g_cr; P.g_cb = above.g_cb;
   P.transfer = above.fmt.transfer;

@@ -44,6 +44,7 @@ struct GatherParams {
   int32_t cbox_w, cbox_h; // chroma box
   int32_t ept;            // 4-byte elements per texel in the tensor map (bpp >= 4), else 0
   int32_t conv_w, conv_h; // FAST=2: size of the converted-footprint buffer (texels)
+  int* fault;             // mapped host word set when an mbarrier wait runs away (zos_sync reports it)
   int32_t align_x;        // box origin x is rounded down to this many texels: the TMA source address must be 16-byte aligned
   StepList src_steps, dst_steps;
 };
@@ -395,9 +396,6 @@ __global__ void __launch_bounds__(THREADS) k_gather_direct(const __grid_constant
   }
 }
 
-// error flag set when an mbarrier wait runs away (never expected; avoids hanging the GPU)
-__device__ int g_tma_timeout = 0;
-
 template <int FAST>
 __global__ void __launch_bounds__(THREADS) k_gather_tma(const __grid_constant__ GatherParams P, const __grid_constant__ TensorMaps M) {
   extern __shared__ __align__(128) uint8_t dyn[];
@@ -447,7 +445,7 @@ __global__ void __launch_bounds__(THREADS) k_gather_tma(const __grid_constant__ 
       if (ti.fits) {
         uint32_t spins = 0;
         while (!mbar_try_wait(&bar[s], phase[s])) {
-          if (++spins > (1u << 24)) { g_tma_timeout = 1; break; }
+          if (++spins > (1u << 24)) { if (P.fault) *reinterpret_cast<volatile int*>(P.fault) = 1; break; }
         }
         phase[s] ^= 1;
         uint8_t* base = dyn + (size_t)s * stage_bytes;
@@ -479,13 +477,6 @@ __global__ void __launch_bounds__(THREADS) k_gather_tma(const __grid_constant__ 
 }
 
 // ---------------- host side ----------------
-bool gather_take_timeout_flag() {
-  int v = 0, zero = 0;
-  if (cudaMemcpyFromSymbol(&v, g_tma_timeout, sizeof v) != cudaSuccess) return false;
-  if (v) cudaMemcpyToSymbol(g_tma_timeout, &zero, sizeof zero);
-  return v != 0;
-}
-
 static bool img_vec_ok(const DevImage& im) {
   return ((uintptr_t)im.p0 % 16) == 0 && (im.pitch % 16) == 0 && (im.bstride % 16) == 0 &&
          im.pitch >= (uint64_t)((im.w + 3) / 4) * 4 * im.bpp && (im.bpp == 4 || im.bpp == 8);
@@ -499,10 +490,16 @@ zos_status launch_gather(zos_ctx* ctx, const DevImage* below, const DevImage& ab
     zos_status st = launch_frame_pipeline(ctx, below, above, dst, cp, batch, &handled);
     if (handled || st != ZOS_OK) return st;
   }
+  {  // the dedicated RGBA16F resampler (affine_f16.cu)
+    bool handled = false;
+    zos_status st = launch_affine_f16(ctx, below, above, dst, cp, batch, &handled);
+    if (handled || st != ZOS_OK) return st;
+  }
   if (below && below->block != ZOS_BLOCK_PIXEL) return fail(ctx, ZOS_ERR_UNSUPPORTED, "planar `below`");
   GatherParams P;
   memset(&P, 0, sizeof P);
   P.above = above; P.dst = dst;
+  P.fault = ctx->fault_dev;
   P.has_below = below != nullptr;
   if (below) { P.below = *below; P.below_vec = img_vec_ok(*below); }
   P.dst_vec = img_vec_ok(dst);

@@ -15,6 +15,7 @@ cudaError_t upload_constants_gather(const TablesGlobal*, const ColorConstants*, 
 cudaError_t upload_constants_misc(const TablesGlobal*, const ColorConstants*, cudaStream_t);
 cudaError_t upload_constants_rowwise_u8(const TablesGlobal*, const ColorConstants*, cudaStream_t);
 cudaError_t upload_constants_frame(const TablesGlobal*, const ColorConstants*, cudaStream_t);
+cudaError_t upload_constants_affine(const TablesGlobal*, const ColorConstants*, cudaStream_t);
 cudaError_t upload_constants_rowwise_lut(const TablesGlobal*, const ColorConstants*, cudaStream_t);
 
 static thread_local std::string g_create_error;
@@ -235,6 +236,10 @@ zos_status zos_ctx_create(int32_t device, zos_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
   }
   if ((st = check_cuda(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "cudaStreamCreate")) != ZOS_OK) goto bad;
+  if (cudaHostAlloc((void**)&ctx->fault_host, sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
+    *ctx->fault_host = 0;
+    if (cudaHostGetDevicePointer((void**)&ctx->fault_dev, ctx->fault_host, 0) != cudaSuccess) ctx->fault_dev = nullptr;
+  }
   {
     TablesGlobal* t = new TablesGlobal();
     ColorConstants* c = new ColorConstants();
@@ -244,6 +249,7 @@ zos_status zos_ctx_create(int32_t device, zos_ctx** out) {
     cudaError_t e3 = upload_constants_misc(t, c, ctx->stream);
     cudaError_t e5 = upload_constants_rowwise_u8(t, c, ctx->stream);
     if (e5 == cudaSuccess) e5 = upload_constants_frame(t, c, ctx->stream);
+    if (e5 == cudaSuccess) e5 = upload_constants_affine(t, c, ctx->stream);
     if (e5 == cudaSuccess) e5 = upload_constants_rowwise_lut(t, c, ctx->stream);
     cudaError_t e4 = cudaStreamSynchronize(ctx->stream);
     delete t;
@@ -265,6 +271,7 @@ void zos_ctx_destroy(zos_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (void* p : ctx->scratch) cudaFree(p);
+  if (ctx->fault_host) cudaFreeHost(ctx->fault_host);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -279,7 +286,12 @@ zos_status zos_ctx_set_flags(zos_ctx* ctx, uint32_t flags) {
 }
 zos_status zos_sync(zos_ctx* ctx) {
   if (!ctx) return ZOS_ERR_INVALID;
-  return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+  zos_status st = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+  if (st == ZOS_OK && ctx->fault_host && *ctx->fault_host) {
+    *ctx->fault_host = 0;
+    return zos::fail(ctx, ZOS_ERR_CUDA, "a TMA wait timed out inside a kernel: results of this launch are incomplete");
+  }
+  return st;
 }
 
 zos_status zos_buf_alloc(zos_ctx* ctx, uint64_t bytes, zos_buf** out) {

@@ -22,6 +22,8 @@ struct zos_ctx {
   std::string err;
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved lazily through the runtime
   std::vector<void*> scratch;    // device scratch owned by the ctx (tensor maps etc.)
+  int* fault_host = nullptr;     // mapped pinned word: kernels set it when an mbarrier wait ran away; zos_sync reports it
+  int* fault_dev = nullptr;      // device view of fault_host
 };
 
 namespace zos {
@@ -73,6 +75,8 @@ bool rowwise_can_compose(const DevImage& below, const DevImage& above, const Dev
 zos_status launch_gather(zos_ctx* ctx, const DevImage* below, const DevImage& above, const DevImage& dst,
                          const zos_compose_params& cp, uint32_t batch);
 bool frame_pipeline_eligible(zos_ctx* ctx, const DevImage* below, const DevImage& above, const DevImage& dst, const zos_compose_params& cp);
+zos_status launch_affine_f16(zos_ctx* ctx, const DevImage* below, const DevImage& above, const DevImage& dst,
+                             const zos_compose_params& cp, uint32_t batch, bool* handled);
 zos_status launch_frame_pipeline(zos_ctx* ctx, const DevImage* below, const DevImage& above, const DevImage& dst,
                                  const zos_compose_params& cp, uint32_t batch, bool* handled);
 zos_status launch_generate(zos_ctx* ctx, const DevImage& dst, const float* p, uint32_t batch, bool solid);
