@@ -79,8 +79,11 @@ __device__ void tile_geometry(const AffParams& P, uint32_t t, Geo& g) {
   minx = fmaxf(minx, 0.0f); miny = fmaxf(miny, 0.0f);
   maxx = fminf(maxx, (float)P.sfw); maxy = fminf(maxy, (float)P.sfh);
   if (minx > maxx || miny > maxy) return;
-  int lox = max((int)floorf(minx) - 2 - P.sox, 0), hix = min((int)floorf(maxx) + 2 - P.sox, P.aw - 1);
-  int loy = max((int)floorf(miny) - 2 - P.soy, 0), hiy = min((int)floorf(maxy) + 2 - P.soy, P.ah - 1);
+  // The mapping is monotone in x and in y separately, in floating point too (fmaf is monotone in each
+  // argument), so the corner values bound every pixel of the tile exactly; bilinear taps of a pixel at p
+  // are floor(p - 0.5) and that + 1, i.e. within [floor(min) - 1, floor(max) + 1].
+  int lox = max((int)floorf(minx) - 1 - P.sox, 0), hix = min((int)floorf(maxx) + 1 - P.sox, P.aw - 1);
+  int loy = max((int)floorf(miny) - 1 - P.soy, 0), hiy = min((int)floorf(maxy) + 1 - P.soy, P.ah - 1);
   if (lox > hix || loy > hiy) return;
   lox &= ~1;  // 8-byte texels: a 16-byte aligned TMA source address
   g.any = 1;
@@ -133,43 +136,121 @@ __device__ __forceinline__ float4 sample(const AffParams& P, float px, float py,
   return o;
 }
 
-template <bool BILINEAR, bool SMEM>
-__device__ __forceinline__ void compute_tile(const AffParams& P, const Geo& g, uint32_t stage_addr) {
+// predicated loads: no branch, no valid address needed when the predicate is off
+__device__ __forceinline__ uint2 lds64_if(uint32_t a, bool p) {
+  uint2 w = make_uint2(0u, 0u);
+  asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q ld.shared.v2.u32 {%0, %1}, [%2];\n\t}" : "+r"(w.x), "+r"(w.y) : "r"(a), "r"((uint32_t)p));
+  return w;
+}
+__device__ __forceinline__ uint2 ldg64_cs_if(const uint8_t* ptr, bool p) {
+  uint2 w = make_uint2(0u, 0u);
+  asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q ld.global.cs.v2.u32 {%0, %1}, [%2];\n\t}" : "+r"(w.x), "+r"(w.y) : "l"(ptr), "r"((uint32_t)p));
+  return w;
+}
+
+// The tile from the staged box, branch-free: GROUP rows of a thread are set up together (coordinates,
+// coverage, tap addresses), their loads are issued predicated and back to back, then the arithmetic
+// runs for all of them; uncovered pixels take `below` (or the clear colour) through a select.
+template <bool BILINEAR, int GROUP>
+__device__ __forceinline__ void compute_tile_smem(const AffParams& P, const Geo& g, uint32_t stage_addr) {
   const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
   const int i = g.x0 + lx;
   if (i >= P.dw) return;
   const float cx = (float)(i + P.dox) + 0.5f;
   const float tx = fmaf(P.inv[0], cx, P.inv[2]), ty = fmaf(P.inv[3], cx, P.inv[5]);
   const float sfw = (float)P.sfw, sfh = (float)P.sfh;
-  const uint32_t rowb = SMEM ? (uint32_t)P.box_w * 8u : (uint32_t)P.above_pitch;
-  // address of texel (0, 0) of the full source: window origin and box origin folded in once per tile
+  const uint32_t rowb = (uint32_t)P.box_w * 8u;
   const uint32_t base = stage_addr - (uint32_t)(g.by + P.soy) * rowb - (uint32_t)(g.bx + P.sox) * 8u;
-  const uint8_t* gbase = P.above + (uint64_t)g.frame * P.above_bstride - (int64_t)P.soy * (int64_t)P.above_pitch - (int64_t)P.sox * 8;
-  const uint64_t off0 = (uint64_t)g.frame * P.dst_bstride + (uint64_t)(g.y0 + ly) * P.dst_pitch + (uint64_t)i * 8u;
-  const uint64_t boff0 = (uint64_t)g.frame * P.below_bstride + (uint64_t)(g.y0 + ly) * P.below_pitch + (uint64_t)i * 8u;
+  const int xmax = P.sfw - 1, ymax = P.sfh - 1;
+  uint8_t* dp = P.dst + (uint64_t)g.frame * P.dst_bstride + (uint64_t)(g.y0 + ly) * P.dst_pitch + (uint64_t)i * 8u;
+  const uint8_t* bp = P.below + (uint64_t)g.frame * P.below_bstride + (uint64_t)(g.y0 + ly) * P.below_pitch + (uint64_t)i * 8u;
+  const uint64_t dstep = (uint64_t)(THREADS / 32) * P.dst_pitch, bstep = (uint64_t)(THREADS / 32) * P.below_pitch;
+  const bool has_below = P.has_below != 0;
+  const float cy0 = (float)(g.y0 + ly + P.doy) + 0.5f;
 #pragma unroll
-  for (int k = 0; k < ROWS; k++) {
-    const int j = g.y0 + ly + (THREADS / 32) * k;
-    if (j < P.dh) {
-      const float cy = (float)(j + P.doy) + 0.5f;
+  for (int k0 = 0; k0 < ROWS; k0 += GROUP) {
+    bool live[GROUP], cov[GROUP];
+    float ax[GROUP], ay[GROUP];
+    uint2 w00[GROUP], w10[GROUP], w01[GROUP], w11[GROUP], wb[GROUP];
+#pragma unroll
+    for (int q = 0; q < GROUP; q++) {
+      const int j = g.y0 + ly + (THREADS / 32) * (k0 + q);
+      live[q] = j < P.dh;
+      const float cy = cy0 + (float)((THREADS / 32) * (k0 + q));  // == (float)(j + doy) + 0.5f: all three are exact
       const float px = fmaf(P.inv[1], cy, tx), py = fmaf(P.inv[4], cy, ty);
-      const bool covered = px >= 0.0f && px < sfw && py >= 0.0f && py < sfh;
-      float4 v = make_float4(0.0f, 0.0f, 1.0f, 1.0f);  // Target::Discard clear colour
-      if (covered) v = sample<BILINEAR, SMEM>(P, px, py, base, gbase, rowb);
-      if (P.has_below && !(covered && P.blend == ZOS_BLEND_OVERWRITE)) {
-        const uint2 w = __ldcs(reinterpret_cast<const uint2*>(P.below + boff0 + (uint64_t)((THREADS / 32) * k) * P.below_pitch));
-        const float4 b = half4_to_float4(w);
-        v = covered ? porter_duff(P.blend, v, b) : b;
+      cov[q] = live[q] && px >= 0.0f && px < sfw && py >= 0.0f && py < sfh;
+      if (BILINEAR) {
+        const float fx = px - 0.5f, fy = py - 0.5f;
+        // floor as ONE conversion; back to float on the integer pipe (exact: |fx| < 2^23 for covered pixels)
+        const int x0 = __float2int_rd(fx), y0 = __float2int_rd(fy);
+        const float x0f = (float)x0, y0f = (float)y0;
+        ax[q] = fx - x0f; ay[q] = fy - y0f;
+        // covered: px in [0, sfw) so x0 in [-1, sfw-1]: clamp(x0) = max(x0, 0), clamp(x0 + 1) = min(x0 + 1, sfw - 1)
+        const int xa = max(x0, 0), xb = min(x0 + 1, xmax), ya = max(y0, 0), yb = min(y0 + 1, ymax);
+        const uint32_t ra = base + (uint32_t)ya * rowb, rb = base + (uint32_t)yb * rowb;
+        w00[q] = lds64_if(ra + (uint32_t)xa * 8u, cov[q]); w10[q] = lds64_if(ra + (uint32_t)xb * 8u, cov[q]);
+        w01[q] = lds64_if(rb + (uint32_t)xa * 8u, cov[q]); w11[q] = lds64_if(rb + (uint32_t)xb * 8u, cov[q]);
+      } else {
+        const int u = (int)floorf(px), w = (int)floorf(py);
+        w00[q] = lds64_if(base + (uint32_t)w * rowb + (uint32_t)u * 8u, cov[q]);
+      }
+      wb[q] = ldg64_cs_if(bp + (uint64_t)(k0 + q) * bstep, has_below && live[q] && !cov[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < GROUP; q++) {
+      float4 v;
+      if (BILINEAR) {
+        const float4 p00 = half4_to_float4(w00[q]), p10 = half4_to_float4(w10[q]), p01 = half4_to_float4(w01[q]), p11 = half4_to_float4(w11[q]);
+#define ZOS_LERP2(c) { float top = fmaf(ax[q], p10.c - p00.c, p00.c), bot = fmaf(ax[q], p11.c - p01.c, p01.c); v.c = fmaf(ay[q], bot - top, top); }
+        ZOS_LERP2(x) ZOS_LERP2(y) ZOS_LERP2(z) ZOS_LERP2(w)
+#undef ZOS_LERP2
+      } else {
+        v = half4_to_float4(w00[q]);
       }
       __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
-      __stcs(reinterpret_cast<uint2*>(P.dst + off0 + (uint64_t)((THREADS / 32) * k) * P.dst_pitch),
-             make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi)));
+      uint2 o = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      // uncovered: `below` as it is (f16 -> f32 -> f16 is the identity), else the clear colour (0, 0, 1, 1)
+      if (!cov[q]) o = has_below ? wb[q] : make_uint2(0u, 0x3c003c00u);
+      if (live[q]) __stcs(reinterpret_cast<uint2*>(dp + (uint64_t)(k0 + q) * dstep), o);
     }
   }
 }
 
+// Tiles whose footprint does not fit the box (strong minification) or that no covered pixel touches:
+// taps straight from global memory.
 template <bool BILINEAR>
-__global__ void __launch_bounds__(THREADS, 4) k_affine_f16(const __grid_constant__ AffParams P, const __grid_constant__ TensorMaps M) {
+__device__ __forceinline__ void compute_tile_global(const AffParams& P, const Geo& g) {
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int i = g.x0 + lx;
+  if (i >= P.dw) return;
+  const float cx = (float)(i + P.dox) + 0.5f;
+  const float tx = fmaf(P.inv[0], cx, P.inv[2]), ty = fmaf(P.inv[3], cx, P.inv[5]);
+  const float sfw = (float)P.sfw, sfh = (float)P.sfh;
+  const uint32_t rowb = (uint32_t)P.above_pitch;
+  const uint8_t* gbase = P.above + (uint64_t)g.frame * P.above_bstride - (int64_t)P.soy * (int64_t)P.above_pitch - (int64_t)P.sox * 8;
+  const uint64_t off0 = (uint64_t)g.frame * P.dst_bstride + (uint64_t)(g.y0 + ly) * P.dst_pitch + (uint64_t)i * 8u;
+  const uint64_t boff0 = (uint64_t)g.frame * P.below_bstride + (uint64_t)(g.y0 + ly) * P.below_pitch + (uint64_t)i * 8u;
+#pragma unroll 1
+  for (int k = 0; k < ROWS; k++) {
+    const int j = g.y0 + ly + (THREADS / 32) * k;
+    if (j >= P.dh) break;
+    const float cy = (float)(j + P.doy) + 0.5f;
+    const float px = fmaf(P.inv[1], cy, tx), py = fmaf(P.inv[4], cy, ty);
+    const bool covered = px >= 0.0f && px < sfw && py >= 0.0f && py < sfh;
+    uint2 o = make_uint2(0u, 0x3c003c00u);  // Target::Discard clear colour (0, 0, 1, 1)
+    if (covered) {
+      const float4 v = sample<BILINEAR, false>(P, px, py, 0u, gbase, rowb);
+      __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+      o = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    } else if (P.has_below) {
+      o = __ldcs(reinterpret_cast<const uint2*>(P.below + boff0 + (uint64_t)((THREADS / 32) * k) * P.below_pitch));
+    }
+    __stcs(reinterpret_cast<uint2*>(P.dst + off0 + (uint64_t)((THREADS / 32) * k) * P.dst_pitch), o);
+  }
+}
+
+template <bool BILINEAR, int GROUP, int CTAS>
+__global__ void __launch_bounds__(THREADS, CTAS) k_affine_f16(const __grid_constant__ AffParams P, const __grid_constant__ TensorMaps M) {
   extern __shared__ __align__(128) uint8_t dyn[];
   __shared__ __align__(8) uint64_t bar[2];
   __shared__ Geo geo[2];
@@ -206,10 +287,10 @@ __global__ void __launch_bounds__(THREADS, 4) k_affine_f16(const __grid_constant
         if (++spins > (1u << 24)) { if (P.fault) *reinterpret_cast<volatile int*>(P.fault) = 1; break; }
       }
       phase[s] ^= 1;
-      compute_tile<BILINEAR, true>(P, g, smem_u32(dyn + (size_t)s * stage_bytes));
+      compute_tile_smem<BILINEAR, GROUP>(P, g, smem_u32(dyn + (size_t)s * stage_bytes));
     } else {
       // no covered pixel (copies `below`), or a footprint larger than the box (strong minification): global taps
-      compute_tile<BILINEAR, false>(P, g, 0u);
+      compute_tile_global<BILINEAR>(P, g);
     }
     __syncthreads();  // stage s is free again; geo[s ^ 1] (written by thread 0 above) is visible
     s ^= 1;
@@ -230,7 +311,7 @@ zos_status launch_affine_f16(zos_ctx* ctx, const DevImage* below, const DevImage
                              const zos_compose_params& cp, uint32_t batch, bool* handled) {
   *handled = false;
   if ((ctx->flags & ZOS_CTX_NO_FAST_PATHS) || !cp.use_tma || cp.map != ZOS_MAP_AFFINE) return ZOS_OK;
-  if (cp.blend == ZOS_BLEND_INJECT || cp.n_src_steps || cp.n_dst_steps) return ZOS_OK;
+  if (cp.blend != ZOS_BLEND_OVERWRITE || cp.n_src_steps || cp.n_dst_steps) return ZOS_OK;  // the reference's affine: no blending (encoder.rs:1493)
   if (cp.sampling != ZOS_SAMPLE_NEAREST && cp.sampling != ZOS_SAMPLE_BILINEAR) return ZOS_OK;
   if (!plain_f16(above) || !plain_f16(dst) || (below && !plain_f16(*below))) return ZOS_OK;
   AffParams P;
@@ -253,8 +334,11 @@ zos_status launch_affine_f16(zos_ctx* ctx, const DevImage* below, const DevImage
   P.div_tx = make_fastdiv(P.tiles_x); P.div_ty = make_fastdiv(P.tiles_y);
   const float ex = (TILE - 1) * (fabsf(P.inv[0]) + fabsf(P.inv[1])), ey = (TILE - 1) * (fabsf(P.inv[3]) + fabsf(P.inv[4]));
   if (!(ex < 200.0f) || !(ey < 200.0f)) return ZOS_OK;
-  P.box_w = ((int)ceilf(ex) + 6 + 1 + 1) & ~1;
-  P.box_h = (int)ceilf(ey) + 6;
+  // taps span ceil(extent) + 4 texels, + 1 for the even box origin; a row of 8 * (4k + 2) bytes puts
+  // vertically adjacent taps 4 banks apart (a multiple of 128 bytes would put them on the same bank)
+  P.box_w = (int)ceilf(ex) + 5;
+  while ((P.box_w & 3) != 2) P.box_w++;
+  P.box_h = (int)ceilf(ey) + 4;
   const size_t stage = ((size_t)P.box_w * P.box_h * 8 + 127) & ~(size_t)127;
   const size_t smem = 2 * stage;
   if (P.box_w * 2 > 256 || P.box_h > 256 || smem > 96 * 1024) return ZOS_OK;
@@ -263,18 +347,26 @@ zos_status launch_affine_f16(zos_ctx* ctx, const DevImage* below, const DevImage
   if (!make_map(ctx, &M.m0, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, above.p0, (uint64_t)above.w * 2, above.h, above.pitch, batch, above.bstride,
                 (uint32_t)P.box_w * 2, (uint32_t)P.box_h))
     return ZOS_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_affine_f16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    cudaFuncSetAttribute(k_affine_f16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr_set = true;
-  }
-  int per_sm = (int)((220 * 1024) / (smem + 2048));
-  per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+  int group = 2;
+  if (const char* e = getenv("ZOS_AFFINE_GROUP")) group = atoi(e);
+  int per_sm = (int)((228 * 1024) / (smem + 1024 + 256));
+  const int max_ctas = group == 4 ? 3 : 5;
+  per_sm = per_sm < 1 ? 1 : (per_sm > max_ctas ? max_ctas : per_sm);
+  if (const char* e = getenv("ZOS_AFFINE_CTAS")) per_sm = atoi(e);
   const uint64_t cap = (uint64_t)ctx->sm_count * per_sm;
   const int grid = (int)(total < cap ? total : cap);
-  if (cp.sampling == ZOS_SAMPLE_BILINEAR) k_affine_f16<true><<<grid, THREADS, smem, ctx->stream>>>(P, M);
-  else k_affine_f16<false><<<grid, THREADS, smem, ctx->stream>>>(P, M);
+#define ZOS_AFF_LAUNCH(B, G, C)                                                                          \
+  do {                                                                                                    \
+    static bool attr_set = false;                                                                         \
+    if (!attr_set) { cudaFuncSetAttribute(k_affine_f16<B, G, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr_set = true; } \
+    k_affine_f16<B, G, C><<<grid, THREADS, smem, ctx->stream>>>(P, M);                                     \
+  } while (0)
+  const bool bil = cp.sampling == ZOS_SAMPLE_BILINEAR;
+  if (bil && group == 4) ZOS_AFF_LAUNCH(true, 4, 3);
+  else if (bil) ZOS_AFF_LAUNCH(true, 2, 5);
+  else if (group == 4) ZOS_AFF_LAUNCH(false, 4, 3);
+  else ZOS_AFF_LAUNCH(false, 2, 5);
+#undef ZOS_AFF_LAUNCH
   ctx->launches++;
   *handled = true;
   return check_cuda(ctx, cudaGetLastError(), "k_affine_f16 launch");
