@@ -20,6 +20,8 @@
 // None of this exists in the reference (no planar texels, no bilinear, no blend: SURVEY.md 0.2);
 // semantics are DESIGN.md section 3, the oracle is oracle/zos_oracle.c (zo_decode_yuv420, zo_linear,
 // zo_resize, zo_blend, zo_encode).
+#include <stdlib.h>
+
 #include "colorops.cuh"
 #include "tma.cuh"
 #include "zos_internal.h"
@@ -52,6 +54,10 @@ struct FrameParams {
   FastDiv div_tx, div_ty;
   int32_t box_w, box_h, cbox_w, cbox_h, conv_w, conv_h;
   int* fault;  // mapped host word set when an mbarrier wait runs away
+  // k_frame_fast
+  uint32_t clear_word;  // the encoded Target::Discard clear colour (0, 0, 1, 1)
+  uint32_t spack;       // byte-permute selector of the destination word (RGBA / BGRA)
+  uint32_t plane_bytes; // bytes of one plane of the converted footprint
 };
 
 struct TileGeo {
@@ -262,6 +268,196 @@ __global__ void __launch_bounds__(THREADS, 3) k_frame_pipeline(const __grid_cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_frame_fast: the same pipeline specialised at compile time for what BASELINE config 4 runs:
+// BT.709-family or linear EOTF, native 8-bit destination, background (if any) in the destination's
+// texel.  Same arithmetic as k_frame_pipeline, far fewer instructions:
+//   * a planar-YUV frame is opaque (alpha = 1 exactly), so source-over of a covered pixel IS the frame's
+//     colour (fmaf(0, b, 1 * v) * 1 == v): neither decode nor blend, and `below` is only read - as raw
+//     words, decode -> encode being the identity - where the frame does not cover the destination;
+//   * the converted footprint is kept as three f32 planes (no alpha plane), sized by the exact tap span;
+//   * sRGB8 encode through the bucket table (texel.cuh): one look-up per channel, no transcendental;
+//   * no run-time format / transfer / sampling switches.
+constexpr int FER = 4;  // replication of the encoder bucket table in shared memory
+
+template <int TRK>
+__device__ __forceinline__ float eotf_k(uint32_t tr, float v) {
+  if (TRK == 0) {  // BT.709 / BT.2020 10- and 12-bit: one curve
+    float lin = v * (1.0f / 4.5f);
+    float l2, pw;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"((v + 0.099f) * (1.0f / 1.099f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pw) : "f"(l2 * (1.0f / 0.45f)));
+    return v >= 0.0812428582f ? pw : lin;
+  }
+  if (TRK == 1) return v;
+  return eo_scalar(tr, v);
+}
+
+template <int TRK>
+__device__ __forceinline__ void convert_store(const FrameParams& P, float Y, float cb, float cr, uint32_t addr) {
+  const float y = (Y - P.yoff) * P.ysc;
+  float r = fmaf(P.r_cr, cr, y), g = fmaf(-P.g_cb, cb, fmaf(-P.g_cr, cr, y)), b = fmaf(P.b_cb, cb, y);
+  r = eotf_k<TRK>(P.transfer, r); g = eotf_k<TRK>(P.transfer, g); b = eotf_k<TRK>(P.transfer, b);
+  if (P.nmat) {
+    float3 t = mat3_mul(P.m, r, g, b);
+    r = t.x; g = t.y; b = t.z;
+  }
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(r) : "memory");
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr + P.plane_bytes), "f"(g) : "memory");
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr + 2u * P.plane_bytes), "f"(b) : "memory");
+}
+
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+
+// correctly rounded sRGB8 code of x in [0, 1], in byte 2 of the result (see texel.cuh)
+__device__ __forceinline__ uint32_t srgb_code_b2(float x, uint32_t enc_lane) {
+  const int idx = max(__float_as_int(x), ZOS_ENC_B0 << 16);
+  const uint32_t a = ((((uint32_t)idx >> 16) - (uint32_t)ZOS_ENC_B0) * (FER * 4u)) + enc_lane;
+  uint32_t e;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(a));
+  return e + (uint32_t)idx;
+}
+
+template <bool BILINEAR, bool SRGB_DST, int TRK>
+__global__ void __launch_bounds__(THREADS, 3) k_frame_fast(const __grid_constant__ FrameParams P, const __grid_constant__ TensorMaps M) {
+  extern __shared__ __align__(128) uint8_t dyn[];
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ TileGeo geo[2];
+  const uint32_t cstep = P.nv12 ? 2 : 1;
+  const uint32_t ybox = (uint32_t)P.box_w * P.box_h, cbox = (uint32_t)P.cbox_w * P.cbox_h * cstep;
+  const uint32_t ybox_al = (ybox + 127) & ~127u, cbox_al = (cbox + 127) & ~127u;
+  const uint32_t nchroma = P.nv12 ? 1 : 2;
+  const uint32_t stage_bytes = ybox_al + nchroma * cbox_al;
+  const uint32_t conv_base = smem_u32(dyn + 2 * (size_t)stage_bytes);
+  uint32_t* enc = reinterpret_cast<uint32_t*>(dyn + 2 * (size_t)stage_bytes + 3 * (size_t)P.plane_bytes);
+  if (SRGB_DST) {
+    for (int i = threadIdx.x; i < ZOS_ENC_N * FER; i += THREADS) enc[i] = g_tables.srgb_enc[i / FER];
+  }
+  const uint32_t enc_lane = smem_u32(enc) + (threadIdx.x & (FER - 1)) * 4u;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const CUtensorMap* const m0 = &M.m0;
+  const CUtensorMap* const m1 = &M.m1;
+  const CUtensorMap* const m2 = &M.m2;
+  if (threadIdx.x == 0 && blockIdx.x < P.total_tiles) ZOS_FRAME_ISSUE(blockIdx.x, 0);
+  __syncthreads();
+  uint32_t phase[2] = {0, 0};
+  int s = 0;
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const uint32_t cw4 = (uint32_t)P.conv_w * 4u;
+  for (uint32_t t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+    const uint32_t next = t + gridDim.x;
+    if (threadIdx.x == 0 && next < P.total_tiles) ZOS_FRAME_ISSUE(next, s ^ 1);
+    const TileGeo g = geo[s];
+    if (g.any) {
+      uint32_t spins = 0;
+      while (!mbar_try_wait(&bar[s], phase[s])) {
+        if (++spins > (1u << 24)) { if (P.fault) *reinterpret_cast<volatile int*>(P.fault) = 1; break; }
+      }
+      phase[s] ^= 1;
+      // ---- phase 1: the footprint, one 2x2 luma block per thread
+      const uint32_t ybase = smem_u32(dyn + (size_t)s * stage_bytes);
+      const uint32_t ubase = ybase + ybox_al, vbase = P.nv12 ? ubase + 1 : ubase + cbox_al;
+      const int offx = g.fx0 - g.bx, offy = g.fy0 - g.by;  // both even
+      const int cbw = P.conv_w >> 1, cbh = P.conv_h >> 1;
+      if (lx < cbw) {
+        for (int byi = ly; byi < cbh; byi += THREADS / 32) {
+          const uint32_t ya = ybase + (uint32_t)((offy + 2 * byi) * P.box_w + offx + 2 * lx);
+          const uint32_t ca = (uint32_t)(((offy >> 1) + byi) * P.cbox_w + (offx >> 1) + lx) * cstep;
+          uint32_t y01, y23, u8, v8;
+          asm("ld.shared.u16 %0, [%1];" : "=r"(y01) : "r"(ya));
+          asm("ld.shared.u16 %0, [%1];" : "=r"(y23) : "r"(ya + (uint32_t)P.box_w));
+          asm("ld.shared.u8 %0, [%1];" : "=r"(u8) : "r"(ubase + ca));
+          asm("ld.shared.u8 %0, [%1];" : "=r"(v8) : "r"(vbase + ca));
+          const float cb = ((float)u8 - 128.0f) * P.csc, cr = ((float)v8 - 128.0f) * P.csc;
+          const uint32_t o = conv_base + (uint32_t)((2 * byi) * P.conv_w + 2 * lx) * 4u;
+          convert_store<TRK>(P, (float)(y01 & 255u), cb, cr, o);
+          convert_store<TRK>(P, (float)(y01 >> 8), cb, cr, o + 4u);
+          convert_store<TRK>(P, (float)(y23 & 255u), cb, cr, o + cw4);
+          convert_store<TRK>(P, (float)(y23 >> 8), cb, cr, o + cw4 + 4u);
+        }
+      }
+      __syncthreads();
+    }
+    // ---- phase 2: sample, pack
+    const int i = g.x0 + lx;
+    if (i < P.dw) {
+      const int kx = i - P.tgt[0];
+      const bool col_in = g.any && kx >= 0 && kx < P.tgt[2];
+      uint32_t xa4 = 0, xb4 = 0;  // byte offsets of the horizontal taps inside a footprint row
+      float ax = 0.0f;
+      if (col_in) {
+        int xa, xb;
+        if (!BILINEAR) {
+          xa = xb = min(max(P.sel[0] + rect_index(kx, P.sel[2], P.tgt[2]), 0), P.sw - 1);
+        } else {
+          const float px = (float)P.sel[0] + ((float)kx + 0.5f) * P.rx;
+          const float fx = px - 0.5f, x0f = floorf(fx);
+          ax = fx - x0f;
+          const int x0 = (int)x0f;
+          xb = min(max(x0 + 1, 0), P.sw - 1);
+          xa = min(max(x0, 0), P.sw - 1);
+        }
+        xa4 = (uint32_t)(xa - g.fx0) * 4u; xb4 = (uint32_t)(xb - g.fx0) * 4u;
+      }
+      const uint64_t off0 = (uint64_t)g.frame * P.dst_bstride + (uint64_t)(g.y0 + ly) * P.dst_pitch + (uint64_t)i * 4u;
+      const uint64_t boff0 = (uint64_t)g.frame * P.below_bstride + (uint64_t)(g.y0 + ly) * P.below_pitch + (uint64_t)i * 4u;
+#pragma unroll
+      for (int k = 0; k < TILE / 8; k++) {
+        const int j = g.y0 + ly + 8 * k;
+        if (j < P.dh) {
+          const int ky = j - P.tgt[1];
+          const bool covered = col_in && ky >= 0 && ky < P.tgt[3];
+          uint32_t word = P.clear_word;
+          if (covered) {
+            float r, gg, b;
+            if (!BILINEAR) {
+              const int w = min(max(P.sel[1] + rect_index(ky, P.sel[3], P.tgt[3]), 0), P.sh - 1) - g.fy0;
+              const uint32_t a = conv_base + (uint32_t)w * cw4 + xa4;
+              r = lds32(a); gg = lds32(a + P.plane_bytes); b = lds32(a + 2u * P.plane_bytes);
+            } else {
+              const float py = (float)P.sel[1] + ((float)ky + 0.5f) * P.ry;
+              const float fy = py - 0.5f, y0f = floorf(fy);
+              const float ay = fy - y0f;
+              const int y0 = (int)y0f;
+              const int yb = min(max(y0 + 1, 0), P.sh - 1) - g.fy0, ya = min(max(y0, 0), P.sh - 1) - g.fy0;
+              const uint32_t ra = conv_base + (uint32_t)ya * cw4, rb = conv_base + (uint32_t)yb * cw4;
+              const uint32_t a00 = ra + xa4, a10 = ra + xb4, a01 = rb + xa4, a11 = rb + xb4;
+#define ZOS_TAP(dst_, off_) { const float p00 = lds32(a00 + (off_)), p10 = lds32(a10 + (off_)), p01 = lds32(a01 + (off_)), p11 = lds32(a11 + (off_)); \
+                              const float top = fmaf(ax, p10 - p00, p00), bot = fmaf(ax, p11 - p01, p01); dst_ = fmaf(ay, bot - top, top); }
+              ZOS_TAP(r, 0u) ZOS_TAP(gg, P.plane_bytes) ZOS_TAP(b, 2u * P.plane_bytes)
+#undef ZOS_TAP
+            }
+            // alpha of the frame is exactly 1: source-over == the frame's colour, alpha code 255
+            r = fminf(fmaxf(r, 0.0f), 1.0f); gg = fminf(fmaxf(gg, 0.0f), 1.0f); b = fminf(fmaxf(b, 0.0f), 1.0f);
+            uint32_t t1, t2;
+            if (SRGB_DST) {
+              t1 = __byte_perm(srgb_code_b2(r, enc_lane), srgb_code_b2(gg, enc_lane), 0x0062);
+              t2 = __byte_perm(srgb_code_b2(b, enc_lane), 0xffu, 0x0042);
+            } else {
+              t1 = __byte_perm(__float_as_uint(r * 255.0f + 8388608.0f), __float_as_uint(gg * 255.0f + 8388608.0f), 0x0040);
+              t2 = __byte_perm(__float_as_uint(b * 255.0f + 8388608.0f), 0xffu, 0x0040);
+            }
+            word = __byte_perm(t1, t2, P.spack);
+          } else if (P.has_below) {
+            word = __ldcs(reinterpret_cast<const uint32_t*>(P.below + boff0 + (uint64_t)(8 * k) * P.below_pitch));
+          }
+          __stcs(reinterpret_cast<uint32_t*>(P.dst + off0 + (uint64_t)(8 * k) * P.dst_pitch), word);
+        }
+      }
+    }
+    __syncthreads();  // conv and stage s are free again; geo[s ^ 1] (written by thread 0 above) is visible
+    s ^= 1;
+  }
+}
+
 bool native8(const DevImage& im) {
   return im.block == ZOS_BLOCK_PIXEL && im.bpp == 4 && (im.fmt.storage == ZOS_STORAGE_SRGB8 || im.fmt.storage == ZOS_STORAGE_UNORM8) &&
          ((uintptr_t)im.p0 % 4) == 0 && (im.pitch % 4) == 0 && (im.bstride % 4) == 0;
@@ -331,6 +527,52 @@ zos_status launch_frame_pipeline(zos_ctx* ctx, const DevImage* below, const DevI
     ok = make_map(ctx, &M.m1, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, above.p1, cw, ch, above.cpitch, batch, above.cbstride, P.cbox_w, P.cbox_h) &&
          make_map(ctx, &M.m2, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, above.p2, cw, ch, above.cpitch, batch, above.cbstride, P.cbox_w, P.cbox_h);
   if (!ok) return ZOS_OK;
+  // the compile-time specialised kernel: known EOTF class, background (if any) in the destination's texel
+  const uint32_t tr = above.fmt.transfer;
+  const int trk = (tr == ZOS_TRANSFER_BT709 || tr == ZOS_TRANSFER_BT2020_10BIT || tr == ZOS_TRANSFER_BT2020_12BIT) ? 0 : tr == ZOS_TRANSFER_LINEAR ? 1 : 2;
+  const bool same_texel = !below || (below->fmt.storage == dst.fmt.storage && below->fmt.parts == dst.fmt.parts);
+  const bool rgba_like = dst.fmt.parts == ZOS_PARTS_RGBA || dst.fmt.parts == ZOS_PARTS_BGRA;
+  if (trk != 2 && same_texel && rgba_like && !getenv("ZOS_FRAME_GENERIC")) {
+    const bool srgb = dst.fmt.storage == ZOS_STORAGE_SRGB8;
+    const bool bgra = dst.fmt.parts == ZOS_PARTS_BGRA;
+    P.clear_word = bgra ? 0xff0000ffu : 0xffff0000u;  // (0, 0, 1, 1): both codecs map 0 -> 0 and 1 -> 255
+    P.spack = bgra ? 0x5014u : 0x5410u;
+    // exact tap span of 32 destination pixels: floor(min - 0.5) rounded down to even ... floor(max - 0.5) + 1
+    P.conv_w = ((int)ceilf((TILE - 1) * P.rx) + 5) & ~1;
+    P.conv_h = ((int)ceilf((TILE - 1) * P.ry) + 5) & ~1;
+    P.box_w = (P.conv_w + 31 + 31) & ~31;
+    P.box_h = P.conv_h;
+    P.cbox_w = P.box_w / 2; P.cbox_h = P.box_h / 2;
+    ybox_al = ((size_t)P.box_w * P.box_h + 127) & ~(size_t)127; cbox_al = ((size_t)P.cbox_w * P.cbox_h * cstep + 127) & ~(size_t)127;
+    stage = ybox_al + (P.nv12 ? 1 : 2) * cbox_al;
+    P.plane_bytes = (uint32_t)(P.conv_w * P.conv_h * 4);
+    const size_t fsmem = 2 * stage + 3 * (size_t)P.plane_bytes + (srgb ? (size_t)ZOS_ENC_N * FER * 4 : 0);
+    bool ok2 = make_map(ctx, &M.m0, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, above.p0, above.w, above.h, above.pitch, batch, above.bstride, P.box_w, P.box_h);
+    if (ok2 && P.nv12) ok2 = make_map(ctx, &M.m1, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, above.p1, cw, ch, above.cpitch, batch, above.cbstride, P.cbox_w, P.cbox_h);
+    if (ok2 && !P.nv12)
+      ok2 = make_map(ctx, &M.m1, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, above.p1, cw, ch, above.cpitch, batch, above.cbstride, P.cbox_w, P.cbox_h) &&
+            make_map(ctx, &M.m2, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, above.p2, cw, ch, above.cpitch, batch, above.cbstride, P.cbox_w, P.cbox_h);
+    if (ok2 && fsmem <= 160 * 1024) {
+      int per_sm = (int)((226 * 1024) / (fsmem + 1024 + 256));
+      per_sm = per_sm < 1 ? 1 : (per_sm > 3 ? 3 : per_sm);
+      const uint64_t cap = (uint64_t)ctx->sm_count * per_sm;
+      const int grid = (int)(total < cap ? total : cap);
+      const bool bil = cp.sampling != ZOS_SAMPLE_NEAREST;
+#define ZOS_FF(B, S, T)                                                                                          \
+  do {                                                                                                            \
+    static bool set_ = false;                                                                                     \
+    if (!set_) { cudaFuncSetAttribute(k_frame_fast<B, S, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); set_ = true; } \
+    k_frame_fast<B, S, T><<<grid, THREADS, fsmem, ctx->stream>>>(P, M);                                            \
+  } while (0)
+      if (trk == 0) { if (bil) { if (srgb) ZOS_FF(true, true, 0); else ZOS_FF(true, false, 0); } else { if (srgb) ZOS_FF(false, true, 0); else ZOS_FF(false, false, 0); } }
+      else { if (bil) { if (srgb) ZOS_FF(true, true, 1); else ZOS_FF(true, false, 1); } else { if (srgb) ZOS_FF(false, true, 1); else ZOS_FF(false, false, 1); } }
+#undef ZOS_FF
+      ctx->launches++;
+      *handled = true;
+      return check_cuda(ctx, cudaGetLastError(), "k_frame_fast launch");
+    }
+    return ZOS_OK;  // (maps were rebuilt for the smaller box: leave this launch to the general kernel)
+  }
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(k_frame_pipeline, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr_set = true; }
   int per_sm = (int)((220 * 1024) / (smem + sizeof(Tables) + 2048));

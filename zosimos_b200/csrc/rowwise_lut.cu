@@ -23,13 +23,10 @@
 #include "zos_internal.h"
 #include "rowwise_params.cuh"
 
-#include <vector>
-
 namespace zos {
 
 constexpr int LUT_THREADS = 1024;
-constexpr int ENC_B0 = 0x3900;                   // top 16 bits of 2^-13
-constexpr int ENC_N = 0x3f80 - ENC_B0 + 1;       // buckets up to and including the one of 1.0
+constexpr int ENC_B0 = ZOS_ENC_B0, ENC_N = ZOS_ENC_N;  // the bucket table of texel.cuh
 constexpr int ER = 16;                           // replication of the encode table
 constexpr uint32_t DEC_BYTES = 256u * 256u;      // [code][0..31] sRGB EOTF, [code][32..63] code/255
 constexpr uint32_t ENC_BYTES = (uint32_t)ENC_N * ER * 4u;
@@ -37,30 +34,7 @@ constexpr uint32_t ENC_SHIFT = 16 - 6;           // bits >> 16 is the bucket, en
 constexpr uint32_t ENC_MASK = 0x7ffu * (ER * 4u);  // the low 11 bits of the bucket are unique over [ENC_B0, 0x3f80]
 constexpr uint32_t ENC_VOFF = (ENC_B0 & 0x7ff) * (ER * 4u);  // masked offset of the first bucket
 
-static __device__ uint32_t g_srgb_enc[ENC_N];
-
-ZOS_DEFINE_CONSTANT_UPLOAD(upload_constants_rowwise_lut_base)
-
-// the bucket table from the rounding thresholds (thr[k] = smallest f32 whose code is >= k)
-cudaError_t upload_constants_rowwise_lut(const TablesGlobal* t, const ColorConstants* c, cudaStream_t stream) {
-  cudaError_t e = upload_constants_rowwise_lut_base(t, c, stream);
-  if (e != cudaSuccess) return e;
-  static std::vector<uint32_t> enc;  // static: the async copy reads it after we return
-  enc.assign(ENC_N, 0);
-  auto bits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
-  for (int b = 0; b < ENC_N; b++) {
-    const uint32_t top = (uint32_t)(ENC_B0 + b), start = top << 16;
-    uint32_t base = 0;
-    while (base < 255 && bits(t->srgb_thr[base + 1]) <= start) base++;
-    uint32_t t16 = 0x10000u;
-    if (base < 255 && (bits(t->srgb_thr[base + 1]) >> 16) == top) {
-      t16 = bits(t->srgb_thr[base + 1]) & 0xffffu;
-      if (base + 2 <= 255 && (bits(t->srgb_thr[base + 2]) >> 16) == top) return cudaErrorInvalidValue;  // two thresholds in one bucket
-    }
-    enc[b] = (base << 16) + (0x10000u - t16) - (top << 16);
-  }
-  return cudaMemcpyToSymbolAsync(g_srgb_enc, enc.data(), sizeof(uint32_t) * ENC_N, 0, cudaMemcpyHostToDevice, stream);
-}
+ZOS_DEFINE_CONSTANT_UPLOAD(upload_constants_rowwise_lut)
 
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
   float v;
@@ -192,7 +166,7 @@ __global__ void __launch_bounds__(LUT_THREADS, 1) k_rowwise_lut(const __grid_con
   for (int i = threadIdx.x; i < 256 * 64; i += LUT_THREADS) dec[i] = (i & 32) ? g_tables.unorm8[i >> 6] : g_tables.srgb_dec[i >> 6];
   if (DK == K_SRGB8) {
 #pragma unroll 4
-    for (int i = threadIdx.x; i < ENC_N * ER; i += LUT_THREADS) enc[i] = g_srgb_enc[i / ER];
+    for (int i = threadIdx.x; i < ENC_N * ER; i += LUT_THREADS) enc[i] = g_tables.srgb_enc[i / ER];
   }
   __syncthreads();
 

@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "colorops.cuh"
@@ -54,7 +55,7 @@ static void mul3_d(const double* a, const double* b, double* o) {
   for (int r = 0; r < 3; r++)
     for (int c = 0; c < 3; c++) o[3 * r + c] = a[3 * r] * b[c] + a[3 * r + 1] * b[3 + c] + a[3 * r + 2] * b[6 + c];
 }
-static void build_constants(TablesGlobal* t, ColorConstants* c) {
+static bool build_constants(TablesGlobal* t, ColorConstants* c) {
   for (int k = 0; k < 256; k++) {
     t->srgb_dec[k] = (float)eotf_srgb_d(k / 255.0);
     t->unorm8[k] = (float)k / 255.0f;
@@ -67,6 +68,20 @@ static void build_constants(TablesGlobal* t, ColorConstants* c) {
     t->srgb_thr[k] = f;
   }
   for (int k = 256; k < 260; k++) t->srgb_thr[k] = INFINITY;
+  {  // bucket table of the exact encoder (texel.cuh); a bucket with two thresholds would break it: checked here
+    auto bits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
+    for (int b = 0; b < ZOS_ENC_N; b++) {
+      const uint32_t top = (uint32_t)(ZOS_ENC_B0 + b), start = top << 16;
+      uint32_t base = 0;
+      while (base < 255 && bits(t->srgb_thr[base + 1]) <= start) base++;
+      uint32_t t16 = 0x10000u;
+      if (base < 255 && (bits(t->srgb_thr[base + 1]) >> 16) == top) {
+        t16 = bits(t->srgb_thr[base + 1]) & 0xffffu;
+        if (base + 2 <= 255 && (bits(t->srgb_thr[base + 2]) >> 16) == top) return false;  // never happens for the sRGB curve; zos_ctx_create reports it
+      }
+      t->srgb_enc[b] = (base << 16) + (0x10000u - t16) - (top << 16);
+    }
+  }
   // Oklab M1, M2 (row-major; lib/std/src/oklab.frag:14-24 lists them column-major)
   static const float m1[9] = {0.8189330101f, 0.3618667424f, -0.1288597137f, 0.0329845436f, 0.9293118715f,
                               0.0361456387f, 0.0482003018f, 0.2643662691f, 0.6338517070f};
@@ -93,6 +108,7 @@ static void build_constants(TablesGlobal* t, ColorConstants* c) {
   for (int i = 0; i < 9; i++) c->sr_hpe_cati[i] = (float)tmp[i];
   mul3_d(cat, hpei, tmp);
   for (int i = 0; i < 9; i++) c->sr_cat_hpei[i] = (float)tmp[i];
+  return true;
 }
 
 static const float YUV_K[3][2] = {{0.299f, 0.114f}, {0.2126f, 0.0722f}, {0.2627f, 0.0593f}};
@@ -243,7 +259,7 @@ zos_status zos_ctx_create(int32_t device, zos_ctx** out) {
   {
     TablesGlobal* t = new TablesGlobal();
     ColorConstants* c = new ColorConstants();
-    build_constants(t, c);
+    if (!build_constants(t, c)) { delete t; delete c; st = fail(ctx, ZOS_ERR_INVALID, "internal: sRGB bucket table has two thresholds in one bucket"); goto bad; }
     cudaError_t e1 = upload_constants_rowwise(t, c, ctx->stream);
     cudaError_t e2 = upload_constants_gather(t, c, ctx->stream);
     cudaError_t e3 = upload_constants_misc(t, c, ctx->stream);

@@ -23,10 +23,18 @@ struct Tables {           // shared-memory copy, filled once per CTA
   float unorm8[256];      // k/255 (IEEE)
   float srgb_thr[260];    // thr[k] = smallest f32 whose correctly rounded sRGB8 code is >= k; [0] = -inf, [256] = +inf
 };
+// Bucket table of the exact sRGB8 encoder (rowwise_lut.cu, frame_pipeline.cu): the f32 bit patterns of
+// [2^-13, 1] cut into buckets of 2^16 patterns (sign / exponent / 7 mantissa bits).  No bucket holds more
+// than one rounding threshold, so with  e = (base << 16) + (0x10000 - t16) - (top16 << 16)  per bucket
+// (base = code at the bucket's start, t16 = low 16 bits of the threshold inside it, or 0x10000),
+// (e + bits(x)) >> 16 is the correctly rounded code of x.  Values below 2^-13 encode to 0.
+constexpr int ZOS_ENC_B0 = 0x3900;                    // top 16 bits of 2^-13
+constexpr int ZOS_ENC_N = 0x3f80 - ZOS_ENC_B0 + 1;    // up to and including the bucket of 1.0
 struct TablesGlobal {
   float srgb_dec[256];
   float unorm8[256];
   float srgb_thr[260];
+  uint32_t srgb_enc[ZOS_ENC_N];  // not part of the per-CTA copy `Tables`
 };
 // One copy per translation unit (no relocatable device code): every kernel .cu exports an
 // upload function built from ZOS_DEFINE_CONSTANT_UPLOAD (colorops.cuh) that runtime.cu calls at
