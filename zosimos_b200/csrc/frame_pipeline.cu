@@ -58,6 +58,7 @@ struct FrameParams {
   uint32_t clear_word;  // the encoded Target::Discard clear colour (0, 0, 1, 1)
   uint32_t spack;       // byte-permute selector of the destination word (RGBA / BGRA)
   uint32_t plane_bytes; // bytes of one plane of the converted footprint
+  FastDiv div_cbw;      // division by conv_w / 2
 };
 
 struct TileGeo {
@@ -294,17 +295,16 @@ __device__ __forceinline__ float eotf_k(uint32_t tr, float v) {
 }
 
 template <int TRK>
-__device__ __forceinline__ void convert_store(const FrameParams& P, float Y, float cb, float cr, uint32_t addr) {
+__device__ __forceinline__ float3 convert_rgb(const FrameParams& P, float Y, float cb, float cr) {
   const float y = (Y - P.yoff) * P.ysc;
   float r = fmaf(P.r_cr, cr, y), g = fmaf(-P.g_cb, cb, fmaf(-P.g_cr, cr, y)), b = fmaf(P.b_cb, cb, y);
   r = eotf_k<TRK>(P.transfer, r); g = eotf_k<TRK>(P.transfer, g); b = eotf_k<TRK>(P.transfer, b);
-  if (P.nmat) {
-    float3 t = mat3_mul(P.m, r, g, b);
-    r = t.x; g = t.y; b = t.z;
-  }
-  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(r) : "memory");
-  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr + P.plane_bytes), "f"(g) : "memory");
-  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr + 2u * P.plane_bytes), "f"(b) : "memory");
+  if (P.nmat) return mat3_mul(P.m, r, g, b);
+  return make_float3(r, g, b);
+}
+// two horizontally adjacent texels of one plane: 8-byte stores, a warp writes 256 contiguous bytes
+__device__ __forceinline__ void sts64(uint32_t addr, float a, float b) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
 }
 
 __device__ __forceinline__ float lds32(uint32_t a) {
@@ -367,22 +367,22 @@ __global__ void __launch_bounds__(THREADS, 3) k_frame_fast(const __grid_constant
       const uint32_t ubase = ybase + ybox_al, vbase = P.nv12 ? ubase + 1 : ubase + cbox_al;
       const int offx = g.fx0 - g.bx, offy = g.fy0 - g.by;  // both even
       const int cbw = P.conv_w >> 1, cbh = P.conv_h >> 1;
-      if (lx < cbw) {
-        for (int byi = ly; byi < cbh; byi += THREADS / 32) {
-          const uint32_t ya = ybase + (uint32_t)((offy + 2 * byi) * P.box_w + offx + 2 * lx);
-          const uint32_t ca = (uint32_t)(((offy >> 1) + byi) * P.cbox_w + (offx >> 1) + lx) * cstep;
-          uint32_t y01, y23, u8, v8;
-          asm("ld.shared.u16 %0, [%1];" : "=r"(y01) : "r"(ya));
-          asm("ld.shared.u16 %0, [%1];" : "=r"(y23) : "r"(ya + (uint32_t)P.box_w));
-          asm("ld.shared.u8 %0, [%1];" : "=r"(u8) : "r"(ubase + ca));
-          asm("ld.shared.u8 %0, [%1];" : "=r"(v8) : "r"(vbase + ca));
-          const float cb = ((float)u8 - 128.0f) * P.csc, cr = ((float)v8 - 128.0f) * P.csc;
-          const uint32_t o = conv_base + (uint32_t)((2 * byi) * P.conv_w + 2 * lx) * 4u;
-          convert_store<TRK>(P, (float)(y01 & 255u), cb, cr, o);
-          convert_store<TRK>(P, (float)(y01 >> 8), cb, cr, o + 4u);
-          convert_store<TRK>(P, (float)(y23 & 255u), cb, cr, o + cw4);
-          convert_store<TRK>(P, (float)(y23 >> 8), cb, cr, o + cw4 + 4u);
-        }
+      // (2x2 blocks are numbered row-major and dealt to the threads round robin: all lanes busy)
+      for (uint32_t blk = threadIdx.x; blk < (uint32_t)(cbw * cbh); blk += THREADS) {
+        const int byi = (int)fastdiv(blk, P.div_cbw), bxi = (int)blk - byi * cbw;
+        const uint32_t ya = ybase + (uint32_t)((offy + 2 * byi) * P.box_w + offx + 2 * bxi);
+        const uint32_t ca = (uint32_t)(((offy >> 1) + byi) * P.cbox_w + (offx >> 1) + bxi) * cstep;
+        uint32_t y01, y23, u8, v8;
+        asm("ld.shared.u16 %0, [%1];" : "=r"(y01) : "r"(ya));
+        asm("ld.shared.u16 %0, [%1];" : "=r"(y23) : "r"(ya + (uint32_t)P.box_w));
+        asm("ld.shared.u8 %0, [%1];" : "=r"(u8) : "r"(ubase + ca));
+        asm("ld.shared.u8 %0, [%1];" : "=r"(v8) : "r"(vbase + ca));
+        const float cb = ((float)u8 - 128.0f) * P.csc, cr = ((float)v8 - 128.0f) * P.csc;
+        const uint32_t o = conv_base + (uint32_t)((2 * byi) * P.conv_w + 2 * bxi) * 4u;
+        const float3 c00 = convert_rgb<TRK>(P, (float)(y01 & 255u), cb, cr), c10 = convert_rgb<TRK>(P, (float)(y01 >> 8), cb, cr);
+        const float3 c01 = convert_rgb<TRK>(P, (float)(y23 & 255u), cb, cr), c11 = convert_rgb<TRK>(P, (float)(y23 >> 8), cb, cr);
+        sts64(o, c00.x, c10.x); sts64(o + P.plane_bytes, c00.y, c10.y); sts64(o + 2u * P.plane_bytes, c00.z, c10.z);
+        sts64(o + cw4, c01.x, c11.x); sts64(o + cw4 + P.plane_bytes, c01.y, c11.y); sts64(o + cw4 + 2u * P.plane_bytes, c01.z, c11.z);
       }
       __syncthreads();
     }
@@ -546,6 +546,7 @@ zos_status launch_frame_pipeline(zos_ctx* ctx, const DevImage* below, const DevI
     ybox_al = ((size_t)P.box_w * P.box_h + 127) & ~(size_t)127; cbox_al = ((size_t)P.cbox_w * P.cbox_h * cstep + 127) & ~(size_t)127;
     stage = ybox_al + (P.nv12 ? 1 : 2) * cbox_al;
     P.plane_bytes = (uint32_t)(P.conv_w * P.conv_h * 4);
+    P.div_cbw = make_fastdiv((uint32_t)(P.conv_w / 2));
     const size_t fsmem = 2 * stage + 3 * (size_t)P.plane_bytes + (srgb ? (size_t)ZOS_ENC_N * FER * 4 : 0);
     bool ok2 = make_map(ctx, &M.m0, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, above.p0, above.w, above.h, above.pitch, batch, above.bstride, P.box_w, P.box_h);
     if (ok2 && P.nv12) ok2 = make_map(ctx, &M.m1, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, above.p1, cw, ch, above.cpitch, batch, above.cbstride, P.cbox_w, P.cbox_h);
