@@ -418,6 +418,33 @@ def test_yuv420_to_rgba8(ctx, nv12, chroma_filter):
 
 
 # ---------------------------------------------------------------- specialised kernels == generic kernels
+@pytest.mark.parametrize("space", ["oklab", "srlab2"])
+@pytest.mark.parametrize("parts", ["LchA", "LabA"])
+def test_lab_kernel_equals_generic(ctx, space, parts):
+    """rowwise_lab.cu (tables + compile-time chain) must give the generic interpreter's bytes for the
+    whole [encode, 8-bit register, decode] chain: every native 8-bit source / destination texel,
+    random colours AND alpha, a width that is not a multiple of 4."""
+    W, H = 1021, 48
+    rng = np.random.default_rng(21)
+    src = rng.integers(0, 256, (H, W * 4), dtype=np.uint8)
+    src.reshape(H, W, 4)[0, :256, :] = np.arange(256, dtype=np.uint8)[:, None]  # every code in every channel
+    model = Color.Oklab if space == "oklab" else Color.SrLab2(Z.Whitepoint.D65)
+    reg = zdesc(W, H, Texel(Z.Block.Pixel, Z.SampleBits.UInt8x4, getattr(SampleParts, parts)), model)
+    T = O.to_xyz("bt709", "D65")
+    enc = ops.step(_ffi.STEP_OKLAB_ENC if space == "oklab" else _ffi.STEP_SRLAB2_ENC, T)
+    dec = ops.step(_ffi.STEP_OKLAB_DEC if space == "oklab" else _ffi.STEP_SRLAB2_DEC, O.inv3(T), v=O.WHITEPOINTS["D65"])
+    lin = Color.Rgb(Z.Primaries.Bt709, Transfer.Linear)
+    for sc, sp in ((Color.SRGB, SampleParts.RgbA), (Color.SRGB, SampleParts.BgrA), (lin, SampleParts.RgbA)):
+        for dc, dp in ((Color.SRGB, SampleParts.RgbA), (lin, SampleParts.BgrA)):
+            sd, dd = zdesc(W, H, Texel.new_u8(sp), sc), zdesc(W, H, Texel.new_u8(dp), dc)
+            res = []
+            for flags in (0, 1):
+                ctx.set_flags(flags)
+                res.append(run_chain(ctx, sd, src, dd, [enc, ops.requant(reg), dec]))
+            ctx.set_flags(0)
+            assert np.array_equal(res[0], res[1]), (space, parts, sc, sp, dc, dp)
+
+
 def test_fast_u8_kernel_equals_generic(ctx):
     """rowwise_u8.cu must produce the bytes of the generic kernel (and of the oracle) for every
     combination of native 8-bit storage, with a matrix step, with overwrite and with source-over."""

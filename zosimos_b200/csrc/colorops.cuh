@@ -42,6 +42,36 @@ __device__ __forceinline__ float sr_nl_inv(float v) {
   return vp * vp * vp;
 }
 
+// The four non-linear colour steps (oklab.frag:34-64, srlab2.frag:36-120), shared by the step interpreter
+// below and by the specialised Lab kernel (rowwise_lab.cu): one definition, identical results.
+__device__ __forceinline__ void oklab_enc(const zos_step& s, float4& v) {
+  float3 xyz = mat3_mul(s.m, v.x, v.y, v.z);
+  float3 lms = mat3_mul(c_color.ok_m1, xyz.x, xyz.y, xyz.z);
+  float3 lab = mat3_mul(c_color.ok_m2, cbrt_signed(lms.x), cbrt_signed(lms.y), cbrt_signed(lms.z));
+  v.x = lab.x; v.y = lab.y; v.z = lab.z;
+}
+__device__ __forceinline__ void oklab_dec(const zos_step& s, float4& v) {
+  float3 l = mat3_mul(c_color.ok_m2i, v.x, v.y, v.z);
+  float3 xyz = mat3_mul(c_color.ok_m1i, l.x * l.x * l.x, l.y * l.y * l.y, l.z * l.z * l.z);
+  float3 rgb = mat3_mul(s.m, xyz.x, xyz.y, xyz.z);
+  v.x = clamp01(rgb.x); v.y = clamp01(rgb.y); v.z = clamp01(rgb.z);
+}
+__device__ __forceinline__ void srlab2_enc(const zos_step& s, float4& v) {
+  float3 xyz = mat3_mul(s.m, v.x, v.y, v.z);
+  float3 rw = mat3_mul(c_color.sr_cat, xyz.x, xyz.y, xyz.z);
+  float3 lms = mat3_mul(c_color.sr_hpe_cati, rw.x, rw.y, rw.z);
+  float3 e = mat3_mul(c_color.sr_hpei, sr_nl(lms.x), sr_nl(lms.y), sr_nl(lms.z));
+  v.x = e.y; v.y = (e.x - e.y) * 5.0f / 1.16f; v.z = (e.z - e.y) * 2.0f / 1.16f;
+}
+__device__ __forceinline__ void srlab2_dec(const zos_step& s, float4& v) {
+  float3 wp = mat3_mul(c_color.sr_cat, s.v[0], s.v[1], s.v[2]);
+  float3 t = mat3_mul(c_color.sr_hpe, v.y * 1.16f / 5.0f + v.x, v.x, v.z * 1.16f / 2.0f + v.x);
+  float3 rw = mat3_mul(c_color.sr_cat_hpei, sr_nl_inv(t.x), sr_nl_inv(t.y), sr_nl_inv(t.z));
+  float3 xyz = mat3_mul(c_color.sr_cati, rw.x * wp.x, rw.y * wp.y, rw.z * wp.z);
+  float3 rgb = mat3_mul(s.m, xyz.x, xyz.y, xyz.z);
+  v.x = clamp01(rgb.x); v.y = clamp01(rgb.y); v.z = clamp01(rgb.z);
+}
+
 static __device__ ZOS_SLOW_ATTR float4 apply_step_slow(const zos_step* sp, float4 v, const Tables* Tp) {
   const zos_step& s = *sp;
   const Tables& T = *Tp;
@@ -51,37 +81,10 @@ static __device__ ZOS_SLOW_ATTR float4 apply_step_slow(const zos_step* sp, float
       v.x = o.x; v.y = o.y; v.z = o.z;
       break;
     }
-    case ZOS_STEP_OKLAB_ENC: {
-      float3 xyz = mat3_mul(s.m, v.x, v.y, v.z);
-      float3 lms = mat3_mul(c_color.ok_m1, xyz.x, xyz.y, xyz.z);
-      float3 lab = mat3_mul(c_color.ok_m2, cbrt_signed(lms.x), cbrt_signed(lms.y), cbrt_signed(lms.z));
-      v.x = lab.x; v.y = lab.y; v.z = lab.z;
-      break;
-    }
-    case ZOS_STEP_OKLAB_DEC: {
-      float3 l = mat3_mul(c_color.ok_m2i, v.x, v.y, v.z);
-      float3 xyz = mat3_mul(c_color.ok_m1i, l.x * l.x * l.x, l.y * l.y * l.y, l.z * l.z * l.z);
-      float3 rgb = mat3_mul(s.m, xyz.x, xyz.y, xyz.z);
-      v.x = clamp01(rgb.x); v.y = clamp01(rgb.y); v.z = clamp01(rgb.z);
-      break;
-    }
-    case ZOS_STEP_SRLAB2_ENC: {
-      float3 xyz = mat3_mul(s.m, v.x, v.y, v.z);
-      float3 rw = mat3_mul(c_color.sr_cat, xyz.x, xyz.y, xyz.z);
-      float3 lms = mat3_mul(c_color.sr_hpe_cati, rw.x, rw.y, rw.z);
-      float3 e = mat3_mul(c_color.sr_hpei, sr_nl(lms.x), sr_nl(lms.y), sr_nl(lms.z));
-      v.x = e.y; v.y = (e.x - e.y) * 5.0f / 1.16f; v.z = (e.z - e.y) * 2.0f / 1.16f;
-      break;
-    }
-    case ZOS_STEP_SRLAB2_DEC: {
-      float3 wp = mat3_mul(c_color.sr_cat, s.v[0], s.v[1], s.v[2]);
-      float3 t = mat3_mul(c_color.sr_hpe, v.y * 1.16f / 5.0f + v.x, v.x, v.z * 1.16f / 2.0f + v.x);
-      float3 rw = mat3_mul(c_color.sr_cat_hpei, sr_nl_inv(t.x), sr_nl_inv(t.y), sr_nl_inv(t.z));
-      float3 xyz = mat3_mul(c_color.sr_cati, rw.x * wp.x, rw.y * wp.y, rw.z * wp.z);
-      float3 rgb = mat3_mul(s.m, xyz.x, xyz.y, xyz.z);
-      v.x = clamp01(rgb.x); v.y = clamp01(rgb.y); v.z = clamp01(rgb.z);
-      break;
-    }
+    case ZOS_STEP_OKLAB_ENC: oklab_enc(s, v); break;
+    case ZOS_STEP_OKLAB_DEC: oklab_dec(s, v); break;
+    case ZOS_STEP_SRLAB2_ENC: srlab2_enc(s, v); break;
+    case ZOS_STEP_SRLAB2_DEC: srlab2_dec(s, v); break;
     case ZOS_STEP_REQUANT: {
       uint4 w = pack_slow(s.fmt, v, Tp);
       v = unpack_slow(s.fmt, w, Tp);

@@ -13,6 +13,7 @@
 #define ZOS_SLOW_ATTR __forceinline__
 #include "colorops.cuh"
 #include "zos_internal.h"
+#include "rowwise_params.cuh"
 
 namespace zos {
 
@@ -32,10 +33,6 @@ struct RowParams {
   StepList src_steps, dst_steps;
 };
 
-__device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv& f) {
-  uint32_t t = __umulhi(n, f.m);
-  return f.l == 0 ? n : (t + ((n - t) >> 1)) >> (f.l - 1);
-}
 
 __device__ __forceinline__ uint4 load1(const int BPP, const uint8_t* p) {
   uint4 w = make_uint4(0, 0, 0, 0);
@@ -125,7 +122,13 @@ zos_status launch_rowwise(zos_ctx* ctx, const DevImage* below, const DevImage* a
   }
   if (!vec_ok(P.below) || !vec_ok(dst))
     return fail(ctx, ZOS_ERR_INVALID, "rowwise: buffers must be 16-byte aligned with padded rows (use zos_aligned_row_stride)");
-  // native 8-bit texels with at most matrix steps: the specialised kernel (rowwise_u8.cu), same results
+  // 8-bit -> Lab colour in an 8-bit register -> 8-bit: the specialised kernel (rowwise_lab.cu), same results
+  if (!(ctx->flags & ZOS_CTX_NO_FAST_PATHS) && !cp && below && !above) {
+    bool handled = false;
+    cudaError_t e = launch_rowwise_lab(ctx, *below, dst, steps, nsteps, batch, &handled);
+    if (handled) { ctx->launches++; return check_cuda(ctx, e, "k_rowwise_lab launch"); }
+  }
+  // native 8-bit / float texels with at most matrix steps: the specialised kernels (rowwise_fast.cu, rowwise_lut.cu), same results
   if (!(ctx->flags & ZOS_CTX_NO_FAST_PATHS) && rowwise_u8_eligible(below, above, dst, cp, steps, nsteps)) return launch_rowwise_u8(ctx, below, above, dst, cp, steps, nsteps, batch);
   uint64_t gpr = (uint64_t)dst.w;  // one pixel per work item
   uint64_t total = gpr * (uint64_t)dst.h * batch;

@@ -1,0 +1,234 @@
+// rowwise_lab.cu -- BASELINE config 1 as one lean kernel: a native 8-bit image converted to a Lab-type
+// colour held in an 8-bit staged register and back,
+//
+//   input(sRGB RGBA8) -> color_convert(Oklab | SrLab2, Texel{UInt8x4, LchA | LabA}) -> color_convert(sRGB RGBA8)
+//
+// i.e. the fused step chain [LAB_ENC, REQUANT(UInt8x4 staged), LAB_DEC] between two native 8-bit texels
+// (command.rs:986-1107, oklab.frag:34-64, srlab2.frag:36-120; the register's quantisation is
+// stage.frag's encode + decode, program.rs:1475-1478,1531-1532).  The generic kernel interprets
+// texel formats and steps per pixel (~650 instructions); here everything is compile time and every
+// 8-bit -> float map is a lane-private shared-memory table:
+//
+//   * source colour decode: one byte permute + one LDS per channel (rowwise_lut.cu's table);
+//   * alpha never meets the colour maths: alpha_out = A[alpha_in], a 256-entry map built at kernel
+//     start by running the generic arithmetic (decode, f16 store, truncating pack, unpack, f16, encode);
+//   * the register: f16 rounding, [Lab -> LCh: sqrt, atan2], clamp, truncation to codes, then tables:
+//     f16(k / 255), k / 255 and cos / sin of the hue a code stands for (built by the generic decode code);
+//   * sRGB8 encode through the bucket table (texel.cuh), no transcendental.
+//
+// The colour steps themselves are the shared functions of colorops.cuh: results equal the generic
+// kernel's bit for bit (tests compare both, and both with the oracle).
+#include "colorops.cuh"
+#include "zos_internal.h"
+#include "rowwise_params.cuh"
+
+namespace zos {
+
+ZOS_DEFINE_CONSTANT_UPLOAD(upload_constants_rowwise_lab)
+
+namespace {
+constexpr int LAB_THREADS = 1024;
+constexpr int ER = 8;                                    // replication of the encoder bucket table
+constexpr uint32_t DEC_BYTES = 256u * 256u;              // [code][0..31] colour decode, [code][32..63] alpha map
+constexpr uint32_t Q_BYTES = 256u * 256u;                // [code][lane & 15] float4 {f16(code/255), code/255, cos(hue(code)), sin(hue(code))}
+constexpr uint32_t ENC_BYTES = (uint32_t)ZOS_ENC_N * ER * 4u;
+constexpr uint32_t ENC_SHIFT = 16 - 5;
+constexpr uint32_t ENC_MASK = 0x7ffu * (ER * 4u);
+constexpr uint32_t ENC_VOFF = (ZOS_ENC_B0 & 0x7ff) * (ER * 4u);
+
+struct LabParams {
+  FastParams F;  // below = the source
+  zos_step enc, dec;
+  int32_t src_srgb;
+};
+
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+struct Ctx {
+  uint32_t dec, q, enc;     // shared addresses (enc minus ENC_VOFF)
+  uint32_t lane4, lane_er;  // (lane & 31) * 4 with zero upper bytes; (lane & (ER-1)) * 4
+  uint32_t lane_q;          // (lane & 15) * 16
+  uint32_t sr, sg, sb, sa, spack;
+};
+
+__device__ __forceinline__ uint32_t srgb_code_b2(float x, const Ctx& c) {
+  const int idx = max(__float_as_int(x), ZOS_ENC_B0 << 16);
+  uint32_t a;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(a) : "r"((uint32_t)idx >> ENC_SHIFT), "r"(ENC_MASK), "r"(c.lane_er));
+  return lds_u32(a + c.enc) + (uint32_t)idx;
+}
+
+// the staged UInt8x4 register (stage.frag encode then decode): f16 attachment, [Lab -> LCh], clamp,
+// truncating pack; unorm decode, [LCh -> Lab], f16 texture.  Everything after the truncation is a table.
+__device__ __forceinline__ uint32_t code8(float x) { return (uint32_t)(clamp01(x) * 255.0f); }
+template <bool LCH>
+__device__ __forceinline__ void requant8(float4& v, const Ctx& c) {
+  float4 t = make_float4(f16r(v.x), f16r(v.y), f16r(v.z), 1.0f);
+  if (LCH) transfer_encode(ZOS_TRANSFER_LABLCH, t);  // C = sqrt(a^2 + b^2), h = atan2(b, a) / 2pi + 0.5
+  const uint32_t qx = c.q + code8(t.x) * 256u + c.lane_q, qy = c.q + code8(t.y) * 256u + c.lane_q, qz_ = c.q + code8(t.z) * 256u + c.lane_q;
+  v.x = lds_f32(qx);
+  if (LCH) {
+    const float C = lds_f32(qy + 4u), cs = lds_f32(qz_ + 8u), sn = lds_f32(qz_ + 12u);
+    v.y = f16r(C * cs); v.z = f16r(C * sn);
+  } else {
+    v.y = lds_f32(qy); v.z = lds_f32(qz_);
+  }
+}
+
+template <int LAB, bool SRGB_DST, bool LCH>
+__device__ __forceinline__ uint32_t pixel(const LabParams& P, uint32_t w, const Ctx& c) {
+  float4 v;
+  v.x = lds_f32(__byte_perm(w, c.lane4, c.sr) + c.dec);
+  v.y = lds_f32(__byte_perm(w, c.lane4, c.sg) + c.dec);
+  v.z = lds_f32(__byte_perm(w, c.lane4, c.sb) + c.dec);
+  v.w = 1.0f;
+  const uint32_t acode = lds_u32(__byte_perm(w, c.lane4, c.sa) + c.dec + 128u);
+  if (LAB == 0) oklab_enc(P.enc, v); else srlab2_enc(P.enc, v);
+  requant8<LCH>(v, c);
+  if (LAB == 0) oklab_dec(P.dec, v); else srlab2_dec(P.dec, v);  // ends with clamp01 on the colour
+  uint32_t t1, t2;
+  if (SRGB_DST) {
+    t1 = __byte_perm(srgb_code_b2(v.x, c), srgb_code_b2(v.y, c), 0x0062);
+    t2 = __byte_perm(srgb_code_b2(v.z, c), acode, 0x0042);
+  } else {
+    t1 = __byte_perm(__float_as_uint(v.x * 255.0f + 8388608.0f), __float_as_uint(v.y * 255.0f + 8388608.0f), 0x0040);
+    t2 = __byte_perm(__float_as_uint(v.z * 255.0f + 8388608.0f), acode, 0x0040);
+  }
+  return __byte_perm(t1, t2, c.spack);
+}
+
+template <int LAB, bool SRGB_DST, bool LCH>
+__global__ void __launch_bounds__(LAB_THREADS, 1) k_rowwise_lab(const __grid_constant__ LabParams P) {
+  extern __shared__ __align__(256) uint8_t smem[];
+  float* dec = reinterpret_cast<float*>(smem);
+  float* q = reinterpret_cast<float*>(smem + DEC_BYTES);
+  uint32_t* enc = reinterpret_cast<uint32_t*>(smem + DEC_BYTES + Q_BYTES);
+#pragma unroll 4
+  for (int i = threadIdx.x; i < 256 * 64; i += LAB_THREADS) {
+    const int k = i >> 6;
+    float val;
+    if (i & 32) {
+      // alpha through the chain: decode, register (f16, clamp, truncate, unorm, f16), encode (round to nearest)
+      const float a = g_tables.unorm8[k];
+      const uint32_t kq = (uint32_t)(clamp01(f16r(a)) * 255.0f);
+      const float a2 = f16r(g_tables.unorm8[kq]);
+      val = __uint_as_float((uint32_t)__float2int_rn(clamp01(a2) * 255.0f));
+    } else {
+      val = P.src_srgb ? g_tables.srgb_dec[k] : g_tables.unorm8[k];
+    }
+    dec[i] = val;
+  }
+#pragma unroll 4
+  for (int i = threadIdx.x; i < 256 * 16; i += LAB_THREADS) {
+    const float u = g_tables.unorm8[i >> 4];
+    float4 c4 = make_float4(0.0f, u, u, 1.0f);  // (L, C = 1 * u ..., h = u): the generic decode of hue code k
+    c4.y = 1.0f;
+    transfer_decode(ZOS_TRANSFER_LABLCH, c4);  // c4.y = cos(hue), c4.z = sin(hue): the very code the generic path runs
+    reinterpret_cast<float4*>(q)[i] = make_float4(f16r(u), u, c4.y, c4.z);
+  }
+  if (SRGB_DST) {
+#pragma unroll 4
+    for (int i = threadIdx.x; i < ZOS_ENC_N * ER; i += LAB_THREADS) enc[i] = g_tables.srgb_enc[i / ER];
+  }
+  __syncthreads();
+
+  Ctx c;
+  c.dec = (uint32_t)__cvta_generic_to_shared(dec);
+  c.q = (uint32_t)__cvta_generic_to_shared(q);
+  c.enc = (uint32_t)__cvta_generic_to_shared(enc) - ENC_VOFF;
+  c.lane4 = (threadIdx.x & 31u) * 4u;
+  c.lane_er = (threadIdx.x & (ER - 1u)) * 4u;
+  c.lane_q = (threadIdx.x & 15u) * 16u;
+  const uint32_t kr = P.F.src_bgra ? 2u : 0u, kb = P.F.src_bgra ? 0u : 2u;
+  c.sr = 0x7604u | (kr << 4); c.sg = 0x7614u; c.sb = 0x7604u | (kb << 4); c.sa = 0x7634u;
+  c.spack = P.F.dst_bgra ? 0x5014u : 0x5410u;
+
+  const uint32_t stride = gridDim.x * LAB_THREADS;
+  for (uint32_t idx = blockIdx.x * LAB_THREADS + threadIdx.x; idx < P.F.total_groups; idx += stride) {
+    const Loc L = locate<0>(P.F, idx);
+    const uint4 rb = __ldcs(reinterpret_cast<const uint4*>(P.F.below + L.ob));
+    uint32_t o[4];
+    o[0] = pixel<LAB, SRGB_DST, LCH>(P, rb.x, c); o[1] = pixel<LAB, SRGB_DST, LCH>(P, rb.y, c);
+    o[2] = pixel<LAB, SRGB_DST, LCH>(P, rb.z, c); o[3] = pixel<LAB, SRGB_DST, LCH>(P, rb.w, c);
+    uint8_t* dp = P.F.dst + L.od;
+    if (L.npx == 4) {
+      __stcs(reinterpret_cast<uint4*>(dp), make_uint4(o[0], o[1], o[2], o[3]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+        if (i < L.npx) reinterpret_cast<uint32_t*>(dp)[i] = o[i];
+    }
+    if (idx + stride < idx) break;  // 32-bit wrap
+  }
+}
+
+bool native8(const DevImage& im, bool* srgb, bool* bgra) {
+  if (im.block != ZOS_BLOCK_PIXEL || im.bpp != 4) return false;
+  if (im.fmt.storage != ZOS_STORAGE_SRGB8 && im.fmt.storage != ZOS_STORAGE_UNORM8) return false;
+  *srgb = im.fmt.storage == ZOS_STORAGE_SRGB8;
+  *bgra = im.fmt.parts == ZOS_PARTS_BGRA;
+  return true;
+}
+
+template <int LAB, bool SRGB_DST, bool LCH>
+cudaError_t launch_one(zos_ctx* ctx, const LabParams& P) {
+  static bool configured = false;
+  auto kern = k_rowwise_lab<LAB, SRGB_DST, LCH>;
+  const uint32_t bytes = DEC_BYTES + Q_BYTES + (SRGB_DST ? ENC_BYTES : 0u);
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DEC_BYTES + Q_BYTES + ENC_BYTES));
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const uint64_t ctas = ((uint64_t)P.F.total_groups + LAB_THREADS - 1) / LAB_THREADS;
+  const int grid = (int)(ctas < (uint64_t)ctx->sm_count ? ctas : (uint64_t)ctx->sm_count);
+  kern<<<grid, LAB_THREADS, bytes, ctx->stream>>>(P);
+  return cudaGetLastError();
+}
+}  // namespace
+
+cudaError_t launch_rowwise_lab(zos_ctx* ctx, const DevImage& src, const DevImage& dst, const zos_step* steps, uint32_t nsteps, uint32_t batch, bool* handled) {
+  *handled = false;
+  if (nsteps != 3) return cudaSuccess;
+  const bool ok_chain = steps[0].kind == ZOS_STEP_OKLAB_ENC && steps[2].kind == ZOS_STEP_OKLAB_DEC;
+  const bool sr_chain = steps[0].kind == ZOS_STEP_SRLAB2_ENC && steps[2].kind == ZOS_STEP_SRLAB2_DEC;
+  if (!(ok_chain || sr_chain) || steps[1].kind != ZOS_STEP_REQUANT) return cudaSuccess;
+  const zos_texfmt& rf = steps[1].fmt;
+  if (rf.storage != ZOS_STORAGE_STAGED || rf.bits != ZOS_BITS_UINT8X4) return cudaSuccess;
+  if (rf.transfer != ZOS_TRANSFER_LINEAR && rf.transfer != ZOS_TRANSFER_LABLCH) return cudaSuccess;  // LabA / LchA registers
+  if (rf.parts != ZOS_PARTS_LABA && rf.parts != ZOS_PARTS_LCHA && rf.parts != ZOS_PARTS_RGBA) return cudaSuccess;  // pass-through swizzles only
+  const bool lch = rf.transfer == ZOS_TRANSFER_LABLCH;
+  bool ssrgb, sbgra, dsrgb, dbgra;
+  if (!native8(src, &ssrgb, &sbgra) || !native8(dst, &dsrgb, &dbgra)) return cudaSuccess;
+  if (src.w != dst.w || src.h != dst.h) return cudaSuccess;
+  LabParams P;
+  memset(&P, 0, sizeof P);
+  P.F.below = src.p0; P.F.below_pitch = src.pitch; P.F.below_bstride = src.bstride;
+  P.F.dst = dst.p0; P.F.dst_pitch = dst.pitch; P.F.dst_bstride = dst.bstride;
+  P.F.w = dst.w; P.F.h = dst.h; P.F.has_below = 1;
+  P.F.src_bgra = sbgra; P.F.dst_bgra = dbgra;
+  P.src_srgb = ssrgb;
+  P.enc = steps[0]; P.dec = steps[2];
+  const uint64_t gpr = (uint64_t)(dst.w + 3) / 4, total = gpr * (uint64_t)dst.h * batch;
+  if (total == 0 || total >= (1ull << 32)) return cudaSuccess;
+  P.F.groups_per_row = (uint32_t)gpr; P.F.total_groups = (uint32_t)total;
+  P.F.div_gpr = make_fastdiv((uint32_t)gpr); P.F.div_h = make_fastdiv((uint32_t)dst.h);
+  *handled = true;
+  if (ok_chain) {
+    if (lch) return dsrgb ? launch_one<0, true, true>(ctx, P) : launch_one<0, false, true>(ctx, P);
+    return dsrgb ? launch_one<0, true, false>(ctx, P) : launch_one<0, false, false>(ctx, P);
+  }
+  if (lch) return dsrgb ? launch_one<1, true, true>(ctx, P) : launch_one<1, false, true>(ctx, P);
+  return dsrgb ? launch_one<1, true, false>(ctx, P) : launch_one<1, false, false>(ctx, P);
+}
+
+}  // namespace zos

@@ -128,32 +128,6 @@ __device__ __forceinline__ uint32_t pixel8(const FastParams& P, uint32_t b, uint
   return encode8<DK, (NMAT > 0), MODE == 0>(v, c, b);
 }
 
-struct Loc {
-  uint64_t ob, oa, od;  // byte offsets of the 4-texel group in below / above / dst
-  int npx, ncov;        // valid texels of the group, of which covered by `above` (from the left)
-};
-
-template <int MODE>
-__device__ __forceinline__ Loc locate(const FastParams& P, uint32_t idx) {
-  Loc L;
-  uint32_t rowid = fastdiv(idx, P.div_gpr);
-  uint32_t g = idx - rowid * P.groups_per_row;
-  uint32_t frame = fastdiv(rowid, P.div_h);
-  int y = (int)(rowid - frame * (uint32_t)P.h);
-  int x0 = (int)g * 4;
-  L.npx = min(4, P.w - x0);
-  L.ncov = 0; L.oa = 0;
-  if (MODE != 0) {
-    int ax0 = x0 - P.tx, ay = y - P.ty;
-    bool row_in = ay >= 0 && ay < P.ah && ax0 >= 0 && ax0 < P.aw;
-    L.ncov = row_in ? min(L.npx, P.aw - ax0) : 0;
-    if (row_in) L.oa = frame * P.above_bstride + (uint64_t)ay * P.above_pitch + (uint64_t)ax0 * 4u;
-  }
-  L.ob = frame * P.below_bstride + (uint64_t)y * P.below_pitch + (uint64_t)x0 * 4u;
-  L.od = frame * P.dst_bstride + (uint64_t)y * P.dst_pitch + (uint64_t)x0 * 4u;
-  return L;
-}
-
 // LINEAR: every layer has the destination's geometry with rows and frames back to back, so the images
 // are plain streams of 16-byte groups (the blend / convert workloads).  Two groups are in flight per
 // thread, ping-pong, so that no register rotation is needed.

@@ -31,7 +31,35 @@ __device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv& f) {
   return f.l == 0 ? n : (t + ((n - t) >> 1)) >> (f.l - 1);
 }
 
+struct Loc {
+  uint64_t ob, oa, od;  // byte offsets of the 4-texel group in below / above / dst
+  int npx, ncov;        // valid texels of the group, of which covered by `above` (from the left)
+};
+
+template <int MODE>
+__device__ __forceinline__ Loc locate(const FastParams& P, uint32_t idx) {
+  Loc L;
+  uint32_t rowid = fastdiv(idx, P.div_gpr);
+  uint32_t g = idx - rowid * P.groups_per_row;
+  uint32_t frame = fastdiv(rowid, P.div_h);
+  int y = (int)(rowid - frame * (uint32_t)P.h);
+  int x0 = (int)g * 4;
+  L.npx = min(4, P.w - x0);
+  L.ncov = 0; L.oa = 0;
+  if (MODE != 0) {
+    int ax0 = x0 - P.tx, ay = y - P.ty;
+    bool row_in = ay >= 0 && ay < P.ah && ax0 >= 0 && ax0 < P.aw;
+    L.ncov = row_in ? min(L.npx, P.aw - ax0) : 0;
+    if (row_in) L.oa = frame * P.above_bstride + (uint64_t)ay * P.above_pitch + (uint64_t)ax0 * 4u;
+  }
+  L.ob = frame * P.below_bstride + (uint64_t)y * P.below_pitch + (uint64_t)x0 * 4u;
+  L.od = frame * P.dst_bstride + (uint64_t)y * P.dst_pitch + (uint64_t)x0 * 4u;
+  return L;
+}
+
 // rowwise_lut.cu: 8-bit -> 8-bit texel pairs (sk, dk in {K_SRGB8, K_UNORM8}); mode 0 = convert, 2 = source-over
 cudaError_t launch_rowwise_lut(zos_ctx* ctx, FastParams& P, int sk, int dk, int mode, int nmat);
+// rowwise_lab.cu: 8-bit -> [Lab encode, 8-bit staged register, Lab decode] -> 8-bit; *handled stays false when not served
+cudaError_t launch_rowwise_lab(zos_ctx* ctx, const DevImage& src, const DevImage& dst, const zos_step* steps, uint32_t nsteps, uint32_t batch, bool* handled);
 
 }  // namespace zos
