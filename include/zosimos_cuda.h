@@ -271,6 +271,13 @@ zos_status zos_program_set_knob(zos_program* prog, uint32_t knob, const void* da
 /* Executable::launch + Execution::step (run.rs:1016,1389): step launches up to max_kernels kernels */
 zos_status zos_program_launch(zos_program* prog);
 zos_status zos_program_step(zos_program* prog, uint32_t max_kernels, int32_t* still_running);
+/* Executable reuse (run.rs:1016,1283-1347; Readme.md "re-use of the pipeline"; tests/loop.rs, tests/knobs.rs):
+ * run the whole schedule again, same plan, possibly other bindings / knob values.  ZOS_RUN_GRAPH relaunches
+ * the schedule as one CUDA graph (captured on the second run, re-captured after zos_program_bind /
+ * zos_program_set_knob).  zos_program_graph_launches counts the runs that went through the graph. */
+enum { ZOS_RUN_EAGER = 0, ZOS_RUN_GRAPH = 1 };
+zos_status zos_program_run(zos_program* prog, uint32_t flags);
+uint64_t zos_program_graph_launches(const zos_program* prog);
 uint32_t zos_program_kernel_count(const zos_program* prog);
 /* fills descriptor + device location of a register the program allocated itself (outputs not bound) */
 zos_status zos_program_register_image(const zos_program* prog, int32_t reg, zos_image* out);

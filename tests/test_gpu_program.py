@@ -313,3 +313,54 @@ def test_run_swap(pool, images, fixtures):  # tests/blend.rs:426-447: extract R 
     from zosimos_b200.command import CommandError
     with pytest.raises(CommandError):  # `above` must be a single-channel image of the matching texel
         c.inject(inp, Z.ColorChannel.R, inp)
+
+
+def test_executable_reuse_cuda_graph(pool, images, fixtures):
+    """SURVEY.md 8f-1 (tests/loop.rs, tests/knobs.rs): one Execution re-run many times.  The second and
+    later runs go through ONE CUDA-graph launch; patching a knob re-captures; results always equal a
+    fresh, stepped execution with the same knob value."""
+    bg, fg = images
+    c = CommandBuffer()
+    background, foreground = c.input(bg.descriptor()), c.input(fg.descriptor())
+    ramp = c.with_knob().bilinear(fg.descriptor(), Bilinear([0, 0, 1, 1], [1, 1, 1, 1], [0, 0, 1, 1], [1, 1, 1, 1]))
+    rect = Rectangle.with_layout(fg.descriptor().layout)
+    mixed = c.inscribe(background, rect, foreground)
+    shifted = c.affine(mixed, Affine.new(AffineSample.Nearest).shift(100.0, 50.0), ramp)
+    result = c.chromatic_adaptation(shifted, ChromaticAdaptationMethod.VonKries, Z.Whitepoint.D50)
+    output, _ = c.output(result)
+    caps = Capabilities.from_device(next(pool.iter_devices()), _ffi.FUSE_NONE)  # one kernel per op: a real multi-kernel schedule
+    executable = Linker.from_included().compile(c).lower_to(caps)
+    knob = executable.query_knob(RegisterKnob(0, ramp))
+    binds = [(background, bg.key()), (foreground, fg.key())]
+    datas = [Bilinear(um, uM, vm, vM).into_std430() for (um, uM, vm, vM) in R.KNOBS[:3]]
+    fresh = [rgba(run_executable_with_output(executable, pool, binds, output, [(knob, d)])[0]) for d in datas]
+    assert not np.array_equal(fresh[0], fresh[1])
+
+    env = executable.from_pool(pool)
+    env.knob(knob, datas[0])
+    for reg, key in binds:
+        env.bind(reg, key)
+    ex = executable.launch(env)
+    assert ex.kernel_count() > 2
+    while ex.is_running():
+        ex.step().block_on()
+
+    def current():
+        r = ex.retire_gracefully(pool)
+        return rgba(r.output(output))
+
+    assert np.array_equal(current(), fresh[0])
+    ex.rerun().block_on()                      # run 1 of zos_program_run: eager
+    assert np.array_equal(current(), fresh[0])
+    for _ in range(3):                         # captured, then replayed
+        ex.rerun().block_on()
+    assert ex.graph_launches() == 3
+    assert np.array_equal(current(), fresh[0])
+    ex.rerun({knob: datas[1]}).block_on()      # knob patched: re-captured with the new parameter block
+    assert np.array_equal(current(), fresh[1])
+    ex.rerun({knob: datas[2]}, graph=False).block_on()
+    assert np.array_equal(current(), fresh[2])
+    ex.rerun().block_on()
+    assert np.array_equal(current(), fresh[2])
+    assert ex.graph_launches() == 5
+    ex.retire_gracefully(pool).finish()

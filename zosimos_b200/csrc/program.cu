@@ -56,6 +56,10 @@ struct zos_program {
   std::vector<Kernel> schedule;
   size_t pc = 0;
   bool running = false;
+  // zos_program_run: the whole schedule as one CUDA graph, re-captured after a bind / knob change
+  cudaGraphExec_t graph_exec = nullptr;
+  bool graph_dirty = true, graph_broken = false;
+  uint64_t runs = 0, graph_launches = 0;
 };
 
 namespace {
@@ -331,6 +335,7 @@ zos_status zos_program_create(zos_ctx* ctx, const zos_op* ops, uint32_t nops, ui
 
 void zos_program_destroy(zos_program* p) {
   if (!p) return;
+  if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
   for (Reg& r : p->regs)
     if (r.owned) zos_buf_free(p->ctx, r.owned);
   delete p;
@@ -351,12 +356,14 @@ zos_status zos_program_bind(zos_program* p, int32_t reg, const zos_image* image)
   if (R.owned) { zos_buf_free(ctx, R.owned); R.owned = nullptr; }
   R.img = *image;
   R.bound = true;
+  p->graph_dirty = true;
   return ZOS_OK;
 }
 
 zos_status zos_program_set_knob(zos_program* p, uint32_t knob, const void* data, uint64_t len) {
   if (!p || !data || knob == 0) return ZOS_ERR_INVALID;
   bool found = false;
+  p->graph_dirty = true;
   for (Kernel& k : p->schedule) {
     if (k.knob != knob) continue;
     found = true;
@@ -401,6 +408,51 @@ zos_status zos_program_step(zos_program* p, uint32_t max_kernels, int32_t* still
   if (still_running) *still_running = p->running ? 1 : 0;
   return ZOS_OK;
 }
+
+// Executable reuse (run.rs:1016,1283-1347; tests/loop.rs): run the whole schedule again without
+// re-planning.  With ZOS_RUN_GRAPH the kernels of the schedule are captured once into a CUDA graph and
+// relaunched as ONE submission; binding another image or patching a knob re-captures on the next run.
+zos_status zos_program_run(zos_program* p, uint32_t flags) {
+  if (!p) return ZOS_ERR_INVALID;
+  zos_ctx* ctx = p->ctx;
+  if (p->running) return fail(ctx, ZOS_ERR_STATE, "run: a stepped execution of this program is in flight");
+  zos_status st = zos_program_launch(p);
+  if (st != ZOS_OK) return st;
+  p->running = false;
+  const bool want_graph = (flags & ZOS_RUN_GRAPH) && !p->graph_broken && p->schedule.size() > 1 && p->runs > 0;  // first run is eager: it also configures the kernels
+  p->runs++;
+  if (want_graph && (p->graph_dirty || !p->graph_exec)) {
+    if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
+    const uint64_t launches_before = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+      for (const Kernel& k : p->schedule)
+        if ((st = run_kernel(p, k)) != ZOS_OK) break;
+      e = cudaStreamEndCapture(ctx->stream, &graph);
+      if (e == cudaSuccess && st == ZOS_OK) e = cudaGraphInstantiate(&p->graph_exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+    }
+    ctx->launches = launches_before;
+    if (e != cudaSuccess || st != ZOS_OK || !p->graph_exec) {  // something in the schedule cannot be captured: stay eager from now on
+      cudaGetLastError();
+      if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
+      p->graph_broken = true;
+    } else {
+      p->graph_dirty = false;
+    }
+  }
+  if (want_graph && p->graph_exec && !p->graph_dirty) {
+    ctx->launches += p->schedule.size();
+    p->graph_launches++;
+    return check_cuda(ctx, cudaGraphLaunch(p->graph_exec, ctx->stream), "cudaGraphLaunch");
+  }
+  for (const Kernel& k : p->schedule)
+    if ((st = run_kernel(p, k)) != ZOS_OK) return st;
+  return ZOS_OK;
+}
+
+uint64_t zos_program_graph_launches(const zos_program* p) { return p ? p->graph_launches : 0; }
 
 uint32_t zos_program_kernel_count(const zos_program* p) { return p ? (uint32_t)p->schedule.size() : 0; }
 

@@ -281,6 +281,21 @@ class Execution:
         self._running = bool(r.value)
         return SyncPoint(self.ctx)
 
+    def rerun(self, knobs: Optional[Dict["Knob", bytes]] = None, graph: bool = True) -> SyncPoint:
+        """Executable reuse (run.rs:1283-1347, tests/loop.rs, tests/knobs.rs): run the same plan again,
+        optionally with other knob values, as one CUDA-graph submission (`zos_program_run`)."""
+        if self._running:
+            raise StepError("execution is still being stepped")
+        lib = self.ctx._lib
+        for k, data in (knobs or {}).items():
+            buf = C.create_string_buffer(bytes(data), len(data))
+            self._check(lib.zos_program_set_knob(self._prog, k.index, buf, len(data)), StartError)
+        self._check(lib.zos_program_run(self._prog, 1 if graph else 0), StepError)
+        return SyncPoint(self.ctx)
+
+    def graph_launches(self) -> int:
+        return int(self.ctx._lib.zos_program_graph_launches(self._prog))
+
     def retire_gracefully(self, pool: Pool) -> "Retire":
         if self._running:
             raise RetireError("execution is still running")
