@@ -120,6 +120,27 @@ def make_gpu_workload(name, ctx, frames, seed):
         wl = Workload(name, "sRGB8 -> Oklab (LchA u8 register) -> sRGB8, one fused kernel", W * H, W * H, W * H * 8, frames)
         return wl, (lambda: ops.pixel_chain(ctx, src, dst, steps)), None
 
+    if name in ("c5_yuv420_yuv420", "c5_yuv420_rgba8"):
+        W = H = 4096
+        sd = Z.yuv420_descriptor(W, H, Color.Rgb(Z.Primaries.Bt2020, Transfer.Bt709), Z.YuvMatrix.Bt2020, False, False, 0)
+        src = ctx.image(sd, frames)
+        y = rng.integers(16, 236, (1, H, W), dtype=np.uint8)
+        u = rng.integers(16, 241, (1, H // 2, W // 2), dtype=np.uint8); vv = rng.integers(16, 241, (1, H // 2, W // 2), dtype=np.uint8)
+        one = ctx.image(sd, 1); one.upload((y, u, vv))
+        for f in range(frames):
+            ctx.check(ctx._lib.zos_buf_copy(ctx.handle, src.buf.handle, f * src.frame_bytes, one.buf.handle, 0, src.frame_bytes))
+        M = O.mul3(O.inv3(O.to_xyz("bt709", "D65")), O.to_xyz("bt2020", "D65"))
+        if name == "c5_yuv420_yuv420":
+            dd = Z.yuv420_descriptor(W, H, Color.Rgb(Z.Primaries.Bt709, Transfer.Bt709), Z.YuvMatrix.Bt709, False, False, 0)
+            dst = ctx.image(dd, frames)
+            wl = Workload(name, "I420 BT.2020 -> linear -> 3x3 -> I420 BT.709, one kernel", W * H, W * H, W * H * 3, frames)
+            return wl, (lambda: ops.pixel_chain(ctx, src, dst, [ops.matrix(M)])), None
+        dd = d(W, H, rgba8, Color.SRGB)
+        dst = ctx.image(dd, frames)
+        p = ops.compose_params(map=_ffi.MAP_SCALE, sampling=_ffi.SAMPLE_NEAREST, blend=_ffi.BLEND_OVERWRITE, src_steps=[ops.matrix(M)], use_tma=True)
+        wl = Workload(name, "I420 BT.2020 -> linear -> 3x3 -> RGBA8 sRGB, one kernel", W * H, W * H, W * H * 11 // 2, frames)
+        return wl, (lambda: ops.compose(ctx, None, src, dst, p)), None
+
     if name.startswith("c5_"):
         fmt = name[3:]
         W = H = 4096

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 out=gpurun_out/sweep_$TAG.jsonl
 : > $out
 timeout 300 python bench.py >> $out 2> gpurun_out/sweep_$TAG.err
-for w in c2_inscribe c1_oklab c5_rgba8 c5_rgba16f c5_rgb10a2; do
+for w in c2_inscribe c1_oklab c5_rgba8 c5_rgba16f c5_rgb10a2 c5_yuv420_yuv420 c5_yuv420_rgba8; do
   timeout 200 python bench.py --workload $w --no-cpu --steps 10 --warmup 3 >> $out 2>> gpurun_out/sweep_$TAG.err
 done
 for w in c3_affine_bilinear c3_affine_nearest; do

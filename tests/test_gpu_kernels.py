@@ -417,6 +417,52 @@ def test_yuv420_to_rgba8(ctx, nv12, chroma_filter):
     assert np.mean(got == exp) > 0.99
 
 
+@pytest.mark.parametrize("nv12", [False, True])
+@pytest.mark.parametrize("odd", [False, True])
+def test_rgba8_to_yuv420(ctx, nv12, odd):
+    """Planar destination (yuv_chain.cu): sRGB8 -> [3x3] -> Y'CbCr 4:2:0, against zo_encode_yuv420; odd sizes
+    exercise the partial 2x2 blocks at the right / bottom edge."""
+    w, h = (323, 131) if odd else (320, 128)
+    rng = np.random.default_rng(14)
+    a = rng.integers(0, 256, (h, w * 4), dtype=np.uint8)
+    sd = zdesc(w, h, Texel.new_u8(SampleParts.RgbA), Color.SRGB)
+    color = Color.Rgb(Z.Primaries.Bt709, Transfer.Bt709)
+    dd = Z.yuv420_descriptor(w, h, color, Z.YuvMatrix.Bt709, False, nv12, 0)
+    src, dst = ctx.upload(sd, a), ctx.image(dd)
+    M = O.mul3(O.inv3(O.to_xyz("bt709", "D65")), O.to_xyz("bt709", "D65"))
+    ops.pixel_chain(ctx, src, dst, [ops.matrix(M)])
+    y, u, v = dst.download()
+    tex = O.linear(O.decode(oracle_image(sd, a)), np.array(M, np.float32).reshape(3, 3))
+    ey, eu, ev = O.encode_yuv420(np.asarray(tex.data if hasattr(tex, "data") else tex).reshape(h, w, 4), 0.2126, 0.0722, False, O.TR_BT709)
+    if nv12:
+        uv = u.reshape((h + 1) // 2, (w + 1) // 2, 2)
+        u, v = uv[..., 0], uv[..., 1]
+    for got, exp in ((y, ey), (u, eu), (v, ev)):
+        assert max_lsb(got, exp) <= 1   # pow in the OETF: SFU vs libm
+        assert np.mean(got == exp) > 0.99
+
+
+def test_yuv420_to_yuv420_chain(ctx):
+    """BASELINE config 5, YUV420 -> YUV420: BT.2020 frames re-encoded with BT.709 primaries (one kernel,
+    3 bytes per pixel of traffic), against the oracle's decode -> linear -> encode."""
+    w, h = 322, 130
+    rng = np.random.default_rng(15)
+    y = rng.integers(16, 236, (h, w), dtype=np.uint8)
+    u = rng.integers(16, 241, (h // 2, w // 2), dtype=np.uint8); v = rng.integers(16, 241, (h // 2, w // 2), dtype=np.uint8)
+    sd = Z.yuv420_descriptor(w, h, Color.Rgb(Z.Primaries.Bt2020, Transfer.Bt709), Z.YuvMatrix.Bt2020, False, False, 0)
+    dd = Z.yuv420_descriptor(w, h, Color.Rgb(Z.Primaries.Bt709, Transfer.Bt709), Z.YuvMatrix.Bt709, False, False, 0)
+    src, dst = ctx.upload(sd, (y, u, v)), ctx.image(dd)
+    M = O.mul3(O.inv3(O.to_xyz("bt709", "D65")), O.to_xyz("bt2020", "D65"))
+    ops.pixel_chain(ctx, src, dst, [ops.matrix(M)])
+    gy, gu, gv = dst.download()
+    tex = O.decode_yuv420(y, u, v, w, h, 0.2627, 0.0593, False, False, 0, O.TR_BT709)
+    tex = O.linear(tex, np.array(M, np.float32).reshape(3, 3))
+    ey, eu, ev = O.encode_yuv420(np.asarray(tex.data if hasattr(tex, "data") else tex).reshape(h, w, 4), 0.2126, 0.0722, False, O.TR_BT709)
+    for got, exp in ((gy, ey), (gu, eu), (gv, ev)):
+        assert max_lsb(got, exp) <= 1
+        assert np.mean(got == exp) > 0.98
+
+
 # ---------------------------------------------------------------- specialised kernels == generic kernels
 @pytest.mark.parametrize("space", ["oklab", "srlab2"])
 @pytest.mark.parametrize("parts", ["LchA", "LabA"])

@@ -19,6 +19,7 @@ cudaError_t upload_constants_frame(const TablesGlobal*, const ColorConstants*, c
 cudaError_t upload_constants_affine(const TablesGlobal*, const ColorConstants*, cudaStream_t);
 cudaError_t upload_constants_rowwise_lut(const TablesGlobal*, const ColorConstants*, cudaStream_t);
 cudaError_t upload_constants_rowwise_lab(const TablesGlobal*, const ColorConstants*, cudaStream_t);
+cudaError_t upload_constants_yuv_chain(const TablesGlobal*, const ColorConstants*, cudaStream_t);
 
 static thread_local std::string g_create_error;
 
@@ -269,6 +270,7 @@ zos_status zos_ctx_create(int32_t device, zos_ctx** out) {
     if (e5 == cudaSuccess) e5 = upload_constants_affine(t, c, ctx->stream);
     if (e5 == cudaSuccess) e5 = upload_constants_rowwise_lut(t, c, ctx->stream);
     if (e5 == cudaSuccess) e5 = upload_constants_rowwise_lab(t, c, ctx->stream);
+    if (e5 == cudaSuccess) e5 = upload_constants_yuv_chain(t, c, ctx->stream);
     cudaError_t e4 = cudaStreamSynchronize(ctx->stream);
     delete t;
     delete c;
@@ -407,8 +409,9 @@ zos_status zos_pixel_chain(zos_ctx* ctx, const zos_image* src, const zos_image* 
   if (s.w != d.w || s.h != d.h) return fail(ctx, ZOS_ERR_TYPE, "pixel_chain: size mismatch %dx%d vs %dx%d", s.w, s.h, d.w, d.h);
   if (batch == 0) return ZOS_OK;
   cudaSetDevice(ctx->device);
-  if (s.block != ZOS_BLOCK_PIXEL || d.block != ZOS_BLOCK_PIXEL) {
-    // planar sources / destinations go through the gather kernel with the identity mapping
+  if (d.block != ZOS_BLOCK_PIXEL) return launch_yuv_chain(ctx, s, d, steps, nsteps, batch);  // planar destination (yuv_chain.cu)
+  if (s.block != ZOS_BLOCK_PIXEL) {
+    // planar sources go through the gather kernel with the identity mapping
     zos_compose_params cp;
     memset(&cp, 0, sizeof cp);
     cp.map = ZOS_MAP_RECT; cp.sampling = ZOS_SAMPLE_NEAREST; cp.blend = ZOS_BLEND_OVERWRITE;

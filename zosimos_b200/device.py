@@ -180,8 +180,24 @@ class DeviceImage:
     def download(self) -> np.ndarray:
         lib, ctx = self.ctx._lib, self.ctx
         w, h = self.desc.size()
-        if self.planar:
-            raise NotImplementedError("planar download")
+        if self.planar:  # (y, u, v) planes of frame 0..batch-1; NV12: (y, interleaved uv, None)
+            nv12 = self.desc.texel.block == Block.Yuv420Nv12
+            crb = self.cw * (2 if nv12 else 1)
+            y = np.empty((self.batch, h, w), np.uint8)
+            u = np.empty((self.batch, self.ch, crb), np.uint8)
+            v = None if nv12 else np.empty((self.batch, self.ch, crb), np.uint8)
+            for f in range(self.batch):
+                base = f * self.frame_bytes
+                ctx.check(lib.zos_buf_download(ctx.handle, self.buf.handle, base, self.pitch, y[f].ctypes.data_as(C.c_void_p), w, w, h))
+                ctx.check(lib.zos_buf_download(ctx.handle, self.buf.handle, base + self.y_bytes, self.cpitch,
+                                               u[f].ctypes.data_as(C.c_void_p), crb, crb, self.ch))
+                if v is not None:
+                    ctx.check(lib.zos_buf_download(ctx.handle, self.buf.handle, base + self.y_bytes + self.c_bytes, self.cpitch,
+                                                   v[f].ctypes.data_as(C.c_void_p), crb, crb, self.ch))
+            ctx.sync()
+            if self.batch == 1:
+                return y[0], u[0], (None if v is None else v[0])
+            return y, u, v
         rb = w * self.desc.layout.texel_stride
         out = np.empty((self.batch, h, rb), np.uint8)
         for f in range(self.batch):
