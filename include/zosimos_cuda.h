@@ -112,7 +112,12 @@ void zos_ctx_destroy(zos_ctx* ctx);
 const char* zos_last_error(const zos_ctx* ctx); /* ctx may be NULL: last error of a failed create */
 int32_t zos_ctx_device(const zos_ctx* ctx);
 void* zos_ctx_stream(const zos_ctx* ctx);       /* the cudaStream_t all launches of this ctx go to */
-zos_status zos_sync(zos_ctx* ctx);              /* SyncPoint::block_on, run.rs:3019 */
+zos_status zos_sync(zos_ctx* ctx);
+/* Verification hook, host only (no context, no GPU): the rounding thresholds of the correctly rounded sRGB8
+ * encoder (thr[k] = smallest f32 whose code is >= k; [0] = -inf, [256..259] = +inf) and the two bucket tables
+ * the kernels derive from them (zosimos_b200/csrc/texel.cuh).  Arrays may be NULL; buckets holds up to 2048
+ * entries.  The reference leaves this encode to the texture unit (program.rs:794-838). */
+zos_status zos_srgb_encoder_tables(float* thresholds260, uint32_t* buckets, uint32_t* n_buckets, uint32_t* buckets2, uint32_t* n_buckets2);              /* SyncPoint::block_on, run.rs:3019 */
 uint64_t zos_ctx_launch_count(const zos_ctx* ctx); /* kernels launched so far (bench: gpu_launches) */
 /* debugging / parity switches; ZOS_CTX_NO_FAST_PATHS routes every launch through the generic kernels */
 enum { ZOS_CTX_NO_FAST_PATHS = 1 };

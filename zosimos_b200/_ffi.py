@@ -116,6 +116,7 @@ SIGNATURES = {
     "zos_program_launch": (C.c_int32, [_P]),
     "zos_program_step": (C.c_int32, [_P, C.c_uint32, C.POINTER(C.c_int32)]),
     "zos_program_kernel_count": (C.c_uint32, [_P]),
+    "zos_srgb_encoder_tables": (C.c_int32, [C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "zos_program_run": (C.c_int32, [_P, C.c_uint32]),
     "zos_program_graph_launches": (C.c_uint64, [_P]),
     "zos_program_register_image": (C.c_int32, [_P, C.c_int32, C.POINTER(ZosImage)]),

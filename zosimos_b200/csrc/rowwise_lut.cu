@@ -26,13 +26,11 @@
 namespace zos {
 
 constexpr int LUT_THREADS = 1024;
-constexpr int ENC_B0 = ZOS_ENC_B0, ENC_N = ZOS_ENC_N;  // the bucket table of texel.cuh
-constexpr int ER = 16;                           // replication of the encode table
-constexpr uint32_t DEC_BYTES = 256u * 256u;      // [code][0..31] sRGB EOTF, [code][32..63] code/255
-constexpr uint32_t ENC_BYTES = (uint32_t)ENC_N * ER * 4u;
-constexpr uint32_t ENC_SHIFT = 16 - 6;           // bits >> 16 is the bucket, entries are ER*4 = 64 bytes apart
-constexpr uint32_t ENC_MASK = 0x7ffu * (ER * 4u);  // the low 11 bits of the bucket are unique over [ENC_B0, 0x3f80]
-constexpr uint32_t ENC_VOFF = (ENC_B0 & 0x7ff) * (ER * 4u);  // masked offset of the first bucket
+constexpr uint32_t DEC_BYTES = 256u * 256u;                    // [code][0..31] sRGB EOTF, [code][32..63] code/255
+constexpr uint32_t ENC_BYTES = (uint32_t)ZOS_ENC2_N * 128u;    // [bucket][0..31]: one private copy per lane
+constexpr uint32_t ENC_SHIFT = 16 - 7;                         // bits(y) >> 16 is the key, rows are 128 bytes apart
+constexpr uint32_t ENC_MASK = 0x3ffu * 128u;                   // the low 10 bits of the key are unique over the table
+constexpr uint32_t ENC_VOFF = (ZOS_ENC2_K0 & 0x3ff) * 128u;    // masked offset of the first row (32 KB: the decode table sits below)
 
 ZOS_DEFINE_CONSTANT_UPLOAD(upload_constants_rowwise_lut)
 
@@ -51,7 +49,6 @@ struct LutCtx {
   uint32_t dec;      // shared address of the decode table
   uint32_t enc;      // shared address of the encode table minus ENC_VOFF
   uint32_t lane4;    // (lane & 31) * 4, upper bytes zero: byte 0 of every decode address
-  uint32_t lane_er;  // (lane & (ER-1)) * 4
   uint32_t sr, sg, sb, sa;  // byte-permute selectors building (code << 8) | lane4 for R, G, B, A of a source word
   uint32_t spack;           // final selector of the destination word (RGBA / BGRA)
 };
@@ -69,11 +66,13 @@ __device__ __forceinline__ Px decode8(uint32_t w, const LutCtx& c) {
   return p;
 }
 
-// correctly rounded sRGB8 code of x (x <= 1 up to one rounding), in byte 2 of the result
-__device__ __forceinline__ uint32_t srgb_code_b2(float x, const LutCtx& c) {
-  const int idx = max(__float_as_int(x), ENC_B0 << 16);
-  uint32_t a;  // ((idx >> SHIFT) & MASK) | lane column, as ONE logic op
-  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(a) : "r"((uint32_t)idx >> ENC_SHIFT), "r"(ENC_MASK), "r"(c.lane_er));
+// correctly rounded sRGB8 code of x (0 <= x <= 1 up to one rounding), in byte 3 of the result: the
+// biased-key bucket table of texel.cuh, one conflict-free look-up
+__device__ __forceinline__ uint32_t srgb_code_b3(float x, const LutCtx& c) {
+  const float y = x + ZOS_ENC2_BIAS;
+  const int idx = max(__float_as_int(x), ZOS_ENC2_LOW);
+  uint32_t a;  // ((bits(y) >> SHIFT) & MASK) | lane column, as ONE logic op
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(a) : "r"(__float_as_uint(y) >> ENC_SHIFT), "r"(ENC_MASK), "r"(c.lane4));
   return lds_u32(a + c.enc) + (uint32_t)idx;
 }
 
@@ -90,8 +89,8 @@ __device__ __forceinline__ uint32_t encode8(const Px& p, const LutCtx& c, uint32
   if (!RAW_ALPHA) ca = __float_as_uint(v[3] * 255.0f + 8388608.0f);  // code in byte 0 (blended alpha is in [0, 1])
   uint32_t t1, t2;
   if constexpr (DK == K_SRGB8) {
-    t1 = __byte_perm(srgb_code_b2(v[0], c), srgb_code_b2(v[1], c), 0x0062);
-    t2 = __byte_perm(srgb_code_b2(v[2], c), ca, RAW_ALPHA ? 0x0072 : 0x0042);
+    t1 = __byte_perm(srgb_code_b3(v[0], c), srgb_code_b3(v[1], c), 0x0073);
+    t2 = __byte_perm(srgb_code_b3(v[2], c), ca, RAW_ALPHA ? 0x0073 : 0x0043);
   } else {
     t1 = __byte_perm(__float_as_uint(v[0] * 255.0f + 8388608.0f), __float_as_uint(v[1] * 255.0f + 8388608.0f), 0x0040);
     t2 = __byte_perm(__float_as_uint(v[2] * 255.0f + 8388608.0f), ca, RAW_ALPHA ? 0x0070 : 0x0040);
@@ -140,7 +139,7 @@ __global__ void __launch_bounds__(LUT_THREADS, 1) k_rowwise_lut(const __grid_con
   for (int i = threadIdx.x; i < 256 * 64; i += LUT_THREADS) dec[i] = (i & 32) ? g_tables.unorm8[i >> 6] : g_tables.srgb_dec[i >> 6];
   if (DK == K_SRGB8) {
 #pragma unroll 4
-    for (int i = threadIdx.x; i < ENC_N * ER; i += LUT_THREADS) enc[i] = g_tables.srgb_enc[i / ER];
+    for (int i = threadIdx.x; i < ZOS_ENC2_N * 32; i += LUT_THREADS) enc[i] = g_tables.srgb_enc2[i >> 5];
   }
   __syncthreads();
 
@@ -148,7 +147,6 @@ __global__ void __launch_bounds__(LUT_THREADS, 1) k_rowwise_lut(const __grid_con
   c.dec = (uint32_t)__cvta_generic_to_shared(dec);
   c.enc = (uint32_t)__cvta_generic_to_shared(enc) - ENC_VOFF;
   c.lane4 = (threadIdx.x & 31u) * 4u;
-  c.lane_er = (threadIdx.x & (ER - 1u)) * 4u;
   // selector nibbles: byte 0 <- lane4.byte0 (4), byte 1 <- word byte k, bytes 2, 3 <- lane4's zero bytes (6, 7)
   const uint32_t kr = P.src_bgra ? 2u : 0u, kb = P.src_bgra ? 0u : 2u;
   c.sr = 0x7604u | (kr << 4); c.sg = 0x7614u; c.sb = 0x7604u | (kb << 4); c.sa = 0x7634u;

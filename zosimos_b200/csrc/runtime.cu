@@ -84,6 +84,31 @@ static bool build_constants(TablesGlobal* t, ColorConstants* c) {
       t->srgb_enc[b] = (base << 16) + (0x10000u - t16) - (top << 16);
     }
   }
+  {  // biased-key bucket table (texel.cuh): buckets are intervals of bit patterns of x found by bisection
+    auto bits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
+    auto fl = [](uint32_t u) { float f; memcpy(&f, &u, 4); return f; };
+    auto key = [&](uint32_t idx) { volatile float y = fl(idx) + ZOS_ENC2_BIAS; return bits(y) >> 16; };
+    const uint32_t LOW = (uint32_t)ZOS_ENC2_LOW, HIGH = bits(1.0f) + 64u;  // blended values may exceed 1 by a rounding
+    uint32_t lo[ZOS_ENC2_N + 1];
+    for (int k = 0; k <= ZOS_ENC2_N; k++) {  // lo[k] = smallest pattern in [LOW, HIGH] whose key is >= K0 + k (HIGH + 1 if none)
+      uint32_t a = LOW, b = HIGH + 1;
+      while (a < b) { uint32_t m = a + (b - a) / 2; if (key(m) >= (uint32_t)(ZOS_ENC2_K0 + k)) b = m; else a = m + 1; }
+      lo[k] = a;
+    }
+    if (lo[0] != LOW) return false;
+    for (int k = 0; k < ZOS_ENC2_N; k++) {
+      const uint32_t l = lo[k], h = lo[k + 1];  // bucket = [l, h)
+      if (h - l >= (1u << 24)) return false;
+      uint32_t base = 0;
+      while (base < 255 && bits(t->srgb_thr[base + 1]) <= l) base++;
+      uint32_t T = l + 0x00ffffffu;
+      if (base < 255 && bits(t->srgb_thr[base + 1]) < h) {
+        T = bits(t->srgb_thr[base + 1]);
+        if (base + 2 <= 255 && bits(t->srgb_thr[base + 2]) < h) return false;  // two thresholds in one bucket
+      }
+      t->srgb_enc2[k] = (base << 24) + (1u << 24) - T;
+    }
+  }
   // Oklab M1, M2 (row-major; lib/std/src/oklab.frag:14-24 lists them column-major)
   static const float m1[9] = {0.8189330101f, 0.3618667424f, -0.1288597137f, 0.0329845436f, 0.9293118715f,
                               0.0361456387f, 0.0482003018f, 0.2643662691f, 0.6338517070f};
@@ -304,6 +329,23 @@ zos_status zos_ctx_set_flags(zos_ctx* ctx, uint32_t flags) {
   ctx->flags = flags;
   return ZOS_OK;
 }
+// Host-only view of the tables behind the exact sRGB8 encoders (texel.cuh), for verification without a GPU.
+zos_status zos_srgb_encoder_tables(float* thresholds260, uint32_t* buckets, uint32_t* n_buckets, uint32_t* buckets2, uint32_t* n_buckets2) {
+  TablesGlobal* t = new TablesGlobal();
+  ColorConstants* c = new ColorConstants();
+  const bool ok = build_constants(t, c);
+  if (ok) {
+    if (thresholds260) memcpy(thresholds260, t->srgb_thr, sizeof t->srgb_thr);
+    if (buckets) memcpy(buckets, t->srgb_enc, sizeof t->srgb_enc);
+    if (buckets2) memcpy(buckets2, t->srgb_enc2, sizeof t->srgb_enc2);
+    if (n_buckets) *n_buckets = ZOS_ENC_N;
+    if (n_buckets2) *n_buckets2 = ZOS_ENC2_N;
+  }
+  delete t;
+  delete c;
+  return ok ? ZOS_OK : ZOS_ERR_INVALID;
+}
+
 zos_status zos_sync(zos_ctx* ctx) {
   if (!ctx) return ZOS_ERR_INVALID;
   zos_status st = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");

@@ -30,11 +30,23 @@ struct Tables {           // shared-memory copy, filled once per CTA
 // (e + bits(x)) >> 16 is the correctly rounded code of x.  Values below 2^-13 encode to 0.
 constexpr int ZOS_ENC_B0 = 0x3900;                    // top 16 bits of 2^-13
 constexpr int ZOS_ENC_N = 0x3f80 - ZOS_ENC_B0 + 1;    // up to and including the bucket of 1.0
+// Second form of the same idea with 2.6x fewer buckets, so that a table with one private copy per lane
+// (no shared-memory bank conflicts at all) fits: the bucket key is taken from the bit pattern of
+// y = x + 2^-5 instead of x.  Adding the bias compresses the low end, where thresholds are sparse in
+// log space, so 7 mantissa bits of y separate all 255 thresholds over [0, 1] with 646 buckets.  A bucket
+// is now just an interval of bit patterns of x (float addition is monotone), not an aligned range, and
+//   e = (base << 24) + 2^24 - T      (T = bit pattern of the bucket's threshold, or one past its end)
+// gives (e + bits(x)) >> 24 == base + (bits(x) >= T) because every bucket is narrower than 2^24 patterns.
+constexpr float ZOS_ENC2_BIAS = 0.03125f;
+constexpr int ZOS_ENC2_K0 = 0x3d00;                     // bits(bias) >> 16
+constexpr int ZOS_ENC2_N = 0x3f85 - ZOS_ENC2_K0 + 1;    // through the bucket of 1 + bias, one spare
+constexpr int ZOS_ENC2_LOW = 0x39000000;                // 2^-13: everything below encodes like it (code 0)
 struct TablesGlobal {
   float srgb_dec[256];
   float unorm8[256];
   float srgb_thr[260];
-  uint32_t srgb_enc[ZOS_ENC_N];  // not part of the per-CTA copy `Tables`
+  uint32_t srgb_enc[ZOS_ENC_N];    // not part of the per-CTA copy `Tables`
+  uint32_t srgb_enc2[ZOS_ENC2_N];  // ditto
 };
 // One copy per translation unit (no relocatable device code): every kernel .cu exports an
 // upload function built from ZOS_DEFINE_CONSTANT_UPLOAD (colorops.cuh) that runtime.cu calls at
