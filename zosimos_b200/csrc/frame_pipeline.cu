@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(THREADS, 3) k_frame_pipeline(const __grid_cons
 //   * the converted footprint is kept as three f32 planes (no alpha plane), sized by the exact tap span;
 //   * sRGB8 encode through the bucket table (texel.cuh): one look-up per channel, no transcendental;
 //   * no run-time format / transfer / sampling switches.
-constexpr int FER = 4;  // replication of the encoder bucket table in shared memory
+constexpr int FER = 8;  // copies of the (biased-key, texel.cuh) encoder bucket table in shared memory
 
 template <int TRK>
 __device__ __forceinline__ float eotf_k(uint32_t tr, float v) {
@@ -313,10 +313,11 @@ __device__ __forceinline__ float lds32(uint32_t a) {
   return v;
 }
 
-// correctly rounded sRGB8 code of x in [0, 1], in byte 2 of the result (see texel.cuh)
-__device__ __forceinline__ uint32_t srgb_code_b2(float x, uint32_t enc_lane) {
-  const int idx = max(__float_as_int(x), ZOS_ENC_B0 << 16);
-  const uint32_t a = ((((uint32_t)idx >> 16) - (uint32_t)ZOS_ENC_B0) * (FER * 4u)) + enc_lane;
+// correctly rounded sRGB8 code of x in [0, 1], in byte 3 of the result (biased-key table, texel.cuh)
+__device__ __forceinline__ uint32_t srgb_code_b3(float x, uint32_t enc_lane) {
+  const float y = x + ZOS_ENC2_BIAS;
+  const int idx = max(__float_as_int(x), ZOS_ENC2_LOW);
+  const uint32_t a = (((__float_as_uint(y) >> 16) - (uint32_t)ZOS_ENC2_K0) * (FER * 4u)) + enc_lane;
   uint32_t e;
   asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(a));
   return e + (uint32_t)idx;
@@ -335,7 +336,7 @@ __global__ void __launch_bounds__(THREADS, 3) k_frame_fast(const __grid_constant
   const uint32_t conv_base = smem_u32(dyn + 2 * (size_t)stage_bytes);
   uint32_t* enc = reinterpret_cast<uint32_t*>(dyn + 2 * (size_t)stage_bytes + 3 * (size_t)P.plane_bytes);
   if (SRGB_DST) {
-    for (int i = threadIdx.x; i < ZOS_ENC_N * FER; i += THREADS) enc[i] = g_tables.srgb_enc[i / FER];
+    for (int i = threadIdx.x; i < ZOS_ENC2_N * FER; i += THREADS) enc[i] = g_tables.srgb_enc2[i / FER];
   }
   const uint32_t enc_lane = smem_u32(enc) + (threadIdx.x & (FER - 1)) * 4u;
   if (threadIdx.x == 0) {
@@ -439,8 +440,8 @@ __global__ void __launch_bounds__(THREADS, 3) k_frame_fast(const __grid_constant
             r = fminf(fmaxf(r, 0.0f), 1.0f); gg = fminf(fmaxf(gg, 0.0f), 1.0f); b = fminf(fmaxf(b, 0.0f), 1.0f);
             uint32_t t1, t2;
             if (SRGB_DST) {
-              t1 = __byte_perm(srgb_code_b2(r, enc_lane), srgb_code_b2(gg, enc_lane), 0x0062);
-              t2 = __byte_perm(srgb_code_b2(b, enc_lane), 0xffu, 0x0042);
+              t1 = __byte_perm(srgb_code_b3(r, enc_lane), srgb_code_b3(gg, enc_lane), 0x0073);
+              t2 = __byte_perm(srgb_code_b3(b, enc_lane), 0xffu, 0x0043);
             } else {
               t1 = __byte_perm(__float_as_uint(r * 255.0f + 8388608.0f), __float_as_uint(gg * 255.0f + 8388608.0f), 0x0040);
               t2 = __byte_perm(__float_as_uint(b * 255.0f + 8388608.0f), 0xffu, 0x0040);
@@ -547,7 +548,7 @@ zos_status launch_frame_pipeline(zos_ctx* ctx, const DevImage* below, const DevI
     stage = ybox_al + (P.nv12 ? 1 : 2) * cbox_al;
     P.plane_bytes = (uint32_t)(P.conv_w * P.conv_h * 4);
     P.div_cbw = make_fastdiv((uint32_t)(P.conv_w / 2));
-    const size_t fsmem = 2 * stage + 3 * (size_t)P.plane_bytes + (srgb ? (size_t)ZOS_ENC_N * FER * 4 : 0);
+    const size_t fsmem = 2 * stage + 3 * (size_t)P.plane_bytes + (srgb ? (size_t)ZOS_ENC2_N * FER * 4 : 0);
     bool ok2 = make_map(ctx, &M.m0, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, above.p0, above.w, above.h, above.pitch, batch, above.bstride, P.box_w, P.box_h);
     if (ok2 && P.nv12) ok2 = make_map(ctx, &M.m1, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, above.p1, cw, ch, above.cpitch, batch, above.cbstride, P.cbox_w, P.cbox_h);
     if (ok2 && !P.nv12)

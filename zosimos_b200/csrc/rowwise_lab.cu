@@ -28,13 +28,12 @@ ZOS_DEFINE_CONSTANT_UPLOAD(upload_constants_rowwise_lab)
 
 namespace {
 constexpr int LAB_THREADS = 1024;
-constexpr int ER = 8;                                    // replication of the encoder bucket table
 constexpr uint32_t DEC_BYTES = 256u * 256u;              // [code][0..31] colour decode, [code][32..63] alpha map
 constexpr uint32_t Q_BYTES = 256u * 256u;                // [code][lane & 15] float4 {f16(code/255), code/255, cos(hue(code)), sin(hue(code))}
-constexpr uint32_t ENC_BYTES = (uint32_t)ZOS_ENC_N * ER * 4u;
-constexpr uint32_t ENC_SHIFT = 16 - 5;
-constexpr uint32_t ENC_MASK = 0x7ffu * (ER * 4u);
-constexpr uint32_t ENC_VOFF = (ZOS_ENC_B0 & 0x7ff) * (ER * 4u);
+constexpr uint32_t ENC_BYTES = (uint32_t)ZOS_ENC2_N * 128u;  // biased-key bucket table (texel.cuh), one private copy per lane
+constexpr uint32_t ENC_SHIFT = 16 - 7;
+constexpr uint32_t ENC_MASK = 0x3ffu * 128u;
+constexpr uint32_t ENC_VOFF = (ZOS_ENC2_K0 & 0x3ff) * 128u;
 
 struct LabParams {
   FastParams F;  // below = the source
@@ -55,15 +54,16 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 
 struct Ctx {
   uint32_t dec, q, enc;     // shared addresses (enc minus ENC_VOFF)
-  uint32_t lane4, lane_er;  // (lane & 31) * 4 with zero upper bytes; (lane & (ER-1)) * 4
+  uint32_t lane4;           // (lane & 31) * 4 with zero upper bytes
   uint32_t lane_q;          // (lane & 15) * 16
   uint32_t sr, sg, sb, sa, spack;
 };
 
-__device__ __forceinline__ uint32_t srgb_code_b2(float x, const Ctx& c) {
-  const int idx = max(__float_as_int(x), ZOS_ENC_B0 << 16);
+__device__ __forceinline__ uint32_t srgb_code_b3(float x, const Ctx& c) {  // x in [0, 1]; code in byte 3
+  const float y = x + ZOS_ENC2_BIAS;
+  const int idx = max(__float_as_int(x), ZOS_ENC2_LOW);
   uint32_t a;
-  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(a) : "r"((uint32_t)idx >> ENC_SHIFT), "r"(ENC_MASK), "r"(c.lane_er));
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(a) : "r"(__float_as_uint(y) >> ENC_SHIFT), "r"(ENC_MASK), "r"(c.lane4));
   return lds_u32(a + c.enc) + (uint32_t)idx;
 }
 
@@ -97,8 +97,8 @@ __device__ __forceinline__ uint32_t pixel(const LabParams& P, uint32_t w, const 
   if (LAB == 0) oklab_dec(P.dec, v); else srlab2_dec(P.dec, v);  // ends with clamp01 on the colour
   uint32_t t1, t2;
   if (SRGB_DST) {
-    t1 = __byte_perm(srgb_code_b2(v.x, c), srgb_code_b2(v.y, c), 0x0062);
-    t2 = __byte_perm(srgb_code_b2(v.z, c), acode, 0x0042);
+    t1 = __byte_perm(srgb_code_b3(v.x, c), srgb_code_b3(v.y, c), 0x0073);
+    t2 = __byte_perm(srgb_code_b3(v.z, c), acode, 0x0043);
   } else {
     t1 = __byte_perm(__float_as_uint(v.x * 255.0f + 8388608.0f), __float_as_uint(v.y * 255.0f + 8388608.0f), 0x0040);
     t2 = __byte_perm(__float_as_uint(v.z * 255.0f + 8388608.0f), acode, 0x0040);
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(LAB_THREADS, 1) k_rowwise_lab(const __grid_con
   }
   if (SRGB_DST) {
 #pragma unroll 4
-    for (int i = threadIdx.x; i < ZOS_ENC_N * ER; i += LAB_THREADS) enc[i] = g_tables.srgb_enc[i / ER];
+    for (int i = threadIdx.x; i < ZOS_ENC2_N * 32; i += LAB_THREADS) enc[i] = g_tables.srgb_enc2[i >> 5];
   }
   __syncthreads();
 
@@ -146,7 +146,6 @@ __global__ void __launch_bounds__(LAB_THREADS, 1) k_rowwise_lab(const __grid_con
   c.q = (uint32_t)__cvta_generic_to_shared(q);
   c.enc = (uint32_t)__cvta_generic_to_shared(enc) - ENC_VOFF;
   c.lane4 = (threadIdx.x & 31u) * 4u;
-  c.lane_er = (threadIdx.x & (ER - 1u)) * 4u;
   c.lane_q = (threadIdx.x & 15u) * 16u;
   const uint32_t kr = P.F.src_bgra ? 2u : 0u, kb = P.F.src_bgra ? 0u : 2u;
   c.sr = 0x7604u | (kr << 4); c.sg = 0x7614u; c.sb = 0x7604u | (kb << 4); c.sa = 0x7634u;
