@@ -59,6 +59,8 @@ __device__ __forceinline__ Loc locate(const FastParams& P, uint32_t idx) {
 
 // rowwise_lut.cu: 8-bit -> 8-bit texel pairs (sk, dk in {K_SRGB8, K_UNORM8}); mode 0 = convert, 2 = source-over
 cudaError_t launch_rowwise_lut(zos_ctx* ctx, FastParams& P, int sk, int dk, int mode, int nmat);
+// rowwise_rgb10.cu: staged RGB10A2 on both sides, convert mode
+cudaError_t launch_rowwise_rgb10(zos_ctx* ctx, const FastParams& P, int nmat);
 // rowwise_lab.cu: 8-bit -> [Lab encode, 8-bit staged register, Lab decode] -> 8-bit; *handled stays false when not served
 cudaError_t launch_rowwise_lab(zos_ctx* ctx, const DevImage& src, const DevImage& dst, const zos_step* steps, uint32_t nsteps, uint32_t batch, bool* handled);
 

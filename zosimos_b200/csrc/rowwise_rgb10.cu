@@ -1,0 +1,127 @@
+// rowwise_rgb10.cu -- staged UInt1010102 RgbA texels on both sides (the RGB10A2 row of BASELINE config 5)
+// with 0..2 matrix steps in between.  The reference handles this texel in stage.frag (decode
+// :471-482,533-582, encode :484-501,590-641: demux, inverse transfer, Rgba16Float working texture; f16
+// attachment, transfer, clamp, TRUNCATING quantisation).  Every stage of that codec is a function of few
+// bits, so both directions become tables built at kernel start BY RUNNING THE GENERIC CODEC'S OWN CODE:
+//
+//   decode: D[k]  = f16(eotf(k / 1023)), 1024 entries (8 copies);   alpha: 4 entries, via A[] below
+//   encode: E[h]  = uint(clamp01(oetf(half(h))) * 1023) for all 65536 f16 bit patterns h (the value
+//           stored in the f16 attachment is all the encoder ever sees), as u16: 128 KB;
+//   alpha:  A[a2] = encode(decode(a2)) (not the identity: f16(1/3) * 3 truncates to 0).
+//
+// Results equal k_rowwise_fast<K_RGB10, K_RGB10> and the generic kernel bit for bit (tests); instead of
+// six pow evaluations a pixel costs three decode and three encode look-ups.
+#include <cuda_fp16.h>
+
+#include "colorops.cuh"
+#include "zos_internal.h"
+#include "rowwise_params.cuh"
+
+namespace zos {
+
+ZOS_DEFINE_CONSTANT_UPLOAD(upload_constants_rowwise_rgb10)
+
+namespace {
+constexpr int THREADS = 1024;
+constexpr int DR = 8;                                  // copies of the decode table
+constexpr uint32_t DEC_BYTES = 1024u * DR * 4u;        // [code][lane & 7]
+constexpr uint32_t ENC_BYTES = 65536u * 2u;            // [f16 bits] -> 10-bit code
+constexpr uint32_t SMEM_BYTES = DEC_BYTES + ENC_BYTES;
+
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+  uint32_t v;
+  asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t half_bits(float v) {
+  return (uint32_t)__half_as_ushort(__float2half_rn(v));
+}
+
+template <int NMAT>
+__device__ __forceinline__ uint32_t pixel(const FastParams& P, uint32_t w, uint32_t dec_lane, uint32_t enc, uint32_t amap) {
+  float r = lds_f32(dec_lane + (w & 1023u) * (DR * 4u));
+  float g = lds_f32(dec_lane + ((w >> 10) & 1023u) * (DR * 4u));
+  float b = lds_f32(dec_lane + ((w >> 20) & 1023u) * (DR * 4u));
+#pragma unroll
+  for (int k = 0; k < NMAT; k++) {
+    float3 t = mat3_mul(P.m[k], r, g, b);
+    r = t.x; g = t.y; b = t.z;
+  }
+  const uint32_t cr = lds_u16(enc + half_bits(r) * 2u), cg = lds_u16(enc + half_bits(g) * 2u), cb = lds_u16(enc + half_bits(b) * 2u);
+  const uint32_t a2 = (amap >> ((w >> 30) * 2u)) & 3u;
+  return cr + (cg << 10) + (cb << 20) + (a2 << 30);
+}
+
+template <int NMAT>
+__global__ void __launch_bounds__(THREADS, 1) k_rowwise_rgb10(const __grid_constant__ FastParams P) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  float* dec = reinterpret_cast<float*>(smem);
+  uint16_t* enc = reinterpret_cast<uint16_t*>(smem + DEC_BYTES);
+  const bool src_srgb = P.src_tr == ZOS_TRANSFER_SRGB, dst_srgb = P.dst_tr == ZOS_TRANSFER_SRGB;
+  // the codec of rowwise_fast.cu's K_RGB10 (== stage.frag), evaluated once per table entry
+  for (int i = threadIdx.x; i < 1024 * DR; i += THREADS) {
+    float p = fld((uint32_t)(i / DR), 1023.0f);
+    if (src_srgb) p = eo_srgb(p);
+    dec[i] = f16r(p);
+  }
+  for (int h = threadIdx.x; h < 65536; h += THREADS) {
+    float r = __half2float(__ushort_as_half((unsigned short)h));  // what the f16 attachment holds
+    if (dst_srgb) r = oe_srgb(r);
+    enc[h] = (uint16_t)(uint32_t)(clamp01(r) * 1023.0f);
+  }
+  uint32_t amap = 0;
+#pragma unroll
+  for (uint32_t a = 0; a < 4; a++) {
+    const float v = f16r(fld(a, 3.0f));                   // decode
+    amap |= ((uint32_t)(clamp01(f16r(v)) * 3.0f)) << (2u * a);  // encode
+  }
+  __syncthreads();
+  const uint32_t dec_lane = (uint32_t)__cvta_generic_to_shared(dec) + (threadIdx.x & (DR - 1)) * 4u;
+  const uint32_t enc_base = (uint32_t)__cvta_generic_to_shared(enc);
+  const uint32_t stride = gridDim.x * THREADS;
+  for (uint32_t idx = blockIdx.x * THREADS + threadIdx.x; idx < P.total_groups; idx += stride) {
+    const Loc L = locate<0>(P, idx);
+    const uint4 rb = __ldcs(reinterpret_cast<const uint4*>(P.below + L.ob));
+    uint32_t o[4];
+    o[0] = pixel<NMAT>(P, rb.x, dec_lane, enc_base, amap); o[1] = pixel<NMAT>(P, rb.y, dec_lane, enc_base, amap);
+    o[2] = pixel<NMAT>(P, rb.z, dec_lane, enc_base, amap); o[3] = pixel<NMAT>(P, rb.w, dec_lane, enc_base, amap);
+    uint8_t* dp = P.dst + L.od;
+    if (L.npx == 4) {
+      __stcs(reinterpret_cast<uint4*>(dp), make_uint4(o[0], o[1], o[2], o[3]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+        if (i < L.npx) reinterpret_cast<uint32_t*>(dp)[i] = o[i];
+    }
+    if (idx + stride < idx) break;  // 32-bit wrap
+  }
+}
+
+template <int NMAT>
+cudaError_t launch_one(zos_ctx* ctx, const FastParams& P) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_rowwise_rgb10<NMAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const uint64_t ctas = ((uint64_t)P.total_groups + THREADS - 1) / THREADS;
+  const int grid = (int)(ctas < (uint64_t)ctx->sm_count ? ctas : (uint64_t)ctx->sm_count);
+  k_rowwise_rgb10<NMAT><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(P);
+  return cudaGetLastError();
+}
+}  // namespace
+
+// staged RGB10A2 -> staged RGB10A2 with `nmat` matrix steps (P as prepared by launch_rowwise_u8)
+cudaError_t launch_rowwise_rgb10(zos_ctx* ctx, const FastParams& P, int nmat) {
+  if (nmat == 0) return launch_one<0>(ctx, P);
+  if (nmat == 1) return launch_one<1>(ctx, P);
+  return launch_one<2>(ctx, P);
+}
+
+}  // namespace zos

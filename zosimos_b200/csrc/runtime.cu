@@ -20,6 +20,7 @@ cudaError_t upload_constants_affine(const TablesGlobal*, const ColorConstants*, 
 cudaError_t upload_constants_rowwise_lut(const TablesGlobal*, const ColorConstants*, cudaStream_t);
 cudaError_t upload_constants_rowwise_lab(const TablesGlobal*, const ColorConstants*, cudaStream_t);
 cudaError_t upload_constants_yuv_chain(const TablesGlobal*, const ColorConstants*, cudaStream_t);
+cudaError_t upload_constants_rowwise_rgb10(const TablesGlobal*, const ColorConstants*, cudaStream_t);
 
 static thread_local std::string g_create_error;
 
@@ -296,6 +297,7 @@ zos_status zos_ctx_create(int32_t device, zos_ctx** out) {
     if (e5 == cudaSuccess) e5 = upload_constants_rowwise_lut(t, c, ctx->stream);
     if (e5 == cudaSuccess) e5 = upload_constants_rowwise_lab(t, c, ctx->stream);
     if (e5 == cudaSuccess) e5 = upload_constants_yuv_chain(t, c, ctx->stream);
+    if (e5 == cudaSuccess) e5 = upload_constants_rowwise_rgb10(t, c, ctx->stream);
     cudaError_t e4 = cudaStreamSynchronize(ctx->stream);
     delete t;
     delete c;
