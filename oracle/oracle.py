@@ -256,6 +256,20 @@ def gen_bilinear(params: Sequence[Sequence[float]], w: int, h: int):
     return out
 
 
+def gen_normal2d(params: Sequence[float], w: int, h: int):
+    p = _f32(np.asarray(params, dtype=np.float32).reshape(7))
+    out = np.empty((h, w, 4), np.float32)
+    lib().zo_gen_normal2d(_fp(p), _fp(out), w, h)
+    return out
+
+
+def gen_fractal_noise(params: Sequence[float], w: int, h: int):
+    p = _f32(np.asarray(params, dtype=np.float32).reshape(5))
+    out = np.empty((h, w, 4), np.float32)
+    lib().zo_gen_fractal_noise(_fp(p), _fp(out), w, h)
+    return out
+
+
 def palette_pass(lhs_tex, rhs_tex, x_coord, y_coord):
     lhs_tex = _f32(lhs_tex); rhs_tex = _f32(rhs_tex)
     h, w = rhs_tex.shape[:2]
@@ -435,6 +449,60 @@ def affine(below: Image, matrix, above: Image, sampling: int = 0) -> Image:
 def bilinear(desc: Desc, params) -> Image:
     """command.rs:1615-1633; params = (u_min, u_max, v_min, v_max, uv_min, uv_max)."""
     return encode(desc, gen_bilinear(params, desc.width, desc.height))
+
+
+def normal2d_with_diagonal(var0: float, var1: float):
+    """shaders/distribution_normal2d.rs:25-39 -> (expectation[2], covariance_inverse row major[4], pseudo_determinant)."""
+    f = np.float32
+    var0, var1 = f(var0), f(var1)
+    d0 = f(0) if var0 == 0 else f(1) / var0
+    d1 = f(0) if var1 == 0 else f(1) / var1
+    pi = f(np.pi)
+    f0 = f(1) if var0 == 0 else f(2) * pi * var0
+    f1 = f(1) if var1 == 0 else f(2) * pi * var1
+    return [0.0, 0.0, float(d0), 0.0, 0.0, float(d1), float(f0 * f1)]
+
+
+def normal2d_with_direction(x: float, y: float):
+    """shaders/distribution_normal2d.rs:50-100 (the 'Herbie' forms, in f32)."""
+    f = np.float32
+    x, y = f(x), f(y)
+    length_sq = f(np.float64(x) * np.float64(x) + np.float64(y) * np.float64(y))
+
+    def hyp(a, b):
+        return f(np.hypot(np.float64(a), np.float64(b)))
+
+    def sym(a, b):
+        h = hyp(a, b)
+        return ((f(1) / h) * (a / h)) / (a + b * (b / a))
+
+    def asym(a, b):
+        a, b = min(a, b), max(a, b)
+        h = hyp(a, b)
+        inner = f(np.float64(a) * np.float64(a / b) + np.float64(b))  # mul_add
+        return ((a / h) / inner) / h
+
+    return [0.0, 0.0, float(sym(x, x)), float(asym(x, y)), float(asym(y, x)), float(sym(y, y)), float(length_sq)]
+
+
+def fractal_noise_with_octaves(n: int, damping: float = None):
+    """shaders/fractal_noise.rs:21-49 -> (scale.x, scale.y, amplitude, damping, octaves)."""
+    f = np.float32
+    amp, damp = f(1.0 / float(n)), f(1.0)
+    if damping is not None:
+        damp = f(damping)
+        total = f(1) - f(np.power(damp, f(n)))
+        amp = f(1) if abs(total) < 1e-7 else (f(1) - damp) / total
+    return [100.0, 100.0, float(amp), float(damp), float(n)]
+
+
+def distribution_normal2d(desc: Desc, params) -> Image:
+    """command.rs distribution_normal2d: a generator like `bilinear`, then the target texel's encode."""
+    return encode(desc, gen_normal2d(params, desc.width, desc.height))
+
+
+def distribution_fractal_noise(desc: Desc, params) -> Image:
+    return encode(desc, gen_fractal_noise(params, desc.width, desc.height))
 
 
 def palette(pal: Image, indices: Image, x_coord, y_coord) -> Image:

@@ -641,6 +641,62 @@ ZO_API void zo_gen_bilinear(const float* p /* u_min,u_max,v_min,v_max,uv_min,uv_
     }
 }
 
+/* distribution_normal2d.frag:43-55: p = expectation[2], covariance_inverse (row major [a b; c d]), pseudo determinant */
+ZO_API void zo_gen_normal2d(const float* p, float* dst, int w, int h) {
+#pragma omp parallel for schedule(static)
+  for (int j = 0; j < h; j++)
+    for (int i = 0; i < w; i++) {
+      float u = ((float)i + 0.5f) / (float)w, v = ((float)j + 0.5f) / (float)h;
+      float px = 2.0f * (u - 0.5f) - p[0], py = 2.0f * (v - 0.5f) - p[1];
+      float tx = p[2] * px + p[3] * py, ty = p[4] * px + p[5] * py;
+      float exponent = 0.5f * (px * tx + py * ty);
+      float value = expf(-exponent) / sqrtf(p[6]);
+      float* o = dst + ((size_t)j * w + i) * 4;
+      o[0] = o[1] = o[2] = value; o[3] = 1.0f;
+    }
+}
+
+/* fractal_noise.frag: pcg4d hash (jcgt.org/published/0009/03/02) of the cell corners, smoothstep interpolation,
+ * `octaves` iterations with the point rotated by 0.5 rad and doubled in between */
+static void zo_pcg4d(uint32_t v[4]) {
+  for (int k = 0; k < 4; k++) v[k] = v[k] * 1664525u + 1013904223u;
+  v[0] += v[1] * v[3]; v[1] += v[2] * v[0]; v[2] += v[0] * v[1]; v[3] += v[1] * v[2];
+  for (int k = 0; k < 4; k++) v[k] ^= v[k] >> 16;
+  v[0] += v[1] * v[3]; v[1] += v[2] * v[0]; v[2] += v[0] * v[1]; v[3] += v[1] * v[2];
+}
+static void zo_hash2(uint32_t sx, uint32_t sy, float out[4]) {
+  uint32_t v[4] = {sx, sy, 0u, 0u};
+  zo_pcg4d(v);
+  for (int k = 0; k < 4; k++) out[k] = (float)v[k] / 4294967296.0f; /* float(0xFFFFFFFFu) == 2^32 */
+}
+ZO_API void zo_gen_fractal_noise(const float* p /* scale.x, scale.y, amplitude, damping, octaves */, float* dst, int w, int h) {
+  const int octaves = (int)p[4];
+  const float c2 = 2.0f * 0.87758255f, s2 = 2.0f * 0.47942555f; /* 2 cos(0.5), 2 sin(0.5) */
+#pragma omp parallel for schedule(static)
+  for (int j = 0; j < h; j++)
+    for (int i = 0; i < w; i++) {
+      float x = ((float)i + 0.5f) / (float)w, y = ((float)j + 0.5f) / (float)h, z = 1.0f;
+      float amp = p[2], acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      for (int o = 0; o < octaves; o++) {
+        float ptx = x * p[0], pty = y * p[1];
+        float flx = floorf(ptx), fly = floorf(pty);
+        float fx = ptx - flx, fy = pty - fly;
+        uint32_t sx = (uint32_t)(int32_t)flx, sy = (uint32_t)(int32_t)fly;
+        float a[4], b[4], c[4], d[4];
+        zo_hash2(sx, sy, a); zo_hash2(sx + 1u, sy, b); zo_hash2(sx, sy + 1u, c); zo_hash2(sx + 1u, sy + 1u, d);
+        float ux = fx * fx * (3.0f - 2.0f * fx), uy = fy * fy * (3.0f - 2.0f * fy);
+        for (int k = 0; k < 4; k++) {
+          float n = (a[k] * (1.0f - ux) + b[k] * ux) + (c[k] - a[k]) * uy * (1.0f - ux) + (d[k] - b[k]) * ux * uy;
+          acc[k] = acc[k] + amp * n;
+        }
+        float nx = c2 * x - s2 * y, ny = s2 * x + c2 * y, nz = 2.0f * x + 2.0f * y + 2.0f * z;
+        x = nx; y = ny; z = nz;
+        amp = amp * p[3];
+      }
+      for (int k = 0; k < 4; k++) dst[((size_t)j * w + i) * 4 + k] = acc[k];
+    }
+}
+
 /* palette.frag:21-32: coordinates come from the index image `rhs` (same size as dst) */
 ZO_API void zo_palette(const float* lhs, int lw, int lh, const float* rhs, int w, int h, const float* xc, const float* yc,
                        float* dst) {

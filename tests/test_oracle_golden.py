@@ -100,3 +100,44 @@ def test_transmute_bytes(fixtures):
     bg = rgba_image(fixtures["background"])
     la16 = O.Desc(512, 512, O.Texel(O.B_UINT16X2, O.P_LUMAA), O.SRGB)
     assert np.array_equal(O.transmute(bg, la16).data, bg.data)
+
+
+def luma_as_rgba(img, bits16, alpha):
+    """What `image::DynamicImage::get_pixel` (the view blockhash hashes, tests/util.rs:21-60) makes of
+    Luma / LumaA images: 16-bit samples go to 8 bits as (x + 128) / 257, luma is replicated."""
+    d = img.desc
+    a = np.frombuffer(np.ascontiguousarray(img.data).tobytes(), dtype=np.uint16 if bits16 else np.uint8)
+    a = a.reshape(d.height, d.width, -1).astype(np.int64)
+    if bits16:
+        a = (a + 128) // 257
+    lum = a[..., 0]
+    al = a[..., 1] if alpha else np.full_like(lum, 255)
+    return np.stack([lum, lum, lum, al], -1).astype(np.uint8)
+
+
+def test_distribution_normal2d(golden_hashes):  # tests/blend.rs:227-254 (LumaA16, sRGB transfer, diagonal covariance)
+    desc = O.Desc(400, 400, O.Texel(O.B_UINT16X2, O.P_LUMAA), O.SRGB)
+    img = O.distribution_normal2d(desc, O.normal2d_with_diagonal(0.2, 0.2))
+    assert O.blockhash256(luma_as_rgba(img, True, True)) in golden_hashes["distribution_normal2d"]
+
+
+def test_distribution_normal1d(golden_hashes):  # tests/blend.rs:256-283 (degenerate covariance from a direction)
+    desc = O.Desc(400, 400, O.Texel(O.B_UINT16X2, O.P_LUMAA), O.SRGB)
+    img = O.distribution_normal2d(desc, O.normal2d_with_direction(0.04998, 0.0501))
+    assert O.blockhash256(luma_as_rgba(img, True, True)) in golden_hashes["distribution_normal1d"]
+
+
+def test_distribution_u8(golden_hashes):  # tests/blend.rs:285-312 (Luma8)
+    desc = O.Desc(400, 400, O.Texel(O.B_UINT8, O.P_LUMA), O.SRGB)
+    img = O.distribution_normal2d(desc, O.normal2d_with_direction(0.04998, 0.0501))
+    assert O.blockhash256(luma_as_rgba(img, False, False)) in golden_hashes["distribution_u8"]
+
+
+def test_distribution_fractal_noise(golden_hashes):  # tests/blend.rs:314-338 (pcg4d hash: integer exact)
+    img = O.distribution_fractal_noise(O.srgb_rgba8(400, 400), O.fractal_noise_with_octaves(4))
+    check(golden_hashes, "distribution_fractal2d", img)
+
+
+def test_bilinear_from_buffer(golden_hashes):  # tests/buffer.rs:121-149: the bilinear parameter block read from a buffer
+    params = ([0, 0, 0, 1], [0, 0, 0.7, 1], [0, 0, 0.3, 1], [0, 1, 0.3, 1], [0, 0, 0, 1], [0, 0, 0, 1])
+    check(golden_hashes, "bilinear_from_buffer", O.bilinear(O.srgb_rgba8(256, 256), params))
