@@ -229,6 +229,14 @@ zos_status zos_compose(zos_ctx* ctx, const zos_image* below, const zos_image* ab
 
 /* constructors (ConstructOp::{Solid,Bilinear}, command.rs:1524-1633; bilinear.frag, solid_rgb.frag):
  * p = 24 floats u_min,u_max,v_min,v_max,uv_min,uv_max; for a solid colour put it in u_min and zero the rest */
+/* Generators (DrawInto without operands): kind + 24 floats (unused ones ignored).
+ *   BILINEAR      u_min,u_max,v_min,v_max,uv_min,uv_max (6 x vec4; bilinear.frag:14-20, shaders/bilinear.rs:34-45)
+ *   SOLID         colour (solid_rgb.frag)
+ *   NORMAL2D      expectation[2], covariance_inverse[4] row major, pseudo_determinant (distribution_normal2d.frag:43-55)
+ *   FRACTAL_NOISE initial_scale[2], amplitude, damping, num_octaves (fractal_noise.frag; shaders/fractal_noise.rs:21-49)
+ * In a zos_op of kind ZOS_OP_GENERATE the generator kind travels in compose.map. */
+enum { ZOS_GEN_BILINEAR = 0, ZOS_GEN_SOLID = 1, ZOS_GEN_NORMAL2D = 2, ZOS_GEN_FRACTAL_NOISE = 3 };
+zos_status zos_generate(zos_ctx* ctx, const zos_image* dst, uint32_t kind, const float* p, uint32_t batch);
 zos_status zos_generate_bilinear(zos_ctx* ctx, const zos_image* dst, const float* p, uint32_t batch);
 zos_status zos_generate_solid(zos_ctx* ctx, const zos_image* dst, const float* color /* 4 floats */, uint32_t batch);
 /* box3.frag:16-52 (derivative, command.rs:1493-1508): m = 3x3 weights, row-major [dy+1][dx+1] */

@@ -64,6 +64,14 @@ int32_t zosh_cb_blend(zosh_cb* cb, int32_t below, zosh_rect rect, int32_t above,
 int32_t zosh_cb_transmute(zosh_cb* cb, int32_t src, const zos_desc* target, int32_t* reg);            /* command.rs:1276 */
 int32_t zosh_cb_bilinear(zosh_cb* cb, const zos_desc* desc, const float p[24], int32_t* reg);         /* command.rs:1615 */
 int32_t zosh_cb_solid_rgba(zosh_cb* cb, const zos_desc* desc, const float color[4], int32_t* reg);    /* command.rs:1524 */
+/* generators of the std library next to `bilinear` (command.rs distribution_normal2d / distribution_fractal_noise;
+ * shaders/distribution_normal2d.rs:25-100, shaders/fractal_noise.rs:21-49).  params as in zos_generate. */
+void zosh_normal2d_with_diagonal(float var0, float var1, float out[7]);
+void zosh_normal2d_with_direction(float x, float y, float out[7]);
+void zosh_fractal_noise_with_octaves(uint32_t octaves, float out[5]);
+void zosh_fractal_noise_set_damping(float params[5], float damping);
+int32_t zosh_cb_distribution_normal2d(zosh_cb* cb, const zos_desc* desc, const float params[7], int32_t* reg);
+int32_t zosh_cb_distribution_fractal_noise(zosh_cb* cb, const zos_desc* desc, const float params[5], int32_t* reg);
 int32_t zosh_cb_derivative(zosh_cb* cb, int32_t src, uint32_t method, uint32_t height_direction, int32_t* reg); /* :1493 */
 int32_t zosh_cb_palette(zosh_cb* cb, int32_t palette, int32_t indices, const float xc[4], const float yc[4], int32_t* reg); /* :1442 */
 /* channel: 0 R, 1 G, 2 B, 3 Alpha (ColorChannel); extract = full copy whose destination texel keeps one channel */

@@ -364,3 +364,54 @@ def test_executable_reuse_cuda_graph(pool, images, fixtures):
     assert np.array_equal(current(), fresh[2])
     assert ex.graph_launches() == 5
     ex.retire_gracefully(pool).finish()
+
+
+def _luma_as_rgba(img, bits16, alpha):
+    d = img.descriptor()
+    a = np.frombuffer(img.as_bytes().tobytes(), dtype=np.uint16 if bits16 else np.uint8).reshape(d.layout.height, d.layout.width, -1).astype(np.int64)
+    if bits16:
+        a = (a + 128) // 257
+    lum = a[..., 0]
+    al = a[..., 1] if alpha else np.full_like(lum, 255)
+    return np.stack([lum, lum, lum, al], -1).astype(np.uint8)
+
+
+@pytest.mark.parametrize("case", ["distribution_normal2d", "distribution_normal1d", "distribution_u8"])
+def test_run_distribution_normal2d(pool, case):  # tests/blend.rs:227-312
+    from zosimos_b200.command import DistributionNormal2d
+    kind = "luma8" if case == "distribution_u8" else "luma_a16"
+    desc = Descriptor.with_srgb_image(kind, 400, 400)
+    dist = DistributionNormal2d.with_diagonal(0.2, 0.2) if case == "distribution_normal2d" else DistributionNormal2d.with_direction([0.04998, 0.0501])
+    c = CommandBuffer()
+    output, _ = c.output(c.distribution_normal2d(desc, dist))
+    img, _ = run_once_with_output(c, pool, [], output)
+    assert O.blockhash256(_luma_as_rgba(img, kind == "luma_a16", kind == "luma_a16")) in hashes()[case]
+    # against the oracle: exp() differs in the last bits between the SFU path and libm, the 16-bit truncating pack may flip by a code
+    params = O.normal2d_with_diagonal(0.2, 0.2) if case == "distribution_normal2d" else O.normal2d_with_direction(0.04998, 0.0501)
+    assert np.allclose(dist.params, params, rtol=1e-6, atol=0)
+    exp = O.distribution_normal2d(oracle_desc(desc), params)
+    dt = np.uint16 if kind == "luma_a16" else np.uint8
+    g = np.frombuffer(img.as_bytes().tobytes(), dtype=dt).astype(int); e = np.frombuffer(np.ascontiguousarray(exp.data).tobytes(), dtype=dt).astype(int)
+    # the steep 1-d gaussian amplifies last-bit differences of the parameters (hypot / fma on the host) and of exp() by the
+    # size of the exponent: a relative bound, plus the truncating pack's +-1
+    assert (np.abs(g - e) <= 2 + 5e-4 * e).all()
+    assert np.mean(np.abs(g - e) <= 1) > 0.9
+
+
+def test_run_fractal_noise(pool):  # tests/blend.rs:314-338; integer hash + fixed operation order: bit exact
+    from zosimos_b200.command import FractalNoise
+    desc = Descriptor.with_srgb_image("rgba8", 400, 400)
+    noise = FractalNoise.with_octaves(4)
+    c = CommandBuffer()
+    output, _ = c.output(c.distribution_fractal_noise(desc, noise))
+    img, _ = run_once_with_output(c, pool, [], output)
+    assert O.blockhash256(rgba(img)) in hashes()["distribution_fractal2d"]
+    exp = O.distribution_fractal_noise(O.srgb_rgba8(400, 400), O.fractal_noise_with_octaves(4))
+    assert np.array_equal(rgba(img), exp.data.reshape(400, 400, 4))
+    noise.set_damping(0.5)
+    c = CommandBuffer()
+    output, _ = c.output(c.distribution_fractal_noise(desc, noise))
+    img2, _ = run_once_with_output(c, pool, [], output)
+    exp2 = O.distribution_fractal_noise(O.srgb_rgba8(400, 400), O.fractal_noise_with_octaves(4, 0.5))
+    assert np.array_equal(rgba(img2), exp2.data.reshape(400, 400, 4))
+    assert not np.array_equal(rgba(img2), rgba(img))

@@ -27,6 +27,7 @@ BLEND_OVERWRITE = -1
  BLEND_DST_OUT, BLEND_SRC_ATOP, BLEND_DST_ATOP, BLEND_XOR) = range(12)
 BLEND_INJECT = 12
 # program ops
+GEN_BILINEAR, GEN_SOLID, GEN_NORMAL2D, GEN_FRACTAL_NOISE = 0, 1, 2, 3
 OP_INPUT, OP_OUTPUT, OP_PIXEL, OP_COMPOSE, OP_COPY, OP_GENERATE, OP_BOX3, OP_PALETTE = range(1, 9)
 FUSE_EXACT, FUSE_WIDE, FUSE_NONE = 0, 1, 2
 BLOCK_PIXEL, BLOCK_YUV420_PLANAR, BLOCK_YUV420_NV12 = 0, 1, 2
@@ -105,6 +106,7 @@ SIGNATURES = {
     "zos_image_download": (C.c_int32, [_P, C.POINTER(ZosImage), C.c_uint32, _P]),
     "zos_pixel_chain": (C.c_int32, [_P, C.POINTER(ZosImage), C.POINTER(ZosImage), C.POINTER(ZosStep), C.c_uint32, C.c_uint32]),
     "zos_compose": (C.c_int32, [_P, C.POINTER(ZosImage), C.POINTER(ZosImage), C.POINTER(ZosImage), C.POINTER(ZosComposeParams), C.c_uint32]),
+    "zos_generate": (C.c_int32, [_P, C.POINTER(ZosImage), C.c_uint32, C.POINTER(C.c_float), C.c_uint32]),
     "zos_generate_bilinear": (C.c_int32, [_P, C.POINTER(ZosImage), C.POINTER(C.c_float), C.c_uint32]),
     "zos_generate_solid": (C.c_int32, [_P, C.POINTER(ZosImage), C.POINTER(C.c_float), C.c_uint32]),
     "zos_box3": (C.c_int32, [_P, C.POINTER(ZosImage), C.POINTER(ZosImage), C.POINTER(C.c_float), C.c_uint32]),

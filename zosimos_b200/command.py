@@ -69,6 +69,12 @@ _HOST_SIGNATURES = {
     "zosh_cb_transmute": (C.c_int32, [_P, C.c_int32, C.POINTER(_ffi.ZosDesc), C.POINTER(C.c_int32)]),
     "zosh_cb_bilinear": (C.c_int32, [_P, C.POINTER(_ffi.ZosDesc), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "zosh_cb_solid_rgba": (C.c_int32, [_P, C.POINTER(_ffi.ZosDesc), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "zosh_cb_distribution_normal2d": (C.c_int32, [_P, C.POINTER(_ffi.ZosDesc), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "zosh_cb_distribution_fractal_noise": (C.c_int32, [_P, C.POINTER(_ffi.ZosDesc), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "zosh_normal2d_with_diagonal": (None, [C.c_float, C.c_float, C.POINTER(C.c_float)]),
+    "zosh_normal2d_with_direction": (None, [C.c_float, C.c_float, C.POINTER(C.c_float)]),
+    "zosh_fractal_noise_with_octaves": (None, [C.c_uint32, C.POINTER(C.c_float)]),
+    "zosh_fractal_noise_set_damping": (None, [C.POINTER(C.c_float), C.c_float]),
     "zosh_cb_derivative": (C.c_int32, [_P, C.c_int32, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32)]),
     "zosh_cb_palette": (C.c_int32, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "zosh_cb_extract": (C.c_int32, [_P, C.c_int32, C.c_uint32, C.POINTER(C.c_int32)]),
@@ -247,6 +253,45 @@ class Bilinear:  # shaders/bilinear.rs:9-32
         return np.asarray(self.flat(), dtype=np.float32).tobytes()
 
 
+class DistributionNormal2d:  # shaders/distribution_normal2d.rs:9-100
+    def __init__(self, params: Sequence[float]):
+        self.params = [float(x) for x in params]  # expectation[2], covariance_inverse[4] row major, pseudo_determinant
+
+    @staticmethod
+    def with_diagonal(var0: float, var1: float) -> "DistributionNormal2d":
+        out = (C.c_float * 7)()
+        host_lib().zosh_normal2d_with_diagonal(var0, var1, out)
+        return DistributionNormal2d(list(out))
+
+    @staticmethod
+    def with_direction(direction: Sequence[float]) -> "DistributionNormal2d":
+        out = (C.c_float * 7)()
+        host_lib().zosh_normal2d_with_direction(float(direction[0]), float(direction[1]), out)
+        return DistributionNormal2d(list(out))
+
+    def into_std430(self) -> bytes:
+        return np.asarray(self.params + [0.0], dtype=np.float32).tobytes()
+
+
+class FractalNoise:  # shaders/fractal_noise.rs:9-49
+    def __init__(self, params: Sequence[float]):
+        self.params = [float(x) for x in params]  # initial_scale[2], amplitude, damping, num_octaves
+
+    @staticmethod
+    def with_octaves(num_octaves: int) -> "FractalNoise":
+        out = (C.c_float * 5)()
+        host_lib().zosh_fractal_noise_with_octaves(int(num_octaves), out)
+        return FractalNoise(list(out))
+
+    def set_damping(self, damping: float):
+        p = (C.c_float * 5)(*self.params)
+        host_lib().zosh_fractal_noise_set_damping(p, float(damping))
+        self.params = list(p)
+
+    def into_std430(self) -> bytes:
+        return np.asarray(self.params[:4], dtype=np.float32).tobytes() + np.asarray([int(self.params[4]), 0], dtype=np.uint32).tobytes()
+
+
 @dataclass(frozen=True)
 class Palette:  # command.rs:566-580
     width: Optional[ColorChannel] = None
@@ -353,6 +398,16 @@ class CommandBuffer:
         out = C.c_int32(); d = describe.to_ffi()
         p = (C.c_float * 24)(*distribution.flat())
         return self._reg(host_lib().zosh_cb_bilinear(self._h, C.byref(d), p, C.byref(out)), out)
+
+    def distribution_normal2d(self, describe: Descriptor, distribution: "DistributionNormal2d") -> Register:
+        out = C.c_int32(); d = describe.to_ffi()
+        p = (C.c_float * 7)(*distribution.params)
+        return self._reg(host_lib().zosh_cb_distribution_normal2d(self._h, C.byref(d), p, C.byref(out)), out)
+
+    def distribution_fractal_noise(self, describe: Descriptor, distribution: "FractalNoise") -> Register:
+        out = C.c_int32(); d = describe.to_ffi()
+        p = (C.c_float * 5)(*distribution.params)
+        return self._reg(host_lib().zosh_cb_distribution_fractal_noise(self._h, C.byref(d), p, C.byref(out)), out)
 
     def solid_rgba(self, describe: Descriptor, color: Sequence[float]) -> Register:
         out = C.c_int32(); d = describe.to_ffi()

@@ -395,6 +395,53 @@ int32_t zosh_cb_solid_rgba(zosh_cb* cb, const zos_desc* desc, const float color[
   return push(cb, op, reg);
 }
 
+// shaders/distribution_normal2d.rs:25-100 and shaders/fractal_noise.rs:21-49: the parameter constructors, in f32 like the reference
+void zosh_normal2d_with_diagonal(float var0, float var1, float out[7]) {
+  const float pi = 3.14159265358979323846f;
+  const float d0 = var0 == 0.0f ? 0.0f : 1.0f / var0, d1 = var1 == 0.0f ? 0.0f : 1.0f / var1;
+  const float f0 = var0 == 0.0f ? 1.0f : 2.0f * pi * var0, f1 = var1 == 0.0f ? 1.0f : 2.0f * pi * var1;
+  out[0] = out[1] = 0.0f;
+  out[2] = d0; out[3] = 0.0f; out[4] = 0.0f; out[5] = d1;
+  out[6] = f0 * f1;
+}
+void zosh_normal2d_with_direction(float x, float y, float out[7]) {
+  auto sym = [](float a, float b) { float h = hypotf(a, b); float up = (1.0f / h) * (a / h); float low = a + b * (b / a); return up / low; };
+  auto asym = [](float a, float b) { float lo = fminf(a, b), hi = fmaxf(a, b); float h = hypotf(lo, hi); float inner = fmaf(lo, lo / hi, hi); return ((lo / h) / inner) / h; };
+  out[0] = out[1] = 0.0f;
+  out[2] = sym(x, x); out[3] = asym(x, y); out[4] = asym(y, x); out[5] = sym(y, y);
+  out[6] = (float)((double)x * (double)x + (double)y * (double)y);
+}
+void zosh_fractal_noise_with_octaves(uint32_t octaves, float out[5]) {
+  out[0] = out[1] = 100.0f;
+  out[2] = (float)(1.0 / (double)octaves);
+  out[3] = 1.0f;
+  out[4] = (float)octaves;
+}
+void zosh_fractal_noise_set_damping(float params[5], float damping) {
+  const float n = params[4];
+  const float total = 1.0f - powf(damping, n);
+  params[2] = fabsf(total) < 1e-7f ? 1.0f : (1.0f - damping) / total;
+  params[3] = damping;
+}
+
+static int32_t push_generator(zosh_cb* cb, const zos_desc* desc, uint32_t kind, const float* p, int n, int32_t* reg, const char* what) {
+  if (!cb || !desc || !p) return err(ZOSH_ERR_OTHER, "null argument");
+  zos_desc d = *desc;
+  if (d.block != ZOS_BLOCK_PIXEL || d.texel_stride != zos_bits_bytes(d.bits) || d.width == 0 || d.height == 0) return err(ZOSH_ERR_BAD_DESCRIPTOR, what);
+  fix_layout(d);
+  zos_op op = new_op(cb, ZOS_OP_GENERATE, -1, -1, d);
+  memcpy(op.gen, p, sizeof(float) * n);
+  op.compose.map = (int32_t)kind;
+  return push(cb, op, reg);
+}
+int32_t zosh_cb_distribution_normal2d(zosh_cb* cb, const zos_desc* desc, const float params[7], int32_t* reg) {
+  return push_generator(cb, desc, ZOS_GEN_NORMAL2D, params, 7, reg, "inconsistent descriptor for distribution_normal2d");
+}
+int32_t zosh_cb_distribution_fractal_noise(zosh_cb* cb, const zos_desc* desc, const float params[5], int32_t* reg) {
+  if (params && !(params[4] >= 0.0f && params[4] <= 64.0f)) return err(ZOSH_ERR_OTHER, "fractal noise: 0..64 octaves");
+  return push_generator(cb, desc, ZOS_GEN_FRACTAL_NOISE, params, 5, reg, "inconsistent descriptor for distribution_fractal_noise");
+}
+
 int32_t zosh_cb_derivative(zosh_cb* cb, int32_t src, uint32_t method, uint32_t height_direction, int32_t* reg) {
   if (!cb || !valid_reg(cb, src)) return err(ZOSH_ERR_OTHER, "bad register");
   float sm[3];

@@ -33,7 +33,17 @@ __device__ __forceinline__ void store_word(const DevImage& im, uint32_t frame, i
   }
 }
 
-struct GenParams { DevImage dst; float p[24]; uint32_t total; uint32_t solid; };
+struct GenParams { DevImage dst; float p[24]; uint32_t total; uint32_t kind; };
+
+// fractal_noise.frag: pcg4d (jcgt.org/published/0009/03/02) of a cell corner -> 4 uniform floats
+__device__ __forceinline__ float4 noise_hash(uint32_t sx, uint32_t sy) {
+  uint32_t x = sx * 1664525u + 1013904223u, y = sy * 1664525u + 1013904223u, z = 1013904223u, w = 1013904223u;
+  x += y * w; y += z * x; z += x * y; w += y * z;
+  x ^= x >> 16; y ^= y >> 16; z ^= z >> 16; w ^= w >> 16;
+  x += y * w; y += z * x; z += x * y; w += y * z;
+  return make_float4((float)x / 4294967296.0f, (float)y / 4294967296.0f, (float)z / 4294967296.0f, (float)w / 4294967296.0f);
+}
+
 __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ GenParams P) {
   __shared__ Tables T;
   load_tables(T);
@@ -43,12 +53,39 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ GenPar
     int j = r / P.dst.w, i = r - j * P.dst.w;
     float u = ((float)i + 0.5f) / (float)P.dst.w, v = ((float)j + 0.5f) / (float)P.dst.h, uv = u * v;
     float c[4];
+    if (P.kind == ZOS_GEN_NORMAL2D) {  // distribution_normal2d.frag:43-55
+      const float px = 2.0f * (u - 0.5f) - P.p[0], py = 2.0f * (v - 0.5f) - P.p[1];
+      const float tx = P.p[2] * px + P.p[3] * py, ty = P.p[4] * px + P.p[5] * py;
+      const float exponent = 0.5f * (px * tx + py * ty);
+      c[0] = c[1] = c[2] = expf(-exponent) / sqrtf(P.p[6]);
+      c[3] = 1.0f;
+    } else if (P.kind == ZOS_GEN_FRACTAL_NOISE) {  // fractal_noise.frag (same operation order as the oracle)
+      const int octaves = (int)P.p[4];
+      const float c2 = 2.0f * 0.87758255f, s2 = 2.0f * 0.47942555f;
+      float x = u, y = v, z = 1.0f, amp = P.p[2];
+      c[0] = c[1] = c[2] = c[3] = 0.0f;
+      for (int o = 0; o < octaves; o++) {
+        const float ptx = x * P.p[0], pty = y * P.p[1];
+        const float flx = floorf(ptx), fly = floorf(pty);
+        const float fx = ptx - flx, fy = pty - fly;
+        const uint32_t sx = (uint32_t)(int32_t)flx, sy = (uint32_t)(int32_t)fly;
+        const float4 a = noise_hash(sx, sy), b = noise_hash(sx + 1u, sy), cc = noise_hash(sx, sy + 1u), d = noise_hash(sx + 1u, sy + 1u);
+        const float ux = fx * fx * (3.0f - 2.0f * fx), uy = fy * fy * (3.0f - 2.0f * fy);
+#define ZOS_NOISE(k, f) c[k] = c[k] + amp * ((a.f * (1.0f - ux) + b.f * ux) + (cc.f - a.f) * uy * (1.0f - ux) + (d.f - b.f) * ux * uy);
+        ZOS_NOISE(0, x) ZOS_NOISE(1, y) ZOS_NOISE(2, z) ZOS_NOISE(3, w)
+#undef ZOS_NOISE
+        const float nx = c2 * x - s2 * y, ny = s2 * x + c2 * y, nz = 2.0f * x + 2.0f * y + 2.0f * z;
+        x = nx; y = ny; z = nz;
+        amp = amp * P.p[3];
+      }
+    } else {
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      float a = P.p[k] * (1.0f - u) + P.p[4 + k] * u;
-      float b = P.p[8 + k] * (1.0f - v) + P.p[12 + k] * v;
-      float d = P.p[16 + k] * (1.0f - uv) + P.p[20 + k] * uv;
-      c[k] = P.solid ? P.p[k] : a + b + d;  // solid_rgb.frag writes the colour as is
+      for (int k = 0; k < 4; k++) {
+        float a = P.p[k] * (1.0f - u) + P.p[4 + k] * u;
+        float b = P.p[8 + k] * (1.0f - v) + P.p[12 + k] * v;
+        float d = P.p[16 + k] * (1.0f - uv) + P.p[20 + k] * uv;
+        c[k] = P.kind == ZOS_GEN_SOLID ? P.p[k] : a + b + d;  // solid_rgb.frag writes the colour as is
+      }
     }
     store_word(P.dst, frame, i, j, pack_texel(P.dst.fmt, make_float4(c[0], c[1], c[2], c[3]), T));
   }
@@ -101,10 +138,10 @@ static zos_status total_px(zos_ctx* ctx, const DevImage& d, uint32_t batch, uint
   return ZOS_OK;
 }
 
-zos_status launch_generate(zos_ctx* ctx, const DevImage& dst, const float* p, uint32_t batch, bool solid) {
+zos_status launch_generate(zos_ctx* ctx, const DevImage& dst, const float* p, uint32_t batch, uint32_t kind) {
   GenParams P;
   P.dst = dst;
-  P.solid = solid ? 1u : 0u;
+  P.kind = kind;
   memcpy(P.p, p, sizeof P.p);
   zos_status st = total_px(ctx, dst, batch, &P.total);
   if (st != ZOS_OK) return st;

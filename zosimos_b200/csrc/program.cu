@@ -294,7 +294,7 @@ zos_status run_kernel(zos_program* p, const Kernel& k) {
   switch (k.kind) {
     case K_PIXEL: return zos_pixel_chain(ctx, img(k.src0), img(k.dst), k.steps, k.nsteps, p->batch);
     case K_COMPOSE: return zos_compose(ctx, img(k.src0), img(k.src1), img(k.dst), &k.cp, p->batch);
-    case K_GENERATE: return k.cp.map ? zos_generate_solid(ctx, img(k.dst), k.gen, p->batch) : zos_generate_bilinear(ctx, img(k.dst), k.gen, p->batch);
+    case K_GENERATE: return zos_generate(ctx, img(k.dst), (uint32_t)k.cp.map, k.gen, p->batch);
     case K_BOX3: return zos_box3(ctx, img(k.src0), img(k.dst), k.gen, p->batch);
     case K_PALETTE: return zos_palette(ctx, img(k.src0), img(k.src1), img(k.dst), k.cp.inv, k.cp.inv + 4, p->batch);
     case K_COPY: {
@@ -369,7 +369,16 @@ zos_status zos_program_set_knob(zos_program* p, uint32_t knob, const void* data,
     found = true;
     const float* f = (const float*)data;
     if (k.kind == K_GENERATE) {  // bilinear: 96 bytes (shaders/bilinear.rs:34-45); solid: 16 bytes (shaders/solid_rgb.rs:22-24)
-      if (len == 96) memcpy(k.gen, f, 96);
+      if (k.cp.map == ZOS_GEN_NORMAL2D) {  // vec2, mat2x2, float (shaders/distribution_normal2d.rs): 28 bytes, padded to 32
+        if (len != 28 && len != 32) return fail(p->ctx, ZOS_ERR_INVALID, "knob %u: expected the 28/32-byte normal2d block", knob);
+        memcpy(k.gen, f, 28);
+      } else if (k.cp.map == ZOS_GEN_FRACTAL_NOISE) {  // vec2, float, float, uint (shaders/fractal_noise.rs:84-91): 20 bytes, padded to 24
+        if (len != 20 && len != 24) return fail(p->ctx, ZOS_ERR_INVALID, "knob %u: expected the 20/24-byte fractal noise block", knob);
+        memcpy(k.gen, f, 16);
+        uint32_t oct; memcpy(&oct, (const uint8_t*)data + 16, 4);
+        if (oct > 64) return fail(p->ctx, ZOS_ERR_INVALID, "knob %u: more than 64 octaves", knob);
+        k.gen[4] = (float)oct;
+      } else if (len == 96) memcpy(k.gen, f, 96);
       else if (len == 16) { memset(k.gen, 0, sizeof k.gen); memcpy(k.gen, f, 16); }
       else return fail(p->ctx, ZOS_ERR_INVALID, "knob %u: expected 96 or 16 bytes", knob);
     } else if ((k.kind == K_PIXEL && k.knob_step >= 0) || k.kind == K_BOX3) {

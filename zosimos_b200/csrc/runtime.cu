@@ -490,25 +490,25 @@ zos_status zos_compose(zos_ctx* ctx, const zos_image* below, const zos_image* ab
   return launch_gather(ctx, below ? &b : nullptr, a, d, *cp, batch);
 }
 
-zos_status zos_generate_bilinear(zos_ctx* ctx, const zos_image* dst, const float* p, uint32_t batch) {
+zos_status zos_generate(zos_ctx* ctx, const zos_image* dst, uint32_t kind, const float* p, uint32_t batch) {
   if (!ctx || !p) return ZOS_ERR_INVALID;
+  if (kind > ZOS_GEN_FRACTAL_NOISE) return fail(ctx, ZOS_ERR_INVALID, "generate: unknown generator %u", kind);
   DevImage d;
   zos_status st;
   if ((st = make_dev_image(ctx, dst, &d, "dst")) != ZOS_OK) return st;
   if (d.block != ZOS_BLOCK_PIXEL) return fail(ctx, ZOS_ERR_UNSUPPORTED, "generate: planar destination");
+  if (kind == ZOS_GEN_FRACTAL_NOISE && !(p[4] >= 0.0f && p[4] <= 64.0f)) return fail(ctx, ZOS_ERR_INVALID, "fractal noise: 0..64 octaves");
   cudaSetDevice(ctx->device);
-  return batch ? launch_generate(ctx, d, p, batch, false) : ZOS_OK;
+  return batch ? launch_generate(ctx, d, p, batch, kind) : ZOS_OK;
+}
+zos_status zos_generate_bilinear(zos_ctx* ctx, const zos_image* dst, const float* p, uint32_t batch) {
+  return zos_generate(ctx, dst, ZOS_GEN_BILINEAR, p, batch);
 }
 zos_status zos_generate_solid(zos_ctx* ctx, const zos_image* dst, const float* color, uint32_t batch) {
-  if (!ctx || !color) return ZOS_ERR_INVALID;
-  DevImage d;
-  zos_status st;
-  if ((st = make_dev_image(ctx, dst, &d, "dst")) != ZOS_OK) return st;
-  if (d.block != ZOS_BLOCK_PIXEL) return fail(ctx, ZOS_ERR_UNSUPPORTED, "generate: planar destination");
+  if (!color) return ZOS_ERR_INVALID;
   float p[24] = {0};
   memcpy(p, color, 16);
-  cudaSetDevice(ctx->device);
-  return batch ? launch_generate(ctx, d, p, batch, true) : ZOS_OK;
+  return zos_generate(ctx, dst, ZOS_GEN_SOLID, p, batch);
 }
 zos_status zos_box3(zos_ctx* ctx, const zos_image* src, const zos_image* dst, const float* m, uint32_t batch) {
   if (!ctx || !m) return ZOS_ERR_INVALID;

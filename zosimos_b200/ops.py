@@ -92,6 +92,14 @@ def generate_bilinear(ctx: Context, dst: DeviceImage, params):
     ctx.check(ctx._lib.zos_generate_bilinear(ctx.handle, C.byref(d), p, dst.batch))
 
 
+def generate(ctx: Context, dst: DeviceImage, kind: int, params):
+    """zos_generate: kind = _ffi.GEN_*; params as documented in include/zosimos_cuda.h."""
+    flat = [float(x) for x in np.asarray(params, dtype=np.float32).reshape(-1)]
+    p = (C.c_float * 24)(*(flat + [0.0] * (24 - len(flat))))
+    d = dst.ffi()
+    ctx.check(ctx._lib.zos_generate(ctx.handle, C.byref(d), int(kind), p, dst.batch))
+
+
 def box3(ctx: Context, src: DeviceImage, dst: DeviceImage, m):
     mm = (C.c_float * 9)(*[float(x) for x in np.asarray(m, dtype=np.float32).reshape(9)])
     a, d = src.ffi(), dst.ffi()
