@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ZOS_ABI_VERSION 1
+#define ZOS_ABI_VERSION 2
 
 typedef int32_t zos_status;
 enum {
@@ -237,6 +237,8 @@ zos_status zos_compose(zos_ctx* ctx, const zos_image* below, const zos_image* ab
  * In a zos_op of kind ZOS_OP_GENERATE the generator kind travels in compose.map. */
 enum { ZOS_GEN_BILINEAR = 0, ZOS_GEN_SOLID = 1, ZOS_GEN_NORMAL2D = 2, ZOS_GEN_FRACTAL_NOISE = 3 };
 zos_status zos_generate(zos_ctx* ctx, const zos_image* dst, uint32_t kind, const float* p, uint32_t batch);
+/* WithBuffer (command.rs:1963-2060, tests/buffer.rs:121-149): the 24-float parameter block is read from device memory */
+zos_status zos_generate_from_buffer(zos_ctx* ctx, const zos_image* dst, uint32_t kind, const zos_buf* params, uint64_t offset, uint32_t batch);
 zos_status zos_generate_bilinear(zos_ctx* ctx, const zos_image* dst, const float* p, uint32_t batch);
 zos_status zos_generate_solid(zos_ctx* ctx, const zos_image* dst, const float* color /* 4 floats */, uint32_t batch);
 /* box3.frag:16-52 (derivative, command.rs:1493-1508): m = 3x3 weights, row-major [dy+1][dx+1] */
@@ -255,7 +257,13 @@ enum {
   ZOS_OP_COPY = 5,         /* High::Copy (transmute)                 src[0] -> dst                  */
   ZOS_OP_GENERATE = 6,     /* DrawInto without operands (bilinear / solid)  gen[24]                 */
   ZOS_OP_BOX3 = 7,
-  ZOS_OP_PALETTE = 8       /* src[0]=palette src[1]=indices, compose.inv[0..7] = xc,yc              */
+  ZOS_OP_PALETTE = 8,      /* src[0]=palette src[1]=indices, compose.inv[0..7] = xc,yc              */
+  /* byte buffers in device memory (command.rs:1777-1803 buffer_init / buffer_zero, :937-968 from_buffer,
+   * WithBuffer :1963-2060; tests/buffer.rs).  A buffer register has no texel: desc is ignored. */
+  ZOS_OP_BUFFER_INIT = 9,  /* dst = buffer register of data_len bytes, filled from `data` (NULL = zeroed)   */
+  ZOS_OP_FROM_BUFFER = 10  /* src[0] = buffer register holding the image in the ALIGNED device layout
+                              (row_stride = zos_aligned_row_stride) -> dst image register (High::Copy)       */
+  /* ZOS_OP_GENERATE with src[0] = a buffer register: the parameter block is read from that buffer at run time */
 };
 typedef struct zos_op {
   uint32_t kind;
@@ -268,6 +276,8 @@ typedef struct zos_op {
   float gen[24];
   uint32_t knob; /* 0 = none, else 1-based knob id whose bytes overwrite this op's parameter block */
   int32_t reg;   /* this op's own register number (Register(idx), command.rs:31); equals dst except for Output ops */
+  const void* data;  /* ZOS_OP_BUFFER_INIT: initial bytes (copied by zos_program_create), or NULL */
+  uint64_t data_len; /* ZOS_OP_BUFFER_INIT: size of the buffer in bytes */
 } zos_op;
 enum { ZOS_FUSE_EXACT = 0 /* every declared register is quantised like the reference, in registers */,
        ZOS_FUSE_WIDE = 1 /* fused intermediates stay f32 */,

@@ -77,6 +77,12 @@ int32_t zosh_cb_palette(zosh_cb* cb, int32_t palette, int32_t indices, const flo
 /* channel: 0 R, 1 G, 2 B, 3 Alpha (ColorChannel); extract = full copy whose destination texel keeps one channel */
 int32_t zosh_cb_extract(zosh_cb* cb, int32_t src, uint32_t channel, int32_t* reg);                       /* command.rs:1221 */
 int32_t zosh_cb_inject(zosh_cb* cb, int32_t below, uint32_t channel, int32_t above, int32_t* reg);      /* command.rs:1360 */
+/* byte buffers in device memory and what consumes them (tests/buffer.rs) */
+int32_t zosh_cb_buffer_init(zosh_cb* cb, const void* data, uint64_t len, int32_t* reg);                 /* command.rs:1777 (knob: :1938) */
+int32_t zosh_cb_buffer_zero(zosh_cb* cb, uint64_t len, int32_t* reg);                                   /* command.rs:1793 */
+int32_t zosh_cb_buffer_size(const zosh_cb* cb, int32_t reg, uint64_t* out);                             /* RegisterDescription::Buffer */
+int32_t zosh_cb_from_buffer(zosh_cb* cb, int32_t buffer, const zos_desc* desc, int32_t* reg);           /* command.rs:937-968 */
+int32_t zosh_cb_with_buffer_bilinear(zosh_cb* cb, int32_t buffer, const zos_desc* desc, int32_t* reg);  /* command.rs:1963-2060 + bilinear */
 int32_t zosh_cb_with_knob(zosh_cb* cb);  /* the NEXT operation gets a knob; returns its 1-based id (command.rs:1865-1874) */
 
 /* Linker::compile (command.rs:2069): liveness + emission of the High-like op list */

@@ -596,6 +596,10 @@ def blockhash256(rgba: np.ndarray) -> str:
     a = np.asarray(rgba).astype(np.int64)
     h, w, _ = a.shape
     bits = 16
+    if w < bits and bits % w == 0 and h < bits and bits % h == 0:
+        # fewer pixels than blocks: a block is a fraction of ONE pixel (blockhash's weighted method), i.e. pixel replication
+        a = np.repeat(np.repeat(a, bits // h, axis=0), bits // w, axis=1)
+        h, w, _ = a.shape
     assert w % bits == 0 and h % bits == 0
     v = np.where(a[..., 3] == 0, 765, a[..., 0] + a[..., 1] + a[..., 2])
     bw, bh = w // bits, h // bits

@@ -415,3 +415,53 @@ def test_run_fractal_noise(pool):  # tests/blend.rs:314-338; integer hash + fixe
     exp2 = O.distribution_fractal_noise(O.srgb_rgba8(400, 400), O.fractal_noise_with_octaves(4, 0.5))
     assert np.array_equal(rgba(img2), exp2.data.reshape(400, 400, 4))
     assert not np.array_equal(rgba(img2), rgba(img))
+
+
+def _luma8_image(width=8, height=8):
+    return Descriptor.with_srgb_image("luma8", width, height)
+
+
+def test_run_from_buffer(pool):  # tests/buffer.rs:39-65: an 8x8 Luma8 image laid out with 256-byte rows in a byte buffer
+    c = CommandBuffer()
+    a = bytearray(b"\xff" * (8 * 256))
+    a[256:264] = b"\x00" * 8
+    buffer = c.buffer_init(bytes(a))
+    result = c.from_buffer(buffer, _luma8_image())
+    output, _ = c.output(result)
+    img, _ = run_once_with_output(c, pool, [], output)
+    got = img.as_bytes().reshape(8, 8)
+    exp = np.full((8, 8), 255, np.uint8); exp[1, :] = 0
+    assert np.array_equal(got, exp)
+    lum = got.astype(np.uint8)
+    assert O.blockhash256(np.stack([lum, lum, lum, np.full_like(lum, 255)], -1)) in hashes()["from_buffer"]
+
+
+def test_run_from_buffer_knob(pool):  # tests/buffer.rs:67-119: the buffer's content is the knob
+    c = CommandBuffer()
+    a = bytearray(b"\xff" * (8 * 256))
+    buffer = c.with_knob().buffer_init(bytes(a))
+    result = c.from_buffer(buffer, _luma8_image())
+    output, _ = c.output(result)
+    executable = Linker.from_included().compile(c).lower_to(Capabilities.from_device(next(pool.iter_devices())))
+    knob = executable.query_knob(RegisterKnob(0, buffer))
+    assert knob is not None
+    a[256:264] = b"\x00" * 8
+    img, _ = run_executable_with_output(executable, pool, [], output, [(knob, bytes(a))])
+    lum = img.as_bytes().reshape(8, 8)
+    assert lum[1].max() == 0 and lum[0].min() == 255
+    assert O.blockhash256(np.stack([lum, lum, lum, np.full_like(lum, 255)], -1)) in hashes()["from_buffer-with-knob"]
+    img2, _ = run_executable_with_output(executable, pool, [], output)  # without the knob: the initial content
+    assert img2.as_bytes().min() == 255
+
+
+def test_run_bilinear_from_buffer(pool):  # tests/buffer.rs:121-149: the generator's parameter block is read from device memory
+    c = CommandBuffer()
+    desc = Descriptor.with_srgb_image("rgba8", 256, 256)
+    params = np.asarray([[0, 0, 0, 1], [0, 0, 0.7, 1], [0, 0, 0.3, 1], [0, 1, 0.3, 1], [0, 0, 0, 1], [0, 0, 0, 1]], np.float32)
+    buffer = c.buffer_init(params.tobytes())
+    result = c.with_buffer(buffer).bilinear(desc, Bilinear([0] * 4, [0] * 4, [0] * 4, [0] * 4))
+    output, _ = c.output(result)
+    img, _ = run_once_with_output(c, pool, [], output)
+    assert O.blockhash256(rgba(img)) in hashes()["bilinear_from_buffer"]
+    exp = O.bilinear(O.srgb_rgba8(256, 256), params)
+    assert np.array_equal(rgba(img), exp.data.reshape(256, 256, 4))

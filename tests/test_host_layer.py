@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), n
     # and the ctypes table covers the device header completely
     assert set(declared("zosimos_cuda.h")) == set(_ffi.SIGNATURES)
-    assert lib.zos_abi_version() == 1
+    assert lib.zos_abi_version() == 2
 
 
 def test_no_cpu_fallback():
@@ -204,3 +204,27 @@ def test_srgb_encoder_bucket_tables_exact():
     assert k2.max() < n2.value
     c2 = (b2[k2] + idx) >> 24
     assert np.array_equal(c2, ref)
+
+
+def test_buffer_builder_errors():
+    """command.rs:937-968: from_buffer type and size checks; buffers are not image registers."""
+    from zosimos_b200.buffer import Descriptor
+    from zosimos_b200.command import CommandBuffer, CommandError
+    c = CommandBuffer()
+    img = c.input(Descriptor.with_srgb_image("rgba8", 16, 16))
+    small = c.buffer_init(b"\x00" * 100)
+    big = c.buffer_zero(8 * 256)
+    assert c.buffer_size(big) == 8 * 256
+    luma = Descriptor.with_srgb_image("luma8", 8, 8)
+    with pytest.raises(CommandError):   # TYPE_ERR: an image register is not a buffer
+        c.from_buffer(img, luma)
+    with pytest.raises(CommandError):   # INVALID_CALL: 8 rows of 256 bytes do not fit 100 bytes
+        c.from_buffer(small, luma)
+    ok = c.from_buffer(big, luma)
+    assert c.describe_reg(ok).layout.width == 8
+    with pytest.raises(CommandError):   # a buffer register is not an image
+        c.output(big)
+    with pytest.raises(CommandError):
+        c.with_buffer(img)
+    with pytest.raises(CommandError):   # the bilinear block needs 96 bytes
+        c.with_buffer(c.buffer_zero(32)).bilinear(Descriptor.with_srgb_image("rgba8", 4, 4))

@@ -28,7 +28,7 @@ BLEND_OVERWRITE = -1
 BLEND_INJECT = 12
 # program ops
 GEN_BILINEAR, GEN_SOLID, GEN_NORMAL2D, GEN_FRACTAL_NOISE = 0, 1, 2, 3
-OP_INPUT, OP_OUTPUT, OP_PIXEL, OP_COMPOSE, OP_COPY, OP_GENERATE, OP_BOX3, OP_PALETTE = range(1, 9)
+OP_INPUT, OP_OUTPUT, OP_PIXEL, OP_COMPOSE, OP_COPY, OP_GENERATE, OP_BOX3, OP_PALETTE, OP_BUFFER_INIT, OP_FROM_BUFFER = range(1, 11)
 FUSE_EXACT, FUSE_WIDE, FUSE_NONE = 0, 1, 2
 BLOCK_PIXEL, BLOCK_YUV420_PLANAR, BLOCK_YUV420_NV12 = 0, 1, 2
 
@@ -66,7 +66,7 @@ class ZosComposeParams(C.Structure):
 class ZosOp(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("src", C.c_int32 * 2), ("dst", C.c_int32), ("desc", ZosDesc),
                 ("nsteps", C.c_uint32), ("steps", ZosStep * ZOS_MAX_STEPS), ("compose", ZosComposeParams),
-                ("gen", C.c_float * 24), ("knob", C.c_uint32), ("reg", C.c_int32)]
+                ("gen", C.c_float * 24), ("knob", C.c_uint32), ("reg", C.c_int32), ("data", C.c_void_p), ("data_len", C.c_uint64)]
 
 
 class ZosError(RuntimeError):
@@ -107,6 +107,7 @@ SIGNATURES = {
     "zos_pixel_chain": (C.c_int32, [_P, C.POINTER(ZosImage), C.POINTER(ZosImage), C.POINTER(ZosStep), C.c_uint32, C.c_uint32]),
     "zos_compose": (C.c_int32, [_P, C.POINTER(ZosImage), C.POINTER(ZosImage), C.POINTER(ZosImage), C.POINTER(ZosComposeParams), C.c_uint32]),
     "zos_generate": (C.c_int32, [_P, C.POINTER(ZosImage), C.c_uint32, C.POINTER(C.c_float), C.c_uint32]),
+    "zos_generate_from_buffer": (C.c_int32, [_P, C.POINTER(ZosImage), C.c_uint32, _P, C.c_uint64, C.c_uint32]),
     "zos_generate_bilinear": (C.c_int32, [_P, C.POINTER(ZosImage), C.POINTER(C.c_float), C.c_uint32]),
     "zos_generate_solid": (C.c_int32, [_P, C.POINTER(ZosImage), C.POINTER(C.c_float), C.c_uint32]),
     "zos_box3": (C.c_int32, [_P, C.POINTER(ZosImage), C.POINTER(ZosImage), C.POINTER(C.c_float), C.c_uint32]),

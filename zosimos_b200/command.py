@@ -69,6 +69,11 @@ _HOST_SIGNATURES = {
     "zosh_cb_transmute": (C.c_int32, [_P, C.c_int32, C.POINTER(_ffi.ZosDesc), C.POINTER(C.c_int32)]),
     "zosh_cb_bilinear": (C.c_int32, [_P, C.POINTER(_ffi.ZosDesc), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "zosh_cb_solid_rgba": (C.c_int32, [_P, C.POINTER(_ffi.ZosDesc), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "zosh_cb_buffer_init": (C.c_int32, [_P, C.c_void_p, C.c_uint64, C.POINTER(C.c_int32)]),
+    "zosh_cb_buffer_zero": (C.c_int32, [_P, C.c_uint64, C.POINTER(C.c_int32)]),
+    "zosh_cb_buffer_size": (C.c_int32, [_P, C.c_int32, C.POINTER(C.c_uint64)]),
+    "zosh_cb_from_buffer": (C.c_int32, [_P, C.c_int32, C.POINTER(_ffi.ZosDesc), C.POINTER(C.c_int32)]),
+    "zosh_cb_with_buffer_bilinear": (C.c_int32, [_P, C.c_int32, C.POINTER(_ffi.ZosDesc), C.POINTER(C.c_int32)]),
     "zosh_cb_distribution_normal2d": (C.c_int32, [_P, C.POINTER(_ffi.ZosDesc), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "zosh_cb_distribution_fractal_noise": (C.c_int32, [_P, C.POINTER(_ffi.ZosDesc), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "zosh_normal2d_with_diagonal": (None, [C.c_float, C.c_float, C.POINTER(C.c_float)]),
@@ -409,6 +414,29 @@ class CommandBuffer:
         p = (C.c_float * 5)(*distribution.params)
         return self._reg(host_lib().zosh_cb_distribution_fractal_noise(self._h, C.byref(d), p, C.byref(out)), out)
 
+    # -- byte buffers (tests/buffer.rs)
+    def buffer_init(self, init: bytes) -> Register:  # command.rs:1777-1790 (with_knob().buffer_init: :1938)
+        out = C.c_int32(); data = bytes(init)
+        buf = C.create_string_buffer(data, len(data))
+        return self._reg(host_lib().zosh_cb_buffer_init(self._h, C.cast(buf, C.c_void_p), len(data), C.byref(out)), out)
+
+    def buffer_zero(self, length: int) -> Register:  # command.rs:1793-1803
+        out = C.c_int32()
+        return self._reg(host_lib().zosh_cb_buffer_zero(self._h, int(length), C.byref(out)), out)
+
+    def buffer_size(self, reg: Register) -> int:
+        out = C.c_uint64()
+        _check(host_lib().zosh_cb_buffer_size(self._h, reg.index, C.byref(out)))
+        return int(out.value)
+
+    def from_buffer(self, buffer_reg: Register, descriptor: Descriptor) -> Register:  # command.rs:937-968
+        out = C.c_int32(); d = descriptor.to_ffi()
+        return self._reg(host_lib().zosh_cb_from_buffer(self._h, buffer_reg.index, C.byref(d), C.byref(out)), out)
+
+    def with_buffer(self, buffer_reg: Register) -> "WithBuffer":  # command.rs:1876-1890
+        self.buffer_size(buffer_reg)  # TYPE_ERR unless it is a buffer register
+        return WithBuffer(self, buffer_reg)
+
     def solid_rgba(self, describe: Descriptor, color: Sequence[float]) -> Register:
         out = C.c_int32(); d = describe.to_ffi()
         c = (C.c_float * 4)(*[float(x) for x in color])
@@ -440,6 +468,16 @@ class CommandBuffer:
             raise CommandError(CommandErrorKind.Other, "inject: channel")
         out = C.c_int32()
         return self._reg(host_lib().zosh_cb_inject(self._h, below.index, self._CHANNEL[channel], above.index, C.byref(out)), out)
+
+
+class WithBuffer:  # command.rs:1963-2060: the next operation's parameter block is read from a device buffer
+    def __init__(self, cb: "CommandBuffer", buffer_reg: Register):
+        self._cb, self._buf = cb, buffer_reg
+
+    def bilinear(self, describe: Descriptor, distribution: Optional[Bilinear] = None) -> Register:
+        """The distribution argument only types the call in the reference; the values come from the buffer."""
+        out = C.c_int32(); d = describe.to_ffi()
+        return self._cb._reg(host_lib().zosh_cb_with_buffer_bilinear(self._cb._h, self._buf.index, C.byref(d), C.byref(out)), out)
 
 
 class Linker:

@@ -7,6 +7,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -113,13 +114,17 @@ zos_step make_step(uint32_t kind, const double* m, const double* v = nullptr) {
 struct zosh_cb {
   std::vector<zos_op> ops;  // op i defines register i (outputs define a register too, like the reference)
   uint32_t next_knob = 0, pending_knob = 0;
+  std::vector<std::shared_ptr<std::vector<uint8_t>>> blobs;  // initial bytes of buffer registers (zos_op::data points into them)
 };
 struct zosh_program {
   std::vector<zos_op> ops;
+  std::vector<std::shared_ptr<std::vector<uint8_t>>> blobs;
 };
 
 namespace {
-bool valid_reg(const zosh_cb* cb, int32_t r) { return r >= 0 && (size_t)r < cb->ops.size() && cb->ops[r].kind != ZOS_OP_OUTPUT; }
+// an IMAGE register (outputs and byte buffers are not: the reference answers TYPE_ERR / BAD_REGISTER for them)
+bool valid_reg(const zosh_cb* cb, int32_t r) { return r >= 0 && (size_t)r < cb->ops.size() && cb->ops[r].kind != ZOS_OP_OUTPUT && cb->ops[r].kind != ZOS_OP_BUFFER_INIT; }
+bool buffer_reg(const zosh_cb* cb, int32_t r) { return r >= 0 && (size_t)r < cb->ops.size() && cb->ops[r].kind == ZOS_OP_BUFFER_INIT; }
 zos_op new_op(zosh_cb* cb, uint32_t kind, int32_t s0, int32_t s1, const zos_desc& d) {
   zos_op op;
   memset(&op, 0, sizeof op);
@@ -442,6 +447,54 @@ int32_t zosh_cb_distribution_fractal_noise(zosh_cb* cb, const zos_desc* desc, co
   return push_generator(cb, desc, ZOS_GEN_FRACTAL_NOISE, params, 5, reg, "inconsistent descriptor for distribution_fractal_noise");
 }
 
+// ---- byte buffers (command.rs:1777-1803, 937-968, 1963-2060; tests/buffer.rs)
+static int32_t push_buffer(zosh_cb* cb, const void* data, uint64_t len, int32_t* reg) {
+  if (!cb) return err(ZOSH_ERR_OTHER, "null argument");
+  if (len == 0 || len > (1ull << 32)) return err(ZOSH_ERR_OTHER, "buffer size out of range");
+  zos_desc none;
+  memset(&none, 0, sizeof none);
+  zos_op op = new_op(cb, ZOS_OP_BUFFER_INIT, -1, -1, none);
+  op.data_len = len;
+  if (data) {
+    auto blob = std::make_shared<std::vector<uint8_t>>((const uint8_t*)data, (const uint8_t*)data + len);
+    cb->blobs.push_back(blob);
+    op.data = blob->data();
+  }
+  return push(cb, op, reg);
+}
+int32_t zosh_cb_buffer_init(zosh_cb* cb, const void* data, uint64_t len, int32_t* reg) {
+  if (!data) return err(ZOSH_ERR_OTHER, "null data");
+  return push_buffer(cb, data, len, reg);
+}
+int32_t zosh_cb_buffer_zero(zosh_cb* cb, uint64_t len, int32_t* reg) { return push_buffer(cb, nullptr, len, reg); }
+int32_t zosh_cb_buffer_size(const zosh_cb* cb, int32_t reg, uint64_t* out) {
+  if (!cb || !out || !buffer_reg(cb, reg)) return err(ZOSH_ERR_TYPE, "not a buffer register");
+  *out = cb->ops[reg].data_len;
+  return ZOSH_OK;
+}
+int32_t zosh_cb_from_buffer(zosh_cb* cb, int32_t buffer, const zos_desc* desc, int32_t* reg) {
+  if (!cb || !desc) return err(ZOSH_ERR_OTHER, "null argument");
+  if (!buffer_reg(cb, buffer)) return err(ZOSH_ERR_TYPE, "from_buffer: not a buffer register (CommandError::TYPE_ERR)");
+  zos_desc d = *desc;
+  if (d.block != ZOS_BLOCK_PIXEL || d.texel_stride != zos_bits_bytes(d.bits) || d.width == 0 || d.height == 0)
+    return err(ZOSH_ERR_OTHER, "from_buffer: descriptor has no aligned layout (CommandError::INVALID_CALL)");
+  fix_layout(d);  // Descriptor::to_aligned
+  if (cb->ops[buffer].data_len < d.row_stride * d.height) return err(ZOSH_ERR_OTHER, "from_buffer: buffer smaller than the aligned image (CommandError::INVALID_CALL)");
+  return push(cb, new_op(cb, ZOS_OP_FROM_BUFFER, buffer, -1, d), reg);
+}
+int32_t zosh_cb_with_buffer_bilinear(zosh_cb* cb, int32_t buffer, const zos_desc* desc, int32_t* reg) {
+  if (!cb || !desc) return err(ZOSH_ERR_OTHER, "null argument");
+  if (!buffer_reg(cb, buffer)) return err(ZOSH_ERR_TYPE, "with_buffer: not a buffer register");
+  if (cb->ops[buffer].data_len < 96) return err(ZOSH_ERR_OTHER, "with_buffer: the bilinear parameter block needs 96 bytes");
+  zos_desc d = *desc;
+  if (d.block != ZOS_BLOCK_PIXEL || d.texel_stride != zos_bits_bytes(d.bits) || d.width == 0 || d.height == 0)
+    return err(ZOSH_ERR_BAD_DESCRIPTOR, "inconsistent descriptor for bilinear");
+  fix_layout(d);
+  zos_op op = new_op(cb, ZOS_OP_GENERATE, buffer, -1, d);
+  op.compose.map = ZOS_GEN_BILINEAR;
+  return push(cb, op, reg);
+}
+
 int32_t zosh_cb_derivative(zosh_cb* cb, int32_t src, uint32_t method, uint32_t height_direction, int32_t* reg) {
   if (!cb || !valid_reg(cb, src)) return err(ZOSH_ERR_OTHER, "bad register");
   float sm[3];
@@ -545,6 +598,7 @@ int32_t zosh_compile(const zosh_cb* cb, zosh_program** out) {
       if (op.src[s] >= 0) live[op.src[s]] = 1;
   }
   zosh_program* p = new zosh_program();
+  p->blobs = cb->blobs;  // zos_op::data of buffer registers points into these
   for (size_t i = 0; i < cb->ops.size(); i++)
     if (live[i]) p->ops.push_back(cb->ops[i]);
   *out = p;

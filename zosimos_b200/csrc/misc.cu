@@ -33,7 +33,7 @@ __device__ __forceinline__ void store_word(const DevImage& im, uint32_t frame, i
   }
 }
 
-struct GenParams { DevImage dst; float p[24]; uint32_t total; uint32_t kind; };
+struct GenParams { DevImage dst; float p[24]; uint32_t total; uint32_t kind; const float* dev; /* parameter block in device memory, or NULL */ };
 
 // fractal_noise.frag: pcg4d (jcgt.org/published/0009/03/02) of a cell corner -> 4 uniform floats
 __device__ __forceinline__ float4 noise_hash(uint32_t sx, uint32_t sy) {
@@ -47,6 +47,9 @@ __device__ __forceinline__ float4 noise_hash(uint32_t sx, uint32_t sy) {
 __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ GenParams P) {
   __shared__ Tables T;
   load_tables(T);
+  __shared__ float pbuf[24];
+  if (threadIdx.x < 24) pbuf[threadIdx.x] = P.dev ? P.dev[threadIdx.x] : P.p[threadIdx.x];
+  __syncthreads();
   const uint32_t wh = (uint32_t)P.dst.w * P.dst.h;
   for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < P.total; idx += gridDim.x * blockDim.x) {
     uint32_t frame = idx / wh, r = idx - frame * wh;
@@ -54,18 +57,18 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ GenPar
     float u = ((float)i + 0.5f) / (float)P.dst.w, v = ((float)j + 0.5f) / (float)P.dst.h, uv = u * v;
     float c[4];
     if (P.kind == ZOS_GEN_NORMAL2D) {  // distribution_normal2d.frag:43-55
-      const float px = 2.0f * (u - 0.5f) - P.p[0], py = 2.0f * (v - 0.5f) - P.p[1];
-      const float tx = P.p[2] * px + P.p[3] * py, ty = P.p[4] * px + P.p[5] * py;
+      const float px = 2.0f * (u - 0.5f) - pbuf[0], py = 2.0f * (v - 0.5f) - pbuf[1];
+      const float tx = pbuf[2] * px + pbuf[3] * py, ty = pbuf[4] * px + pbuf[5] * py;
       const float exponent = 0.5f * (px * tx + py * ty);
-      c[0] = c[1] = c[2] = expf(-exponent) / sqrtf(P.p[6]);
+      c[0] = c[1] = c[2] = expf(-exponent) / sqrtf(pbuf[6]);
       c[3] = 1.0f;
     } else if (P.kind == ZOS_GEN_FRACTAL_NOISE) {  // fractal_noise.frag (same operation order as the oracle)
-      const int octaves = (int)P.p[4];
+      const int octaves = (int)pbuf[4];
       const float c2 = 2.0f * 0.87758255f, s2 = 2.0f * 0.47942555f;
-      float x = u, y = v, z = 1.0f, amp = P.p[2];
+      float x = u, y = v, z = 1.0f, amp = pbuf[2];
       c[0] = c[1] = c[2] = c[3] = 0.0f;
       for (int o = 0; o < octaves; o++) {
-        const float ptx = x * P.p[0], pty = y * P.p[1];
+        const float ptx = x * pbuf[0], pty = y * pbuf[1];
         const float flx = floorf(ptx), fly = floorf(pty);
         const float fx = ptx - flx, fy = pty - fly;
         const uint32_t sx = (uint32_t)(int32_t)flx, sy = (uint32_t)(int32_t)fly;
@@ -76,15 +79,15 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ GenPar
 #undef ZOS_NOISE
         const float nx = c2 * x - s2 * y, ny = s2 * x + c2 * y, nz = 2.0f * x + 2.0f * y + 2.0f * z;
         x = nx; y = ny; z = nz;
-        amp = amp * P.p[3];
+        amp = amp * pbuf[3];
       }
     } else {
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        float a = P.p[k] * (1.0f - u) + P.p[4 + k] * u;
-        float b = P.p[8 + k] * (1.0f - v) + P.p[12 + k] * v;
-        float d = P.p[16 + k] * (1.0f - uv) + P.p[20 + k] * uv;
-        c[k] = P.kind == ZOS_GEN_SOLID ? P.p[k] : a + b + d;  // solid_rgb.frag writes the colour as is
+        float a = pbuf[k] * (1.0f - u) + pbuf[4 + k] * u;
+        float b = pbuf[8 + k] * (1.0f - v) + pbuf[12 + k] * v;
+        float d = pbuf[16 + k] * (1.0f - uv) + pbuf[20 + k] * uv;
+        c[k] = P.kind == ZOS_GEN_SOLID ? pbuf[k] : a + b + d;  // solid_rgb.frag writes the colour as is
       }
     }
     store_word(P.dst, frame, i, j, pack_texel(P.dst.fmt, make_float4(c[0], c[1], c[2], c[3]), T));
@@ -138,11 +141,12 @@ static zos_status total_px(zos_ctx* ctx, const DevImage& d, uint32_t batch, uint
   return ZOS_OK;
 }
 
-zos_status launch_generate(zos_ctx* ctx, const DevImage& dst, const float* p, uint32_t batch, uint32_t kind) {
+zos_status launch_generate(zos_ctx* ctx, const DevImage& dst, const float* p, uint32_t batch, uint32_t kind, const float* dev) {
   GenParams P;
   P.dst = dst;
   P.kind = kind;
-  memcpy(P.p, p, sizeof P.p);
+  P.dev = dev;
+  if (p) memcpy(P.p, p, sizeof P.p); else memset(P.p, 0, sizeof P.p);
   zos_status st = total_px(ctx, dst, batch, &P.total);
   if (st != ZOS_OK) return st;
   k_generate<<<grid_for(ctx, P.total, 256, 8), 256, 0, ctx->stream>>>(P);

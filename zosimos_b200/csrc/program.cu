@@ -23,7 +23,7 @@ using namespace zos;
 
 namespace {
 
-enum KKind { K_PIXEL, K_COMPOSE, K_COPY, K_GENERATE, K_BOX3, K_PALETTE };
+enum KKind { K_PIXEL, K_COMPOSE, K_COPY, K_GENERATE, K_BOX3, K_PALETTE, K_BUFFER_INIT, K_FROM_BUFFER };
 
 struct Kernel {
   KKind kind;
@@ -34,6 +34,7 @@ struct Kernel {
   float gen[24];                       // K_GENERATE; K_BOX3 uses gen[0..8]
   uint32_t knob = 0;                   // knob id patched into this kernel's parameter block
   int knob_step = -1;                  // which step carries the knob-able matrix (K_PIXEL)
+  std::vector<uint8_t> bytes;          // K_BUFFER_INIT: the initial content (patched by a knob)
 };
 
 struct Reg {
@@ -45,6 +46,8 @@ struct Reg {
   zos_buf* owned = nullptr;
   bool has_pending = false;
   Kernel pending;
+  bool is_buffer = false;  // a byte buffer register (ZOS_OP_BUFFER_INIT): `owned` is its storage, buf_bytes its size
+  uint64_t buf_bytes = 0;
 };
 
 }  // namespace
@@ -143,7 +146,8 @@ zos_status plan(zos_program* p, const zos_op* ops, uint32_t nops) {
       D.defined = true;
       D.desc = op.desc;
       zos_texfmt f;
-      if ((st = zos_desc_texfmt(&D.desc, &f)) != ZOS_OK) return fail(ctx, st, "op %u: register %d has no texture representation", i, op.dst);
+      if (op.kind != ZOS_OP_BUFFER_INIT && (st = zos_desc_texfmt(&D.desc, &f)) != ZOS_OK)
+        return fail(ctx, st, "op %u: register %d has no texture representation", i, op.dst);
     }
     switch (op.kind) {
       case ZOS_OP_INPUT:
@@ -245,10 +249,41 @@ zos_status plan(zos_program* p, const zos_op* ops, uint32_t nops) {
         p->schedule.push_back(k);
         break;
       }
+      case ZOS_OP_BUFFER_INIT: {
+        Reg& D = p->regs[op.dst];
+        if (op.data_len == 0 || op.data_len > (1ull << 32)) return fail(ctx, ZOS_ERR_INVALID, "op %u: buffer of %llu bytes", i, (unsigned long long)op.data_len);
+        D.is_buffer = true; D.buf_bytes = op.data_len; D.materialised = true;
+        if ((st = zos_buf_alloc(ctx, (op.data_len + 255) & ~255ull, &D.owned)) != ZOS_OK) return st;
+        Kernel k;
+        k.kind = K_BUFFER_INIT; k.dst = op.dst; k.knob = op.knob;
+        k.bytes.assign((size_t)op.data_len, 0);
+        if (op.data) memcpy(k.bytes.data(), op.data, (size_t)op.data_len);
+        p->schedule.push_back(k);
+        break;
+      }
+      case ZOS_OP_FROM_BUFFER: {
+        if ((st = check_reg(p, op.src[0], "from_buffer")) != ZOS_OK) return st;
+        Reg& S = p->regs[op.src[0]];
+        Reg& D = p->regs[op.dst];
+        if (!S.is_buffer) return fail(ctx, ZOS_ERR_TYPE, "op %u: from_buffer needs a buffer register (CommandError::TYPE_ERR)", i);
+        if (D.desc.block != ZOS_BLOCK_PIXEL) return fail(ctx, ZOS_ERR_UNSUPPORTED, "op %u: from_buffer of a planar image", i);
+        if ((st = alloc_reg(p, op.dst)) != ZOS_OK) return st;
+        if (S.buf_bytes < D.desc.row_stride * D.desc.height) return fail(ctx, ZOS_ERR_INVALID, "op %u: buffer smaller than the aligned image (command.rs:955-961)", i);
+        if (p->batch != 1) return fail(ctx, ZOS_ERR_UNSUPPORTED, "op %u: from_buffer in a batched program", i);
+        Kernel k;
+        k.kind = K_FROM_BUFFER; k.src0 = op.src[0]; k.dst = op.dst;
+        p->schedule.push_back(k);
+        break;
+      }
       case ZOS_OP_GENERATE: {
+        if (op.src[0] >= 0) {  // WithBuffer: the parameter block lives in a device buffer
+          if ((st = check_reg(p, op.src[0], "generate (with_buffer)")) != ZOS_OK) return st;
+          if (!p->regs[op.src[0]].is_buffer || p->regs[op.src[0]].buf_bytes < 96)
+            return fail(ctx, ZOS_ERR_TYPE, "op %u: with_buffer needs a buffer register of at least 96 bytes", i);
+        }
         if ((st = alloc_reg(p, op.dst)) != ZOS_OK) return st;
         Kernel k;
-        k.kind = K_GENERATE; k.dst = op.dst; k.knob = op.knob;
+        k.kind = K_GENERATE; k.dst = op.dst; k.knob = op.knob; k.src0 = op.src[0];
         memset(&k.cp, 0, sizeof k.cp);
         k.cp.map = op.compose.map;  // 1 = solid colour
         memcpy(k.gen, op.gen, sizeof k.gen);
@@ -290,11 +325,19 @@ zos_status run_kernel(zos_program* p, const Kernel& k) {
   zos_ctx* ctx = p->ctx;
   auto img = [&](int r) -> const zos_image* { return r >= 0 ? &p->regs[r].img : nullptr; };
   for (int r : {k.src0, k.src1, k.dst})
-    if (r >= 0 && !p->regs[r].img.data) return fail(ctx, ZOS_ERR_STATE, "register %d is not bound (StartError::MissingKey)", r);
+    if (r >= 0 && !p->regs[r].is_buffer && !p->regs[r].img.data) return fail(ctx, ZOS_ERR_STATE, "register %d is not bound (StartError::MissingKey)", r);
   switch (k.kind) {
     case K_PIXEL: return zos_pixel_chain(ctx, img(k.src0), img(k.dst), k.steps, k.nsteps, p->batch);
     case K_COMPOSE: return zos_compose(ctx, img(k.src0), img(k.src1), img(k.dst), &k.cp, p->batch);
-    case K_GENERATE: return zos_generate(ctx, img(k.dst), (uint32_t)k.cp.map, k.gen, p->batch);
+    case K_GENERATE:
+      if (k.src0 >= 0) return zos_generate_from_buffer(ctx, img(k.dst), (uint32_t)k.cp.map, p->regs[k.src0].owned, 0, p->batch);
+      return zos_generate(ctx, img(k.dst), (uint32_t)k.cp.map, k.gen, p->batch);
+    case K_BUFFER_INIT:  // (the host bytes belong to the program: they outlive the asynchronous copy)
+      return check_cuda(ctx, cudaMemcpyAsync(p->regs[k.dst].owned->ptr, k.bytes.data(), k.bytes.size(), cudaMemcpyHostToDevice, ctx->stream), "buffer_init");
+    case K_FROM_BUFFER: {
+      const zos_image* d = img(k.dst);
+      return check_cuda(ctx, cudaMemcpyAsync(d->data, p->regs[k.src0].owned->ptr, d->desc.row_stride * d->desc.height, cudaMemcpyDeviceToDevice, ctx->stream), "from_buffer");
+    }
     case K_BOX3: return zos_box3(ctx, img(k.src0), img(k.dst), k.gen, p->batch);
     case K_PALETTE: return zos_palette(ctx, img(k.src0), img(k.src1), img(k.dst), k.cp.inv, k.cp.inv + 4, p->batch);
     case K_COPY: {
@@ -368,6 +411,11 @@ zos_status zos_program_set_knob(zos_program* p, uint32_t knob, const void* data,
     if (k.knob != knob) continue;
     found = true;
     const float* f = (const float*)data;
+    if (k.kind == K_BUFFER_INIT) {  // the whole content is the parameter block (tests/buffer.rs:67-118)
+      if (len != k.bytes.size()) return fail(p->ctx, ZOS_ERR_INVALID, "knob %u: buffer holds %zu bytes", knob, k.bytes.size());
+      memcpy(k.bytes.data(), data, (size_t)len);
+      continue;
+    }
     if (k.kind == K_GENERATE) {  // bilinear: 96 bytes (shaders/bilinear.rs:34-45); solid: 16 bytes (shaders/solid_rgb.rs:22-24)
       if (k.cp.map == ZOS_GEN_NORMAL2D) {  // vec2, mat2x2, float (shaders/distribution_normal2d.rs): 28 bytes, padded to 32
         if (len != 28 && len != 32) return fail(p->ctx, ZOS_ERR_INVALID, "knob %u: expected the 28/32-byte normal2d block", knob);

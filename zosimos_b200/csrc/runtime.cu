@@ -501,6 +501,17 @@ zos_status zos_generate(zos_ctx* ctx, const zos_image* dst, uint32_t kind, const
   cudaSetDevice(ctx->device);
   return batch ? launch_generate(ctx, d, p, batch, kind) : ZOS_OK;
 }
+zos_status zos_generate_from_buffer(zos_ctx* ctx, const zos_image* dst, uint32_t kind, const zos_buf* params, uint64_t offset, uint32_t batch) {
+  if (!ctx || !params) return ZOS_ERR_INVALID;
+  if (kind > ZOS_GEN_FRACTAL_NOISE) return fail(ctx, ZOS_ERR_INVALID, "generate: unknown generator %u", kind);
+  if ((offset & 3) || offset + 96 > params->size) return fail(ctx, ZOS_ERR_INVALID, "generate: the parameter block (96 bytes, 4-byte aligned) does not fit the buffer");
+  DevImage d;
+  zos_status st;
+  if ((st = make_dev_image(ctx, dst, &d, "dst")) != ZOS_OK) return st;
+  if (d.block != ZOS_BLOCK_PIXEL) return fail(ctx, ZOS_ERR_UNSUPPORTED, "generate: planar destination");
+  cudaSetDevice(ctx->device);
+  return batch ? launch_generate(ctx, d, nullptr, batch, kind, reinterpret_cast<const float*>((const uint8_t*)params->ptr + offset)) : ZOS_OK;
+}
 zos_status zos_generate_bilinear(zos_ctx* ctx, const zos_image* dst, const float* p, uint32_t batch) {
   return zos_generate(ctx, dst, ZOS_GEN_BILINEAR, p, batch);
 }

@@ -80,7 +80,7 @@ zos_status launch_affine_f16(zos_ctx* ctx, const DevImage* below, const DevImage
                              const zos_compose_params& cp, uint32_t batch, bool* handled);
 zos_status launch_frame_pipeline(zos_ctx* ctx, const DevImage* below, const DevImage& above, const DevImage& dst,
                                  const zos_compose_params& cp, uint32_t batch, bool* handled);
-zos_status launch_generate(zos_ctx* ctx, const DevImage& dst, const float* p, uint32_t batch, uint32_t kind);
+zos_status launch_generate(zos_ctx* ctx, const DevImage& dst, const float* p, uint32_t batch, uint32_t kind, const float* dev = nullptr);
 zos_status launch_box3(zos_ctx* ctx, const DevImage& src, const DevImage& dst, const float* m, uint32_t batch);
 zos_status launch_palette(zos_ctx* ctx, const DevImage& pal, const DevImage& idx, const DevImage& dst, const float* xc,
                           const float* yc, uint32_t batch);
