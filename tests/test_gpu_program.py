@@ -174,6 +174,9 @@ def test_run_transmute_bytes_equal(pool, images, fixtures):  # tests/blend.rs:34
     img, _ = run_once_with_output(c, pool, [(inp, bg.key())], output)
     assert fmt.texel.bits == SampleBits.UInt16x2
     assert np.array_equal(img.as_bytes(), fixtures["background"].reshape(-1))
+    a16 = (np.frombuffer(img.as_bytes().tobytes(), np.uint16).reshape(512, 512, 2).astype(np.int64) + 128) // 257
+    view = np.stack([a16[..., 0]] * 3 + [a16[..., 1]], -1).astype(np.uint8)  # DynamicImage::get_pixel of a LumaA16 image
+    assert O.blockhash256(view) in hashes()["transmute"]
 
 
 def test_run_palette(pool, images, fixtures):  # tests/blend.rs:377-424 (goldens differ per device; checked against the oracle)

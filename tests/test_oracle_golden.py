@@ -141,3 +141,10 @@ def test_distribution_fractal_noise(golden_hashes):  # tests/blend.rs:314-338 (p
 def test_bilinear_from_buffer(golden_hashes):  # tests/buffer.rs:121-149: the bilinear parameter block read from a buffer
     params = ([0, 0, 0, 1], [0, 0, 0.7, 1], [0, 0, 0.3, 1], [0, 1, 0.3, 1], [0, 0, 0, 1], [0, 0, 0, 1])
     check(golden_hashes, "bilinear_from_buffer", O.bilinear(O.srgb_rgba8(256, 256), params))
+
+
+def test_transmute_hash(fixtures, golden_hashes):  # tests/blend.rs:340-375: the RGBA8 bytes viewed as LumaA16, hashed by the reference
+    bg = fixtures["background"]
+    h, w, _ = bg.shape
+    img = O.Image(O.Desc(w, h, O.Texel(O.B_UINT16X2, O.P_LUMAA), O.SRGB), np.ascontiguousarray(bg).reshape(h, w * 4))
+    assert O.blockhash256(luma_as_rgba(img, True, True)) in golden_hashes["transmute"]
