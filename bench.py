@@ -353,6 +353,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     import zosimos_b200 as Z
+    from zosimos_b200.shard import bind_to_gpu_numa
+    numa_cpus = bind_to_gpu_numa(local) if world > 1 else None  # staging memory local to each rank's GPU
     ctx = Z.Context(local)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local)
     wl, launch, e2e = make_gpu_workload(args.workload, ctx, args.frames, seed=1 + rank)
@@ -413,7 +415,8 @@ def main():
         e2e_val = wl.out_px * nfr * world / (float(te.item()) * 1e-3) / 1e6
         e2e_out = {"value": round(e2e_val, 1), "unit": "MP/s", "h2d_bytes_per_step": h2d * args.frames, "d2h_bytes_per_step": d2h * args.frames,
                    "note": "per frame: pinned host -> device (2 layers), kernel, device -> pinned host; 3 streams round robin so "
-                           "copies overlap the kernels (PCIe bound)"}
+                           "copies overlap the kernels (PCIe bound)",
+                   "host_affinity": ("%d CPUs of the GPU's NUMA node" % len(numa_cpus)) if numa_cpus else "unbound"}
         for c in lane_ctxs:
             c.close()
     if sampler:

@@ -14,6 +14,36 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 
+def bind_to_gpu_numa(device: int) -> Optional[List[int]]:
+    """One process per GPU: pin this process to the CPUs that share the GPU's PCIe root (its NUMA node)
+    BEFORE allocating pinned host memory, so that staging buffers are local to the GPU.  Without it the
+    end-to-end (host buffer) throughput of 8 ranks collapses onto one socket's memory and interconnect.
+    Returns the CPU list, or None when the topology cannot be read (then nothing is changed)."""
+    import os
+    import subprocess
+    try:
+        bdf = subprocess.run(["nvidia-smi", "-i", str(device), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if bdf.startswith("00000000:"):
+            bdf = "0000:" + bdf[9:]
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bdf) as f:
+            spec = f.read().strip()
+        cpus: List[int] = []
+        for part in spec.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.extend(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.append(int(part))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
+
+
 def frame_shard(n_frames: int, rank: int, world: int) -> range:
     """Contiguous, balanced partition: rank r owns frames [r*n/world, (r+1)*n/world)."""
     if not (0 <= rank < world):
