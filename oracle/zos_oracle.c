@@ -867,6 +867,8 @@ ZO_API void zo_encode_yuv420(const zo_yuv* p, const float* tex, int w, int h, ui
                              uint8_t* vp, size_t cpitch) {
   int cw = (w + 1) / 2, ch = (h + 1) / 2, step = p->nv12 ? 2 : 1;
   float kg = 1.0f - p->kr - p->kb;
+  /* chroma scaling by ONE rounded reciprocal each (like the decode side's host-prepared constants) */
+  const float rcb = 1.0f / (2.0f * (1.0f - p->kb)), rcr = 1.0f / (2.0f * (1.0f - p->kr));
 #pragma omp parallel for schedule(static)
   for (int cj = 0; cj < ch; cj++)
     for (int ci = 0; ci < cw; ci++) {
@@ -878,7 +880,7 @@ ZO_API void zo_encode_yuv420(const zo_yuv* p, const float* tex, int w, int h, ui
           const float* t = tex + ((size_t)y * w + x) * 4;
           float r = oe_scalar(p->transfer, t[0]), g = oe_scalar(p->transfer, t[1]), b = oe_scalar(p->transfer, t[2]);
           float yy = fmaf(p->kb, b, fmaf(kg, g, p->kr * r));
-          float cb = (b - yy) / (2.0f * (1.0f - p->kb)), cr = (r - yy) / (2.0f * (1.0f - p->kr));
+          float cb = (b - yy) * rcb, cr = (r - yy) * rcr;
           float Yq = p->full_range ? yy * 255.0f : fmaf(yy, 219.0f, 16.0f);
           yp[(size_t)y * ypitch + x] = (uint8_t)rintf(fminf(fmaxf(Yq, 0.0f), 255.0f));
           cbs += cb; crs += cr; cnt++;

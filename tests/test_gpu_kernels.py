@@ -464,6 +464,37 @@ def test_yuv420_to_yuv420_chain(ctx):
 
 
 # ---------------------------------------------------------------- specialised kernels == generic kernels
+@pytest.mark.parametrize("nv12", [False, True])
+@pytest.mark.parametrize("size", [(322, 130), (323, 131)])
+def test_yuv_fast_kernel_equals_generic(ctx, nv12, size):
+    """k_yuv_fast (yuv_chain.cu) against the general kernels: planar BT.709-family source, 0..2 matrices, to
+    sRGB8 / unorm8 RGBA / BGRA and to planar YUV; odd sizes exercise the partial 2x2 blocks."""
+    w, h = size
+    cw, ch = (w + 1) // 2, (h + 1) // 2
+    rng = np.random.default_rng(44)
+    y = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    u = rng.integers(0, 256, (ch, cw), dtype=np.uint8); v = rng.integers(0, 256, (ch, cw), dtype=np.uint8)
+    sd = Z.yuv420_descriptor(w, h, Color.Rgb(Z.Primaries.Bt2020, Transfer.Bt709), Z.YuvMatrix.Bt2020, False, nv12, 0)
+    planes = (y, np.stack([u, v], -1).reshape(ch, 2 * cw) if nv12 else u, None if nv12 else v)
+    src = ctx.upload(sd, planes)
+    M = O.mul3(O.inv3(O.to_xyz("bt709", "D65")), O.to_xyz("bt2020", "D65"))
+    lin = Color.Rgb(Z.Primaries.Bt709, Transfer.Linear)
+    dsts = [zdesc(w, h, Texel.new_u8(SampleParts.RgbA), Color.SRGB), zdesc(w, h, Texel.new_u8(SampleParts.BgrA), lin),
+            Z.yuv420_descriptor(w, h, Color.Rgb(Z.Primaries.Bt709, Transfer.Bt709), Z.YuvMatrix.Bt709, False, not nv12, 0)]
+    for dd in dsts:
+        for steps in ([], [ops.matrix(M)], [ops.matrix(M), ops.matrix(O.inv3(M))]):
+            res = []
+            for flags in (0, 1):
+                ctx.set_flags(flags)
+                dst = ctx.image(dd)
+                ops.pixel_chain(ctx, src, dst, steps)
+                out = dst.download()
+                res.append(out if isinstance(out, np.ndarray) else np.concatenate([p.reshape(-1) for p in out if p is not None]))
+                dst.free()
+            ctx.set_flags(0)
+            assert np.array_equal(res[0], res[1]), (nv12, size, dd.texel, len(steps))
+
+
 @pytest.mark.parametrize("space", ["oklab", "srlab2"])
 @pytest.mark.parametrize("parts", ["LchA", "LabA"])
 def test_lab_kernel_equals_generic(ctx, space, parts):

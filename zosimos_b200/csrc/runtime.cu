@@ -455,7 +455,10 @@ zos_status zos_pixel_chain(zos_ctx* ctx, const zos_image* src, const zos_image* 
   cudaSetDevice(ctx->device);
   if (d.block != ZOS_BLOCK_PIXEL) return launch_yuv_chain(ctx, s, d, steps, nsteps, batch);  // planar destination (yuv_chain.cu)
   if (s.block != ZOS_BLOCK_PIXEL) {
-    // planar sources go through the gather kernel with the identity mapping
+    bool handled = false;  // planar -> native 8-bit, same size: the streaming kernel of yuv_chain.cu
+    st = launch_yuv_fast(ctx, s, d, steps, nsteps, batch, &handled);
+    if (handled || st != ZOS_OK) return st;
+    // other planar sources go through the gather kernel with the identity mapping
     zos_compose_params cp;
     memset(&cp, 0, sizeof cp);
     cp.map = ZOS_MAP_RECT; cp.sampling = ZOS_SAMPLE_NEAREST; cp.blend = ZOS_BLEND_OVERWRITE;

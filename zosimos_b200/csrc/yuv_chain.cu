@@ -2,7 +2,7 @@
 // YUV420 -> YUV420 and RGBA -> YUV420 rows of BASELINE config 5.  The reference has no planar texels
 // at all (program.rs:794-938 lowers Block::Pixel only); semantics are ours and
 // the oracle is zo_encode_yuv420 (oracle/zos_oracle.c): OETF of the colour, Y' = Kr R' + Kg G' + Kb B',
-// Cb = (B' - Y') / (2 (1 - Kb)), Cr likewise, range scaling, round to nearest even; one chroma sample
+// Cb = (B' - Y') * (1 / (2 (1 - Kb))) with one rounded reciprocal, Cr likewise, range scaling, round to nearest even; one chroma sample
 // per 2x2 block = the mean of the block's (up to 4) chroma values.
 //
 // One thread owns one 2x2 block: 4 source texels in, 4 Y' bytes and one Cb / Cr pair out; a warp
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256) k_yuv_chain(const __grid_constant__ YuvPa
   const DevImage& D = P.dst;
   const int cstep_s = P.src.block == ZOS_BLOCK_YUV420_NV12 ? 2 : 1, cstep_d = D.block == ZOS_BLOCK_YUV420_NV12 ? 2 : 1;
   const float kg = 1.0f - D.kr - D.kb;
-  const float cbd = 2.0f * (1.0f - D.kb), crd = 2.0f * (1.0f - D.kr);
+  const float rcb = 1.0f / (2.0f * (1.0f - D.kb)), rcr = 1.0f / (2.0f * (1.0f - D.kr));
   const float cscale = D.full_range ? 255.0f : 224.0f;
   const uint32_t tr = D.fmt.transfer;
   const uint32_t stride = gridDim.x * blockDim.x;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) k_yuv_chain(const __grid_constant__ YuvPa
         apply_steps(P.steps, t, T);
         const float r = oe_scalar(tr, t.x), g = oe_scalar(tr, t.y), b = oe_scalar(tr, t.z);
         const float yy = fmaf(D.kb, b, fmaf(kg, g, D.kr * r));
-        const float cb = (b - yy) / cbd, cr = (r - yy) / crd;
+        const float cb = (b - yy) * rcb, cr = (r - yy) * rcr;
         const float Yq = D.full_range ? yy * 255.0f : fmaf(yy, 219.0f, 16.0f);
         D.p0[frame * D.bstride + (uint64_t)y * D.pitch + x] = q8(Yq);
         cbs += cb; crs += cr; cnt++;
@@ -101,9 +101,170 @@ __global__ void __launch_bounds__(256) k_yuv_chain(const __grid_constant__ YuvPa
     D.p2[co] = q8(fmaf(crm, cscale, 128.0f));
   }
 }
+
+// ---- the same chains with everything known at compile time: planar source with nearest chroma and a
+// BT.709-family EOTF, 0..2 matrix steps, and one of three destinations.  Same arithmetic as k_yuv_chain
+// (and, for the pixel destinations, as gather.cu / rowwise.cu), a fraction of the instructions.
+enum { D_YUV709 = 0, D_SRGB8 = 1, D_UNORM8 = 2 };
+constexpr int YER = 8;  // copies of the biased-key sRGB encoder table (texel.cuh)
+
+struct YuvFastParams {
+  DevImage src, dst;
+  int32_t nmat;
+  float m[2][9];
+  uint32_t bw, bh, total;
+  FastDiv div_bw, div_bh;
+  uint32_t spack;
+};
+
+__device__ __forceinline__ float eotf709(float v) {  // == yuv_eotf for the BT.709 family
+  float lin = v * (1.0f / 4.5f);
+  float l2, pw;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"((v + 0.099f) * (1.0f / 1.099f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pw) : "f"(l2 * (1.0f / 0.45f)));
+  return v >= 0.0812428582f ? pw : lin;
+}
+__device__ __forceinline__ uint32_t srgb_code_b3(float x, uint32_t enc_lane) {  // x in [0, 1]; code in byte 3
+  const float y = x + ZOS_ENC2_BIAS;
+  const int idx = max(__float_as_int(x), ZOS_ENC2_LOW);
+  const uint32_t a = (((__float_as_uint(y) >> 16) - (uint32_t)ZOS_ENC2_K0) * (YER * 4u)) + enc_lane;
+  uint32_t e;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(a));
+  return e + (uint32_t)idx;
+}
+
+template <int DST>
+__global__ void __launch_bounds__(256) k_yuv_fast(const __grid_constant__ YuvFastParams P) {
+  __shared__ uint32_t enc[DST == D_SRGB8 ? ZOS_ENC2_N * YER : 1];
+  if (DST == D_SRGB8) {
+    for (int i = threadIdx.x; i < ZOS_ENC2_N * YER; i += blockDim.x) enc[i] = g_tables.srgb_enc2[i / YER];
+    __syncthreads();
+  }
+  const uint32_t enc_lane = (uint32_t)__cvta_generic_to_shared(enc) + (threadIdx.x & (YER - 1)) * 4u;
+  const DevImage& A = P.src;
+  const DevImage& D = P.dst;
+  const int cstep_s = A.block == ZOS_BLOCK_YUV420_NV12 ? 2 : 1, cstep_d = D.block == ZOS_BLOCK_YUV420_NV12 ? 2 : 1;
+  const float kg = 1.0f - D.kr - D.kb;
+  const float rcb = 1.0f / (2.0f * (1.0f - D.kb)), rcr = 1.0f / (2.0f * (1.0f - D.kr));
+  const float cscale = D.full_range ? 255.0f : 224.0f;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < P.total; idx += stride) {
+    const uint32_t rowid = fastdiv(idx, P.div_bw);
+    const int ci = (int)(idx - rowid * P.bw);
+    const uint32_t frame = fastdiv(rowid, P.div_bh);
+    const int cj = (int)(rowid - frame * P.bh);
+    const uint64_t sco = frame * A.cbstride + (uint64_t)cj * A.cpitch + (uint64_t)ci * cstep_s;
+    const float cb_in = ((float)A.p1[sco] - 128.0f) * A.csc, cr_in = ((float)A.p2[sco] - 128.0f) * A.csc;
+    // both pixels of a block row come from one 16-bit load (the frame width is even for video formats; odd tails take bytes)
+    const int x0 = 2 * ci, y0 = 2 * cj;
+    const bool two_x = x0 + 1 < D.w, two_y = y0 + 1 < D.h;
+    float cbs = 0.0f, crs = 0.0f;
+#pragma unroll
+    for (int dy = 0; dy < 2; dy++) {
+      if (dy == 1 && !two_y) break;
+      const uint8_t* yrow = A.p0 + frame * A.bstride + (uint64_t)(y0 + dy) * A.pitch + x0;
+      uint32_t ypair = two_x ? (uint32_t)*reinterpret_cast<const uint16_t*>(yrow) : (uint32_t)*yrow;
+      uint32_t words[2];
+#pragma unroll
+      for (int dx = 0; dx < 2; dx++) {
+        if (dx == 1 && !two_x) break;
+        const float Y = (float)((ypair >> (8 * dx)) & 255u);
+        const float yy = (Y - A.yoff) * A.ysc;
+        float r = fmaf(A.r_cr, cr_in, yy), g = fmaf(-A.g_cb, cb_in, fmaf(-A.g_cr, cr_in, yy)), b = fmaf(A.b_cb, cb_in, yy);
+        r = eotf709(r); g = eotf709(g); b = eotf709(b);
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          if (k < P.nmat) {
+            float3 t = mat3_mul(P.m[k], r, g, b);
+            r = t.x; g = t.y; b = t.z;
+          }
+        }
+        if (DST == D_YUV709) {
+          const float er = oe_bt709(r), eg = oe_bt709(g), eb = oe_bt709(b);
+          const float yo = fmaf(D.kb, eb, fmaf(kg, eg, D.kr * er));
+          const float cb = (eb - yo) * rcb, cr = (er - yo) * rcr;
+          const float Yq = D.full_range ? yo * 255.0f : fmaf(yo, 219.0f, 16.0f);
+          D.p0[frame * D.bstride + (uint64_t)(y0 + dy) * D.pitch + x0 + dx] = q8(Yq);
+          cbs += cb; crs += cr;
+        } else {
+          r = fminf(fmaxf(r, 0.0f), 1.0f); g = fminf(fmaxf(g, 0.0f), 1.0f); b = fminf(fmaxf(b, 0.0f), 1.0f);
+          uint32_t t1, t2;
+          if (DST == D_SRGB8) {
+            t1 = __byte_perm(srgb_code_b3(r, enc_lane), srgb_code_b3(g, enc_lane), 0x0073);
+            t2 = __byte_perm(srgb_code_b3(b, enc_lane), 0xffu, 0x0043);
+          } else {
+            t1 = __byte_perm(__float_as_uint(r * 255.0f + 8388608.0f), __float_as_uint(g * 255.0f + 8388608.0f), 0x0040);
+            t2 = __byte_perm(__float_as_uint(b * 255.0f + 8388608.0f), 0xffu, 0x0040);
+          }
+          words[dx] = __byte_perm(t1, t2, P.spack);
+        }
+      }
+      if (DST != D_YUV709) {
+        uint8_t* drow = D.p0 + frame * D.bstride + (uint64_t)(y0 + dy) * D.pitch + (uint64_t)x0 * 4u;
+        if (two_x) __stcs(reinterpret_cast<uint2*>(drow), make_uint2(words[0], words[1]));
+        else *reinterpret_cast<uint32_t*>(drow) = words[0];
+      }
+    }
+    if (DST == D_YUV709) {
+      const int cnt = (two_x ? 2 : 1) * (two_y ? 2 : 1);
+      const float inv = cnt == 4 ? 0.25f : cnt == 2 ? 0.5f : 1.0f;  // == dividing by 1, 2 or 4
+      const uint64_t co = frame * D.cbstride + (uint64_t)cj * D.cpitch + (uint64_t)ci * cstep_d;
+      D.p1[co] = q8(fmaf(cbs * inv, cscale, 128.0f));
+      D.p2[co] = q8(fmaf(crs * inv, cscale, 128.0f));
+    }
+  }
+}
+
+bool bt709_family(uint32_t tr) { return tr == ZOS_TRANSFER_BT709 || tr == ZOS_TRANSFER_BT2020_10BIT || tr == ZOS_TRANSFER_BT2020_12BIT; }
 }  // namespace
 
+// Planar source (nearest chroma, BT.709-family EOTF), matrix-only steps, same size -> BT.709-family planar or native
+// 8-bit RGBA / BGRA.  *handled stays false when the chain is not of that shape.
+zos_status launch_yuv_fast(zos_ctx* ctx, const DevImage& src, const DevImage& dst, const zos_step* steps, uint32_t nsteps, uint32_t batch, bool* handled) {
+  *handled = false;
+  if (ctx->flags & ZOS_CTX_NO_FAST_PATHS) return ZOS_OK;
+  if (src.block == ZOS_BLOCK_PIXEL || src.chroma_filter != 0 || !bt709_family(src.fmt.transfer)) return ZOS_OK;
+  if (src.w != dst.w || src.h != dst.h || nsteps > 2) return ZOS_OK;
+  for (uint32_t i = 0; i < nsteps; i++)
+    if (steps[i].kind != ZOS_STEP_MATRIX) return ZOS_OK;
+  int kind;
+  if (dst.block != ZOS_BLOCK_PIXEL) {
+    if (!bt709_family(dst.fmt.transfer)) return ZOS_OK;
+    kind = D_YUV709;
+  } else {
+    if (dst.bpp != 4 || (dst.fmt.parts != ZOS_PARTS_RGBA && dst.fmt.parts != ZOS_PARTS_BGRA)) return ZOS_OK;
+    if (dst.fmt.storage == ZOS_STORAGE_SRGB8) kind = D_SRGB8;
+    else if (dst.fmt.storage == ZOS_STORAGE_UNORM8) kind = D_UNORM8;
+    else return ZOS_OK;
+    if (((uintptr_t)dst.p0 % 8) || (dst.pitch % 8) || (dst.bstride % 8)) return ZOS_OK;
+  }
+  if ((src.pitch % 2) || ((uintptr_t)src.p0 % 2) || (src.bstride % 2)) return ZOS_OK;
+  YuvFastParams P;
+  memset(&P, 0, sizeof P);
+  P.src = src; P.dst = dst;
+  P.nmat = (int32_t)nsteps;
+  for (uint32_t i = 0; i < nsteps; i++) memcpy(P.m[i], steps[i].m, sizeof(float) * 9);
+  P.spack = dst.fmt.parts == ZOS_PARTS_BGRA ? 0x5014u : 0x5410u;
+  P.bw = (uint32_t)(dst.w + 1) / 2; P.bh = (uint32_t)(dst.h + 1) / 2;
+  const uint64_t total = (uint64_t)P.bw * P.bh * batch;
+  if (total == 0 || total >= (1ull << 32)) return ZOS_OK;
+  P.total = (uint32_t)total;
+  P.div_bw = make_fastdiv(P.bw); P.div_bh = make_fastdiv(P.bh);
+  const int grid = grid_for(ctx, total, 256, 8);
+  if (kind == D_YUV709) k_yuv_fast<D_YUV709><<<grid, 256, 0, ctx->stream>>>(P);
+  else if (kind == D_SRGB8) k_yuv_fast<D_SRGB8><<<grid, 256, 0, ctx->stream>>>(P);
+  else k_yuv_fast<D_UNORM8><<<grid, 256, 0, ctx->stream>>>(P);
+  ctx->launches++;
+  *handled = true;
+  return check_cuda(ctx, cudaGetLastError(), "k_yuv_fast launch");
+}
+
 zos_status launch_yuv_chain(zos_ctx* ctx, const DevImage& src, const DevImage& dst, const zos_step* steps, uint32_t nsteps, uint32_t batch) {
+  {
+    bool handled = false;
+    zos_status st = launch_yuv_fast(ctx, src, dst, steps, nsteps, batch, &handled);
+    if (handled || st != ZOS_OK) return st;
+  }
   if (dst.block == ZOS_BLOCK_PIXEL) return fail(ctx, ZOS_ERR_INVALID, "yuv_chain: destination is not planar");
   if (src.block != ZOS_BLOCK_PIXEL && src.chroma_filter != 0)
     return fail(ctx, ZOS_ERR_UNSUPPORTED, "planar -> planar chains take nearest chroma sources (chroma_filter = 0)");

@@ -75,6 +75,7 @@ bool rowwise_can_compose(const DevImage& below, const DevImage& above, const Dev
 zos_status launch_gather(zos_ctx* ctx, const DevImage* below, const DevImage& above, const DevImage& dst,
                          const zos_compose_params& cp, uint32_t batch);
 bool frame_pipeline_eligible(zos_ctx* ctx, const DevImage* below, const DevImage& above, const DevImage& dst, const zos_compose_params& cp);
+zos_status launch_yuv_fast(zos_ctx* ctx, const DevImage& src, const DevImage& dst, const zos_step* steps, uint32_t nsteps, uint32_t batch, bool* handled);
 zos_status launch_yuv_chain(zos_ctx* ctx, const DevImage& src, const DevImage& dst, const zos_step* steps, uint32_t nsteps, uint32_t batch);
 zos_status launch_affine_f16(zos_ctx* ctx, const DevImage* below, const DevImage& above, const DevImage& dst,
                              const zos_compose_params& cp, uint32_t batch, bool* handled);
