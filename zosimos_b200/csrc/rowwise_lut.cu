@@ -242,9 +242,10 @@ static cudaError_t launch_one(zos_ctx* ctx, const FastParams& P) {
 
 cudaError_t launch_rowwise_lut(zos_ctx* ctx, FastParams& P, int sk, int dk, int mode, int nmat) {
   // linear addressing: every layer has the destination's geometry, rows and frames back to back
-  const uint64_t row = (uint64_t)P.w * 4u;
-  const bool full = mode == 0 || (P.tx == 0 && P.ty == 0 && P.aw == P.w && P.ah == P.h && P.above_pitch == row && P.above_bstride == row * P.h);
-  P.linear = (P.w % 4 == 0) && full && P.below_pitch == row && P.dst_pitch == row && P.below_bstride == row * P.h && P.dst_bstride == row * P.h;
+  const uint64_t row = (uint64_t)P.w * 4u, frame = row * P.h;
+  const bool one = (uint64_t)P.total_groups == (uint64_t)P.groups_per_row * (uint64_t)P.h;  // a single frame: frame strides are not used
+  const bool full = mode == 0 || (P.tx == 0 && P.ty == 0 && P.aw == P.w && P.ah == P.h && P.above_pitch == row && (one || P.above_bstride == frame));
+  P.linear = (P.w % 4 == 0) && full && P.below_pitch == row && P.dst_pitch == row && (one || (P.below_bstride == frame && P.dst_bstride == frame));
 #define ZOS_LUT(SK_, DK_)                                                 \
   if (sk == SK_ && dk == DK_) {                                           \
     if (mode == 0 && nmat == 0) return launch_one<SK_, DK_, 0, 0>(ctx, P); \
