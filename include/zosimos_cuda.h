@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ZOS_ABI_VERSION 2
+#define ZOS_ABI_VERSION 3
 
 typedef int32_t zos_status;
 enum {
@@ -261,8 +261,11 @@ enum {
   /* byte buffers in device memory (command.rs:1777-1803 buffer_init / buffer_zero, :937-968 from_buffer,
    * WithBuffer :1963-2060; tests/buffer.rs).  A buffer register has no texel: desc is ignored. */
   ZOS_OP_BUFFER_INIT = 9,  /* dst = buffer register of data_len bytes, filled from `data` (NULL = zeroed)   */
-  ZOS_OP_FROM_BUFFER = 10  /* src[0] = buffer register holding the image in the ALIGNED device layout
+  ZOS_OP_FROM_BUFFER = 10, /* src[0] = buffer register holding the image in the ALIGNED device layout
                               (row_stride = zos_aligned_row_stride) -> dst image register (High::Copy)       */
+  ZOS_OP_DYNAMIC = 11      /* user operator (command.rs:2933-3060 {construct,unary,binary}_dynamic): `source` = CUDA C
+                              defining zos_shade (see zos_dynamic_create), data / data_len = its parameter bytes,
+                              src[0], src[1] = operands or -1, desc = the image it produces                   */
   /* ZOS_OP_GENERATE with src[0] = a buffer register: the parameter block is read from that buffer at run time */
 };
 typedef struct zos_op {
@@ -276,8 +279,9 @@ typedef struct zos_op {
   float gen[24];
   uint32_t knob; /* 0 = none, else 1-based knob id whose bytes overwrite this op's parameter block */
   int32_t reg;   /* this op's own register number (Register(idx), command.rs:31); equals dst except for Output ops */
-  const void* data;  /* ZOS_OP_BUFFER_INIT: initial bytes (copied by zos_program_create), or NULL */
-  uint64_t data_len; /* ZOS_OP_BUFFER_INIT: size of the buffer in bytes */
+  const void* data;  /* ZOS_OP_BUFFER_INIT: initial bytes (copied by zos_program_create), or NULL; ZOS_OP_DYNAMIC: parameter bytes */
+  uint64_t data_len; /* ZOS_OP_BUFFER_INIT: size of the buffer in bytes; ZOS_OP_DYNAMIC: size of the parameter block */
+  const char* source; /* ZOS_OP_DYNAMIC: NUL-terminated CUDA C source (copied by zos_program_create) */
 } zos_op;
 enum { ZOS_FUSE_EXACT = 0 /* every declared register is quantised like the reference, in registers */,
        ZOS_FUSE_WIDE = 1 /* fused intermediates stay f32 */,
@@ -294,6 +298,17 @@ zos_status zos_program_set_knob(zos_program* prog, uint32_t knob, const void* da
 /* Executable::launch + Execution::step (run.rs:1016,1389): step launches up to max_kernels kernels */
 zos_status zos_program_launch(zos_program* prog);
 zos_status zos_program_step(zos_program* prog, uint32_t max_kernels, int32_t* still_running);
+/* User operators: the CUDA analogue of the reference's plugin interface `trait ShaderCommand` (command/dynamic.rs:7-60,
+ * SPIR-V fragment shaders there).  `cuda_source` defines
+ *     __device__ float4 zos_shade(float2 uv, const unsigned char* params, zos_tex in0, zos_tex in1);
+ * evaluated per destination pixel at uv = pixel centre / size; in0.fetch(uv) / in0.at(x, y) read the operands' working
+ * values (nearest texel).  Compiled with NVRTC for sm_100a on first use, cached per context by source text; the
+ * compiler log is in zos_last_error on failure.  A zos_dynamic belongs to its context (freed by zos_ctx_destroy). */
+typedef struct zos_dynamic zos_dynamic;
+zos_status zos_dynamic_create(zos_ctx* ctx, const char* cuda_source, zos_dynamic** out);
+zos_status zos_dynamic_launch(zos_ctx* ctx, zos_dynamic* dyn, const zos_image* dst, const zos_image* in0, const zos_image* in1,
+                              const void* params, uint64_t params_len);
+
 /* Executable reuse (run.rs:1016,1283-1347; Readme.md "re-use of the pipeline"; tests/loop.rs, tests/knobs.rs):
  * run the whole schedule again, same plan, possibly other bindings / knob values.  ZOS_RUN_GRAPH relaunches
  * the schedule as one CUDA graph (captured on the second run, re-captured after zos_program_bind /

@@ -83,6 +83,10 @@ int32_t zosh_cb_buffer_zero(zosh_cb* cb, uint64_t len, int32_t* reg);           
 int32_t zosh_cb_buffer_size(const zosh_cb* cb, int32_t reg, uint64_t* out);                             /* RegisterDescription::Buffer */
 int32_t zosh_cb_from_buffer(zosh_cb* cb, int32_t buffer, const zos_desc* desc, int32_t* reg);           /* command.rs:937-968 */
 int32_t zosh_cb_with_buffer_bilinear(zosh_cb* cb, int32_t buffer, const zos_desc* desc, int32_t* reg);  /* command.rs:1963-2060 + bilinear */
+/* user operators: construct_dynamic (no operand), unary_dynamic (src0), binary_dynamic (src0, src1), command.rs:2933-3060.
+ * `cuda_source` is the plugin (see zos_dynamic_create), `desc` the descriptor ShaderCommand::data returns, params its data. */
+int32_t zosh_cb_dynamic(zosh_cb* cb, int32_t src0, int32_t src1, const char* cuda_source, const zos_desc* desc, const void* params,
+                        uint64_t params_len, int32_t* reg);
 int32_t zosh_cb_with_knob(zosh_cb* cb);  /* the NEXT operation gets a knob; returns its 1-based id (command.rs:1865-1874) */
 
 /* Linker::compile (command.rs:2069): liveness + emission of the High-like op list */

@@ -468,3 +468,124 @@ def test_run_bilinear_from_buffer(pool):  # tests/buffer.rs:121-149: the generat
     assert O.blockhash256(rgba(img)) in hashes()["bilinear_from_buffer"]
     exp = O.bilinear(O.srgb_rgba8(256, 256), params)
     assert np.array_equal(rgba(img), exp.data.reshape(256, 256, 4))
+
+
+# ---------------------------------------------------------------- user operators (tests/custom.rs)
+MANDELBROT_CU = r"""
+// lib/std/src/mandelbrot.frag as a CUDA plugin
+__device__ float4 zos_shade(float2 uv, const unsigned char* params, zos_tex in0, zos_tex in1) {
+  const float* p = (const float*)params;               // scale.xy, position.xy
+  const float cx = (uv.x - p[2]) * p[0], cy = (uv.y - p[3]) * p[1];
+  float x = 0.0f, y = 0.0f, sx = 0.0f, sy = 0.0f;
+  for (int i = 0; i < 2048; i++) {
+    sx += x; sy += y;
+    const float real = x * x + y * (-y);
+    const float imag = fmaf(2.0f * x, y, cy);
+    x = real + cx; y = imag;
+  }
+  sx = sx / 2048.0f - cx; sy = sy / 2048.0f - cy;
+  const float len = sqrtf(x * x + y * y);
+  const float light = fminf(fmaxf(2.0f - len, 0.0f), 0.7f);
+  return make_float4(light, sx / 2.0f, sy / 2.0f, 1.0f);
+}
+"""
+
+CRT_CU = r"""
+// lib/std/src/crt.frag as a CUDA plugin: every source pixel becomes a 3x3 cell of R, G, B stripes
+__device__ float4 zos_shade(float2 uv, const unsigned char* params, zos_tex in0, zos_tex in1) {
+  const unsigned* scale = (const unsigned*)params;
+  const unsigned sx = (unsigned)(uv.x * (float)scale[0]), sy = (unsigned)(uv.y * (float)scale[1]);
+  const float4 rgba = in0.fetch(uv);
+  const unsigned bias = ((sx / 3u) % 2u) * 3u;
+  const unsigned cell = (sy + bias) % 6u;
+  const float off_center = (float)cell * (float)(5u - cell);
+  float m[4] = {0.0f, 0.0f, 0.0f, 1.0f};
+  m[sx % 3u] = 0.16f * off_center;
+  return make_float4(rgba.x * m[0], rgba.y * m[1], rgba.z * m[2], rgba.w * m[3]);
+}
+"""
+
+
+def _shader(source, desc, data):
+    from zosimos_b200.command import ShaderCommand
+
+    class Cmd(ShaderCommand):
+        def source(self):
+            return source
+
+        def data(self, sd):
+            sd.set_data(data)
+            return desc
+    return Cmd()
+
+
+def test_dynamic_mandelbrot(pool):  # tests/custom.rs:15-96: construct_dynamic into an Oklab LchA image, then to sRGB
+    w = h = 256
+    lch = Descriptor(Z.ByteLayout(w, h, 4 * w, 4), Color.Oklab, Texel(Z.Block.Pixel, SampleBits.UInt8x4, SampleParts.LchA))
+    c = CommandBuffer()
+    brot = c.construct_dynamic(_shader(MANDELBROT_CU, lch, np.asarray([3.0, 3.0, 0.6, 0.5], np.float32)))
+    srgb = Descriptor.with_srgb_image("rgba8", w, h)
+    output, _ = c.output(c.color_convert(brot, srgb.color, srgb.texel))
+    img, n = run_once_with_output(c, pool, [], output)
+    got = rgba(img)
+    # the same iteration in numpy f32 (fma through f64), then the oracle's encode / colour conversion
+    f = np.float32
+    u = (np.arange(w, dtype=f) + f(0.5)) / f(w); v = (np.arange(h, dtype=f) + f(0.5)) / f(h)
+    U, V = np.meshgrid(u, v)
+    cx, cy = (U - f(0.6)) * f(3.0), (V - f(0.5)) * f(3.0)
+    x = np.zeros_like(cx); y = np.zeros_like(cx); sx = np.zeros_like(cx); sy = np.zeros_like(cx)
+    with np.errstate(all="ignore"):
+        for _ in range(2048):
+            sx = sx + x; sy = sy + y
+            real = x * x + y * (-y)
+            imag = (np.float64(f(2.0) * x) * np.float64(y) + np.float64(cy)).astype(f)
+            x = real + cx; y = imag
+        sx = sx / f(2048.0) - cx; sy = sy / f(2048.0) - cy
+        ln = np.sqrt(x * x + y * y)
+        light = np.minimum(np.maximum(f(2.0) - ln, f(0.0)), f(0.7))
+        light = np.where(np.isnan(light), f(0.0), light)   # fminf(fmaxf(NaN, 0), 0.7) == 0
+    tex = np.stack([light, sx / f(2.0), sy / f(2.0), np.ones_like(light)], -1).astype(f)
+    reg = O.encode(oracle_desc(lch), tex)
+    exp = O.color_convert(reg, O.SRGB, O.RGBA8).data.reshape(h, w, 4)
+    d = np.abs(got.astype(int) - exp.astype(int))
+    assert np.mean(d <= 1) > 0.98      # chaotic near the set's boundary: last-bit differences of the iteration flip pixels there
+    hsh = O.blockhash256(got)
+    dist = min(bin(int(hsh, 16) ^ int(g, 16)).count("1") for g in hashes()["mandelbrot"])
+    assert dist <= 4, (hsh, hashes()["mandelbrot"])   # the reference itself lists two device-dependent hashes 3 bits apart
+
+
+def test_dynamic_crt(pool, images, fixtures):  # tests/custom.rs:98-186: unary_dynamic, output three times the input's size
+    bg, _ = images
+    d = bg.descriptor()
+    w, h = 3 * d.layout.width, 3 * d.layout.height
+    big = Descriptor(Z.ByteLayout(w, h, 4 * w, 4), d.color, d.texel)
+    c = CommandBuffer()
+    inp = c.input(d)
+    crt = c.unary_dynamic(inp, _shader(CRT_CU, big, np.asarray([w, h], np.uint32)))
+    srgb = Descriptor.with_srgb_image("rgba8", w, h)
+    output, _ = c.output(c.color_convert(crt, srgb.color, srgb.texel))
+    img, _ = run_once_with_output(c, pool, [(inp, bg.key())], output)
+    got = rgba(img)
+    assert O.blockhash256(got) in hashes()["crt"]
+    # against the definition: decode, stripe multipliers, encode (all exact: one multiply per channel)
+    src = O.decode(oracle_image(d, fixtures["background"]))
+    X, Y = np.meshgrid(np.arange(w), np.arange(h))
+    bias = ((X // 3) % 2) * 3
+    cell = (Y + bias) % 6
+    off = (cell * (5 - cell)).astype(np.float32) * np.float32(0.16)
+    tex = np.repeat(np.repeat(src, 3, axis=0), 3, axis=1).copy()
+    for ch in range(3):
+        tex[..., ch] = np.where(X % 3 == ch, tex[..., ch] * off, np.float32(0.0))
+    exp = O.encode(O.srgb_rgba8(w, h), tex).data.reshape(h, w, 4)
+    assert np.array_equal(got, exp)
+
+
+def test_dynamic_compile_error(pool):
+    from zosimos_b200.program import LaunchError
+    desc = Descriptor.with_srgb_image("rgba8", 16, 16)
+    c = CommandBuffer()
+    output, _ = c.output(c.construct_dynamic(_shader("__device__ float4 zos_shade(float2 uv) { return nonsense; }", desc, b"")))
+    executable = Linker.from_included().compile(c).lower_to(Capabilities.from_device(next(pool.iter_devices())))
+    with pytest.raises(LaunchError) as e:
+        executable.launch(executable.from_pool(pool))
+    assert "compile" in str(e.value)

@@ -28,7 +28,7 @@ BLEND_OVERWRITE = -1
 BLEND_INJECT = 12
 # program ops
 GEN_BILINEAR, GEN_SOLID, GEN_NORMAL2D, GEN_FRACTAL_NOISE = 0, 1, 2, 3
-OP_INPUT, OP_OUTPUT, OP_PIXEL, OP_COMPOSE, OP_COPY, OP_GENERATE, OP_BOX3, OP_PALETTE, OP_BUFFER_INIT, OP_FROM_BUFFER = range(1, 11)
+OP_INPUT, OP_OUTPUT, OP_PIXEL, OP_COMPOSE, OP_COPY, OP_GENERATE, OP_BOX3, OP_PALETTE, OP_BUFFER_INIT, OP_FROM_BUFFER, OP_DYNAMIC = range(1, 12)
 FUSE_EXACT, FUSE_WIDE, FUSE_NONE = 0, 1, 2
 BLOCK_PIXEL, BLOCK_YUV420_PLANAR, BLOCK_YUV420_NV12 = 0, 1, 2
 
@@ -66,7 +66,7 @@ class ZosComposeParams(C.Structure):
 class ZosOp(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("src", C.c_int32 * 2), ("dst", C.c_int32), ("desc", ZosDesc),
                 ("nsteps", C.c_uint32), ("steps", ZosStep * ZOS_MAX_STEPS), ("compose", ZosComposeParams),
-                ("gen", C.c_float * 24), ("knob", C.c_uint32), ("reg", C.c_int32), ("data", C.c_void_p), ("data_len", C.c_uint64)]
+                ("gen", C.c_float * 24), ("knob", C.c_uint32), ("reg", C.c_int32), ("data", C.c_void_p), ("data_len", C.c_uint64), ("source", C.c_char_p)]
 
 
 class ZosError(RuntimeError):
@@ -120,6 +120,8 @@ SIGNATURES = {
     "zos_program_step": (C.c_int32, [_P, C.c_uint32, C.POINTER(C.c_int32)]),
     "zos_program_kernel_count": (C.c_uint32, [_P]),
     "zos_srgb_encoder_tables": (C.c_int32, [C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "zos_dynamic_create": (C.c_int32, [_P, C.c_char_p, C.POINTER(_P)]),
+    "zos_dynamic_launch": (C.c_int32, [_P, _P, C.POINTER(ZosImage), C.POINTER(ZosImage), C.POINTER(ZosImage), C.c_void_p, C.c_uint64]),
     "zos_program_run": (C.c_int32, [_P, C.c_uint32]),
     "zos_program_graph_launches": (C.c_uint64, [_P]),
     "zos_program_register_image": (C.c_int32, [_P, C.c_int32, C.POINTER(ZosImage)]),

@@ -69,6 +69,7 @@ _HOST_SIGNATURES = {
     "zosh_cb_transmute": (C.c_int32, [_P, C.c_int32, C.POINTER(_ffi.ZosDesc), C.POINTER(C.c_int32)]),
     "zosh_cb_bilinear": (C.c_int32, [_P, C.POINTER(_ffi.ZosDesc), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "zosh_cb_solid_rgba": (C.c_int32, [_P, C.POINTER(_ffi.ZosDesc), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "zosh_cb_dynamic": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_char_p, C.POINTER(_ffi.ZosDesc), C.c_void_p, C.c_uint64, C.POINTER(C.c_int32)]),
     "zosh_cb_buffer_init": (C.c_int32, [_P, C.c_void_p, C.c_uint64, C.POINTER(C.c_int32)]),
     "zosh_cb_buffer_zero": (C.c_int32, [_P, C.c_uint64, C.POINTER(C.c_int32)]),
     "zosh_cb_buffer_size": (C.c_int32, [_P, C.c_int32, C.POINTER(C.c_uint64)]),
@@ -414,6 +415,27 @@ class CommandBuffer:
         p = (C.c_float * 5)(*distribution.params)
         return self._reg(host_lib().zosh_cb_distribution_fractal_noise(self._h, C.byref(d), p, C.byref(out)), out)
 
+    # -- user operators (tests/custom.rs)
+    def _dynamic(self, src0: int, src1: int, dynamic: "ShaderCommand") -> Register:
+        sd = ShaderData()
+        source = dynamic.source()
+        desc = dynamic.data(sd)
+        out = C.c_int32(); d = desc.to_ffi()
+        content = sd.content or b""
+        buf = C.create_string_buffer(content, len(content)) if content else None
+        st = host_lib().zosh_cb_dynamic(self._h, src0, src1, source.encode(), C.byref(d), C.cast(buf, C.c_void_p) if buf else None,
+                                        len(content), C.byref(out))
+        return self._reg(st, out)
+
+    def construct_dynamic(self, dynamic: "ShaderCommand") -> Register:  # command.rs:2933-2961
+        return self._dynamic(-1, -1, dynamic)
+
+    def unary_dynamic(self, op: Register, dynamic: "ShaderCommand") -> Register:  # command.rs:2963-3002
+        return self._dynamic(op.index, -1, dynamic)
+
+    def binary_dynamic(self, lhs: Register, rhs: Register, dynamic: "ShaderCommand") -> Register:  # command.rs:3004-3060
+        return self._dynamic(lhs.index, rhs.index, dynamic)
+
     # -- byte buffers (tests/buffer.rs)
     def buffer_init(self, init: bytes) -> Register:  # command.rs:1777-1790 (with_knob().buffer_init: :1938)
         out = C.c_int32(); data = bytes(init)
@@ -468,6 +490,22 @@ class CommandBuffer:
             raise CommandError(CommandErrorKind.Other, "inject: channel")
         out = C.c_int32()
         return self._reg(host_lib().zosh_cb_inject(self._h, below.index, self._CHANNEL[channel], above.index, C.byref(out)), out)
+
+
+class ShaderData:  # command/dynamic.rs:40-58
+    def __init__(self):
+        self.content: Optional[bytes] = None
+
+    def set_data(self, data) -> None:
+        self.content = np.asarray(data).tobytes() if not isinstance(data, (bytes, bytearray)) else bytes(data)
+
+
+class ShaderCommand:  # command/dynamic.rs:7-28; the source is CUDA C instead of SPIR-V (see include/zosimos_cuda.h, zos_dynamic_create)
+    def source(self) -> str:
+        raise NotImplementedError
+
+    def data(self, data: ShaderData) -> Descriptor:
+        raise NotImplementedError
 
 
 class WithBuffer:  # command.rs:1963-2060: the next operation's parameter block is read from a device buffer

@@ -495,6 +495,32 @@ int32_t zosh_cb_with_buffer_bilinear(zosh_cb* cb, int32_t buffer, const zos_desc
   return push(cb, op, reg);
 }
 
+// ---- user operators (command.rs:2933-3060 construct_dynamic / unary_dynamic / binary_dynamic; command/dynamic.rs)
+int32_t zosh_cb_dynamic(zosh_cb* cb, int32_t src0, int32_t src1, const char* cuda_source, const zos_desc* desc, const void* params,
+                        uint64_t params_len, int32_t* reg) {
+  if (!cb || !cuda_source || !desc) return err(ZOSH_ERR_OTHER, "null argument");
+  if (src0 < 0 && src1 >= 0) return err(ZOSH_ERR_OTHER, "binary_dynamic needs both operands");
+  for (int32_t r : {src0, src1})
+    if (r >= 0 && !valid_reg(cb, r)) return err(ZOSH_ERR_OTHER, "dynamic operand is not an image register (CommandError::INVALID_CALL)");
+  if (params_len > 4096 || (params_len && !params)) return err(ZOSH_ERR_OTHER, "dynamic operator: 0..4096 bytes of data");
+  zos_desc d = *desc;
+  if (d.block != ZOS_BLOCK_PIXEL || d.texel_stride != zos_bits_bytes(d.bits) || d.width == 0 || d.height == 0)
+    return err(ZOSH_ERR_BAD_DESCRIPTOR, "inconsistent descriptor returned by the shader command");
+  fix_layout(d);
+  zos_op op = new_op(cb, ZOS_OP_DYNAMIC, src0, src1, d);
+  const size_t n = strlen(cuda_source);
+  auto text = std::make_shared<std::vector<uint8_t>>((const uint8_t*)cuda_source, (const uint8_t*)cuda_source + n + 1);
+  cb->blobs.push_back(text);
+  op.source = (const char*)text->data();
+  if (params_len) {
+    auto blob = std::make_shared<std::vector<uint8_t>>((const uint8_t*)params, (const uint8_t*)params + params_len);
+    cb->blobs.push_back(blob);
+    op.data = blob->data();
+    op.data_len = params_len;
+  }
+  return push(cb, op, reg);
+}
+
 int32_t zosh_cb_derivative(zosh_cb* cb, int32_t src, uint32_t method, uint32_t height_direction, int32_t* reg) {
   if (!cb || !valid_reg(cb, src)) return err(ZOSH_ERR_OTHER, "bad register");
   float sm[3];

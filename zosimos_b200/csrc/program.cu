@@ -23,7 +23,7 @@ using namespace zos;
 
 namespace {
 
-enum KKind { K_PIXEL, K_COMPOSE, K_COPY, K_GENERATE, K_BOX3, K_PALETTE, K_BUFFER_INIT, K_FROM_BUFFER };
+enum KKind { K_PIXEL, K_COMPOSE, K_COPY, K_GENERATE, K_BOX3, K_PALETTE, K_BUFFER_INIT, K_FROM_BUFFER, K_DYNAMIC };
 
 struct Kernel {
   KKind kind;
@@ -34,7 +34,8 @@ struct Kernel {
   float gen[24];                       // K_GENERATE; K_BOX3 uses gen[0..8]
   uint32_t knob = 0;                   // knob id patched into this kernel's parameter block
   int knob_step = -1;                  // which step carries the knob-able matrix (K_PIXEL)
-  std::vector<uint8_t> bytes;          // K_BUFFER_INIT: the initial content (patched by a knob)
+  std::vector<uint8_t> bytes;          // K_BUFFER_INIT: the initial content; K_DYNAMIC: the parameter block (both knob-able)
+  zos_dynamic* dyn = nullptr;          // K_DYNAMIC: the compiled plugin (owned by the context's cache)
 };
 
 struct Reg {
@@ -261,6 +262,23 @@ zos_status plan(zos_program* p, const zos_op* ops, uint32_t nops) {
         p->schedule.push_back(k);
         break;
       }
+      case ZOS_OP_DYNAMIC: {
+        if (!op.source) return fail(ctx, ZOS_ERR_INVALID, "op %u: dynamic operator without source", i);
+        if (p->batch != 1) return fail(ctx, ZOS_ERR_UNSUPPORTED, "op %u: dynamic operators in a batched program", i);
+        for (int s2 = 0; s2 < 2; s2++)
+          if (op.src[s2] >= 0) {
+            if ((st = check_reg(p, op.src[s2], "dynamic operand")) != ZOS_OK) return st;
+            if (p->regs[op.src[s2]].is_buffer) return fail(ctx, ZOS_ERR_TYPE, "op %u: dynamic operands are images (CommandError::INVALID_CALL)", i);
+            if ((st = flush(p, op.src[s2])) != ZOS_OK) return st;
+          }
+        if ((st = alloc_reg(p, op.dst)) != ZOS_OK) return st;
+        Kernel k;
+        k.kind = K_DYNAMIC; k.src0 = op.src[0]; k.src1 = op.src[1]; k.dst = op.dst; k.knob = op.knob;
+        if (op.data && op.data_len) k.bytes.assign((const uint8_t*)op.data, (const uint8_t*)op.data + op.data_len);
+        if ((st = zos_dynamic_create(ctx, op.source, &k.dyn)) != ZOS_OK) return st;
+        p->schedule.push_back(k);
+        break;
+      }
       case ZOS_OP_FROM_BUFFER: {
         if ((st = check_reg(p, op.src[0], "from_buffer")) != ZOS_OK) return st;
         Reg& S = p->regs[op.src[0]];
@@ -332,6 +350,8 @@ zos_status run_kernel(zos_program* p, const Kernel& k) {
     case K_GENERATE:
       if (k.src0 >= 0) return zos_generate_from_buffer(ctx, img(k.dst), (uint32_t)k.cp.map, p->regs[k.src0].owned, 0, p->batch);
       return zos_generate(ctx, img(k.dst), (uint32_t)k.cp.map, k.gen, p->batch);
+    case K_DYNAMIC:
+      return zos_dynamic_launch(ctx, k.dyn, img(k.dst), img(k.src0), img(k.src1), k.bytes.data(), k.bytes.size());
     case K_BUFFER_INIT:  // (the host bytes belong to the program: they outlive the asynchronous copy)
       return check_cuda(ctx, cudaMemcpyAsync(p->regs[k.dst].owned->ptr, k.bytes.data(), k.bytes.size(), cudaMemcpyHostToDevice, ctx->stream), "buffer_init");
     case K_FROM_BUFFER: {
@@ -411,7 +431,7 @@ zos_status zos_program_set_knob(zos_program* p, uint32_t knob, const void* data,
     if (k.knob != knob) continue;
     found = true;
     const float* f = (const float*)data;
-    if (k.kind == K_BUFFER_INIT) {  // the whole content is the parameter block (tests/buffer.rs:67-118)
+    if (k.kind == K_BUFFER_INIT || k.kind == K_DYNAMIC) {  // the whole content is the parameter block (tests/buffer.rs:67-118)
       if (len != k.bytes.size()) return fail(p->ctx, ZOS_ERR_INVALID, "knob %u: buffer holds %zu bytes", knob, k.bytes.size());
       memcpy(k.bytes.data(), data, (size_t)len);
       continue;

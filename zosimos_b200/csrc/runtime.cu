@@ -317,6 +317,7 @@ void zos_ctx_destroy(zos_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  destroy_dynamic_cache(ctx);
   for (void* p : ctx->scratch) cudaFree(p);
   if (ctx->fault_host) cudaFreeHost(ctx->fault_host);
   cudaStreamDestroy(ctx->stream);

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
 #include <string>
 #include <vector>
 
@@ -24,6 +25,7 @@ struct zos_ctx {
   std::vector<void*> scratch;    // device scratch owned by the ctx (tensor maps etc.)
   int* fault_host = nullptr;     // mapped pinned word: kernels set it when an mbarrier wait ran away; zos_sync reports it
   int* fault_dev = nullptr;      // device view of fault_host
+  std::map<std::string, struct zos_dynamic*> dynamic_cache;  // NVRTC-compiled plugins by source text (dynamic.cu)
 };
 
 namespace zos {
@@ -75,6 +77,7 @@ bool rowwise_can_compose(const DevImage& below, const DevImage& above, const Dev
 zos_status launch_gather(zos_ctx* ctx, const DevImage* below, const DevImage& above, const DevImage& dst,
                          const zos_compose_params& cp, uint32_t batch);
 bool frame_pipeline_eligible(zos_ctx* ctx, const DevImage* below, const DevImage& above, const DevImage& dst, const zos_compose_params& cp);
+void destroy_dynamic_cache(zos_ctx* ctx);
 zos_status launch_yuv_fast(zos_ctx* ctx, const DevImage& src, const DevImage& dst, const zos_step* steps, uint32_t nsteps, uint32_t batch, bool* handled);
 zos_status launch_yuv_chain(zos_ctx* ctx, const DevImage& src, const DevImage& dst, const zos_step* steps, uint32_t nsteps, uint32_t batch);
 zos_status launch_affine_f16(zos_ctx* ctx, const DevImage* below, const DevImage& above, const DevImage& dst,
