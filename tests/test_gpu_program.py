@@ -589,3 +589,43 @@ def test_dynamic_compile_error(pool):
     with pytest.raises(LaunchError) as e:
         executable.launch(executable.from_pool(pool))
     assert "compile" in str(e.value)
+
+
+FLAT_FIELD_CU = r"""
+// lib/std/src/flat_field.frag as a CUDA plugin
+__device__ float4 zos_shade(float2 uv, const unsigned char* params, zos_tex in0, zos_tex in1) {
+  const float mean = *(const float*)params;
+  const float4 rgba = in0.fetch(uv), field = in1.fetch(uv);
+  const float e = mean / field.x;
+  return make_float4(rgba.x * e, rgba.y * e, rgba.z * e, rgba.w);
+}
+"""
+
+
+def test_dynamic_flat_field(pool, images, fixtures):  # tests/custom.rs:188-290: binary_dynamic(background, fractal noise in Luma8)
+    from zosimos_b200.command import FractalNoise
+    bg, _ = images
+    d = bg.descriptor()
+    flat_desc = Descriptor.with_srgb_image("luma8", 512, 512)
+    noise = FractalNoise([10.0, 10.0, 0.1, 0.2, 8])
+    c = CommandBuffer()
+    inp = c.input(d)
+    flat = c.distribution_fractal_noise(flat_desc, noise)
+    corrected = c.binary_dynamic(inp, flat, _shader(FLAT_FIELD_CU, d, np.asarray([0.124 / 2.0], np.float32)))
+    srgb = Descriptor.with_srgb_image("rgba8", 512, 512)
+    output, _ = c.output(c.color_convert(corrected, srgb.color, srgb.texel))
+    img, _ = run_once_with_output(c, pool, [(inp, bg.key())], output)
+    got = rgba(img)
+    hsh = O.blockhash256(got)
+    dist = min(bin(int(hsh, 16) ^ int(g, 16)).count("1") for g in hashes()["flat_field"])
+    assert dist <= 4, (hsh, hashes()["flat_field"])
+    # against the oracle: the noise through its Luma8 register (staged: sRGB OETF, truncating pack; decoded luma in .x)
+    field = O.decode(O.distribution_fractal_noise(oracle_desc(flat_desc), [10.0, 10.0, 0.1, 0.2, 8]))
+    src = O.decode(oracle_image(d, fixtures["background"]))
+    with np.errstate(all="ignore"):
+        e = np.float32(0.124 / 2.0) / field[..., 0]
+    tex = src.copy()
+    for ch in range(3):
+        tex[..., ch] = src[..., ch] * e
+    exp = O.encode(O.srgb_rgba8(512, 512), tex).data.reshape(512, 512, 4)
+    assert np.mean(np.abs(got.astype(int) - exp.astype(int)) <= 1) > 0.999
