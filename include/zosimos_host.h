@@ -53,6 +53,7 @@ void zosh_cb_free(zosh_cb* cb);
 /* every builder returns ZOSH_OK and the new register in *reg, or an error kind */
 int32_t zosh_cb_input(zosh_cb* cb, const zos_desc* desc, int32_t* reg);                               /* command.rs:743 */
 int32_t zosh_cb_output(zosh_cb* cb, int32_t src, int32_t* reg);                                      /* command.rs:1707 */
+uint32_t zosh_cb_num_ops(const zosh_cb* cb);                                                         /* number of operations pushed so far */
 int32_t zosh_cb_describe(const zosh_cb* cb, int32_t reg, zos_desc* out);                             /* describe_reg */
 int32_t zosh_cb_color_convert(zosh_cb* cb, int32_t src, const zos_desc* color_and_texel, int32_t* reg); /* command.rs:986 */
 int32_t zosh_cb_chromatic_adaptation(zosh_cb* cb, int32_t src, uint32_t method, uint32_t target_wp, int32_t* reg); /* :1112 */

@@ -629,3 +629,46 @@ def test_dynamic_flat_field(pool, images, fixtures):  # tests/custom.rs:188-290:
         tex[..., ch] = src[..., ch] * e
     exp = O.encode(O.srgb_rgba8(512, 512), tex).data.reshape(512, 512, 4)
     assert np.mean(np.abs(got.astype(int) - exp.astype(int)) <= 1) > 0.999
+
+
+def test_generic_palette_function(pool, images, fixtures):  # tests/generic.rs: a generic callee, invoked and linked
+    from zosimos_b200.command import GenericDeclaration, InvocationArguments, CommandError
+    bg, _ = images
+    ramp = Bilinear([0] * 4, [0] * 4, [0] * 4, [0] * 4, [0] * 4, [1, 1, 0, 0])
+    idx_desc = Descriptor.with_texel(Texel.new_u8(SampleParts.RgbA), 2048, 2048)
+
+    fixed_palette = CommandBuffer()
+    in_a = fixed_palette.generic(GenericDeclaration(bounds=()))
+    img_input = fixed_palette.input_generic(in_a)
+    img_idx = fixed_palette.bilinear(idx_desc, ramp)
+    img_palette = fixed_palette.palette(img_input, Palette(height=Z.ColorChannel.R, width=Z.ColorChannel.G), img_idx)
+    fixed_palette.output(img_palette)
+    sig = fixed_palette.computed_signature()
+    assert (sig.num_generics, sig.num_inputs, sig.num_outputs) == (1, 1, 1)
+
+    main = CommandBuffer()
+    converter = main.function(sig)
+    inp = main.input(Descriptor.with_srgb_image("rgba8", 512, 512))
+    ty = main.register_descriptor(inp)
+    with pytest.raises(CommandError):   # wrong number of generics
+        main.invoke(converter, InvocationArguments(generics=[], arguments=[inp]))
+    with pytest.raises(CommandError):   # the argument does not have the bound type
+        main.invoke(converter, InvocationArguments(generics=[idx_desc], arguments=[inp]))
+    (img_output,) = main.invoke(converter, InvocationArguments(generics=[ty], arguments=[inp]))
+    output, _ = main.output(img_output)
+    with pytest.raises(CommandError):   # link tables must name the invoked function
+        Linker.from_included().link(main, [], [fixed_palette], [[2], []])
+    plan = Linker.from_included().link(main, [], [fixed_palette], [[1], []])
+    executable = plan.lower_to(Capabilities.from_device(next(pool.iter_devices())))
+    img, _ = run_executable_with_output(executable, pool, [(inp, bg.key())], output)
+    got = rgba(img)
+    assert got.shape == (2048, 2048, 4)
+    # the same pipeline written without the function
+    c = CommandBuffer()
+    i2 = c.input(bg.descriptor())
+    o2, _ = c.output(c.palette(i2, Palette(height=Z.ColorChannel.R, width=Z.ColorChannel.G), c.bilinear(idx_desc, ramp)))
+    direct, _ = run_once_with_output(c, pool, [(i2, bg.key())], o2)
+    assert np.array_equal(got, rgba(direct))
+    hsh = O.blockhash256(got)
+    dist = min(bin(int(hsh, 16) ^ int(g, 16)).count("1") for g in hashes()["generic"])
+    assert dist <= 6, (hsh, hashes()["generic"])   # the reference lists two device-dependent hashes for this pipeline

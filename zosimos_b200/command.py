@@ -69,6 +69,7 @@ _HOST_SIGNATURES = {
     "zosh_cb_transmute": (C.c_int32, [_P, C.c_int32, C.POINTER(_ffi.ZosDesc), C.POINTER(C.c_int32)]),
     "zosh_cb_bilinear": (C.c_int32, [_P, C.POINTER(_ffi.ZosDesc), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "zosh_cb_solid_rgba": (C.c_int32, [_P, C.POINTER(_ffi.ZosDesc), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "zosh_cb_num_ops": (C.c_uint32, [_P]),
     "zosh_cb_dynamic": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_char_p, C.POINTER(_ffi.ZosDesc), C.c_void_p, C.c_uint64, C.POINTER(C.c_int32)]),
     "zosh_cb_buffer_init": (C.c_int32, [_P, C.c_void_p, C.c_uint64, C.POINTER(C.c_int32)]),
     "zosh_cb_buffer_zero": (C.c_int32, [_P, C.c_uint64, C.POINTER(C.c_int32)]),
@@ -335,6 +336,78 @@ class CommandBuffer:
         except Exception:
             pass
 
+    # -- functions and generics
+    _record = None
+    _num_generics = 0
+
+    def generic(self, declaration: "GenericDeclaration" = None) -> "GenericVar":  # command.rs:856-870
+        if self._record is None:
+            if host_lib().zosh_cb_num_ops(self._h) != 0:
+                raise CommandError(4, "generics must be declared before the first operation")
+            self._record = []
+            for name in _TEMPLATE_METHODS:  # from now on operations are recorded, not built
+                setattr(self, name, self._recorder(name))
+        self._num_generics += 1
+        return GenericVar(self._num_generics - 1)
+
+    def _recorder(self, name):
+        def record(*args, **kwargs):
+            self._record.append((name, args, kwargs))
+            r = _SymReg(len(self._record) - 1)
+            return (r, None) if name == "output" else r
+        return record
+
+    def input_generic(self, var: "GenericVar") -> Register:  # command.rs:872-884
+        if self._record is None or not (0 <= var.index < self._num_generics):
+            raise CommandError(4, "input_generic: unknown generic")
+        self._record.append(("input_generic", (var,), {}))
+        return _SymReg(len(self._record) - 1)
+
+    def computed_signature(self) -> "FunctionSignature":  # command.rs:886-905
+        if self._record is None:
+            self._record = []
+            raise CommandError(5, "signatures of non-generic command buffers are not supported")
+        return FunctionSignature(self)
+
+    def function(self, signature: "FunctionSignature") -> "FunctionVar":  # command.rs:907-922
+        self._functions = list(getattr(self, "_functions", []))
+        self._functions.append(signature)
+        return FunctionVar(len(self._functions) - 1)
+
+    _functions = ()
+
+    def register_descriptor(self, reg: Register) -> Descriptor:  # the concrete type bound to a generic
+        return self.describe_reg(reg)
+
+    def invoke(self, function: "FunctionVar", arguments: "InvocationArguments") -> List[Register]:  # command.rs:2821-2869
+        if not (0 <= function.index < len(self._functions)):
+            raise CommandError(4, "invoke: unknown function")
+        sig = self._functions[function.index]
+        if len(arguments.generics) != sig.num_generics or len(arguments.arguments) != sig.num_inputs:
+            raise CommandError(3, "invoke: %d generics / %d arguments expected (CommandError::TYPE_ERR)" % (sig.num_generics, sig.num_inputs))
+        mapping, outputs, nxt = {}, [], 0
+
+        def subst(v):
+            if isinstance(v, _SymReg):
+                return mapping[v.index]
+            if isinstance(v, (list, tuple)) and any(isinstance(x, _SymReg) for x in v):
+                return type(v)(subst(x) for x in v)
+            return v
+
+        for pos, (name, args, kwargs) in enumerate(sig.template._record):
+            if name in ("input", "input_generic"):
+                real = arguments.arguments[nxt]; nxt += 1
+                have = self.describe_reg(real)
+                want = arguments.generics[args[0].index] if name == "input_generic" else args[0]
+                if (have.size(), have.texel, have.color) != (want.size(), want.texel, want.color):
+                    raise CommandError(3, "invoke: argument %d does not have the declared type (CommandError::TYPE_ERR)" % (nxt - 1))
+                mapping[pos] = real
+            elif name == "output":
+                outputs.append(subst(args[0]))
+            else:
+                mapping[pos] = getattr(CommandBuffer, name)(self, *[subst(a) for a in args], **{k: subst(v) for k, v in kwargs.items()})
+        return outputs
+
     # -- plumbing
     def _reg(self, st: int, out: C.c_int32) -> Register:
         _check(st)
@@ -518,6 +591,52 @@ class WithBuffer:  # command.rs:1963-2060: the next operation's parameter block 
         return self._cb._reg(host_lib().zosh_cb_with_buffer_bilinear(self._cb._h, self._buf.index, C.byref(d), C.byref(out)), out)
 
 
+# ---- functions and generics (command.rs:856-922, 2083-2185, 2821-2869; tests/generic.rs) -------------------
+# A command buffer that declares a generic becomes a TEMPLATE: its operations are recorded, not built, because
+# their descriptors depend on the types the caller binds.  `invoke` monomorphises: it replays the callee's
+# record into the caller with the generic inputs replaced by the argument registers (the reference does the
+# same at link time, command.rs:2083-2185; here the callee travels inside the signature object, and
+# `Linker.link` checks that the linked functions are the ones that were invoked).
+@dataclass(frozen=True)
+class GenericDeclaration:
+    bounds: Sequence = ()
+
+
+@dataclass(frozen=True)
+class GenericVar:
+    index: int
+
+
+@dataclass(frozen=True)
+class FunctionVar:
+    index: int
+
+
+@dataclass(frozen=True)
+class InvocationArguments:
+    generics: Sequence[Descriptor]
+    arguments: Sequence[Register]
+
+
+@dataclass(frozen=True)
+class _SymReg(Register):
+    """A register of a template command buffer (position in its record)."""
+
+
+class FunctionSignature:
+    def __init__(self, template: "CommandBuffer"):
+        self.template = template
+        self.num_generics = template._num_generics
+        self.num_inputs = sum(1 for r in template._record if r[0] in ("input", "input_generic"))
+        self.num_outputs = sum(1 for r in template._record if r[0] == "output")
+
+
+_TEMPLATE_METHODS = ("input", "output", "color_convert", "chromatic_adaptation", "inscribe", "crop", "affine", "resize", "blend",
+                     "transmute", "bilinear", "solid_rgba", "derivative", "palette", "extract", "inject", "distribution_normal2d",
+                     "distribution_fractal_noise", "construct_dynamic", "unary_dynamic", "binary_dynamic", "buffer_init", "buffer_zero",
+                     "from_buffer")
+
+
 class Linker:
     """command.rs:38-41, 2069: the reference's Linker carries the SPIR-V blobs; this one needs nothing
     (the kernels live in libzosimos_cuda.so)."""
@@ -525,6 +644,25 @@ class Linker:
     @staticmethod
     def from_included() -> "Linker":
         return Linker()
+
+    def link(self, main: "CommandBuffer", tys: Sequence[Descriptor], functions: Sequence["CommandBuffer"], links: Sequence[Sequence[int]]) -> "Program":
+        """command.rs:2083-2185: program 0 is `main`, program k >= 1 is functions[k - 1]; links[p][f] names the
+        program that function variable f of program p calls.  Calls were monomorphised by `invoke`, so linking
+        verifies the wiring and compiles `main`."""
+        if tys:
+            raise CommandError(5, "generic entry points are not supported (CommandError::UNIMPLEMENTED)")
+        if len(links) != 1 + len(functions):
+            raise CommandError(4, "link: one link table per program")
+        for p, table in enumerate(links):
+            decl = main._functions if p == 0 else functions[p - 1]._functions
+            if len(table) != len(decl):
+                raise CommandError(4, "link: program %d declares %d functions, %d linked" % (p, len(decl), len(table)))
+            for f, target in enumerate(table):
+                if not (1 <= target <= len(functions)):
+                    raise CommandError(4, "link: bad function index %d" % target)
+                if functions[target - 1] is not decl[f].template:
+                    raise CommandError(3, "link: function %d of program %d has another signature (CommandError::TYPE_ERR)" % (f, p))
+        return self.compile(main)
 
     def compile(self, commands: CommandBuffer) -> "Program":
         from .program import Program

@@ -188,6 +188,7 @@ int32_t zosh_cb_with_knob(zosh_cb* cb) {
   return (int32_t)cb->pending_knob;
 }
 
+uint32_t zosh_cb_num_ops(const zosh_cb* cb) { return cb ? (uint32_t)cb->ops.size() : 0; }
 int32_t zosh_cb_describe(const zosh_cb* cb, int32_t reg, zos_desc* out) {
   if (!cb || !out || !valid_reg(cb, reg)) return err(ZOSH_ERR_OTHER, "bad register");
   *out = cb->ops[reg].desc;
