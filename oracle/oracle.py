@@ -151,7 +151,7 @@ def storage_fmt(d: Desc) -> Fmt:
     if c.model in ("rgb", "scalars"):
         if t.bits in (B_FLOAT16X4, B_FLOAT32X4):
             return Fmt(c.transfer, t.parts, t.bits, ST_FLOAT)  # OURS (reference: todo!())
-        if t.bytes not in (1, 2, 4):
+        if t.bytes not in (1, 2, 4) and t.bits != B_UINT16X4:  # UInt16x4: OURS (declared, never defined in stage.frag)
             raise ValueError("unsupported staged texel (stage.rs:63-72)")
         return Fmt(c.transfer, t.parts, t.bits, ST_STAGED)
     if c.model in ("oklab", "srlab2") and t.parts in (P_LCHA, P_LABA):

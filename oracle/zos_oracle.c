@@ -347,6 +347,14 @@ static void decode_texel(const zo_fmt* f, const uint8_t* p, float* o) {
     default: {
       uint32_t n = 0;
       int nb = bits_bytes(f->bits);
+      if (f->bits == B_INT16X4) { /* OURS: the reference declares decode_rgba16ui (shaders/stage.rs:158) but stage.frag never defines it */
+        float c[4], e[4];
+        for (int i = 0; i < 4; i++) { uint16_t v; memcpy(&v, p + 2 * i, 2); c[i] = (float)v / 65535.0f; }
+        parts_norm(c, f->parts, e);
+        transfer_apply(f->transfer, e, 0);
+        for (int i = 0; i < 4; i++) o[i] = f16r(e[i]);
+        return;
+      }
       if (nb < 1 || nb > 4 || nb == 3) { memcpy(o, FAIL_DEC, 16); return; }
       memcpy(&n, p, nb); /* little endian sub-word of the R32Uint staging texel */
       float c[4], e[4];
@@ -379,6 +387,14 @@ static void encode_texel(const zo_fmt* f, const float* t, uint8_t* p) {
     }
     default: {
       int nb = bits_bytes(f->bits);
+      if (f->bits == B_INT16X4) { /* OURS, the mirror image of the decode above: f16 attachment, transfer, clamp, truncation */
+        float e[4], c[4];
+        for (int i = 0; i < 4; i++) e[i] = f16r(t[i]);
+        transfer_apply(f->transfer, e, 1);
+        parts_denorm(e, f->parts, c);
+        for (int i = 0; i < 4; i++) { uint16_t v = (uint16_t)(uint32_t)(clamp01(c[i]) * 65535.0f); memcpy(p + 2 * i, &v, 2); }
+        return;
+      }
       if (nb < 1 || nb > 4 || nb == 3) return;
       float e[4], c[4];
       for (int i = 0; i < 4; i++) e[i] = f16r(t[i]); /* the draw wrote an Rgba16Float attachment */

@@ -39,7 +39,7 @@ STAGED_LINEAR = [
     (SampleBits.UInt565, SampleParts.Rgb), (SampleBits.UInt565, SampleParts.Bgr), (SampleBits.UInt4x4, SampleParts.RgbA),
     (SampleBits.UInt332, SampleParts.Rgb), (SampleBits.UInt233, SampleParts.Bgr), (SampleBits.UInt8, SampleParts.Luma),
     (SampleBits.UInt8, SampleParts.A), (SampleBits.UInt8x2, SampleParts.LumaA), (SampleBits.UInt16, SampleParts.Luma),
-    (SampleBits.UInt16x2, SampleParts.LumaA),
+    (SampleBits.UInt16x2, SampleParts.LumaA), (SampleBits.UInt16x4, SampleParts.RgbA), (SampleBits.UInt16x4, SampleParts.BgrA),
 ]
 
 

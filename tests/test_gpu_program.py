@@ -672,3 +672,15 @@ def test_generic_palette_function(pool, images, fixtures):  # tests/generic.rs: 
     hsh = O.blockhash256(got)
     dist = min(bin(int(hsh, 16) ^ int(g, 16)).count("1") for g in hashes()["generic"])
     assert dist <= 6, (hsh, hashes()["generic"])   # the reference lists two device-dependent hashes for this pipeline
+
+
+@pytest.mark.parametrize("kind", ["rgba8", "rgba16", "luma8", "luma_a16"])
+def test_descriptor_as_gpu_texture(pool, kind):  # tests/color_support.rs: input -> output of zeros in the descriptor's own texel
+    desc = Descriptor.with_srgb_image(kind, 4, 4)
+    key = pool.insert(desc, np.zeros(4 * 4 * desc.layout.texel_stride, np.uint8)).key()
+    c = CommandBuffer()
+    inp = c.input(desc)
+    output, out_desc = c.output(inp)
+    assert (out_desc.texel, out_desc.color, out_desc.size()) == (desc.texel, desc.color, desc.size())
+    img, _ = run_once_with_output(c, pool, [(inp, key)], output)
+    assert img.as_bytes().size == 4 * 4 * desc.layout.texel_stride and not img.as_bytes().any()

@@ -239,14 +239,14 @@ zos_status zos_desc_texfmt(const zos_desc* d, zos_texfmt* out) {
   }
   if (rgb || scalars) {
     if (flt) { *out = zos_texfmt{d->transfer, d->parts, d->bits, ZOS_STORAGE_FLOAT}; return ZOS_OK; }
-    if (bytes != 1 && bytes != 2 && bytes != 4) return ZOS_ERR_UNSUPPORTED;  // stage.rs:63-72
+    if (bytes != 1 && bytes != 2 && bytes != 4 && d->bits != ZOS_BITS_UINT16X4) return ZOS_ERR_UNSUPPORTED;  // stage.rs:63-72 (+ UInt16x4, ours)
     *out = zos_texfmt{d->transfer, d->parts, d->bits, ZOS_STORAGE_STAGED};
     return ZOS_OK;
   }
   if ((d->color == ZOS_COLOR_OKLAB || d->color == ZOS_COLOR_SRLAB2) && (d->parts == ZOS_PARTS_LCHA || d->parts == ZOS_PARTS_LABA)) {
     uint32_t tr = d->parts == ZOS_PARTS_LCHA ? (uint32_t)ZOS_TRANSFER_LABLCH : (uint32_t)ZOS_TRANSFER_LINEAR;
     if (flt) { *out = zos_texfmt{tr, ZOS_PARTS_LCHA, d->bits, ZOS_STORAGE_FLOAT}; return ZOS_OK; }
-    if (bytes != 1 && bytes != 2 && bytes != 4) return ZOS_ERR_UNSUPPORTED;
+    if (bytes != 1 && bytes != 2 && bytes != 4 && d->bits != ZOS_BITS_UINT16X4) return ZOS_ERR_UNSUPPORTED;
     *out = zos_texfmt{tr, ZOS_PARTS_LCHA, d->bits, ZOS_STORAGE_STAGED};  // program.rs:882-890
     return ZOS_OK;
   }

@@ -286,7 +286,11 @@ static __device__ ZOS_SLOW_ATTR float4 unpack_slow(zos_texfmt f, uint4 w, const 
       return c;
     }
     default: {
-      float4 c = parts_norm(demux(w.x, f.bits, T), f.parts);
+      // UInt16x4 (8 bytes): ours -- the reference declares decode_rgba16ui / encode_rgba16ui (shaders/stage.rs:148-158)
+      // but stage.frag never defines them; same pipeline as every staged texel, fields of 16 bits
+      float4 d = f.bits == ZOS_BITS_UINT16X4 ? make_float4(fld(w.x & 65535u, 65535.0f), fld(w.x >> 16, 65535.0f), fld(w.y & 65535u, 65535.0f), fld(w.y >> 16, 65535.0f))
+                                            : demux(w.x, f.bits, T);
+      float4 c = parts_norm(d, f.parts);
       transfer_decode(f.transfer, c);
       return make_float4(f16r(c.x), f16r(c.y), f16r(c.z), f16r(c.w));
     }
@@ -322,6 +326,11 @@ static __device__ ZOS_SLOW_ATTR uint4 pack_slow(zos_texfmt f, float4 v, const Ta
       transfer_encode(f.transfer, v);
       float4 c = parts_denorm(v, f.parts);
       c = make_float4(clamp01(c.x), clamp01(c.y), clamp01(c.z), clamp01(c.w));
+      if (f.bits == ZOS_BITS_UINT16X4) {
+        w.x = qz(c.x, 65535.0f) + (qz(c.y, 65535.0f) << 16);
+        w.y = qz(c.z, 65535.0f) + (qz(c.w, 65535.0f) << 16);
+        return w;
+      }
       w.x = mux(c, f.bits);
       return w;
     }
