@@ -347,12 +347,10 @@ zos_status launch_affine_f16(zos_ctx* ctx, const DevImage* below, const DevImage
   if (!make_map(ctx, &M.m0, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, above.p0, (uint64_t)above.w * 2, above.h, above.pitch, batch, above.bstride,
                 (uint32_t)P.box_w * 2, (uint32_t)P.box_h))
     return ZOS_OK;
-  int group = 2;
-  if (const char* e = getenv("ZOS_AFFINE_GROUP")) group = atoi(e);
+  const int group = 2;  // rows of a thread set up together; 4 needs 80 registers (3 CTAs per SM) and measured slower
   int per_sm = (int)((228 * 1024) / (smem + 1024 + 256));
   const int max_ctas = group == 4 ? 3 : 5;
   per_sm = per_sm < 1 ? 1 : (per_sm > max_ctas ? max_ctas : per_sm);
-  if (const char* e = getenv("ZOS_AFFINE_CTAS")) per_sm = atoi(e);
   const uint64_t cap = (uint64_t)ctx->sm_count * per_sm;
   const int grid = (int)(total < cap ? total : cap);
 #define ZOS_AFF_LAUNCH(B, G, C)                                                                          \

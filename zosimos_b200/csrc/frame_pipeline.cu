@@ -533,7 +533,7 @@ zos_status launch_frame_pipeline(zos_ctx* ctx, const DevImage* below, const DevI
   const int trk = (tr == ZOS_TRANSFER_BT709 || tr == ZOS_TRANSFER_BT2020_10BIT || tr == ZOS_TRANSFER_BT2020_12BIT) ? 0 : tr == ZOS_TRANSFER_LINEAR ? 1 : 2;
   const bool same_texel = !below || (below->fmt.storage == dst.fmt.storage && below->fmt.parts == dst.fmt.parts);
   const bool rgba_like = dst.fmt.parts == ZOS_PARTS_RGBA || dst.fmt.parts == ZOS_PARTS_BGRA;
-  if (trk != 2 && same_texel && rgba_like && !getenv("ZOS_FRAME_GENERIC")) {
+  if (trk != 2 && same_texel && rgba_like) {
     const bool srgb = dst.fmt.storage == ZOS_STORAGE_SRGB8;
     const bool bgra = dst.fmt.parts == ZOS_PARTS_BGRA;
     P.clear_word = bgra ? 0xff0000ffu : 0xffff0000u;  // (0, 0, 1, 1): both codecs map 0 -> 0 and 1 -> 255

@@ -65,8 +65,7 @@ static inline bool make_map(zos_ctx* ctx, CUtensorMap* m, CUtensorMapDataType dt
   cuuint64_t strides[2] = {pitch, frames > 1 ? frame_stride : pitch * h};
   cuuint32_t box[3] = {box_w_elems, box_h, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
-  if (const char* e = getenv("ZOS_TMA_L2_PROMOTION")) promo = (CUtensorMapL2promotion)atoi(e);  // experiment knob: 0 none, 1 64B, 2 128B, 3 256B
+  const CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;  // none / 64 B / 256 B measured the same within noise
   CUresult r = enc(m, dt, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
