@@ -261,6 +261,7 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_affine_f16(const __grid_const
     mbar_init(&bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __syncthreads();  // the barriers exist before anybody (thread 0 included) arms or polls them
   const CUtensorMap* const m0 = &M.m0;  // stays in param space (see gather.cu)
 #define ZOS_AFF_ISSUE(TILE_INDEX, STAGE)                                                         \
   do {                                                                                            \

@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(THREADS, 3) k_frame_pipeline(const __grid_cons
     mbar_init(&bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __syncthreads();  // the barriers exist before anybody (thread 0 included) arms or polls them
   const CUtensorMap* const m0 = &M.m0;
   const CUtensorMap* const m1 = &M.m1;
   const CUtensorMap* const m2 = &M.m2;
@@ -344,6 +345,7 @@ __global__ void __launch_bounds__(THREADS, 3) k_frame_fast(const __grid_constant
     mbar_init(&bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __syncthreads();  // the barriers exist before anybody (thread 0 included) arms or polls them
   const CUtensorMap* const m0 = &M.m0;
   const CUtensorMap* const m1 = &M.m1;
   const CUtensorMap* const m2 = &M.m2;
