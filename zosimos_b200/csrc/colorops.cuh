@@ -30,7 +30,7 @@ __device__ __forceinline__ float3 mat3_mul(const float* M, float x, float y, flo
 }
 __device__ __forceinline__ float cbrt_signed(float v) {
   // pow(abs(v), 1/3) * sign(v), oklab.frag:43
-  float r = exp2f(__log2f(fabsf(v)) * (1.0f / 3.0f));
+  float r = pow_fast(fabsf(v), 1.0f / 3.0f);  // lg2.approx / ex2.approx on the SFU, like every other pow of the path
   return v == 0.0f ? 0.0f : copysignf(r, v);
 }
 __device__ __forceinline__ float sr_nl(float v) {

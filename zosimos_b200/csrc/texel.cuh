@@ -129,13 +129,43 @@ __device__ __forceinline__ float eo_scalar(uint32_t tr, float v) {
 }
 
 #define ZOS_PI_F 3.14159265358979323846f
+// atan2 and sqrt for the Lab <-> LCh form (stage.frag:415-425).  GLSL leaves the precision of atan / sqrt to the
+// device; the library versions cost ~45 and ~10 instructions with slow-path branches.  These cost ~22 and 2:
+// odd minimax polynomial of degree 15 on [0, 1] (max error 4e-8 rad before rounding, i.e. the accuracy class of
+// atan2f) after the usual octant reduction, and the SFU's rsqrt-based approximation.
+__device__ __forceinline__ float atan2_fast(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(mx));
+  const float t = mx > 0.0f ? mn * r : 0.0f;
+  const float s = t * t;
+  float p = -0.004054565913975239f;
+  p = fmaf(p, s, 0.021862953901290894f);
+  p = fmaf(p, s, -0.0559123232960701f);
+  p = fmaf(p, s, 0.0964219719171524f);
+  p = fmaf(p, s, -0.1390862911939621f);
+  p = fmaf(p, s, 0.19946566224098206f);
+  p = fmaf(p, s, -0.33329859375953674f);
+  p = fmaf(p, s, 0.9999993443489075f);
+  p = p * t;
+  if (ay > ax) p = 1.57079632679489662f - p;
+  if (x < 0.0f) p = 3.14159265358979324f - p;
+  return copysignf(p, y);
+}
+__device__ __forceinline__ float sqrt_fast(float v) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+
 // parts_transfer / parts_untransfer (stage.frag:750-809): rgb through the curve, alpha untouched
 __device__ __forceinline__ void transfer_encode(uint32_t tr, float4& c) {
   if (tr == ZOS_TRANSFER_LINEAR) return;
   if (tr == ZOS_TRANSFER_LABLCH) {  // stage.frag:415-420
     float a = c.y, b = c.z;
-    c.y = sqrtf(a * a + b * b);
-    c.z = (atan2f(b, a) * (180.0f / ZOS_PI_F)) / 360.0f + 0.5f;
+    c.y = sqrt_fast(a * a + b * b);
+    c.z = (atan2_fast(b, a) * (180.0f / ZOS_PI_F)) / 360.0f + 0.5f;
     return;
   }
   c.x = oe_scalar(tr, c.x); c.y = oe_scalar(tr, c.y); c.z = oe_scalar(tr, c.z);
