@@ -38,7 +38,7 @@ struct AffParams {
   float inv[6];
   int32_t dox, doy, sox, soy, sfw, sfh;
   uint32_t tiles_x, tiles_y, total_tiles;
-  FastDiv div_tx, div_ty;
+  FastDiv div_frame, div_band;  // tiles per frame, tiles per band of 8 tile rows
   int32_t box_w, box_h;
   int* fault;  // mapped host word set when an mbarrier wait runs away
 };
@@ -60,10 +60,14 @@ __device__ __forceinline__ void map_point(const AffParams& P, float cx, float cy
 
 // the bounding box of the tile's taps (the same construction as gather.cu's tile_info)
 __device__ void tile_geometry(const AffParams& P, uint32_t t, Geo& g) {
-  uint32_t r = fastdiv(t, P.div_tx);
-  uint32_t txi = t - r * P.tiles_x;
-  uint32_t fr = fastdiv(r, P.div_ty);
-  uint32_t tyi = r - fr * P.tiles_y;
+  // tiles are walked in bands of 8 tile rows, column by column inside a band: the ~700 tiles in flight at any
+  // time then form a compact 2-D block whose source footprints overlap in L2 instead of three full-width strips
+  const uint32_t per_frame = P.tiles_x * P.tiles_y;
+  const uint32_t fr = fastdiv(t, P.div_frame), tf = t - fr * per_frame;
+  const uint32_t band_tiles = 8u * P.tiles_x;
+  const uint32_t band = fastdiv(tf, P.div_band), in_band = tf - band * band_tiles;
+  const uint32_t rows = min(8u, P.tiles_y - band * 8u);
+  const uint32_t txi = rows == 8u ? in_band >> 3 : in_band / rows, tyi = band * 8u + (in_band - txi * rows);
   g.frame = (int)fr; g.x0 = (int)txi * TILE; g.y0 = (int)tyi * TILE;
   g.bx = g.by = 0; g.fits = 0; g.any = 0;
   const int x1 = min(g.x0 + TILE, P.dw) - 1, y1 = min(g.y0 + TILE, P.dh) - 1;
@@ -332,7 +336,7 @@ zos_status launch_affine_f16(zos_ctx* ctx, const DevImage* below, const DevImage
   const uint64_t total = (uint64_t)P.tiles_x * P.tiles_y * batch;
   if (total == 0 || total >= (1ull << 31)) return ZOS_OK;
   P.total_tiles = (uint32_t)total;
-  P.div_tx = make_fastdiv(P.tiles_x); P.div_ty = make_fastdiv(P.tiles_y);
+  P.div_frame = make_fastdiv(P.tiles_x * P.tiles_y); P.div_band = make_fastdiv(8u * P.tiles_x);
   const float ex = (TILE - 1) * (fabsf(P.inv[0]) + fabsf(P.inv[1])), ey = (TILE - 1) * (fabsf(P.inv[3]) + fabsf(P.inv[4]));
   if (!(ex < 200.0f) || !(ey < 200.0f)) return ZOS_OK;
   // taps span ceil(extent) + 4 texels, + 1 for the even box origin; a row of 8 * (4k + 2) bytes puts
