@@ -5,10 +5,10 @@
 // (zo_paint_affine_window): identical coordinate arithmetic (fmaf order of map_point), identical
 // tap clamping and lerp order.  What is different is the instruction count per pixel:
 //
-//   * a CTA produces 32x32 destination tiles (persistent, grid-stride); the source bounding box of
-//     the NEXT tile is fetched by one TMA bulk tensor copy while the current tile is computed;
-//   * tile geometry (4 corner mappings, box origin, alignment) is computed by ONE thread and
-//     broadcast through shared memory instead of by all 256;
+//   * a CTA produces 32x32 destination tiles (persistent, grid-stride, tiles walked in compact 2-D bands);
+//     a dedicated PRODUCER warp works out each tile's geometry (4 corner mappings, box origin, alignment),
+//     publishes it in shared memory and issues ONE TMA bulk tensor copy for the tile's source bounding box,
+//     up to 3 tiles ahead; full / empty mbarriers per stage, no CTA-wide barrier in the loop;
 //   * the x half of the inverse mapping is hoisted out of the 4-row loop of a thread, coverage of a
 //     covered pixel bounds its taps so each clamp is one instruction, taps are LDS.64 at 32-bit
 //     shared addresses, rows of a thread are fully unrolled so their 16 loads are in flight together.
@@ -253,54 +253,66 @@ __device__ __forceinline__ void compute_tile_global(const AffParams& P, const Ge
   }
 }
 
+// Warp-specialised pipeline: warps 0..7 compute tiles, warp 8 (one lane) is the producer.  The producer runs
+// up to STAGES tiles ahead: it works out the next tile's geometry, publishes it in shared memory and issues the
+// TMA load; `full[s]` completes when the box has landed (or at once for tiles that need none).  A consumer warp
+// that is done with stage s arrives on `empty[s]` (8 arrivals free the stage).  There is no CTA-wide barrier in
+// the loop: warps drift apart by up to STAGES tiles, and the ~250 serial instructions of the geometry are off
+// the compute warps' critical path.
+constexpr int STAGES = 3;
+constexpr int CONSUMER_WARPS = THREADS / 32;
+constexpr int THREADS_ALL = THREADS + 32;
+
 template <bool BILINEAR, int GROUP, int CTAS>
-__global__ void __launch_bounds__(THREADS, CTAS) k_affine_f16(const __grid_constant__ AffParams P, const __grid_constant__ TensorMaps M) {
+__global__ void __launch_bounds__(THREADS_ALL, CTAS) k_affine_f16(const __grid_constant__ AffParams P, const __grid_constant__ TensorMaps M) {
   extern __shared__ __align__(128) uint8_t dyn[];
-  __shared__ __align__(8) uint64_t bar[2];
-  __shared__ Geo geo[2];
+  __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES];
+  __shared__ Geo geo[STAGES];
   const uint32_t box_bytes = (uint32_t)P.box_w * P.box_h * 8u;
   const uint32_t stage_bytes = (box_bytes + 127u) & ~127u;
   if (threadIdx.x == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], CONSUMER_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();  // the barriers exist before anybody (thread 0 included) arms or polls them
+  __syncthreads();  // the barriers exist before anybody arms or polls them
   const CUtensorMap* const m0 = &M.m0;  // stays in param space (see gather.cu)
-#define ZOS_AFF_ISSUE(TILE_INDEX, STAGE)                                                         \
-  do {                                                                                            \
-    Geo g_;                                                                                       \
-    tile_geometry(P, (TILE_INDEX), g_);                                                           \
-    geo[(STAGE)] = g_;                                                                            \
-    if (g_.any && g_.fits) {                                                                      \
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                              \
-      mbar_expect_tx(&bar[(STAGE)], box_bytes);                                                   \
-      tma_load_3d(dyn + (size_t)(STAGE) * stage_bytes, m0, g_.bx * 2, g_.by, g_.frame, &bar[(STAGE)]); \
-    }                                                                                             \
-  } while (0)
-  if (threadIdx.x == 0 && blockIdx.x < P.total_tiles) ZOS_AFF_ISSUE(blockIdx.x, 0);
-  __syncthreads();
-  uint32_t phase[2] = {0, 0};
-  int s = 0;
-  for (uint32_t t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
-    const uint32_t next = t + gridDim.x;
-    if (threadIdx.x == 0 && next < P.total_tiles) ZOS_AFF_ISSUE(next, s ^ 1);
-    const Geo g = geo[s];
-    if (g.any && g.fits) {
-      uint32_t spins = 0;
-      while (!mbar_try_wait(&bar[s], phase[s])) {
-        if (++spins > (1u << 24)) { if (P.fault) *reinterpret_cast<volatile int*>(P.fault) = 1; break; }
+  const uint32_t warp = threadIdx.x >> 5;
+  uint32_t it = 0;
+  if (warp == CONSUMER_WARPS) {
+    if ((threadIdx.x & 31) != 0) return;
+    for (uint32_t t = blockIdx.x; t < P.total_tiles; t += gridDim.x, it++) {
+      const uint32_t s = it % STAGES, round = it / STAGES;
+      if (round > 0) {  // wait until the consumers have released the stage's previous tile
+        uint32_t spins = 0;
+        while (!mbar_try_wait(&empty[s], (round - 1) & 1)) {
+          if (++spins > (1u << 26)) { if (P.fault) *reinterpret_cast<volatile int*>(P.fault) = 1; break; }
+        }
       }
-      phase[s] ^= 1;
-      compute_tile_smem<BILINEAR, GROUP>(P, g, smem_u32(dyn + (size_t)s * stage_bytes));
-    } else {
-      // no covered pixel (copies `below`), or a footprint larger than the box (strong minification): global taps
-      compute_tile_global<BILINEAR>(P, g);
+      Geo g_;
+      tile_geometry(P, t, g_);
+      geo[s] = g_;
+      if (g_.any && g_.fits) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&full[s], box_bytes);
+        tma_load_3d(dyn + (size_t)s * stage_bytes, m0, g_.bx * 2, g_.by, g_.frame, &full[s]);
+      } else {
+        mbar_arrive(&full[s]);  // nothing to load: the geometry alone is the payload
+      }
     }
-    __syncthreads();  // stage s is free again; geo[s ^ 1] (written by thread 0 above) is visible
-    s ^= 1;
+    return;
   }
-#undef ZOS_AFF_ISSUE
+  for (uint32_t t = blockIdx.x; t < P.total_tiles; t += gridDim.x, it++) {
+    const uint32_t s = it % STAGES, round = it / STAGES;
+    uint32_t spins = 0;
+    while (!mbar_try_wait(&full[s], round & 1)) {
+      if (++spins > (1u << 26)) { if (P.fault) *reinterpret_cast<volatile int*>(P.fault) = 1; break; }
+    }
+    const Geo g = geo[s];
+    if (g.any && g.fits) compute_tile_smem<BILINEAR, GROUP>(P, g, smem_u32(dyn + (size_t)s * stage_bytes));
+    else compute_tile_global<BILINEAR>(P, g);  // no covered pixel (copies `below`), or a footprint larger than the box
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);  // this warp is done with stage s (its shared-memory reads have completed)
+  }
 }
 
 bool plain_f16(const DevImage& im) {
@@ -345,30 +357,26 @@ zos_status launch_affine_f16(zos_ctx* ctx, const DevImage* below, const DevImage
   while ((P.box_w & 3) != 2) P.box_w++;
   P.box_h = (int)ceilf(ey) + 4;
   const size_t stage = ((size_t)P.box_w * P.box_h * 8 + 127) & ~(size_t)127;
-  const size_t smem = 2 * stage;
-  if (P.box_w * 2 > 256 || P.box_h > 256 || smem > 96 * 1024) return ZOS_OK;
+  const size_t smem = STAGES * stage;
+  if (P.box_w * 2 > 256 || P.box_h > 256 || smem > 144 * 1024) return ZOS_OK;
   TensorMaps M;
   memset(&M, 0, sizeof M);
   if (!make_map(ctx, &M.m0, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, above.p0, (uint64_t)above.w * 2, above.h, above.pitch, batch, above.bstride,
                 (uint32_t)P.box_w * 2, (uint32_t)P.box_h))
     return ZOS_OK;
-  const int group = 2;  // rows of a thread set up together; 4 needs 80 registers (3 CTAs per SM) and measured slower
+  // 3 stages of ~19 KB (30 degree rotation): 4 CTAs of 9 warps per SM, 56 registers per thread
   int per_sm = (int)((228 * 1024) / (smem + 1024 + 256));
-  const int max_ctas = group == 4 ? 3 : 5;
-  per_sm = per_sm < 1 ? 1 : (per_sm > max_ctas ? max_ctas : per_sm);
+  per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
   const uint64_t cap = (uint64_t)ctx->sm_count * per_sm;
   const int grid = (int)(total < cap ? total : cap);
 #define ZOS_AFF_LAUNCH(B, G, C)                                                                          \
   do {                                                                                                    \
     static bool attr_set = false;                                                                         \
-    if (!attr_set) { cudaFuncSetAttribute(k_affine_f16<B, G, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr_set = true; } \
-    k_affine_f16<B, G, C><<<grid, THREADS, smem, ctx->stream>>>(P, M);                                     \
+    if (!attr_set) { cudaFuncSetAttribute(k_affine_f16<B, G, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 144 * 1024); attr_set = true; } \
+    k_affine_f16<B, G, C><<<grid, THREADS_ALL, smem, ctx->stream>>>(P, M);                                    \
   } while (0)
-  const bool bil = cp.sampling == ZOS_SAMPLE_BILINEAR;
-  if (bil && group == 4) ZOS_AFF_LAUNCH(true, 4, 3);
-  else if (bil) ZOS_AFF_LAUNCH(true, 2, 5);
-  else if (group == 4) ZOS_AFF_LAUNCH(false, 4, 3);
-  else ZOS_AFF_LAUNCH(false, 2, 5);
+  if (cp.sampling == ZOS_SAMPLE_BILINEAR) ZOS_AFF_LAUNCH(true, 2, 4);   // GROUP = rows of a thread set up together
+  else ZOS_AFF_LAUNCH(false, 2, 4);
 #undef ZOS_AFF_LAUNCH
   ctx->launches++;
   *handled = true;
