@@ -193,6 +193,8 @@ def test_run_palette(pool, images, fixtures):  # tests/blend.rs:377-424 (goldens
     exp = O.palette(oracle_image(bg.descriptor(), fixtures["background"]), oramp, [1, 0, 0, 0], [0, 1, 0, 0])
     got = rgba(img)
     assert np.mean(np.all(got == exp.data.reshape(400, 400, 4), axis=-1)) > 0.99  # pow in the ramp's sRGB pack: a few coordinates flip
+    hsh = O.blockhash256(got)   # the two hashes the reference lists (two devices) are themselves 8 bits apart
+    assert min(bin(int(hsh, 16) ^ int(g, 16)).count("1") for g in hashes()["palette"]) <= 8
 
 
 def test_bilinear_knobs(pool):  # tests/knobs.rs: one Executable, five launches with a patched parameter block

