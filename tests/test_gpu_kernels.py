@@ -723,3 +723,49 @@ def test_field_division_exact_all_codes(ctx, bits, parts, n):
     got = run_chain(ctx, d, data, f32, []).view(np.float32)
     exp = O.encode(oracle_desc(f32), O.decode(oracle_image(d, data))).data.view(np.float32)
     assert np.array_equal(got, exp)
+
+
+# ---------------------------------------------------------------- batches (one launch, many frames)
+@pytest.mark.parametrize("width", [256, 253])   # 256: rows and frames contiguous -> the linear addressing variants; 253: general addressing
+def test_batched_launches_equal_per_frame_launches(ctx, width):
+    """A batch of frames in one launch (what bench.py and the 8-GPU sharding run) must give, frame by frame, the
+    bytes of single-frame launches: blend, convert with a matrix, Lab chain, RGB10A2 and RGBA16F conversions."""
+    W, H, N = width, 40, 5
+    rng = np.random.default_rng(77)
+    M = O.mul3(O.inv3(O.to_xyz("bt709", "D65")), O.to_xyz("bt2020", "D65"))
+    T = O.to_xyz("bt709", "D65")
+    srgb = zdesc(W, H, Texel.new_u8(SampleParts.RgbA), Color.SRGB)
+    lch = zdesc(W, H, Texel(Z.Block.Pixel, Z.SampleBits.UInt8x4, SampleParts.LchA), Color.Oklab)
+    rgb10 = zdesc(W, H, Texel(Z.Block.Pixel, Z.SampleBits.UInt1010102, SampleParts.RgbA), Color.SRGB)
+    f16 = zdesc(W, H, Texel.new_f16(), Color.Rgb(Z.Primaries.Bt709, Transfer.Linear))
+    chains = [
+        (srgb, srgb, [ops.matrix(M)]),
+        (srgb, srgb, [ops.step(_ffi.STEP_OKLAB_ENC, T), ops.requant(lch), ops.step(_ffi.STEP_OKLAB_DEC, O.inv3(T))]),
+        (rgb10, rgb10, [ops.matrix(M)]),
+        (srgb, f16, []),
+        (f16, f16, [ops.matrix(M)]),
+    ]
+    for sd, dd, steps in chains:
+        rb = W * sd.layout.texel_stride
+        data = rng.integers(0, 256, (N, H, rb), dtype=np.uint8)
+        if sd is f16:
+            data = rng.random((N, H, W * 4), dtype=np.float32).astype(np.float16).view(np.uint8).reshape(N, H, rb)
+        src, dst = ctx.image(sd, N), ctx.image(dd, N)
+        src.upload(data)
+        ops.pixel_chain(ctx, src, dst, steps)
+        got = dst.download()
+        for f in range(N):
+            assert np.array_equal(got[f], run_chain(ctx, sd, data[f], dd, steps)), (sd.texel, dd.texel, len(steps), f)
+        src.free(); dst.free()
+    # source-over of two batches
+    a = rng.integers(0, 256, (N, H, W * 4), dtype=np.uint8); b = rng.integers(0, 256, (N, H, W * 4), dtype=np.uint8)
+    below, above, dst = ctx.image(srgb, N), ctx.image(srgb, N), ctx.image(srgb, N)
+    below.upload(b); above.upload(a)
+    p = ops.compose_params(blend=_ffi.BLEND_SRC_OVER, sel=(0, 0, W, H), tgt=(0, 0, W, H))
+    ops.compose(ctx, below, above, dst, p)
+    got = dst.download()
+    for f in range(N):
+        exp = O.blend(oracle_image(srgb, b[f]), (0, 0, W, H), oracle_image(srgb, a[f]), 3).data
+        assert np.array_equal(got[f], exp)
+    for im in (below, above, dst):
+        im.free()
