@@ -28,6 +28,7 @@ ZOS_DEFINE_CONSTANT_UPLOAD(upload_constants_rowwise_lab)
 
 namespace {
 constexpr int LAB_THREADS = 1024;
+static_assert(ZOS_ENC2_N <= LAB_THREADS, "one thread per encoder bucket in the table fill");
 constexpr uint32_t DEC_BYTES = 256u * 256u;              // [code][0..31] colour decode, [code][32..63] alpha map
 constexpr uint32_t Q_BYTES = 256u * 256u;                // [code][lane & 15] float4 {f16(code/255), code/255, cos(hue(code)), sin(hue(code))}
 constexpr uint32_t ENC_BYTES = (uint32_t)ZOS_ENC2_N * 128u;  // biased-key bucket table (texel.cuh), one private copy per lane
@@ -112,32 +113,39 @@ __global__ void __launch_bounds__(LAB_THREADS, 1) k_rowwise_lab(const __grid_con
   float* dec = reinterpret_cast<float*>(smem);
   float* q = reinterpret_cast<float*>(smem + DEC_BYTES);
   uint32_t* enc = reinterpret_cast<uint32_t*>(smem + DEC_BYTES + Q_BYTES);
-#pragma unroll 4
-  for (int i = threadIdx.x; i < 256 * 64; i += LAB_THREADS) {
-    const int k = i >> 6;
-    float val;
-    if (i & 32) {
+  // table fill (see rowwise_lut.cu): 16-byte stores, a warp writes 512 contiguous bytes per instruction
+#pragma unroll
+  for (int k = 0; k < 256 * 64 / 4 / LAB_THREADS; k++) {
+    const int f = k * LAB_THREADS + threadIdx.x, code = f >> 4;
+    const float u = g_tables.unorm8[code];
+    float v;
+    if (f & 8) {
       // alpha through the chain: decode, register (f16, clamp, truncate, unorm, f16), encode (round to nearest)
-      const float a = g_tables.unorm8[k];
-      const uint32_t kq = (uint32_t)(clamp01(f16r(a)) * 255.0f);
+      const uint32_t kq = (uint32_t)(clamp01(f16r(u)) * 255.0f);
       const float a2 = f16r(g_tables.unorm8[kq]);
-      val = __uint_as_float((uint32_t)__float2int_rn(clamp01(a2) * 255.0f));
+      v = __uint_as_float((uint32_t)__float2int_rn(clamp01(a2) * 255.0f));
     } else {
-      val = P.src_srgb ? g_tables.srgb_dec[k] : g_tables.unorm8[k];
+      v = P.src_srgb ? g_tables.srgb_dec[code] : u;
     }
-    dec[i] = val;
+    reinterpret_cast<float4*>(dec)[f] = make_float4(v, v, v, v);
   }
-#pragma unroll 4
-  for (int i = threadIdx.x; i < 256 * 16; i += LAB_THREADS) {
-    const float u = g_tables.unorm8[i >> 4];
-    float4 c4 = make_float4(0.0f, u, u, 1.0f);  // (L, C = 1 * u ..., h = u): the generic decode of hue code k
-    c4.y = 1.0f;
-    transfer_decode(ZOS_TRANSFER_LABLCH, c4);  // c4.y = cos(hue), c4.z = sin(hue): the very code the generic path runs
-    reinterpret_cast<float4*>(q)[i] = make_float4(f16r(u), u, c4.y, c4.z);
+#pragma unroll
+  for (int k = 0; k < 256 * 16 / LAB_THREADS; k++) {
+    const int f = k * LAB_THREADS + threadIdx.x;
+    const float u = g_tables.unorm8[f >> 4];
+    float4 c4 = make_float4(0.0f, 1.0f, u, 1.0f);  // the generic decode of hue code f / 16 at chroma 1
+    transfer_decode(ZOS_TRANSFER_LABLCH, c4);       // c4.y = cos(hue), c4.z = sin(hue): the very code the generic path runs
+    reinterpret_cast<float4*>(q)[f] = make_float4(f16r(u), u, c4.y, c4.z);
   }
   if (SRGB_DST) {
-#pragma unroll 4
-    for (int i = threadIdx.x; i < ZOS_ENC2_N * 32; i += LAB_THREADS) enc[i] = g_tables.srgb_enc2[i >> 5];
+#pragma unroll
+    for (int k = 0; k < (ZOS_ENC2_N * 8 + LAB_THREADS - 1) / LAB_THREADS; k++) {
+      const int f = k * LAB_THREADS + threadIdx.x;
+      if (f < ZOS_ENC2_N * 8) {
+        const uint32_t e = g_tables.srgb_enc2[f >> 3];
+        reinterpret_cast<uint4*>(enc)[f] = make_uint4(e, e, e, e);
+      }
+    }
   }
   __syncthreads();
 

@@ -26,6 +26,7 @@
 namespace zos {
 
 constexpr int LUT_THREADS = 1024;
+static_assert(ZOS_ENC2_N <= LUT_THREADS, "one thread per encoder bucket in the table fill");
 constexpr uint32_t DEC_BYTES = 256u * 256u;                    // [code][0..31] sRGB EOTF, [code][32..63] code/255
 constexpr uint32_t ENC_BYTES = (uint32_t)ZOS_ENC2_N * 128u;    // [bucket][0..31]: one private copy per lane
 constexpr uint32_t ENC_SHIFT = 16 - 7;                         // bits(y) >> 16 is the key, rows are 128 bytes apart
@@ -135,11 +136,23 @@ __global__ void __launch_bounds__(LUT_THREADS, 1) k_rowwise_lut(const __grid_con
   extern __shared__ __align__(256) uint8_t smem[];
   float* dec = reinterpret_cast<float*>(smem);
   uint32_t* enc = reinterpret_cast<uint32_t*>(smem + DEC_BYTES);
-#pragma unroll 4
-  for (int i = threadIdx.x; i < 256 * 64; i += LUT_THREADS) dec[i] = (i & 32) ? g_tables.unorm8[i >> 6] : g_tables.srgb_dec[i >> 6];
+  // Table fill, the fixed cost of a launch (it dominates for small images): 16-byte stores, a warp writes 512
+  // contiguous bytes per instruction, all (L2-resident) source loads of a thread are independent.
+#pragma unroll
+  for (int k = 0; k < 256 * 64 / 4 / LUT_THREADS; k++) {
+    const int f = k * LUT_THREADS + threadIdx.x;                 // float4 index: row f / 16, floats [4 (f % 16), +4)
+    const float v = (f & 8) ? g_tables.unorm8[f >> 4] : g_tables.srgb_dec[f >> 4];
+    reinterpret_cast<float4*>(dec)[f] = make_float4(v, v, v, v);
+  }
   if (DK == K_SRGB8) {
-#pragma unroll 4
-    for (int i = threadIdx.x; i < ZOS_ENC2_N * 32; i += LUT_THREADS) enc[i] = g_tables.srgb_enc2[i >> 5];
+#pragma unroll
+    for (int k = 0; k < (ZOS_ENC2_N * 8 + LUT_THREADS - 1) / LUT_THREADS; k++) {
+      const int f = k * LUT_THREADS + threadIdx.x;               // uint4 index: bucket f / 8
+      if (f < ZOS_ENC2_N * 8) {
+        const uint32_t e = g_tables.srgb_enc2[f >> 3];
+        reinterpret_cast<uint4*>(enc)[f] = make_uint4(e, e, e, e);
+      }
+    }
   }
   __syncthreads();
 
