@@ -284,8 +284,8 @@ __global__ void __launch_bounds__(THREADS_ALL, CTAS) k_affine_f16(const __grid_c
       const uint32_t s = it % STAGES, round = it / STAGES;
       if (round > 0) {  // wait until the consumers have released the stage's previous tile
         uint32_t spins = 0;
-        while (!mbar_try_wait(&empty[s], (round - 1) & 1)) {
-          if (++spins > (1u << 26)) { if (P.fault) *reinterpret_cast<volatile int*>(P.fault) = 1; break; }
+        while (!mbar_try_wait_sleep(&empty[s], (round - 1) & 1, 20000u)) {
+          if (++spins > (1u << 20)) { if (P.fault) *reinterpret_cast<volatile int*>(P.fault) = 1; break; }
         }
       }
       Geo g_;
@@ -304,8 +304,8 @@ __global__ void __launch_bounds__(THREADS_ALL, CTAS) k_affine_f16(const __grid_c
   for (uint32_t t = blockIdx.x; t < P.total_tiles; t += gridDim.x, it++) {
     const uint32_t s = it % STAGES, round = it / STAGES;
     uint32_t spins = 0;
-    while (!mbar_try_wait(&full[s], round & 1)) {
-      if (++spins > (1u << 26)) { if (P.fault) *reinterpret_cast<volatile int*>(P.fault) = 1; break; }
+    while (!mbar_try_wait_sleep(&full[s], round & 1, 20000u)) {
+      if (++spins > (1u << 20)) { if (P.fault) *reinterpret_cast<volatile int*>(P.fault) = 1; break; }
     }
     const Geo g = geo[s];
     if (g.any && g.fits) compute_tile_smem<BILINEAR, GROUP>(P, g, smem_u32(dyn + (size_t)s * stage_bytes));
