@@ -371,8 +371,7 @@ zos_status launch_affine_f16(zos_ctx* ctx, const DevImage* below, const DevImage
   const int grid = (int)(total < cap ? total : cap);
 #define ZOS_AFF_LAUNCH(B, G, C)                                                                          \
   do {                                                                                                    \
-    static bool attr_set = false;                                                                         \
-    if (!attr_set) { cudaFuncSetAttribute(k_affine_f16<B, G, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 144 * 1024); attr_set = true; } \
+    ensure_dyn_smem(ctx, k_affine_f16<B, G, C>, 144 * 1024);                                                \
     k_affine_f16<B, G, C><<<grid, THREADS_ALL, smem, ctx->stream>>>(P, M);                                    \
   } while (0)
   if (cp.sampling == ZOS_SAMPLE_BILINEAR) ZOS_AFF_LAUNCH(true, 2, 4);   // GROUP = rows of a thread set up together

@@ -564,8 +564,7 @@ zos_status launch_frame_pipeline(zos_ctx* ctx, const DevImage* below, const DevI
       const bool bil = cp.sampling != ZOS_SAMPLE_NEAREST;
 #define ZOS_FF(B, S, T)                                                                                          \
   do {                                                                                                            \
-    static bool set_ = false;                                                                                     \
-    if (!set_) { cudaFuncSetAttribute(k_frame_fast<B, S, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); set_ = true; } \
+    ensure_dyn_smem(ctx, k_frame_fast<B, S, T>, 160 * 1024);                                                        \
     k_frame_fast<B, S, T><<<grid, THREADS, fsmem, ctx->stream>>>(P, M);                                            \
   } while (0)
       if (trk == 0) { if (bil) { if (srgb) ZOS_FF(true, true, 0); else ZOS_FF(true, false, 0); } else { if (srgb) ZOS_FF(false, true, 0); else ZOS_FF(false, false, 0); } }
@@ -577,8 +576,7 @@ zos_status launch_frame_pipeline(zos_ctx* ctx, const DevImage* below, const DevI
     }
     return ZOS_OK;  // (maps were rebuilt for the smaller box: leave this launch to the general kernel)
   }
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(k_frame_pipeline, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr_set = true; }
+  ensure_dyn_smem(ctx, k_frame_pipeline, 160 * 1024);
   int per_sm = (int)((220 * 1024) / (smem + sizeof(Tables) + 2048));
   per_sm = per_sm < 1 ? 1 : (per_sm > 3 ? 3 : per_sm);
   uint64_t cap = (uint64_t)ctx->sm_count * per_sm;

@@ -604,13 +604,9 @@ zos_status launch_gather(zos_ctx* ctx, const DevImage* below, const DevImage& ab
                     plain_f16(above) && plain_f16(dst) && (!below || plain_f16(*below));
   cudaError_t e;
   if (tma) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(k_gather_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      cudaFuncSetAttribute(k_gather_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      cudaFuncSetAttribute(k_gather_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024);
-      attr_set = true;
-    }
+    ensure_dyn_smem(ctx, k_gather_tma<0>, 96 * 1024);
+    ensure_dyn_smem(ctx, k_gather_tma<1>, 96 * 1024);
+    ensure_dyn_smem(ctx, k_gather_tma<2>, 150 * 1024);
     int per_sm = (int)((200 * 1024) / (smem + sizeof(Tables) + 1024));
     per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
     uint64_t cap = (uint64_t)ctx->sm_count * per_sm;

@@ -188,13 +188,11 @@ bool native8(const DevImage& im, bool* srgb, bool* bgra) {
 
 template <int LAB, bool SRGB_DST, bool LCH>
 cudaError_t launch_one(zos_ctx* ctx, const LabParams& P) {
-  static bool configured = false;
   auto kern = k_rowwise_lab<LAB, SRGB_DST, LCH>;
   const uint32_t bytes = DEC_BYTES + Q_BYTES + (SRGB_DST ? ENC_BYTES : 0u);
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DEC_BYTES + Q_BYTES + ENC_BYTES));
+  {
+    cudaError_t e = ensure_dyn_smem(ctx, kern, (int)(DEC_BYTES + Q_BYTES + ENC_BYTES));
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   const uint64_t ctas = ((uint64_t)P.F.total_groups + LAB_THREADS - 1) / LAB_THREADS;
   const int grid = (int)(ctas < (uint64_t)ctx->sm_count ? ctas : (uint64_t)ctx->sm_count);

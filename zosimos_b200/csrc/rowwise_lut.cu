@@ -236,15 +236,13 @@ __global__ void __launch_bounds__(LUT_THREADS, 1) k_rowwise_lut(const __grid_con
 
 template <int SK, int DK, int MODE, int NMAT>
 static cudaError_t launch_one(zos_ctx* ctx, const FastParams& P) {
-  static bool configured[16] = {};  // per device: opt in to > 48 KB of dynamic shared memory once
   const uint32_t bytes = DEC_BYTES + (DK == K_SRGB8 ? ENC_BYTES : 0u);
   auto kern = k_rowwise_lut<SK, DK, MODE, NMAT, false>;
   auto kern_lin = k_rowwise_lut<SK, DK, MODE, NMAT, true>;
-  if (ctx->device < 0 || ctx->device >= 16 || !configured[ctx->device]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DEC_BYTES + ENC_BYTES));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_lin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DEC_BYTES + ENC_BYTES));
+  {
+    cudaError_t e = ensure_dyn_smem(ctx, kern, (int)(DEC_BYTES + ENC_BYTES));
+    if (e == cudaSuccess) e = ensure_dyn_smem(ctx, kern_lin, (int)(DEC_BYTES + ENC_BYTES));
     if (e != cudaSuccess) return e;
-    if (ctx->device >= 0 && ctx->device < 16) configured[ctx->device] = true;
   }
   const uint64_t ctas = (P.total_groups + LUT_THREADS - 1) / LUT_THREADS;
   const int grid = (int)(ctas < (uint64_t)ctx->sm_count ? ctas : (uint64_t)ctx->sm_count);

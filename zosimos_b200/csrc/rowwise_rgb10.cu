@@ -104,11 +104,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_rowwise_rgb10(const __grid_const
 
 template <int NMAT>
 cudaError_t launch_one(zos_ctx* ctx, const FastParams& P) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_rowwise_rgb10<NMAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+  {
+    cudaError_t e = ensure_dyn_smem(ctx, k_rowwise_rgb10<NMAT>, (int)SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   const uint64_t ctas = ((uint64_t)P.total_groups + THREADS - 1) / THREADS;
   const int grid = (int)(ctas < (uint64_t)ctx->sm_count ? ctas : (uint64_t)ctx->sm_count);

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -25,6 +26,7 @@ struct zos_ctx {
   std::vector<void*> scratch;    // device scratch owned by the ctx (tensor maps etc.)
   int* fault_host = nullptr;     // mapped pinned word: kernels set it when an mbarrier wait ran away; zos_sync reports it
   int* fault_dev = nullptr;      // device view of fault_host
+  std::set<const void*> smem_configured;  // kernels whose dynamic shared memory limit was raised ON THIS CONTEXT'S DEVICE
   std::map<std::string, struct zos_dynamic*> dynamic_cache;  // NVRTC-compiled plugins by source text (dynamic.cu)
 };
 
@@ -65,6 +67,16 @@ zos_status check_cuda(zos_ctx* ctx, cudaError_t e, const char* what);
 zos_status make_dev_image(zos_ctx* ctx, const zos_image* img, DevImage* out, const char* name);
 zos_status validate_steps(zos_ctx* ctx, const zos_step* steps, uint32_t n);
 int grid_for(const zos_ctx* ctx, uint64_t work_items, int threads, int ctas_per_sm);
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device setting: remembered per context, not per process
+template <typename F>
+inline cudaError_t ensure_dyn_smem(zos_ctx* ctx, F func, int bytes) {
+  const void* key = reinterpret_cast<const void*>(func);
+  if (ctx->smem_configured.count(key)) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) ctx->smem_configured.insert(key);
+  return e;
+}
 
 // kernel launchers (one per .cu)
 zos_status launch_rowwise(zos_ctx* ctx, const DevImage* below, const DevImage* above, const DevImage& dst,
