@@ -40,13 +40,22 @@ struct AffParams {
   uint32_t tiles_x, tiles_y, total_tiles;
   FastDiv div_frame, div_band;  // tiles per frame, tiles per band of 8 tile rows
   int32_t box_w, box_h;
+  float sfwf, sfhf;  // (float)sfw, (float)sfh
   int* fault;  // mapped host word set when an mbarrier wait runs away
 };
 
-struct Geo {
+struct __align__(16) Geo {
+  // what the compute warps of the staged path read (the producer works all of it out once per tile)
+  uint32_t base;                // shared address of texel (0, 0) of the FULL source, relative to this stage's box
+  int32_t staged;               // any && fits: the box is in shared memory
+  float cx0, cy0;               // centre of the tile's first pixel in full-destination coordinates
+  uint64_t dst_off, below_off;  // byte offsets of the tile's first pixel
+  int32_t nx, ny;               // live columns / rows of the tile
+  // the rest is for the producer and the direct path
   int32_t frame, x0, y0;  // destination tile
   int32_t bx, by;         // box origin in the window `above` holds
   int32_t fits, any;
+  int32_t pad_;
 };
 
 __device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv& f) {
@@ -152,39 +161,62 @@ __device__ __forceinline__ uint2 ldg64_cs_if(const uint8_t* ptr, bool p) {
   return w;
 }
 
-// The tile from the staged box, branch-free: GROUP rows of a thread are set up together (coordinates,
-// coverage, tap addresses), their loads are issued predicated and back to back, then the arithmetic
-// runs for all of them; uncovered pixels take `below` (or the clear colour) through a select.
-template <bool BILINEAR, int GROUP>
-__device__ __forceinline__ void compute_tile_smem(const AffParams& P, const Geo& g, uint32_t stage_addr) {
-  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
-  const int i = g.x0 + lx;
-  if (i >= P.dw) return;
-  const float cx = (float)(i + P.dox) + 0.5f;
-  const float tx = fmaf(P.inv[0], cx, P.inv[2]), ty = fmaf(P.inv[3], cx, P.inv[5]);
-  const float sfw = (float)P.sfw, sfh = (float)P.sfh;
+// sm_100 mixed-precision add (FHADD): (float)h - c with ONE rounding, i.e. exactly the f32 subtraction of the
+// converted half (the conversion is exact) -- it saves the separate f16 -> f32 conversion of the minuend.
+__device__ __forceinline__ float hsub_lo(uint32_t w, float c) {
+  float d;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tsub.rn.f32.f16 %0, l, %2;\n\t}" : "=f"(d) : "r"(w), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float hsub_hi(uint32_t w, float c) {
+  float d;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tsub.rn.f32.f16 %0, h, %2;\n\t}" : "=f"(d) : "r"(w), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float h2f_lo(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xffffu))); }
+__device__ __forceinline__ float h2f_hi(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
+
+// fma(ay, bot - top, top) of top = fma(ax, p10 - p00, p00), bot = fma(ax, p11 - p01, p01): the lerp order of the
+// oracle (zo_paint_affine_window) and gather.cu, 8 instructions per channel
+#define ZOS_BILERP(EXT, SUB, W00, W10, W01, W11, AX, AY, OUT) \
+  {                                                           \
+    const float a_ = EXT(W00), b_ = EXT(W01);                 \
+    const float top_ = fmaf(AX, SUB(W10, a_), a_);            \
+    const float bot_ = fmaf(AX, SUB(W11, b_), b_);            \
+    OUT = fmaf(AY, bot_ - top_, top_);                        \
+  }
+
+struct Lane {  // per-thread constants of a compute thread
+  uint32_t lx, ly;
+  float lxf, lyf;
+  uint64_t dst_thr, below_thr;  // ly * pitch + lx * 8
+};
+
+// The rows of one thread from the staged box, branch-free: GROUP rows are set up together (coordinates,
+// coverage, tap addresses), their loads are issued back to back, then the arithmetic runs for all of them.
+// ALLCOV: every pixel of the warp's rows is live and covered (the common case: interior tiles) -- plain loads,
+// no `below`, no select.  Otherwise loads are predicated and uncovered pixels take `below` (or the clear colour)
+// through a select.
+template <bool BILINEAR, bool ALLCOV, int GROUP>
+__device__ __forceinline__ void compute_rows(const AffParams& P, const Geo& g, const Lane& L, const float (&px)[ROWS], const float (&py)[ROWS],
+                                             const bool (&live)[ROWS], const bool (&cov)[ROWS]) {
   const uint32_t rowb = (uint32_t)P.box_w * 8u;
-  const uint32_t base = stage_addr - (uint32_t)(g.by + P.soy) * rowb - (uint32_t)(g.bx + P.sox) * 8u;
+  const uint32_t base = g.base;
   const int xmax = P.sfw - 1, ymax = P.sfh - 1;
-  uint8_t* dp = P.dst + (uint64_t)g.frame * P.dst_bstride + (uint64_t)(g.y0 + ly) * P.dst_pitch + (uint64_t)i * 8u;
-  const uint8_t* bp = P.below + (uint64_t)g.frame * P.below_bstride + (uint64_t)(g.y0 + ly) * P.below_pitch + (uint64_t)i * 8u;
+  uint8_t* dp = P.dst + (g.dst_off + L.dst_thr);
+  const uint8_t* bp = P.below + (g.below_off + L.below_thr);
   const uint64_t dstep = (uint64_t)(THREADS / 32) * P.dst_pitch, bstep = (uint64_t)(THREADS / 32) * P.below_pitch;
   const bool has_below = P.has_below != 0;
-  const float cy0 = (float)(g.y0 + ly + P.doy) + 0.5f;
 #pragma unroll
   for (int k0 = 0; k0 < ROWS; k0 += GROUP) {
-    bool live[GROUP], cov[GROUP];
     float ax[GROUP], ay[GROUP];
     uint2 w00[GROUP], w10[GROUP], w01[GROUP], w11[GROUP], wb[GROUP];
 #pragma unroll
     for (int q = 0; q < GROUP; q++) {
-      const int j = g.y0 + ly + (THREADS / 32) * (k0 + q);
-      live[q] = j < P.dh;
-      const float cy = cy0 + (float)((THREADS / 32) * (k0 + q));  // == (float)(j + doy) + 0.5f: all three are exact
-      const float px = fmaf(P.inv[1], cy, tx), py = fmaf(P.inv[4], cy, ty);
-      cov[q] = live[q] && px >= 0.0f && px < sfw && py >= 0.0f && py < sfh;
+      const int k = k0 + q;
+      const bool c = ALLCOV || cov[k];
       if (BILINEAR) {
-        const float fx = px - 0.5f, fy = py - 0.5f;
+        const float fx = px[k] - 0.5f, fy = py[k] - 0.5f;
         // floor as ONE conversion; back to float on the integer pipe (exact: |fx| < 2^23 for covered pixels)
         const int x0 = __float2int_rd(fx), y0 = __float2int_rd(fy);
         const float x0f = (float)x0, y0f = (float)y0;
@@ -192,32 +224,72 @@ __device__ __forceinline__ void compute_tile_smem(const AffParams& P, const Geo&
         // covered: px in [0, sfw) so x0 in [-1, sfw-1]: clamp(x0) = max(x0, 0), clamp(x0 + 1) = min(x0 + 1, sfw - 1)
         const int xa = max(x0, 0), xb = min(x0 + 1, xmax), ya = max(y0, 0), yb = min(y0 + 1, ymax);
         const uint32_t ra = base + (uint32_t)ya * rowb, rb = base + (uint32_t)yb * rowb;
-        w00[q] = lds64_if(ra + (uint32_t)xa * 8u, cov[q]); w10[q] = lds64_if(ra + (uint32_t)xb * 8u, cov[q]);
-        w01[q] = lds64_if(rb + (uint32_t)xa * 8u, cov[q]); w11[q] = lds64_if(rb + (uint32_t)xb * 8u, cov[q]);
+        if (ALLCOV) {
+          w00[q] = lds64(ra + (uint32_t)xa * 8u); w10[q] = lds64(ra + (uint32_t)xb * 8u);
+          w01[q] = lds64(rb + (uint32_t)xa * 8u); w11[q] = lds64(rb + (uint32_t)xb * 8u);
+        } else {
+          w00[q] = lds64_if(ra + (uint32_t)xa * 8u, c); w10[q] = lds64_if(ra + (uint32_t)xb * 8u, c);
+          w01[q] = lds64_if(rb + (uint32_t)xa * 8u, c); w11[q] = lds64_if(rb + (uint32_t)xb * 8u, c);
+        }
       } else {
-        const int u = (int)floorf(px), w = (int)floorf(py);
-        w00[q] = lds64_if(base + (uint32_t)w * rowb + (uint32_t)u * 8u, cov[q]);
+        const int u = __float2int_rd(px[k]), w = __float2int_rd(py[k]);
+        const uint32_t a = base + (uint32_t)w * rowb + (uint32_t)u * 8u;
+        w00[q] = ALLCOV ? lds64(a) : lds64_if(a, c);
       }
-      wb[q] = ldg64_cs_if(bp + (uint64_t)(k0 + q) * bstep, has_below && live[q] && !cov[q]);
+      if (!ALLCOV) wb[q] = ldg64_cs_if(bp + (uint64_t)k * bstep, has_below && live[k] && !c);
     }
 #pragma unroll
     for (int q = 0; q < GROUP; q++) {
-      float4 v;
+      const int k = k0 + q;
+      uint2 o;
       if (BILINEAR) {
-        const float4 p00 = half4_to_float4(w00[q]), p10 = half4_to_float4(w10[q]), p01 = half4_to_float4(w01[q]), p11 = half4_to_float4(w11[q]);
-#define ZOS_LERP2(c) { float top = fmaf(ax[q], p10.c - p00.c, p00.c), bot = fmaf(ax[q], p11.c - p01.c, p01.c); v.c = fmaf(ay[q], bot - top, top); }
-        ZOS_LERP2(x) ZOS_LERP2(y) ZOS_LERP2(z) ZOS_LERP2(w)
-#undef ZOS_LERP2
+        float4 v;
+        ZOS_BILERP(h2f_lo, hsub_lo, w00[q].x, w10[q].x, w01[q].x, w11[q].x, ax[q], ay[q], v.x)
+        ZOS_BILERP(h2f_hi, hsub_hi, w00[q].x, w10[q].x, w01[q].x, w11[q].x, ax[q], ay[q], v.y)
+        ZOS_BILERP(h2f_lo, hsub_lo, w00[q].y, w10[q].y, w01[q].y, w11[q].y, ax[q], ay[q], v.z)
+        ZOS_BILERP(h2f_hi, hsub_hi, w00[q].y, w10[q].y, w01[q].y, w11[q].y, ax[q], ay[q], v.w)
+        __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+        o = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
       } else {
-        v = half4_to_float4(w00[q]);
+        // the working value of a nearest tap is the texel itself, and f16 -> f32 -> f16 is the identity
+        o = w00[q];
       }
-      __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
-      uint2 o = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-      // uncovered: `below` as it is (f16 -> f32 -> f16 is the identity), else the clear colour (0, 0, 1, 1)
-      if (!cov[q]) o = has_below ? wb[q] : make_uint2(0u, 0x3c003c00u);
-      if (live[q]) __stcs(reinterpret_cast<uint2*>(dp + (uint64_t)(k0 + q) * dstep), o);
+      if (ALLCOV) {
+        __stcs(reinterpret_cast<uint2*>(dp + (uint64_t)k * dstep), o);
+      } else {
+        // uncovered: `below` as it is, else the clear colour (0, 0, 1, 1)
+        if (!cov[k]) o = has_below ? wb[q] : make_uint2(0u, 0x3c003c00u);
+        if (live[k]) __stcs(reinterpret_cast<uint2*>(dp + (uint64_t)k * dstep), o);
+      }
     }
   }
+}
+
+template <bool BILINEAR, int GROUP>
+__device__ __forceinline__ void compute_tile_smem(const AffParams& P, const Geo& g, const Lane& L) {
+  // == (float)(i + dox) + 0.5f: every term is an exact float below 2^22 (checked by the launcher)
+  const float cx = g.cx0 + L.lxf;
+  const float tx = fmaf(P.inv[0], cx, P.inv[2]), ty = fmaf(P.inv[3], cx, P.inv[5]);
+  // covered <=> 0 <= p < size.  No coordinate is -0 (the launcher turns -0 coefficients into +0, sums that
+  // cancel give +0), so the bit patterns of non-negative floats order like unsigned integers and every negative
+  // or NaN pattern is above bits(size): one unsigned compare per axis.
+  const uint32_t wbits = __float_as_uint(P.sfwf), hbits = __float_as_uint(P.sfhf);
+  const float cyb = g.cy0 + L.lyf;
+  const bool col_live = (int)L.lx < g.nx;
+  const int rows_left = g.ny - (int)L.ly;  // row k of this thread is live when (THREADS / 32) * k < rows_left
+  float px[ROWS], py[ROWS];
+  bool live[ROWS], cov[ROWS];
+  bool all = true;
+#pragma unroll
+  for (int k = 0; k < ROWS; k++) {
+    const float cy = cyb + (float)((THREADS / 32) * k);  // == (float)(j + doy) + 0.5f, exact
+    px[k] = fmaf(P.inv[1], cy, tx); py[k] = fmaf(P.inv[4], cy, ty);
+    live[k] = col_live && (THREADS / 32) * k < rows_left;
+    cov[k] = live[k] && __float_as_uint(px[k]) < wbits && __float_as_uint(py[k]) < hbits;
+    all = all && cov[k];
+  }
+  if (__all_sync(0xffffffffu, all)) compute_rows<BILINEAR, true, GROUP>(P, g, L, px, py, live, cov);
+  else compute_rows<BILINEAR, false, GROUP>(P, g, L, px, py, live, cov);
 }
 
 // Tiles whose footprint does not fit the box (strong minification) or that no covered pixel touches:
@@ -253,13 +325,40 @@ __device__ __forceinline__ void compute_tile_global(const AffParams& P, const Ge
   }
 }
 
-// Warp-specialised pipeline: warps 0..7 compute tiles, warp 8 (one lane) is the producer.  The producer runs
-// up to STAGES tiles ahead: it works out the next tile's geometry, publishes it in shared memory and issues the
-// TMA load; `full[s]` completes when the box has landed (or at once for tiles that need none).  A consumer warp
-// that is done with stage s arrives on `empty[s]` (8 arrivals free the stage).  There is no CTA-wide barrier in
-// the loop: warps drift apart by up to STAGES tiles, and the ~250 serial instructions of the geometry are off
-// the compute warps' critical path.
+// A tile no covered pixel can touch: `below` (or the clear colour) as it is.  All rows of a thread are loaded
+// before the first store so that a warp pays one memory round trip per tile, not one per row.
+__device__ __forceinline__ void copy_tile(const AffParams& P, const Geo& g, const Lane& L) {
+  const bool col_live = (int)L.lx < g.nx;
+  const int rows_left = g.ny - (int)L.ly;
+  uint8_t* dp = P.dst + (g.dst_off + L.dst_thr);
+  const uint8_t* bp = P.below + (g.below_off + L.below_thr);
+  const uint64_t dstep = (uint64_t)(THREADS / 32) * P.dst_pitch, bstep = (uint64_t)(THREADS / 32) * P.below_pitch;
+  uint2 w[ROWS];
+  bool live[ROWS];
+#pragma unroll
+  for (int k = 0; k < ROWS; k++) {
+    live[k] = col_live && (THREADS / 32) * k < rows_left;
+    w[k] = make_uint2(0u, 0x3c003c00u);  // Target::Discard clear colour (0, 0, 1, 1)
+    if (P.has_below && live[k]) w[k] = __ldcs(reinterpret_cast<const uint2*>(bp + (uint64_t)k * bstep));
+  }
+#pragma unroll
+  for (int k = 0; k < ROWS; k++)
+    if (live[k]) __stcs(reinterpret_cast<uint2*>(dp + (uint64_t)k * dstep), w[k]);
+}
+
+// Warp-specialised pipeline: warps 0..7 compute tiles, warp 8 (one lane) is the producer.  The producer works out
+// the geometry of a tile AHEAD iterations before the tile's turn and stores it in a ring in shared memory, so that
+// the moment the tile's stage is free the TMA load goes out (the ~250 serial instructions of the geometry are
+// not between "stage released" and "load issued").  `full[s]` completes when the box has landed (or at once for
+// tiles that need none).  (Measured and dropped: cp.async.bulk.prefetch.tensor of the box into L2 at geometry
+// time -- 0.72 -> 0.61 of the HBM peak at 2 frames, 0.49 at 16: the prefetched lines displace the overlap between
+// neighbouring boxes that L2 serves today.  Also measured and dropped: the producer warp staging the box with
+// 16-byte cp.async copies instead of the TMA box load -- 0.72 -> 0.32-0.38.)  A consumer warp that is done with stage s arrives on
+// `empty[s]` (8 arrivals free the stage).  There is no CTA-wide barrier in the loop: warps drift apart by up
+// to STAGES tiles, and the ~250 serial instructions of the geometry are off the compute warps' critical path.
 constexpr int STAGES = 3;
+constexpr int AHEAD = 4;
+constexpr int RING = 8;  // > AHEAD + STAGES: an entry is rewritten only after its tile has been consumed
 constexpr int CONSUMER_WARPS = THREADS / 32;
 constexpr int THREADS_ALL = THREADS + 32;
 
@@ -267,7 +366,7 @@ template <bool BILINEAR, int GROUP, int CTAS>
 __global__ void __launch_bounds__(THREADS_ALL, CTAS) k_affine_f16(const __grid_constant__ AffParams P, const __grid_constant__ TensorMaps M) {
   extern __shared__ __align__(128) uint8_t dyn[];
   __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES];
-  __shared__ Geo geo[STAGES];
+  __shared__ Geo geo[RING];
   const uint32_t box_bytes = (uint32_t)P.box_w * P.box_h * 8u;
   const uint32_t stage_bytes = (box_bytes + 127u) & ~127u;
   if (threadIdx.x == 0) {
@@ -277,41 +376,60 @@ __global__ void __launch_bounds__(THREADS_ALL, CTAS) k_affine_f16(const __grid_c
   __syncthreads();  // the barriers exist before anybody arms or polls them
   const CUtensorMap* const m0 = &M.m0;  // stays in param space (see gather.cu)
   const uint32_t warp = threadIdx.x >> 5;
-  uint32_t it = 0;
+  const uint32_t my_tiles = blockIdx.x < P.total_tiles ? (P.total_tiles - 1u - blockIdx.x) / gridDim.x + 1u : 0u;
   if (warp == CONSUMER_WARPS) {
     if ((threadIdx.x & 31) != 0) return;
-    for (uint32_t t = blockIdx.x; t < P.total_tiles; t += gridDim.x, it++) {
-      const uint32_t s = it % STAGES, round = it / STAGES;
+    const uint32_t rowb = (uint32_t)P.box_w * 8u;
+    uint32_t s = 0, round = 0;  // stage and use count of the stage for the tile being issued
+    for (uint32_t it = 0; it < my_tiles + AHEAD; it++) {
+      if (it < my_tiles) {  // geometry of tile `it`, AHEAD iterations ahead of its load
+        Geo& g_ = geo[it % RING];
+        tile_geometry(P, blockIdx.x + it * gridDim.x, g_);
+        g_.staged = g_.any && g_.fits;
+        g_.base = smem_u32(dyn + (size_t)(it % STAGES) * stage_bytes) - (uint32_t)(g_.by + P.soy) * rowb - (uint32_t)(g_.bx + P.sox) * 8u;
+        g_.cx0 = (float)(g_.x0 + P.dox) + 0.5f; g_.cy0 = (float)(g_.y0 + P.doy) + 0.5f;
+        g_.dst_off = (uint64_t)g_.frame * P.dst_bstride + (uint64_t)g_.y0 * P.dst_pitch + (uint64_t)g_.x0 * 8u;
+        g_.below_off = (uint64_t)g_.frame * P.below_bstride + (uint64_t)g_.y0 * P.below_pitch + (uint64_t)g_.x0 * 8u;
+        g_.nx = min(TILE, P.dw - g_.x0); g_.ny = min(TILE, P.dh - g_.y0);
+      }
+      if (it < AHEAD) continue;
+      const Geo& g = geo[(it - AHEAD) % RING];
       if (round > 0) {  // wait until the consumers have released the stage's previous tile
         uint32_t spins = 0;
         while (!mbar_try_wait_sleep(&empty[s], (round - 1) & 1, 20000u)) {
           if (++spins > (1u << 20)) { if (P.fault) *reinterpret_cast<volatile int*>(P.fault) = 1; break; }
         }
       }
-      Geo g_;
-      tile_geometry(P, t, g_);
-      geo[s] = g_;
-      if (g_.any && g_.fits) {
+      if (g.staged) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(&full[s], box_bytes);
-        tma_load_3d(dyn + (size_t)s * stage_bytes, m0, g_.bx * 2, g_.by, g_.frame, &full[s]);
+        tma_load_3d(dyn + (size_t)s * stage_bytes, m0, g.bx * 2, g.by, g.frame, &full[s]);
       } else {
-        mbar_arrive(&full[s]);  // nothing to load: the geometry alone is the payload
+        mbar_arrive(&full[s]);  // nothing to load: the geometry alone is the payload (release: the ring entry is visible)
       }
+      if (++s == STAGES) { s = 0; round++; }
     }
     return;
   }
-  for (uint32_t t = blockIdx.x; t < P.total_tiles; t += gridDim.x, it++) {
-    const uint32_t s = it % STAGES, round = it / STAGES;
+  Lane L;
+  L.lx = threadIdx.x & 31; L.ly = threadIdx.x >> 5;
+  L.lxf = (float)L.lx; L.lyf = (float)L.ly;
+  L.dst_thr = (uint64_t)L.ly * P.dst_pitch + (uint64_t)L.lx * 8u;
+  L.below_thr = (uint64_t)L.ly * P.below_pitch + (uint64_t)L.lx * 8u;
+  uint32_t s = 0, parity = 0, r = 0;
+  for (uint32_t it = 0; it < my_tiles; it++) {
     uint32_t spins = 0;
-    while (!mbar_try_wait_sleep(&full[s], round & 1, 20000u)) {
+    while (!mbar_try_wait_sleep(&full[s], parity, 20000u)) {
       if (++spins > (1u << 20)) { if (P.fault) *reinterpret_cast<volatile int*>(P.fault) = 1; break; }
     }
-    const Geo g = geo[s];
-    if (g.any && g.fits) compute_tile_smem<BILINEAR, GROUP>(P, g, smem_u32(dyn + (size_t)s * stage_bytes));
-    else compute_tile_global<BILINEAR>(P, g);  // no covered pixel (copies `below`), or a footprint larger than the box
+    const Geo& g = geo[r];
+    if (g.staged) compute_tile_smem<BILINEAR, GROUP>(P, g, L);
+    else if (!g.any) copy_tile(P, g, L);            // no covered pixel
+    else compute_tile_global<BILINEAR>(P, g);       // a footprint larger than the box: taps straight from global memory
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);  // this warp is done with stage s (its shared-memory reads have completed)
+    if (++s == STAGES) { s = 0; parity ^= 1u; }
+    r = (r + 1) & (RING - 1);
   }
 }
 
@@ -339,11 +457,13 @@ zos_status launch_affine_f16(zos_ctx* ctx, const DevImage* below, const DevImage
   P.has_below = below != nullptr;
   P.dst = dst.p0; P.dst_pitch = dst.pitch; P.dst_bstride = dst.bstride; P.dw = dst.w; P.dh = dst.h;
   P.blend = cp.blend;
-  for (int k = 0; k < 6; k++) P.inv[k] = cp.inv[k];
+  for (int k = 0; k < 6; k++) P.inv[k] = cp.inv[k] == 0.0f ? 0.0f : cp.inv[k];  // -0 -> +0: same results (see compute_tile_smem), no -0 coordinate
   P.dox = cp.dst_origin[0]; P.doy = cp.dst_origin[1]; P.sox = cp.src_origin[0]; P.soy = cp.src_origin[1];
   P.sfw = cp.src_full[0] > 0 ? cp.src_full[0] : above.w; P.sfh = cp.src_full[1] > 0 ? cp.src_full[1] : above.h;
   if (P.dox < 0 || P.doy < 0 || P.sox < 0 || P.soy < 0 || P.sox + above.w > P.sfw || P.soy + above.h > P.sfh) return ZOS_OK;  // gather.cu reports it
   if (above.pitch >= (1ull << 31)) return ZOS_OK;
+  if ((int64_t)P.dox + dst.w >= (1 << 22) || (int64_t)P.doy + dst.h >= (1 << 22) || P.sfw >= (1 << 22) || P.sfh >= (1 << 22)) return ZOS_OK;
+  P.sfwf = (float)P.sfw; P.sfhf = (float)P.sfh;
   P.tiles_x = (dst.w + TILE - 1) / TILE; P.tiles_y = (dst.h + TILE - 1) / TILE;
   const uint64_t total = (uint64_t)P.tiles_x * P.tiles_y * batch;
   if (total == 0 || total >= (1ull << 31)) return ZOS_OK;
