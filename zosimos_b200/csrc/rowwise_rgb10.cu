@@ -5,8 +5,13 @@
 // bits, so both directions become tables built at kernel start BY RUNNING THE GENERIC CODEC'S OWN CODE:
 //
 //   decode: D[k]  = f16(eotf(k / 1023)), 1024 entries (8 copies);   alpha: 4 entries, via A[] below
-//   encode: E[h]  = uint(clamp01(oetf(half(h))) * 1023) for all 65536 f16 bit patterns h (the value
-//           stored in the f16 attachment is all the encoder ever sees), as u16: 128 KB;
+//   encode: E[h]  = uint(clamp01(oetf(half(h))) * 1023) for the f16 bit patterns h of [0, 1] (the value stored
+//           in the f16 attachment is all the encoder ever sees; the clamp is applied BEFORE the f16 rounding,
+//           which commutes with it because 0 and 1 are f16 values and rounding is monotone), as u16:
+//           15361 entries + one for everything above 1 (oetf(1) may evaluate a hair below 1) = 30 KB, 4 copies interleaved entry by entry ([h][lane & 3]: the address is one
+//           multiply-add, and the 16 lanes of copies 0-1 / 2-3 spread over the 16 even / odd banks: fewer wavefronts
+//           per look-up than 32 lanes over one 128 KB table; word-interleaved copies conflict less still but their
+//           address arithmetic made the kernel issue-bound at the same speed);
 //   alpha:  A[a2] = encode(decode(a2)) (not the identity: f16(1/3) * 3 truncates to 0).
 //
 // Results equal k_rowwise_fast<K_RGB10, K_RGB10> and the generic kernel bit for bit (tests); instead of
@@ -23,9 +28,11 @@ ZOS_DEFINE_CONSTANT_UPLOAD(upload_constants_rowwise_rgb10)
 
 namespace {
 constexpr int THREADS = 1024;
-constexpr int DR = 8;                                  // copies of the decode table
-constexpr uint32_t DEC_BYTES = 1024u * DR * 4u;        // [code][lane & 7]
-constexpr uint32_t ENC_BYTES = 65536u * 2u;            // [f16 bits] -> 10-bit code
+constexpr int DR = 16;                                 // copies of the decode table
+constexpr uint32_t DEC_BYTES = 1024u * DR * 4u;        // [code][lane & 15]
+constexpr int ER = 4;                                  // copies of the encode table
+constexpr uint32_t ENC_N = 0x3c00u + 2u;               // f16 patterns of [0, 1], padded to whole words
+constexpr uint32_t ENC_BYTES = ENC_N * ER * 2u;        // [h][lane & 3] u16 entries
 constexpr uint32_t SMEM_BYTES = DEC_BYTES + ENC_BYTES;
 
 __device__ __forceinline__ float lds_f32(uint32_t a) {
@@ -42,6 +49,12 @@ __device__ __forceinline__ uint32_t half_bits(float v) {
   return (uint32_t)__half_as_ushort(__float2half_rn(v));
 }
 
+// byte address of entry h = f16(clamp01(v)) in this lane's copy
+__device__ __forceinline__ uint32_t enc_addr(uint32_t enc_lane, float v) {
+  const uint32_t h = min(half_bits(fmaxf(v, 0.0f)), ENC_N - 1u);  // fmaxf(NaN, 0) = 0 like clamp01; the last entry stands for everything above 1
+  return enc_lane + h * (ER * 2u);
+}
+
 template <int NMAT>
 __device__ __forceinline__ uint32_t pixel(const FastParams& P, uint32_t w, uint32_t dec_lane, uint32_t enc, uint32_t amap) {
   float r = lds_f32(dec_lane + (w & 1023u) * (DR * 4u));
@@ -52,7 +65,7 @@ __device__ __forceinline__ uint32_t pixel(const FastParams& P, uint32_t w, uint3
     float3 t = mat3_mul(P.m[k], r, g, b);
     r = t.x; g = t.y; b = t.z;
   }
-  const uint32_t cr = lds_u16(enc + half_bits(r) * 2u), cg = lds_u16(enc + half_bits(g) * 2u), cb = lds_u16(enc + half_bits(b) * 2u);
+  const uint32_t cr = lds_u16(enc_addr(enc, r)), cg = lds_u16(enc_addr(enc, g)), cb = lds_u16(enc_addr(enc, b));
   const uint32_t a2 = (amap >> ((w >> 30) * 2u)) & 3u;
   return cr + (cg << 10) + (cb << 20) + (a2 << 30);
 }
@@ -69,10 +82,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_rowwise_rgb10(const __grid_const
     if (src_srgb) p = eo_srgb(p);
     dec[i] = f16r(p);
   }
-  for (int h = threadIdx.x; h < 65536; h += THREADS) {
-    float r = __half2float(__ushort_as_half((unsigned short)h));  // what the f16 attachment holds
+  for (int i = threadIdx.x; i < (int)(ENC_N * ER); i += THREADS) {
+    const uint32_t h = (uint32_t)i / ER, c = (uint32_t)i % ER;
+    float r = __half2float(__ushort_as_half((unsigned short)h));  // what the f16 attachment holds (0x3c01: any value above 1)
     if (dst_srgb) r = oe_srgb(r);
-    enc[h] = (uint16_t)(uint32_t)(clamp01(r) * 1023.0f);
+    enc[h * ER + c] = (uint16_t)(uint32_t)(clamp01(r) * 1023.0f);
   }
   uint32_t amap = 0;
 #pragma unroll
@@ -82,11 +96,23 @@ __global__ void __launch_bounds__(THREADS, 1) k_rowwise_rgb10(const __grid_const
   }
   __syncthreads();
   const uint32_t dec_lane = (uint32_t)__cvta_generic_to_shared(dec) + (threadIdx.x & (DR - 1)) * 4u;
-  const uint32_t enc_base = (uint32_t)__cvta_generic_to_shared(enc);
+  const uint32_t enc_base = (uint32_t)__cvta_generic_to_shared(enc) + (threadIdx.x & (ER - 1)) * 2u;
   const uint32_t stride = gridDim.x * THREADS;
-  for (uint32_t idx = blockIdx.x * THREADS + threadIdx.x; idx < P.total_groups; idx += stride) {
-    const Loc L = locate<0>(P, idx);
-    const uint4 rb = __ldcs(reinterpret_cast<const uint4*>(P.below + L.ob));
+  // software pipeline: the next group's 16 bytes are in flight while the current group goes through its
+  // ~200 instructions (one CTA of 32 warps per SM: without it every warp idles for a full DRAM round trip
+  // per group -- 41 % of the stall samples, profiles/r01_c5_rgb10_kernel.txt)
+  uint32_t idx = blockIdx.x * THREADS + threadIdx.x;
+  if (idx >= P.total_groups) return;
+  Loc L = locate<0>(P, idx);
+  uint4 rb = __ldcs(reinterpret_cast<const uint4*>(P.below + L.ob));
+  for (;;) {
+    const uint32_t nidx = idx + stride;
+    const bool more = nidx > idx && nidx < P.total_groups;  // (32-bit wrap ends the walk)
+    const Loc Ln = locate<0>(P, more ? nidx : idx);
+    uint4 rn = rb;
+    // (volatile + predicated: the compiler otherwise sinks the conditional load below the arithmetic)
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
+                 : "+r"(rn.x), "+r"(rn.y), "+r"(rn.z), "+r"(rn.w) : "l"(P.below + Ln.ob), "r"((uint32_t)more) : "memory");
     uint32_t o[4];
     o[0] = pixel<NMAT>(P, rb.x, dec_lane, enc_base, amap); o[1] = pixel<NMAT>(P, rb.y, dec_lane, enc_base, amap);
     o[2] = pixel<NMAT>(P, rb.z, dec_lane, enc_base, amap); o[3] = pixel<NMAT>(P, rb.w, dec_lane, enc_base, amap);
@@ -98,7 +124,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_rowwise_rgb10(const __grid_const
       for (int i = 0; i < 3; i++)
         if (i < L.npx) reinterpret_cast<uint32_t*>(dp)[i] = o[i];
     }
-    if (idx + stride < idx) break;  // 32-bit wrap
+    if (!more) break;
+    idx = nidx; L = Ln; rb = rn;
   }
 }
 
