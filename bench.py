@@ -259,28 +259,62 @@ def cpu_baseline_child(name, budget_s=12.0):
 
 # ------------------------------------------------------------------ clocks
 class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons sampled DURING the timed regions.  NVML is polled directly (about 1 ms per
+    sample, so even a few-millisecond region gets samples); `nvidia-smi` (tens of ms per call) is the fallback."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz, self.how = index, [], set(), False, None, None
 
-    def run(self):
+    def _nvml_handle(self):
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(self.index)
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)  # survives CUDA_VISIBLE_DEVICES
+        return pynvml, pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+
+    def _run_nvml(self):
+        nv, h = self._nvml_handle()
+        self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        bits = [nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown,
+                nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap]
+        self.how = "nvml"
+        while not self.stop_flag:
+            self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            for nme, bit in zip(self.NAMES, bits):
+                if r & bit:
+                    self.reasons.add(nme)
+            time.sleep(0.001)
+
+    def _run_smi(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        self.how = "nvidia-smi"
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip().split(",")
                 self.samples.append(float(out[0])); self.max_mhz = float(out[1])
-                for nme, v in zip(names, out[2:]):
+                for nme, v in zip(self.NAMES, out[2:]):
                     if v.strip().lower().startswith("active"):
                         self.reasons.add(nme)
             except Exception:
                 pass
             time.sleep(0.05)
 
+    def run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            if not self.stop_flag:
+                self._run_smi()
+
     def result(self):
         s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s),
+                "how": self.how}
 
 
 # ------------------------------------------------------------------ main
