@@ -66,6 +66,7 @@ struct TileGeo {
   int32_t bx, by;         // luma box origin (multiple of 32 / even), chroma box origin is half of it
   int32_t fx0, fy0;       // origin of the converted footprint (even)
   int32_t any;            // does the placement of the frame touch this tile at all
+  int32_t full;           // every pixel of the tile is a destination pixel covered by the frame (k_frame_fast's straight path)
 };
 
 __device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv& f) {
@@ -79,7 +80,7 @@ __device__ void tile_geometry(const FrameParams& P, uint32_t t, TileGeo& g) {
   uint32_t fr = fastdiv(r, P.div_ty);
   uint32_t tyi = r - fr * P.tiles_y;
   g.frame = (int)fr; g.x0 = (int)txi * TILE; g.y0 = (int)tyi * TILE;
-  g.bx = g.by = g.fx0 = g.fy0 = 0; g.any = 0;
+  g.bx = g.by = g.fx0 = g.fy0 = 0; g.any = 0; g.full = 0;
   const int x1 = min(g.x0 + TILE, P.dw) - 1, y1 = min(g.y0 + TILE, P.dh) - 1;
   const int ix0 = max(g.x0, P.tgt[0]), ix1 = min(x1, P.tgt[0] + P.tgt[2] - 1);
   const int iy0 = max(g.y0, P.tgt[1]), iy1 = min(y1, P.tgt[1] + P.tgt[3] - 1);
@@ -91,6 +92,7 @@ __device__ void tile_geometry(const FrameParams& P, uint32_t t, TileGeo& g) {
   g.bx = g.fx0 & ~31;  // 16-byte aligned TMA source address for the luma AND the (half width) chroma planes
   g.by = g.fy0;
   g.any = 1;
+  g.full = ix0 == g.x0 && iy0 == g.y0 && ix1 == g.x0 + TILE - 1 && iy1 == g.y0 + TILE - 1;
 }
 
 // EOTF of video samples (same code as gather.cu's yuv_eotf)
@@ -329,6 +331,9 @@ __global__ void __launch_bounds__(THREADS, 3) k_frame_fast(const __grid_constant
   extern __shared__ __align__(128) uint8_t dyn[];
   __shared__ __align__(8) uint64_t bar[2];
   __shared__ TileGeo geo[2];
+  // taps of a fully covered tile are separable: one entry per destination column and per destination row, worked
+  // out once per tile by 64 threads (the coordinates of a row are the same for all 32 lanes of a warp)
+  __shared__ __align__(16) uint4 ctab[TILE], rtab[TILE];  // {offset of tap a, offset of tap b, weight, -}
   const uint32_t cstep = P.nv12 ? 2 : 1;
   const uint32_t ybox = (uint32_t)P.box_w * P.box_h, cbox = (uint32_t)P.cbox_w * P.cbox_h * cstep;
   const uint32_t ybox_al = (ybox + 127) & ~127u, cbox_al = (cbox + 127) & ~127u;
@@ -365,6 +370,19 @@ __global__ void __launch_bounds__(THREADS, 3) k_frame_fast(const __grid_constant
         if (++spins > (1u << 24)) { if (P.fault) *reinterpret_cast<volatile int*>(P.fault) = 1; break; }
       }
       phase[s] ^= 1;
+      if (BILINEAR && g.full && threadIdx.x < 2 * TILE) {
+        // the arithmetic of the per-pixel path below, once per column (threads 0..31) and per row (32..63)
+        const bool col = threadIdx.x < TILE;
+        const int q = col ? (int)threadIdx.x : (int)threadIdx.x - TILE;
+        const int kq = (col ? g.x0 - P.tgt[0] : g.y0 - P.tgt[1]) + q;
+        const float p = (float)(col ? P.sel[0] : P.sel[1]) + ((float)kq + 0.5f) * (col ? P.rx : P.ry);
+        const float f = p - 0.5f, f0 = floorf(f);
+        const int i0 = (int)f0, lim = (col ? P.sw : P.sh) - 1, org = col ? g.fx0 : g.fy0;
+        const uint32_t unit = col ? 4u : cw4;
+        const uint4 e = make_uint4((uint32_t)(min(max(i0, 0), lim) - org) * unit, (uint32_t)(min(max(i0 + 1, 0), lim) - org) * unit,
+                                   __float_as_uint(f - f0), 0u);
+        if (col) ctab[q] = e; else rtab[q] = e;
+      }
       // ---- phase 1: the footprint, one 2x2 luma block per thread
       const uint32_t ybase = smem_u32(dyn + (size_t)s * stage_bytes);
       const uint32_t ubase = ybase + ybox_al, vbase = P.nv12 ? ubase + 1 : ubase + cbox_al;
@@ -391,7 +409,35 @@ __global__ void __launch_bounds__(THREADS, 3) k_frame_fast(const __grid_constant
     }
     // ---- phase 2: sample, pack
     const int i = g.x0 + lx;
-    if (i < P.dw) {
+    if (BILINEAR && g.full) {
+      // straight path: no coverage tests, no `below`; a pixel is 12 loads at column + row offsets, 3 lerps, 3 encodes
+      const uint4 ct = ctab[lx];
+      const float ax = __uint_as_float(ct.z);
+      const uint32_t ca = conv_base + ct.x, cb = conv_base + ct.y;
+      uint8_t* dp = P.dst + ((uint64_t)g.frame * P.dst_bstride + (uint64_t)(g.y0 + ly) * P.dst_pitch + (uint64_t)i * 4u);
+      const uint64_t dstep = 8u * P.dst_pitch;
+#pragma unroll
+      for (int k = 0; k < TILE / 8; k++) {
+        const uint4 rt = rtab[ly + 8 * k];
+        const float ay = __uint_as_float(rt.z);
+        const uint32_t a00 = ca + rt.x, a10 = cb + rt.x, a01 = ca + rt.y, a11 = cb + rt.y;
+        float r, gg, b;
+#define ZOS_TAP(dst_, off_) { const float p00 = lds32(a00 + (off_)), p10 = lds32(a10 + (off_)), p01 = lds32(a01 + (off_)), p11 = lds32(a11 + (off_)); \
+                              const float top = fmaf(ax, p10 - p00, p00), bot = fmaf(ax, p11 - p01, p01); dst_ = fmaf(ay, bot - top, top); }
+        ZOS_TAP(r, 0u) ZOS_TAP(gg, P.plane_bytes) ZOS_TAP(b, 2u * P.plane_bytes)
+#undef ZOS_TAP
+        r = fminf(fmaxf(r, 0.0f), 1.0f); gg = fminf(fmaxf(gg, 0.0f), 1.0f); b = fminf(fmaxf(b, 0.0f), 1.0f);
+        uint32_t t1, t2;
+        if (SRGB_DST) {
+          t1 = __byte_perm(srgb_code_b3(r, enc_lane), srgb_code_b3(gg, enc_lane), 0x0073);
+          t2 = __byte_perm(srgb_code_b3(b, enc_lane), 0xffu, 0x0043);
+        } else {
+          t1 = __byte_perm(__float_as_uint(r * 255.0f + 8388608.0f), __float_as_uint(gg * 255.0f + 8388608.0f), 0x0040);
+          t2 = __byte_perm(__float_as_uint(b * 255.0f + 8388608.0f), 0xffu, 0x0040);
+        }
+        __stcs(reinterpret_cast<uint32_t*>(dp + (uint64_t)k * dstep), __byte_perm(t1, t2, P.spack));
+      }
+    } else if (i < P.dw) {
       const int kx = i - P.tgt[0];
       const bool col_in = g.any && kx >= 0 && kx < P.tgt[2];
       uint32_t xa4 = 0, xb4 = 0;  // byte offsets of the horizontal taps inside a footprint row
