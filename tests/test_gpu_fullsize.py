@@ -63,13 +63,14 @@ def test_c3_full_size_affine_properties(ctx):
     ang = np.deg2rad(30.0)
     m = (O.shift(W / 2, H / 2) @ O.rotate(ang) @ O.shift(-W / 2, -H / 2)).astype(np.float32)
     inv = O.inv3(m.astype(np.float64)).astype(np.float32)
-    res = []
-    for flags in (0, 1):
-        ctx.set_flags(flags)
-        ops.compose(ctx, below, above, dst, ops.compose_params(map=_ffi.MAP_AFFINE, sampling=_ffi.SAMPLE_BILINEAR, inv=inv, use_tma=True))
-        res.append(dst.download())
-    ctx.set_flags(0)
-    assert np.array_equal(res[0], res[1])
+    for sampling in (_ffi.SAMPLE_NEAREST, _ffi.SAMPLE_BILINEAR):
+        res = []
+        for flags in (0, 1):
+            ctx.set_flags(flags)
+            ops.compose(ctx, below, above, dst, ops.compose_params(map=_ffi.MAP_AFFINE, sampling=sampling, inv=inv, use_tma=True))
+            res.append(dst.download())
+        ctx.set_flags(0)
+        assert np.array_equal(res[0], res[1])
     # and the oracle on a 256-row window of it (full-image coordinates through the window origin)
     y0, rows = 2048, 256
     band = O.decode(oracle_image(d, bel))[y0:y0 + rows].copy()

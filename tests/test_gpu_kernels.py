@@ -297,6 +297,36 @@ def test_affine_bilinear_f16(ctx, use_tma, angle, scale):
     assert np.array_equal(got2, tex.astype(np.float16))
 
 
+@pytest.mark.parametrize("sampling", [_ffi.SAMPLE_NEAREST, _ffi.SAMPLE_BILINEAR])
+@pytest.mark.parametrize("with_below", [False, True])
+def test_affine_f16_special_values_equal_general_kernel(ctx, sampling, with_below):
+    """The dedicated RGBA16F affine kernel moves nearest taps and `below` texels as raw words and forms lerp
+    differences with the mixed-precision add: infinities, signed zeros, subnormals and the largest finite halves
+    must come out like the general gather kernel's (which converts every texel to f32 and back)."""
+    W, H, w, h = 300, 200, 260, 170
+    rng = np.random.default_rng(17)
+    pool = np.array([0x0000, 0x8000, 0x0001, 0x03ff, 0x0400, 0x7bff, 0xfbff, 0x7c00, 0xfc00, 0x3c00, 0xbc00, 0x3555], np.uint16)
+    a16 = rng.random((h, w, 4), dtype=np.float32).astype(np.float16).view(np.uint16)
+    b16 = rng.random((H, W, 4), dtype=np.float32).astype(np.float16).view(np.uint16)
+    ma, mb = rng.random((h, w, 4)) < 0.05, rng.random((H, W, 4)) < 0.05
+    a16[ma] = rng.choice(pool, int(ma.sum())); b16[mb] = rng.choice(pool, int(mb.sum()))
+    t = Texel.new_f16(); c = Color.Rgb(Z.Primaries.Bt709, Transfer.Linear)
+    da, dbb = zdesc(w, h, t, c), zdesc(W, H, t, c)
+    m = (O.shift(W / 2, H / 2) @ O.rotate(np.deg2rad(23.0)) @ O.shift(-w / 2, -h / 2)).astype(np.float32)
+    inv = O.inv3(m.astype(np.float64)).astype(np.float32)
+    below, above = ctx.upload(dbb, b16.view(np.uint8).reshape(H, W * 8)), ctx.upload(da, a16.view(np.uint8).reshape(h, w * 8))
+    res = []
+    for flags in (0, 1):
+        ctx.set_flags(flags)
+        dst = ctx.image(dbb)
+        ops.compose(ctx, below if with_below else None, above, dst, ops.compose_params(map=_ffi.MAP_AFFINE, sampling=sampling, inv=inv))
+        res.append(dst.download().view(np.uint16))
+    ctx.set_flags(0)
+    nan0, nan1 = np.isnan(res[0].view(np.float16)), np.isnan(res[1].view(np.float16))
+    assert np.array_equal(nan0, nan1)                       # inf - inf in a lerp: NaN in both
+    assert np.array_equal(res[0][~nan0], res[1][~nan0])
+
+
 @pytest.mark.parametrize("mode", list(range(12)))
 def test_porter_duff_bit_exact(ctx, mode):
     """BASELINE config 2 at test size: blend two RGBA8 sRGB layers in linear light (ours; the
@@ -700,6 +730,35 @@ def test_fused_frame_pipeline(ctx, nv12, chroma_filter):
         exp = O.encode(oracle_desc(od), canvas).data
         assert max_lsb(outs[0][f], exp) <= 1
         assert np.mean(outs[0][f] == exp) > 0.99
+
+
+@pytest.mark.parametrize("tgt", [(37, 21, 200, 120), (0, 0, 320, 180), (64, 32, 96, 64), (300, 170, 60, 40)])
+def test_frame_fast_placements_equal_general_kernels(ctx, tgt):
+    """k_frame_fast takes a straight path (separable tap tables, no coverage tests) for destination tiles the
+    frame covers completely and the per-pixel path for the others: frames placed at offsets that leave fully
+    covered, partly covered and untouched tiles (and a placement hanging over the edge) must give the bytes of
+    the general kernels (ZOS_CTX_NO_FAST_PATHS)."""
+    W, H, w, h, N = 480, 270, 320, 180, 2
+    rng = np.random.default_rng(81)
+    d = Z.yuv420_descriptor(W, H, Color.Rgb(Z.Primaries.Bt2020, Transfer.Bt709), Z.YuvMatrix.Bt709, False, False, 0)
+    ys = rng.integers(16, 236, (N, H, W), dtype=np.uint8)
+    us = rng.integers(16, 241, (N, H // 2, W // 2), dtype=np.uint8); vs = rng.integers(16, 241, (N, H // 2, W // 2), dtype=np.uint8)
+    src = ctx.image(d, N)
+    src.upload((ys, us, vs))
+    od = zdesc(w, h, Texel.new_u8(SampleParts.RgbA), Color.SRGB)
+    bg = ctx.upload(od, rng.integers(0, 256, (h, w * 4), dtype=np.uint8))
+    M = O.mul3(O.inv3(O.to_xyz("bt709", "D65")), O.to_xyz("bt2020", "D65"))
+    res = []
+    for flags in (0, 1):
+        ctx.set_flags(flags)
+        dst = ctx.image(od, N)
+        p = ops.compose_params(map=_ffi.MAP_RECT, sampling=_ffi.SAMPLE_BILINEAR, blend=_ffi.BLEND_SRC_OVER, sel=(0, 0, W, H), tgt=tgt,
+                               src_steps=[ops.matrix(M)])
+        ops.compose(ctx, bg, src, dst, p)
+        res.append(dst.download())
+    ctx.set_flags(0)
+    assert np.array_equal(res[0], res[1])
+    assert not np.array_equal(res[0][0], bg.download())  # the frame was drawn
 
 
 @pytest.mark.parametrize("bits,parts,n", [(SampleBits.UInt16, SampleParts.Luma, 16), (SampleBits.UInt1010102, SampleParts.RgbA, 10),
