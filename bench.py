@@ -325,9 +325,9 @@ def run_reference(args):
     if rank != 0:
         return
     name = args.workload
-    from oracle import oracle as O
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    os.environ["OMP_NUM_THREADS"] = str(cores)  # all host threads (torchrun exports OMP_NUM_THREADS=1 to its workers); before libgomp loads
+    from oracle import oracle as O
     W, H = 3840, 2160
     rng = np.random.default_rng(1)
     od = O.srgb_rgba8(W, H)
