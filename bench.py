@@ -169,12 +169,12 @@ def make_gpu_workload(name, ctx, frames, seed):
         v[rng.random(v.shape) < 0.01] *= 4.0
         tile = np.tile(v.astype(np.float16), (1, H // 270, 1)).view(np.uint8)
         _replicate(ctx, below, tile); _replicate(ctx, above, tile[:, ::-1].copy())
-        ang = np.deg2rad(30.0)
+        ang = np.deg2rad(C3_ANGLE_DEG)
         m = (O.shift(W / 2, H / 2) @ O.rotate(ang) @ O.shift(-W / 2, -H / 2)).astype(np.float32)
         inv = O.inv3(m.astype(np.float64)).astype(np.float32)
         p = ops.compose_params(map=_ffi.MAP_AFFINE, sampling=_ffi.SAMPLE_BILINEAR if name.endswith("bilinear") else _ffi.SAMPLE_NEAREST,
                                inv=inv, use_tma=True)
-        wl = Workload(name, "affine rotate 30deg, %s, RGBA16F over RGBA16F" % name.split("_")[-1], W * H, W * H, W * H * 16, frames)
+        wl = Workload(name, "affine rotate %gdeg, %s, RGBA16F over RGBA16F" % (C3_ANGLE_DEG, name.split("_")[-1]), W * H, W * H, W * H * 16, frames)
         return wl, (lambda: ops.compose(ctx, below, above, dst, p)), None
 
     if name == "c4_fused":
@@ -255,6 +255,9 @@ def cpu_baseline_child(name, budget_s=12.0):
             break
     return {"value": round(px * n / dt / 1e6, 2), "unit": "MP/s", "cores": cores, "kind": "port",
             "sample": "%s, %d repetitions in %.1f s, oracle/zos_oracle.c with OpenMP on %d threads" % (sample, n, dt, cores)}
+
+
+C3_ANGLE_DEG = 30.0
 
 
 # ------------------------------------------------------------------ clocks
@@ -362,6 +365,7 @@ def main():
     ap.add_argument("--workload", default="c2_blend")
     ap.add_argument("--frames", type=int, default=16, help="frames per step per GPU")
     ap.add_argument("--impl", default="ours")
+    ap.add_argument("--angle", type=float, default=30.0, help="rotation of the c3_affine_* workloads in degrees (BASELINE: 30)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-baseline-child", default=None, help=argparse.SUPPRESS)
     ap.add_argument("--budget", type=float, default=12.0, help=argparse.SUPPRESS)
@@ -371,6 +375,8 @@ def main():
         return
     if args.impl == "reference":
         return run_reference(args)
+    global C3_ANGLE_DEG
+    C3_ANGLE_DEG = args.angle
 
     import torch
     import torch.distributed as dist

@@ -353,7 +353,11 @@ __device__ __forceinline__ void copy_tile(const AffParams& P, const Geo& g, cons
 // tiles that need none).  (Measured and dropped: cp.async.bulk.prefetch.tensor of the box into L2 at geometry
 // time -- 0.72 -> 0.61 of the HBM peak at 2 frames, 0.49 at 16: the prefetched lines displace the overlap between
 // neighbouring boxes that L2 serves today.  Also measured and dropped: the producer warp staging the box with
-// 16-byte cp.async copies instead of the TMA box load -- 0.72 -> 0.32-0.38.)  A consumer warp that is done with stage s arrives on
+// 16-byte cp.async copies instead of the TMA box load -- 0.72 -> 0.32-0.38; prefetch.global.L2 of the box's lines
+// from the producer warp's idle lanes 1, 2 or 4 tiles ahead -- 0.73 -> 0.60 (nearest), 0.50 (bilinear).  Every
+// extra request for a line costs L2 slice throughput, and that is the bound: SM-side traffic (2.3x the source
+// texels used + `below` + stores, 1.6 GB per launch) plus the DRAM-side fills and write-backs (1.06 GB) pass
+// through the slices at ~12 TB/s, their measured cap; a 0.5 degree rotation (box 1.35x) runs at the same speed.)  A consumer warp that is done with stage s arrives on
 // `empty[s]` (8 arrivals free the stage).  There is no CTA-wide barrier in the loop: warps drift apart by up
 // to STAGES tiles, and the ~250 serial instructions of the geometry are off the compute warps' critical path.
 constexpr int STAGES = 3;
