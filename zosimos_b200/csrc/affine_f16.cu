@@ -40,6 +40,7 @@ struct AffParams {
   uint32_t tiles_x, tiles_y, total_tiles;
   FastDiv div_frame, div_band;  // tiles per frame, tiles per band of 8 tile rows
   int32_t box_w, box_h;
+  int32_t margin;    // texels a tap may lie outside of [floor(min), floor(max)] of the mapped corners: 1 bilinear, 0 nearest
   float sfwf, sfhf;  // (float)sfw, (float)sfh
   int* fault;  // mapped host word set when an mbarrier wait runs away
 };
@@ -95,8 +96,9 @@ __device__ void tile_geometry(const AffParams& P, uint32_t t, Geo& g) {
   // The mapping is monotone in x and in y separately, in floating point too (fmaf is monotone in each
   // argument), so the corner values bound every pixel of the tile exactly; bilinear taps of a pixel at p
   // are floor(p - 0.5) and that + 1, i.e. within [floor(min) - 1, floor(max) + 1].
-  int lox = max((int)floorf(minx) - 1 - P.sox, 0), hix = min((int)floorf(maxx) + 1 - P.sox, P.aw - 1);
-  int loy = max((int)floorf(miny) - 1 - P.soy, 0), hiy = min((int)floorf(maxy) + 1 - P.soy, P.ah - 1);
+  // (a nearest tap of a pixel at p is floor(p): no margin)
+  int lox = max((int)floorf(minx) - P.margin - P.sox, 0), hix = min((int)floorf(maxx) + P.margin - P.sox, P.aw - 1);
+  int loy = max((int)floorf(miny) - P.margin - P.soy, 0), hiy = min((int)floorf(maxy) + P.margin - P.soy, P.ah - 1);
   if (lox > hix || loy > hiy) return;
   lox &= ~1;  // 8-byte texels: a 16-byte aligned TMA source address
   g.any = 1;
@@ -475,11 +477,12 @@ zos_status launch_affine_f16(zos_ctx* ctx, const DevImage* below, const DevImage
   P.div_frame = make_fastdiv(P.tiles_x * P.tiles_y); P.div_band = make_fastdiv(8u * P.tiles_x);
   const float ex = (TILE - 1) * (fabsf(P.inv[0]) + fabsf(P.inv[1])), ey = (TILE - 1) * (fabsf(P.inv[3]) + fabsf(P.inv[4]));
   if (!(ex < 200.0f) || !(ey < 200.0f)) return ZOS_OK;
-  // taps span ceil(extent) + 4 texels, + 1 for the even box origin; a row of 8 * (4k + 2) bytes puts
+  // taps span ceil(extent) + 2 texels + the sampling margin on both sides, + 1 for the even box origin; a row of 8 * (4k + 2) bytes puts
   // vertically adjacent taps 4 banks apart (a multiple of 128 bytes would put them on the same bank)
-  P.box_w = (int)ceilf(ex) + 5;
+  P.margin = cp.sampling == ZOS_SAMPLE_BILINEAR ? 1 : 0;
+  P.box_w = (int)ceilf(ex) + 3 + 2 * P.margin;
   while ((P.box_w & 3) != 2) P.box_w++;
-  P.box_h = (int)ceilf(ey) + 4;
+  P.box_h = (int)ceilf(ey) + 2 + 2 * P.margin;
   const size_t stage = ((size_t)P.box_w * P.box_h * 8 + 127) & ~(size_t)127;
   const size_t smem = STAGES * stage;
   if (P.box_w * 2 > 256 || P.box_h > 256 || smem > 144 * 1024) return ZOS_OK;
