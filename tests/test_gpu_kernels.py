@@ -554,16 +554,17 @@ def test_lab_kernel_equals_generic(ctx, space, parts):
 
 @pytest.mark.parametrize("src_tr", ["Srgb", "Linear"])
 @pytest.mark.parametrize("dst_tr", ["Srgb", "Linear"])
-def test_rgb10a2_table_kernel_equals_generic(ctx, src_tr, dst_tr):
+@pytest.mark.parametrize("W", [1023, 1024])  # 1024: rows fill their pitch -> the kernel's linear-addressing variant
+def test_rgb10a2_table_kernel_equals_generic(ctx, src_tr, dst_tr, W):
     """rowwise_rgb10.cu (decode / encode tables built from the codec's own code) against the generic
     interpreter and the oracle: every 10-bit code in every channel, every alpha code, random words,
     0..2 matrix steps (the second one pushes values outside [0, 1]: clamp and f16 overflow paths)."""
-    W, H = 1023, 40
+    H = 40
     rng = np.random.default_rng(33)
     words = rng.integers(0, 2**32, (H, W), dtype=np.uint64).astype(np.uint32)
     k = np.arange(1023, dtype=np.uint32)
-    words[0, :] = k | (k << 10) | (k << 20) | ((k & 3) << 30)
-    words[1, :] = (1023 - k) | (k << 10) | ((k ^ 0x155) << 20) | (((k >> 2) & 3) << 30)
+    words[0, :1023] = k | (k << 10) | (k << 20) | ((k & 3) << 30)
+    words[1, :1023] = (1023 - k) | (k << 10) | ((k ^ 0x155) << 20) | (((k >> 2) & 3) << 30)
     src = words.view(np.uint8).reshape(H, W * 4)
     tex = Texel(Z.Block.Pixel, Z.SampleBits.UInt1010102, SampleParts.RgbA)
     sd = zdesc(W, H, tex, Color.Rgb(Z.Primaries.Bt709, getattr(Transfer, src_tr)))

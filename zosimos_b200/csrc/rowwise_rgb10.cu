@@ -8,10 +8,11 @@
 //   encode: E[h]  = uint(clamp01(oetf(half(h))) * 1023) for the f16 bit patterns h of [0, 1] (the value stored
 //           in the f16 attachment is all the encoder ever sees; the clamp is applied BEFORE the f16 rounding,
 //           which commutes with it because 0 and 1 are f16 values and rounding is monotone), as u16:
-//           15361 entries + one for everything above 1 (oetf(1) may evaluate a hair below 1) = 30 KB, 4 copies interleaved entry by entry ([h][lane & 3]: the address is one
-//           multiply-add, and the 16 lanes of copies 0-1 / 2-3 spread over the 16 even / odd banks: fewer wavefronts
-//           per look-up than 32 lanes over one 128 KB table; word-interleaved copies conflict less still but their
-//           address arithmetic made the kernel issue-bound at the same speed);
+//           15361 entries + one for everything above 1 (oetf(1) may evaluate a hair below 1) = 30 KB, 4 copies
+//           interleaved entry by entry ([h][lane & 3]: the address is one multiply-add, and the 16 lanes of copies
+//           0-1 / 2-3 spread over the 16 even / odd banks: 2.65 wavefronts per look-up instead of 3.2 for one
+//           128 KB table; word-interleaved copies were measured twice and are no faster, their address costs
+//           three more integer instructions per channel);
 //   alpha:  A[a2] = encode(decode(a2)) (not the identity: f16(1/3) * 3 truncates to 0).
 //
 // Results equal k_rowwise_fast<K_RGB10, K_RGB10> and the generic kernel bit for bit (tests); instead of
@@ -70,7 +71,7 @@ __device__ __forceinline__ uint32_t pixel(const FastParams& P, uint32_t w, uint3
   return cr + (cg << 10) + (cb << 20) + (a2 << 30);
 }
 
-template <int NMAT>
+template <int NMAT, bool LINEAR>
 __global__ void __launch_bounds__(THREADS, 1) k_rowwise_rgb10(const __grid_constant__ FastParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   float* dec = reinterpret_cast<float*>(smem);
@@ -98,11 +99,36 @@ __global__ void __launch_bounds__(THREADS, 1) k_rowwise_rgb10(const __grid_const
   const uint32_t dec_lane = (uint32_t)__cvta_generic_to_shared(dec) + (threadIdx.x & (DR - 1)) * 4u;
   const uint32_t enc_base = (uint32_t)__cvta_generic_to_shared(enc) + (threadIdx.x & (ER - 1)) * 2u;
   const uint32_t stride = gridDim.x * THREADS;
+  uint32_t idx = blockIdx.x * THREADS + threadIdx.x;
+  if (idx >= P.total_groups) return;
+  if constexpr (LINEAR) {
+    // source and destination are plain streams of 16-byte groups (rows and frames back to back, width a multiple
+    // of 4): no index arithmetic (the two divisions + 64-bit offsets of locate() were 14 of 60 instructions per
+    // pixel on a kernel bound by its integer work), the loads of the next two groups in flight
+    constexpr int D = 3;
+    const uint32_t mine = (P.total_groups - 1u - idx) / stride + 1u;  // groups of this thread: idx + k * stride, k < mine
+    const uint4* pb = reinterpret_cast<const uint4*>(P.below) + idx;
+    uint4* pd = reinterpret_cast<uint4*>(P.dst) + idx;
+    uint4 b[D];
+#pragma unroll
+    for (int j = 0; j < D; j++) b[j] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int j = 0; j < D - 1; j++)
+      if ((uint32_t)j < mine) b[j] = __ldcs(pb + (size_t)j * stride);
+    for (uint32_t k = 0;; k += D) {
+#pragma unroll
+      for (int j = 0; j < D; j++) {
+        if (k + j >= mine) return;
+        if (k + j + (D - 1) < mine) b[(j + D - 1) % D] = __ldcs(pb + (size_t)(j + D - 1) * stride);
+        __stcs(pd + (size_t)j * stride, make_uint4(pixel<NMAT>(P, b[j].x, dec_lane, enc_base, amap), pixel<NMAT>(P, b[j].y, dec_lane, enc_base, amap),
+                                                    pixel<NMAT>(P, b[j].z, dec_lane, enc_base, amap), pixel<NMAT>(P, b[j].w, dec_lane, enc_base, amap)));
+      }
+      pb += (size_t)D * stride; pd += (size_t)D * stride;
+    }
+  } else {
   // software pipeline: the next group's 16 bytes are in flight while the current group goes through its
   // ~200 instructions (one CTA of 32 warps per SM: without it every warp idles for a full DRAM round trip
   // per group -- 41 % of the stall samples, profiles/r01_c5_rgb10_kernel.txt)
-  uint32_t idx = blockIdx.x * THREADS + threadIdx.x;
-  if (idx >= P.total_groups) return;
   Loc L = locate<0>(P, idx);
   uint4 rb = __ldcs(reinterpret_cast<const uint4*>(P.below + L.ob));
   for (;;) {
@@ -127,17 +153,25 @@ __global__ void __launch_bounds__(THREADS, 1) k_rowwise_rgb10(const __grid_const
     if (!more) break;
     idx = nidx; L = Ln; rb = rn;
   }
+  }
 }
 
 template <int NMAT>
 cudaError_t launch_one(zos_ctx* ctx, const FastParams& P) {
   {
-    cudaError_t e = ensure_dyn_smem(ctx, k_rowwise_rgb10<NMAT>, (int)SMEM_BYTES);
+    cudaError_t e = ensure_dyn_smem(ctx, k_rowwise_rgb10<NMAT, false>, (int)SMEM_BYTES);
+    if (e == cudaSuccess) e = ensure_dyn_smem(ctx, k_rowwise_rgb10<NMAT, true>, (int)SMEM_BYTES);
     if (e != cudaSuccess) return e;
   }
   const uint64_t ctas = ((uint64_t)P.total_groups + THREADS - 1) / THREADS;
   const int grid = (int)(ctas < (uint64_t)ctx->sm_count ? ctas : (uint64_t)ctx->sm_count);
-  k_rowwise_rgb10<NMAT><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(P);
+  // linear addressing: rows and frames of source and destination back to back, whole groups only
+  const uint64_t row = (uint64_t)P.w * 4u, frame = row * P.h;
+  const bool one = (uint64_t)P.total_groups == (uint64_t)P.groups_per_row * (uint64_t)P.h;  // a single frame: frame strides are not used
+  const bool linear = (P.w % 4 == 0) && P.below_pitch == row && P.dst_pitch == row && (one || (P.below_bstride == frame && P.dst_bstride == frame)) &&
+                      ((uintptr_t)P.below % 16 == 0) && ((uintptr_t)P.dst % 16 == 0);
+  if (linear) k_rowwise_rgb10<NMAT, true><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(P);
+  else k_rowwise_rgb10<NMAT, false><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(P);
   return cudaGetLastError();
 }
 }  // namespace
