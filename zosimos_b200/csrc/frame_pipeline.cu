@@ -282,7 +282,9 @@ __global__ void __launch_bounds__(THREADS, 3) k_frame_pipeline(const __grid_cons
 //   * the converted footprint is kept as three f32 planes (no alpha plane), sized by the exact tap span;
 //   * sRGB8 encode through the bucket table (texel.cuh): one look-up per channel, no transcendental;
 //   * no run-time format / transfer / sampling switches.
-constexpr int FER = 8;  // copies of the (biased-key, texel.cuh) encoder bucket table in shared memory
+constexpr int FER = 2;  // copies of the (biased-key, texel.cuh) encoder bucket table in shared memory: 5 KB, so that 4 CTAs fit
+                        // an SM (8 copies and 3 CTAs: 0.170 of the HBM peak on C4; 2 copies and 4 CTAs: 0.178 -- the three encoder
+                        // look-ups of a pixel conflict more, the two CTA barriers per tile hurt less)
 
 template <int TRK>
 __device__ __forceinline__ float eotf_k(uint32_t tr, float v) {
@@ -327,7 +329,7 @@ __device__ __forceinline__ uint32_t srgb_code_b3(float x, uint32_t enc_lane) {
 }
 
 template <bool BILINEAR, bool SRGB_DST, int TRK>
-__global__ void __launch_bounds__(THREADS, 3) k_frame_fast(const __grid_constant__ FrameParams P, const __grid_constant__ TensorMaps M) {
+__global__ void __launch_bounds__(THREADS, 4) k_frame_fast(const __grid_constant__ FrameParams P, const __grid_constant__ TensorMaps M) {
   extern __shared__ __align__(128) uint8_t dyn[];
   __shared__ __align__(8) uint64_t bar[2];
   __shared__ TileGeo geo[2];
@@ -604,7 +606,7 @@ zos_status launch_frame_pipeline(zos_ctx* ctx, const DevImage* below, const DevI
             make_map(ctx, &M.m2, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, above.p2, cw, ch, above.cpitch, batch, above.cbstride, P.cbox_w, P.cbox_h);
     if (ok2 && fsmem <= 160 * 1024) {
       int per_sm = (int)((226 * 1024) / (fsmem + 1024 + 256));
-      per_sm = per_sm < 1 ? 1 : (per_sm > 3 ? 3 : per_sm);
+      per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
       const uint64_t cap = (uint64_t)ctx->sm_count * per_sm;
       const int grid = (int)(total < cap ? total : cap);
       const bool bil = cp.sampling != ZOS_SAMPLE_NEAREST;
