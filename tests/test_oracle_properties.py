@@ -1,0 +1,157 @@
+"""Property tests of the oracle for the semantics that have NO reference implementation (SURVEY.md 8c /
+DESIGN.md section 3: Porter-Duff blending, bilinear sampling, planar YUV 4:2:0, float texels).  The
+reference's goldens cannot pin these, so the definitions are checked against the algebra they are meant
+to implement: identities, the classic Porter-Duff table, associativity of `over`, round trips.  CPU only.
+"""
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from oracle import oracle as O
+
+SET = settings(max_examples=25, deadline=None)
+
+
+def rgba(rng, h, w, alpha=None):
+    t = rng.random((h, w, 4), dtype=np.float32)
+    if alpha is not None:
+        t[..., 3] = alpha
+    return t
+
+
+def premul(t):
+    return np.concatenate([t[..., :3].astype(np.float64) * t[..., 3:4], t[..., 3:4].astype(np.float64)], -1)
+
+
+# ---------------------------------------------------------------- Porter-Duff (command.rs:1510-1519 is UNIMPLEMENTED)
+@SET
+@given(seed=st.integers(0, 2**31 - 1), mode=st.integers(0, 11))
+def test_porter_duff_matches_the_premultiplied_table(seed, mode):
+    """co = Fa * cs + Fb * cd on premultiplied colours with the classic (Fa, Fb) pairs (Porter & Duff 1984,
+    table 1); the oracle works on straight alpha with one reciprocal, so compare after premultiplying."""
+    rng = np.random.default_rng(seed)
+    s, d = rgba(rng, 5, 7), rgba(rng, 5, 7)
+    if seed % 3 == 0:
+        s[0, :, 3] = 0.0; d[1, :, 3] = 0.0; s[2, :, 3] = 1.0; d[3, :, 3] = 1.0
+    out = O.blend_pass(d.copy(), s, 0, 0, mode)
+    a_s, a_d = s[..., 3:4].astype(np.float64), d[..., 3:4].astype(np.float64)
+    fa, fb = {0: (0 * a_s, 0 * a_s), 1: (1 + 0 * a_s, 0 * a_s), 2: (0 * a_s, 1 + 0 * a_s), 3: (1 + 0 * a_s, 1 - a_s), 4: (1 - a_d, 1 + 0 * a_s),
+              5: (a_d, 0 * a_s), 6: (0 * a_s, a_s), 7: (1 - a_d, 0 * a_s), 8: (0 * a_s, 1 - a_s), 9: (a_d, 1 - a_s), 10: (1 - a_d, a_s),
+              11: (1 - a_d, 1 - a_s)}[mode]
+    exp = fa * premul(s) + fb * premul(d)
+    assert np.allclose(premul(out), exp, atol=2e-6)
+    assert np.all(out[..., :3][out[..., 3] == 0] == 0)  # alpha 0 -> colour 0, not NaN
+
+
+@SET
+@given(seed=st.integers(0, 2**31 - 1))
+def test_over_identities(seed):
+    rng = np.random.default_rng(seed)
+    d = rgba(rng, 4, 6)
+    clear = rgba(rng, 4, 6, alpha=0.0)
+    opaque = rgba(rng, 4, 6, alpha=1.0)
+    assert np.array_equal(O.blend_pass(d.copy(), clear, 0, 0, 3)[..., 3], d[..., 3])       # transparent source: alpha kept exactly
+    assert np.allclose(O.blend_pass(d.copy(), clear, 0, 0, 3), d, rtol=3e-7, atol=1e-7)    # ... colour within one rounding of c * a / a
+    assert np.array_equal(O.blend_pass(d.copy(), opaque, 0, 0, 3), opaque)                  # opaque source replaces, exactly
+    assert np.array_equal(O.blend_pass(d.copy(), opaque, 0, 0, 1), opaque)                  # `src`
+    assert np.allclose(O.blend_pass(d.copy(), opaque, 0, 0, 2), d, rtol=3e-7, atol=1e-7)   # `dst`
+    assert np.all(O.blend_pass(d.copy(), opaque, 0, 0, 0) == 0)                             # `clear`
+
+
+@SET
+@given(seed=st.integers(0, 2**31 - 1))
+def test_over_is_associative(seed):
+    rng = np.random.default_rng(seed)
+    a, b, c = rgba(rng, 3, 5), rgba(rng, 3, 5), rgba(rng, 3, 5)
+    left = O.blend_pass(O.blend_pass(c.copy(), b, 0, 0, 3), a, 0, 0, 3)        # a over (b over c)
+    ab = O.blend_pass(b.copy(), a, 0, 0, 3)
+    right = O.blend_pass(c.copy(), ab, 0, 0, 3)                                # (a over b) over c
+    assert np.allclose(premul(left), premul(right), atol=3e-6)
+
+
+def test_blend_placement_clips():
+    rng = np.random.default_rng(5)
+    d, s = rgba(rng, 6, 8), rgba(rng, 4, 4, alpha=1.0)
+    out = O.blend_pass(d.copy(), s, 6, 4, 3)  # only the top-left 2x2 of `s` lands inside
+    assert np.array_equal(out[4:, 6:], s[:2, :2])
+    mask = np.ones((6, 8), bool); mask[4:, 6:] = False
+    assert np.array_equal(out[mask], d[mask])
+    assert np.array_equal(O.blend_pass(d.copy(), s, -10, -10, 3), d)  # completely outside
+
+
+# ---------------------------------------------------------------- bilinear sampling (AffineSample::BiLinear is rejected, command.rs:1659-1665)
+@SET
+@given(seed=st.integers(0, 2**31 - 1), w=st.integers(1, 9), h=st.integers(1, 9))
+def test_resize_identity_and_constants(seed, w, h):
+    rng = np.random.default_rng(seed)
+    t = rgba(rng, h, w)
+    for sampling in (0, 1):
+        assert np.array_equal(O.resize_pass(t, w, h, sampling), t)      # same size: texel centres map onto texel centres
+    const = np.empty((h, w, 4), np.float32); const[:] = rng.random(4, dtype=np.float32)
+    out = O.resize_pass(const, 2 * w + 1, 3 * h + 2, 1)
+    assert np.array_equal(out, np.broadcast_to(const[0, 0], out.shape))  # fma(a, c - c, c) == c: no drift on flat fields
+
+
+def test_bilinear_is_linear_interpolation_with_edge_clamp():
+    ramp = np.zeros((1, 4, 4), np.float32); ramp[0, :, 0] = [0.0, 1.0, 2.0, 3.0]; ramp[..., 3] = 1.0
+    out = O.resize_pass(ramp, 8, 1, 1)[0, :, 0]   # centres at (i + 0.5) / 2 - 0.5 = -0.25, 0.25, 0.75, ...
+    assert np.allclose(out, [0.0, 0.25, 0.75, 1.25, 1.75, 2.25, 2.75, 3.0])
+    near = O.resize_pass(ramp, 8, 1, 0)[0, :, 0]
+    assert np.array_equal(near, [0, 0, 1, 1, 2, 2, 3, 3])
+
+
+@SET
+@given(seed=st.integers(0, 2**31 - 1))
+def test_affine_identity_and_integer_shift(seed):
+    rng = np.random.default_rng(seed)
+    src = rgba(rng, 7, 9)
+    ident = np.eye(3, dtype=np.float32).reshape(9)
+    for sampling in (0, 1):
+        dst = np.zeros((7, 9, 4), np.float32)
+        O.paint_affine(dst, src, ident, sampling)
+        assert np.array_equal(dst, src)
+        sx, sy = 2, 3
+        inv = np.array([1, 0, -sx, 0, 1, -sy, 0, 0, 1], np.float32)
+        bg = rgba(rng, 7, 9)
+        dst = bg.copy()
+        O.paint_affine(dst, src, inv, sampling)
+        assert np.array_equal(dst[sy:, sx:], src[:7 - sy, :9 - sx])   # covered: exact copy
+        assert np.array_equal(dst[:sy], bg[:sy]) and np.array_equal(dst[:, :sx], bg[:, :sx])  # uncovered: untouched
+
+
+# ---------------------------------------------------------------- planar YUV 4:2:0 (program.rs:794-938 lowers Block::Pixel only)
+@pytest.mark.parametrize("kr,kb", [(0.2126, 0.0722), (0.299, 0.114), (0.2627, 0.0593)])
+@pytest.mark.parametrize("full_range", [False, True])
+def test_yuv_grey_axis_and_round_trip(kr, kb, full_range):
+    """Neutral chroma decodes to R' = G' = B' = the luma ramp; encode(decode(.)) gives the codes back when every
+    2x2 block is flat (4:2:0 carries one chroma sample per block)."""
+    h, w = 16, 32
+    lo, hi = (0, 255) if full_range else (16, 235)
+    y = np.linspace(lo, hi, w * h // 4).round().astype(np.uint8).reshape(h // 2, w // 2).repeat(2, 0).repeat(2, 1)
+    u = np.full((h // 2, w // 2), 128, np.uint8); v = u.copy()
+    tex = O.decode_yuv420(y, u, v, w, h, kr, kb, full_range, False, 0, O.TR_LINEAR)
+    assert np.allclose(tex[..., 0], tex[..., 1], atol=1e-6) and np.allclose(tex[..., 1], tex[..., 2], atol=1e-6)
+    assert np.allclose(tex[..., 0], (y.astype(np.float32) - lo) / (hi - lo), atol=1e-6)
+    assert np.all(tex[..., 3] == 1.0)
+    rng = np.random.default_rng(11)
+    c_lo, c_hi = (0, 256) if full_range else (16, 241)
+    y2 = rng.integers(lo, hi + 1, (h // 2, w // 2), dtype=np.uint8).repeat(2, 0).repeat(2, 1)
+    u2 = rng.integers(c_lo, c_hi, (h // 2, w // 2), dtype=np.uint8); v2 = rng.integers(c_lo, c_hi, (h // 2, w // 2), dtype=np.uint8)
+    for tr in (O.TR_LINEAR, O.TR_BT709):
+        t2 = O.decode_yuv420(y2, u2, v2, w, h, kr, kb, full_range, False, 0, tr)
+        inside = np.all((t2[..., :3] >= 0.0) & (t2[..., :3] <= 1.0), -1)  # out-of-gamut YUV triples do not survive the [0, 1] working range of an EOTF
+        ye, ue, ve = O.encode_yuv420(t2, kr, kb, full_range, tr)
+        assert np.max(np.abs(ye.astype(int) - y2.astype(int))[inside], initial=0) <= 1
+        blk = inside.reshape(h // 2, 2, w // 2, 2).all((1, 3))
+        assert np.max(np.abs(ue.astype(int) - u2.astype(int))[blk], initial=0) <= 1
+        assert np.max(np.abs(ve.astype(int) - v2.astype(int))[blk], initial=0) <= 1
+
+
+def test_yuv_nearest_and_bilinear_chroma_agree_on_flat_chroma():
+    rng = np.random.default_rng(2)
+    h, w = 8, 12
+    y = rng.integers(16, 236, (h, w), dtype=np.uint8)
+    u = np.full((h // 2, w // 2), 90, np.uint8); v = np.full((h // 2, w // 2), 200, np.uint8)
+    a = O.decode_yuv420(y, u, v, w, h, 0.2126, 0.0722, False, False, 0, O.TR_BT709)
+    b = O.decode_yuv420(y, u, v, w, h, 0.2126, 0.0722, False, False, 1, O.TR_BT709)
+    assert np.array_equal(a, b)
