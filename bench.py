@@ -121,7 +121,7 @@ def make_gpu_workload(name, ctx, frames, seed):
         return wl, (lambda: ops.pixel_chain(ctx, src, dst, steps)), None
 
     if name in ("c5_yuv420_yuv420", "c5_yuv420_rgba8"):
-        W = H = 4096
+        W, H = C5_SIZE
         sd = Z.yuv420_descriptor(W, H, Color.Rgb(Z.Primaries.Bt2020, Transfer.Bt709), Z.YuvMatrix.Bt2020, False, False, 0)
         src = ctx.image(sd, frames)
         y = rng.integers(16, 236, (1, H, W), dtype=np.uint8)
@@ -142,7 +142,7 @@ def make_gpu_workload(name, ctx, frames, seed):
 
     if name.startswith("c5_"):
         fmt = name[3:]
-        W = H = 4096
+        W, H = C5_SIZE
         M = O.mul3(O.inv3(O.to_xyz("bt709", "D65")), O.to_xyz("bt2020", "D65"))
         if fmt == "rgba8":
             sd = dd = d(W, H, rgba8, Color.SRGB); bpp = 8
@@ -258,6 +258,7 @@ def cpu_baseline_child(name, budget_s=12.0):
 
 
 C3_ANGLE_DEG = 30.0
+C5_SIZE = (4096, 4096)
 
 
 # ------------------------------------------------------------------ clocks
@@ -366,6 +367,7 @@ def main():
     ap.add_argument("--frames", type=int, default=16, help="frames per step per GPU")
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--angle", type=float, default=30.0, help="rotation of the c3_affine_* workloads in degrees (BASELINE: 30)")
+    ap.add_argument("--size", default="4096x4096", help="image size WxH of the c5_* workloads (BASELINE config 5 sweeps 1-64 MP)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-baseline-child", default=None, help=argparse.SUPPRESS)
     ap.add_argument("--budget", type=float, default=12.0, help=argparse.SUPPRESS)
@@ -375,8 +377,9 @@ def main():
         return
     if args.impl == "reference":
         return run_reference(args)
-    global C3_ANGLE_DEG
+    global C3_ANGLE_DEG, C5_SIZE
     C3_ANGLE_DEG = args.angle
+    C5_SIZE = tuple(int(v) for v in args.size.lower().split("x"))
 
     import torch
     import torch.distributed as dist
