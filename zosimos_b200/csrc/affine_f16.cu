@@ -43,6 +43,7 @@ struct AffParams {
   int32_t margin;    // texels a tap may lie outside of [floor(min), floor(max)] of the mapped corners: 1 bilinear, 0 nearest
   float sfwf, sfhf;  // (float)sfw, (float)sfh
   int* fault;  // mapped host word set when an mbarrier wait runs away
+  float* counter;  // tile dispenser (zero at launch): see the producer
 };
 
 struct __align__(16) Geo {
@@ -382,21 +383,41 @@ __global__ void __launch_bounds__(THREADS_ALL, CTAS) k_affine_f16(const __grid_c
   __syncthreads();  // the barriers exist before anybody arms or polls them
   const CUtensorMap* const m0 = &M.m0;  // stays in param space (see gather.cu)
   const uint32_t warp = threadIdx.x >> 5;
-  const uint32_t my_tiles = blockIdx.x < P.total_tiles ? (P.total_tiles - 1u - blockIdx.x) / gridDim.x + 1u : 0u;
   if (warp == CONSUMER_WARPS) {
     if ((threadIdx.x & 31) != 0) return;
+    // Tiles are handed out dynamically: the producer draws tile numbers from a counter in global memory instead of
+    // walking blockIdx.x + k * gridDim.x.  Equal static shares end with the slowest SM (SMs differ by ~10 % in
+    // their distance to L2 / HBM); numbers drawn at about the same time are neighbours in the banded order, so
+    // the tiles in flight still form one compact block.  The draw for the next tile is in flight while this
+    // tile's geometry is worked out, AHEAD tiles before its load.  The counter is a FLOAT (tile numbers are below
+    // 2^24, every value exact): ptxas wraps an integer atom.add into its warp-aggregation sequence, whose shuffle
+    // waits for the atomic's round trip on the spot.
+    auto draw = [&]() { float t; asm volatile("atom.global.add.f32 %0, [%1], 0f3F800000;" : "=f"(t) : "l"(P.counter) : "memory"); return t; };
     const uint32_t rowb = (uint32_t)P.box_w * 8u;
+    // (TILES_PER_DRAW tiles per draw: one draw per tile ran into the throughput of atomics on a single address,
+    //  ~0.6 per ns were needed for 130 k tiles in 0.22 ms -- nearest fell from 0.75 to 0.65)
+    constexpr uint32_t TILES_PER_DRAW = 4;
+    uint32_t tile = (uint32_t)draw() * TILES_PER_DRAW, left = TILES_PER_DRAW;
+    float next_draw = draw();
+    bool done = false;
     uint32_t s = 0, round = 0;  // stage and use count of the stage for the tile being issued
-    for (uint32_t it = 0; it < my_tiles + AHEAD; it++) {
-      if (it < my_tiles) {  // geometry of tile `it`, AHEAD iterations ahead of its load
+    for (uint32_t it = 0;; it++) {
+      if (!done) {  // geometry of this CTA's tile number `it`, AHEAD iterations ahead of its load
         Geo& g_ = geo[it % RING];
-        tile_geometry(P, blockIdx.x + it * gridDim.x, g_);
-        g_.staged = g_.any && g_.fits;
-        g_.base = smem_u32(dyn + (size_t)(it % STAGES) * stage_bytes) - (uint32_t)(g_.by + P.soy) * rowb - (uint32_t)(g_.bx + P.sox) * 8u;
-        g_.cx0 = (float)(g_.x0 + P.dox) + 0.5f; g_.cy0 = (float)(g_.y0 + P.doy) + 0.5f;
-        g_.dst_off = (uint64_t)g_.frame * P.dst_bstride + (uint64_t)g_.y0 * P.dst_pitch + (uint64_t)g_.x0 * 8u;
-        g_.below_off = (uint64_t)g_.frame * P.below_bstride + (uint64_t)g_.y0 * P.below_pitch + (uint64_t)g_.x0 * 8u;
-        g_.nx = min(TILE, P.dw - g_.x0); g_.ny = min(TILE, P.dh - g_.y0);
+        if (tile < P.total_tiles) {
+          tile_geometry(P, tile, g_);
+          g_.staged = g_.any && g_.fits;
+          g_.base = smem_u32(dyn + (size_t)(it % STAGES) * stage_bytes) - (uint32_t)(g_.by + P.soy) * rowb - (uint32_t)(g_.bx + P.sox) * 8u;
+          g_.cx0 = (float)(g_.x0 + P.dox) + 0.5f; g_.cy0 = (float)(g_.y0 + P.doy) + 0.5f;
+          g_.dst_off = (uint64_t)g_.frame * P.dst_bstride + (uint64_t)g_.y0 * P.dst_pitch + (uint64_t)g_.x0 * 8u;
+          g_.below_off = (uint64_t)g_.frame * P.below_bstride + (uint64_t)g_.y0 * P.below_pitch + (uint64_t)g_.x0 * 8u;
+          g_.nx = min(TILE, P.dw - g_.x0); g_.ny = min(TILE, P.dh - g_.y0);
+          tile++;
+          if (--left == 0) { tile = (uint32_t)next_draw * TILES_PER_DRAW; left = TILES_PER_DRAW; next_draw = draw(); }
+        } else {
+          g_.staged = -1;  // no tile left: the compute warps stop at this entry
+          done = true;
+        }
       }
       if (it < AHEAD) continue;
       const Geo& g = geo[(it - AHEAD) % RING];
@@ -406,12 +427,13 @@ __global__ void __launch_bounds__(THREADS_ALL, CTAS) k_affine_f16(const __grid_c
           if (++spins > (1u << 20)) { if (P.fault) *reinterpret_cast<volatile int*>(P.fault) = 1; break; }
         }
       }
-      if (g.staged) {
+      if (g.staged > 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(&full[s], box_bytes);
         tma_load_3d(dyn + (size_t)s * stage_bytes, m0, g.bx * 2, g.by, g.frame, &full[s]);
       } else {
         mbar_arrive(&full[s]);  // nothing to load: the geometry alone is the payload (release: the ring entry is visible)
+        if (g.staged < 0) break;
       }
       if (++s == STAGES) { s = 0; round++; }
     }
@@ -423,13 +445,15 @@ __global__ void __launch_bounds__(THREADS_ALL, CTAS) k_affine_f16(const __grid_c
   L.dst_thr = (uint64_t)L.ly * P.dst_pitch + (uint64_t)L.lx * 8u;
   L.below_thr = (uint64_t)L.ly * P.below_pitch + (uint64_t)L.lx * 8u;
   uint32_t s = 0, parity = 0, r = 0;
-  for (uint32_t it = 0; it < my_tiles; it++) {
+  for (;;) {
     uint32_t spins = 0;
+    bool lost = false;
     while (!mbar_try_wait_sleep(&full[s], parity, 20000u)) {
-      if (++spins > (1u << 20)) { if (P.fault) *reinterpret_cast<volatile int*>(P.fault) = 1; break; }
+      if (++spins > (1u << 20)) { if (P.fault) *reinterpret_cast<volatile int*>(P.fault) = 1; lost = true; break; }
     }
     const Geo& g = geo[r];
-    if (g.staged) compute_tile_smem<BILINEAR, GROUP>(P, g, L);
+    if (g.staged < 0 || lost) break;  // the producer has no tile left (or a barrier ran away: reported through zos_sync)
+    if (g.staged > 0) compute_tile_smem<BILINEAR, GROUP>(P, g, L);
     else if (!g.any) copy_tile(P, g, L);            // no covered pixel
     else compute_tile_global<BILINEAR>(P, g);       // a footprint larger than the box: taps straight from global memory
     __syncwarp();
@@ -472,7 +496,7 @@ zos_status launch_affine_f16(zos_ctx* ctx, const DevImage* below, const DevImage
   P.sfwf = (float)P.sfw; P.sfhf = (float)P.sfh;
   P.tiles_x = (dst.w + TILE - 1) / TILE; P.tiles_y = (dst.h + TILE - 1) / TILE;
   const uint64_t total = (uint64_t)P.tiles_x * P.tiles_y * batch;
-  if (total == 0 || total >= (1ull << 31)) return ZOS_OK;
+  if (total == 0 || total >= (1ull << 24)) return ZOS_OK;  // (tile numbers are drawn from a float counter)
   P.total_tiles = (uint32_t)total;
   P.div_frame = make_fastdiv(P.tiles_x * P.tiles_y); P.div_band = make_fastdiv(8u * P.tiles_x);
   const float ex = (TILE - 1) * (fabsf(P.inv[0]) + fabsf(P.inv[1])), ey = (TILE - 1) * (fabsf(P.inv[3]) + fabsf(P.inv[4]));
@@ -496,6 +520,8 @@ zos_status launch_affine_f16(zos_ctx* ctx, const DevImage* below, const DevImage
   per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
   const uint64_t cap = (uint64_t)ctx->sm_count * per_sm;
   const int grid = (int)(total < cap ? total : cap);
+  P.counter = ctx->work_counter;
+  if (cudaMemsetAsync(ctx->work_counter, 0, sizeof(float), ctx->stream) != cudaSuccess) return check_cuda(ctx, cudaGetLastError(), "affine_f16 counter reset");
 #define ZOS_AFF_LAUNCH(B, G, C)                                                                          \
   do {                                                                                                    \
     ensure_dyn_smem(ctx, k_affine_f16<B, G, C>, 144 * 1024);                                                \

@@ -285,6 +285,12 @@ zos_status zos_ctx_create(int32_t device, zos_ctx** out) {
     if (cudaHostGetDevicePointer((void**)&ctx->fault_dev, ctx->fault_host, 0) != cudaSuccess) ctx->fault_dev = nullptr;
   }
   {
+    void* wc = nullptr;
+    if ((st = check_cuda(ctx, cudaMalloc(&wc, 256), "cudaMalloc(work counter)")) != ZOS_OK) goto bad;
+    ctx->scratch.push_back(wc);
+    ctx->work_counter = reinterpret_cast<float*>(wc);
+  }
+  {
     TablesGlobal* t = new TablesGlobal();
     ColorConstants* c = new ColorConstants();
     if (!build_constants(t, c)) { delete t; delete c; st = fail(ctx, ZOS_ERR_INVALID, "internal: sRGB bucket table has two thresholds in one bucket"); goto bad; }

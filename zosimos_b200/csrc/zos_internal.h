@@ -26,6 +26,7 @@ struct zos_ctx {
   std::vector<void*> scratch;    // device scratch owned by the ctx (tensor maps etc.)
   int* fault_host = nullptr;     // mapped pinned word: kernels set it when an mbarrier wait ran away; zos_sync reports it
   int* fault_dev = nullptr;      // device view of fault_host
+  float* work_counter = nullptr; // device word: tile dispenser of dynamically scheduled kernels (zeroed before each launch)
   std::set<const void*> smem_configured;  // kernels whose dynamic shared memory limit was raised ON THIS CONTEXT'S DEVICE
   std::map<std::string, struct zos_dynamic*> dynamic_cache;  // NVRTC-compiled plugins by source text (dynamic.cu)
 };
