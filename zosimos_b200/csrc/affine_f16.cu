@@ -57,7 +57,7 @@ struct __align__(16) Geo {
   int32_t frame, x0, y0;  // destination tile
   int32_t bx, by;         // box origin in the window `above` holds
   int32_t fits, any;
-  int32_t pad_;
+  int32_t last;  // this is the CTA's final tile (set by the producer one iteration later, before the entry is published)
 };
 
 __device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv& f) {
@@ -412,10 +412,13 @@ __global__ void __launch_bounds__(THREADS_ALL, CTAS) k_affine_f16(const __grid_c
           g_.dst_off = (uint64_t)g_.frame * P.dst_bstride + (uint64_t)g_.y0 * P.dst_pitch + (uint64_t)g_.x0 * 8u;
           g_.below_off = (uint64_t)g_.frame * P.below_bstride + (uint64_t)g_.y0 * P.below_pitch + (uint64_t)g_.x0 * 8u;
           g_.nx = min(TILE, P.dw - g_.x0); g_.ny = min(TILE, P.dh - g_.y0);
+          g_.last = 0;
           tile++;
           if (--left == 0) { tile = (uint32_t)next_draw * TILES_PER_DRAW; left = TILES_PER_DRAW; next_draw = draw(); }
         } else {
-          g_.staged = -1;  // no tile left: the compute warps stop at this entry
+          // no tile left.  The previous entry (not yet published: entries go out AHEAD iterations after their geometry)
+          // becomes the CTA's last one; a CTA that drew nothing publishes one empty entry.
+          if (it == 0) g_.staged = -1; else geo[(it - 1) % RING].last = 1;
           done = true;
         }
       }
@@ -433,8 +436,8 @@ __global__ void __launch_bounds__(THREADS_ALL, CTAS) k_affine_f16(const __grid_c
         tma_load_3d(dyn + (size_t)s * stage_bytes, m0, g.bx * 2, g.by, g.frame, &full[s]);
       } else {
         mbar_arrive(&full[s]);  // nothing to load: the geometry alone is the payload (release: the ring entry is visible)
-        if (g.staged < 0) break;
       }
+      if (g.staged < 0 || g.last) break;
       if (++s == STAGES) { s = 0; round++; }
     }
     return;
@@ -452,10 +455,12 @@ __global__ void __launch_bounds__(THREADS_ALL, CTAS) k_affine_f16(const __grid_c
       if (++spins > (1u << 20)) { if (P.fault) *reinterpret_cast<volatile int*>(P.fault) = 1; lost = true; break; }
     }
     const Geo& g = geo[r];
-    if (g.staged < 0 || lost) break;  // the producer has no tile left (or a barrier ran away: reported through zos_sync)
+    if (g.staged < 0 || lost) break;  // this CTA drew no tile at all (or a barrier ran away: reported through zos_sync)
+    const bool last = g.last != 0;
     if (g.staged > 0) compute_tile_smem<BILINEAR, GROUP>(P, g, L);
     else if (!g.any) copy_tile(P, g, L);            // no covered pixel
     else compute_tile_global<BILINEAR>(P, g);       // a footprint larger than the box: taps straight from global memory
+    if (last) break;                                // the producer has left: nobody waits for this stage any more
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);  // this warp is done with stage s (its shared-memory reads have completed)
     if (++s == STAGES) { s = 0; parity ^= 1u; }
