@@ -214,7 +214,7 @@ zos_status zos_dynamic_launch(zos_ctx* ctx, zos_dynamic* dyn, const zos_image* d
   const unsigned char* pp = (const unsigned char*)dparams;
   void* args[] = {&outp, &w, &h, &pitch, &tex[0], &tex[1], &pp};
   const uint64_t total = (uint64_t)w * h;
-  const unsigned grid = (unsigned)grid_for(ctx, total, 256, 8);
+  const unsigned grid = (unsigned)grid_for(ctx, total, 256, 32);
   if (d.launch(dyn->fn, grid, 1, 1, 256, 1, 1, 0, (CUstream)s, args, nullptr) != CUDA_SUCCESS) { cleanup(); return fail(ctx, ZOS_ERR_CUDA, "cuLaunchKernel failed for the dynamic operator"); }
   ctx->launches++;
   st = launch_rowwise(ctx, &out32, nullptr, D, nullptr, nullptr, 0, 1);

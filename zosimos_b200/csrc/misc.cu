@@ -149,7 +149,7 @@ zos_status launch_generate(zos_ctx* ctx, const DevImage& dst, const float* p, ui
   if (p) memcpy(P.p, p, sizeof P.p); else memset(P.p, 0, sizeof P.p);
   zos_status st = total_px(ctx, dst, batch, &P.total);
   if (st != ZOS_OK) return st;
-  k_generate<<<grid_for(ctx, P.total, 256, 8), 256, 0, ctx->stream>>>(P);
+  k_generate<<<grid_for(ctx, P.total, 256, 32), 256, 0, ctx->stream>>>(P);
   ctx->launches++;
   return check_cuda(ctx, cudaGetLastError(), "k_generate launch");
 }
@@ -159,7 +159,7 @@ zos_status launch_box3(zos_ctx* ctx, const DevImage& src, const DevImage& dst, c
   memcpy(P.m, m, sizeof P.m);
   zos_status st = total_px(ctx, dst, batch, &P.total);
   if (st != ZOS_OK) return st;
-  k_box3<<<grid_for(ctx, P.total, 256, 8), 256, 0, ctx->stream>>>(P);
+  k_box3<<<grid_for(ctx, P.total, 256, 32), 256, 0, ctx->stream>>>(P);
   ctx->launches++;
   return check_cuda(ctx, cudaGetLastError(), "k_box3 launch");
 }
@@ -171,7 +171,7 @@ zos_status launch_palette(zos_ctx* ctx, const DevImage& pal, const DevImage& idx
   zos_status st = total_px(ctx, dst, batch, &P.total);
   if (st != ZOS_OK) return st;
   if (batch > 1 && pal.bstride == 0) { /* one palette shared by all frames: fine */ }
-  k_palette<<<grid_for(ctx, P.total, 256, 8), 256, 0, ctx->stream>>>(P);
+  k_palette<<<grid_for(ctx, P.total, 256, 32), 256, 0, ctx->stream>>>(P);
   ctx->launches++;
   return check_cuda(ctx, cudaGetLastError(), "k_palette launch");
 }

@@ -280,7 +280,7 @@ zos_status launch_yuv_chain(zos_ctx* ctx, const DevImage& src, const DevImage& d
   if (total >= (1ull << 32)) return fail(ctx, ZOS_ERR_UNSUPPORTED, "yuv_chain: more than 2^32 blocks in one launch");
   P.total = (uint32_t)total;
   P.div_bw = make_fastdiv(P.bw); P.div_bh = make_fastdiv(P.bh);
-  const int grid = grid_for(ctx, total, 256, 8);
+  const int grid = grid_for(ctx, total, 256, 32);
   k_yuv_chain<<<grid, 256, 0, ctx->stream>>>(P);
   ctx->launches++;
   return check_cuda(ctx, cudaGetLastError(), "k_yuv_chain launch");
