@@ -386,9 +386,9 @@ __global__ void __launch_bounds__(THREADS_ALL, CTAS) k_affine_f16(const __grid_c
   if (warp == CONSUMER_WARPS) {
     if ((threadIdx.x & 31) != 0) return;
     // Tiles are handed out dynamically: the producer draws tile numbers from a counter in global memory instead of
-    // walking blockIdx.x + k * gridDim.x.  Equal static shares end with the slowest SM (SMs differ by ~10 % in
-    // their distance to L2 / HBM); numbers drawn at about the same time are neighbours in the banded order, so
-    // the tiles in flight still form one compact block.  The draw for the next tile is in flight while this
+    // walking blockIdx.x + k * gridDim.x.  Tiles do not cost the same (one without covered pixels is a copy), so
+    // equal static shares are unequal work; numbers drawn at about the same time are neighbours in the banded
+    // order, so the tiles in flight still form one compact block.  The draw for the next tile is in flight while this
     // tile's geometry is worked out, AHEAD tiles before its load.  The counter is a FLOAT (tile numbers are below
     // 2^24, every value exact): ptxas wraps an integer atom.add into its warp-aggregation sequence, whose shuffle
     // waits for the atomic's round trip on the spot.

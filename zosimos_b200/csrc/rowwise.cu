@@ -138,7 +138,7 @@ zos_status launch_rowwise(zos_ctx* ctx, const DevImage* below, const DevImage* a
   P.total_groups = (uint32_t)total;
   P.div_gpr = make_fastdiv((uint32_t)gpr);
   P.div_h = make_fastdiv((uint32_t)dst.h);
-  int grid = grid_for(ctx, total, 256, 32);  // more CTAs than resident: the hardware's hand-out balances the SMs (grid-size note)
+  int grid = grid_for(ctx, total, 256, 32);  // more CTAs than resident (grid-size note)
   k_rowwise<<<grid, 256, 0, ctx->stream>>>(P);
   cudaError_t e = cudaGetLastError();
   ctx->launches++;

@@ -250,7 +250,7 @@ zos_status launch_yuv_fast(zos_ctx* ctx, const DevImage& src, const DevImage& ds
   if (total == 0 || total >= (1ull << 32)) return ZOS_OK;
   P.total = (uint32_t)total;
   P.div_bw = make_fastdiv(P.bw); P.div_bh = make_fastdiv(P.bh);
-  const int grid = grid_for(ctx, total, 256, 32);  // (more CTAs than resident: dynamic balance across SMs, +10 %; each CTA fills a 5-20 KB table)
+  const int grid = grid_for(ctx, total, 256, 32);  // (more CTAs than resident, +10 %: DESIGN.md "grid size of the streaming kernels"; each CTA fills a 5-20 KB table)
   if (kind == D_YUV709) k_yuv_fast<D_YUV709><<<grid, 256, 0, ctx->stream>>>(P);
   else if (kind == D_SRGB8) k_yuv_fast<D_SRGB8><<<grid, 256, 0, ctx->stream>>>(P);
   else k_yuv_fast<D_UNORM8><<<grid, 256, 0, ctx->stream>>>(P);
