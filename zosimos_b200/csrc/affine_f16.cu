@@ -44,6 +44,7 @@ struct AffParams {
   float sfwf, sfhf;  // (float)sfw, (float)sfh
   int* fault;  // mapped host word set when an mbarrier wait runs away
   float* counter;  // tile dispenser (zero at launch): see the producer
+  int32_t below_map;  // TensorMaps::m1 describes `below`: tiles without covered pixels are staged through it too
 };
 
 struct __align__(16) Geo {
@@ -349,6 +350,21 @@ __device__ __forceinline__ void copy_tile(const AffParams& P, const Geo& g, cons
     if (live[k]) __stcs(reinterpret_cast<uint2*>(dp + (uint64_t)k * dstep), w[k]);
 }
 
+// The same tile when the producer has staged `below`'s 32 x 32 texels in the stage buffer (one TMA box, like a source
+// box): the round trip to DRAM is hidden by the pipeline instead of being paid by all eight warps at once.
+__device__ __forceinline__ void copy_tile_staged(const AffParams& P, const Geo& g, const Lane& L) {
+  const bool col_live = (int)L.lx < g.nx;
+  const int rows_left = g.ny - (int)L.ly;
+  uint8_t* dp = P.dst + (g.dst_off + L.dst_thr);
+  const uint64_t dstep = (uint64_t)(THREADS / 32) * P.dst_pitch;
+  const uint32_t a = g.base + L.ly * (TILE * 8u) + L.lx * 8u;
+#pragma unroll
+  for (int k = 0; k < ROWS; k++) {
+    const uint2 w = lds64(a + (uint32_t)k * ((THREADS / 32) * TILE * 8u));
+    if (col_live && (THREADS / 32) * k < rows_left) __stcs(reinterpret_cast<uint2*>(dp + (uint64_t)k * dstep), w);
+  }
+}
+
 // Warp-specialised pipeline: warps 0..7 compute tiles, warp 8 (one lane) is the producer.  The producer works out
 // the geometry of a tile AHEAD iterations before the tile's turn and stores it in a ring in shared memory, so that
 // the moment the tile's stage is free the TMA load goes out (the ~250 serial instructions of the geometry are
@@ -382,6 +398,7 @@ __global__ void __launch_bounds__(THREADS_ALL, CTAS) k_affine_f16(const __grid_c
   }
   __syncthreads();  // the barriers exist before anybody arms or polls them
   const CUtensorMap* const m0 = &M.m0;  // stays in param space (see gather.cu)
+  const CUtensorMap* const m1 = &M.m1;
   const uint32_t warp = threadIdx.x >> 5;
   if (warp == CONSUMER_WARPS) {
     if ((threadIdx.x & 31) != 0) return;
@@ -406,8 +423,9 @@ __global__ void __launch_bounds__(THREADS_ALL, CTAS) k_affine_f16(const __grid_c
         Geo& g_ = geo[it % RING];
         if (tile < P.total_tiles) {
           tile_geometry(P, tile, g_);
-          g_.staged = g_.any && g_.fits;
-          g_.base = smem_u32(dyn + (size_t)(it % STAGES) * stage_bytes) - (uint32_t)(g_.by + P.soy) * rowb - (uint32_t)(g_.bx + P.sox) * 8u;
+          g_.staged = (g_.any && g_.fits) ? 1 : (!g_.any && P.below_map) ? 2 : 0;  // 1: source box staged, 2: `below` tile staged
+          g_.base = smem_u32(dyn + (size_t)(it % STAGES) * stage_bytes);
+          if (g_.staged == 1) g_.base -= (uint32_t)(g_.by + P.soy) * rowb + (uint32_t)(g_.bx + P.sox) * 8u;
           g_.cx0 = (float)(g_.x0 + P.dox) + 0.5f; g_.cy0 = (float)(g_.y0 + P.doy) + 0.5f;
           g_.dst_off = (uint64_t)g_.frame * P.dst_bstride + (uint64_t)g_.y0 * P.dst_pitch + (uint64_t)g_.x0 * 8u;
           g_.below_off = (uint64_t)g_.frame * P.below_bstride + (uint64_t)g_.y0 * P.below_pitch + (uint64_t)g_.x0 * 8u;
@@ -430,10 +448,14 @@ __global__ void __launch_bounds__(THREADS_ALL, CTAS) k_affine_f16(const __grid_c
           if (++spins > (1u << 20)) { if (P.fault) *reinterpret_cast<volatile int*>(P.fault) = 1; break; }
         }
       }
-      if (g.staged > 0) {
+      if (g.staged == 1) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(&full[s], box_bytes);
         tma_load_3d(dyn + (size_t)s * stage_bytes, m0, g.bx * 2, g.by, g.frame, &full[s]);
+      } else if (g.staged == 2) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&full[s], TILE * TILE * 8u);
+        tma_load_3d(dyn + (size_t)s * stage_bytes, m1, g.x0 * 2, g.y0, g.frame, &full[s]);
       } else {
         mbar_arrive(&full[s]);  // nothing to load: the geometry alone is the payload (release: the ring entry is visible)
       }
@@ -457,8 +479,9 @@ __global__ void __launch_bounds__(THREADS_ALL, CTAS) k_affine_f16(const __grid_c
     const Geo& g = geo[r];
     if (g.staged < 0 || lost) break;  // this CTA drew no tile at all (or a barrier ran away: reported through zos_sync)
     const bool last = g.last != 0;
-    if (g.staged > 0) compute_tile_smem<BILINEAR, GROUP>(P, g, L);
-    else if (!g.any) copy_tile(P, g, L);            // no covered pixel
+    if (g.staged == 1) compute_tile_smem<BILINEAR, GROUP>(P, g, L);
+    else if (g.staged == 2) copy_tile_staged(P, g, L);  // no covered pixel, `below` staged
+    else if (!g.any) copy_tile(P, g, L);                // no covered pixel
     else compute_tile_global<BILINEAR>(P, g);       // a footprint larger than the box: taps straight from global memory
     if (last) break;                                // the producer has left: nobody waits for this stage any more
     __syncwarp();
@@ -520,6 +543,10 @@ zos_status launch_affine_f16(zos_ctx* ctx, const DevImage* below, const DevImage
   if (!make_map(ctx, &M.m0, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, above.p0, (uint64_t)above.w * 2, above.h, above.pitch, batch, above.bstride,
                 (uint32_t)P.box_w * 2, (uint32_t)P.box_h))
     return ZOS_OK;
+  // `below` tiles (32 x 32 texels) go through the same stages; without the map they are read directly
+  P.below_map = below && stage >= (size_t)TILE * TILE * 8 && (P.dox | P.doy) == 0 &&
+                make_map(ctx, &M.m1, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, below->p0, (uint64_t)below->w * 2, below->h, below->pitch, batch, below->bstride,
+                         TILE * 2, TILE);
   // 3 stages of ~19 KB (30 degree rotation): 4 CTAs of 9 warps per SM, 56 registers per thread
   int per_sm = (int)((228 * 1024) / (smem + 1024 + 256));
   per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
