@@ -59,6 +59,8 @@ struct __align__(16) Geo {
   int32_t bx, by;         // box origin in the window `above` holds
   int32_t fits, any;
   int32_t last;  // this is the CTA's final tile (set by the producer one iteration later, before the entry is published)
+  int32_t interior;  // a full 32 x 32 tile whose every bilinear tap lies inside the source without clamping (so every pixel is covered)
+  int32_t pad_[3];
 };
 
 __device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv& f) {
@@ -81,7 +83,7 @@ __device__ void tile_geometry(const AffParams& P, uint32_t t, Geo& g) {
   const uint32_t rows = min(8u, P.tiles_y - band * 8u);
   const uint32_t txi = rows == 8u ? in_band >> 3 : in_band / rows, tyi = band * 8u + (in_band - txi * rows);
   g.frame = (int)fr; g.x0 = (int)txi * TILE; g.y0 = (int)tyi * TILE;
-  g.bx = g.by = 0; g.fits = 0; g.any = 0;
+  g.bx = g.by = 0; g.fits = 0; g.any = 0; g.interior = 0;
   const int x1 = min(g.x0 + TILE, P.dw) - 1, y1 = min(g.y0 + TILE, P.dh) - 1;
   float px[4], py[4];
   const float gx0 = (float)(g.x0 + P.dox) + 0.5f, gx1 = (float)(x1 + P.dox) + 0.5f;
@@ -92,6 +94,8 @@ __device__ void tile_geometry(const AffParams& P, uint32_t t, Geo& g) {
   map_point(P, gx1, gy1, px[3], py[3]);
   float minx = fminf(fminf(px[0], px[1]), fminf(px[2], px[3])), maxx = fmaxf(fmaxf(px[0], px[1]), fmaxf(px[2], px[3]));
   float miny = fminf(fminf(py[0], py[1]), fminf(py[2], py[3])), maxy = fmaxf(fmaxf(py[0], py[1]), fmaxf(py[2], py[3]));
+  // taps floor(p - 0.5), + 1 need no clamp when 0.5 <= p < size - 0.5 for every pixel; the corner values bound all of them
+  g.interior = x1 - g.x0 == TILE - 1 && y1 - g.y0 == TILE - 1 && minx >= 0.5f && miny >= 0.5f && maxx < (float)P.sfw - 0.5f && maxy < (float)P.sfh - 0.5f;
   minx = fmaxf(minx, 0.0f); miny = fmaxf(miny, 0.0f);
   maxx = fminf(maxx, (float)P.sfw); maxy = fminf(maxy, (float)P.sfh);
   if (minx > maxx || miny > maxy) return;
@@ -201,7 +205,7 @@ struct Lane {  // per-thread constants of a compute thread
 // ALLCOV: every pixel of the warp's rows is live and covered (the common case: interior tiles) -- plain loads,
 // no `below`, no select.  Otherwise loads are predicated and uncovered pixels take `below` (or the clear colour)
 // through a select.
-template <bool BILINEAR, bool ALLCOV, int GROUP>
+template <bool BILINEAR, bool ALLCOV, int GROUP, bool NOCLAMP = false>
 __device__ __forceinline__ void compute_rows(const AffParams& P, const Geo& g, const Lane& L, const float (&px)[ROWS], const float (&py)[ROWS],
                                              const bool (&live)[ROWS], const bool (&cov)[ROWS]) {
   const uint32_t rowb = (uint32_t)P.box_w * 8u;
@@ -226,6 +230,13 @@ __device__ __forceinline__ void compute_rows(const AffParams& P, const Geo& g, c
         const float x0f = (float)x0, y0f = (float)y0;
         ax[q] = fx - x0f; ay[q] = fy - y0f;
         // covered: px in [0, sfw) so x0 in [-1, sfw-1]: clamp(x0) = max(x0, 0), clamp(x0 + 1) = min(x0 + 1, sfw - 1)
+        if (NOCLAMP) {
+          // interior tile: the four taps are x0, x0 + 1 on rows y0, y0 + 1 -- one address, constant offsets
+          const uint32_t a00 = base + (uint32_t)y0 * rowb + (uint32_t)x0 * 8u, a01 = a00 + rowb;
+          w00[q] = lds64(a00); w10[q] = lds64(a00 + 8u);
+          w01[q] = lds64(a01); w11[q] = lds64(a01 + 8u);
+          continue;
+        }
         const int xa = max(x0, 0), xb = min(x0 + 1, xmax), ya = max(y0, 0), yb = min(y0 + 1, ymax);
         const uint32_t ra = base + (uint32_t)ya * rowb, rb = base + (uint32_t)yb * rowb;
         if (ALLCOV) {
@@ -274,6 +285,20 @@ __device__ __forceinline__ void compute_tile_smem(const AffParams& P, const Geo&
   // == (float)(i + dox) + 0.5f: every term is an exact float below 2^22 (checked by the launcher)
   const float cx = g.cx0 + L.lxf;
   const float tx = fmaf(P.inv[0], cx, P.inv[2]), ty = fmaf(P.inv[3], cx, P.inv[5]);
+  if (g.interior) {
+    // most tiles: full, every pixel covered, no tap needs a clamp -- no coverage tests, no vote
+    const float cyb = g.cy0 + L.lyf;
+    float px[ROWS], py[ROWS];
+    bool live[ROWS], cov[ROWS];
+#pragma unroll
+    for (int k = 0; k < ROWS; k++) {
+      const float cy = cyb + (float)((THREADS / 32) * k);
+      px[k] = fmaf(P.inv[1], cy, tx); py[k] = fmaf(P.inv[4], cy, ty);
+      live[k] = cov[k] = true;
+    }
+    compute_rows<BILINEAR, true, GROUP, true>(P, g, L, px, py, live, cov);
+    return;
+  }
   // covered <=> 0 <= p < size.  No coordinate is -0 (the launcher turns -0 coefficients into +0, sums that
   // cancel give +0), so the bit patterns of non-negative floats order like unsigned integers and every negative
   // or NaN pattern is above bits(size): one unsigned compare per axis.
