@@ -270,6 +270,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz, self.how = index, [], set(), False, None, None
+        self.ready = threading.Event()  # set once the first poll is about to happen (NVML initialised), so that short regions get samples
 
     def _nvml_handle(self):
         import pynvml
@@ -285,6 +286,7 @@ class ClockSampler(threading.Thread):
         bits = [nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown,
                 nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap]
         self.how = "nvml"
+        self.ready.set()
         while not self.stop_flag:
             self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
             r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
@@ -296,6 +298,7 @@ class ClockSampler(threading.Thread):
     def _run_smi(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         self.how = "nvidia-smi"
+        self.ready.set()
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
@@ -413,6 +416,7 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+        sampler.ready.wait(timeout=5)
     l0 = ctx.launch_count
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     ev[0].record(stream)
