@@ -31,6 +31,7 @@ enum { ZOSH_DERIV_PREWITT = 0, ZOSH_DERIV_SOBEL = 1, ZOSH_DERIV_SCHARR3 = 2, ZOS
 
 typedef struct zosh_cb zosh_cb;           /* command::CommandBuffer */
 typedef struct zosh_program zosh_program; /* program::Program (the linked High stream) */
+typedef struct zosh_signature zosh_signature; /* command::CommandSignature (the callee travels inside it) */
 typedef struct zosh_rect { uint32_t x, y, max_x, max_y; } zosh_rect; /* command::Rectangle, command.rs:311-317 */
 
 const char* zosh_last_error(void); /* message of the last failure on this thread */
@@ -89,6 +90,30 @@ int32_t zosh_cb_with_buffer_bilinear(zosh_cb* cb, int32_t buffer, const zos_desc
 int32_t zosh_cb_dynamic(zosh_cb* cb, int32_t src0, int32_t src1, const char* cuda_source, const zos_desc* desc, const void* params,
                         uint64_t params_len, int32_t* reg);
 int32_t zosh_cb_with_knob(zosh_cb* cb);  /* the NEXT operation gets a knob; returns its 1-based id (command.rs:1865-1874) */
+
+/* Functions and generics (command.rs:856-922, 2821-2869; tests/generic.rs).  A command buffer that declares a generic is a
+ * TEMPLATE: its builders record their calls (registers = positions in the record; zosh_cb_describe has nothing to answer
+ * until types are bound) and zosh_cb_invoke replays the record into the caller with the generic inputs replaced by the
+ * argument registers -- monomorphisation by inlining, which the reference does at link time (command.rs:2083-2185).
+ * Type errors of the callee under the bound types therefore surface at invoke, and leave the caller unchanged. */
+int32_t zosh_cb_generic(zosh_cb* cb, int32_t* var);                                                      /* command.rs:856-870 */
+int32_t zosh_cb_input_generic(zosh_cb* cb, int32_t var, int32_t* reg);                                   /* command.rs:872-884 */
+int32_t zosh_cb_computed_signature(const zosh_cb* cb, zosh_signature** out);                             /* command.rs:886-905 */
+void zosh_signature_free(zosh_signature* sig);
+uint32_t zosh_signature_num_generics(const zosh_signature* sig);
+uint32_t zosh_signature_num_inputs(const zosh_signature* sig);
+uint32_t zosh_signature_num_outputs(const zosh_signature* sig);
+int32_t zosh_cb_function(zosh_cb* cb, const zosh_signature* sig, int32_t* function);                     /* command.rs:907-922 */
+uint32_t zosh_cb_num_functions(const zosh_cb* cb);
+/* InvocationArguments{generics, arguments}; results[] receives the registers of the callee's outputs, in order.
+ * ZOSH_ERR_TYPE = CommandError::INVALID_CALL (count or type mismatch), ZOSH_ERR_OTHER = BAD_REGISTER. */
+int32_t zosh_cb_invoke(zosh_cb* cb, int32_t function, const zos_desc* generics, uint32_t num_generics, const int32_t* arguments,
+                       uint32_t num_arguments, int32_t* results, uint32_t results_cap, uint32_t* num_results); /* command.rs:2821-2869 */
+/* Linker::link (command.rs:2083-2185): program 0 is `main`, program k >= 1 is functions[k - 1]; the link tables of all programs
+ * are concatenated in `links` (links_per_program[p] entries for program p), entry f of a table names the program that function
+ * variable f calls.  Calls were inlined by zosh_cb_invoke, so linking verifies the wiring and compiles `main`. */
+int32_t zosh_link(const zosh_cb* main_cb, const zosh_cb* const* functions, uint32_t num_functions, const uint32_t* links,
+                  const uint32_t* links_per_program, zosh_program** out);
 
 /* Linker::compile (command.rs:2069): liveness + emission of the High-like op list */
 int32_t zosh_compile(const zosh_cb* cb, zosh_program** out);

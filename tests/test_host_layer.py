@@ -228,3 +228,140 @@ def test_buffer_builder_errors():
         c.with_buffer(img)
     with pytest.raises(CommandError):   # the bilinear block needs 96 bytes
         c.with_buffer(c.buffer_zero(32)).bilinear(Descriptor.with_srgb_image("rgba8", 4, 4))
+
+
+# ---------------------------------------------------------------- functions and generics (tests/generic.rs; host.cpp)
+def _op_bytes(op):
+    return bytes(op)[:_ffi.ZosOp.data.offset]  # everything but the pointers to blobs / source text
+
+
+def _same_ops(a, b):
+    return len(a) == len(b) and all(_op_bytes(x) == _op_bytes(y) for x, y in zip(a, b))
+
+
+def _palette_template(idx_desc, ramp):
+    from zosimos_b200.command import GenericDeclaration, Palette
+    t = CommandBuffer()
+    var = t.generic(GenericDeclaration(bounds=()))
+    img = t.input_generic(var)
+    idx = t.bilinear(idx_desc, ramp)
+    out, desc = t.output(t.palette(img, Palette(height=Z.ColorChannel.R, width=Z.ColorChannel.G), idx))
+    assert desc is None  # the types of a template are bound by its caller
+    return t
+
+
+def test_generic_function_is_inlined_into_the_caller():  # tests/generic.rs
+    from zosimos_b200.command import InvocationArguments, Palette
+    ramp = Bilinear([0] * 4, [0] * 4, [0] * 4, [0] * 4, [0] * 4, [1, 1, 0, 0])
+    idx_desc = Descriptor.with_texel(Texel.new_u8(SampleParts.RgbA), 64, 48)
+    template = _palette_template(idx_desc, ramp)
+    sig = template.computed_signature()
+    assert (sig.num_generics, sig.num_inputs, sig.num_outputs) == (1, 1, 1)
+
+    main = CommandBuffer()
+    f = main.function(sig)
+    inp = main.input(srgb(32, 32))
+    ty = main.register_descriptor(inp)
+    n0 = command.host_lib().zosh_cb_num_ops(main._h)
+    with pytest.raises(CommandError) as e:  # wrong number of generics: INVALID_CALL
+        main.invoke(f, InvocationArguments(generics=[], arguments=[inp]))
+    assert e.value.is_type_err()
+    with pytest.raises(CommandError) as e:  # the argument does not have the bound type
+        main.invoke(f, InvocationArguments(generics=[idx_desc], arguments=[inp]))
+    assert e.value.is_type_err()
+    with pytest.raises(CommandError):       # unknown function variable: BAD_REGISTER
+        main.invoke(command.FunctionVar(3), InvocationArguments(generics=[ty], arguments=[inp]))
+    assert command.host_lib().zosh_cb_num_ops(main._h) == n0  # failed calls leave the caller untouched
+    (res,) = main.invoke(f, InvocationArguments(generics=[ty], arguments=[inp]))
+    _, out_desc = main.output(res)
+    assert out_desc.size() == (64, 48) and out_desc.color == ty.color  # layout of the indices, chroma of the palette
+
+    linker = Linker.from_included()
+    with pytest.raises(CommandError):  # link tables must name the invoked function
+        linker.link(main, [], [template], [[2], []])
+    with pytest.raises(CommandError):  # one table per program
+        linker.link(main, [], [template], [[1]])
+    with pytest.raises(CommandError) as e:  # another template with the same shape is still another function
+        linker.link(main, [], [_palette_template(idx_desc, ramp)], [[1], []])
+    assert e.value.is_type_err()
+    linked = linker.link(main, [], [template], [[1], []]).ops()
+
+    direct = CommandBuffer()
+    i2 = direct.input(srgb(32, 32))
+    direct.output(direct.palette(i2, Palette(height=Z.ColorChannel.R, width=Z.ColorChannel.G), direct.bilinear(idx_desc, ramp)))
+    assert _same_ops(linked, linker.compile(direct).ops())  # same stream as the pipeline written without the function
+
+
+def test_function_with_two_results_called_twice():
+    from zosimos_b200.command import GenericDeclaration, InvocationArguments
+    t = CommandBuffer()
+    var = t.generic(GenericDeclaration())
+    fixed = t.input(srgb(16, 16))        # a concrete parameter next to the generic one
+    img = t.input_generic(var)
+    placed = t.inscribe(img, Rectangle(0, 0, 16, 16), fixed)
+    t.output(placed)
+    t.output(t.resize(placed, (8, 8), ResizeMode.Nearest))
+    sig = t.computed_signature()
+    assert (sig.num_generics, sig.num_inputs, sig.num_outputs) == (1, 2, 2)
+
+    def build(with_function):
+        c = CommandBuffer()
+        small, a, b = c.input(srgb(16, 16)), c.input(srgb(64, 64)), c.input(srgb(40, 32))
+        outs = []
+        if with_function:
+            f = c.function(sig)
+            for big in (a, b):
+                outs += c.invoke(f, InvocationArguments(generics=[c.register_descriptor(big)], arguments=[small, big]))
+        else:
+            for big in (a, b):
+                p = c.inscribe(big, Rectangle(0, 0, 16, 16), small)
+                outs += [p, c.resize(p, (8, 8), ResizeMode.Nearest)]
+        sizes = [c.describe_reg(r).size() for r in outs]
+        for r in outs:
+            c.output(r)
+        return c, sizes
+    with_f, sizes = build(True)
+    assert sizes == [(64, 64), (8, 8), (40, 32), (8, 8)]  # one monomorphic copy per call
+    without, _ = build(False)
+    linker = Linker.from_included()
+    assert _same_ops(linker.link(with_f, [], [t], [[1], []]).ops(), linker.compile(without).ops())
+
+    # a callee that does not type check under the bound types fails at invoke and is rolled back
+    c = CommandBuffer()
+    f = c.function(sig)
+    small, tiny = c.input(srgb(16, 16)), c.input(srgb(8, 8))
+    n0 = command.host_lib().zosh_cb_num_ops(c._h)
+    with pytest.raises(CommandError):  # inscribe: the rectangle is not contained in an 8x8 image
+        c.invoke(f, InvocationArguments(generics=[c.register_descriptor(tiny)], arguments=[small, tiny]))
+    assert command.host_lib().zosh_cb_num_ops(c._h) == n0
+    with pytest.raises(CommandError) as e:  # the concrete parameter is checked against its declared type
+        c.invoke(f, InvocationArguments(generics=[c.register_descriptor(small)], arguments=[tiny, small]))
+    assert e.value.is_type_err()
+
+
+def test_template_restrictions():
+    from zosimos_b200.command import GenericVar, InvocationArguments
+    c = CommandBuffer()
+    c.input(srgb(4, 4))
+    with pytest.raises(CommandError):  # generics are declared before the first operation
+        c.generic()
+    with pytest.raises(CommandError) as e:  # command.rs:886-905: only generic command buffers have a computed signature here
+        c.computed_signature()
+    assert e.value.kind == CommandErrorKind.Unimplemented
+    with pytest.raises(CommandError):
+        c.input_generic(GenericVar(0))
+    t = CommandBuffer()
+    v = t.generic()
+    with pytest.raises(CommandError):
+        t.input_generic(GenericVar(v.index + 1))
+    r = t.input_generic(v)
+    with pytest.raises(CommandError):  # no descriptor before the types are bound
+        t.describe_reg(r)
+    with pytest.raises(CommandError):  # operands must be earlier entries of the record
+        t.crop(command.Register(7), Rectangle(0, 0, 1, 1))
+    t.output(r)
+    with pytest.raises(CommandError) as e:  # a generic entry point cannot be compiled (CommandError::UNIMPLEMENTED)
+        Linker.from_included().compile(t)
+    assert e.value.kind == CommandErrorKind.Unimplemented
+    with pytest.raises(CommandError):
+        t.invoke(command.FunctionVar(0), InvocationArguments(generics=[], arguments=[]))

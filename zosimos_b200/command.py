@@ -87,6 +87,18 @@ _HOST_SIGNATURES = {
     "zosh_cb_extract": (C.c_int32, [_P, C.c_int32, C.c_uint32, C.POINTER(C.c_int32)]),
     "zosh_cb_inject": (C.c_int32, [_P, C.c_int32, C.c_uint32, C.c_int32, C.POINTER(C.c_int32)]),
     "zosh_cb_with_knob": (C.c_int32, [_P]),
+    "zosh_cb_generic": (C.c_int32, [_P, C.POINTER(C.c_int32)]),
+    "zosh_cb_input_generic": (C.c_int32, [_P, C.c_int32, C.POINTER(C.c_int32)]),
+    "zosh_cb_computed_signature": (C.c_int32, [_P, C.POINTER(_P)]),
+    "zosh_signature_free": (None, [_P]),
+    "zosh_signature_num_generics": (C.c_uint32, [_P]),
+    "zosh_signature_num_inputs": (C.c_uint32, [_P]),
+    "zosh_signature_num_outputs": (C.c_uint32, [_P]),
+    "zosh_cb_function": (C.c_int32, [_P, _P, C.POINTER(C.c_int32)]),
+    "zosh_cb_num_functions": (C.c_uint32, [_P]),
+    "zosh_cb_invoke": (C.c_int32, [_P, C.c_int32, C.POINTER(_ffi.ZosDesc), C.c_uint32, C.POINTER(C.c_int32), C.c_uint32, C.POINTER(C.c_int32),
+                                   C.c_uint32, C.POINTER(C.c_uint32)]),
+    "zosh_link": (C.c_int32, [_P, C.POINTER(_P), C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(_P)]),
     "zosh_compile": (C.c_int32, [_P, C.POINTER(_P)]),
     "zosh_program_free": (None, [_P]),
     "zosh_program_num_ops": (C.c_uint32, [_P]),
@@ -336,77 +348,39 @@ class CommandBuffer:
         except Exception:
             pass
 
-    # -- functions and generics
-    _record = None
-    _num_generics = 0
+    # -- functions and generics (host.cpp: a command buffer that declares a generic records its builder calls, `invoke` replays them)
+    _is_template = False
 
     def generic(self, declaration: "GenericDeclaration" = None) -> "GenericVar":  # command.rs:856-870
-        if self._record is None:
-            if host_lib().zosh_cb_num_ops(self._h) != 0:
-                raise CommandError(4, "generics must be declared before the first operation")
-            self._record = []
-            for name in _TEMPLATE_METHODS:  # from now on operations are recorded, not built
-                setattr(self, name, self._recorder(name))
-        self._num_generics += 1
-        return GenericVar(self._num_generics - 1)
-
-    def _recorder(self, name):
-        def record(*args, **kwargs):
-            self._record.append((name, args, kwargs))
-            r = _SymReg(len(self._record) - 1)
-            return (r, None) if name == "output" else r
-        return record
+        v = C.c_int32()
+        _check(host_lib().zosh_cb_generic(self._h, C.byref(v)))
+        self._is_template = True
+        return GenericVar(int(v.value))
 
     def input_generic(self, var: "GenericVar") -> Register:  # command.rs:872-884
-        if self._record is None or not (0 <= var.index < self._num_generics):
-            raise CommandError(4, "input_generic: unknown generic")
-        self._record.append(("input_generic", (var,), {}))
-        return _SymReg(len(self._record) - 1)
+        out = C.c_int32()
+        return self._reg(host_lib().zosh_cb_input_generic(self._h, var.index, C.byref(out)), out)
 
     def computed_signature(self) -> "FunctionSignature":  # command.rs:886-905
-        if self._record is None:
-            self._record = []
-            raise CommandError(5, "signatures of non-generic command buffers are not supported")
-        return FunctionSignature(self)
+        h = _P()
+        _check(host_lib().zosh_cb_computed_signature(self._h, C.byref(h)))
+        return FunctionSignature(h, self)
 
     def function(self, signature: "FunctionSignature") -> "FunctionVar":  # command.rs:907-922
-        self._functions = list(getattr(self, "_functions", []))
-        self._functions.append(signature)
-        return FunctionVar(len(self._functions) - 1)
-
-    _functions = ()
+        f = C.c_int32()
+        _check(host_lib().zosh_cb_function(self._h, signature._h, C.byref(f)))
+        return FunctionVar(int(f.value))
 
     def register_descriptor(self, reg: Register) -> Descriptor:  # the concrete type bound to a generic
         return self.describe_reg(reg)
 
     def invoke(self, function: "FunctionVar", arguments: "InvocationArguments") -> List[Register]:  # command.rs:2821-2869
-        if not (0 <= function.index < len(self._functions)):
-            raise CommandError(4, "invoke: unknown function")
-        sig = self._functions[function.index]
-        if len(arguments.generics) != sig.num_generics or len(arguments.arguments) != sig.num_inputs:
-            raise CommandError(3, "invoke: %d generics / %d arguments expected (CommandError::TYPE_ERR)" % (sig.num_generics, sig.num_inputs))
-        mapping, outputs, nxt = {}, [], 0
-
-        def subst(v):
-            if isinstance(v, _SymReg):
-                return mapping[v.index]
-            if isinstance(v, (list, tuple)) and any(isinstance(x, _SymReg) for x in v):
-                return type(v)(subst(x) for x in v)
-            return v
-
-        for pos, (name, args, kwargs) in enumerate(sig.template._record):
-            if name in ("input", "input_generic"):
-                real = arguments.arguments[nxt]; nxt += 1
-                have = self.describe_reg(real)
-                want = arguments.generics[args[0].index] if name == "input_generic" else args[0]
-                if (have.size(), have.texel, have.color) != (want.size(), want.texel, want.color):
-                    raise CommandError(3, "invoke: argument %d does not have the declared type (CommandError::TYPE_ERR)" % (nxt - 1))
-                mapping[pos] = real
-            elif name == "output":
-                outputs.append(subst(args[0]))
-            else:
-                mapping[pos] = getattr(CommandBuffer, name)(self, *[subst(a) for a in args], **{k: subst(v) for k, v in kwargs.items()})
-        return outputs
+        ng, na = len(arguments.generics), len(arguments.arguments)
+        gens = (_ffi.ZosDesc * max(ng, 1))(*[d.to_ffi() for d in arguments.generics])
+        args = (C.c_int32 * max(na, 1))(*[r.index for r in arguments.arguments])
+        results, n = (C.c_int32 * 64)(), C.c_uint32()
+        _check(host_lib().zosh_cb_invoke(self._h, function.index, gens, ng, args, na, results, 64, C.byref(n)))
+        return [Register(int(results[i])) for i in range(n.value)]
 
     # -- plumbing
     def _reg(self, st: int, out: C.c_int32) -> Register:
@@ -437,7 +411,7 @@ class CommandBuffer:
     def output(self, src: Register) -> Tuple[Register, Descriptor]:
         out = C.c_int32()
         r = self._reg(host_lib().zosh_cb_output(self._h, src.index, C.byref(out)), out)
-        return r, self.describe_reg(src)
+        return r, (None if self._is_template else self.describe_reg(src))  # a template's types are bound by the caller
 
     def color_convert(self, src: Register, color: Color, texel: Texel) -> Register:
         out = C.c_int32()
@@ -596,7 +570,8 @@ class WithBuffer:  # command.rs:1963-2060: the next operation's parameter block 
 # their descriptors depend on the types the caller binds.  `invoke` monomorphises: it replays the callee's
 # record into the caller with the generic inputs replaced by the argument registers (the reference does the
 # same at link time, command.rs:2083-2185; here the callee travels inside the signature object, and
-# `Linker.link` checks that the linked functions are the ones that were invoked).
+# `Linker.link` checks that the linked functions are the ones that were invoked).  All of it lives in host.cpp
+# (zosh_cb_generic / zosh_cb_invoke / zosh_link); these classes carry the handles.
 @dataclass(frozen=True)
 class GenericDeclaration:
     bounds: Sequence = ()
@@ -618,23 +593,21 @@ class InvocationArguments:
     arguments: Sequence[Register]
 
 
-@dataclass(frozen=True)
-class _SymReg(Register):
-    """A register of a template command buffer (position in its record)."""
+class FunctionSignature:  # command::CommandSignature
+    def __init__(self, handle, template: "CommandBuffer"):
+        self._h, self.template = handle, template  # the template stays alive: zosh_link compares its identity
+        l = host_lib()
+        self.num_generics = int(l.zosh_signature_num_generics(handle))
+        self.num_inputs = int(l.zosh_signature_num_inputs(handle))
+        self.num_outputs = int(l.zosh_signature_num_outputs(handle))
 
-
-class FunctionSignature:
-    def __init__(self, template: "CommandBuffer"):
-        self.template = template
-        self.num_generics = template._num_generics
-        self.num_inputs = sum(1 for r in template._record if r[0] in ("input", "input_generic"))
-        self.num_outputs = sum(1 for r in template._record if r[0] == "output")
-
-
-_TEMPLATE_METHODS = ("input", "output", "color_convert", "chromatic_adaptation", "inscribe", "crop", "affine", "resize", "blend",
-                     "transmute", "bilinear", "solid_rgba", "derivative", "palette", "extract", "inject", "distribution_normal2d",
-                     "distribution_fractal_noise", "construct_dynamic", "unary_dynamic", "binary_dynamic", "buffer_init", "buffer_zero",
-                     "from_buffer")
+    def __del__(self):
+        try:
+            if self._h:
+                host_lib().zosh_signature_free(self._h)
+                self._h = None
+        except Exception:
+            pass
 
 
 class Linker:
@@ -653,16 +626,14 @@ class Linker:
             raise CommandError(5, "generic entry points are not supported (CommandError::UNIMPLEMENTED)")
         if len(links) != 1 + len(functions):
             raise CommandError(4, "link: one link table per program")
-        for p, table in enumerate(links):
-            decl = main._functions if p == 0 else functions[p - 1]._functions
-            if len(table) != len(decl):
-                raise CommandError(4, "link: program %d declares %d functions, %d linked" % (p, len(decl), len(table)))
-            for f, target in enumerate(table):
-                if not (1 <= target <= len(functions)):
-                    raise CommandError(4, "link: bad function index %d" % target)
-                if functions[target - 1] is not decl[f].template:
-                    raise CommandError(3, "link: function %d of program %d has another signature (CommandError::TYPE_ERR)" % (f, p))
-        return self.compile(main)
+        from .program import Program
+        flat = [int(t) for table in links for t in table]
+        fns = (_P * max(len(functions), 1))(*[f._h for f in functions])
+        tab = (C.c_uint32 * max(len(flat), 1))(*flat)
+        per = (C.c_uint32 * len(links))(*[len(t) for t in links])
+        h = _P()
+        _check(host_lib().zosh_link(main._h, fns, len(functions), tab, per, C.byref(h)))
+        return Program(h, dict(main._knobs))
 
     def compile(self, commands: CommandBuffer) -> "Program":
         from .program import Program

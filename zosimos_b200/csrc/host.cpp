@@ -111,10 +111,41 @@ zos_step make_step(uint32_t kind, const double* m, const double* v = nullptr) {
 
 }  // namespace
 
+// One recorded builder call of a TEMPLATE command buffer (one that declared a generic, command.rs:856-870): the
+// descriptors of its registers depend on the types the caller binds, so its operations are kept as calls and built
+// when `zosh_cb_invoke` replays them into the caller (monomorphisation by inlining; the reference monomorphises at
+// link time, command.rs:2083-2185).  Register operands are positions in the record.
+enum CallFn : uint32_t {
+  FN_INPUT, FN_INPUT_GENERIC, FN_OUTPUT, FN_COLOR_CONVERT, FN_CHROMATIC_ADAPTATION, FN_INSCRIBE, FN_BLEND, FN_CROP, FN_AFFINE, FN_RESIZE,
+  FN_TRANSMUTE, FN_BILINEAR, FN_SOLID_RGBA, FN_NORMAL2D, FN_FRACTAL_NOISE, FN_DERIVATIVE, FN_PALETTE, FN_EXTRACT, FN_INJECT, FN_BUFFER_INIT,
+  FN_BUFFER_ZERO, FN_FROM_BUFFER, FN_WITH_BUFFER_BILINEAR, FN_DYNAMIC
+};
+struct Call {
+  uint32_t fn = 0;
+  int32_t r[2] = {-1, -1};  // register operands (record positions), -1 = none
+  zos_desc d{};             // the descriptor argument, if the builder takes one
+  uint32_t u[3] = {0, 0, 0};
+  int32_t i = 0;
+  float f[24] = {};
+  zosh_rect rect{};
+  std::vector<uint8_t> blob;  // buffer_init bytes / params of a user operator
+  uint64_t len = 0;
+  std::string source;
+  bool knob = false;          // with_knob() preceded the call
+};
+struct zosh_signature {  // command::CommandSignature of a template, with the callee travelling inside
+  std::shared_ptr<const std::vector<Call>> record;
+  uint32_t num_generics = 0, num_inputs = 0, num_outputs = 0;
+  const zosh_cb* origin = nullptr;  // identity of the template, checked by zosh_link
+};
 struct zosh_cb {
   std::vector<zos_op> ops;  // op i defines register i (outputs define a register too, like the reference)
   uint32_t next_knob = 0, pending_knob = 0;
   std::vector<std::shared_ptr<std::vector<uint8_t>>> blobs;  // initial bytes of buffer registers (zos_op::data points into them)
+  bool is_template = false;
+  uint32_t num_generics = 0;
+  std::vector<Call> record;               // template only
+  std::vector<zosh_signature> functions;  // FunctionVar i = functions[i] (command.rs:907-922)
 };
 struct zosh_program {
   std::vector<zos_op> ops;
@@ -140,6 +171,36 @@ zos_op new_op(zosh_cb* cb, uint32_t kind, int32_t s0, int32_t s1, const zos_desc
 int32_t push(zosh_cb* cb, const zos_op& op, int32_t* reg) {
   cb->ops.push_back(op);
   if (reg) *reg = op.dst;
+  return ZOSH_OK;
+}
+// ---- template command buffers: builders record instead of building ----
+bool recording(const zosh_cb* cb) { return cb && cb->is_template; }
+Call call(uint32_t fn, int32_t r0 = -1, int32_t r1 = -1) {
+  Call c;
+  c.fn = fn; c.r[0] = r0; c.r[1] = r1;
+  return c;
+}
+Call call_d(uint32_t fn, const zos_desc* d, int32_t r0 = -1, int32_t r1 = -1) {
+  Call c = call(fn, r0, r1);
+  if (d) c.d = *d;
+  return c;
+}
+Call call_f(Call c, const float* f, int n, int at = 0) {
+  if (f) memcpy(c.f + at, f, sizeof(float) * n);
+  return c;
+}
+Call call_u(Call c, uint32_t u0, uint32_t u1 = 0, uint32_t u2 = 0) {
+  c.u[0] = u0; c.u[1] = u1; c.u[2] = u2;
+  return c;
+}
+int32_t record(zosh_cb* cb, Call c, int32_t* reg) {
+  for (int k = 0; k < 2; k++)  // operands name earlier, non-output entries of the record
+    if (c.r[k] != -1 && (c.r[k] < 0 || (size_t)c.r[k] >= cb->record.size() || cb->record[c.r[k]].fn == FN_OUTPUT))
+      return err(ZOSH_ERR_OTHER, "bad register");
+  c.knob = cb->pending_knob != 0;
+  cb->pending_knob = 0;
+  cb->record.push_back(std::move(c));
+  if (reg) *reg = (int32_t)cb->record.size() - 1;
   return ZOSH_OK;
 }
 }  // namespace
@@ -196,6 +257,7 @@ int32_t zosh_cb_describe(const zosh_cb* cb, int32_t reg, zos_desc* out) {
 }
 
 int32_t zosh_cb_input(zosh_cb* cb, const zos_desc* desc, int32_t* reg) {
+  if (recording(cb) && desc) return record(cb, call_d(FN_INPUT, desc), reg);
   if (!cb || !desc) return err(ZOSH_ERR_OTHER, "null argument");
   zos_desc d = *desc;
   if (d.block == ZOS_BLOCK_PIXEL && d.texel_stride != zos_bits_bytes(d.bits))
@@ -206,6 +268,7 @@ int32_t zosh_cb_input(zosh_cb* cb, const zos_desc* desc, int32_t* reg) {
 }
 
 int32_t zosh_cb_output(zosh_cb* cb, int32_t src, int32_t* reg) {
+  if (recording(cb)) return record(cb, call(FN_OUTPUT, src), reg);
   if (!cb || !valid_reg(cb, src)) return err(ZOSH_ERR_OTHER, "bad register");
   zos_op op = new_op(cb, ZOS_OP_OUTPUT, src, -1, cb->ops[src].desc);
   if (reg) *reg = op.dst;
@@ -215,6 +278,7 @@ int32_t zosh_cb_output(zosh_cb* cb, int32_t src, int32_t* reg) {
 }
 
 int32_t zosh_cb_color_convert(zosh_cb* cb, int32_t src, const zos_desc* target, int32_t* reg) {
+  if (recording(cb) && target) return record(cb, call_d(FN_COLOR_CONVERT, target, src), reg);
   if (!cb || !target || !valid_reg(cb, src)) return err(ZOSH_ERR_OTHER, "bad register");
   const zos_desc& s = cb->ops[src].desc;
   zos_desc d = *target;
@@ -255,6 +319,7 @@ int32_t zosh_cb_color_convert(zosh_cb* cb, int32_t src, const zos_desc* target, 
 }
 
 int32_t zosh_cb_chromatic_adaptation(zosh_cb* cb, int32_t src, uint32_t method, uint32_t target, int32_t* reg) {
+  if (recording(cb)) return record(cb, call_u(call(FN_CHROMATIC_ADAPTATION, src), method, target), reg);
   if (!cb || !valid_reg(cb, src)) return err(ZOSH_ERR_OTHER, "bad register");
   const zos_desc& s = cb->ops[src].desc;
   if (s.color != ZOS_COLOR_RGB) return err(ZOSH_ERR_BAD_DESCRIPTOR, "non-rgb chromatic adaptation");  // command.rs:1149-1157
@@ -279,6 +344,7 @@ static void compose_defaults(zos_compose_params& p) {
 }
 
 int32_t zosh_cb_inscribe(zosh_cb* cb, int32_t below, zosh_rect rect, int32_t above, int32_t* reg) {
+  if (recording(cb)) { Call c = call(FN_INSCRIBE, below, above); c.rect = rect; return record(cb, c, reg); }
   if (!cb || !valid_reg(cb, below) || !valid_reg(cb, above)) return err(ZOSH_ERR_OTHER, "bad register");
   const zos_desc& b = cb->ops[below].desc;
   const zos_desc& a = cb->ops[above].desc;
@@ -295,6 +361,7 @@ int32_t zosh_cb_inscribe(zosh_cb* cb, int32_t below, zosh_rect rect, int32_t abo
 }
 
 int32_t zosh_cb_blend(zosh_cb* cb, int32_t below, zosh_rect rect, int32_t above, int32_t mode, int32_t* reg) {
+  if (recording(cb)) { Call c = call(FN_BLEND, below, above); c.rect = rect; c.i = mode; return record(cb, c, reg); }
   // The reference returns UNIMPLEMENTED here (command.rs:1510-1519); semantics: DESIGN.md section 3.
   if (!cb || !valid_reg(cb, below) || !valid_reg(cb, above)) return err(ZOSH_ERR_OTHER, "bad register");
   const zos_desc& b = cb->ops[below].desc;
@@ -315,6 +382,7 @@ int32_t zosh_cb_blend(zosh_cb* cb, int32_t below, zosh_rect rect, int32_t above,
 }
 
 int32_t zosh_cb_crop(zosh_cb* cb, int32_t src, zosh_rect rect, int32_t* reg) {
+  if (recording(cb)) { Call c = call(FN_CROP, src); c.rect = rect; return record(cb, c, reg); }
   if (!cb || !valid_reg(cb, src)) return err(ZOSH_ERR_OTHER, "bad register");
   const zos_desc& s = cb->ops[src].desc;
   if (rect.max_x <= rect.x || rect.max_y <= rect.y) return err(ZOSH_ERR_OTHER, "crop: empty rectangle");
@@ -328,6 +396,7 @@ int32_t zosh_cb_crop(zosh_cb* cb, int32_t src, zosh_rect rect, int32_t* reg) {
 }
 
 int32_t zosh_cb_affine(zosh_cb* cb, int32_t below, const float m[9], uint32_t sampling, int32_t above, int32_t* reg) {
+  if (recording(cb) && m) return record(cb, call_u(call_f(call(FN_AFFINE, below, above), m, 9), sampling), reg);
   if (!cb || !m || !valid_reg(cb, below) || !valid_reg(cb, above)) return err(ZOSH_ERR_OTHER, "bad register");
   const zos_desc& b = cb->ops[below].desc;
   const zos_desc& a = cb->ops[above].desc;
@@ -351,6 +420,7 @@ int32_t zosh_cb_affine(zosh_cb* cb, int32_t below, const float m[9], uint32_t sa
 }
 
 int32_t zosh_cb_resize(zosh_cb* cb, int32_t below, uint32_t w, uint32_t h, uint32_t mode, int32_t* reg) {
+  if (recording(cb)) return record(cb, call_u(call(FN_RESIZE, below), w, h, mode), reg);
   if (!cb || !valid_reg(cb, below)) return err(ZOSH_ERR_OTHER, "bad register");
   if (w == 0 || h == 0 || mode > ZOSH_RESIZE_BILINEAR) return err(ZOSH_ERR_OTHER, "resize: bad size / mode");
   zos_desc d = cb->ops[below].desc;
@@ -367,6 +437,7 @@ int32_t zosh_cb_resize(zosh_cb* cb, int32_t below, uint32_t w, uint32_t h, uint3
 }
 
 int32_t zosh_cb_transmute(zosh_cb* cb, int32_t src, const zos_desc* target, int32_t* reg) {
+  if (recording(cb) && target) return record(cb, call_d(FN_TRANSMUTE, target, src), reg);
   if (!cb || !target || !valid_reg(cb, src)) return err(ZOSH_ERR_OTHER, "bad register");
   const zos_desc& s = cb->ops[src].desc;
   zos_desc d = *target;
@@ -379,6 +450,7 @@ int32_t zosh_cb_transmute(zosh_cb* cb, int32_t src, const zos_desc* target, int3
 }
 
 int32_t zosh_cb_bilinear(zosh_cb* cb, const zos_desc* desc, const float p[24], int32_t* reg) {
+  if (recording(cb) && desc && p) return record(cb, call_f(call_d(FN_BILINEAR, desc), p, 24), reg);
   if (!cb || !desc || !p) return err(ZOSH_ERR_OTHER, "null argument");
   zos_desc d = *desc;
   if (d.block != ZOS_BLOCK_PIXEL || d.texel_stride != zos_bits_bytes(d.bits) || d.width == 0 || d.height == 0)
@@ -390,6 +462,7 @@ int32_t zosh_cb_bilinear(zosh_cb* cb, const zos_desc* desc, const float p[24], i
 }
 
 int32_t zosh_cb_solid_rgba(zosh_cb* cb, const zos_desc* desc, const float color[4], int32_t* reg) {
+  if (recording(cb) && desc && color) return record(cb, call_f(call_d(FN_SOLID_RGBA, desc), color, 4), reg);
   if (!cb || !desc || !color) return err(ZOSH_ERR_OTHER, "null argument");
   zos_desc d = *desc;
   if (d.block != ZOS_BLOCK_PIXEL || d.texel_stride != zos_bits_bytes(d.bits) || d.width == 0 || d.height == 0)
@@ -441,9 +514,11 @@ static int32_t push_generator(zosh_cb* cb, const zos_desc* desc, uint32_t kind, 
   return push(cb, op, reg);
 }
 int32_t zosh_cb_distribution_normal2d(zosh_cb* cb, const zos_desc* desc, const float params[7], int32_t* reg) {
+  if (recording(cb) && desc && params) return record(cb, call_f(call_d(FN_NORMAL2D, desc), params, 7), reg);
   return push_generator(cb, desc, ZOS_GEN_NORMAL2D, params, 7, reg, "inconsistent descriptor for distribution_normal2d");
 }
 int32_t zosh_cb_distribution_fractal_noise(zosh_cb* cb, const zos_desc* desc, const float params[5], int32_t* reg) {
+  if (recording(cb) && desc && params) return record(cb, call_f(call_d(FN_FRACTAL_NOISE, desc), params, 5), reg);
   if (params && !(params[4] >= 0.0f && params[4] <= 64.0f)) return err(ZOSH_ERR_OTHER, "fractal noise: 0..64 octaves");
   return push_generator(cb, desc, ZOS_GEN_FRACTAL_NOISE, params, 5, reg, "inconsistent descriptor for distribution_fractal_noise");
 }
@@ -464,16 +539,25 @@ static int32_t push_buffer(zosh_cb* cb, const void* data, uint64_t len, int32_t*
   return push(cb, op, reg);
 }
 int32_t zosh_cb_buffer_init(zosh_cb* cb, const void* data, uint64_t len, int32_t* reg) {
+  if (recording(cb) && data && len && len <= (1ull << 32)) {
+    Call c = call(FN_BUFFER_INIT);
+    c.blob.assign((const uint8_t*)data, (const uint8_t*)data + len);
+    return record(cb, std::move(c), reg);
+  }
   if (!data) return err(ZOSH_ERR_OTHER, "null data");
   return push_buffer(cb, data, len, reg);
 }
-int32_t zosh_cb_buffer_zero(zosh_cb* cb, uint64_t len, int32_t* reg) { return push_buffer(cb, nullptr, len, reg); }
+int32_t zosh_cb_buffer_zero(zosh_cb* cb, uint64_t len, int32_t* reg) {
+  if (recording(cb) && len && len <= (1ull << 32)) { Call c = call(FN_BUFFER_ZERO); c.len = len; return record(cb, c, reg); }
+  return push_buffer(cb, nullptr, len, reg);
+}
 int32_t zosh_cb_buffer_size(const zosh_cb* cb, int32_t reg, uint64_t* out) {
   if (!cb || !out || !buffer_reg(cb, reg)) return err(ZOSH_ERR_TYPE, "not a buffer register");
   *out = cb->ops[reg].data_len;
   return ZOSH_OK;
 }
 int32_t zosh_cb_from_buffer(zosh_cb* cb, int32_t buffer, const zos_desc* desc, int32_t* reg) {
+  if (recording(cb) && desc) return record(cb, call_d(FN_FROM_BUFFER, desc, buffer), reg);
   if (!cb || !desc) return err(ZOSH_ERR_OTHER, "null argument");
   if (!buffer_reg(cb, buffer)) return err(ZOSH_ERR_TYPE, "from_buffer: not a buffer register (CommandError::TYPE_ERR)");
   zos_desc d = *desc;
@@ -484,6 +568,7 @@ int32_t zosh_cb_from_buffer(zosh_cb* cb, int32_t buffer, const zos_desc* desc, i
   return push(cb, new_op(cb, ZOS_OP_FROM_BUFFER, buffer, -1, d), reg);
 }
 int32_t zosh_cb_with_buffer_bilinear(zosh_cb* cb, int32_t buffer, const zos_desc* desc, int32_t* reg) {
+  if (recording(cb) && desc) return record(cb, call_d(FN_WITH_BUFFER_BILINEAR, desc, buffer), reg);
   if (!cb || !desc) return err(ZOSH_ERR_OTHER, "null argument");
   if (!buffer_reg(cb, buffer)) return err(ZOSH_ERR_TYPE, "with_buffer: not a buffer register");
   if (cb->ops[buffer].data_len < 96) return err(ZOSH_ERR_OTHER, "with_buffer: the bilinear parameter block needs 96 bytes");
@@ -499,6 +584,12 @@ int32_t zosh_cb_with_buffer_bilinear(zosh_cb* cb, int32_t buffer, const zos_desc
 // ---- user operators (command.rs:2933-3060 construct_dynamic / unary_dynamic / binary_dynamic; command/dynamic.rs)
 int32_t zosh_cb_dynamic(zosh_cb* cb, int32_t src0, int32_t src1, const char* cuda_source, const zos_desc* desc, const void* params,
                         uint64_t params_len, int32_t* reg) {
+  if (recording(cb) && cuda_source && desc && !(src0 < 0 && src1 >= 0)) {
+    Call c = call_d(FN_DYNAMIC, desc, src0 < 0 ? -1 : src0, src1 < 0 ? -1 : src1);
+    c.source = cuda_source;
+    if (params && params_len) c.blob.assign((const uint8_t*)params, (const uint8_t*)params + params_len);
+    return record(cb, std::move(c), reg);
+  }
   if (!cb || !cuda_source || !desc) return err(ZOSH_ERR_OTHER, "null argument");
   if (src0 < 0 && src1 >= 0) return err(ZOSH_ERR_OTHER, "binary_dynamic needs both operands");
   for (int32_t r : {src0, src1})
@@ -523,6 +614,7 @@ int32_t zosh_cb_dynamic(zosh_cb* cb, int32_t src0, int32_t src1, const char* cud
 }
 
 int32_t zosh_cb_derivative(zosh_cb* cb, int32_t src, uint32_t method, uint32_t height_direction, int32_t* reg) {
+  if (recording(cb)) return record(cb, call_u(call(FN_DERIVATIVE, src), method, height_direction), reg);
   if (!cb || !valid_reg(cb, src)) return err(ZOSH_ERR_OTHER, "bad register");
   float sm[3];
   switch (method) {  // command.rs:3343-3409
@@ -544,6 +636,7 @@ int32_t zosh_cb_derivative(zosh_cb* cb, int32_t src, uint32_t method, uint32_t h
 }
 
 int32_t zosh_cb_palette(zosh_cb* cb, int32_t palette, int32_t indices, const float xc[4], const float yc[4], int32_t* reg) {
+  if (recording(cb) && xc && yc) return record(cb, call_f(call_f(call(FN_PALETTE, palette, indices), xc, 4), yc, 4, 4), reg);
   if (!cb || !xc || !yc || !valid_reg(cb, palette) || !valid_reg(cb, indices)) return err(ZOSH_ERR_OTHER, "bad register");
   const zos_desc& p = cb->ops[palette].desc;
   zos_desc d = cb->ops[indices].desc;  // layout of the indices, chroma of the palette (command.rs:1467-1471)
@@ -576,6 +669,7 @@ static bool channel_texel(const zos_desc& s, uint32_t channel, zos_desc& d) {
 }
 
 int32_t zosh_cb_extract(zosh_cb* cb, int32_t src, uint32_t channel, int32_t* reg) {
+  if (recording(cb)) return record(cb, call_u(call(FN_EXTRACT, src), channel), reg);
   if (!cb || !valid_reg(cb, src)) return err(ZOSH_ERR_OTHER, "bad register");
   zos_desc d;
   if (cb->ops[src].desc.block != ZOS_BLOCK_PIXEL || !channel_texel(cb->ops[src].desc, channel, d)) return err(ZOSH_ERR_OTHER, "extract: no such channel texel");  // :1232-1235
@@ -585,6 +679,7 @@ int32_t zosh_cb_extract(zosh_cb* cb, int32_t src, uint32_t channel, int32_t* reg
 }
 
 int32_t zosh_cb_inject(zosh_cb* cb, int32_t below, uint32_t channel, int32_t above, int32_t* reg) {
+  if (recording(cb)) return record(cb, call_u(call(FN_INJECT, below, above), channel), reg);
   if (!cb || !valid_reg(cb, below) || !valid_reg(cb, above)) return err(ZOSH_ERR_OTHER, "bad register");
   const zos_desc& b = cb->ops[below].desc;
   const zos_desc& a = cb->ops[above].desc;
@@ -613,8 +708,142 @@ int32_t zosh_cb_inject(zosh_cb* cb, int32_t below, uint32_t channel, int32_t abo
   return push(cb, op, reg);
 }
 
+// ---- functions and generics (command.rs:856-922, 2821-2869; linking :2083-2185) ----
+int32_t zosh_cb_generic(zosh_cb* cb, int32_t* var) {
+  if (!cb) return err(ZOSH_ERR_OTHER, "null argument");
+  if (!cb->is_template && !cb->ops.empty()) return err(ZOSH_ERR_OTHER, "generics must be declared before the first operation");
+  cb->is_template = true;
+  if (var) *var = (int32_t)cb->num_generics;
+  cb->num_generics++;
+  return ZOSH_OK;
+}
+int32_t zosh_cb_input_generic(zosh_cb* cb, int32_t var, int32_t* reg) {
+  if (!cb || !cb->is_template || var < 0 || (uint32_t)var >= cb->num_generics) return err(ZOSH_ERR_OTHER, "input_generic: unknown generic");
+  Call c = call(FN_INPUT_GENERIC);
+  c.i = var;
+  return record(cb, c, reg);
+}
+int32_t zosh_cb_computed_signature(const zosh_cb* cb, zosh_signature** out) {
+  if (!cb || !out) return err(ZOSH_ERR_OTHER, "null argument");
+  if (!cb->is_template) return err(ZOSH_ERR_UNIMPLEMENTED, "signatures of non-generic command buffers are not supported");
+  zosh_signature* sig = new zosh_signature();
+  sig->record = std::make_shared<const std::vector<Call>>(cb->record);
+  sig->num_generics = cb->num_generics;
+  for (const Call& c : cb->record) {
+    sig->num_inputs += c.fn == FN_INPUT || c.fn == FN_INPUT_GENERIC;
+    sig->num_outputs += c.fn == FN_OUTPUT;
+  }
+  sig->origin = cb;
+  *out = sig;
+  return ZOSH_OK;
+}
+void zosh_signature_free(zosh_signature* sig) { delete sig; }
+uint32_t zosh_signature_num_generics(const zosh_signature* sig) { return sig ? sig->num_generics : 0; }
+uint32_t zosh_signature_num_inputs(const zosh_signature* sig) { return sig ? sig->num_inputs : 0; }
+uint32_t zosh_signature_num_outputs(const zosh_signature* sig) { return sig ? sig->num_outputs : 0; }
+int32_t zosh_cb_function(zosh_cb* cb, const zosh_signature* sig, int32_t* function) {
+  if (!cb || !sig) return err(ZOSH_ERR_OTHER, "null argument");
+  cb->functions.push_back(*sig);
+  if (function) *function = (int32_t)cb->functions.size() - 1;
+  return ZOSH_OK;
+}
+uint32_t zosh_cb_num_functions(const zosh_cb* cb) { return cb ? (uint32_t)cb->functions.size() : 0; }
+
+static int32_t replay(zosh_cb* cb, const Call& c, int32_t r0, int32_t r1, int32_t* reg) {
+  if (c.knob) zosh_cb_with_knob(cb);
+  switch (c.fn) {
+    case FN_COLOR_CONVERT: return zosh_cb_color_convert(cb, r0, &c.d, reg);
+    case FN_CHROMATIC_ADAPTATION: return zosh_cb_chromatic_adaptation(cb, r0, c.u[0], c.u[1], reg);
+    case FN_INSCRIBE: return zosh_cb_inscribe(cb, r0, c.rect, r1, reg);
+    case FN_BLEND: return zosh_cb_blend(cb, r0, c.rect, r1, c.i, reg);
+    case FN_CROP: return zosh_cb_crop(cb, r0, c.rect, reg);
+    case FN_AFFINE: return zosh_cb_affine(cb, r0, c.f, c.u[0], r1, reg);
+    case FN_RESIZE: return zosh_cb_resize(cb, r0, c.u[0], c.u[1], c.u[2], reg);
+    case FN_TRANSMUTE: return zosh_cb_transmute(cb, r0, &c.d, reg);
+    case FN_BILINEAR: return zosh_cb_bilinear(cb, &c.d, c.f, reg);
+    case FN_SOLID_RGBA: return zosh_cb_solid_rgba(cb, &c.d, c.f, reg);
+    case FN_NORMAL2D: return zosh_cb_distribution_normal2d(cb, &c.d, c.f, reg);
+    case FN_FRACTAL_NOISE: return zosh_cb_distribution_fractal_noise(cb, &c.d, c.f, reg);
+    case FN_DERIVATIVE: return zosh_cb_derivative(cb, r0, c.u[0], c.u[1], reg);
+    case FN_PALETTE: return zosh_cb_palette(cb, r0, r1, c.f, c.f + 4, reg);
+    case FN_EXTRACT: return zosh_cb_extract(cb, r0, c.u[0], reg);
+    case FN_INJECT: return zosh_cb_inject(cb, r0, c.u[0], r1, reg);
+    case FN_BUFFER_INIT: return zosh_cb_buffer_init(cb, c.blob.data(), c.blob.size(), reg);
+    case FN_BUFFER_ZERO: return zosh_cb_buffer_zero(cb, c.len, reg);
+    case FN_FROM_BUFFER: return zosh_cb_from_buffer(cb, r0, &c.d, reg);
+    case FN_WITH_BUFFER_BILINEAR: return zosh_cb_with_buffer_bilinear(cb, r0, &c.d, reg);
+    case FN_DYNAMIC: return zosh_cb_dynamic(cb, r0, r1, c.source.c_str(), &c.d, c.blob.empty() ? nullptr : c.blob.data(), c.blob.size(), reg);
+    default: return err(ZOSH_ERR_OTHER, "invoke: unknown recorded call");
+  }
+}
+
+int32_t zosh_cb_invoke(zosh_cb* cb, int32_t function, const zos_desc* generics, uint32_t num_generics, const int32_t* arguments,
+                       uint32_t num_arguments, int32_t* results, uint32_t results_cap, uint32_t* num_results) {
+  if (!cb || (num_generics && !generics) || (num_arguments && !arguments)) return err(ZOSH_ERR_OTHER, "null argument");
+  if (cb->is_template) return err(ZOSH_ERR_UNIMPLEMENTED, "invoke inside a generic command buffer");
+  if (function < 0 || (size_t)function >= cb->functions.size()) return err(ZOSH_ERR_OTHER, "invoke: unknown function");  // BAD_REGISTER
+  const zosh_signature sig = cb->functions[function];  // by value: replay may grow cb->functions' owner
+  if (num_generics != sig.num_generics || num_arguments != sig.num_inputs)
+    return err(ZOSH_ERR_TYPE, "invoke: number of generics / arguments differs from the signature (CommandError::INVALID_CALL)");
+  if (results_cap < sig.num_outputs) return err(ZOSH_ERR_OTHER, "invoke: results array too small");
+  const std::vector<Call>& rec = *sig.record;
+  // arguments are type checked before anything is pushed, so that a failed call leaves the caller untouched
+  uint32_t nxt = 0;
+  for (const Call& c : rec) {
+    if (c.fn != FN_INPUT && c.fn != FN_INPUT_GENERIC) continue;
+    const int32_t real = arguments[nxt++];
+    if (!valid_reg(cb, real)) return err(ZOSH_ERR_OTHER, "invoke: bad argument register");
+    zos_desc want = c.fn == FN_INPUT_GENERIC ? generics[c.i] : c.d;
+    const zos_desc& have = cb->ops[real].desc;
+    if (!same_chroma(have, want) || have.width != want.width || have.height != want.height)
+      return err(ZOSH_ERR_TYPE, "invoke: an argument does not have the declared type (CommandError::INVALID_CALL)");
+  }
+  std::vector<int32_t> map(rec.size(), -1);
+  const size_t ops_before = cb->ops.size(), blobs_before = cb->blobs.size();
+  const uint32_t knob_before = cb->next_knob;
+  uint32_t nout = 0;
+  nxt = 0;
+  for (size_t pos = 0; pos < rec.size(); pos++) {
+    const Call& c = rec[pos];
+    if (c.fn == FN_INPUT || c.fn == FN_INPUT_GENERIC) { map[pos] = arguments[nxt++]; continue; }
+    const int32_t r0 = c.r[0] >= 0 ? map[c.r[0]] : -1, r1 = c.r[1] >= 0 ? map[c.r[1]] : -1;
+    if (c.fn == FN_OUTPUT) { results[nout++] = r0; continue; }
+    const int32_t st = replay(cb, c, r0, r1, &map[pos]);
+    if (st != ZOSH_OK) {  // the callee does not type check with these types: undo the partial inlining
+      cb->ops.resize(ops_before);
+      cb->blobs.resize(blobs_before);
+      cb->next_knob = knob_before;
+      cb->pending_knob = 0;
+      return st;
+    }
+  }
+  if (num_results) *num_results = nout;
+  return ZOSH_OK;
+}
+
+int32_t zosh_link(const zosh_cb* main_cb, const zosh_cb* const* functions, uint32_t num_functions, const uint32_t* links,
+                  const uint32_t* links_per_program, zosh_program** out) {
+  if (!main_cb || !out || (num_functions && !functions) || !links_per_program) return err(ZOSH_ERR_OTHER, "null argument");
+  if (main_cb->is_template) return err(ZOSH_ERR_UNIMPLEMENTED, "generic entry points are not supported (CommandError::UNIMPLEMENTED)");
+  const uint32_t* table = links;
+  for (uint32_t p = 0; p <= num_functions; p++) {
+    const zosh_cb* prog = p == 0 ? main_cb : functions[p - 1];
+    if (!prog) return err(ZOSH_ERR_OTHER, "link: null program");
+    if (links_per_program[p] != prog->functions.size()) return err(ZOSH_ERR_OTHER, "link: one link per declared function of every program");
+    for (uint32_t f = 0; f < links_per_program[p]; f++) {
+      const uint32_t target = table[f];
+      if (target < 1 || target > num_functions) return err(ZOSH_ERR_OTHER, "link: bad function index");
+      if (functions[target - 1] != prog->functions[f].origin)
+        return err(ZOSH_ERR_TYPE, "link: the linked function has another signature (CommandError::TYPE_ERR)");
+    }
+    table += links_per_program[p];
+  }
+  return zosh_compile(main_cb, out);
+}
+
 int32_t zosh_compile(const zosh_cb* cb, zosh_program** out) {
   if (!cb || !out) return err(ZOSH_ERR_OTHER, "null argument");
+  if (cb->is_template) return err(ZOSH_ERR_UNIMPLEMENTED, "generic entry points are not supported (CommandError::UNIMPLEMENTED)");
   // liveness (command.rs:2216-2291): only operations that reach an output are emitted
   std::vector<char> live(cb->ops.size(), 0);
   for (size_t i = cb->ops.size(); i-- > 0;) {
