@@ -157,3 +157,12 @@ def test_palette_near_golden(fixtures, golden_hashes):
     ramp = O.bilinear(O.srgb_rgba8(400, 400), ([0, 0, 0, 1], [0.7, 0, 0, 1], [0, 0, 0, 1], [0, 0.7, 0, 1], [0, 0, 0, 1], [0.3, 0.3, 0, 1]))
     h = O.blockhash256(as_rgba(O.palette(bg, ramp, [1, 0, 0, 0], [0, 1, 0, 0])))
     assert min(bin(int(h, 16) ^ int(g, 16)).count("1") for g in golden_hashes["palette"]) <= 8
+
+
+def test_generic_near_golden(fixtures, golden_hashes):
+    """tests/generic.rs: the palette look-up through a 2048 x 2048 identity ramp (Scalars RGBA8 indices, height = R, width = G).
+    As for `palette`, the reference lists two device-dependent hashes (15 of 256 bits apart); the oracle lands within 4 bits of one."""
+    bg = rgba_image(fixtures["background"])
+    ramp = O.bilinear(O.Desc(2048, 2048, O.RGBA8, O.SCALARS_LINEAR), ([0] * 4, [0] * 4, [0] * 4, [0] * 4, [0] * 4, [1, 1, 0, 0]))
+    h = O.blockhash256(as_rgba(O.palette(bg, ramp, [0, 1, 0, 0], [1, 0, 0, 0])))
+    assert min(bin(int(h, 16) ^ int(g, 16)).count("1") for g in golden_hashes["generic"]) <= 6
