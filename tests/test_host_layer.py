@@ -365,3 +365,20 @@ def test_template_restrictions():
     assert e.value.kind == CommandErrorKind.Unimplemented
     with pytest.raises(CommandError):
         t.invoke(command.FunctionVar(0), InvocationArguments(generics=[], arguments=[]))
+
+
+def test_plain_c_caller_of_the_host_api(tmp_path):
+    """tests/c_abi/host_generic.c: include/zosimos_host.h compiles as C99 and a C program drives the op builder,
+    invoke and link through the shared library (host code only, no GPU call)."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    libdir = os.path.join(ROOT, "zosimos_b200")
+    exe = str(tmp_path / "host_generic")
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c_abi", "host_generic.c"), "-o", exe, "-L", libdir, "-lzosimos_cuda",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "host_generic ok" in out.stdout, out.stderr
