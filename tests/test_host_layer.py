@@ -382,3 +382,77 @@ def test_plain_c_caller_of_the_host_api(tmp_path):
                            "-Wl,-rpath," + libdir])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0 and "host_generic ok" in out.stdout, out.stderr
+
+
+def _random_chain(cb, image, other, steps):
+    """Apply `steps` (a list of small integers) as operations on `image`; `other` is a second 16 x 16 sRGB image."""
+    from zosimos_b200.buffer import Whitepoint
+    rgba8 = Texel.new_u8(SampleParts.RgbA)
+    r = image
+    for s in steps:
+        if s == 0:
+            r = cb.color_convert(r, Color.BT709_RGB, rgba8)
+        elif s == 1:
+            r = cb.color_convert(r, Color.Oklab, Texel(Z.Block.Pixel, SampleBits.UInt8x4, SampleParts.LchA))
+            r = cb.color_convert(r, Color.SRGB, rgba8)
+        elif s == 2:
+            r = cb.resize(r, (24, 20), ResizeMode.Bilinear)
+        elif s == 3:
+            r = cb.resize(r, (33, 17), ResizeMode.Reference)
+        elif s == 4:
+            r = cb.inscribe(r, Rectangle(0, 0, 16, 16), other)
+        elif s == 5:
+            r = cb.blend(r, Rectangle(0, 0, 16, 16), other, Blend.Alpha)
+        elif s == 6:
+            r = cb.affine(r, Affine.new(AffineSample.Nearest).rotate(0.3).shift(2.0, 1.0), other)
+        elif s == 7:
+            r = cb.chromatic_adaptation(r, ChromaticAdaptationMethod.VonKries, Whitepoint.D50)
+        elif s == 8:
+            r = cb.derivative(r, Derivative(DerivativeMethod.Sobel, command.Direction.Width))
+        elif s == 9:
+            r = cb.inject(r, Z.ColorChannel.G, cb.extract(r, Z.ColorChannel.R))
+        elif s == 10:
+            r = cb.crop(r, Rectangle(1, 1, 9, 9))
+        else:
+            r = cb.with_knob().solid_rgba(cb.describe_reg(other) if not cb._is_template else srgb(16, 16), [0.25, 0.5, 0.75, 1.0])
+    return r
+
+
+def test_random_callees_inline_to_the_direct_stream():
+    """Property: for random operation chains, a generic callee invoked from `main` links to exactly the stream of the same
+    chain written into `main` directly (same operations, registers, descriptors and parameter blocks) -- or both fail."""
+    from hypothesis import given, settings, strategies as st
+    from zosimos_b200.command import InvocationArguments
+
+    @settings(max_examples=60, deadline=None)
+    @given(steps=st.lists(st.integers(0, 11), min_size=1, max_size=6), w=st.integers(16, 40), h=st.integers(16, 40))
+    def prop(steps, w, h):
+        t = CommandBuffer()
+        var = t.generic()
+        other_t, image_t = t.input(srgb(16, 16)), t.input_generic(var)
+        t.output(_random_chain(t, image_t, other_t, steps))
+        sig = t.computed_signature()
+
+        direct = CommandBuffer()
+        o, i = direct.input(srgb(16, 16)), direct.input(srgb(w, h))
+        try:
+            direct.output(_random_chain(direct, i, o, steps))
+            expected = Linker.from_included().compile(direct).ops()
+        except CommandError as e:
+            expected = e.kind
+
+        main = CommandBuffer()
+        f = main.function(sig)
+        o, i = main.input(srgb(16, 16)), main.input(srgb(w, h))
+        try:
+            (res,) = main.invoke(f, InvocationArguments(generics=[main.register_descriptor(i)], arguments=[o, i]))
+            main.output(res)
+            got = Linker.from_included().link(main, [], [t], [[1], []]).ops()
+        except CommandError as e:
+            got = e.kind
+            assert command.host_lib().zosh_cb_num_ops(main._h) == 2  # rolled back to the two inputs
+        if isinstance(expected, list):
+            assert isinstance(got, list) and _same_ops(got, expected)
+        else:
+            assert got == expected
+    prop()

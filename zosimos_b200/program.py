@@ -156,7 +156,9 @@ class Program:
     def ops(self) -> List[_ffi.ZosOp]:
         n = host_lib().zosh_program_num_ops(self._h)
         p = host_lib().zosh_program_ops(self._h)
-        return [p[i] for i in range(n)]
+        # copies: p[i] would be a view into the program's memory, dangling once a temporary Program is collected
+        # (the data / source pointers inside still belong to the program -- keep it alive while they are used)
+        return [_ffi.ZosOp.from_buffer_copy(p[i]) for i in range(n)]
 
     def lower_to(self, capabilities: Capabilities) -> "Executable":
         return Executable(self, capabilities)
