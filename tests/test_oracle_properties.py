@@ -155,3 +155,24 @@ def test_yuv_nearest_and_bilinear_chroma_agree_on_flat_chroma():
     a = O.decode_yuv420(y, u, v, w, h, 0.2126, 0.0722, False, False, 0, O.TR_BT709)
     b = O.decode_yuv420(y, u, v, w, h, 0.2126, 0.0722, False, False, 1, O.TR_BT709)
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("src_wh,dst_wh", [((64, 48), (32, 24)), ((300, 200), (517, 333)), ((1000, 7), (400, 400)), ((5, 5), (1, 1))])
+def test_reference_resize_is_an_8_bit_coordinate_lookup(src_wh, dst_wh):
+    """command.rs:1675-1702 + bilinear.frag:14-20 + palette.frag:21-32, restated independently in numpy: the (u, v) ramp
+    rests in an f16 texture, is packed into an RGBA8 `Scalars` register by TRUNCATION, unpacked to k / 255 (f16 again), biased
+    by half a texel OF THE GRID and used for a nearest fetch -- so at most 256 distinct source columns / rows are ever
+    read.  Integer / index work: exact."""
+    (sw, sh), (dw, dh) = src_wh, dst_wh
+    src = np.random.default_rng(sw * 31 + dw).integers(0, 256, (sh, sw, 4), dtype=np.uint8)
+    got = O.resize(O.Image(O.srgb_rgba8(sw, sh), src.reshape(sh, sw * 4)), (dw, dh), "reference").data.reshape(dh, dw, 4)
+    f32, f16 = np.float32, lambda a: a.astype(np.float16).astype(np.float32)
+
+    def index(n_dst, n_src):
+        u = f16((np.arange(n_dst, dtype=f32) + f32(0.5)) / f32(n_dst))                 # the draw wrote an Rgba16Float attachment
+        k = (np.clip(u, f32(0), f32(1)) * f32(255)).astype(np.uint32)                  # mux_uint: truncation
+        c = f16(k.astype(f32) / f32(255)) + f32(0.5) / f32(n_dst)                      # demux_uint, then palette.frag's bias
+        return np.clip(np.floor(c * f32(n_src)).astype(np.int64), 0, n_src - 1)        # nearest, clamp to edge
+    xs, ys = index(dw, sw), index(dh, sh)
+    assert np.array_equal(got, src[ys][:, xs])
+    assert len(np.unique(xs)) <= 256 and len(np.unique(ys)) <= 256
