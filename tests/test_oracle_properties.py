@@ -176,3 +176,28 @@ def test_reference_resize_is_an_8_bit_coordinate_lookup(src_wh, dst_wh):
     xs, ys = index(dw, sw), index(dh, sh)
     assert np.array_equal(got, src[ys][:, xs])
     assert len(np.unique(xs)) <= 256 and len(np.unique(ys)) <= 256
+
+
+@SET
+@given(seed=st.integers(0, 2**31 - 1), angle=st.floats(-3.1, 3.1), sx=st.floats(0.4, 2.5), sy=st.floats(0.4, 2.5),
+       tx=st.floats(-20, 40), ty=st.floats(-20, 40))
+def test_affine_nearest_is_the_inverse_map_of_pixel_centres(seed, angle, sx, sy, tx, ty):
+    """program.rs:1898-1935 + box.vert:43-59 + copy.frag:8-10, restated in float64: dst pixel (i, j) is covered iff
+    p = A^-1 (i + 1/2, j + 1/2) lies inside `above`, and then takes above[floor p_y][floor p_x]; uncovered pixels keep `below`.
+    Pixels whose p is within 1e-3 of a texel edge are left out (f32 vs f64 may floor them differently); index work: exact."""
+    rng = np.random.default_rng(seed)
+    aw, ah, bw, bh = 23, 17, 61, 47
+    above, below = rgba(rng, ah, aw), rgba(rng, bh, bw)
+    A = O.shift(tx, ty) @ O.rotate(angle) @ O.scale(sx, sy)      # Affine::{scale, rotate, shift} left-multiply
+    inv = np.linalg.inv(A.astype(np.float64))
+    dst = below.copy()
+    O.paint_affine(dst, above, inv.astype(np.float32).reshape(9), 0)
+    jj, ii = np.mgrid[0:bh, 0:bw]
+    p = np.einsum("rc,chw->rhw", inv, np.stack([ii + 0.5, jj + 0.5, np.ones_like(ii, dtype=np.float64)]))
+    px, py = p[0] / p[2], p[1] / p[2]
+    near_edge = (np.abs(px - np.round(px)) < 1e-3) | (np.abs(py - np.round(py)) < 1e-3)
+    inside = (px >= 0) & (px < aw) & (py >= 0) & (py < ah)
+    fx, fy = np.clip(np.floor(px).astype(int), 0, aw - 1), np.clip(np.floor(py).astype(int), 0, ah - 1)
+    exp = np.where(inside[..., None], above[fy, fx], below)
+    sure = ~near_edge
+    assert np.array_equal(dst[sure], exp[sure])
