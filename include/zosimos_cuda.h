@@ -112,12 +112,12 @@ void zos_ctx_destroy(zos_ctx* ctx);
 const char* zos_last_error(const zos_ctx* ctx); /* ctx may be NULL: last error of a failed create */
 int32_t zos_ctx_device(const zos_ctx* ctx);
 void* zos_ctx_stream(const zos_ctx* ctx);       /* the cudaStream_t all launches of this ctx go to */
-zos_status zos_sync(zos_ctx* ctx);
+zos_status zos_sync(zos_ctx* ctx);             /* SyncPoint::block_on, run.rs:3019 */
 /* Verification hook, host only (no context, no GPU): the rounding thresholds of the correctly rounded sRGB8
  * encoder (thr[k] = smallest f32 whose code is >= k; [0] = -inf, [256..259] = +inf) and the two bucket tables
  * the kernels derive from them (zosimos_b200/csrc/texel.cuh).  Arrays may be NULL; buckets holds up to 2048
  * entries.  The reference leaves this encode to the texture unit (program.rs:794-838). */
-zos_status zos_srgb_encoder_tables(float* thresholds260, uint32_t* buckets, uint32_t* n_buckets, uint32_t* buckets2, uint32_t* n_buckets2);              /* SyncPoint::block_on, run.rs:3019 */
+zos_status zos_srgb_encoder_tables(float* thresholds260, uint32_t* buckets, uint32_t* n_buckets, uint32_t* buckets2, uint32_t* n_buckets2);
 uint64_t zos_ctx_launch_count(const zos_ctx* ctx); /* kernels launched so far (bench: gpu_launches) */
 /* debugging / parity switches; ZOS_CTX_NO_FAST_PATHS routes every launch through the generic kernels */
 enum { ZOS_CTX_NO_FAST_PATHS = 1 };
@@ -227,9 +227,8 @@ typedef struct zos_compose_params {
 zos_status zos_compose(zos_ctx* ctx, const zos_image* below, const zos_image* above, const zos_image* dst,
                        const zos_compose_params* params, uint32_t batch);
 
-/* constructors (ConstructOp::{Solid,Bilinear}, command.rs:1524-1633; bilinear.frag, solid_rgb.frag):
- * p = 24 floats u_min,u_max,v_min,v_max,uv_min,uv_max; for a solid colour put it in u_min and zero the rest */
-/* Generators (DrawInto without operands): kind + 24 floats (unused ones ignored).
+/* Generators (ConstructOp::{Solid,Bilinear,...}, command.rs:1524-1633; DrawInto without operands): kind + 24 floats
+ * (unused ones ignored).
  *   BILINEAR      u_min,u_max,v_min,v_max,uv_min,uv_max (6 x vec4; bilinear.frag:14-20, shaders/bilinear.rs:34-45)
  *   SOLID         colour (solid_rgb.frag)
  *   NORMAL2D      expectation[2], covariance_inverse[4] row major, pseudo_determinant (distribution_normal2d.frag:43-55)
