@@ -1,6 +1,7 @@
 """CPU-side tests (no GPU): the C-ABI library loads and exports every symbol the headers declare,
 and the C++ host mirror of the op builder (CommandBuffer / Linker) behaves like the reference:
 same checks, same error kinds (lib/zosimos/src/command.rs), same parameter matrices as the oracle."""
+import ctypes as C
 import os
 import re
 
@@ -456,3 +457,57 @@ def test_random_callees_inline_to_the_direct_stream():
         else:
             assert got == expected
     prop()
+
+
+def test_every_builder_replays():
+    """The builders the random chains above do not reach: generators, byte buffers, transmute, palette, user operators."""
+    from zosimos_b200.command import (DistributionNormal2d, FractalNoise, InvocationArguments, Palette, ShaderCommand)
+
+    class Tint(ShaderCommand):
+        def source(self):
+            return "__device__ float4 zos_shade(float2 uv, const unsigned char* p, zos_tex a, zos_tex b) { return a.fetch(uv); }"
+
+        def data(self, sd):
+            sd.set_data(np.arange(4, dtype=np.float32))
+            return srgb(20, 10)
+    luma_a16 = Descriptor.with_srgb_image("luma_a16", 20, 10)
+    ramp = Bilinear([0] * 4, [1, 0, 0, 1], [0] * 4, [0, 1, 0, 1], [0] * 4, [0] * 4)
+
+    def body(cb, image):
+        outs = [cb.transmute(image, luma_a16)]
+        outs.append(cb.distribution_normal2d(srgb(20, 10), DistributionNormal2d.with_diagonal(0.1, 0.2)))
+        outs.append(cb.distribution_fractal_noise(srgb(20, 10), FractalNoise.with_octaves(3)))
+        buf = cb.buffer_init(np.asarray(ramp.flat(), np.float32).tobytes())
+        assert cb.buffer_size(buf) == 96
+        outs.append(cb.with_buffer(buf).bilinear(srgb(20, 10), ramp))
+        zero = cb.buffer_zero(zos_bytes)
+        outs.append(cb.from_buffer(zero, srgb(20, 10)))
+        idx = cb.bilinear(srgb(20, 10), ramp)
+        outs.append(cb.palette(image, Palette(width=Z.ColorChannel.R, height=Z.ColorChannel.G), idx))
+        outs.append(cb.construct_dynamic(Tint()))
+        outs.append(cb.unary_dynamic(image, Tint()))
+        outs.append(cb.binary_dynamic(image, idx, Tint()))
+        for r in outs:
+            cb.output(r)
+        return len(outs)
+    zos_bytes = int(srgb(20, 10).to_aligned().row_stride) * 10
+
+    t = CommandBuffer()
+    n = body(t, t.input_generic(t.generic()))
+    sig = t.computed_signature()
+    assert sig.num_outputs == n
+    main = CommandBuffer()
+    f = main.function(sig)
+    inp = main.input(srgb(20, 10))
+    for r in main.invoke(f, InvocationArguments(generics=[main.register_descriptor(inp)], arguments=[inp])):
+        main.output(r)
+    linked_prog = Linker.from_included().link(main, [], [t], [[1], []])
+    direct = CommandBuffer()
+    body(direct, direct.input(srgb(20, 10)))
+    direct_prog = Linker.from_included().compile(direct)
+    a, b = linked_prog.ops(), direct_prog.ops()
+    assert _same_ops(a, b)
+    for x, y in zip(a, b):  # blobs and source text travel with the replayed operations
+        assert x.data_len == y.data_len and (x.source or b"") == (y.source or b"")
+        if x.data_len and x.data:
+            assert C.string_at(x.data, x.data_len) == C.string_at(y.data, y.data_len)

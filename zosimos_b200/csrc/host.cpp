@@ -552,6 +552,11 @@ int32_t zosh_cb_buffer_zero(zosh_cb* cb, uint64_t len, int32_t* reg) {
   return push_buffer(cb, nullptr, len, reg);
 }
 int32_t zosh_cb_buffer_size(const zosh_cb* cb, int32_t reg, uint64_t* out) {
+  if (recording(cb) && out && reg >= 0 && (size_t)reg < cb->record.size() &&
+      (cb->record[reg].fn == FN_BUFFER_INIT || cb->record[reg].fn == FN_BUFFER_ZERO)) {  // a buffer's size does not depend on the bound types
+    *out = cb->record[reg].fn == FN_BUFFER_INIT ? cb->record[reg].blob.size() : cb->record[reg].len;
+    return ZOSH_OK;
+  }
   if (!cb || !out || !buffer_reg(cb, reg)) return err(ZOSH_ERR_TYPE, "not a buffer register");
   *out = cb->ops[reg].data_len;
   return ZOSH_OK;
