@@ -105,6 +105,10 @@ uint32_t zosh_signature_num_inputs(const zosh_signature* sig);
 uint32_t zosh_signature_num_outputs(const zosh_signature* sig);
 int32_t zosh_cb_function(zosh_cb* cb, const zosh_signature* sig, int32_t* function);                     /* command.rs:907-922 */
 uint32_t zosh_cb_num_functions(const zosh_cb* cb);
+/* Inside a template, a generic of the callee can be bound to one of the template's own generics: pass a zos_desc whose
+ * `reserved` field is ZOSH_GENERIC_VAR | var (everything else ignored).  Such calls are recorded and inlined, with their
+ * types checked, when the enclosing template is itself invoked. */
+#define ZOSH_GENERIC_VAR 0x80000000u
 /* InvocationArguments{generics, arguments}; results[] receives the registers of the callee's outputs, in order.
  * ZOSH_ERR_TYPE = CommandError::INVALID_CALL (count or type mismatch), ZOSH_ERR_OTHER = BAD_REGISTER. */
 int32_t zosh_cb_invoke(zosh_cb* cb, int32_t function, const zos_desc* generics, uint32_t num_generics, const int32_t* arguments,

@@ -511,3 +511,53 @@ def test_every_builder_replays():
         assert x.data_len == y.data_len and (x.source or b"") == (y.source or b"")
         if x.data_len and x.data:
             assert C.string_at(x.data, x.data_len) == C.string_at(y.data, y.data_len)
+
+
+def test_generic_function_calling_a_generic_function():
+    """A template that declares and invokes another function, binding the callee's generic to its own: two levels of
+    inlining give the stream of the flat pipeline; the inner type error surfaces at the outer invoke and rolls back."""
+    from zosimos_b200.command import InvocationArguments
+    rgba8 = Texel.new_u8(SampleParts.RgbA)
+
+    inner = CommandBuffer()                      # inner<T>(small: srgb 16x16, image: T) -> inscribe
+    v = inner.generic()
+    small_i, image_i = inner.input(srgb(16, 16)), inner.input_generic(v)
+    inner.output(inner.inscribe(image_i, Rectangle(0, 0, 16, 16), small_i))
+    inner_sig = inner.computed_signature()
+
+    outer = CommandBuffer()                      # outer<U>(image: U, small) -> (inner<U>(small, bt709(image)) resized, its input converted)
+    u = outer.generic()
+    f_inner = outer.function(inner_sig)
+    image_o, small_o = outer.input_generic(u), outer.input(srgb(16, 16))
+    conv = outer.color_convert(image_o, Color.SRGB, rgba8)
+    (placed,) = outer.invoke(f_inner, InvocationArguments(generics=[u], arguments=[small_o, conv]))
+    outer.output(outer.resize(placed, (8, 8), ResizeMode.Nearest))
+    outer.output(conv)
+    with pytest.raises(CommandError):            # counts are checked when the call is recorded
+        outer.invoke(f_inner, InvocationArguments(generics=[], arguments=[small_o, conv]))
+    with pytest.raises(CommandError):            # a generic the template does not have
+        outer.invoke(f_inner, InvocationArguments(generics=[command.GenericVar(5)], arguments=[small_o, conv]))
+    outer_sig = outer.computed_signature()
+    assert (outer_sig.num_generics, outer_sig.num_inputs, outer_sig.num_outputs) == (1, 2, 2)
+
+    main = CommandBuffer()
+    f = main.function(outer_sig)
+    big, small, tiny = main.input(srgb(48, 40)), main.input(srgb(16, 16)), main.input(srgb(8, 8))
+    n0 = command.host_lib().zosh_cb_num_ops(main._h)
+    with pytest.raises(CommandError):            # 16x16 does not fit into 8x8: the INNER inscribe fails, everything is undone
+        main.invoke(f, InvocationArguments(generics=[main.register_descriptor(tiny)], arguments=[tiny, small]))
+    assert command.host_lib().zosh_cb_num_ops(main._h) == n0
+    a, b = main.invoke(f, InvocationArguments(generics=[main.register_descriptor(big)], arguments=[big, small]))
+    assert main.describe_reg(a).size() == (8, 8) and main.describe_reg(b).size() == (48, 40)
+    main.output(a); main.output(b)
+    linker = Linker.from_included()
+    with pytest.raises(CommandError):            # outer's own link table is checked as well: it calls program 2, not itself
+        linker.link(main, [], [outer, inner], [[1], [1], []])
+    linked = linker.link(main, [], [outer, inner], [[1], [2], []])
+
+    flat = CommandBuffer()
+    big, small, tiny = flat.input(srgb(48, 40)), flat.input(srgb(16, 16)), flat.input(srgb(8, 8))
+    conv = flat.color_convert(big, Color.SRGB, rgba8)
+    flat.output(flat.resize(flat.inscribe(conv, Rectangle(0, 0, 16, 16), small), (8, 8), ResizeMode.Nearest))
+    flat.output(conv)
+    assert _same_ops(linked.ops(), linker.compile(flat).ops())

@@ -376,7 +376,13 @@ class CommandBuffer:
 
     def invoke(self, function: "FunctionVar", arguments: "InvocationArguments") -> List[Register]:  # command.rs:2821-2869
         ng, na = len(arguments.generics), len(arguments.arguments)
-        gens = (_ffi.ZosDesc * max(ng, 1))(*[d.to_ffi() for d in arguments.generics])
+        def bound(g):  # inside a template a generic of the callee may be bound to one of the template's own generics
+            if isinstance(g, GenericVar):
+                d = _ffi.ZosDesc()
+                d.reserved = 0x80000000 | g.index  # ZOSH_GENERIC_VAR
+                return d
+            return g.to_ffi()
+        gens = (_ffi.ZosDesc * max(ng, 1))(*[bound(g) for g in arguments.generics])
         args = (C.c_int32 * max(na, 1))(*[r.index for r in arguments.arguments])
         results, n = (C.c_int32 * 64)(), C.c_uint32()
         _check(host_lib().zosh_cb_invoke(self._h, function.index, gens, ng, args, na, results, 64, C.byref(n)))
@@ -589,7 +595,7 @@ class FunctionVar:
 
 @dataclass(frozen=True)
 class InvocationArguments:
-    generics: Sequence[Descriptor]
+    generics: Sequence  # Descriptor, or (inside a template) a GenericVar of the calling template
     arguments: Sequence[Register]
 
 

@@ -118,7 +118,9 @@ zos_step make_step(uint32_t kind, const double* m, const double* v = nullptr) {
 enum CallFn : uint32_t {
   FN_INPUT, FN_INPUT_GENERIC, FN_OUTPUT, FN_COLOR_CONVERT, FN_CHROMATIC_ADAPTATION, FN_INSCRIBE, FN_BLEND, FN_CROP, FN_AFFINE, FN_RESIZE,
   FN_TRANSMUTE, FN_BILINEAR, FN_SOLID_RGBA, FN_NORMAL2D, FN_FRACTAL_NOISE, FN_DERIVATIVE, FN_PALETTE, FN_EXTRACT, FN_INJECT, FN_BUFFER_INIT,
-  FN_BUFFER_ZERO, FN_FROM_BUFFER, FN_WITH_BUFFER_BILINEAR, FN_DYNAMIC
+  FN_BUFFER_ZERO, FN_FROM_BUFFER, FN_WITH_BUFFER_BILINEAR, FN_DYNAMIC,
+  FN_INVOKE,         // a call of another function from inside a template: i = function variable, generics / args below
+  FN_INVOKED_RESULT  // Op::InvokedResult (command.rs:2821-2869): result u[0] of the FN_INVOKE at record position r[0]
 };
 struct Call {
   uint32_t fn = 0;
@@ -132,11 +134,14 @@ struct Call {
   uint64_t len = 0;
   std::string source;
   bool knob = false;          // with_knob() preceded the call
+  std::vector<zos_desc> generics;  // FN_INVOKE: a descriptor, or ZOSH_GENERIC_VAR | k in `reserved` = the template's generic k
+  std::vector<int32_t> args;       // FN_INVOKE: argument registers (record positions)
 };
 struct zosh_signature {  // command::CommandSignature of a template, with the callee travelling inside
   std::shared_ptr<const std::vector<Call>> record;
   uint32_t num_generics = 0, num_inputs = 0, num_outputs = 0;
   const zosh_cb* origin = nullptr;  // identity of the template, checked by zosh_link
+  std::shared_ptr<const std::vector<zosh_signature>> functions;  // the functions the template itself declared (nested calls)
 };
 struct zosh_cb {
   std::vector<zos_op> ops;  // op i defines register i (outputs define a register too, like the reference)
@@ -195,7 +200,7 @@ Call call_u(Call c, uint32_t u0, uint32_t u1 = 0, uint32_t u2 = 0) {
 }
 int32_t record(zosh_cb* cb, Call c, int32_t* reg) {
   for (int k = 0; k < 2; k++)  // operands name earlier, non-output entries of the record
-    if (c.r[k] != -1 && (c.r[k] < 0 || (size_t)c.r[k] >= cb->record.size() || cb->record[c.r[k]].fn == FN_OUTPUT))
+    if (c.r[k] != -1 && (c.r[k] < 0 || (size_t)c.r[k] >= cb->record.size() || cb->record[c.r[k]].fn == FN_OUTPUT || cb->record[c.r[k]].fn == FN_INVOKE))
       return err(ZOSH_ERR_OTHER, "bad register");
   c.knob = cb->pending_knob != 0;
   cb->pending_knob = 0;
@@ -739,6 +744,7 @@ int32_t zosh_cb_computed_signature(const zosh_cb* cb, zosh_signature** out) {
     sig->num_outputs += c.fn == FN_OUTPUT;
   }
   sig->origin = cb;
+  sig->functions = std::make_shared<const std::vector<zosh_signature>>(cb->functions);
   *out = sig;
   return ZOSH_OK;
 }
@@ -782,17 +788,14 @@ static int32_t replay(zosh_cb* cb, const Call& c, int32_t r0, int32_t r1, int32_
   }
 }
 
-int32_t zosh_cb_invoke(zosh_cb* cb, int32_t function, const zos_desc* generics, uint32_t num_generics, const int32_t* arguments,
-                       uint32_t num_arguments, int32_t* results, uint32_t results_cap, uint32_t* num_results) {
-  if (!cb || (num_generics && !generics) || (num_arguments && !arguments)) return err(ZOSH_ERR_OTHER, "null argument");
-  if (cb->is_template) return err(ZOSH_ERR_UNIMPLEMENTED, "invoke inside a generic command buffer");
-  if (function < 0 || (size_t)function >= cb->functions.size()) return err(ZOSH_ERR_OTHER, "invoke: unknown function");  // BAD_REGISTER
-  const zosh_signature sig = cb->functions[function];  // by value: replay may grow cb->functions' owner
+// Inline `sig` into the (non-template) command buffer `cb`.  Type errors of the callee under the bound types surface here.
+static int32_t inline_signature(zosh_cb* cb, const zosh_signature& sig, const zos_desc* generics, uint32_t num_generics,
+                                const int32_t* arguments, uint32_t num_arguments, std::vector<int32_t>& results, int depth) {
+  if (depth > 32) return err(ZOSH_ERR_OTHER, "invoke: functions nest deeper than 32 calls (recursion?)");
   if (num_generics != sig.num_generics || num_arguments != sig.num_inputs)
     return err(ZOSH_ERR_TYPE, "invoke: number of generics / arguments differs from the signature (CommandError::INVALID_CALL)");
-  if (results_cap < sig.num_outputs) return err(ZOSH_ERR_OTHER, "invoke: results array too small");
   const std::vector<Call>& rec = *sig.record;
-  // arguments are type checked before anything is pushed, so that a failed call leaves the caller untouched
+  // arguments are type checked before anything is pushed
   uint32_t nxt = 0;
   for (const Call& c : rec) {
     if (c.fn != FN_INPUT && c.fn != FN_INPUT_GENERIC) continue;
@@ -804,25 +807,78 @@ int32_t zosh_cb_invoke(zosh_cb* cb, int32_t function, const zos_desc* generics, 
       return err(ZOSH_ERR_TYPE, "invoke: an argument does not have the declared type (CommandError::INVALID_CALL)");
   }
   std::vector<int32_t> map(rec.size(), -1);
-  const size_t ops_before = cb->ops.size(), blobs_before = cb->blobs.size();
-  const uint32_t knob_before = cb->next_knob;
-  uint32_t nout = 0;
+  std::vector<std::vector<int32_t>> nested(rec.size());  // results of the FN_INVOKE at each position
   nxt = 0;
   for (size_t pos = 0; pos < rec.size(); pos++) {
     const Call& c = rec[pos];
     if (c.fn == FN_INPUT || c.fn == FN_INPUT_GENERIC) { map[pos] = arguments[nxt++]; continue; }
     const int32_t r0 = c.r[0] >= 0 ? map[c.r[0]] : -1, r1 = c.r[1] >= 0 ? map[c.r[1]] : -1;
-    if (c.fn == FN_OUTPUT) { results[nout++] = r0; continue; }
-    const int32_t st = replay(cb, c, r0, r1, &map[pos]);
-    if (st != ZOSH_OK) {  // the callee does not type check with these types: undo the partial inlining
-      cb->ops.resize(ops_before);
-      cb->blobs.resize(blobs_before);
-      cb->next_knob = knob_before;
-      cb->pending_knob = 0;
-      return st;
+    if (c.fn == FN_OUTPUT) { results.push_back(r0); continue; }
+    if (c.fn == FN_INVOKED_RESULT) { map[pos] = nested[c.r[0]][c.u[0]]; continue; }
+    if (c.fn == FN_INVOKE) {
+      if (c.i < 0 || (size_t)c.i >= sig.functions->size()) return err(ZOSH_ERR_OTHER, "invoke: unknown function");
+      std::vector<zos_desc> gens;
+      for (const zos_desc& g : c.generics)  // the callee's own generics flow into the nested call
+        gens.push_back((g.reserved & ZOSH_GENERIC_VAR) ? generics[g.reserved & ~ZOSH_GENERIC_VAR] : g);
+      std::vector<int32_t> args;
+      for (int32_t a : c.args) args.push_back(map[a]);
+      const int32_t st = inline_signature(cb, (*sig.functions)[c.i], gens.data(), (uint32_t)gens.size(), args.data(), (uint32_t)args.size(),
+                                          nested[pos], depth + 1);
+      if (st != ZOSH_OK) return st;
+      continue;
     }
+    const int32_t st = replay(cb, c, r0, r1, &map[pos]);
+    if (st != ZOSH_OK) return st;
   }
-  if (num_results) *num_results = nout;
+  return ZOSH_OK;
+}
+
+int32_t zosh_cb_invoke(zosh_cb* cb, int32_t function, const zos_desc* generics, uint32_t num_generics, const int32_t* arguments,
+                       uint32_t num_arguments, int32_t* results, uint32_t results_cap, uint32_t* num_results) {
+  if (!cb || (num_generics && !generics) || (num_arguments && !arguments)) return err(ZOSH_ERR_OTHER, "null argument");
+  if (function < 0 || (size_t)function >= cb->functions.size()) return err(ZOSH_ERR_OTHER, "invoke: unknown function");  // BAD_REGISTER
+  const zosh_signature sig = cb->functions[function];
+  if (results_cap < sig.num_outputs) return err(ZOSH_ERR_OTHER, "invoke: results array too small");
+  if (cb->is_template) {  // recorded; types are checked when the enclosing template is itself inlined
+    if (num_generics != sig.num_generics || num_arguments != sig.num_inputs)
+      return err(ZOSH_ERR_TYPE, "invoke: number of generics / arguments differs from the signature (CommandError::INVALID_CALL)");
+    Call c = call(FN_INVOKE);
+    c.i = function;
+    for (uint32_t k = 0; k < num_generics; k++) {
+      if ((generics[k].reserved & ZOSH_GENERIC_VAR) && (generics[k].reserved & ~ZOSH_GENERIC_VAR) >= cb->num_generics)
+        return err(ZOSH_ERR_OTHER, "invoke: unknown generic");
+      c.generics.push_back(generics[k]);
+    }
+    for (uint32_t k = 0; k < num_arguments; k++) {
+      const int32_t a = arguments[k];
+      if (a < 0 || (size_t)a >= cb->record.size() || cb->record[a].fn == FN_OUTPUT || cb->record[a].fn == FN_INVOKE)
+        return err(ZOSH_ERR_OTHER, "invoke: bad argument register");
+      c.args.push_back(a);
+    }
+    int32_t at = -1;
+    record(cb, std::move(c), &at);
+    for (uint32_t k = 0; k < sig.num_outputs; k++) {
+      Call r = call_u(call(FN_INVOKED_RESULT), k);
+      r.r[0] = at;
+      cb->record.push_back(r);
+      results[k] = (int32_t)cb->record.size() - 1;
+    }
+    if (num_results) *num_results = sig.num_outputs;
+    return ZOSH_OK;
+  }
+  const size_t ops_before = cb->ops.size(), blobs_before = cb->blobs.size();
+  const uint32_t knob_before = cb->next_knob;
+  std::vector<int32_t> out;
+  const int32_t st = inline_signature(cb, sig, generics, num_generics, arguments, num_arguments, out, 0);
+  if (st != ZOSH_OK) {  // a failed call leaves the caller untouched: undo the partial inlining
+    cb->ops.resize(ops_before);
+    cb->blobs.resize(blobs_before);
+    cb->next_knob = knob_before;
+    cb->pending_knob = 0;
+    return st;
+  }
+  for (size_t k = 0; k < out.size(); k++) results[k] = out[k];
+  if (num_results) *num_results = (uint32_t)out.size();
   return ZOSH_OK;
 }
 
