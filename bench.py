@@ -58,12 +58,39 @@ def _descs():
     return Z, d, Color, Texel, SampleParts, Transfer
 
 
+class HostParams:
+    """The matrices the workloads need, from the product's host layer (zosh_to_xyz_matrix and Affine of
+    libzosimos_cuda.so) and float64 numpy -- this arm must not execute anything under oracle/."""
+
+    @staticmethod
+    def to_xyz(primaries, whitepoint):
+        import zosimos_b200 as Z
+        from zosimos_b200 import command
+        prim = {"bt709": Z.Primaries.Bt709, "bt2020": Z.Primaries.Bt2020}[primaries]
+        return command.to_xyz_matrix(prim, {"D65": Z.Whitepoint.D65}[whitepoint]).astype(np.float64)
+
+    @staticmethod
+    def inv3(m):
+        return np.linalg.inv(np.asarray(m, dtype=np.float64).reshape(3, 3))
+
+    @staticmethod
+    def mul3(a, b):
+        return np.asarray(a, dtype=np.float64).reshape(3, 3) @ np.asarray(b, dtype=np.float64).reshape(3, 3)
+
+    @staticmethod
+    def rotation_about(cx, cy, rad):
+        """above -> below matrix of a rotation about (cx, cy): Affine::{shift, rotate, shift}, each a left multiplication."""
+        from zosimos_b200.command import Affine, AffineSample
+        a = Affine.new(AffineSample.Nearest).shift(-cx, -cy).rotate(rad).shift(cx, cy)
+        return np.asarray(a.transformation, dtype=np.float32).reshape(3, 3)
+
+
 def make_gpu_workload(name, ctx, frames, seed):
     """Returns (workload, launch(), e2e_step() or None).  Inputs are generated on the host with the
     seeds of SURVEY.md 8(d) and uploaded before timing."""
     Z, d, Color, Texel, SampleParts, Transfer = _descs()
-    from oracle import oracle as O  # only for host-side parameter preparation of some workloads (matrices)
     from zosimos_b200 import _ffi, ops
+    O = HostParams()  # parameter blocks come from the product's own host layer; the oracle is not touched by this arm
     rng = np.random.default_rng(seed)
     rgba8 = Texel.new_u8(SampleParts.RgbA)
     lin = Color.Rgb(Z.Primaries.Bt709, Transfer.Linear)
@@ -170,7 +197,7 @@ def make_gpu_workload(name, ctx, frames, seed):
         tile = np.tile(v.astype(np.float16), (1, H // 270, 1)).view(np.uint8)
         _replicate(ctx, below, tile); _replicate(ctx, above, tile[:, ::-1].copy())
         ang = np.deg2rad(C3_ANGLE_DEG)
-        m = (O.shift(W / 2, H / 2) @ O.rotate(ang) @ O.shift(-W / 2, -H / 2)).astype(np.float32)
+        m = O.rotation_about(W / 2, H / 2, float(ang))
         inv = O.inv3(m.astype(np.float64)).astype(np.float32)
         p = ops.compose_params(map=_ffi.MAP_AFFINE, sampling=_ffi.SAMPLE_BILINEAR if name.endswith("bilinear") else _ffi.SAMPLE_NEAREST,
                                inv=inv, use_tma=True)

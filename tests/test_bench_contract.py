@@ -41,3 +41,24 @@ def test_reference_arm_under_torchrun():
     lines = json_lines(out.stdout)
     assert len(lines) == 1  # rank 0 only
     check(lines[0], 2)
+
+
+def test_gpu_arm_parameters_come_from_the_product_host_layer():
+    """The GPU arm must not execute anything under oracle/: its matrices come from libzosimos_cuda.so's host layer
+    (bench.HostParams) and agree with the oracle's to f32 rounding; only the cpu_baseline / reference legs import the oracle."""
+    import inspect
+
+    import numpy as np
+
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import oracle as O
+    assert "oracle" not in inspect.getsource(bench.make_gpu_workload).replace("the oracle is not touched", "")
+    assert "oracle" not in inspect.getsource(bench.HostParams).replace("under oracle/", "")
+    H = bench.HostParams
+    a = O.mul3(O.inv3(O.to_xyz("bt709", "D65")), O.to_xyz("bt2020", "D65"))
+    b = H.mul3(H.inv3(H.to_xyz("bt709", "D65")), H.to_xyz("bt2020", "D65"))
+    assert np.abs(a - b).max() < 1e-6
+    W, Hh, ang = 7680, 4320, float(np.deg2rad(30.0))
+    m = (O.shift(W / 2, Hh / 2) @ O.rotate(ang) @ O.shift(-W / 2, -Hh / 2))
+    assert np.abs(m - H.rotation_about(W / 2, Hh / 2, ang)).max() < 1e-3  # f32 left multiplications vs one f64 product
