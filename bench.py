@@ -515,7 +515,8 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl.name, "what": wl.desc, "frames_per_step_per_gpu": wl.frames,
-                       "out_px_per_frame": wl.out_px, "l2": "each step touches %.0f MB once (> 126 MB L2)" % (wl.bytes_per_frame * wl.frames / 1e6),
+                       "out_px_per_frame": wl.out_px, "l2": "each step touches %.0f MB once (%s)" % (wl.bytes_per_frame * wl.frames / 1e6, "> 126 MB L2" if wl.bytes_per_frame * wl.frames > 126e6
+                                                                         else "NOT larger than the 126 MB L2: raise --frames for a valid number"),
                        "parallelism": "frame-batch sharding over %d GPU(s), no collective" % world},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": wl.bytes_per_frame * wl.frames,
