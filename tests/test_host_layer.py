@@ -561,3 +561,74 @@ def test_generic_function_calling_a_generic_function():
     flat.output(flat.resize(flat.inscribe(conv, Rectangle(0, 0, 16, 16), small), (8, 8), ResizeMode.Nearest))
     flat.output(conv)
     assert _same_ops(linked.ops(), linker.compile(flat).ops())
+
+
+def test_builder_fuzz_never_crashes():
+    """Random (mostly invalid) arguments through the raw C entry points: every call answers ZOSH_OK or one of the error
+    kinds, registers stay dense, and whatever was built still compiles."""
+    from hypothesis import given, settings, strategies as st
+    L = command.host_lib()
+    reg = st.integers(-3, 12)
+    u32 = st.one_of(st.integers(0, 24), st.sampled_from([0xFFFFFFFF, 0x80000000, 255, 256, 65535]))
+    dim = st.one_of(st.integers(0, 70), st.sampled_from([0xFFFFFFFF, 1 << 16, 1 << 30]))
+
+    def desc(draw):
+        d = _ffi.ZosDesc()
+        d.width, d.height = draw(dim), draw(dim)
+        d.block, d.bits, d.parts, d.color, d.transfer = draw(st.integers(0, 3)), draw(u32), draw(u32), draw(st.integers(0, 5)), draw(u32)
+        d.primaries, d.whitepoint, d.texel_stride = draw(st.integers(0, 7)), draw(st.integers(0, 12)), draw(st.integers(0, 17))
+        d.row_stride = draw(st.integers(0, 1 << 20))
+        return d
+
+    @settings(max_examples=150, deadline=None)
+    @given(data=st.data())
+    def prop(data):
+        draw = data.draw
+        cb = L.zosh_cb_new()
+        template = draw(st.booleans()) and draw(st.booleans())
+        out = C.c_int32(-1)
+        try:
+            if template:
+                assert L.zosh_cb_generic(cb, C.byref(out)) == 0
+                L.zosh_cb_input_generic(cb, draw(st.integers(-1, 2)), C.byref(out))
+            good = srgb(32, 24).to_ffi()
+            assert L.zosh_cb_input(cb, C.byref(good), C.byref(out)) == 0
+            for _ in range(draw(st.integers(1, 12))):
+                k = draw(st.integers(0, 15))
+                d = desc(draw) if draw(st.booleans()) else srgb(draw(st.integers(1, 40)), draw(st.integers(1, 40))).to_ffi()
+                rect = command.ZoshRect(draw(dim), draw(dim), draw(dim), draw(dim))
+                f24 = (C.c_float * 24)(*[draw(st.floats(-4, 4, width=32)) for _ in range(24)])
+                a, b = draw(reg), draw(reg)
+                st_ = [
+                    lambda: L.zosh_cb_input(cb, C.byref(d), C.byref(out)),
+                    lambda: L.zosh_cb_output(cb, a, C.byref(out)),
+                    lambda: L.zosh_cb_color_convert(cb, a, C.byref(d), C.byref(out)),
+                    lambda: L.zosh_cb_chromatic_adaptation(cb, a, draw(u32), draw(u32), C.byref(out)),
+                    lambda: L.zosh_cb_inscribe(cb, a, rect, b, C.byref(out)),
+                    lambda: L.zosh_cb_blend(cb, a, rect, b, draw(st.integers(-3, 14)), C.byref(out)),
+                    lambda: L.zosh_cb_crop(cb, a, rect, C.byref(out)),
+                    lambda: L.zosh_cb_affine(cb, a, f24, draw(u32), b, C.byref(out)),
+                    lambda: L.zosh_cb_resize(cb, a, draw(dim), draw(dim), draw(u32), C.byref(out)),
+                    lambda: L.zosh_cb_transmute(cb, a, C.byref(d), C.byref(out)),
+                    lambda: L.zosh_cb_bilinear(cb, C.byref(d), f24, C.byref(out)),
+                    lambda: L.zosh_cb_derivative(cb, a, draw(u32), draw(u32), C.byref(out)),
+                    lambda: L.zosh_cb_palette(cb, a, b, f24, f24, C.byref(out)),
+                    lambda: L.zosh_cb_extract(cb, a, draw(u32), C.byref(out)),
+                    lambda: L.zosh_cb_inject(cb, a, draw(u32), b, C.byref(out)),
+                    lambda: L.zosh_cb_from_buffer(cb, a, C.byref(d), C.byref(out)),
+                ][k]()
+                assert 0 <= st_ <= 6
+                got = _ffi.ZosDesc()
+                L.zosh_cb_describe(cb, draw(reg), C.byref(got))
+            prog = command._P()
+            st_ = L.zosh_compile(cb, C.byref(prog))
+            assert st_ == (5 if template else 0)
+            if st_ == 0:
+                n = L.zosh_program_num_ops(prog)
+                ops = L.zosh_program_ops(prog)
+                for i in range(n):
+                    assert all(s < ops[i].reg or s == -1 for s in ops[i].src)  # operands precede their users
+                L.zosh_program_free(prog)
+        finally:
+            L.zosh_cb_free(cb)
+    prop()
