@@ -632,3 +632,26 @@ def test_builder_fuzz_never_crashes():
         finally:
             L.zosh_cb_free(cb)
     prop()
+
+
+def test_descriptor_helpers_fuzz():
+    """zos_desc_texfmt / zos_desc_device_bytes / zos_aligned_row_stride are host code: random descriptors either get a
+    texture format or ZOS_ERR_UNSUPPORTED / INVALID, never a crash; strides are 256-aligned and cover the row."""
+    from hypothesis import given, settings, strategies as st
+    L = _ffi.lib()
+
+    @settings(max_examples=300, deadline=None)
+    @given(w=st.integers(0, 1 << 20), h=st.integers(0, 1 << 16), block=st.integers(0, 4), bits=st.integers(0, 40), parts=st.integers(0, 40),
+           color=st.integers(0, 6), transfer=st.one_of(st.integers(0, 14), st.just(0x100)), ts=st.integers(0, 20))
+    def prop(w, h, block, bits, parts, color, transfer, ts):
+        d = _ffi.ZosDesc()
+        d.width, d.height, d.block, d.bits, d.parts, d.color, d.transfer, d.texel_stride = w, h, block, bits, parts, color, transfer, ts
+        f = _ffi.ZosTexFmt()
+        st_ = L.zos_desc_texfmt(C.byref(d), C.byref(f))
+        assert 0 <= st_ < len(_ffi.STATUS_NAMES)
+        L.zos_desc_device_bytes(C.byref(d))
+        nb = L.zos_bits_bytes(bits)
+        assert 0 <= nb <= 16
+        stride = L.zos_aligned_row_stride(w, ts)
+        assert stride % 256 == 0 and stride >= w * ts and stride < w * ts + 256
+    prop()
