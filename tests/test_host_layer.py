@@ -655,3 +655,31 @@ def test_descriptor_helpers_fuzz():
         stride = L.zos_aligned_row_stride(w, ts)
         assert stride % 256 == 0 and stride >= w * ts and stride < w * ts + 256
     prop()
+
+
+def test_every_entry_point_survives_null_arguments():
+    """INTEGRATION.md's contract: nothing aborts across the boundary.  Every exported function of both headers is called
+    with NULL / zero arguments in a child process (a crash there is a failure here); status-returning ones answer an error."""
+    import subprocess
+    import sys
+    code = '''
+import ctypes as C, sys
+sys.path.insert(0, %r)
+from zosimos_b200 import _ffi, command
+L = _ffi.lib(); command.host_lib()
+sigs = dict(_ffi.SIGNATURES); sigs.update(command._HOST_SIGNATURES)
+def zero(t):
+    if t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents"): return None
+    if issubclass(t, C.Structure): return t()
+    if t in (C.c_float, C.c_double): return 0.0
+    return 0
+for name in sorted(sigs):
+    res, args = sigs[name]
+    print(name, flush=True)
+    r = getattr(L, name)(*[zero(a) for a in args])
+    if res is C.c_int32 and any(a is C.c_void_p or hasattr(a, "contents") for a in args) and name not in ("zos_ctx_device", "zosh_cb_with_knob", "zos_srgb_encoder_tables"):
+        assert r != 0, name
+print("ALL-OK")
+''' % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ALL-OK"), (out.stdout[-300:], out.stderr[-1500:])

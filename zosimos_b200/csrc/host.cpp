@@ -216,30 +216,34 @@ const char* zosh_last_error(void) { return g_err.c_str(); }
 
 int32_t zosh_to_xyz_matrix(uint32_t primaries, uint32_t whitepoint, float out[9]) {
   double m[9];
+  if (!out) return err(ZOSH_ERR_OTHER, "null argument");
   if (!to_xyz_d(primaries, whitepoint, m)) return err(ZOSH_ERR_OTHER, "unknown primaries / whitepoint");
   to_f32(m, out);
   return ZOSH_OK;
 }
 int32_t zosh_adaptation_matrix(uint32_t method, uint32_t s, uint32_t d, float out[9]) {
   double m[9];
+  if (!out) return err(ZOSH_ERR_OTHER, "null argument");
   if (method == ZOSH_ADAPT_BRADFORD_NONLINEAR) return err(ZOSH_ERR_UNIMPLEMENTED, "BradfordNonLinear (command.rs:3327-3331)");
   if (!adaptation_d(method, s, d, m)) return err(ZOSH_ERR_OTHER, "unknown adaptation method / whitepoint");
   to_f32(m, out);
   return ZOSH_OK;
 }
 int32_t zosh_whitepoint_xyz(uint32_t wp, float out[3]) {
+  if (!out) return err(ZOSH_ERR_OTHER, "null argument");
   if (wp > 10) return err(ZOSH_ERR_OTHER, "unknown whitepoint");
   for (int i = 0; i < 3; i++) out[i] = (float)WP[wp][i];
   return ZOSH_OK;
 }
-void zosh_affine_identity(float m[9]) { const float id[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}; memcpy(m, id, sizeof id); }
-void zosh_affine_scale(float m[9], float x, float y) { const float p[9] = {x, 0, 0, 0, y, 0, 0, 0, 1}; mul3_f32(p, m, m); }
+void zosh_affine_identity(float m[9]) { if (!m) return; const float id[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}; memcpy(m, id, sizeof id); }
+void zosh_affine_scale(float m[9], float x, float y) { if (!m) return; const float p[9] = {x, 0, 0, 0, y, 0, 0, 0, 1}; mul3_f32(p, m, m); }
 void zosh_affine_rotate(float m[9], float rad) {
+  if (!m) return;
   const float c = cosf(rad), s = sinf(rad);
   const float p[9] = {c, s, 0, -s, c, 0, 0, 0, 1};
   mul3_f32(p, m, m);
 }
-void zosh_affine_shift(float m[9], float x, float y) { const float p[9] = {1, 0, x, 0, 1, y, 0, 0, 1}; mul3_f32(p, m, m); }
+void zosh_affine_shift(float m[9], float x, float y) { if (!m) return; const float p[9] = {1, 0, x, 0, 1, y, 0, 0, 1}; mul3_f32(p, m, m); }
 zosh_rect zosh_rect_normalize(zosh_rect r) {
   uint32_t w = r.max_x > r.x ? r.max_x - r.x : 0;
   return zosh_rect{r.x, r.y, r.x + w, r.y + w};  // sic: max_y = y + width(), command.rs:3536-3543
@@ -481,6 +485,7 @@ int32_t zosh_cb_solid_rgba(zosh_cb* cb, const zos_desc* desc, const float color[
 
 // shaders/distribution_normal2d.rs:25-100 and shaders/fractal_noise.rs:21-49: the parameter constructors, in f32 like the reference
 void zosh_normal2d_with_diagonal(float var0, float var1, float out[7]) {
+  if (!out) return;
   const float pi = 3.14159265358979323846f;
   const float d0 = var0 == 0.0f ? 0.0f : 1.0f / var0, d1 = var1 == 0.0f ? 0.0f : 1.0f / var1;
   const float f0 = var0 == 0.0f ? 1.0f : 2.0f * pi * var0, f1 = var1 == 0.0f ? 1.0f : 2.0f * pi * var1;
@@ -489,6 +494,7 @@ void zosh_normal2d_with_diagonal(float var0, float var1, float out[7]) {
   out[6] = f0 * f1;
 }
 void zosh_normal2d_with_direction(float x, float y, float out[7]) {
+  if (!out) return;
   auto sym = [](float a, float b) { float h = hypotf(a, b); float up = (1.0f / h) * (a / h); float low = a + b * (b / a); return up / low; };
   auto asym = [](float a, float b) { float lo = fminf(a, b), hi = fmaxf(a, b); float h = hypotf(lo, hi); float inner = fmaf(lo, lo / hi, hi); return ((lo / h) / inner) / h; };
   out[0] = out[1] = 0.0f;
@@ -496,12 +502,14 @@ void zosh_normal2d_with_direction(float x, float y, float out[7]) {
   out[6] = (float)((double)x * (double)x + (double)y * (double)y);
 }
 void zosh_fractal_noise_with_octaves(uint32_t octaves, float out[5]) {
+  if (!out) return;
   out[0] = out[1] = 100.0f;
   out[2] = (float)(1.0 / (double)octaves);
   out[3] = 1.0f;
   out[4] = (float)octaves;
 }
 void zosh_fractal_noise_set_damping(float params[5], float damping) {
+  if (!params) return;
   const float n = params[4];
   const float total = 1.0f - powf(damping, n);
   params[2] = fabsf(total) < 1e-7f ? 1.0f : (1.0f - damping) / total;
