@@ -683,3 +683,28 @@ print("ALL-OK")
 ''' % ROOT
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and out.stdout.strip().endswith("ALL-OK"), (out.stdout[-300:], out.stderr[-1500:])
+
+
+def test_colour_science_known_answers():
+    """The third-party arithmetic of the path (image-canvas `to_xyz_row_matrix`, palette `TransformMatrix`) is
+    not vendored in the reference, so it is pinned to the published tables both crates follow: Lindbloom's sRGB -> XYZ (D65)
+    matrix and his Bradford / von Kries D65 -> D50 adaptation matrices (ASTM E308 whitepoints), and BT.2020's NPM
+    (ITU-R BT.2020-2 / SMPTE RP 177, whose D65 is the chromaticity (0.3127, 0.3290): 3e-4 from the ASTM XYZ triple)."""
+    from zosimos_b200.buffer import Primaries, Whitepoint
+    srgb_d65 = [[0.4124564, 0.3575761, 0.1804375], [0.2126729, 0.7151522, 0.0721750], [0.0193339, 0.1191920, 0.9503041]]
+    assert np.abs(command.to_xyz_matrix(Primaries.Bt709, Whitepoint.D65) - srgb_d65).max() < 2e-7
+    bt2020 = [[0.6369580, 0.1446169, 0.1688810], [0.2627002, 0.6779981, 0.0593017], [0.0, 0.0280727, 1.0609851]]
+    assert np.abs(command.to_xyz_matrix(Primaries.Bt2020, Whitepoint.D65) - bt2020).max() < 3e-4
+    bradford = [[1.0478112, 0.0228866, -0.0501270], [0.0295424, 0.9904844, -0.0170491], [-0.0092345, 0.0150436, 0.7521316]]
+    got = command.adaptation_matrix(ChromaticAdaptationMethod.BradfordVonKries, Whitepoint.D65, Whitepoint.D50)
+    assert np.abs(got - bradford).max() < 2e-7
+    von_kries = [[1.0160803, 0.0552297, -0.0521326], [0.0060666, 0.9955661, -0.0012235], [0.0, 0.0, 0.7578869]]
+    got = command.adaptation_matrix(ChromaticAdaptationMethod.VonKries, Whitepoint.D65, Whitepoint.D50)
+    assert np.abs(got - von_kries).max() < 2e-7
+    # white is a fixed point: primaries -> XYZ of (1, 1, 1) is the whitepoint, and adaptation maps whitepoint to whitepoint
+    for wp, xyz in ((Whitepoint.D65, (0.95047, 1.0, 1.08883)), (Whitepoint.D50, (0.96422, 1.0, 0.82521))):
+        for prim in (Primaries.Bt709, Primaries.Bt2020, Primaries.Bt601_625):
+            assert np.abs(command.to_xyz_matrix(prim, wp) @ np.ones(3, np.float32) - xyz).max() < 1e-6
+    for method in (ChromaticAdaptationMethod.BradfordVonKries, ChromaticAdaptationMethod.VonKries):
+        m = command.adaptation_matrix(method, Whitepoint.D65, Whitepoint.D50)
+        assert np.abs(m @ np.array([0.95047, 1.0, 1.08883], np.float32) - (0.96422, 1.0, 0.82521)).max() < 1e-6
