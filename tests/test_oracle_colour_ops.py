@@ -81,3 +81,13 @@ def test_srlab2_encode_decode():
     lab32 = np.concatenate([got[:, :3], tex[0, :, 3:]], 1)[None]
     back = O.srlab2_decode(lab32, Ti, wp)[0]
     assert close(back[:, :3], exp, ab=2e-5) and np.array_equal(back[:, 3], tex[0, :, 3])
+
+
+def test_oklab_published_vectors():
+    """Ottosson's table of example XYZ -> Oklab pairs ("A perceptual color space for image processing", 2020), given to three
+    decimals; with T = identity the operator takes XYZ directly."""
+    pairs = [((0.950, 1.000, 1.089), (1.000, 0.000, 0.000)), ((1.000, 0.000, 0.000), (0.450, 1.236, -0.019)),
+             ((0.000, 1.000, 0.000), (0.922, -0.671, 0.263)), ((0.000, 0.000, 1.000), (0.153, -1.415, -0.449))]
+    tex = np.array([[list(x) + [1.0] for x, _ in pairs]], np.float32)
+    got = O.oklab_encode(tex, np.eye(3))[0, :, :3]
+    assert np.abs(got - np.array([l for _, l in pairs])).max() < 1.5e-3
