@@ -201,3 +201,19 @@ def test_affine_nearest_is_the_inverse_map_of_pixel_centres(seed, angle, sx, sy,
     exp = np.where(inside[..., None], above[fy, fx], below)
     sure = ~near_edge
     assert np.array_equal(dst[sure], exp[sure])
+
+
+def test_yuv_bt709_colour_bars_known_answers():
+    """The 100 % colour bars in 8-bit limited-range BT.709 Y'CbCr (ITU-R BT.709-6 section 3 quantisation; the values every
+    test-pattern generator prints): a known-answer test for the planar YUV semantics, which have no reference implementation."""
+    bars = {  # R, G, B -> Y, Cb, Cr
+        (1, 1, 1): (235, 128, 128), (1, 1, 0): (219, 16, 138), (0, 1, 1): (188, 154, 16), (0, 1, 0): (173, 42, 26),
+        (1, 0, 1): (78, 214, 230), (1, 0, 0): (63, 102, 240), (0, 0, 1): (32, 240, 118), (0, 0, 0): (16, 128, 128)}
+    for rgb, (Y, Cb, Cr) in bars.items():
+        tex = np.zeros((4, 4, 4), np.float32)
+        tex[..., :3] = rgb
+        tex[..., 3] = 1
+        y, u, v = O.encode_yuv420(tex, 0.2126, 0.0722)
+        assert (y == Y).all() and (u == Cb).all() and (v == Cr).all(), (rgb, y[0, 0], u[0, 0], v[0, 0])
+        back = O.decode_yuv420(np.full((4, 4), Y, np.uint8), np.full((2, 2), Cb, np.uint8), np.full((2, 2), Cr, np.uint8), 4, 4, 0.2126, 0.0722)
+        assert np.abs(back[..., :3] - np.array(rgb, np.float32)).max() < 0.012 and (back[..., 3] == 1).all()  # half a code of 219, through the EOTF
