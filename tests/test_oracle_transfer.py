@@ -103,3 +103,27 @@ def test_lab_lch():  # stage.frag:407-418: C = |ab|, h = atan2(b, a) / 360 deg +
     assert np.all(np.minimum(dh, 1 - dh) <= 2e-6)
     back = O.decode(O.Image(desc, np.ascontiguousarray(lch).view(np.uint8).reshape(1, -1)))[0]
     assert np.all(np.abs(back.astype(np.float64) - lab) <= 2e-6)
+
+
+def test_native_srgb8_texture_path():
+    """Native Rgba8UnormSrgb (program.rs:794-838): the texture unit decodes sRGB8 exactly (the correctly rounded f32 of the
+    piecewise formula) and encodes with round-to-nearest; alpha is linear unorm8.  All 256 codes, and the rounding boundary
+    between neighbouring codes located to one f32 step."""
+    k = np.arange(256, dtype=np.uint8)
+    px = np.stack([k, k, k, k], -1).reshape(1, -1)
+    desc = O.srgb_rgba8(256, 1)
+    tex = O.decode(O.Image(desc, px))[0]
+    exp = eo_srgb(k.astype(np.float64) / 255.0)
+    assert np.array_equal(tex[:, 0], exp.astype(np.float32)) and np.array_equal(tex[:, 3], (k.astype(np.float64) / 255).astype(np.float32))
+    assert np.array_equal(O.encode(desc, tex[None]).data.reshape(-1, 4), px.reshape(-1, 4))  # round trip of every code
+    # the boundary between codes c and c + 1 is where oe_srgb(v) * 255 crosses c + 1/2
+    for c in (0, 1, 10, 11, 127, 200, 254):
+        lo, hi = eo_srgb(c / 255.0), eo_srgb((c + 1) / 255.0)
+        for _ in range(60):
+            mid = (lo + hi) / 2
+            lo, hi = (mid, hi) if oe_srgb(np.float64(mid)) * 255 < c + 0.5 else (lo, mid)
+        b = np.float32(lo)
+        below, above = np.nextafter(b, np.float32(-1), dtype=np.float32), np.nextafter(np.nextafter(b, np.float32(2), dtype=np.float32), np.float32(2), dtype=np.float32)
+        t = np.array([[[below, above, 0, 1]]], np.float32)
+        enc = O.encode(O.srgb_rgba8(1, 1), t).data[0]
+        assert (enc[0], enc[1]) == (c, c + 1), (c, enc[:2])
