@@ -115,9 +115,13 @@ int32_t zosh_cb_invoke(zosh_cb* cb, int32_t function, const zos_desc* generics, 
                        uint32_t num_arguments, int32_t* results, uint32_t results_cap, uint32_t* num_results); /* command.rs:2821-2869 */
 /* Linker::link (command.rs:2083-2185): program 0 is `main`, program k >= 1 is functions[k - 1]; the link tables of all programs
  * are concatenated in `links` (links_per_program[p] entries for program p), entry f of a table names the program that function
- * variable f calls.  Calls were inlined by zosh_cb_invoke, so linking verifies the wiring and compiles `main`. */
-int32_t zosh_link(const zosh_cb* main_cb, const zosh_cb* const* functions, uint32_t num_functions, const uint32_t* links,
-                  const uint32_t* links_per_program, zosh_program** out);
+ * variable f calls.  Calls were inlined by zosh_cb_invoke, so linking verifies the wiring and compiles `main`.
+ * `tys` binds the generics of a generic entry point (main itself a template; num_tys = its number of generics, else 0): the
+ * compiled stream is main's monomorphic copy, and zosh_program_register translates main's registers (inputs to bind, outputs
+ * to retire, knobs keep their ids) into the program's; for a non-generic main it is the identity.  -1 = no such register. */
+int32_t zosh_link(const zosh_cb* main_cb, const zos_desc* tys, uint32_t num_tys, const zosh_cb* const* functions, uint32_t num_functions,
+                  const uint32_t* links, const uint32_t* links_per_program, zosh_program** out);
+int32_t zosh_program_register(const zosh_program* p, int32_t reg);
 
 /* Linker::compile (command.rs:2069): liveness + emission of the High-like op list */
 int32_t zosh_compile(const zosh_cb* cb, zosh_program** out);

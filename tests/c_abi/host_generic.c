@@ -64,11 +64,11 @@ int main(void) {
     const zosh_cb* fns[1];
     const uint32_t good[1] = {1}, bad[1] = {2}, per[2] = {1, 0};
     fns[0] = callee;
-    CHECK(zosh_link(main_cb, fns, 1, bad, per, &linked) == ZOSH_ERR_OTHER);
+    CHECK(zosh_link(main_cb, NULL, 0, fns, 1, bad, per, &linked) == ZOSH_ERR_OTHER);
     fns[0] = direct;
-    CHECK(zosh_link(main_cb, fns, 1, good, per, &linked) == ZOSH_ERR_TYPE); /* not the invoked function */
+    CHECK(zosh_link(main_cb, NULL, 0, fns, 1, good, per, &linked) == ZOSH_ERR_TYPE); /* not the invoked function */
     fns[0] = callee;
-    CHECK(zosh_link(main_cb, fns, 1, good, per, &linked) == ZOSH_OK);
+    CHECK(zosh_link(main_cb, NULL, 0, fns, 1, good, per, &linked) == ZOSH_OK);
   }
 
   /* the same pipeline without the function */

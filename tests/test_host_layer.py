@@ -708,3 +708,53 @@ def test_colour_science_known_answers():
     for method in (ChromaticAdaptationMethod.BradfordVonKries, ChromaticAdaptationMethod.VonKries):
         m = command.adaptation_matrix(method, Whitepoint.D65, Whitepoint.D50)
         assert np.abs(m @ np.array([0.95047, 1.0, 1.08883], np.float32) - (0.96422, 1.0, 0.82521)).max() < 1e-6
+
+
+def test_generic_entry_point():
+    """Linker::link with `tys` (command.rs:2083-2185): a generic `main` is compiled as its monomorphic copy under the bound
+    types; its registers are translated for binding inputs and retiring outputs."""
+    from zosimos_b200.command import InvocationArguments
+    from zosimos_b200.program import Environment, Executable, Pool, StartError
+    rgba8 = Texel.new_u8(SampleParts.RgbA)
+
+    helper = CommandBuffer()                     # helper<T>(x: T) -> BT.709 transfer
+    hv = helper.generic()
+    helper.output(helper.color_convert(helper.input_generic(hv), Color.BT709_RGB, rgba8))
+    helper_sig = helper.computed_signature()
+
+    main = CommandBuffer()                       # main<T>(image: T, small: srgb 16x16): calls helper<T>, then inscribes
+    t = main.generic()
+    f = main.function(helper_sig)
+    image, small = main.input_generic(t), main.input(srgb(16, 16))
+    (conv,) = main.invoke(f, InvocationArguments(generics=[t], arguments=[image]))
+    placed = main.inscribe(conv, Rectangle(0, 0, 16, 16), main.color_convert(small, Color.BT709_RGB, rgba8))
+    out, _ = main.output(placed)
+
+    linker = Linker.from_included()
+    with pytest.raises(CommandError) as e:       # one type per generic
+        linker.link(main, [], [helper], [[1], []])
+    assert e.value.is_type_err()
+    with pytest.raises(CommandError):            # 16x16 does not fit: the entry point does not type check under this type
+        linker.link(main, [srgb(8, 8)], [helper], [[1], []])
+    prog = linker.link(main, [srgb(40, 30)], [helper], [[1], []])
+
+    flat = CommandBuffer()
+    i2, s2 = flat.input(srgb(40, 30)), flat.input(srgb(16, 16))
+    c2 = flat.color_convert(i2, Color.BT709_RGB, rgba8)
+    o2, _ = flat.output(flat.inscribe(c2, Rectangle(0, 0, 16, 16), flat.color_convert(s2, Color.BT709_RGB, rgba8)))
+    plain = linker.compile(flat)
+    assert _same_ops(prog.ops(), plain.ops())
+    assert [prog.register_index(r.index) for r in (image, small, out)] == [i2.index, s2.index, o2.index]
+    assert prog.register_index(99) == -1 and [plain.register_index(r.index) for r in (i2, s2, o2)] == [i2.index, s2.index, o2.index]
+
+    # binding goes through the translation (host-side part of Environment, no device involved)
+    pool = Pool()
+    big = pool.insert(srgb(40, 30), np.zeros(40 * 30 * 4, np.uint8))
+    little = pool.insert(srgb(16, 16), np.zeros(16 * 16 * 4, np.uint8))
+    env = Environment(Executable(prog, None), pool, None)
+    env.bind(image, big.key()); env.bind(small, little.key())
+    assert sorted(env.inputs) == [i2.index, s2.index]
+    with pytest.raises(StartError):
+        env.bind(small, big.key())               # MismatchedDescriptor
+    with pytest.raises(StartError):
+        env.bind(out, big.key())                 # not an input

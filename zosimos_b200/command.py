@@ -98,7 +98,9 @@ _HOST_SIGNATURES = {
     "zosh_cb_num_functions": (C.c_uint32, [_P]),
     "zosh_cb_invoke": (C.c_int32, [_P, C.c_int32, C.POINTER(_ffi.ZosDesc), C.c_uint32, C.POINTER(C.c_int32), C.c_uint32, C.POINTER(C.c_int32),
                                    C.c_uint32, C.POINTER(C.c_uint32)]),
-    "zosh_link": (C.c_int32, [_P, C.POINTER(_P), C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(_P)]),
+    "zosh_link": (C.c_int32, [_P, C.POINTER(_ffi.ZosDesc), C.c_uint32, C.POINTER(_P), C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                              C.POINTER(_P)]),
+    "zosh_program_register": (C.c_int32, [_P, C.c_int32]),
     "zosh_compile": (C.c_int32, [_P, C.POINTER(_P)]),
     "zosh_program_free": (None, [_P]),
     "zosh_program_num_ops": (C.c_uint32, [_P]),
@@ -627,9 +629,8 @@ class Linker:
     def link(self, main: "CommandBuffer", tys: Sequence[Descriptor], functions: Sequence["CommandBuffer"], links: Sequence[Sequence[int]]) -> "Program":
         """command.rs:2083-2185: program 0 is `main`, program k >= 1 is functions[k - 1]; links[p][f] names the
         program that function variable f of program p calls.  Calls were monomorphised by `invoke`, so linking
-        verifies the wiring and compiles `main`."""
-        if tys:
-            raise CommandError(5, "generic entry points are not supported (CommandError::UNIMPLEMENTED)")
+        verifies the wiring and compiles `main`; `tys` binds the generics of a generic `main` (its registers are
+        translated by `Program.register_index`)."""
         if len(links) != 1 + len(functions):
             raise CommandError(4, "link: one link table per program")
         from .program import Program
@@ -638,7 +639,8 @@ class Linker:
         tab = (C.c_uint32 * max(len(flat), 1))(*flat)
         per = (C.c_uint32 * len(links))(*[len(t) for t in links])
         h = _P()
-        _check(host_lib().zosh_link(main._h, fns, len(functions), tab, per, C.byref(h)))
+        bound = (_ffi.ZosDesc * max(len(tys), 1))(*[d.to_ffi() for d in tys])  # types of a generic entry point's generics
+        _check(host_lib().zosh_link(main._h, bound, len(tys), fns, len(functions), tab, per, C.byref(h)))
         return Program(h, dict(main._knobs))
 
     def compile(self, commands: CommandBuffer) -> "Program":

@@ -155,6 +155,7 @@ struct zosh_cb {
 struct zosh_program {
   std::vector<zos_op> ops;
   std::vector<std::shared_ptr<std::vector<uint8_t>>> blobs;
+  std::vector<int32_t> regmap;  // generic entry point: register of the template `main` -> register of its monomorphic copy
 };
 
 namespace {
@@ -798,7 +799,11 @@ static int32_t replay(zosh_cb* cb, const Call& c, int32_t r0, int32_t r1, int32_
 
 // Inline `sig` into the (non-template) command buffer `cb`.  Type errors of the callee under the bound types surface here.
 static int32_t inline_signature(zosh_cb* cb, const zosh_signature& sig, const zos_desc* generics, uint32_t num_generics,
-                                const int32_t* arguments, uint32_t num_arguments, std::vector<int32_t>& results, int depth) {
+                                const int32_t* arguments, uint32_t num_arguments, std::vector<int32_t>& results, int depth,
+                                std::vector<int32_t>* entry_map = nullptr) {
+  // entry_map != nullptr: `sig` is a generic ENTRY POINT -- its inputs and outputs become Input / Output operations of cb
+  // (instead of the caller's registers), and the map from its registers to cb's is handed back.
+  if (entry_map) num_arguments = sig.num_inputs;
   if (depth > 32) return err(ZOSH_ERR_OTHER, "invoke: functions nest deeper than 32 calls (recursion?)");
   if (num_generics != sig.num_generics || num_arguments != sig.num_inputs)
     return err(ZOSH_ERR_TYPE, "invoke: number of generics / arguments differs from the signature (CommandError::INVALID_CALL)");
@@ -806,7 +811,7 @@ static int32_t inline_signature(zosh_cb* cb, const zosh_signature& sig, const zo
   // arguments are type checked before anything is pushed
   uint32_t nxt = 0;
   for (const Call& c : rec) {
-    if (c.fn != FN_INPUT && c.fn != FN_INPUT_GENERIC) continue;
+    if (entry_map || (c.fn != FN_INPUT && c.fn != FN_INPUT_GENERIC)) continue;
     const int32_t real = arguments[nxt++];
     if (!valid_reg(cb, real)) return err(ZOSH_ERR_OTHER, "invoke: bad argument register");
     zos_desc want = c.fn == FN_INPUT_GENERIC ? generics[c.i] : c.d;
@@ -819,9 +824,22 @@ static int32_t inline_signature(zosh_cb* cb, const zosh_signature& sig, const zo
   nxt = 0;
   for (size_t pos = 0; pos < rec.size(); pos++) {
     const Call& c = rec[pos];
-    if (c.fn == FN_INPUT || c.fn == FN_INPUT_GENERIC) { map[pos] = arguments[nxt++]; continue; }
+    if (c.fn == FN_INPUT || c.fn == FN_INPUT_GENERIC) {
+      if (!entry_map) { map[pos] = arguments[nxt++]; continue; }
+      if (c.knob) zosh_cb_with_knob(cb);
+      const int32_t st = zosh_cb_input(cb, c.fn == FN_INPUT_GENERIC ? &generics[c.i] : &c.d, &map[pos]);
+      if (st != ZOSH_OK) return st;
+      continue;
+    }
     const int32_t r0 = c.r[0] >= 0 ? map[c.r[0]] : -1, r1 = c.r[1] >= 0 ? map[c.r[1]] : -1;
-    if (c.fn == FN_OUTPUT) { results.push_back(r0); continue; }
+    if (c.fn == FN_OUTPUT) {
+      results.push_back(r0);
+      if (entry_map) {
+        const int32_t st = zosh_cb_output(cb, r0, &map[pos]);
+        if (st != ZOSH_OK) return st;
+      }
+      continue;
+    }
     if (c.fn == FN_INVOKED_RESULT) { map[pos] = nested[c.r[0]][c.u[0]]; continue; }
     if (c.fn == FN_INVOKE) {
       if (c.i < 0 || (size_t)c.i >= sig.functions->size()) return err(ZOSH_ERR_OTHER, "invoke: unknown function");
@@ -838,6 +856,7 @@ static int32_t inline_signature(zosh_cb* cb, const zosh_signature& sig, const zo
     const int32_t st = replay(cb, c, r0, r1, &map[pos]);
     if (st != ZOSH_OK) return st;
   }
+  if (entry_map) *entry_map = map;
   return ZOSH_OK;
 }
 
@@ -890,10 +909,11 @@ int32_t zosh_cb_invoke(zosh_cb* cb, int32_t function, const zos_desc* generics, 
   return ZOSH_OK;
 }
 
-int32_t zosh_link(const zosh_cb* main_cb, const zosh_cb* const* functions, uint32_t num_functions, const uint32_t* links,
-                  const uint32_t* links_per_program, zosh_program** out) {
-  if (!main_cb || !out || (num_functions && !functions) || !links_per_program) return err(ZOSH_ERR_OTHER, "null argument");
-  if (main_cb->is_template) return err(ZOSH_ERR_UNIMPLEMENTED, "generic entry points are not supported (CommandError::UNIMPLEMENTED)");
+int32_t zosh_link(const zosh_cb* main_cb, const zos_desc* tys, uint32_t num_tys, const zosh_cb* const* functions, uint32_t num_functions,
+                  const uint32_t* links, const uint32_t* links_per_program, zosh_program** out) {
+  if (!main_cb || !out || (num_functions && !functions) || !links_per_program || (num_tys && !tys)) return err(ZOSH_ERR_OTHER, "null argument");
+  if (num_tys != main_cb->num_generics)
+    return err(ZOSH_ERR_TYPE, "link: one type per generic of the entry point (CommandError::TYPE_ERR)");
   const uint32_t* table = links;
   for (uint32_t p = 0; p <= num_functions; p++) {
     const zosh_cb* prog = p == 0 ? main_cb : functions[p - 1];
@@ -907,7 +927,24 @@ int32_t zosh_link(const zosh_cb* main_cb, const zosh_cb* const* functions, uint3
     }
     table += links_per_program[p];
   }
-  return zosh_compile(main_cb, out);
+  if (!main_cb->is_template) return zosh_compile(main_cb, out);
+  // generic entry point: build the monomorphic copy of `main` under `tys`, compile that, remember how registers map
+  zosh_signature* sig = nullptr;
+  int32_t st = zosh_cb_computed_signature(main_cb, &sig);
+  if (st != ZOSH_OK) return st;
+  zosh_cb mono;
+  std::vector<int32_t> results, map;
+  st = inline_signature(&mono, *sig, tys, num_tys, nullptr, 0, results, 0, &map);
+  delete sig;
+  if (st != ZOSH_OK) return st;
+  st = zosh_compile(&mono, out);
+  if (st == ZOSH_OK) (*out)->regmap = map;
+  return st;
+}
+int32_t zosh_program_register(const zosh_program* p, int32_t reg) {
+  if (!p || reg < 0) return -1;
+  if (p->regmap.empty()) return reg;
+  return (size_t)reg < p->regmap.size() ? p->regmap[reg] : -1;
 }
 
 int32_t zosh_compile(const zosh_cb* cb, zosh_program** out) {

@@ -160,6 +160,11 @@ class Program:
         # (the data / source pointers inside still belong to the program -- keep it alive while they are used)
         return [_ffi.ZosOp.from_buffer_copy(p[i]) for i in range(n)]
 
+    def register_index(self, index: int) -> int:
+        """Register of the command buffer that was linked -> register of this program: the identity except for a generic
+        entry point, whose program is its monomorphic copy (zosh_program_register)."""
+        return int(host_lib().zosh_program_register(self._h, int(index)))
+
     def lower_to(self, capabilities: Capabilities) -> "Executable":
         return Executable(self, capabilities)
 
@@ -194,7 +199,8 @@ class Environment:
         self.knobs: Dict[int, bytes] = {}
 
     def bind(self, reg: Register, key: PoolKey):
-        op = next((o for o in self.exe._ops if o.kind == _ffi.OP_INPUT and o.dst == reg.index), None)
+        idx = self.exe.program.register_index(reg.index)
+        op = next((o for o in self.exe._ops if o.kind == _ffi.OP_INPUT and o.dst == idx), None)
         if op is None:
             raise StartError("register %d is not an input (StartError::MissingKey)" % reg.index)
         img = self.pool.entry(key)
@@ -204,7 +210,7 @@ class Environment:
         have = img.descriptor()
         if (want.size(), want.texel, want.color) != (have.size(), have.texel, have.color):
             raise StartError("MismatchedDescriptor for register %d" % reg.index)  # run.rs:376-380
-        self.inputs[reg.index] = key
+        self.inputs[idx] = key
 
     def knob(self, knob: Knob, data: bytes):
         self.knobs[knob.index] = bytes(data)
@@ -312,7 +318,8 @@ class Retire:
 
     def output(self, reg: Register) -> PoolImage:
         ex = self.ex
-        op = next((o for o in ex.exe._ops if o.kind == _ffi.OP_OUTPUT and o.reg == reg.index), None)
+        idx = ex.exe.program.register_index(reg.index)
+        op = next((o for o in ex.exe._ops if o.kind == _ffi.OP_OUTPUT and o.reg == idx), None)
         if op is None:
             raise RetireError("register %d is not an output" % reg.index)
         im = _ffi.ZosImage()
