@@ -75,7 +75,7 @@ def band_source_rows(inv: Sequence[float], band: Tuple[int, int], dst_width: int
     for cx in (0.5, dst_width - 0.5):
         for cy in (y0 + 0.5, y1 - 0.5):
             ys.append(m[1, 0] * cx + m[1, 1] * cy + m[1, 2])
-    lo = max(int(math.floor(min(ys))) - margin, 0)
+    lo = min(max(int(math.floor(min(ys))) - margin, 0), src_height)  # a band that maps entirely below the source gets an empty window at its end
     hi = min(int(math.floor(max(ys))) + margin + 1, src_height)
     return (lo, max(hi, lo))
 
