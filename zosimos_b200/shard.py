@@ -66,7 +66,7 @@ def row_bands(height: int, world: int, align: int = 1) -> List[Tuple[int, int]]:
 def band_source_rows(inv: Sequence[float], band: Tuple[int, int], dst_width: int, src_height: int, margin: int = 2) -> Tuple[int, int]:
     """Source rows [sy0, sy1) an output band needs under the inverse affine map `inv` (row-major 3x3,
     destination pixel centre -> source coordinates): the map is linear, so the extremes are at the
-    band's corners; `margin` covers the bilinear footprint and rounding."""
+    band's corners; `margin` covers the bilinear footprint and rounding.  Never empty for a non-empty source."""
     y0, y1 = band
     if y1 <= y0:
         return (0, 0)
@@ -77,6 +77,9 @@ def band_source_rows(inv: Sequence[float], band: Tuple[int, int], dst_width: int
             ys.append(m[1, 0] * cx + m[1, 1] * cy + m[1, 2])
     lo = min(max(int(math.floor(min(ys))) - margin, 0), src_height)  # a band that maps entirely below the source gets an empty window at its end
     hi = min(int(math.floor(max(ys))) + margin + 1, src_height)
+    if hi <= lo and src_height > 0:  # the band does not touch the source: one (unread) row, so that callers never upload an empty image
+        lo = min(lo, src_height - 1)
+        hi = lo + 1
     return (lo, max(hi, lo))
 
 
