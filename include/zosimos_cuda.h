@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ZOS_ABI_VERSION 3
+#define ZOS_ABI_VERSION 4
 
 typedef int32_t zos_status;
 enum {
@@ -123,8 +123,24 @@ uint64_t zos_ctx_launch_count(const zos_ctx* ctx); /* kernels launched so far (b
 enum { ZOS_CTX_NO_FAST_PATHS = 1 };
 zos_status zos_ctx_set_flags(zos_ctx* ctx, uint32_t flags);
 
+/* Device memory comes from a per-context arena of size-class free lists: zos_buf_free parks the block instead of
+ * returning it to the driver and does NOT synchronise (work of a context is ordered on its one stream, so the next
+ * owner's kernels run after the previous owner's); zos_buf_alloc takes a parked block of the class when there is one.
+ * A relaunched program therefore allocates nothing after its first run -- the role of the pool cache behind
+ * Environment::recover_buffers / Retire::retire_buffers (lib/zosimos/src/run.rs:1312-1347, 2876-2942; pool.rs:93-99).
+ * A buffer that another context (stream) still uses must not be freed before that context was synchronised. */
 zos_status zos_buf_alloc(zos_ctx* ctx, uint64_t bytes, zos_buf** out);
 void zos_buf_free(zos_ctx* ctx, zos_buf* buf);
+typedef struct zos_arena_stats {
+  uint64_t device_allocs;   /* cudaMalloc calls made for buffers so far */
+  uint64_t reuses;          /* allocations served from a parked block */
+  uint64_t bytes_reserved;  /* device memory held by the arena (in use + parked) */
+  uint64_t bytes_in_use;
+  uint64_t bytes_parked;
+} zos_arena_stats;
+zos_status zos_ctx_arena_stats(const zos_ctx* ctx, zos_arena_stats* out);
+/* Pool::clear_cache (pool.rs:450-455): hand every parked block back to the driver (synchronises the context) */
+zos_status zos_ctx_arena_trim(zos_ctx* ctx);
 void* zos_buf_ptr(const zos_buf* buf);
 uint64_t zos_buf_size(const zos_buf* buf);
 /* pinned host staging memory (the map_write / map_read buffers of encoder.rs:574-616) */
@@ -316,6 +332,22 @@ enum { ZOS_RUN_EAGER = 0, ZOS_RUN_GRAPH = 1 };
 zos_status zos_program_run(zos_program* prog, uint32_t flags);
 uint64_t zos_program_graph_launches(const zos_program* prog);
 uint32_t zos_program_kernel_count(const zos_program* prog);
+/* Resource recovery between launches (Environment::recover_buffers, run.rs:1312-1347; Retire::retire_buffers, run.rs:2876-2942;
+ * tests/util.rs:95-118).  A program provides storage for every register that is neither a bound input nor a bound output.
+ * zos_program_release_buffers parks that storage in the context's arena (any program may take it from there);
+ * zos_program_recover_buffers takes it back -- bytes_reused came from parked blocks, bytes_allocated needed cudaMalloc --
+ * and zos_program_launch / zos_program_run do so implicitly.  Either pointer may be NULL. */
+typedef struct zos_program_stats {
+  uint32_t kernels;       /* launches per run of the fused schedule */
+  uint32_t temp_buffers;  /* registers the program provides storage for */
+  uint64_t temp_bytes;
+  uint32_t released;      /* 1 while that storage is parked in the arena */
+  uint32_t reserved;
+  uint64_t runs, graph_launches;
+} zos_program_stats;
+zos_status zos_program_release_buffers(zos_program* prog, uint64_t* bytes, uint32_t* count);
+zos_status zos_program_recover_buffers(zos_program* prog, uint64_t* bytes_reused, uint64_t* bytes_allocated);
+zos_status zos_program_resources(const zos_program* prog, zos_program_stats* out);
 /* fills descriptor + device location of a register the program allocated itself (outputs not bound) */
 zos_status zos_program_register_image(const zos_program* prog, int32_t reg, zos_image* out);
 

@@ -122,6 +122,11 @@ int32_t zosh_cb_invoke(zosh_cb* cb, int32_t function, const zos_desc* generics, 
 int32_t zosh_link(const zosh_cb* main_cb, const zos_desc* tys, uint32_t num_tys, const zosh_cb* const* functions, uint32_t num_functions,
                   const uint32_t* links, const uint32_t* links_per_program, zosh_program** out);
 int32_t zosh_program_register(const zosh_program* p, int32_t reg);
+/* Executable::query_knob for RegisterKnob{link_idx, register} (command.rs:701-705, 2134-2145): the Knob id the linker
+ * assigned (ids count in emission order, knobs inside invoked functions included), 0 = none.  link_idx 0 = main's own
+ * registers (the template's registers for a generic entry point), k >= 1 = registers of functions[k - 1]; where a
+ * function was instantiated several times the last instantiation answers, like the reference's map insert. */
+uint32_t zosh_program_knob(const zosh_program* p, uint32_t link_idx, int32_t reg);
 
 /* Linker::compile (command.rs:2069): liveness + emission of the High-like op list */
 int32_t zosh_compile(const zosh_cb* cb, zosh_program** out);

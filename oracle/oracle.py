@@ -482,7 +482,7 @@ def normal2d_with_direction(x: float, y: float):
         inner = f(np.float64(a) * np.float64(a / b) + np.float64(b))  # mul_add
         return ((a / h) / inner) / h
 
-    return [0.0, 0.0, float(sym(x, x)), float(asym(x, y)), float(asym(y, x)), float(sym(y, y)), float(length_sq)]
+    return [0.0, 0.0, float(sym(x, x)), float(asym(x, y)), float(asym(y, x)), float(sym(y, y)), float(f(f(f(2.0) * f(np.pi)) * length_sq))]  # 2.0 * PIf32 * length_sq (:96)
 
 
 def fractal_noise_with_octaves(n: int, damping: float = None):

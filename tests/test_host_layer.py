@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), n
     # and the ctypes table covers the device header completely
     assert set(declared("zosimos_cuda.h")) == set(_ffi.SIGNATURES)
-    assert lib.zos_abi_version() == 3
+    assert lib.zos_abi_version() == 4
 
 
 def test_no_cpu_fallback():
@@ -758,3 +758,81 @@ def test_generic_entry_point():
         env.bind(small, big.key())               # MismatchedDescriptor
     with pytest.raises(StartError):
         env.bind(out, big.key())                 # not an input
+
+
+def test_knobs_inside_invoked_functions_keep_their_register():
+    """RegisterKnob{link_idx, register} -> Knob (command.rs:701-705, 2134-2145).  Knob ids count in emission order, the
+    knobs inside invoked functions included, so a generic entry point's own knobs do NOT carry the numbers its template
+    handed out: `query_knob` has to answer with the id of the operation the register became."""
+    from zosimos_b200.command import InvocationArguments, RegisterKnob
+    from zosimos_b200.program import Executable
+    rgba8 = Texel.new_u8(SampleParts.RgbA)
+
+    helper = CommandBuffer()                     # helper<T>(x: T): a knob-able conversion
+    hv = helper.generic()
+    h_conv = helper.with_knob().color_convert(helper.input_generic(hv), Color.BT709_RGB, rgba8)
+    helper.output(h_conv)
+    helper_sig = helper.computed_signature()
+
+    main = CommandBuffer()                       # main<T>(image: T): helper<T>(image), then a knob-able adaptation
+    t = main.generic()
+    f = main.function(helper_sig)
+    image = main.input_generic(t)
+    (conv,) = main.invoke(f, InvocationArguments(generics=[t], arguments=[image]))
+    adapted = main.with_knob().chromatic_adaptation(conv, ChromaticAdaptationMethod.VonKries, Z.Whitepoint.D50)
+    out, _ = main.output(adapted)
+
+    prog = Linker.from_included().link(main, [srgb(40, 30)], [helper], [[1], []])
+    ops = prog.ops()
+    by_knob = {o.knob: o for o in ops if o.knob}
+    assert sorted(by_knob) == [1, 2]
+    exe = Executable(prog, None)
+    k_main = exe.query_knob(RegisterKnob(0, adapted))
+    k_helper = exe.query_knob(RegisterKnob(1, h_conv))
+    assert k_main is not None and k_helper is not None and k_main.index != k_helper.index
+    # the knob of main's op is the one on the op main's register translates to; same for the helper's
+    assert by_knob[k_main.index].reg == prog.register_index(adapted.index)
+    assert by_knob[k_helper.index].dst == ops[[o.reg for o in ops].index(prog.register_index(adapted.index))].src[0]
+    assert exe.query_knob(RegisterKnob(0, image)) is None and exe.query_knob(RegisterKnob(2, h_conv)) is None
+
+    # a non-generic main: its own registers under link 0, the callee's under its link index
+    flat = CommandBuffer()
+    g = flat.function(helper_sig)
+    i2 = flat.input(srgb(40, 30))
+    (c2,) = flat.invoke(g, InvocationArguments(generics=[srgb(40, 30)], arguments=[i2]))
+    a2 = flat.with_knob().chromatic_adaptation(c2, ChromaticAdaptationMethod.VonKries, Z.Whitepoint.D50)
+    flat.output(a2)
+    p2 = Linker.from_included().link(flat, [], [helper], [[1], []])
+    e2 = Executable(p2, None)
+    assert e2.query_knob(RegisterKnob(0, a2)).index == 2 and e2.query_knob(RegisterKnob(1, h_conv)).index == 1
+    assert {o.knob: o.reg for o in p2.ops() if o.knob} == {1: c2.index, 2: a2.index}
+
+
+def test_failed_builder_does_not_leave_a_pending_knob():
+    """with_knob() marks the NEXT operation (command.rs:1865-1874); when that operation is rejected the mark is gone on both
+    sides of the veneer instead of landing on an unrelated later call."""
+    rgba8 = Texel.new_u8(SampleParts.RgbA)
+    cb = CommandBuffer()
+    i = cb.input(srgb(20, 20))
+    with pytest.raises(CommandError):
+        cb.with_knob().chromatic_adaptation(i, ChromaticAdaptationMethod.BradfordNonLinear, Z.Whitepoint.D50)  # Unimplemented
+    conv = cb.color_convert(i, Color.BT709_RGB, rgba8)
+    cb.output(conv)
+    assert cb._knobs == {} and cb._pending_knob == 0
+    assert all(o.knob == 0 for o in Linker.from_included().compile(cb).ops())
+    with pytest.raises(CommandError):
+        cb.with_knob().inscribe(i, Rectangle(0, 0, 99, 99), conv)
+    later = cb.with_knob().solid_rgba(srgb(4, 4), [0, 0, 0, 1])
+    assert cb._knobs == {later.index: 3}  # ids keep counting: the two failed calls consumed 1 and 2 without attaching them anywhere
+
+
+def test_normal2d_constructors_match_the_reference_values():
+    """shaders/distribution_normal2d.rs:25-100: the host layer's parameter blocks equal the oracle's, and with_direction
+    carries 2 pi length^2 (0.031466 for the direction the reference tests use), not length^2 (0.005008)."""
+    from zosimos_b200.command import DistributionNormal2d
+    d = DistributionNormal2d.with_direction([0.04998, 0.0501])
+    assert np.allclose(d.params, O.normal2d_with_direction(0.04998, 0.0501), rtol=1e-6, atol=0)
+    assert abs(d.params[6] - 0.031466) < 1e-6
+    assert np.frombuffer(d.into_std430(), np.float32)[6] == np.float32(d.params[6])
+    g = DistributionNormal2d.with_diagonal(0.2, 0.2)
+    assert np.allclose(g.params, O.normal2d_with_diagonal(0.2, 0.2), rtol=1e-6, atol=0)

@@ -69,6 +69,16 @@ class ZosOp(C.Structure):
                 ("gen", C.c_float * 24), ("knob", C.c_uint32), ("reg", C.c_int32), ("data", C.c_void_p), ("data_len", C.c_uint64), ("source", C.c_char_p)]
 
 
+class ZosArenaStats(C.Structure):
+    _fields_ = [("device_allocs", C.c_uint64), ("reuses", C.c_uint64), ("bytes_reserved", C.c_uint64),
+                ("bytes_in_use", C.c_uint64), ("bytes_parked", C.c_uint64)]
+
+
+class ZosProgramStats(C.Structure):
+    _fields_ = [("kernels", C.c_uint32), ("temp_buffers", C.c_uint32), ("temp_bytes", C.c_uint64), ("released", C.c_uint32),
+                ("reserved", C.c_uint32), ("runs", C.c_uint64), ("graph_launches", C.c_uint64)]
+
+
 class ZosError(RuntimeError):
     def __init__(self, status: int, message: str):
         super().__init__("zosimos_cuda: %s: %s" % (STATUS_NAMES[status] if 0 <= status < len(STATUS_NAMES) else status, message))
@@ -125,6 +135,11 @@ SIGNATURES = {
     "zos_program_run": (C.c_int32, [_P, C.c_uint32]),
     "zos_program_graph_launches": (C.c_uint64, [_P]),
     "zos_program_register_image": (C.c_int32, [_P, C.c_int32, C.POINTER(ZosImage)]),
+    "zos_ctx_arena_stats": (C.c_int32, [_P, C.POINTER(ZosArenaStats)]),
+    "zos_ctx_arena_trim": (C.c_int32, [_P]),
+    "zos_program_release_buffers": (C.c_int32, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
+    "zos_program_recover_buffers": (C.c_int32, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "zos_program_resources": (C.c_int32, [_P, C.POINTER(ZosProgramStats)]),
 }
 
 _lib = None

@@ -101,6 +101,7 @@ _HOST_SIGNATURES = {
     "zosh_link": (C.c_int32, [_P, C.POINTER(_ffi.ZosDesc), C.c_uint32, C.POINTER(_P), C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                               C.POINTER(_P)]),
     "zosh_program_register": (C.c_int32, [_P, C.c_int32]),
+    "zosh_program_knob": (C.c_uint32, [_P, C.c_uint32, C.c_int32]),
     "zosh_compile": (C.c_int32, [_P, C.POINTER(_P)]),
     "zosh_program_free": (None, [_P]),
     "zosh_program_num_ops": (C.c_uint32, [_P]),
@@ -392,11 +393,11 @@ class CommandBuffer:
 
     # -- plumbing
     def _reg(self, st: int, out: C.c_int32) -> Register:
+        knob, self._pending_knob = self._pending_knob, 0  # a failed builder must not leave the mark for the next call (the host layer clears its side too)
         _check(st)
         r = Register(int(out.value))
-        if self._pending_knob:
-            self._knobs[r.index] = self._pending_knob
-            self._pending_knob = 0
+        if knob:
+            self._knobs[r.index] = knob
         return r
 
     _pending_knob = 0
@@ -406,10 +407,10 @@ class CommandBuffer:
         _check(host_lib().zosh_cb_describe(self._h, reg.index, C.byref(d)))
         return descriptor_from_ffi(d)
 
-    def with_knob(self) -> "CommandBuffer":
-        """command.rs:1865-1874: the next operation's parameter block can be overridden at run time."""
-        self._pending_knob = int(host_lib().zosh_cb_with_knob(self._h))
-        return self
+    def with_knob(self) -> "WithKnob":
+        """command.rs:1865-1874: the operation built through the returned wrapper gets a knob -- its parameter block can be
+        overridden at run time."""
+        return WithKnob(self)
 
     # -- operations
     def input(self, desc: Descriptor) -> Register:
@@ -547,6 +548,24 @@ class CommandBuffer:
         return self._reg(host_lib().zosh_cb_inject(self._h, below.index, self._CHANNEL[channel], above.index, C.byref(out)), out)
 
 
+class WithKnob:
+    """command.rs:1846-1874 `WithKnob<'lt>`: borrows the command buffer for ONE builder call.  The mark is set when that
+    call is made, after its arguments were evaluated, so `cb.with_knob().op(cb.other_op(..))` knobs `op` like in Rust."""
+
+    def __init__(self, cb: "CommandBuffer"):
+        self._cb = cb
+
+    def __getattr__(self, name):
+        fn = getattr(self._cb, name)
+        if name.startswith("_") or not callable(fn):
+            raise AttributeError(name)
+
+        def build(*args, **kwargs):
+            self._cb._pending_knob = int(host_lib().zosh_cb_with_knob(self._cb._h))
+            return fn(*args, **kwargs)
+        return build
+
+
 class ShaderData:  # command/dynamic.rs:40-58
     def __init__(self):
         self.content: Optional[bytes] = None
@@ -641,13 +660,13 @@ class Linker:
         h = _P()
         bound = (_ffi.ZosDesc * max(len(tys), 1))(*[d.to_ffi() for d in tys])  # types of a generic entry point's generics
         _check(host_lib().zosh_link(main._h, bound, len(tys), fns, len(functions), tab, per, C.byref(h)))
-        return Program(h, dict(main._knobs))
+        return Program(h)
 
     def compile(self, commands: CommandBuffer) -> "Program":
         from .program import Program
         h = _P()
         _check(host_lib().zosh_compile(commands._h, C.byref(h)))
-        return Program(h, dict(commands._knobs))
+        return Program(h)
 
 
 def to_xyz_matrix(primaries: Primaries, whitepoint: Whitepoint) -> np.ndarray:

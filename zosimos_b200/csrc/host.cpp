@@ -143,22 +143,38 @@ struct zosh_signature {  // command::CommandSignature of a template, with the ca
   const zosh_cb* origin = nullptr;  // identity of the template, checked by zosh_link
   std::shared_ptr<const std::vector<zosh_signature>> functions;  // the functions the template itself declared (nested calls)
 };
+struct KnobNote {  // a knob handed out while a function was inlined: which template, which of its registers, which id
+  const zosh_cb* origin;
+  int32_t pos;
+  uint32_t knob;
+};
 struct zosh_cb {
   std::vector<zos_op> ops;  // op i defines register i (outputs define a register too, like the reference)
   uint32_t next_knob = 0, pending_knob = 0;
+  std::vector<KnobNote> knob_notes;  // knobs of inlined calls, addressed as RegisterKnob{link_idx, register} after linking (command.rs:2134-2145)
   std::vector<std::shared_ptr<std::vector<uint8_t>>> blobs;  // initial bytes of buffer registers (zos_op::data points into them)
   bool is_template = false;
   uint32_t num_generics = 0;
   std::vector<Call> record;               // template only
   std::vector<zosh_signature> functions;  // FunctionVar i = functions[i] (command.rs:907-922)
 };
+struct KnobEntry { uint32_t link_idx; int32_t reg; uint32_t knob; };
 struct zosh_program {
+  std::vector<KnobEntry> knobs;  // RegisterKnob{link_idx, register} -> Knob (command.rs:701-705, 2134-2145); a later instantiation wins
   std::vector<zos_op> ops;
   std::vector<std::shared_ptr<std::vector<uint8_t>>> blobs;
   std::vector<int32_t> regmap;  // generic entry point: register of the template `main` -> register of its monomorphic copy
 };
 
 namespace {
+// with_knob() marks the NEXT operation (command.rs:1865-1874).  A builder that fails must not leave the mark behind for an unrelated
+// later call: every builder holds one of these, and a return without a pushed operation / recorded call clears the pending knob.
+struct KnobGuard {
+  zosh_cb* cb;
+  size_t before;
+  explicit KnobGuard(zosh_cb* c) : cb(c), before(c ? c->ops.size() + c->record.size() : 0) {}
+  ~KnobGuard() { if (cb && cb->ops.size() + cb->record.size() == before) cb->pending_knob = 0; }
+};
 // an IMAGE register (outputs and byte buffers are not: the reference answers TYPE_ERR / BAD_REGISTER for them)
 bool valid_reg(const zosh_cb* cb, int32_t r) { return r >= 0 && (size_t)r < cb->ops.size() && cb->ops[r].kind != ZOS_OP_OUTPUT && cb->ops[r].kind != ZOS_OP_BUFFER_INIT; }
 bool buffer_reg(const zosh_cb* cb, int32_t r) { return r >= 0 && (size_t)r < cb->ops.size() && cb->ops[r].kind == ZOS_OP_BUFFER_INIT; }
@@ -267,6 +283,7 @@ int32_t zosh_cb_describe(const zosh_cb* cb, int32_t reg, zos_desc* out) {
 }
 
 int32_t zosh_cb_input(zosh_cb* cb, const zos_desc* desc, int32_t* reg) {
+  KnobGuard knob_guard(cb);
   if (recording(cb) && desc) return record(cb, call_d(FN_INPUT, desc), reg);
   if (!cb || !desc) return err(ZOSH_ERR_OTHER, "null argument");
   zos_desc d = *desc;
@@ -278,6 +295,7 @@ int32_t zosh_cb_input(zosh_cb* cb, const zos_desc* desc, int32_t* reg) {
 }
 
 int32_t zosh_cb_output(zosh_cb* cb, int32_t src, int32_t* reg) {
+  KnobGuard knob_guard(cb);
   if (recording(cb)) return record(cb, call(FN_OUTPUT, src), reg);
   if (!cb || !valid_reg(cb, src)) return err(ZOSH_ERR_OTHER, "bad register");
   zos_op op = new_op(cb, ZOS_OP_OUTPUT, src, -1, cb->ops[src].desc);
@@ -288,6 +306,7 @@ int32_t zosh_cb_output(zosh_cb* cb, int32_t src, int32_t* reg) {
 }
 
 int32_t zosh_cb_color_convert(zosh_cb* cb, int32_t src, const zos_desc* target, int32_t* reg) {
+  KnobGuard knob_guard(cb);
   if (recording(cb) && target) return record(cb, call_d(FN_COLOR_CONVERT, target, src), reg);
   if (!cb || !target || !valid_reg(cb, src)) return err(ZOSH_ERR_OTHER, "bad register");
   const zos_desc& s = cb->ops[src].desc;
@@ -329,6 +348,7 @@ int32_t zosh_cb_color_convert(zosh_cb* cb, int32_t src, const zos_desc* target, 
 }
 
 int32_t zosh_cb_chromatic_adaptation(zosh_cb* cb, int32_t src, uint32_t method, uint32_t target, int32_t* reg) {
+  KnobGuard knob_guard(cb);
   if (recording(cb)) return record(cb, call_u(call(FN_CHROMATIC_ADAPTATION, src), method, target), reg);
   if (!cb || !valid_reg(cb, src)) return err(ZOSH_ERR_OTHER, "bad register");
   const zos_desc& s = cb->ops[src].desc;
@@ -354,6 +374,7 @@ static void compose_defaults(zos_compose_params& p) {
 }
 
 int32_t zosh_cb_inscribe(zosh_cb* cb, int32_t below, zosh_rect rect, int32_t above, int32_t* reg) {
+  KnobGuard knob_guard(cb);
   if (recording(cb)) { Call c = call(FN_INSCRIBE, below, above); c.rect = rect; return record(cb, c, reg); }
   if (!cb || !valid_reg(cb, below) || !valid_reg(cb, above)) return err(ZOSH_ERR_OTHER, "bad register");
   const zos_desc& b = cb->ops[below].desc;
@@ -371,6 +392,7 @@ int32_t zosh_cb_inscribe(zosh_cb* cb, int32_t below, zosh_rect rect, int32_t abo
 }
 
 int32_t zosh_cb_blend(zosh_cb* cb, int32_t below, zosh_rect rect, int32_t above, int32_t mode, int32_t* reg) {
+  KnobGuard knob_guard(cb);
   if (recording(cb)) { Call c = call(FN_BLEND, below, above); c.rect = rect; c.i = mode; return record(cb, c, reg); }
   // The reference returns UNIMPLEMENTED here (command.rs:1510-1519); semantics: DESIGN.md section 3.
   if (!cb || !valid_reg(cb, below) || !valid_reg(cb, above)) return err(ZOSH_ERR_OTHER, "bad register");
@@ -392,6 +414,7 @@ int32_t zosh_cb_blend(zosh_cb* cb, int32_t below, zosh_rect rect, int32_t above,
 }
 
 int32_t zosh_cb_crop(zosh_cb* cb, int32_t src, zosh_rect rect, int32_t* reg) {
+  KnobGuard knob_guard(cb);
   if (recording(cb)) { Call c = call(FN_CROP, src); c.rect = rect; return record(cb, c, reg); }
   if (!cb || !valid_reg(cb, src)) return err(ZOSH_ERR_OTHER, "bad register");
   const zos_desc& s = cb->ops[src].desc;
@@ -406,6 +429,7 @@ int32_t zosh_cb_crop(zosh_cb* cb, int32_t src, zosh_rect rect, int32_t* reg) {
 }
 
 int32_t zosh_cb_affine(zosh_cb* cb, int32_t below, const float m[9], uint32_t sampling, int32_t above, int32_t* reg) {
+  KnobGuard knob_guard(cb);
   if (recording(cb) && m) return record(cb, call_u(call_f(call(FN_AFFINE, below, above), m, 9), sampling), reg);
   if (!cb || !m || !valid_reg(cb, below) || !valid_reg(cb, above)) return err(ZOSH_ERR_OTHER, "bad register");
   const zos_desc& b = cb->ops[below].desc;
@@ -430,6 +454,7 @@ int32_t zosh_cb_affine(zosh_cb* cb, int32_t below, const float m[9], uint32_t sa
 }
 
 int32_t zosh_cb_resize(zosh_cb* cb, int32_t below, uint32_t w, uint32_t h, uint32_t mode, int32_t* reg) {
+  KnobGuard knob_guard(cb);
   if (recording(cb)) return record(cb, call_u(call(FN_RESIZE, below), w, h, mode), reg);
   if (!cb || !valid_reg(cb, below)) return err(ZOSH_ERR_OTHER, "bad register");
   if (w == 0 || h == 0 || mode > ZOSH_RESIZE_BILINEAR) return err(ZOSH_ERR_OTHER, "resize: bad size / mode");
@@ -447,6 +472,7 @@ int32_t zosh_cb_resize(zosh_cb* cb, int32_t below, uint32_t w, uint32_t h, uint3
 }
 
 int32_t zosh_cb_transmute(zosh_cb* cb, int32_t src, const zos_desc* target, int32_t* reg) {
+  KnobGuard knob_guard(cb);
   if (recording(cb) && target) return record(cb, call_d(FN_TRANSMUTE, target, src), reg);
   if (!cb || !target || !valid_reg(cb, src)) return err(ZOSH_ERR_OTHER, "bad register");
   const zos_desc& s = cb->ops[src].desc;
@@ -460,6 +486,7 @@ int32_t zosh_cb_transmute(zosh_cb* cb, int32_t src, const zos_desc* target, int3
 }
 
 int32_t zosh_cb_bilinear(zosh_cb* cb, const zos_desc* desc, const float p[24], int32_t* reg) {
+  KnobGuard knob_guard(cb);
   if (recording(cb) && desc && p) return record(cb, call_f(call_d(FN_BILINEAR, desc), p, 24), reg);
   if (!cb || !desc || !p) return err(ZOSH_ERR_OTHER, "null argument");
   zos_desc d = *desc;
@@ -472,6 +499,7 @@ int32_t zosh_cb_bilinear(zosh_cb* cb, const zos_desc* desc, const float p[24], i
 }
 
 int32_t zosh_cb_solid_rgba(zosh_cb* cb, const zos_desc* desc, const float color[4], int32_t* reg) {
+  KnobGuard knob_guard(cb);
   if (recording(cb) && desc && color) return record(cb, call_f(call_d(FN_SOLID_RGBA, desc), color, 4), reg);
   if (!cb || !desc || !color) return err(ZOSH_ERR_OTHER, "null argument");
   zos_desc d = *desc;
@@ -500,7 +528,8 @@ void zosh_normal2d_with_direction(float x, float y, float out[7]) {
   auto asym = [](float a, float b) { float lo = fminf(a, b), hi = fmaxf(a, b); float h = hypotf(lo, hi); float inner = fmaf(lo, lo / hi, hi); return ((lo / h) / inner) / h; };
   out[0] = out[1] = 0.0f;
   out[2] = sym(x, x); out[3] = asym(x, y); out[4] = asym(y, x); out[5] = sym(y, y);
-  out[6] = (float)((double)x * (double)x + (double)y * (double)y);
+  const float length_sq = (float)((double)x * (double)x + (double)y * (double)y);
+  out[6] = 2.0f * 3.14159265358979323846f * length_sq;  // pseudo_determinant: 2.0 * PIf32 * length_sq, shaders/distribution_normal2d.rs:96
 }
 void zosh_fractal_noise_with_octaves(uint32_t octaves, float out[5]) {
   if (!out) return;
@@ -518,6 +547,7 @@ void zosh_fractal_noise_set_damping(float params[5], float damping) {
 }
 
 static int32_t push_generator(zosh_cb* cb, const zos_desc* desc, uint32_t kind, const float* p, int n, int32_t* reg, const char* what) {
+  KnobGuard knob_guard(cb);
   if (!cb || !desc || !p) return err(ZOSH_ERR_OTHER, "null argument");
   zos_desc d = *desc;
   if (d.block != ZOS_BLOCK_PIXEL || d.texel_stride != zos_bits_bytes(d.bits) || d.width == 0 || d.height == 0) return err(ZOSH_ERR_BAD_DESCRIPTOR, what);
@@ -528,10 +558,12 @@ static int32_t push_generator(zosh_cb* cb, const zos_desc* desc, uint32_t kind, 
   return push(cb, op, reg);
 }
 int32_t zosh_cb_distribution_normal2d(zosh_cb* cb, const zos_desc* desc, const float params[7], int32_t* reg) {
+  KnobGuard knob_guard(cb);
   if (recording(cb) && desc && params) return record(cb, call_f(call_d(FN_NORMAL2D, desc), params, 7), reg);
   return push_generator(cb, desc, ZOS_GEN_NORMAL2D, params, 7, reg, "inconsistent descriptor for distribution_normal2d");
 }
 int32_t zosh_cb_distribution_fractal_noise(zosh_cb* cb, const zos_desc* desc, const float params[5], int32_t* reg) {
+  KnobGuard knob_guard(cb);
   if (recording(cb) && desc && params) return record(cb, call_f(call_d(FN_FRACTAL_NOISE, desc), params, 5), reg);
   if (params && !(params[4] >= 0.0f && params[4] <= 64.0f)) return err(ZOSH_ERR_OTHER, "fractal noise: 0..64 octaves");
   return push_generator(cb, desc, ZOS_GEN_FRACTAL_NOISE, params, 5, reg, "inconsistent descriptor for distribution_fractal_noise");
@@ -539,6 +571,7 @@ int32_t zosh_cb_distribution_fractal_noise(zosh_cb* cb, const zos_desc* desc, co
 
 // ---- byte buffers (command.rs:1777-1803, 937-968, 1963-2060; tests/buffer.rs)
 static int32_t push_buffer(zosh_cb* cb, const void* data, uint64_t len, int32_t* reg) {
+  KnobGuard knob_guard(cb);
   if (!cb) return err(ZOSH_ERR_OTHER, "null argument");
   if (len == 0 || len > (1ull << 32)) return err(ZOSH_ERR_OTHER, "buffer size out of range");
   zos_desc none;
@@ -553,6 +586,7 @@ static int32_t push_buffer(zosh_cb* cb, const void* data, uint64_t len, int32_t*
   return push(cb, op, reg);
 }
 int32_t zosh_cb_buffer_init(zosh_cb* cb, const void* data, uint64_t len, int32_t* reg) {
+  KnobGuard knob_guard(cb);
   if (recording(cb) && data && len && len <= (1ull << 32)) {
     Call c = call(FN_BUFFER_INIT);
     c.blob.assign((const uint8_t*)data, (const uint8_t*)data + len);
@@ -562,6 +596,7 @@ int32_t zosh_cb_buffer_init(zosh_cb* cb, const void* data, uint64_t len, int32_t
   return push_buffer(cb, data, len, reg);
 }
 int32_t zosh_cb_buffer_zero(zosh_cb* cb, uint64_t len, int32_t* reg) {
+  KnobGuard knob_guard(cb);
   if (recording(cb) && len && len <= (1ull << 32)) { Call c = call(FN_BUFFER_ZERO); c.len = len; return record(cb, c, reg); }
   return push_buffer(cb, nullptr, len, reg);
 }
@@ -576,6 +611,7 @@ int32_t zosh_cb_buffer_size(const zosh_cb* cb, int32_t reg, uint64_t* out) {
   return ZOSH_OK;
 }
 int32_t zosh_cb_from_buffer(zosh_cb* cb, int32_t buffer, const zos_desc* desc, int32_t* reg) {
+  KnobGuard knob_guard(cb);
   if (recording(cb) && desc) return record(cb, call_d(FN_FROM_BUFFER, desc, buffer), reg);
   if (!cb || !desc) return err(ZOSH_ERR_OTHER, "null argument");
   if (!buffer_reg(cb, buffer)) return err(ZOSH_ERR_TYPE, "from_buffer: not a buffer register (CommandError::TYPE_ERR)");
@@ -587,6 +623,7 @@ int32_t zosh_cb_from_buffer(zosh_cb* cb, int32_t buffer, const zos_desc* desc, i
   return push(cb, new_op(cb, ZOS_OP_FROM_BUFFER, buffer, -1, d), reg);
 }
 int32_t zosh_cb_with_buffer_bilinear(zosh_cb* cb, int32_t buffer, const zos_desc* desc, int32_t* reg) {
+  KnobGuard knob_guard(cb);
   if (recording(cb) && desc) return record(cb, call_d(FN_WITH_BUFFER_BILINEAR, desc, buffer), reg);
   if (!cb || !desc) return err(ZOSH_ERR_OTHER, "null argument");
   if (!buffer_reg(cb, buffer)) return err(ZOSH_ERR_TYPE, "with_buffer: not a buffer register");
@@ -603,6 +640,7 @@ int32_t zosh_cb_with_buffer_bilinear(zosh_cb* cb, int32_t buffer, const zos_desc
 // ---- user operators (command.rs:2933-3060 construct_dynamic / unary_dynamic / binary_dynamic; command/dynamic.rs)
 int32_t zosh_cb_dynamic(zosh_cb* cb, int32_t src0, int32_t src1, const char* cuda_source, const zos_desc* desc, const void* params,
                         uint64_t params_len, int32_t* reg) {
+  KnobGuard knob_guard(cb);
   if (recording(cb) && cuda_source && desc && !(src0 < 0 && src1 >= 0)) {
     Call c = call_d(FN_DYNAMIC, desc, src0 < 0 ? -1 : src0, src1 < 0 ? -1 : src1);
     c.source = cuda_source;
@@ -633,6 +671,7 @@ int32_t zosh_cb_dynamic(zosh_cb* cb, int32_t src0, int32_t src1, const char* cud
 }
 
 int32_t zosh_cb_derivative(zosh_cb* cb, int32_t src, uint32_t method, uint32_t height_direction, int32_t* reg) {
+  KnobGuard knob_guard(cb);
   if (recording(cb)) return record(cb, call_u(call(FN_DERIVATIVE, src), method, height_direction), reg);
   if (!cb || !valid_reg(cb, src)) return err(ZOSH_ERR_OTHER, "bad register");
   float sm[3];
@@ -655,6 +694,7 @@ int32_t zosh_cb_derivative(zosh_cb* cb, int32_t src, uint32_t method, uint32_t h
 }
 
 int32_t zosh_cb_palette(zosh_cb* cb, int32_t palette, int32_t indices, const float xc[4], const float yc[4], int32_t* reg) {
+  KnobGuard knob_guard(cb);
   if (recording(cb) && xc && yc) return record(cb, call_f(call_f(call(FN_PALETTE, palette, indices), xc, 4), yc, 4, 4), reg);
   if (!cb || !xc || !yc || !valid_reg(cb, palette) || !valid_reg(cb, indices)) return err(ZOSH_ERR_OTHER, "bad register");
   const zos_desc& p = cb->ops[palette].desc;
@@ -688,6 +728,7 @@ static bool channel_texel(const zos_desc& s, uint32_t channel, zos_desc& d) {
 }
 
 int32_t zosh_cb_extract(zosh_cb* cb, int32_t src, uint32_t channel, int32_t* reg) {
+  KnobGuard knob_guard(cb);
   if (recording(cb)) return record(cb, call_u(call(FN_EXTRACT, src), channel), reg);
   if (!cb || !valid_reg(cb, src)) return err(ZOSH_ERR_OTHER, "bad register");
   zos_desc d;
@@ -698,6 +739,7 @@ int32_t zosh_cb_extract(zosh_cb* cb, int32_t src, uint32_t channel, int32_t* reg
 }
 
 int32_t zosh_cb_inject(zosh_cb* cb, int32_t below, uint32_t channel, int32_t above, int32_t* reg) {
+  KnobGuard knob_guard(cb);
   if (recording(cb)) return record(cb, call_u(call(FN_INJECT, below, above), channel), reg);
   if (!cb || !valid_reg(cb, below) || !valid_reg(cb, above)) return err(ZOSH_ERR_OTHER, "bad register");
   const zos_desc& b = cb->ops[below].desc;
@@ -737,6 +779,7 @@ int32_t zosh_cb_generic(zosh_cb* cb, int32_t* var) {
   return ZOSH_OK;
 }
 int32_t zosh_cb_input_generic(zosh_cb* cb, int32_t var, int32_t* reg) {
+  KnobGuard knob_guard(cb);
   if (!cb || !cb->is_template || var < 0 || (uint32_t)var >= cb->num_generics) return err(ZOSH_ERR_OTHER, "input_generic: unknown generic");
   Call c = call(FN_INPUT_GENERIC);
   c.i = var;
@@ -829,6 +872,7 @@ static int32_t inline_signature(zosh_cb* cb, const zosh_signature& sig, const zo
       if (c.knob) zosh_cb_with_knob(cb);
       const int32_t st = zosh_cb_input(cb, c.fn == FN_INPUT_GENERIC ? &generics[c.i] : &c.d, &map[pos]);
       if (st != ZOSH_OK) return st;
+      if (c.knob) cb->knob_notes.push_back(KnobNote{sig.origin, (int32_t)pos, cb->next_knob});
       continue;
     }
     const int32_t r0 = c.r[0] >= 0 ? map[c.r[0]] : -1, r1 = c.r[1] >= 0 ? map[c.r[1]] : -1;
@@ -855,6 +899,7 @@ static int32_t inline_signature(zosh_cb* cb, const zosh_signature& sig, const zo
     }
     const int32_t st = replay(cb, c, r0, r1, &map[pos]);
     if (st != ZOSH_OK) return st;
+    if (c.knob) cb->knob_notes.push_back(KnobNote{sig.origin, (int32_t)pos, cb->next_knob});  // the id replay() just handed out
   }
   if (entry_map) *entry_map = map;
   return ZOSH_OK;
@@ -862,6 +907,7 @@ static int32_t inline_signature(zosh_cb* cb, const zosh_signature& sig, const zo
 
 int32_t zosh_cb_invoke(zosh_cb* cb, int32_t function, const zos_desc* generics, uint32_t num_generics, const int32_t* arguments,
                        uint32_t num_arguments, int32_t* results, uint32_t results_cap, uint32_t* num_results) {
+  KnobGuard knob_guard(cb);
   if (!cb || (num_generics && !generics) || (num_arguments && !arguments)) return err(ZOSH_ERR_OTHER, "null argument");
   if (function < 0 || (size_t)function >= cb->functions.size()) return err(ZOSH_ERR_OTHER, "invoke: unknown function");  // BAD_REGISTER
   const zosh_signature sig = cb->functions[function];
@@ -893,13 +939,14 @@ int32_t zosh_cb_invoke(zosh_cb* cb, int32_t function, const zos_desc* generics, 
     if (num_results) *num_results = sig.num_outputs;
     return ZOSH_OK;
   }
-  const size_t ops_before = cb->ops.size(), blobs_before = cb->blobs.size();
+  const size_t ops_before = cb->ops.size(), blobs_before = cb->blobs.size(), notes_before = cb->knob_notes.size();
   const uint32_t knob_before = cb->next_knob;
   std::vector<int32_t> out;
   const int32_t st = inline_signature(cb, sig, generics, num_generics, arguments, num_arguments, out, 0);
   if (st != ZOSH_OK) {  // a failed call leaves the caller untouched: undo the partial inlining
     cb->ops.resize(ops_before);
     cb->blobs.resize(blobs_before);
+    cb->knob_notes.resize(notes_before);
     cb->next_knob = knob_before;
     cb->pending_knob = 0;
     return st;
@@ -927,7 +974,23 @@ int32_t zosh_link(const zosh_cb* main_cb, const zos_desc* tys, uint32_t num_tys,
     }
     table += links_per_program[p];
   }
-  if (!main_cb->is_template) return zosh_compile(main_cb, out);
+  // RegisterKnob{link_idx, register} -> Knob: link 0 = main's own operations, link k = the template functions[k - 1]
+  auto knob_table = [&](const zosh_cb& built, bool main_is_template, zosh_program* prog) {
+    if (!main_is_template)
+      for (const zos_op& op : built.ops)
+        if (op.knob) prog->knobs.push_back(KnobEntry{0, op.reg, op.knob});
+    for (const KnobNote& n : built.knob_notes) {
+      uint32_t link = n.origin == main_cb ? 0 : ~0u;
+      for (uint32_t k = 0; k < num_functions && link == ~0u; k++)
+        if (functions[k] == n.origin) link = k + 1;
+      if (link != ~0u) prog->knobs.push_back(KnobEntry{link, n.pos, n.knob});
+    }
+  };
+  if (!main_cb->is_template) {
+    const int32_t st0 = zosh_compile(main_cb, out);
+    if (st0 == ZOSH_OK) { (*out)->knobs.clear(); knob_table(*main_cb, false, *out); }
+    return st0;
+  }
   // generic entry point: build the monomorphic copy of `main` under `tys`, compile that, remember how registers map
   zosh_signature* sig = nullptr;
   int32_t st = zosh_cb_computed_signature(main_cb, &sig);
@@ -938,8 +1001,20 @@ int32_t zosh_link(const zosh_cb* main_cb, const zos_desc* tys, uint32_t num_tys,
   delete sig;
   if (st != ZOSH_OK) return st;
   st = zosh_compile(&mono, out);
-  if (st == ZOSH_OK) (*out)->regmap = map;
+  if (st == ZOSH_OK) {
+    (*out)->regmap = map;
+    (*out)->knobs.clear();
+    knob_table(mono, true, *out);
+  }
   return st;
+}
+// Executable::query_knob (run.rs:1016ff; RegisterKnob, command.rs:701-705): 0 = that register has no knob
+uint32_t zosh_program_knob(const zosh_program* p, uint32_t link_idx, int32_t reg) {
+  uint32_t found = 0;
+  if (p)
+    for (const KnobEntry& e : p->knobs)
+      if (e.link_idx == link_idx && e.reg == reg) found = e.knob;
+  return found;
 }
 int32_t zosh_program_register(const zosh_program* p, int32_t reg) {
   if (!p || reg < 0) return -1;
@@ -963,6 +1038,8 @@ int32_t zosh_compile(const zosh_cb* cb, zosh_program** out) {
   p->blobs = cb->blobs;  // zos_op::data of buffer registers points into these
   for (size_t i = 0; i < cb->ops.size(); i++)
     if (live[i]) p->ops.push_back(cb->ops[i]);
+  for (const zos_op& op : cb->ops)
+    if (op.knob) p->knobs.push_back(KnobEntry{0, op.reg, op.knob});
   *out = p;
   return ZOSH_OK;
 }

@@ -49,6 +49,8 @@ struct Reg {
   Kernel pending;
   bool is_buffer = false;  // a byte buffer register (ZOS_OP_BUFFER_INIT): `owned` is its storage, buf_bytes its size
   uint64_t buf_bytes = 0;
+  uint64_t owned_bytes = 0;   // size of the storage the program itself provides for this register (0 = none)
+  void* last_ptr = nullptr;   // where that storage was before zos_program_release_buffers (a recaptured graph is needed if it moves)
 };
 
 }  // namespace
@@ -64,6 +66,7 @@ struct zos_program {
   cudaGraphExec_t graph_exec = nullptr;
   bool graph_dirty = true, graph_broken = false;
   uint64_t runs = 0, graph_launches = 0;
+  bool released = false;  // temporaries are parked in the context's arena (zos_program_release_buffers)
 };
 
 namespace {
@@ -80,6 +83,7 @@ zos_status alloc_reg(zos_program* p, int r) {
   uint64_t frame = d.row_stride * d.height;
   zos_status st = zos_buf_alloc(p->ctx, frame * p->batch, &R.owned);
   if (st != ZOS_OK) return st;
+  R.owned_bytes = frame * p->batch;
   memset(&R.img, 0, sizeof R.img);
   R.img.desc = d;
   R.img.data = R.owned->ptr;
@@ -254,7 +258,8 @@ zos_status plan(zos_program* p, const zos_op* ops, uint32_t nops) {
         Reg& D = p->regs[op.dst];
         if (op.data_len == 0 || op.data_len > (1ull << 32)) return fail(ctx, ZOS_ERR_INVALID, "op %u: buffer of %llu bytes", i, (unsigned long long)op.data_len);
         D.is_buffer = true; D.buf_bytes = op.data_len; D.materialised = true;
-        if ((st = zos_buf_alloc(ctx, (op.data_len + 255) & ~255ull, &D.owned)) != ZOS_OK) return st;
+        D.owned_bytes = (op.data_len + 255) & ~255ull;
+        if ((st = zos_buf_alloc(ctx, D.owned_bytes, &D.owned)) != ZOS_OK) return st;
         Kernel k;
         k.kind = K_BUFFER_INIT; k.dst = op.dst; k.knob = op.knob;
         k.bytes.assign((size_t)op.data_len, 0);
@@ -417,6 +422,12 @@ zos_status zos_program_bind(zos_program* p, int32_t reg, const zos_image* image)
   if (!image->data) return fail(ctx, ZOS_ERR_INVALID, "bind: null image data");
   if (p->batch > 1 && image->batch_stride == 0) return fail(ctx, ZOS_ERR_INVALID, "bind: batch_stride required for batch > 1");
   if (R.owned) { zos_buf_free(ctx, R.owned); R.owned = nullptr; }
+  R.owned_bytes = 0;  // the caller provides this register from now on
+  if (R.bound && R.img.data == image->data && R.img.plane1 == image->plane1 && R.img.plane2 == image->plane2 &&
+      R.img.batch_stride == image->batch_stride && R.img.desc.row_stride == image->desc.row_stride && R.img.chroma_stride == image->chroma_stride) {
+    R.img = *image;  // the very same storage as last time: the captured graph stays valid (relaunch loops rebind every run)
+    return ZOS_OK;
+  }
   R.img = *image;
   R.bound = true;
   p->graph_dirty = true;
@@ -468,8 +479,62 @@ zos_status zos_program_launch(zos_program* p) {
     Reg& R = p->regs[r];
     if (R.defined && R.is_input && R.materialised && !R.bound) return fail(p->ctx, ZOS_ERR_STATE, "input register %zu is not bound (StartError::MissingKey)", r);
   }
+  if (p->released) {
+    zos_status st = zos_program_recover_buffers(p, nullptr, nullptr);
+    if (st != ZOS_OK) return st;
+  }
   p->pc = 0;
-  p->running = true;
+  p->running = !p->schedule.empty();  // nothing to step through (an output taken straight from an input): not in flight
+  return ZOS_OK;
+}
+
+// Retire::retire_buffers / Environment::recover_buffers (run.rs:2876-2942, 1312-1347): between two launches the storage the
+// program provides for its registers can wait in the context's arena, where any other program may take it.
+zos_status zos_program_release_buffers(zos_program* p, uint64_t* bytes, uint32_t* count) {
+  if (!p) return ZOS_ERR_INVALID;
+  if (p->running) return fail(p->ctx, ZOS_ERR_STATE, "release_buffers: program is running");
+  uint64_t b = 0;
+  uint32_t n = 0;
+  for (Reg& R : p->regs) {
+    if (!R.owned) continue;
+    R.last_ptr = R.owned->ptr;
+    b += R.owned_bytes;
+    n++;
+    zos_buf_free(p->ctx, R.owned);
+    R.owned = nullptr;
+    if (!R.is_buffer) R.img.data = nullptr;
+  }
+  p->released = true;
+  if (bytes) *bytes = b;
+  if (count) *count = n;
+  return ZOS_OK;
+}
+zos_status zos_program_recover_buffers(zos_program* p, uint64_t* bytes_reused, uint64_t* bytes_allocated) {
+  if (!p) return ZOS_ERR_INVALID;
+  uint64_t reused = 0, fresh = 0;
+  for (Reg& R : p->regs) {
+    if (R.owned || R.owned_bytes == 0) continue;
+    const uint64_t before = p->ctx->arena.reuses;
+    zos_status st = zos_buf_alloc(p->ctx, R.owned_bytes, &R.owned);
+    if (st != ZOS_OK) return st;
+    (p->ctx->arena.reuses != before ? reused : fresh) += R.owned_bytes;
+    if (!R.is_buffer) R.img.data = R.owned->ptr;
+    if (R.owned->ptr != R.last_ptr) p->graph_dirty = true;
+  }
+  p->released = false;
+  if (bytes_reused) *bytes_reused = reused;
+  if (bytes_allocated) *bytes_allocated = fresh;
+  return ZOS_OK;
+}
+zos_status zos_program_resources(const zos_program* p, zos_program_stats* out) {
+  if (!p || !out) return ZOS_ERR_INVALID;
+  memset(out, 0, sizeof *out);
+  out->kernels = (uint32_t)p->schedule.size();
+  for (const Reg& R : p->regs)
+    if (R.owned_bytes) { out->temp_buffers++; out->temp_bytes += R.owned_bytes; }
+  out->released = p->released ? 1 : 0;
+  out->runs = p->runs;
+  out->graph_launches = p->graph_launches;
   return ZOS_OK;
 }
 

@@ -199,6 +199,19 @@ zos_status validate_steps(zos_ctx* ctx, const zos_step* steps, uint32_t n) {
 
 using namespace zos;
 
+// Size classes of the arena: powers of two up to 2 MiB, multiples of 2 MiB above (the driver's own granularity), so that the
+// registers of a relaunched program -- and of another program with images of the same shape -- find their blocks again.
+static uint64_t arena_class(uint64_t bytes) {
+  if (bytes <= 256) return 256;
+  if (bytes <= (2ull << 20)) { uint64_t c = 256; while (c < bytes) c <<= 1; return c; }
+  return (bytes + (2ull << 20) - 1) & ~((2ull << 20) - 1);
+}
+static void arena_release_parked(zos_ctx* ctx) {
+  for (auto& cls : ctx->arena_free)
+    for (void* p : cls.second) { cudaFree(p); ctx->arena.bytes_reserved -= cls.first; ctx->arena.bytes_parked -= cls.first; }
+  ctx->arena_free.clear();
+}
+
 extern "C" {
 
 uint32_t zos_abi_version(void) { return ZOS_ABI_VERSION; }
@@ -324,6 +337,7 @@ void zos_ctx_destroy(zos_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   destroy_dynamic_cache(ctx);
+  arena_release_parked(ctx);
   for (void* p : ctx->scratch) cudaFree(p);
   if (ctx->fault_host) cudaFreeHost(ctx->fault_host);
   cudaStreamDestroy(ctx->stream);
@@ -368,21 +382,56 @@ zos_status zos_sync(zos_ctx* ctx) {
 zos_status zos_buf_alloc(zos_ctx* ctx, uint64_t bytes, zos_buf** out) {
   if (!ctx || !out) return ZOS_ERR_INVALID;
   *out = nullptr;
-  cudaSetDevice(ctx->device);
+  const uint64_t cap = arena_class(bytes);
   void* p = nullptr;
-  zos_status st = check_cuda(ctx, cudaMalloc(&p, bytes ? bytes : 256), "cudaMalloc");
-  if (st != ZOS_OK) return st;
+  auto it = ctx->arena_free.find(cap);
+  if (it != ctx->arena_free.end() && !it->second.empty()) {
+    p = it->second.back();  // most recently parked first: a relaunch gets the very pointers it had (its CUDA graph stays valid)
+    it->second.pop_back();
+    ctx->arena.reuses++;
+    ctx->arena.bytes_parked -= cap;
+  } else {
+    cudaSetDevice(ctx->device);
+    cudaError_t e = cudaMalloc(&p, cap);
+    if (e == cudaErrorMemoryAllocation && ctx->arena.bytes_parked) {  // parked blocks of other classes are in the way: give them back, once
+      cudaGetLastError();
+      cudaStreamSynchronize(ctx->stream);
+      arena_release_parked(ctx);
+      e = cudaMalloc(&p, cap);
+    }
+    zos_status st = check_cuda(ctx, e, "cudaMalloc");
+    if (st != ZOS_OK) return st;
+    ctx->arena.device_allocs++;
+    ctx->arena.bytes_reserved += cap;
+  }
+  ctx->arena.bytes_in_use += cap;
   zos_buf* b = new zos_buf();
   b->ptr = p;
   b->size = bytes;
+  b->cap = cap;
   *out = b;
   return ZOS_OK;
 }
 void zos_buf_free(zos_ctx* ctx, zos_buf* buf) {
   if (!buf) return;
-  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
-  cudaFree(buf->ptr);
+  if (!ctx) { cudaFree(buf->ptr); delete buf; return; }  // the context is gone: nothing to park the block in
+  ctx->arena_free[buf->cap].push_back(buf->ptr);
+  ctx->arena.bytes_in_use -= buf->cap;
+  ctx->arena.bytes_parked += buf->cap;
   delete buf;
+}
+zos_status zos_ctx_arena_stats(const zos_ctx* ctx, zos_arena_stats* out) {
+  if (!ctx || !out) return ZOS_ERR_INVALID;
+  *out = ctx->arena;
+  return ZOS_OK;
+}
+zos_status zos_ctx_arena_trim(zos_ctx* ctx) {
+  if (!ctx) return ZOS_ERR_INVALID;
+  if (ctx->arena_free.empty()) return ZOS_OK;
+  cudaSetDevice(ctx->device);
+  zos_status st = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");  // kernels may still read parked blocks
+  arena_release_parked(ctx);
+  return st;
 }
 void* zos_buf_ptr(const zos_buf* buf) { return buf ? buf->ptr : nullptr; }
 uint64_t zos_buf_size(const zos_buf* buf) { return buf ? buf->size : 0; }

@@ -12,7 +12,8 @@
 
 struct zos_buf {
   void* ptr = nullptr;
-  uint64_t size = 0;
+  uint64_t size = 0;  // bytes the caller asked for
+  uint64_t cap = 0;   // bytes of the arena block behind it (its size class)
 };
 
 struct zos_ctx {
@@ -29,6 +30,12 @@ struct zos_ctx {
   float* work_counter = nullptr; // device word: tile dispenser of dynamically scheduled kernels (zeroed before each launch)
   std::set<const void*> smem_configured;  // kernels whose dynamic shared memory limit was raised ON THIS CONTEXT'S DEVICE
   std::map<std::string, struct zos_dynamic*> dynamic_cache;  // NVRTC-compiled plugins by source text (dynamic.cu)
+  // Device arena: freed blocks wait here, by size class, for the next allocation of that class.  All work of a context is
+  // ordered on its one stream, so a block can be handed out again without waiting for the kernels that still read it
+  // (they were enqueued before anything the next owner enqueues).  This is what the reference's pool cache does for
+  // buffers and textures between runs (pool.rs:93-99, run.rs:1312-1347, 2876-2942).
+  std::map<uint64_t, std::vector<void*>> arena_free;
+  zos_arena_stats arena{};
 };
 
 namespace zos {

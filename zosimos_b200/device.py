@@ -44,6 +44,16 @@ class Context:
     def sync(self):
         self.check(self._lib.zos_sync(self.handle))
 
+    def arena_stats(self) -> dict:
+        """zos_ctx_arena_stats: cudaMalloc calls so far, allocations served from parked blocks, bytes held / in use / parked."""
+        st = _ffi.ZosArenaStats()
+        self.check(self._lib.zos_ctx_arena_stats(self.handle, C.byref(st)))
+        return {k: int(getattr(st, k)) for k, _ in _ffi.ZosArenaStats._fields_}
+
+    def arena_trim(self):
+        """Pool::clear_cache for this device (pool.rs:450-455): parked blocks go back to the driver."""
+        self.check(self._lib.zos_ctx_arena_trim(self.handle))
+
     def close(self):
         if self.handle:
             self._lib.zos_ctx_destroy(self.handle)
@@ -205,6 +215,29 @@ class DeviceImage:
                                            out[f].ctypes.data_as(C.c_void_p), rb, rb, h))
         ctx.sync()
         return out[0] if self.batch == 1 else out
+
+    def host_frame_bytes(self) -> int:
+        """Bytes of one frame in the tight host layout (plane 0 rows, then the chroma planes)."""
+        w, h = self.desc.size()
+        if not self.planar:
+            return w * h * self.desc.layout.texel_stride
+        return w * h + 2 * self.cw * self.ch
+
+    def upload_from(self, host_ptr: int, sync: bool = True):
+        """Every frame from tight host memory at `host_ptr` (zos_image_upload).  Asynchronous on the context's stream when
+        the memory is pinned and `sync` is False."""
+        im, ctx, fb = self.ffi(), self.ctx, self.host_frame_bytes()
+        for f in range(self.batch):
+            ctx.check(ctx._lib.zos_image_upload(ctx.handle, C.byref(im), f, C.c_void_p(host_ptr + f * fb)))
+        if sync:
+            ctx.sync()
+
+    def download_into(self, host_ptr: int, sync: bool = True):
+        im, ctx, fb = self.ffi(), self.ctx, self.host_frame_bytes()
+        for f in range(self.batch):
+            ctx.check(ctx._lib.zos_image_download(ctx.handle, C.byref(im), f, C.c_void_p(host_ptr + f * fb)))
+        if sync:
+            ctx.sync()
 
     def free(self):
         self.buf.free()
