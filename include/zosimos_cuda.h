@@ -308,6 +308,9 @@ zos_status zos_program_create(zos_ctx* ctx, const zos_op* ops, uint32_t nops, ui
 void zos_program_destroy(zos_program* prog);
 /* Environment::bind / bind_output (run.rs:1171-1244): registers of Input ops and the src of Output ops */
 zos_status zos_program_bind(zos_program* prog, int32_t reg, const zos_image* image);
+/* undo a binding before the program is launched again with other images: an input is unbound again, an output register
+ * gets its storage from the program again */
+zos_status zos_program_unbind(zos_program* prog, int32_t reg);
 /* Environment::knob (run.rs:1292-1306) */
 zos_status zos_program_set_knob(zos_program* prog, uint32_t knob, const void* data, uint64_t len);
 /* Executable::launch + Execution::step (run.rs:1016,1389): step launches up to max_kernels kernels */

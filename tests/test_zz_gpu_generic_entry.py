@@ -1,12 +1,12 @@
 """GPU cases for the two parts of the function support that were written after the round's GPU budget was spent: a
 generic ENTRY POINT run through Execution / Retire (register translation) and a function invoked from inside a template.
 Their host side is covered on the CPU (tests/test_host_layer.py: the linked streams equal the flat pipeline's); these run
-the same pipelines on the device and compare bytes with the flat pipeline.  Marked xfail(strict=False) until they have been
-seen passing on a B200 once -- an XPASS in the round-end log is that evidence; remove the marker then."""
+the same pipelines on the device and compare bytes with the flat pipeline.  (Seen passing on a B200 at the end of round 1:
+GPUTEST_r01 lists it as XPASS; the xfail guard it carried until then is gone.)"""
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="not yet run on a GPU (written after the budget was spent)", strict=False)]
+pytestmark = pytest.mark.gpu
 
 from zosimos_b200.buffer import Color, Descriptor, SampleParts, Texel  # noqa: E402
 from zosimos_b200.command import CommandBuffer, InvocationArguments, Linker, Rectangle  # noqa: E402

@@ -125,6 +125,7 @@ SIGNATURES = {
     "zos_program_create": (C.c_int32, [_P, C.POINTER(ZosOp), C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(_P)]),
     "zos_program_destroy": (None, [_P]),
     "zos_program_bind": (C.c_int32, [_P, C.c_int32, C.POINTER(ZosImage)]),
+    "zos_program_unbind": (C.c_int32, [_P, C.c_int32]),
     "zos_program_set_knob": (C.c_int32, [_P, C.c_uint32, _P, C.c_uint64]),
     "zos_program_launch": (C.c_int32, [_P]),
     "zos_program_step": (C.c_int32, [_P, C.c_uint32, C.POINTER(C.c_int32)]),

@@ -434,6 +434,32 @@ zos_status zos_program_bind(zos_program* p, int32_t reg, const zos_image* image)
   return ZOS_OK;
 }
 
+// A cached program is launched again with other bindings: a register that is not bound this time goes back to what it was
+// after planning -- an input waits for its image (StartError::MissingKey), anything else gets storage from the program.
+zos_status zos_program_unbind(zos_program* p, int32_t reg) {
+  if (!p) return ZOS_ERR_INVALID;
+  zos_ctx* ctx = p->ctx;
+  if (reg < 0 || (size_t)reg >= p->regs.size() || !p->regs[reg].defined) return fail(ctx, ZOS_ERR_INVALID, "unbind: bad register %d", reg);
+  if (p->running) return fail(ctx, ZOS_ERR_STATE, "unbind: program is running");
+  Reg& R = p->regs[reg];
+  if (!R.bound) return ZOS_OK;
+  R.bound = false;
+  R.img.data = nullptr;
+  p->graph_dirty = true;
+  if (!R.is_input && R.materialised && !R.is_buffer) {
+    zos_desc d = R.desc;
+    d.row_stride = zos_aligned_row_stride(d.width, d.texel_stride);
+    const uint64_t frame = d.row_stride * d.height;
+    memset(&R.img, 0, sizeof R.img);
+    R.img.desc = d;
+    R.img.batch_stride = p->batch > 1 ? frame : 0;
+    R.owned_bytes = frame * p->batch;
+    R.last_ptr = nullptr;
+    p->released = true;  // the next launch allocates it together with whatever else is parked
+  }
+  return ZOS_OK;
+}
+
 zos_status zos_program_set_knob(zos_program* p, uint32_t knob, const void* data, uint64_t len) {
   if (!p || !data || knob == 0) return ZOS_ERR_INVALID;
   bool found = false;

@@ -453,6 +453,8 @@ zos_status zos_buf_upload(zos_ctx* ctx, zos_buf* dst, uint64_t off, uint64_t dpi
   if (row_bytes > dpitch || row_bytes > hpitch || off + (rows - 1) * dpitch + row_bytes > dst->size)
     return fail(ctx, ZOS_ERR_INVALID, "upload out of bounds");
   cudaSetDevice(ctx->device);
+  if (dpitch == row_bytes && hpitch == row_bytes)  // tight on both sides (e.g. 3840 x 4 bytes is already 256-aligned): one linear copy
+    return check_cuda(ctx, cudaMemcpyAsync((uint8_t*)dst->ptr + off, host, row_bytes * rows, cudaMemcpyHostToDevice, ctx->stream), "upload");
   return check_cuda(ctx, cudaMemcpy2DAsync((uint8_t*)dst->ptr + off, dpitch, host, hpitch, row_bytes, rows, cudaMemcpyHostToDevice, ctx->stream), "upload");
 }
 zos_status zos_buf_download(zos_ctx* ctx, const zos_buf* src, uint64_t off, uint64_t spitch, void* host, uint64_t hpitch,
@@ -462,6 +464,8 @@ zos_status zos_buf_download(zos_ctx* ctx, const zos_buf* src, uint64_t off, uint
   if (row_bytes > spitch || row_bytes > hpitch || off + (rows - 1) * spitch + row_bytes > src->size)
     return fail(ctx, ZOS_ERR_INVALID, "download out of bounds");
   cudaSetDevice(ctx->device);
+  if (spitch == row_bytes && hpitch == row_bytes)
+    return check_cuda(ctx, cudaMemcpyAsync(host, (const uint8_t*)src->ptr + off, row_bytes * rows, cudaMemcpyDeviceToHost, ctx->stream), "download");
   return check_cuda(ctx, cudaMemcpy2DAsync(host, hpitch, (const uint8_t*)src->ptr + off, spitch, row_bytes, rows, cudaMemcpyDeviceToHost, ctx->stream), "download");
 }
 zos_status zos_buf_copy(zos_ctx* ctx, zos_buf* dst, uint64_t doff, const zos_buf* src, uint64_t soff, uint64_t bytes) {
@@ -482,6 +486,9 @@ static zos_status image_xfer(zos_ctx* ctx, const zos_image* img, uint32_t frame,
   const zos_desc& d = img->desc;
   cudaSetDevice(ctx->device);
   auto copy = [&](uint8_t* dev, uint64_t dpitch, uint8_t* h, uint64_t row, uint64_t rows) {
+    if (dpitch == row)  // the device pitch has no padding: one linear copy instead of a row loop in the copy engine
+      return check_cuda(ctx, cudaMemcpyAsync(up ? (void*)dev : (void*)h, up ? (const void*)h : (const void*)dev, row * rows,
+                                             up ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, ctx->stream), up ? "image upload" : "image download");
     cudaError_t e = up ? cudaMemcpy2DAsync(dev, dpitch, h, row, row, rows, cudaMemcpyHostToDevice, ctx->stream)
                        : cudaMemcpy2DAsync(h, row, dev, dpitch, row, rows, cudaMemcpyDeviceToHost, ctx->stream);
     return check_cuda(ctx, e, up ? "image upload" : "image download");

@@ -493,8 +493,9 @@ class Execution:
         try:
             for idx, op in exe._inputs.items():
                 key = env.inputs.get(idx)
-                if key is None:
-                    continue  # unused inputs may stay unbound; a needed one fails in zos_program_launch
+                if key is None:  # unused inputs may stay unbound; a needed one fails in zos_program_launch
+                    self._check(lib.zos_program_unbind(self._prog, idx), StartError)  # (a cached program remembers its last bindings)
+                    continue
                 e = env.pool._images[key.index]
                 if e.device is not None and e.device.ctx is self.ctx:
                     dev = e.device  # ImageData::GpuBuffer: read in place
@@ -507,11 +508,16 @@ class Execution:
                     dev.upload_from(e.host_ptr(), sync=e.pinned is None)  # pinned: asynchronous on the context's stream
                 im = dev.ffi()
                 self._check(lib.zos_program_bind(self._prog, idx, C.byref(im)), StartError)
-            for idx, key in env.outputs.items():
-                e = env.pool._images[key.index]
-                if e.device is not None and e.device.ctx is self.ctx:
+            for idx, op in exe._outputs.items():
+                key = env.outputs.get(idx)
+                e = env.pool._images[key.index] if key is not None else None
+                if op.src[0] in exe._inputs:
+                    continue  # an input handed through: it is the input's binding
+                if e is not None and e.device is not None and e.device.ctx is self.ctx:
                     im = e.device.ffi()
-                    self._check(lib.zos_program_bind(self._prog, exe._outputs[idx].src[0], C.byref(im)), StartError)
+                    self._check(lib.zos_program_bind(self._prog, op.src[0], C.byref(im)), StartError)
+                else:
+                    self._check(lib.zos_program_unbind(self._prog, op.src[0]), StartError)
             for k, data in env.knobs.items():
                 buf = C.create_string_buffer(data, len(data))
                 self._check(lib.zos_program_set_knob(self._prog, k, buf, len(data)), StartError)
@@ -635,7 +641,7 @@ class Retire:
             raise RetireError("NoSuchOutput: register %d" % reg.index)
         key = ex.env.outputs.get(idx)
         entry = self.pool._images[key.index] if key is not None and self.pool.entry(key) is not None else None
-        if entry is not None and entry.device is not None and entry.device.ctx is ex.ctx:
+        if entry is not None and entry.device is not None and entry.device.ctx is ex.ctx and op.src[0] not in ex.exe._inputs:
             return PoolImage(self.pool, key)  # the program wrote into the pool's device image
         im = _ffi.ZosImage()
         if ex.ctx._lib.zos_program_register_image(ex._prog, op.src[0], C.byref(im)) != _ffi.OK:
