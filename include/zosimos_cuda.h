@@ -313,6 +313,9 @@ zos_status zos_program_bind(zos_program* prog, int32_t reg, const zos_image* ima
 zos_status zos_program_unbind(zos_program* prog, int32_t reg);
 /* Environment::knob (run.rs:1292-1306) */
 zos_status zos_program_set_knob(zos_program* prog, uint32_t knob, const void* data, uint64_t len);
+/* every knob back to the parameter block the program was planned with: knobs belong to one Environment (run.rs:1292-1306),
+ * so a cached program is reset before the next environment's knobs are applied */
+zos_status zos_program_reset_knobs(zos_program* prog);
 /* Executable::launch + Execution::step (run.rs:1016,1389): step launches up to max_kernels kernels */
 zos_status zos_program_launch(zos_program* prog);
 zos_status zos_program_step(zos_program* prog, uint32_t max_kernels, int32_t* still_running);

@@ -182,9 +182,9 @@ def test_step_to_limits_and_empty_schedules(pool, fixtures):
     rgba8 = Texel.new_u8(SampleParts.RgbA)
     c = CommandBuffer()
     i = c.input(bg.descriptor())
-    a = c.chromatic_adaptation(i, ChromaticAdaptationMethod.VonKries, Z.Whitepoint.D50)
+    a = c.color_convert(i, Color.BT709_RGB, rgba8)
     o1, _ = c.output(a)                                   # `a` is read twice: it is materialised, two kernels
-    o2, _ = c.output(c.color_convert(a, Color.BT709_RGB, rgba8))
+    o2, _ = c.output(c.chromatic_adaptation(a, ChromaticAdaptationMethod.VonKries, Z.Whitepoint.D50))
     executable = Linker.from_included().compile(c).lower_to(Capabilities.from_device(next(pool.iter_devices())))
 
     def launch():

@@ -67,6 +67,10 @@ struct zos_program {
   bool graph_dirty = true, graph_broken = false;
   uint64_t runs = 0, graph_launches = 0;
   bool released = false;  // temporaries are parked in the context's arena (zos_program_release_buffers)
+  // parameter blocks as planned, for every kernel a knob can patch: a cached program starts each launch from them
+  // (a knob belongs to ONE Environment, run.rs:1292-1306; the next environment sees the initial content again)
+  std::vector<std::pair<size_t, Kernel>> pristine;
+  bool knobs_patched = false;
 };
 
 namespace {
@@ -397,6 +401,8 @@ zos_status zos_program_create(zos_ctx* ctx, const zos_op* ops, uint32_t nops, ui
   p->fuse_mode = fuse_mode;
   zos_status st = plan(p, ops, nops);
   if (st != ZOS_OK) { zos_program_destroy(p); return st; }
+  for (size_t i = 0; i < p->schedule.size(); i++)
+    if (p->schedule[i].knob) p->pristine.emplace_back(i, p->schedule[i]);
   *out = p;
   return ZOS_OK;
 }
@@ -460,10 +466,21 @@ zos_status zos_program_unbind(zos_program* p, int32_t reg) {
   return ZOS_OK;
 }
 
+zos_status zos_program_reset_knobs(zos_program* p) {
+  if (!p) return ZOS_ERR_INVALID;
+  if (p->running) return fail(p->ctx, ZOS_ERR_STATE, "reset_knobs: program is running");
+  if (!p->knobs_patched) return ZOS_OK;
+  for (auto& pr : p->pristine) p->schedule[pr.first] = pr.second;
+  p->knobs_patched = false;
+  p->graph_dirty = true;
+  return ZOS_OK;
+}
+
 zos_status zos_program_set_knob(zos_program* p, uint32_t knob, const void* data, uint64_t len) {
   if (!p || !data || knob == 0) return ZOS_ERR_INVALID;
   bool found = false;
   p->graph_dirty = true;
+  p->knobs_patched = true;
   for (Kernel& k : p->schedule) {
     if (k.knob != knob) continue;
     found = true;

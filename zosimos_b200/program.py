@@ -518,6 +518,7 @@ class Execution:
                     self._check(lib.zos_program_bind(self._prog, op.src[0], C.byref(im)), StartError)
                 else:
                     self._check(lib.zos_program_unbind(self._prog, op.src[0]), StartError)
+            self._check(lib.zos_program_reset_knobs(self._prog), StartError)  # (a cached program remembers the last environment's knobs)
             for k, data in env.knobs.items():
                 buf = C.create_string_buffer(data, len(data))
                 self._check(lib.zos_program_set_knob(self._prog, k, buf, len(data)), StartError)
