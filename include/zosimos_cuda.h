@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ZOS_ABI_VERSION 4
+#define ZOS_ABI_VERSION 5
 
 typedef int32_t zos_status;
 enum {
@@ -356,6 +356,31 @@ zos_status zos_program_recover_buffers(zos_program* prog, uint64_t* bytes_reused
 zos_status zos_program_resources(const zos_program* prog, zos_program_stats* out);
 /* fills descriptor + device location of a register the program allocated itself (outputs not bound) */
 zos_status zos_program_register_image(const zos_program* prog, int32_t reg, zos_image* out);
+
+/* ---- several GPUs.  The path shards into independent units -- frames of a batch, row bands of one large
+ * image -- with no exchange step; the reference always uses the first device of its pool (pool.rs:227-230; "If multi-device
+ * then this should become a set", run.rs:416-420).  What a host needs across devices:
+ *   zos_multi_launch   one host thread starts the programs of several contexts (zos_program_run each, ZOS_RUN_* flags)
+ *                      without waiting; zos_multi_sync waits for all of them and reports the first error
+ *   zos_gather_peer    contexts of ONE process: shard i (srcs[i] + src_offsets[i], bytes[i]) is copied over NVLink to
+ *                      dst + dst_offsets[i]; each copy is ordered after the work already enqueued on its source context,
+ *                      and the destination context's stream waits for all of them (no host synchronisation)
+ *   zos_comm_* / zos_gather_nccl   one process per GPU: an NCCL communicator bound to the context (NCCL is loaded at run
+ *                      time, libnccl.so.2 or $ZOS_NCCL_LIBRARY; ZOS_ERR_UNSUPPORTED if absent).  Rank 0 makes the 128-byte
+ *                      id with zos_comm_unique_id and hands it to the other ranks by any host channel.  zos_gather_nccl:
+ *                      every rank contributes shard_bytes[rank] bytes from send + send_off; rank `root` (or every rank when
+ *                      root < 0) receives shard r at recv + recv_offsets[r].  Enqueued on the context's stream. */
+typedef struct zos_comm zos_comm;
+zos_status zos_multi_launch(zos_program* const* progs, uint32_t n, uint32_t flags);
+zos_status zos_multi_sync(zos_ctx* const* ctxs, uint32_t n);
+zos_status zos_gather_peer(zos_ctx* dst_ctx, zos_buf* dst, const uint64_t* dst_offsets, zos_ctx* const* src_ctxs,
+                           const zos_buf* const* srcs, const uint64_t* src_offsets, const uint64_t* bytes, uint32_t n);
+zos_status zos_comm_unique_id(uint8_t* id128);
+zos_status zos_comm_create(zos_ctx* ctx, const uint8_t* id128, uint32_t rank, uint32_t world, zos_comm** out);
+void zos_comm_destroy(zos_comm* comm);
+int32_t zos_comm_nccl_version(void); /* e.g. 22809; 0 when NCCL cannot be loaded */
+zos_status zos_gather_nccl(zos_comm* comm, const zos_buf* send, uint64_t send_off, zos_buf* recv, const uint64_t* recv_offsets,
+                           const uint64_t* shard_bytes, int32_t root);
 
 #ifdef __cplusplus
 }

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), n
     # and the ctypes table covers the device header completely
     assert set(declared("zosimos_cuda.h")) == set(_ffi.SIGNATURES)
-    assert lib.zos_abi_version() == 4
+    assert lib.zos_abi_version() == 5
 
 
 def test_no_cpu_fallback():

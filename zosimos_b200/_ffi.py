@@ -22,6 +22,7 @@ STEP_MATRIX, STEP_OKLAB_ENC, STEP_OKLAB_DEC, STEP_SRLAB2_ENC, STEP_SRLAB2_DEC, S
 # compose
 SAMPLE_NEAREST, SAMPLE_BILINEAR = 0, 1
 MAP_RECT, MAP_AFFINE, MAP_GRID8, MAP_SCALE = 0, 1, 2, 3
+RUN_EAGER, RUN_GRAPH = 0, 1
 BLEND_OVERWRITE = -1
 (BLEND_CLEAR, BLEND_SRC, BLEND_DST, BLEND_SRC_OVER, BLEND_DST_OVER, BLEND_SRC_IN, BLEND_DST_IN, BLEND_SRC_OUT,
  BLEND_DST_OUT, BLEND_SRC_ATOP, BLEND_DST_ATOP, BLEND_XOR) = range(12)
@@ -128,6 +129,14 @@ SIGNATURES = {
     "zos_program_unbind": (C.c_int32, [_P, C.c_int32]),
     "zos_program_set_knob": (C.c_int32, [_P, C.c_uint32, _P, C.c_uint64]),
     "zos_program_reset_knobs": (C.c_int32, [_P]),
+    "zos_multi_launch": (C.c_int32, [C.POINTER(_P), C.c_uint32, C.c_uint32]),
+    "zos_multi_sync": (C.c_int32, [C.POINTER(_P), C.c_uint32]),
+    "zos_gather_peer": (C.c_int32, [_P, _P, C.POINTER(C.c_uint64), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_uint32]),
+    "zos_comm_unique_id": (C.c_int32, [C.POINTER(C.c_uint8)]),
+    "zos_comm_create": (C.c_int32, [_P, C.POINTER(C.c_uint8), C.c_uint32, C.c_uint32, C.POINTER(_P)]),
+    "zos_comm_destroy": (None, [_P]),
+    "zos_comm_nccl_version": (C.c_int32, []),
+    "zos_gather_nccl": (C.c_int32, [_P, _P, C.c_uint64, _P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int32]),
     "zos_program_launch": (C.c_int32, [_P]),
     "zos_program_step": (C.c_int32, [_P, C.c_uint32, C.POINTER(C.c_int32)]),
     "zos_program_kernel_count": (C.c_uint32, [_P]),

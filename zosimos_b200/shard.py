@@ -83,6 +83,91 @@ def band_source_rows(inv: Sequence[float], band: Tuple[int, int], dst_width: int
     return (lo, max(hi, lo))
 
 
+class Comm:
+    """zos_comm: an NCCL communicator bound to a context (one process per GPU).  `id128` is made by rank 0
+    (`Comm.unique_id()`) and handed to the other ranks by any host channel; `from_torch_distributed` uses the process
+    group that is already up (gloo or nccl) for that hand-over only -- the gather itself is zos_gather_nccl on the
+    context's stream."""
+
+    def __init__(self, ctx, rank: int, world: int, id128: bytes):
+        import ctypes as C
+        from . import _ffi
+        self.ctx, self.rank, self.world = ctx, int(rank), int(world)
+        h = C.c_void_p()
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(id128))
+        ctx.check(ctx._lib.zos_comm_create(ctx.handle, buf, self.rank, self.world, C.byref(h)))
+        self.handle = h
+
+    @staticmethod
+    def unique_id() -> bytes:
+        import ctypes as C
+        from . import _ffi
+        lib = _ffi.lib()
+        buf = (C.c_uint8 * 128)()
+        st = lib.zos_comm_unique_id(buf)
+        if st != _ffi.OK:
+            raise _ffi.ZosError(st, (lib.zos_last_error(None) or b"").decode())
+        return bytes(buf)
+
+    @staticmethod
+    def from_torch_distributed(ctx, group=None) -> "Comm":
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        return Comm(ctx, rank, world, box[0])
+
+    def gather(self, send, send_off: int, recv, recv_offsets: Sequence[int], shard_bytes: Sequence[int], root: int = -1):
+        """Every rank contributes shard_bytes[rank] bytes of `send` (a DeviceBuffer) from send_off; rank `root` (every rank
+        when root < 0) receives shard r at recv + recv_offsets[r].  Asynchronous on the context's stream."""
+        import ctypes as C
+        n = self.world
+        offs = (C.c_uint64 * n)(*[int(v) for v in recv_offsets]) if recv_offsets is not None else None
+        sizes = (C.c_uint64 * n)(*[int(v) for v in shard_bytes])
+        self.ctx.check(self.ctx._lib.zos_gather_nccl(self.handle, send.handle if send is not None else None, int(send_off),
+                                                     recv.handle if recv is not None else None, offs, sizes, int(root)))
+
+    def close(self):
+        if self.handle:
+            self.ctx._lib.zos_comm_destroy(self.handle)
+            self.handle = None
+
+
+def gather_peer(dst_ctx, dst, dst_offsets: Sequence[int], shards):
+    """zos_gather_peer for contexts of ONE process: shards = [(ctx, DeviceBuffer, offset, bytes), ...] copied over NVLink
+    into `dst` (a DeviceBuffer of dst_ctx) at dst_offsets; ordered after each source context's queued work."""
+    import ctypes as C
+    n = len(shards)
+    ctxs = (C.c_void_p * n)(*[s[0].handle for s in shards])
+    bufs = (C.c_void_p * n)(*[s[1].handle for s in shards])
+    soff = (C.c_uint64 * n)(*[int(s[2]) for s in shards])
+    size = (C.c_uint64 * n)(*[int(s[3]) for s in shards])
+    doff = (C.c_uint64 * n)(*[int(v) for v in dst_offsets])
+    dst_ctx.check(dst_ctx._lib.zos_gather_peer(dst_ctx.handle, dst.handle, doff, ctxs, bufs, soff, size, n))
+
+
+def multi_launch(programs, graph: bool = True):
+    """zos_multi_launch: start the (already bound) zos_program handles of several contexts from one host thread."""
+    import ctypes as C
+    from . import _ffi
+    lib = _ffi.lib()
+    n = len(programs)
+    arr = (C.c_void_p * n)(*programs)
+    st = lib.zos_multi_launch(arr, n, _ffi.RUN_GRAPH if graph else _ffi.RUN_EAGER)
+    if st != _ffi.OK:
+        raise _ffi.ZosError(st, "zos_multi_launch")
+
+
+def multi_sync(ctxs):
+    import ctypes as C
+    from . import _ffi
+    n = len(ctxs)
+    arr = (C.c_void_p * n)(*[c.handle for c in ctxs])
+    st = _ffi.lib().zos_multi_sync(arr, n)
+    if st != _ffi.OK:
+        raise _ffi.ZosError(st, "; ".join((c._lib.zos_last_error(c.handle) or b"").decode() for c in ctxs))
+
+
 def gather_outputs(local, group=None):
     """All-gather of per-rank outputs (a torch tensor; equal shapes) -> list of tensors, rank order.
     Outside of any timed region: the data path itself has no collective."""
