@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzosimos_cuda.so")
+# ZOS_CUDA_LIB: another build of the same library (A/B runs of two kernel versions on one box, profiles/ab.sh)
+LIB_PATH = os.environ.get("ZOS_CUDA_LIB") or os.path.join(_HERE, "libzosimos_cuda.so")
 
 ZOS_MAX_STEPS = 8
 
