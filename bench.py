@@ -88,6 +88,9 @@ def workload_config(name):
         "c5_rgb10a2": dict(what="decode -> 3x3 primaries matrix -> encode, RGB10A2 sRGB transfer (staged texel)", width=W5, height=H5, bytes_per_px=8, baseline_config=4),
         "c5_yuv420_yuv420": dict(what="I420 BT.2020 -> linear -> 3x3 -> I420 BT.709, one kernel", width=W5, height=H5, bytes_per_px=3, baseline_config=4),
         "c5_yuv420_rgba8": dict(what="I420 BT.2020 -> linear -> 3x3 -> RGBA8 sRGB, one kernel", width=W5, height=H5, bytes_per_px=5.5, baseline_config=4),
+        "band_affine": dict(what="ONE 8192x8192 RGBA16F image, affine rotate 17 deg + scale, bilinear, split into N row bands (one per GPU), each band resampled "
+                                 "from the source rows it needs; with and without a gather of the bands (zos_gather_nccl)", width=8192, height=8192, bytes_per_px=16,
+                            baseline_config=4),
         "loop_rs": dict(what="the reference's tests/loop.rs: inscribe 157x151 on 512x512 RGBA8 sRGB, one pre-lowered Executable relaunched with host upload + "
                              "read-back every iteration (Program API)", width=512, height=512, baseline_config=None),
     }.get(name)
@@ -522,6 +525,13 @@ class Rig:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
+    def sum_over_ranks(self, v):
+        if self.world == 1:
+            return v
+        t = self.torch.tensor([float(v)], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return type(v)(t.item())
+
     def event(self):
         return self.torch.cuda.Event(enable_timing=True)
 
@@ -536,11 +546,11 @@ def time_kernel_workload(rig, name, frames):
     rig.barrier()
     e0, e1 = rig.event(), rig.event()
     e0.record(rig.stream)
-    for _ in range(3):
+    for _ in range(10):  # calibration = the BURST figure: ten launches on a GPU at its full clock (a few milliseconds)
         launch()
     e1.record(rig.stream)
     rig.barrier()
-    t_launch_ms = rig.max_over_ranks(e0.elapsed_time(e1) / 3.0)
+    t_launch_ms = rig.max_over_ranks(e0.elapsed_time(e1) / 10.0)
     lps = max(1, int(math.ceil(args.min_seconds * 1e3 / (args.steps * t_launch_ms))))
     if args.launches_per_step:
         lps = args.launches_per_step
@@ -559,7 +569,8 @@ def time_kernel_workload(rig, name, frames):
     per = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps))
     peak, peak_src = hbm_peak()
     ms_step = total_ms_max / args.steps
-    value = wl.out_px * wl.frames * lps * rig.world / (ms_step * 1e-3) / 1e6
+    frames_all = rig.sum_over_ranks(wl.frames)  # (equal per rank unless --total-frames does not divide)
+    value = wl.out_px * frames_all * lps / (ms_step * 1e-3) / 1e6
     k_ms = total_ms / (args.steps * lps)
     achieved = wl.bytes_per_frame * wl.frames / (k_ms * 1e-3) / 1e9
     facts = kernel_facts(name)
@@ -567,17 +578,25 @@ def time_kernel_workload(rig, name, frames):
             "traffic": facts.get("traffic_bytes") if facts.get("frames") == wl.frames else None, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": wl.bytes_per_frame * wl.frames, "kernel_ms_avg": round(k_ms, 4),
             "kernel_ms_median_step": round(per[len(per) // 2] / lps, 4)}
+    b_ach = wl.bytes_per_frame * wl.frames / (t_launch_ms * 1e-3) / 1e9
+    roof["burst"] = {"kernel_ms": round(t_launch_ms, 4), "achieved": round(b_ach, 1), "frac": round(b_ach / peak, 4),
+                     "note": "10 launches back to back before the timed region (full SM clock; the timed region runs into the board's power cap)"}
     if facts.get("limiter"):  # the kernel's real ceiling when it is not HBM (instruction issue / SFU), from the ncu capture
         roof["limiter"] = facts["limiter"]
     res = {"value": round(value, 1), "unit": "MP/s", "ms_per_step": round(ms_step, 4), "launches_per_step": lps, "frames_per_launch_per_gpu": wl.frames,
            "timed_s": round(total_ms_max * 1e-3, 3), "gpu_launches": int(launches), "roofline": roof, "clocks": smp.result()}
     if wl.in_px != wl.out_px:
-        res["value_input_px"] = round(wl.in_px * wl.frames * lps * rig.world / (ms_step * 1e-3) / 1e6, 1)
+        res["value_input_px"] = round(wl.in_px * frames_all * lps / (ms_step * 1e-3) / 1e6, 1)
     return res, wl, images, extra
 
 
 def rank_seed(rig, name):
     return rig.rank
+
+
+def shard_frames(total, rank, world):
+    from zosimos_b200.shard import frame_shard
+    return frame_shard(total, rank, world)
 
 
 def e2e_c_abi(rig, wl, extra):
@@ -638,6 +657,32 @@ def e2e_c_abi(rig, wl, extra):
             "host_affinity": ("%d CPUs of the GPU's NUMA node" % len(rig.numa_cpus)) if rig.numa_cpus else "unbound", "clocks": smp.result()}
 
 
+def gather_leg(rig, dst):
+    """The optional collective of the path: every rank's FIRST output frame gathered to all ranks over NVLink with
+    zos_gather_nccl (equal shards: ncclAllGather), timed alone with CUDA events on the context's stream, max over ranks."""
+    from zosimos_b200 import shard
+    ctx = rig.ctx
+    comm = shard.Comm.from_torch_distributed(ctx)
+    fb = dst.frame_bytes
+    full = ctx.alloc(fb * rig.world)
+    sizes, offs = [fb] * rig.world, [r * fb for r in range(rig.world)]
+    for _ in range(3):
+        comm.gather(dst.buf, 0, full, offs, sizes, -1)
+    rig.barrier()
+    n = 20
+    e0, e1 = rig.event(), rig.event()
+    e0.record(rig.stream)
+    for _ in range(n):
+        comm.gather(dst.buf, 0, full, offs, sizes, -1)
+    e1.record(rig.stream)
+    rig.barrier()
+    ms = rig.max_over_ranks(e0.elapsed_time(e1)) / n
+    comm.close()
+    full.free()
+    return {"what": "all-gather of one %.1f MB output frame per rank to every rank (zos_gather_nccl, NCCL %d)" % (fb / 1e6, ctx._lib.zos_comm_nccl_version()),
+            "ms": round(ms, 4), "gbs_received_per_gpu": round(fb * (rig.world - 1) / ms / 1e6, 1), "in_timed_region": False}
+
+
 def program_blend(rig, extra, pin):
     """c2_blend as a CommandBuffer program (input, input, blend, output) lowered once; returns run(n) -> ms for n relaunches
     through Executable.launch / Execution.step / Retire.output with HOST images of the pool (pageable numpy, or page-locked
@@ -695,6 +740,83 @@ def e2e_program(rig, wl, extra):
     out["note"] = ("CommandBuffer(input, input, blend, output) lowered once; per launch: Executable.from_pool, bind x2, bind_output, launch, "
                    "step().block_on() until done, Retire.output (device -> host image), finish; serial, host clock")
     return out
+
+
+def band_affine(rig):
+    """SURVEY.md 8e, tile path: row bands of the OUTPUT of one very large image; every rank reads the source rows its band needs
+    (the source is replicated), no halo exchange; the optional collective is the gather of the bands.  Strong scaling."""
+    import ctypes as C
+    from zosimos_b200 import _ffi, ops, shard
+    from zosimos_b200.buffer import ByteLayout, Color, Descriptor, Texel, Transfer
+    from zosimos_b200.command import Affine, AffineSample
+    Z, ctx, args = rig.Z, rig.ctx, rig.args
+    W = H = 8192
+    lin = Color.Rgb(Z.Primaries.Bt709, Transfer.Linear)
+
+    def desc(w, h):
+        return Descriptor(ByteLayout(w, h, w * 8, 8), lin, Texel.new_f16())
+    rng = np.random.default_rng(5)
+    tile = rng.random((256, W * 4), dtype=np.float32).astype(np.float16)
+    src = np.tile(tile, (H // 256, 1)).view(np.uint8)
+    a = Affine.new(AffineSample.Nearest).shift(-W / 2, -H / 2).rotate(float(np.deg2rad(17.0))).scale(1.1, 0.9).shift(W / 2, H / 2)
+    inv = np.linalg.inv(np.asarray(a.transformation, dtype=np.float64).reshape(3, 3)).astype(np.float32)
+    bands = shard.row_bands(H, rig.world, 32)
+    y0, y1 = bands[rig.rank]
+    s0, s1 = shard.band_source_rows(inv.reshape(9), (y0, y1), W, H)
+    above, below, dst = ctx.upload(desc(W, s1 - s0), src[s0:s1]), ctx.upload(desc(W, y1 - y0), src[y0:y1]), ctx.image(desc(W, y1 - y0))
+    p = ops.compose_params(map=_ffi.MAP_AFFINE, sampling=_ffi.SAMPLE_BILINEAR, inv=inv, use_tma=True, dst_origin=(0, y0), src_origin=(0, s0), src_full=(W, H))
+    comm = shard.Comm.from_torch_distributed(ctx) if rig.world > 1 else None
+    full = ctx.alloc(H * W * 8) if comm else None
+    sizes = [(b[1] - b[0]) * W * 8 for b in bands]
+    offs = [b[0] * W * 8 for b in bands]
+
+    def step(mode):
+        ops.compose(ctx, below, above, dst, p)
+        if comm and mode == "all":
+            comm.gather(dst.buf, 0, full, offs, sizes, -1)
+        elif comm and mode == "root":
+            comm.gather(dst.buf, 0, full if rig.rank == 0 else None, offs if rig.rank == 0 else None, sizes, 0)
+    out = {}
+    for mode in (["off", "all", "root"] if comm else ["off"]):
+        for _ in range(max(args.warmup, 3)):
+            step(mode)
+        rig.barrier()
+        e0, e1 = rig.event(), rig.event()
+        e0.record(rig.stream)
+        for _ in range(3):
+            step(mode)
+        e1.record(rig.stream)
+        rig.barrier()
+        t = rig.max_over_ranks(e0.elapsed_time(e1) / 3.0)
+        lps = max(1, int(math.ceil(args.min_seconds * 1e3 / (args.steps * t))))
+        with Sampling(rig.local, rig.rank == 0) as smp:
+            ev = [rig.event() for _ in range(args.steps + 1)]
+            ev[0].record(rig.stream)
+            for i in range(args.steps):
+                for _ in range(lps):
+                    step(mode)
+                ev[i + 1].record(rig.stream)
+            rig.barrier()
+        ms = rig.max_over_ranks(ev[0].elapsed_time(ev[-1]))
+        per_image_ms = ms / (args.steps * lps)
+        out[mode] = {"value": round(W * H / (per_image_ms * 1e-3) / 1e6, 1), "unit": "MP/s", "ms_per_image": round(per_image_ms, 4), "launches_per_step": lps,
+                     "timed_s": round(ms * 1e-3, 3), "clocks": smp.result()}
+    peak, peak_src = hbm_peak()
+    res = {"value": out["off"]["value"], "unit": "MP/s", "ms_per_step": round(out["off"]["ms_per_image"] * out["off"]["launches_per_step"], 4),
+           "launches_per_step": out["off"]["launches_per_step"], "gpu_launches": args.steps * out["off"]["launches_per_step"],
+           "roofline": {"bound": "hbm", "achieved": round(W * H * 16 / (out["off"]["ms_per_image"] * 1e-3) / 1e9, 1), "peak": peak * rig.world, "unit": "GB/s",
+                        "frac": round(W * H * 16 / (out["off"]["ms_per_image"] * 1e-3) / 1e9 / (peak * rig.world), 4), "traffic": None, "peak_source": peak_src + " x n_gpus",
+                        "algorithmic_bytes_per_launch": W * H * 16},
+           "clocks": out["off"]["clocks"], "bands": bands,
+           "gather": {"off": out["off"], "all_ranks": out.get("all"), "root_only": out.get("root"),
+                      "note": "zos_gather_nccl on the context's stream after the band's kernel; image = %.0f MB, each rank contributes 1/N" % (W * H * 8 / 1e6)}}
+    for im in (above, below, dst):
+        im.free()
+    if full:
+        full.free()
+    if comm:
+        comm.close()
+    return res
 
 
 def loop_rs(rig):
@@ -761,6 +883,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="all", help="all | one name | comma list; the first one is the headline of the line")
     ap.add_argument("--frames", type=int, default=0, help="frames per launch per GPU (0 = the workload's default)")
+    ap.add_argument("--total-frames", type=int, default=0, help="STRONG scaling: this many frames per launch over ALL GPUs (each rank takes total / N); "
+                    "BASELINE config 3 is c4_fused with 256")
     ap.add_argument("--min-seconds", type=float, default=1.0, help="each timed region lasts at least this long (launches per step are calibrated)")
     ap.add_argument("--launches-per-step", type=int, default=0, help="fix the launches per step instead of calibrating")
     ap.add_argument("--impl", default="ours")
@@ -790,8 +914,13 @@ def main():
     total_launches = 0
     for name in names:
         frames = args.frames or DEFAULT_FRAMES[name]
-        if name == "loop_rs":
-            res = loop_rs(rig)
+        if args.total_frames and name != "loop_rs":
+            frames = len(shard_frames(args.total_frames, rig.rank, rig.world))
+            if frames == 0:
+                raise SystemExit("--total-frames %d leaves rank %d without work" % (args.total_frames, rig.rank))
+        if name in ("loop_rs", "band_affine"):
+            res = loop_rs(rig) if name == "loop_rs" else band_affine(rig)
+            total_launches += res.get("gpu_launches", 0) if name == "band_affine" else 0
             res["config"] = workload_config(name)
         else:
             res, wl, images, extra = time_kernel_workload(rig, name, frames)
@@ -800,6 +929,7 @@ def main():
                 if name == "c2_blend" and not args.no_e2e:
                     res["e2e"] = e2e_c_abi(rig, wl, extra)
                     res["e2e_program"] = e2e_program(rig, wl, extra)
+                    res["gather"] = gather_leg(rig, images[2]) if rig.world > 1 else None
             for im in images:
                 im.free()
             rig.ctx.arena_trim()
@@ -811,10 +941,13 @@ def main():
     if rig.rank == 0:
         cfg = line.pop("config")
         top = {"metric": "frames/sec" if head == "loop_rs" else "megapixels/sec", "value": line.pop("value"), "unit": line.pop("unit"), "n_gpus": rig.world,
-               "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": line.pop("ms_per_step", None), "higher_is_better": True, "scaling": "weak",
+               "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": line.pop("ms_per_step", None), "higher_is_better": True,
+               "scaling": "strong" if (args.total_frames or head == "band_affine") else "weak",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg}
         top.update(line)
-        top["parallelism"] = "frame-batch sharding over %d GPU(s), no collective on the data path" % rig.world
+        top["parallelism"] = ("row bands of one image over %d GPU(s)" if head == "band_affine" else "frame-batch sharding over %d GPU(s), no collective on the data path") % rig.world
+        if args.total_frames:
+            top["total_frames_per_launch"] = args.total_frames
         if not args.no_cpu:
             top["cpu_baseline"] = cpu_baseline(head, args.budget)
             for n, r in others.items():  # a short sample each, so that every row has its CPU number beside it
