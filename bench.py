@@ -40,7 +40,7 @@ HEADLINE = "c2_blend"
 ALL_WORKLOADS = ["c2_blend", "c2_inscribe", "c1_oklab", "c3_affine_nearest", "c3_affine_bilinear", "c4_fused", "c5_rgba8", "c5_rgba16f",
                  "c5_rgb10a2", "c5_yuv420_yuv420", "c5_yuv420_rgba8", "loop_rs"]
 DEFAULT_FRAMES = {"c2_blend": 16, "c2_inscribe": 16, "c1_oklab": 8, "c3_affine_nearest": 4, "c3_affine_bilinear": 4, "c4_fused": 64,
-                  "c5_rgba8": 8, "c5_rgba16f": 8, "c5_rgb10a2": 8, "c5_yuv420_yuv420": 16, "c5_yuv420_rgba8": 16, "loop_rs": 1}
+                  "c5_rgba8": 8, "c5_rgba16f": 8, "c5_rgb10a2": 8, "c5_yuv420_yuv420": 16, "c5_yuv420_rgba8": 16, "loop_rs": 1, "band_affine": 1}
 C3_ANGLE_DEG = 30.0
 C5_SIZE = (4096, 4096)
 
@@ -914,7 +914,7 @@ def main():
     total_launches = 0
     for name in names:
         frames = args.frames or DEFAULT_FRAMES[name]
-        if args.total_frames and name != "loop_rs":
+        if args.total_frames and name not in ("loop_rs", "band_affine"):
             frames = len(shard_frames(args.total_frames, rig.rank, rig.world))
             if frames == 0:
                 raise SystemExit("--total-frames %d leaves rank %d without work" % (args.total_frames, rig.rank))

@@ -4,11 +4,13 @@
 N=$1; TAG=$2; OUT=gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
 run() { n=$1; shift; if [ $n = 1 ]; then python bench.py --gpus 1 "$@"; else $TR --nproc-per-node $n --master-port $((29600+n)) bench.py --gpus $n "$@"; fi 2>>$OUT/${TAG}_err.txt | grep '^{'; }
-for n in 1 2 4 8; do
+for n in ${NS:-1 2 4 8}; do
   [ $n -le $N ] || continue
   run $n --workload c2_blend --no-cpu >> $OUT/${TAG}_c2_blend.jsonl
-  run $n --workload c4_fused --total-frames 256 --no-cpu >> $OUT/${TAG}_c4_strong.jsonl
-  run $n --workload band_affine --no-cpu >> $OUT/${TAG}_bands.jsonl
+  if [ $n = 1 ] || [ $n = $N ] || [ -n "$ALL_N" ]; then
+    run $n --workload c4_fused --total-frames 256 --no-cpu >> $OUT/${TAG}_c4_strong.jsonl
+    run $n --workload band_affine --no-cpu >> $OUT/${TAG}_bands.jsonl
+  fi
 done
 python - <<PY
 import json
