@@ -650,7 +650,16 @@ def e2e_c_abi(rig, wl, extra):
         l[1].free(); l[2].free()
         l[0].close()
     val = wl.out_px * nfr * rig.world / (ms * 1e-3) / 1e6
-    return {"value": round(val, 1), "unit": "MP/s", "h2d_bytes_per_step": 2 * fb * nfr, "d2h_bytes_per_step": fb * nfr, "frames": nfr, "timed_s": round(ms * 1e-3, 3),
+    ceiling = None  # the raw pinned-copy ceiling of an 8-GPU box of this pool at this N (profiles/pcie_ceiling.py, no kernels), committed
+    try:
+        for l in open(os.path.join(ROOT, "profiles", "r02_pcie_ceiling_8gpu_box.jsonl")):
+            r = json.loads(l)
+            if r["n_gpus"] == rig.world:
+                ceiling = {"raw_copy_ceiling": r["c2_blend_e2e_ceiling_mps"], "unit": "MP/s", "fraction": round(val / r["c2_blend_e2e_ceiling_mps"], 3),
+                           "source": "profiles/r02_multi_gpu.md: pinned cudaMemcpyAsync both directions, %.1f GB/s aggregate at %d GPU(s) on that box" % (r["both_gbs_aggregate"], rig.world)}
+    except Exception:
+        pass
+    return {"value": round(val, 1), "ceiling": ceiling, "unit": "MP/s", "h2d_bytes_per_step": 2 * fb * nfr, "d2h_bytes_per_step": fb * nfr, "frames": nfr, "timed_s": round(ms * 1e-3, 3),
             "pcie_gbs": {"h2d": round(2 * fb * nfr / ms / 1e6, 1), "d2h": round(fb * nfr / ms / 1e6, 1), "note": "per GPU, both directions concurrently"},
             "note": "per frame: zos_buf_upload x2 from pinned host, zos_compose, zos_buf_download to pinned host; 3 streams round robin so "
                     "copies overlap the kernels (PCIe bound)",

@@ -74,7 +74,8 @@ def main_nccl():
     report = []
     for label, bands in (("equal bands", shard.row_bands(H, world, 32)),
                          ("ragged bands", [(0, 0)] * 0 + _ragged(world))):
-        above, below, dst, p = band_job(ctx, src, bel, inv, bands[rank])
+        empty = bands[rank][1] <= bands[rank][0]  # a rank without rows still takes part in the gather (0 bytes)
+        above, below, dst, p = band_job(ctx, src, bel, inv, bands[rank] if not empty else (0, 32))
         sizes = [(b[1] - b[0]) * W * 8 for b in bands]
         offs = [b[0] * W * 8 for b in bands]
         full = ctx.alloc(H * W * 8)
@@ -84,7 +85,8 @@ def main_nccl():
                 e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
                 ctx.sync(); dist.barrier()
                 e[0].record(stream)
-                ops.compose(ctx, below, above, dst, p)
+                if not empty:
+                    ops.compose(ctx, below, above, dst, p)
                 e[1].record(stream)
                 comm.gather(dst.buf, 0, full if (root < 0 or rank == root) else None, offs if (root < 0 or rank == root) else None, sizes, root)
                 e[2].record(stream)

@@ -19,6 +19,7 @@
 // The colour steps themselves are the shared functions of colorops.cuh: results equal the generic
 // kernel's bit for bit (tests compare both, and both with the oracle).
 #include "colorops.cuh"
+#include "f32x2.cuh"
 #include "zos_internal.h"
 #include "rowwise_params.cuh"
 
@@ -107,6 +108,109 @@ __device__ __forceinline__ uint32_t pixel(const LabParams& P, uint32_t w, const 
   return __byte_perm(t1, t2, c.spack);
 }
 
+// ---- two pixels at once for the Oklab chain (round 2).  The kernel is bound by instruction issue (90 % busy, 186
+// instructions per pixel, FMA pipe 1/3 busy: profiles/r01_c1_lab_kernel.txt) and about half of those instructions are
+// IEEE multiplies, adds and fmas: on the packed f32x2 instructions of sm_100a (f32x2.cuh) a pair of pixels pays one issue
+// slot for each.  Operation for operation the code of oklab_enc / requant8 / oklab_dec above and in colorops.cuh /
+// texel.cuh (results stay bit-identical to the generic kernel: tests); what is not a plain multiply-add -- SFU calls,
+// comparisons, sign transfers, the division by 360, float -> int -- stays scalar, and so does a sum whose only producer is
+// a product the scalar code rounds separately (ptxas would contract the packed pair, f32x2.cuh).
+__device__ __forceinline__ F2 f16r2(F2 v) {  // f16r on both halves: one packed conversion down, two up
+  const float2 f = __half22float2(__floats2half2_rn(f2_lo(v), f2_hi(v)));
+  return f2(f.x, f.y);
+}
+__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float lg2_approx(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ F2 cbrt_signed2(F2 v) {  // cbrt_signed (colorops.cuh): pow_fast(|v|, 1/3) with the sign of v, 0 for 0
+  const float v0 = f2_lo(v), v1 = f2_hi(v);
+  const F2 e = f2_mul(f2(1.0f / 3.0f), f2(lg2_approx(fabsf(v0)), lg2_approx(fabsf(v1))));
+  const float r0 = ex2_approx(f2_lo(e)), r1 = ex2_approx(f2_hi(e));
+  return f2(v0 == 0.0f ? 0.0f : copysignf(r0, v0), v1 == 0.0f ? 0.0f : copysignf(r1, v1));
+}
+// atan2_fast (texel.cuh) followed by the hue scaling of transfer_encode(LABLCH)
+__device__ __forceinline__ F2 hue2(F2 y, F2 x) {
+  const float x0 = f2_lo(x), x1 = f2_hi(x), y0 = f2_lo(y), y1 = f2_hi(y);
+  const float ax0 = fabsf(x0), ay0 = fabsf(y0), ax1 = fabsf(x1), ay1 = fabsf(y1);
+  const float mx0 = fmaxf(ax0, ay0), mn0 = fminf(ax0, ay0), mx1 = fmaxf(ax1, ay1), mn1 = fminf(ax1, ay1);
+  float q0, q1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(q0) : "f"(mx0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(q1) : "f"(mx1));
+  const F2 tq = f2_mul(f2(mn0, mn1), f2(q0, q1));
+  const F2 t = f2(mx0 > 0.0f ? f2_lo(tq) : 0.0f, mx1 > 0.0f ? f2_hi(tq) : 0.0f);
+  const F2 s = f2_mul(t, t);
+  F2 p = f2(-0.004054565913975239f);
+  p = f2_fma(p, s, f2(0.021862953901290894f));
+  p = f2_fma(p, s, f2(-0.0559123232960701f));
+  p = f2_fma(p, s, f2(0.0964219719171524f));
+  p = f2_fma(p, s, f2(-0.1390862911939621f));
+  p = f2_fma(p, s, f2(0.19946566224098206f));
+  p = f2_fma(p, s, f2(-0.33329859375953674f));
+  p = f2_fma(p, s, f2(0.9999993443489075f));
+  p = f2_mul(p, t);
+  float p0 = f2_lo(p), p1 = f2_hi(p);
+  if (ay0 > ax0) p0 = 1.57079632679489662f - p0;
+  if (ay1 > ax1) p1 = 1.57079632679489662f - p1;
+  if (x0 < 0.0f) p0 = 3.14159265358979324f - p0;
+  if (x1 < 0.0f) p1 = 3.14159265358979324f - p1;
+  p0 = copysignf(p0, y0); p1 = copysignf(p1, y1);
+  const F2 d = f2_mul(f2(p0, p1), f2(180.0f / ZOS_PI_F));
+  return f2(f2_lo(d) / 360.0f + 0.5f, f2_hi(d) / 360.0f + 0.5f);
+}
+
+template <bool SRGB_DST, bool LCH>
+__device__ __forceinline__ void pixel2_oklab(const LabParams& P, uint32_t w0, uint32_t w1, const Ctx& c, uint32_t& o0, uint32_t& o1) {
+  F2 x = f2(lds_f32(__byte_perm(w0, c.lane4, c.sr) + c.dec), lds_f32(__byte_perm(w1, c.lane4, c.sr) + c.dec));
+  F2 y = f2(lds_f32(__byte_perm(w0, c.lane4, c.sg) + c.dec), lds_f32(__byte_perm(w1, c.lane4, c.sg) + c.dec));
+  F2 z = f2(lds_f32(__byte_perm(w0, c.lane4, c.sb) + c.dec), lds_f32(__byte_perm(w1, c.lane4, c.sb) + c.dec));
+  const uint32_t acode0 = lds_u32(__byte_perm(w0, c.lane4, c.sa) + c.dec + 128u), acode1 = lds_u32(__byte_perm(w1, c.lane4, c.sa) + c.dec + 128u);
+  // oklab_enc
+  f2_mat3(P.enc.m, x, y, z);
+  f2_mat3(c_color.ok_m1, x, y, z);
+  x = cbrt_signed2(x); y = cbrt_signed2(y); z = cbrt_signed2(z);
+  f2_mat3(c_color.ok_m2, x, y, z);
+  // requant8: the staged UInt8x4 register
+  F2 tx = f16r2(x), ty = f16r2(y), tz = f16r2(z);
+  if (LCH) {
+    const F2 aa = f2_mul(ty, ty), bb = f2_mul(tz, tz);
+    const F2 hue = hue2(tz, ty);
+    ty = f2(sqrt_fast(f2_lo(aa) + f2_lo(bb)), sqrt_fast(f2_hi(aa) + f2_hi(bb)));  // (scalar sums of the rounded products)
+    tz = hue;
+  }
+  const uint32_t qx0 = c.q + code8(f2_lo(tx)) * 256u + c.lane_q, qy0 = c.q + code8(f2_lo(ty)) * 256u + c.lane_q, qz0 = c.q + code8(f2_lo(tz)) * 256u + c.lane_q;
+  const uint32_t qx1 = c.q + code8(f2_hi(tx)) * 256u + c.lane_q, qy1 = c.q + code8(f2_hi(ty)) * 256u + c.lane_q, qz1 = c.q + code8(f2_hi(tz)) * 256u + c.lane_q;
+  x = f2(lds_f32(qx0), lds_f32(qx1));
+  if (LCH) {
+    const F2 C = f2(lds_f32(qy0 + 4u), lds_f32(qy1 + 4u));
+    y = f16r2(f2_mul(C, f2(lds_f32(qz0 + 8u), lds_f32(qz1 + 8u))));
+    z = f16r2(f2_mul(C, f2(lds_f32(qz0 + 12u), lds_f32(qz1 + 12u))));
+  } else {
+    y = f2(lds_f32(qy0), lds_f32(qy1)); z = f2(lds_f32(qz0), lds_f32(qz1));
+  }
+  // oklab_dec
+  f2_mat3(c_color.ok_m2i, x, y, z);
+  x = f2_mul(f2_mul(x, x), x); y = f2_mul(f2_mul(y, y), y); z = f2_mul(f2_mul(z, z), z);
+  f2_mat3(c_color.ok_m1i, x, y, z);
+  f2_mat3(P.dec.m, x, y, z);
+  const float v0[3] = {clamp01(f2_lo(x)), clamp01(f2_lo(y)), clamp01(f2_lo(z))}, v1[3] = {clamp01(f2_hi(x)), clamp01(f2_hi(y)), clamp01(f2_hi(z))};
+  uint32_t t1, t2, u1, u2;
+  if (SRGB_DST) {
+    t1 = __byte_perm(srgb_code_b3(v0[0], c), srgb_code_b3(v0[1], c), 0x0073);
+    t2 = __byte_perm(srgb_code_b3(v0[2], c), acode0, 0x0043);
+    u1 = __byte_perm(srgb_code_b3(v1[0], c), srgb_code_b3(v1[1], c), 0x0073);
+    u2 = __byte_perm(srgb_code_b3(v1[2], c), acode1, 0x0043);
+  } else {
+    const F2 k = f2(255.0f);
+    const F2 qr = f2_mul(f2(v0[0], v1[0]), k), qg = f2_mul(f2(v0[1], v1[1]), k), qb = f2_mul(f2(v0[2], v1[2]), k);
+    const float m = 8388608.0f;  // (scalar adds: two roundings)
+    t1 = __byte_perm(__float_as_uint(f2_lo(qr) + m), __float_as_uint(f2_lo(qg) + m), 0x0040);
+    t2 = __byte_perm(__float_as_uint(f2_lo(qb) + m), acode0, 0x0040);
+    u1 = __byte_perm(__float_as_uint(f2_hi(qr) + m), __float_as_uint(f2_hi(qg) + m), 0x0040);
+    u2 = __byte_perm(__float_as_uint(f2_hi(qb) + m), acode1, 0x0040);
+  }
+  o0 = __byte_perm(t1, t2, c.spack);
+  o1 = __byte_perm(u1, u2, c.spack);
+}
+
 template <int LAB, bool SRGB_DST, bool LCH>
 __global__ void __launch_bounds__(LAB_THREADS, 1) k_rowwise_lab(const __grid_constant__ LabParams P) {
   extern __shared__ __align__(256) uint8_t smem[];
@@ -164,8 +268,13 @@ __global__ void __launch_bounds__(LAB_THREADS, 1) k_rowwise_lab(const __grid_con
     const Loc L = locate<0>(P.F, idx);
     const uint4 rb = __ldcs(reinterpret_cast<const uint4*>(P.F.below + L.ob));
     uint32_t o[4];
-    o[0] = pixel<LAB, SRGB_DST, LCH>(P, rb.x, c); o[1] = pixel<LAB, SRGB_DST, LCH>(P, rb.y, c);
-    o[2] = pixel<LAB, SRGB_DST, LCH>(P, rb.z, c); o[3] = pixel<LAB, SRGB_DST, LCH>(P, rb.w, c);
+    if (LAB == 0) {
+      pixel2_oklab<SRGB_DST, LCH>(P, rb.x, rb.y, c, o[0], o[1]);
+      pixel2_oklab<SRGB_DST, LCH>(P, rb.z, rb.w, c, o[2], o[3]);
+    } else {
+      o[0] = pixel<LAB, SRGB_DST, LCH>(P, rb.x, c); o[1] = pixel<LAB, SRGB_DST, LCH>(P, rb.y, c);
+      o[2] = pixel<LAB, SRGB_DST, LCH>(P, rb.z, c); o[3] = pixel<LAB, SRGB_DST, LCH>(P, rb.w, c);
+    }
     uint8_t* dp = P.F.dst + L.od;
     if (L.npx == 4) {
       __stcs(reinterpret_cast<uint4*>(dp), make_uint4(o[0], o[1], o[2], o[3]));

@@ -8,6 +8,7 @@
 // One thread owns one 2x2 block: 4 source texels in, 4 Y' bytes and one Cb / Cr pair out; a warp
 // covers 64 x 2 pixels.  Sources: any pixel texel (generic codec) or planar YUV with nearest chroma.
 #include "colorops.cuh"
+#include "f32x2.cuh"
 #include "zos_internal.h"
 #include "rowwise_params.cuh"
 
@@ -133,6 +134,36 @@ __device__ __forceinline__ uint32_t srgb_code_b3(float x, uint32_t enc_lane) {  
   return e + (uint32_t)idx;
 }
 
+// Round 2: the block's two pixels of a row go through the arithmetic TOGETHER, on the packed f32x2 instructions of
+// sm_100a (f32x2.cuh): the kernel is bound by instruction issue and by the SFU (12 MUFU per pixel for YUV -> YUV), the FMA
+// pipe is 39 % busy (profiles/r01_c5_yuv_yuv_kernel.txt), so every packed instruction frees an issue slot.  Same IEEE
+// operations in the same order as k_yuv_chain: where that code rounds a product and a sum separately and the product has
+// no other user the sum stays scalar (ptxas would contract the packed pair into one FFMA2, see f32x2.cuh).  Integer ->
+// float conversions (SFU pipe) are replaced by the exact 2^23 construction on the FMA pipe, 8-bit results leave through
+// the same construction, and the two Y' bytes of a row are one 16-bit store.
+__device__ __forceinline__ float lg2a(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float ex2a(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ F2 eotf709x2(F2 v) {  // == eotf709 on both halves
+  const F2 lin = f2_mul(v, f2(1.0f / 4.5f));
+  const F2 arg = f2_mul(f2_add(v, f2(0.099f)), f2(1.0f / 1.099f));
+  const F2 e = f2_mul(f2(lg2a(f2_lo(arg)), lg2a(f2_hi(arg))), f2(1.0f / 0.45f));
+  const float p0 = ex2a(f2_lo(e)), p1 = ex2a(f2_hi(e));
+  return f2(f2_lo(v) >= 0.0812428582f ? p0 : f2_lo(lin), f2_hi(v) >= 0.0812428582f ? p1 : f2_hi(lin));
+}
+__device__ __forceinline__ F2 oe709x2(F2 v) {  // == oe_bt709 (texel.cuh) on both halves
+  const F2 e = f2_mul(f2(lg2a(f2_lo(v)), lg2a(f2_hi(v))), f2(0.45f));   // pow_fast(v, 0.45f) = ex2(0.45 * lg2 v)
+  const F2 m = f2_mul(f2(1.099f), f2(ex2a(f2_lo(e)), ex2a(f2_hi(e))));
+  const F2 lin = f2_mul(f2(4.5f), v);
+  return f2(f2_lo(v) >= 0.018f ? f2_lo(m) - 0.099f : f2_lo(lin), f2_hi(v) >= 0.018f ? f2_hi(m) - 0.099f : f2_hi(lin));  // (scalar subtractions)
+}
+// the float of byte k of `w`: 0x4b0000cc - 2^23, exact
+__device__ __forceinline__ F2 bytes_to_f2(uint32_t w0, uint32_t sel0, uint32_t w1, uint32_t sel1) {
+  return f2_sub(f2(__uint_as_float(__byte_perm(w0, 0x4b000000u, sel0)), __uint_as_float(__byte_perm(w1, 0x4b000000u, sel1))), f2(8388608.0f));
+}
+__device__ __forceinline__ F2 clamp255x2(F2 v) {
+  return f2(fminf(fmaxf(f2_lo(v), 0.0f), 255.0f), fminf(fmaxf(f2_hi(v), 0.0f), 255.0f));
+}
+
 template <int DST>
 __global__ void __launch_bounds__(256) k_yuv_fast(const __grid_constant__ YuvFastParams P) {
   __shared__ uint32_t enc[DST == D_SRGB8 ? ZOS_ENC2_N * YER : 1];
@@ -147,6 +178,7 @@ __global__ void __launch_bounds__(256) k_yuv_fast(const __grid_constant__ YuvFas
   const float kg = 1.0f - D.kr - D.kb;
   const float rcb = 1.0f / (2.0f * (1.0f - D.kb)), rcr = 1.0f / (2.0f * (1.0f - D.kr));
   const float cscale = D.full_range ? 255.0f : 224.0f;
+  const float yk = D.full_range ? 255.0f : 219.0f, y0k = D.full_range ? 0.0f : 16.0f;
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < P.total; idx += stride) {
     const uint32_t rowid = fastdiv(idx, P.div_bw);
@@ -154,52 +186,49 @@ __global__ void __launch_bounds__(256) k_yuv_fast(const __grid_constant__ YuvFas
     const uint32_t frame = fastdiv(rowid, P.div_bh);
     const int cj = (int)(rowid - frame * P.bh);
     const uint64_t sco = frame * A.cbstride + (uint64_t)cj * A.cpitch + (uint64_t)ci * cstep_s;
-    const float cb_in = ((float)A.p1[sco] - 128.0f) * A.csc, cr_in = ((float)A.p2[sco] - 128.0f) * A.csc;
+    // chroma: ((float)code - 128) * csc, both samples at once
+    const F2 cc = f2_mul(f2_sub(bytes_to_f2((uint32_t)A.p1[sco], 0x7540, (uint32_t)A.p2[sco], 0x7540), f2(128.0f)), f2(A.csc));
+    const float cb_in = f2_lo(cc), cr_in = f2_hi(cc);
     // both pixels of a block row come from one 16-bit load (the frame width is even for video formats; odd tails take bytes)
     const int x0 = 2 * ci, y0 = 2 * cj;
     const bool two_x = x0 + 1 < D.w, two_y = y0 + 1 < D.h;
-    float cbs = 0.0f, crs = 0.0f;
+    float cbs = 0.0f, crs = 0.0f;  // summed in k_yuv_chain's order (0,0), (1,0), (0,1), (1,1): scalar adds
 #pragma unroll
     for (int dy = 0; dy < 2; dy++) {
       if (dy == 1 && !two_y) break;
       const uint8_t* yrow = A.p0 + frame * A.bstride + (uint64_t)(y0 + dy) * A.pitch + x0;
-      uint32_t ypair = two_x ? (uint32_t)*reinterpret_cast<const uint16_t*>(yrow) : (uint32_t)*yrow;
-      uint32_t words[2];
+      const uint32_t ypair = two_x ? (uint32_t)*reinterpret_cast<const uint16_t*>(yrow) : (uint32_t)*yrow;
+      const F2 yy = f2_mul(f2_sub(bytes_to_f2(ypair, 0x7540, ypair, 0x7541), f2(A.yoff)), f2(A.ysc));
+      F2 r = f2_fma(f2(A.r_cr), f2(cr_in), yy), g = f2_fma(f2(-A.g_cb), f2(cb_in), f2_fma(f2(-A.g_cr), f2(cr_in), yy)), b = f2_fma(f2(A.b_cb), f2(cb_in), yy);
+      r = eotf709x2(r); g = eotf709x2(g); b = eotf709x2(b);
 #pragma unroll
-      for (int dx = 0; dx < 2; dx++) {
-        if (dx == 1 && !two_x) break;
-        const float Y = (float)((ypair >> (8 * dx)) & 255u);
-        const float yy = (Y - A.yoff) * A.ysc;
-        float r = fmaf(A.r_cr, cr_in, yy), g = fmaf(-A.g_cb, cb_in, fmaf(-A.g_cr, cr_in, yy)), b = fmaf(A.b_cb, cb_in, yy);
-        r = eotf709(r); g = eotf709(g); b = eotf709(b);
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-          if (k < P.nmat) {
-            float3 t = mat3_mul(P.m[k], r, g, b);
-            r = t.x; g = t.y; b = t.z;
-          }
-        }
-        if (DST == D_YUV709) {
-          const float er = oe_bt709(r), eg = oe_bt709(g), eb = oe_bt709(b);
-          const float yo = fmaf(D.kb, eb, fmaf(kg, eg, D.kr * er));
-          const float cb = (eb - yo) * rcb, cr = (er - yo) * rcr;
-          const float Yq = D.full_range ? yo * 255.0f : fmaf(yo, 219.0f, 16.0f);
-          D.p0[frame * D.bstride + (uint64_t)(y0 + dy) * D.pitch + x0 + dx] = q8(Yq);
-          cbs += cb; crs += cr;
+      for (int k = 0; k < 2; k++)
+        if (k < P.nmat) f2_mat3(P.m[k], r, g, b);
+      if (DST == D_YUV709) {
+        const F2 er = oe709x2(r), eg = oe709x2(g), eb = oe709x2(b);
+        const F2 yo = f2_fma(f2(D.kb), eb, f2_fma(f2(kg), eg, f2_mul(f2(D.kr), er)));
+        const F2 cb = f2_mul(f2_sub(eb, yo), f2(rcb)), cr = f2_mul(f2_sub(er, yo), f2(rcr));
+        // full range: yo * 255 (a product); limited: fmaf(yo, 219, 16) -- fma(yo, 255, 0) is that product exactly
+        const F2 yq = f2_add(clamp255x2(f2_fma(yo, f2(yk), f2(y0k))), f2(8388608.0f));  // low byte = round to nearest even
+        uint8_t* drow = D.p0 + frame * D.bstride + (uint64_t)(y0 + dy) * D.pitch + x0;
+        if (two_x) *reinterpret_cast<uint16_t*>(drow) = (uint16_t)__byte_perm(__float_as_uint(f2_lo(yq)), __float_as_uint(f2_hi(yq)), 0x0040);
+        else *drow = (uint8_t)__float_as_uint(f2_lo(yq));
+        cbs += f2_lo(cb); crs += f2_lo(cr);
+        if (two_x) { cbs += f2_hi(cb); crs += f2_hi(cr); }
+      } else {
+        const float v0[3] = {fminf(fmaxf(f2_lo(r), 0.0f), 1.0f), fminf(fmaxf(f2_lo(g), 0.0f), 1.0f), fminf(fmaxf(f2_lo(b), 0.0f), 1.0f)};
+        const float v1[3] = {fminf(fmaxf(f2_hi(r), 0.0f), 1.0f), fminf(fmaxf(f2_hi(g), 0.0f), 1.0f), fminf(fmaxf(f2_hi(b), 0.0f), 1.0f)};
+        uint32_t words[2];
+        if (DST == D_SRGB8) {
+          words[0] = __byte_perm(__byte_perm(srgb_code_b3(v0[0], enc_lane), srgb_code_b3(v0[1], enc_lane), 0x0073), __byte_perm(srgb_code_b3(v0[2], enc_lane), 0xffu, 0x0043), P.spack);
+          words[1] = __byte_perm(__byte_perm(srgb_code_b3(v1[0], enc_lane), srgb_code_b3(v1[1], enc_lane), 0x0073), __byte_perm(srgb_code_b3(v1[2], enc_lane), 0xffu, 0x0043), P.spack);
         } else {
-          r = fminf(fmaxf(r, 0.0f), 1.0f); g = fminf(fmaxf(g, 0.0f), 1.0f); b = fminf(fmaxf(b, 0.0f), 1.0f);
-          uint32_t t1, t2;
-          if (DST == D_SRGB8) {
-            t1 = __byte_perm(srgb_code_b3(r, enc_lane), srgb_code_b3(g, enc_lane), 0x0073);
-            t2 = __byte_perm(srgb_code_b3(b, enc_lane), 0xffu, 0x0043);
-          } else {
-            t1 = __byte_perm(__float_as_uint(r * 255.0f + 8388608.0f), __float_as_uint(g * 255.0f + 8388608.0f), 0x0040);
-            t2 = __byte_perm(__float_as_uint(b * 255.0f + 8388608.0f), 0xffu, 0x0040);
-          }
-          words[dx] = __byte_perm(t1, t2, P.spack);
+          const F2 k = f2(255.0f);
+          const F2 qr = f2_mul(f2(v0[0], v1[0]), k), qg = f2_mul(f2(v0[1], v1[1]), k), qb = f2_mul(f2(v0[2], v1[2]), k);
+          const float m = 8388608.0f;  // (scalar adds: v * 255 and + 2^23 are two roundings)
+          words[0] = __byte_perm(__byte_perm(__float_as_uint(f2_lo(qr) + m), __float_as_uint(f2_lo(qg) + m), 0x0040), __byte_perm(__float_as_uint(f2_lo(qb) + m), 0xffu, 0x0040), P.spack);
+          words[1] = __byte_perm(__byte_perm(__float_as_uint(f2_hi(qr) + m), __float_as_uint(f2_hi(qg) + m), 0x0040), __byte_perm(__float_as_uint(f2_hi(qb) + m), 0xffu, 0x0040), P.spack);
         }
-      }
-      if (DST != D_YUV709) {
         uint8_t* drow = D.p0 + frame * D.bstride + (uint64_t)(y0 + dy) * D.pitch + (uint64_t)x0 * 4u;
         if (two_x) __stcs(reinterpret_cast<uint2*>(drow), make_uint2(words[0], words[1]));
         else *reinterpret_cast<uint32_t*>(drow) = words[0];
@@ -209,8 +238,9 @@ __global__ void __launch_bounds__(256) k_yuv_fast(const __grid_constant__ YuvFas
       const int cnt = (two_x ? 2 : 1) * (two_y ? 2 : 1);
       const float inv = cnt == 4 ? 0.25f : cnt == 2 ? 0.5f : 1.0f;  // == dividing by 1, 2 or 4
       const uint64_t co = frame * D.cbstride + (uint64_t)cj * D.cpitch + (uint64_t)ci * cstep_d;
-      D.p1[co] = q8(fmaf(cbs * inv, cscale, 128.0f));
-      D.p2[co] = q8(fmaf(crs * inv, cscale, 128.0f));
+      const F2 q = f2_add(clamp255x2(f2_fma(f2_mul(f2(cbs, crs), f2(inv)), f2(cscale), f2(128.0f))), f2(8388608.0f));
+      D.p1[co] = (uint8_t)__float_as_uint(f2_lo(q));
+      D.p2[co] = (uint8_t)__float_as_uint(f2_hi(q));
     }
   }
 }
@@ -239,6 +269,7 @@ zos_status launch_yuv_fast(zos_ctx* ctx, const DevImage& src, const DevImage& ds
     if (((uintptr_t)dst.p0 % 8) || (dst.pitch % 8) || (dst.bstride % 8)) return ZOS_OK;
   }
   if ((src.pitch % 2) || ((uintptr_t)src.p0 % 2) || (src.bstride % 2)) return ZOS_OK;
+  if (kind == D_YUV709 && ((dst.pitch % 2) || ((uintptr_t)dst.p0 % 2) || (dst.bstride % 2))) return ZOS_OK;  // 16-bit Y' stores
   YuvFastParams P;
   memset(&P, 0, sizeof P);
   P.src = src; P.dst = dst;
