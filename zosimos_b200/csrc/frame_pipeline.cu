@@ -23,6 +23,7 @@
 #include <stdlib.h>
 
 #include "colorops.cuh"
+#include "f32x2.cuh"
 #include "tma.cuh"
 #include "zos_internal.h"
 
@@ -312,6 +313,35 @@ __device__ __forceinline__ void sts64(uint32_t addr, float a, float b) {
   asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
 }
 
+// ---- round 2: two texels at once on the packed f32x2 instructions (f32x2.cuh); same operations, same order, same bits.
+__device__ __forceinline__ void sts64(uint32_t addr, F2 v) { sts64(addr, f2_lo(v), f2_hi(v)); }
+template <int TRK>
+__device__ __forceinline__ F2 eotf_k2(uint32_t tr, F2 v) {
+  if (TRK == 0) {
+    const F2 lin = f2_mul(v, f2(1.0f / 4.5f));
+    const F2 arg = f2_mul(f2_add(v, f2(0.099f)), f2(1.0f / 1.099f));
+    float l0, l1, p0, p1;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l0) : "f"(f2_lo(arg)));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l1) : "f"(f2_hi(arg)));
+    const F2 e = f2_mul(f2(l0, l1), f2(1.0f / 0.45f));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(f2_lo(e)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(f2_hi(e)));
+    return f2(f2_lo(v) >= 0.0812428582f ? p0 : f2_lo(lin), f2_hi(v) >= 0.0812428582f ? p1 : f2_hi(lin));
+  }
+  if (TRK == 1) return v;
+  return f2(eo_scalar(tr, f2_lo(v)), eo_scalar(tr, f2_hi(v)));
+}
+// convert_rgb on the two luma samples in bytes 0 and 1 of `ypair` (they share the block's chroma)
+template <int TRK>
+__device__ __forceinline__ void convert_rgb2(const FrameParams& P, uint32_t ypair, float cb, float cr, F2& r, F2& g, F2& b) {
+  // (float)code as 0x4b0000cc - 2^23, exact, on the FMA pipe instead of the conversion unit
+  const F2 Y = f2_sub(f2(__uint_as_float(__byte_perm(ypair, 0x4b000000u, 0x7540)), __uint_as_float(__byte_perm(ypair, 0x4b000000u, 0x7541))), f2(8388608.0f));
+  const F2 y = f2_mul(f2_sub(Y, f2(P.yoff)), f2(P.ysc));
+  r = f2_fma(f2(P.r_cr), f2(cr), y); g = f2_fma(f2(-P.g_cb), f2(cb), f2_fma(f2(-P.g_cr), f2(cr), y)); b = f2_fma(f2(P.b_cb), f2(cb), y);
+  r = eotf_k2<TRK>(P.transfer, r); g = eotf_k2<TRK>(P.transfer, g); b = eotf_k2<TRK>(P.transfer, b);
+  if (P.nmat) f2_mat3(P.m, r, g, b);
+}
+
 __device__ __forceinline__ float lds32(uint32_t a) {
   float v;
   asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
@@ -402,10 +432,11 @@ __global__ void __launch_bounds__(THREADS, 4) k_frame_fast(const __grid_constant
         asm("ld.shared.u8 %0, [%1];" : "=r"(v8) : "r"(vbase + ca));
         const float cb = ((float)u8 - 128.0f) * P.csc, cr = ((float)v8 - 128.0f) * P.csc;
         const uint32_t o = conv_base + (uint32_t)((2 * byi) * P.conv_w + 2 * bxi) * 4u;
-        const float3 c00 = convert_rgb<TRK>(P, (float)(y01 & 255u), cb, cr), c10 = convert_rgb<TRK>(P, (float)(y01 >> 8), cb, cr);
-        const float3 c01 = convert_rgb<TRK>(P, (float)(y23 & 255u), cb, cr), c11 = convert_rgb<TRK>(P, (float)(y23 >> 8), cb, cr);
-        sts64(o, c00.x, c10.x); sts64(o + P.plane_bytes, c00.y, c10.y); sts64(o + 2u * P.plane_bytes, c00.z, c10.z);
-        sts64(o + cw4, c01.x, c11.x); sts64(o + cw4 + P.plane_bytes, c01.y, c11.y); sts64(o + cw4 + 2u * P.plane_bytes, c01.z, c11.z);
+        F2 r0, g0, b0, r1, g1, b1;  // the block's upper and lower pair of texels
+        convert_rgb2<TRK>(P, y01, cb, cr, r0, g0, b0);
+        convert_rgb2<TRK>(P, y23, cb, cr, r1, g1, b1);
+        sts64(o, r0); sts64(o + P.plane_bytes, g0); sts64(o + 2u * P.plane_bytes, b0);
+        sts64(o + cw4, r1); sts64(o + cw4 + P.plane_bytes, g1); sts64(o + cw4 + 2u * P.plane_bytes, b1);
       }
       __syncthreads();
     }
@@ -419,25 +450,31 @@ __global__ void __launch_bounds__(THREADS, 4) k_frame_fast(const __grid_constant
       uint8_t* dp = P.dst + ((uint64_t)g.frame * P.dst_bstride + (uint64_t)(g.y0 + ly) * P.dst_pitch + (uint64_t)i * 4u);
       const uint64_t dstep = 8u * P.dst_pitch;
 #pragma unroll
-      for (int k = 0; k < TILE / 8; k++) {
-        const uint4 rt = rtab[ly + 8 * k];
-        const float ay = __uint_as_float(rt.z);
-        const uint32_t a00 = ca + rt.x, a10 = cb + rt.x, a01 = ca + rt.y, a11 = cb + rt.y;
-        float r, gg, b;
-#define ZOS_TAP(dst_, off_) { const float p00 = lds32(a00 + (off_)), p10 = lds32(a10 + (off_)), p01 = lds32(a01 + (off_)), p11 = lds32(a11 + (off_)); \
-                              const float top = fmaf(ax, p10 - p00, p00), bot = fmaf(ax, p11 - p01, p01); dst_ = fmaf(ay, bot - top, top); }
+      for (int k = 0; k < TILE / 8; k += 2) {  // two of the thread's four rows at a time: the lerps are packed
+        const uint4 rt0 = rtab[ly + 8 * k], rt1 = rtab[ly + 8 * k + 8];
+        const F2 ay = f2(__uint_as_float(rt0.z), __uint_as_float(rt1.z)), axx = f2(ax);
+        const uint32_t a00 = ca + rt0.x, a10 = cb + rt0.x, a01 = ca + rt0.y, a11 = cb + rt0.y;
+        const uint32_t c00 = ca + rt1.x, c10 = cb + rt1.x, c01 = ca + rt1.y, c11 = cb + rt1.y;
+        F2 r, gg, b;
+#define ZOS_TAP(dst_, off_) { const F2 p00 = f2(lds32(a00 + (off_)), lds32(c00 + (off_))), p10 = f2(lds32(a10 + (off_)), lds32(c10 + (off_))); \
+                              const F2 p01 = f2(lds32(a01 + (off_)), lds32(c01 + (off_))), p11 = f2(lds32(a11 + (off_)), lds32(c11 + (off_))); \
+                              const F2 top = f2_fma(axx, f2_sub(p10, p00), p00), bot = f2_fma(axx, f2_sub(p11, p01), p01); dst_ = f2_fma(ay, f2_sub(bot, top), top); }
         ZOS_TAP(r, 0u) ZOS_TAP(gg, P.plane_bytes) ZOS_TAP(b, 2u * P.plane_bytes)
 #undef ZOS_TAP
-        r = fminf(fmaxf(r, 0.0f), 1.0f); gg = fminf(fmaxf(gg, 0.0f), 1.0f); b = fminf(fmaxf(b, 0.0f), 1.0f);
-        uint32_t t1, t2;
-        if (SRGB_DST) {
-          t1 = __byte_perm(srgb_code_b3(r, enc_lane), srgb_code_b3(gg, enc_lane), 0x0073);
-          t2 = __byte_perm(srgb_code_b3(b, enc_lane), 0xffu, 0x0043);
-        } else {
-          t1 = __byte_perm(__float_as_uint(r * 255.0f + 8388608.0f), __float_as_uint(gg * 255.0f + 8388608.0f), 0x0040);
-          t2 = __byte_perm(__float_as_uint(b * 255.0f + 8388608.0f), 0xffu, 0x0040);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const float rr = fminf(fmaxf(h ? f2_hi(r) : f2_lo(r), 0.0f), 1.0f), g1 = fminf(fmaxf(h ? f2_hi(gg) : f2_lo(gg), 0.0f), 1.0f),
+                      bb = fminf(fmaxf(h ? f2_hi(b) : f2_lo(b), 0.0f), 1.0f);
+          uint32_t t1, t2;
+          if (SRGB_DST) {
+            t1 = __byte_perm(srgb_code_b3(rr, enc_lane), srgb_code_b3(g1, enc_lane), 0x0073);
+            t2 = __byte_perm(srgb_code_b3(bb, enc_lane), 0xffu, 0x0043);
+          } else {
+            t1 = __byte_perm(__float_as_uint(rr * 255.0f + 8388608.0f), __float_as_uint(g1 * 255.0f + 8388608.0f), 0x0040);
+            t2 = __byte_perm(__float_as_uint(bb * 255.0f + 8388608.0f), 0xffu, 0x0040);
+          }
+          __stcs(reinterpret_cast<uint32_t*>(dp + (uint64_t)(k + h) * dstep), __byte_perm(t1, t2, P.spack));
         }
-        __stcs(reinterpret_cast<uint32_t*>(dp + (uint64_t)k * dstep), __byte_perm(t1, t2, P.spack));
       }
     } else if (i < P.dw) {
       const int kx = i - P.tgt[0];
