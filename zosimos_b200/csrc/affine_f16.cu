@@ -280,6 +280,47 @@ __device__ __forceinline__ void compute_rows(const AffParams& P, const Geo& g, c
   }
 }
 
+// The width of the staged box decides which shared-memory banks the taps of a warp meet: lane i of a row reads texel
+// (x + i * inv[0], y + i * inv[3]), an LDS.64 serves a half-warp per wavefront when its 16 lanes hit 16 different bank
+// pairs, and bank pair = (column + row * box_w) mod 16.  A fixed rule (round 1: box_w = 2 mod 4) is good for some rotations
+// and very bad for others (30 degrees: 2.0 wavefronts per half-warp load, -30 degrees: 6.3, because the row term cancels the
+// column term; ncu had 45 % of this kernel's shared wavefronts as conflict replays, and the L1 data pipe is its busiest
+// unit: profiles/r02_kernel_facts.md).  So the launcher simulates the four taps of a row of 32 lanes on a lattice of
+// sub-texel phases for the 8 even widths from the minimum up, and takes the cheapest (ties: the narrowest, every extra
+// column is fetched by the TMA unit).
+static int pick_box_width(int min_w, float dxl, float dyl) {
+  int best_w = min_w;
+  long best = -1;
+  for (int w = min_w; w < min_w + 16; w += 2) {
+    long cost = 0;
+    for (int ph = 0; ph < 16; ph++) {
+      const float x0 = 64.0f + 0.25f * (float)(ph & 3) + 0.125f, y0 = 64.0f + 0.25f * (float)(ph >> 2) + 0.125f;
+      for (int tap = 0; tap < 4; tap++)
+        for (int half = 0; half < 2; half++) {
+          int addr[16], worst = 0;
+          for (int l = 0; l < 16; l++) {
+            const int i = half * 16 + l;
+            const int X = (int)floorf(x0 + (float)i * dxl - 0.5f) + (tap & 1), Y = (int)floorf(y0 + (float)i * dyl - 0.5f) + (tap >> 1);
+            addr[l] = Y * w + X;
+          }
+          for (int b = 0; b < 16; b++) {
+            int distinct = 0;
+            for (int l = 0; l < 16; l++) {
+              if ((addr[l] & 15) != b) continue;
+              bool seen = false;
+              for (int k = 0; k < l; k++) seen = seen || addr[k] == addr[l];
+              distinct += !seen;
+            }
+            worst = distinct > worst ? distinct : worst;
+          }
+          cost += worst;
+        }
+    }
+    if (best < 0 || cost < best) { best = cost; best_w = w; }
+  }
+  return best_w;
+}
+
 template <bool BILINEAR, int GROUP>
 __device__ __forceinline__ void compute_tile_smem(const AffParams& P, const Geo& g, const Lane& L) {
   // == (float)(i + dox) + 0.5f: every term is an exact float below 2^22 (checked by the launcher)
@@ -558,7 +599,12 @@ zos_status launch_affine_f16(zos_ctx* ctx, const DevImage* below, const DevImage
   // vertically adjacent taps 4 banks apart (a multiple of 128 bytes would put them on the same bank)
   P.margin = cp.sampling == ZOS_SAMPLE_BILINEAR ? 1 : 0;
   P.box_w = (int)ceilf(ex) + 3 + 2 * P.margin;
-  while ((P.box_w & 3) != 2) P.box_w++;
+  P.box_w += P.box_w & 1;  // (the TMA box's inner extent is a multiple of 16 bytes)
+  if (ctx->box_cache.w == 0 || ctx->box_cache.min_w != P.box_w || ctx->box_cache.dxl != P.inv[0] || ctx->box_cache.dyl != P.inv[3]) {
+    ctx->box_cache.w = pick_box_width(P.box_w, P.inv[0], P.inv[3]);  // ~1 ms of host work: once per mapping, not per launch
+    ctx->box_cache.min_w = P.box_w; ctx->box_cache.dxl = P.inv[0]; ctx->box_cache.dyl = P.inv[3];
+  }
+  P.box_w = ctx->box_cache.w;
   P.box_h = (int)ceilf(ey) + 2 + 2 * P.margin;
   const size_t stage = ((size_t)P.box_w * P.box_h * 8 + 127) & ~(size_t)127;
   const size_t smem = STAGES * stage;

@@ -36,6 +36,8 @@ struct zos_ctx {
   // buffers and textures between runs (pool.rs:93-99, run.rs:1312-1347, 2876-2942).
   std::map<uint64_t, std::vector<void*>> arena_free;
   zos_arena_stats arena{};
+  // affine_f16.cu: the last staged-box width worked out for (minimum width, per-lane source step): launches of one program repeat it
+  struct { int min_w = 0; float dxl = 0.0f, dyl = 0.0f; int w = 0; } box_cache;
 };
 
 namespace zos {
