@@ -229,8 +229,11 @@ def test_fused_c1_chain_matches_unfused(ctx, fixtures):
     assert np.array_equal(one, two)
     exp = O.color_convert(O.color_convert(oracle_image(srgb, bg), O.OKLAB, oracle_desc(lch).texel), O.SRGB, O.RGBA8).data
     d = np.abs(one.astype(int) - exp.astype(int))
-    assert np.mean(d > 1) < 0.01   # a flipped truncation of the 8-bit LCh register moves a few pixels by > 1
-    assert np.mean(d == 0) > 0.97
+    # a flipped truncation of the 8-bit LCh register moves a few pixels by > 1.  Measured on a B200 (round 2,
+    # scratch script now folded into this test's message): 0.000007 of the bytes differ by more than 1 LSB, 0.999958 are equal;
+    # the bounds are ~15x / ~25x those figures so that a regression of the arithmetic shows
+    far, same = float(np.mean(d > 1)), float(np.mean(d == 0))
+    assert far < 1e-4 and same > 0.999, "fraction > 1 LSB %.6f (measured 0.000007), fraction equal %.6f (measured 0.999958)" % (far, same)
 
 
 # ---------------------------------------------------------------- composition

@@ -44,16 +44,18 @@ __device__ __forceinline__ float sr_nl_inv(float v) {
 
 // The four non-linear colour steps (oklab.frag:34-64, srlab2.frag:36-120), shared by the step interpreter
 // below and by the specialised Lab kernel (rowwise_lab.cu): one definition, identical results.
+// s.m of the two Oklab steps is the FOLDED matrix here: M1 * to_xyz for the encoder, from_xyz * M1^-1 for the decoder, multiplied
+// in double precision by the C-ABI entry points (zos::fold_steps, runtime.cu) -- one 3x3 product per pixel and direction less
+// than oklab.frag:34-64 spells out (two matrices applied in turn); the chain carries the <= 1 LSB tolerance of its SFU cube
+// roots anyway.
 __device__ __forceinline__ void oklab_enc(const zos_step& s, float4& v) {
-  float3 xyz = mat3_mul(s.m, v.x, v.y, v.z);
-  float3 lms = mat3_mul(c_color.ok_m1, xyz.x, xyz.y, xyz.z);
+  float3 lms = mat3_mul(s.m, v.x, v.y, v.z);
   float3 lab = mat3_mul(c_color.ok_m2, cbrt_signed(lms.x), cbrt_signed(lms.y), cbrt_signed(lms.z));
   v.x = lab.x; v.y = lab.y; v.z = lab.z;
 }
 __device__ __forceinline__ void oklab_dec(const zos_step& s, float4& v) {
   float3 l = mat3_mul(c_color.ok_m2i, v.x, v.y, v.z);
-  float3 xyz = mat3_mul(c_color.ok_m1i, l.x * l.x * l.x, l.y * l.y * l.y, l.z * l.z * l.z);
-  float3 rgb = mat3_mul(s.m, xyz.x, xyz.y, xyz.z);
+  float3 rgb = mat3_mul(s.m, l.x * l.x * l.x, l.y * l.y * l.y, l.z * l.z * l.z);
   v.x = clamp01(rgb.x); v.y = clamp01(rgb.y); v.z = clamp01(rgb.z);
 }
 __device__ __forceinline__ void srlab2_enc(const zos_step& s, float4& v) {

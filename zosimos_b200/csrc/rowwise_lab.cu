@@ -164,8 +164,7 @@ __device__ __forceinline__ void pixel2_oklab(const LabParams& P, uint32_t w0, ui
   F2 z = f2(lds_f32(__byte_perm(w0, c.lane4, c.sb) + c.dec), lds_f32(__byte_perm(w1, c.lane4, c.sb) + c.dec));
   const uint32_t acode0 = lds_u32(__byte_perm(w0, c.lane4, c.sa) + c.dec + 128u), acode1 = lds_u32(__byte_perm(w1, c.lane4, c.sa) + c.dec + 128u);
   // oklab_enc
-  f2_mat3(P.enc.m, x, y, z);
-  f2_mat3(c_color.ok_m1, x, y, z);
+  f2_mat3(P.enc.m, x, y, z);  // (M1 * to_xyz, folded by the entry point: colorops.cuh)
   x = cbrt_signed2(x); y = cbrt_signed2(y); z = cbrt_signed2(z);
   f2_mat3(c_color.ok_m2, x, y, z);
   // requant8: the staged UInt8x4 register
@@ -189,8 +188,7 @@ __device__ __forceinline__ void pixel2_oklab(const LabParams& P, uint32_t w0, ui
   // oklab_dec
   f2_mat3(c_color.ok_m2i, x, y, z);
   x = f2_mul(f2_mul(x, x), x); y = f2_mul(f2_mul(y, y), y); z = f2_mul(f2_mul(z, z), z);
-  f2_mat3(c_color.ok_m1i, x, y, z);
-  f2_mat3(P.dec.m, x, y, z);
+  f2_mat3(P.dec.m, x, y, z);  // (from_xyz * M1^-1)
   const float v0[3] = {clamp01(f2_lo(x)), clamp01(f2_lo(y)), clamp01(f2_lo(z))}, v1[3] = {clamp01(f2_hi(x)), clamp01(f2_hi(y)), clamp01(f2_hi(z))};
   uint32_t t1, t2, u1, u2;
   if (SRGB_DST) {

@@ -185,6 +185,22 @@ zos_status make_dev_image(zos_ctx* ctx, const zos_image* img, DevImage* out, con
   return ZOS_OK;
 }
 
+// The kernels' form of the Oklab steps (colorops.cuh): the caller's xyz_transform folded with the constant M1 / M1^-1, in double.
+void fold_steps(zos_step* steps, uint32_t n) {
+  static const double m1[9] = {0.8189330101f, 0.3618667424f, -0.1288597137f, 0.0329845436f, 0.9293118715f,
+                               0.0361456387f, 0.0482003018f, 0.2643662691f, 0.6338517070f};  // the float constants of build_constants, widened
+  static double m1i[9];
+  static bool have = false;
+  if (!have) { inv3_d(m1, m1i); have = true; }
+  for (uint32_t i = 0; i < n; i++) {
+    if (steps[i].kind != ZOS_STEP_OKLAB_ENC && steps[i].kind != ZOS_STEP_OKLAB_DEC) continue;
+    double m[9], o[9];
+    for (int k = 0; k < 9; k++) m[k] = (double)steps[i].m[k];
+    if (steps[i].kind == ZOS_STEP_OKLAB_ENC) mul3_d(m1, m, o); else mul3_d(m, m1i, o);
+    for (int k = 0; k < 9; k++) steps[i].m[k] = (float)o[k];
+  }
+}
+
 zos_status validate_steps(zos_ctx* ctx, const zos_step* steps, uint32_t n) {
   if (n > ZOS_MAX_STEPS) return fail(ctx, ZOS_ERR_INVALID, "too many steps (%u > %d)", n, ZOS_MAX_STEPS);
   if (n && !steps) return fail(ctx, ZOS_ERR_INVALID, "null steps");
@@ -513,6 +529,10 @@ zos_status zos_pixel_chain(zos_ctx* ctx, const zos_image* src, const zos_image* 
   if ((st = make_dev_image(ctx, src, &s, "src")) != ZOS_OK) return st;
   if ((st = make_dev_image(ctx, dst, &d, "dst")) != ZOS_OK) return st;
   if ((st = validate_steps(ctx, steps, nsteps)) != ZOS_OK) return st;
+  zos_step folded[ZOS_MAX_STEPS];
+  for (uint32_t i = 0; i < nsteps; i++) folded[i] = steps[i];
+  fold_steps(folded, nsteps);
+  steps = folded;
   if (s.w != d.w || s.h != d.h) return fail(ctx, ZOS_ERR_TYPE, "pixel_chain: size mismatch %dx%d vs %dx%d", s.w, s.h, d.w, d.h);
   if (batch == 0) return ZOS_OK;
   cudaSetDevice(ctx->device);
@@ -543,6 +563,10 @@ zos_status zos_compose(zos_ctx* ctx, const zos_image* below, const zos_image* ab
   if ((st = make_dev_image(ctx, dst, &d, "dst")) != ZOS_OK) return st;
   if ((st = validate_steps(ctx, cp->src_steps, cp->n_src_steps)) != ZOS_OK) return st;
   if ((st = validate_steps(ctx, cp->dst_steps, cp->n_dst_steps)) != ZOS_OK) return st;
+  zos_compose_params folded = *cp;
+  fold_steps(folded.src_steps, folded.n_src_steps);
+  fold_steps(folded.dst_steps, folded.n_dst_steps);
+  cp = &folded;
   if (below && (b.w != d.w || b.h != d.h)) return fail(ctx, ZOS_ERR_TYPE, "compose: `below` and dst differ in size");
   if (cp->map < ZOS_MAP_RECT || cp->map > ZOS_MAP_SCALE) return fail(ctx, ZOS_ERR_INVALID, "compose: bad map %d", cp->map);
   if (cp->sampling != ZOS_SAMPLE_NEAREST && cp->sampling != ZOS_SAMPLE_BILINEAR) return fail(ctx, ZOS_ERR_INVALID, "compose: bad sampling");
