@@ -881,7 +881,9 @@ def loop_rs(rig):
         pool.clear_cache()
     best = max(out["pinned_host"]["fps"], out["pageable_host"]["fps"])
     out.update({"value": best, "unit": "fps", "reference_published": "around 240 fps (tests/loop.rs:85, author's machine, 2021, hardware unstated)",
-                "mp_per_s": round(best * 512 * 512 / 1e6, 1)})
+                "mp_per_s": round(best * 512 * 512 / 1e6, 1),
+                "vs_baseline": round(best / rig.world / 240.0, 1),  # per GPU, against the one number BASELINE.md holds (other, unstated hardware)
+                "note": "per iteration: Executable.from_pool, bind x2, bind_output, launch, step().block_on(), Retire.output (read-back into a pool host image), finish"})
     return out
 
 
