@@ -117,6 +117,10 @@ zos_status zos_sync(zos_ctx* ctx);             /* SyncPoint::block_on, run.rs:30
  * encoder (thr[k] = smallest f32 whose code is >= k; [0] = -inf, [256..259] = +inf) and the two bucket tables
  * the kernels derive from them (zosimos_b200/csrc/texel.cuh).  Arrays may be NULL; buckets holds up to 2048
  * entries.  The reference leaves this encode to the texture unit (program.rs:794-838). */
+/* Host-only view of how k_affine_f16 sizes its staged source box (affine_f16.cu: the width, in texels, whose rows put the
+ * taps of a 32-lane row on the fewest shared-memory bank conflicts for a source step of (step_x, step_y) texels per lane);
+ * -1 for a width outside [2, 256].  For verification without a GPU. */
+int32_t zos_affine_box_width(int32_t min_width, float step_x_per_lane, float step_y_per_lane);
 zos_status zos_srgb_encoder_tables(float* thresholds260, uint32_t* buckets, uint32_t* n_buckets, uint32_t* buckets2, uint32_t* n_buckets2);
 uint64_t zos_ctx_launch_count(const zos_ctx* ctx); /* kernels launched so far (bench: gpu_launches) */
 /* debugging / parity switches; ZOS_CTX_NO_FAST_PATHS routes every launch through the generic kernels */

@@ -836,3 +836,41 @@ def test_normal2d_constructors_match_the_reference_values():
     assert np.frombuffer(d.into_std430(), np.float32)[6] == np.float32(d.params[6])
     g = DistributionNormal2d.with_diagonal(0.2, 0.2)
     assert np.allclose(g.params, O.normal2d_with_diagonal(0.2, 0.2), rtol=1e-6, atol=0)
+
+
+def test_affine_box_width_minimises_modelled_bank_conflicts():
+    """k_affine_f16 sizes its staged source box so that the taps of a 32-lane row meet as few shared-memory bank conflicts as possible
+    (affine_f16.cu pick_box_width, host code).  An independent model of the banks -- LDS.64, 16 lanes per wavefront, bank pair =
+    (column + row * width) mod 16, distinct addresses on one bank pair serialise -- must agree that the chosen width is the cheapest of
+    the candidates, and the choice must repair the rotation the fixed round-1 rule (width = 2 mod 4) handled worst."""
+    import math
+
+    def cost(width, dx, dy):
+        total = 0
+        for ph in range(16):
+            x0, y0 = 64.0 + 0.25 * (ph & 3) + 0.125, 64.0 + 0.25 * (ph >> 2) + 0.125
+            for tap in range(4):
+                for half in range(2):
+                    addr = []
+                    for l in range(16):
+                        i = half * 16 + l
+                        X = math.floor(np.float32(x0) + np.float32(i) * np.float32(dx) - np.float32(0.5)) + (tap & 1)
+                        Y = math.floor(np.float32(y0) + np.float32(i) * np.float32(dy) - np.float32(0.5)) + (tap >> 1)
+                        addr.append(Y * width + X)
+                    total += max(len({a for a in addr if a % 16 == b}) for b in range(16))
+        return total
+
+    lib = _ffi.lib()
+    assert lib.zos_affine_box_width(0, 1.0, 0.0) == -1 and lib.zos_affine_box_width(300, 1.0, 0.0) == -1
+    for deg in (30.0, -30.0, 17.0, 45.0, 5.0, 90.0, 133.0):
+        c, s = math.cos(math.radians(deg)), math.sin(math.radians(deg))
+        min_w = int(math.ceil(31 * (abs(c) + abs(s)))) + 5
+        min_w += min_w & 1
+        w = lib.zos_affine_box_width(min_w, c, s)
+        cands = list(range(min_w, min_w + 16, 2))
+        costs = {k: cost(k, c, s) for k in cands}
+        assert w in cands and costs[w] == min(costs.values()), (deg, w, costs)
+        assert w == min(k for k in cands if costs[k] == costs[w])  # ties: the narrowest
+    # -30 degrees: the round-1 width (50) put 16 lanes on 2-3 bank pairs
+    w = lib.zos_affine_box_width(48, math.cos(math.radians(-30.0)), math.sin(math.radians(-30.0)))
+    assert cost(50, 0.8660254, -0.5) > 2.5 * cost(w, 0.8660254, -0.5)

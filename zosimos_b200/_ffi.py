@@ -141,6 +141,7 @@ SIGNATURES = {
     "zos_program_launch": (C.c_int32, [_P]),
     "zos_program_step": (C.c_int32, [_P, C.c_uint32, C.POINTER(C.c_int32)]),
     "zos_program_kernel_count": (C.c_uint32, [_P]),
+    "zos_affine_box_width": (C.c_int32, [C.c_int32, C.c_float, C.c_float]),
     "zos_srgb_encoder_tables": (C.c_int32, [C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "zos_dynamic_create": (C.c_int32, [_P, C.c_char_p, C.POINTER(_P)]),
     "zos_dynamic_launch": (C.c_int32, [_P, _P, C.POINTER(ZosImage), C.POINTER(ZosImage), C.POINTER(ZosImage), C.c_void_p, C.c_uint64]),

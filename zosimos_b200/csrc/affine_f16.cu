@@ -288,7 +288,7 @@ __device__ __forceinline__ void compute_rows(const AffParams& P, const Geo& g, c
 // unit: profiles/r02_kernel_facts.md).  So the launcher simulates the four taps of a row of 32 lanes on a lattice of
 // sub-texel phases for the 8 even widths from the minimum up, and takes the cheapest (ties: the narrowest, every extra
 // column is fetched by the TMA unit).
-static int pick_box_width(int min_w, float dxl, float dyl) {
+int pick_box_width(int min_w, float dxl, float dyl) {
   int best_w = min_w;
   long best = -1;
   for (int w = min_w; w < min_w + 16; w += 2) {
@@ -639,3 +639,9 @@ zos_status launch_affine_f16(zos_ctx* ctx, const DevImage* below, const DevImage
 }
 
 }  // namespace zos
+
+// Host-only view of the staged-box width rule (no device needed): tests compare it with an independent model of the banks.
+extern "C" int32_t zos_affine_box_width(int32_t min_width, float step_x_per_lane, float step_y_per_lane) {
+  if (min_width < 2 || min_width > 256) return -1;
+  return zos::pick_box_width(min_width + (min_width & 1), step_x_per_lane, step_y_per_lane);
+}

@@ -44,7 +44,8 @@ constexpr uint32_t ENC_KEY0 = (uint32_t)ZOS_ENC2_K0 * ROW;           // (bits(y)
 // The table's shared address is a COMPILE-TIME constant, so that it costs no instruction: it is the immediate offset of
 // every look-up (the compiler kept the base in a uniform register for the blend variant but spent one add per look-up, 6 per
 // pixel, in the convert variants).  Dynamic shared memory starts at 0x400 on sm_100 (1 KB is reserved in front of it) when a
-// kernel has no static shared memory; the kernel checks that and traps if the layout is ever different.
+// kernel has no static shared memory; the kernel checks that and, if the layout is ever different, writes nothing and raises
+// the context's fault word (zos_sync then fails with ZOS_ERR_CUDA) -- it does not trap, the context stays usable.
 // (Measured dead end: placing the table at the next multiple of 64 KB instead, so that the base folds into the byte permute,
 // needs 63 KB of padding -- the larger carve-out leaves the L1 too small to keep the streaming loads in flight and the
 // kernel lost 15 %.)
@@ -190,7 +191,10 @@ template <int SK, int DK, int MODE, int NMAT, bool LINEAR>
 __global__ void __launch_bounds__(LUT_THREADS, 1) k_rowwise_lut(const __grid_constant__ FastParams P) {
   extern __shared__ __align__(256) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
-  if ((uint32_t)__cvta_generic_to_shared(smem_raw) != TABLE_AT) __trap();
+  if ((uint32_t)__cvta_generic_to_shared(smem_raw) != TABLE_AT) {  // not the layout the look-up immediates were built for: report, do not compute
+    if (threadIdx.x == 0 && P.fault) *reinterpret_cast<volatile int*>(P.fault) = 2;
+    return;
+  }
   // Table fill, the fixed cost of a launch (it dominates for small images): 16-byte stores, a warp writes 512
   // contiguous bytes per instruction, all (L2-resident) source loads of a thread are independent.
 #pragma unroll

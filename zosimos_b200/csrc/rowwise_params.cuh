@@ -24,6 +24,7 @@ struct FastParams {
   float m[2][9];
   uint32_t groups_per_row, total_groups;
   FastDiv div_gpr, div_h;
+  int* fault;  // mapped host word (zos_ctx::fault_dev): a kernel that cannot run as built sets it and returns; zos_sync reports it
 };
 
 __device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv& f) {

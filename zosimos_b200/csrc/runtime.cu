@@ -389,7 +389,9 @@ zos_status zos_sync(zos_ctx* ctx) {
   if (!ctx) return ZOS_ERR_INVALID;
   zos_status st = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
   if (st == ZOS_OK && ctx->fault_host && *ctx->fault_host) {
+    const int what = *ctx->fault_host;
     *ctx->fault_host = 0;
+    if (what == 2) return zos::fail(ctx, ZOS_ERR_CUDA, "a table kernel found its shared memory at an unexpected address and did not run: results of this launch are missing");
     return zos::fail(ctx, ZOS_ERR_CUDA, "a TMA wait timed out inside a kernel: results of this launch are incomplete");
   }
   return st;
