@@ -124,7 +124,8 @@ int32_t zos_affine_box_width(int32_t min_width, float step_x_per_lane, float ste
 zos_status zos_srgb_encoder_tables(float* thresholds260, uint32_t* buckets, uint32_t* n_buckets, uint32_t* buckets2, uint32_t* n_buckets2);
 uint64_t zos_ctx_launch_count(const zos_ctx* ctx); /* kernels launched so far (bench: gpu_launches) */
 /* debugging / parity switches; ZOS_CTX_NO_FAST_PATHS routes every launch through the generic kernels */
-enum { ZOS_CTX_NO_FAST_PATHS = 1 };
+enum { ZOS_CTX_NO_FAST_PATHS = 1,
+       ZOS_CTX_FRAME_FAST_ONLY = 2 /* frame pipeline: the one-role kernel (k_frame_fast) instead of the warp-specialised one: A/B and parity */ };
 zos_status zos_ctx_set_flags(zos_ctx* ctx, uint32_t flags);
 
 /* Device memory comes from a per-context arena of size-class free lists: zos_buf_free parks the block instead of

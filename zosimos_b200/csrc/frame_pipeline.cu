@@ -546,6 +546,249 @@ __global__ void __launch_bounds__(THREADS, 4) k_frame_fast(const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_frame_spec (round 2): k_frame_fast with the two phases on DIFFERENT warps.  In k_frame_fast every warp converts, waits at a
+// CTA barrier, samples, waits again; 676 conversion blocks over 256 threads are 2.64 passes, so two of eight warps idle through
+// the third, and ncu has 1.7 warps per issue stalled at the barrier with 70 % of the issue slots used
+// (profiles/r02_c4_fused_kernel_packed.txt).  Here 8 conversion warps and 4 sampling warps (the phases are 2 : 1 by
+// instruction count) pass footprint tiles through TWO buffers with full / empty mbarriers: conversion of tile j + 1 runs while
+// tile j is sampled, nobody waits for the slowest warp of the other phase, and a warp that finished its share of a tile goes
+// on to the next one.  The first lane of the first sampling warp also is the TMA producer: when the footprint of tile j is
+// complete its YUV stage is free, so it works out the geometry of tile j + 2 and issues the loads.  Same arithmetic, same
+// bytes as k_frame_fast (the phase bodies are the same code).
+#ifndef ZOS_SPEC_CW
+#define ZOS_SPEC_CW 8
+#define ZOS_SPEC_SW 4
+#define ZOS_SPEC_CTAS 2
+#endif
+constexpr int SPEC_CW = ZOS_SPEC_CW, SPEC_SW = ZOS_SPEC_SW, SPEC_CTAS = ZOS_SPEC_CTAS;  // conversion / sampling warps of a CTA, CTAs per SM
+constexpr int SPEC_C = SPEC_CW * 32, SPEC_THREADS = (SPEC_CW + SPEC_SW) * 32;
+
+#define ZOS_SPEC_WAIT(BAR, PARITY)                                                                  \
+  {                                                                                                 \
+    uint32_t spins_ = 0;                                                                            \
+    while (!mbar_try_wait_sleep((BAR), (PARITY), 2000u)) {                                          \
+      if (++spins_ > (1u << 22)) { if (P.fault) *reinterpret_cast<volatile int*>(P.fault) = 1; break; } \
+    }                                                                                               \
+  }
+
+template <bool BILINEAR, bool SRGB_DST, int TRK>
+__global__ void __launch_bounds__(SPEC_THREADS, SPEC_CTAS) k_frame_spec(const __grid_constant__ FrameParams P, const __grid_constant__ TensorMaps M) {
+  extern __shared__ __align__(128) uint8_t dyn[];
+  __shared__ __align__(8) uint64_t bar_yuv[2], bar_full[2], bar_empty[2];
+  __shared__ TileGeo geo[4];
+  __shared__ __align__(16) uint4 ctab[2][TILE], rtab[2][TILE];  // per footprint buffer: {offset of tap a, offset of tap b, weight, -}
+  const uint32_t cstep = P.nv12 ? 2 : 1;
+  const uint32_t ybox = (uint32_t)P.box_w * P.box_h, cbox = (uint32_t)P.cbox_w * P.cbox_h * cstep;
+  const uint32_t ybox_al = (ybox + 127) & ~127u, cbox_al = (cbox + 127) & ~127u;
+  const uint32_t nchroma = P.nv12 ? 1 : 2;
+  const uint32_t stage_bytes = ybox_al + nchroma * cbox_al;
+  const uint32_t conv_bytes = 3u * P.plane_bytes;
+  uint32_t* enc = reinterpret_cast<uint32_t*>(dyn + 2 * (size_t)stage_bytes + 2 * (size_t)conv_bytes);
+  if (SRGB_DST) {
+    for (int i = threadIdx.x; i < ZOS_ENC2_N * FER; i += SPEC_THREADS) enc[i] = g_tables.srgb_enc2[i / FER];
+  }
+  const uint32_t enc_lane = smem_u32(enc) + (threadIdx.x & (FER - 1)) * 4u;
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 2; k++) { mbar_init(&bar_yuv[k], 1); mbar_init(&bar_full[k], SPEC_CW); mbar_init(&bar_empty[k], SPEC_SW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const CUtensorMap* const m0 = &M.m0;
+  const CUtensorMap* const m1 = &M.m1;
+  const CUtensorMap* const m2 = &M.m2;
+  const uint32_t ntiles = blockIdx.x < P.total_tiles ? (P.total_tiles - 1u - blockIdx.x) / gridDim.x + 1u : 0u;  // tiles of this CTA: blockIdx.x + j * gridDim.x
+  // geometry + loads of tile J into YUV stage J & 1; a tile the frame does not touch completes its barrier without a load
+#define ZOS_SPEC_ISSUE(J)                                                                                   \
+  do {                                                                                                      \
+    TileGeo g_;                                                                                             \
+    tile_geometry(P, blockIdx.x + (J) * gridDim.x, g_);                                                     \
+    geo[(J) & 3u] = g_;                                                                                     \
+    uint64_t* bar_ = &bar_yuv[(J) & 1u];                                                                    \
+    if (g_.any) {                                                                                           \
+      uint8_t* base_ = dyn + (size_t)((J) & 1u) * stage_bytes;                                              \
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                                        \
+      mbar_expect_tx(bar_, ybox + nchroma * cbox);                                                          \
+      tma_load_3d(base_, m0, g_.bx, g_.by, g_.frame, bar_);                                                 \
+      tma_load_3d(base_ + ybox_al, m1, g_.bx >> 1, g_.by >> 1, g_.frame, bar_);                             \
+      if (nchroma == 2) tma_load_3d(base_ + ybox_al + cbox_al, m2, g_.bx >> 1, g_.by >> 1, g_.frame, bar_); \
+    } else {                                                                                                \
+      mbar_arrive(bar_);                                                                                    \
+    }                                                                                                       \
+  } while (0)
+  const uint32_t cw4 = (uint32_t)P.conv_w * 4u;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x < SPEC_C) {
+    // ================= conversion warps: YUV stage j & 1 -> footprint buffer j & 1
+    const int tC = (int)threadIdx.x;
+    for (uint32_t j = 0; j < ntiles; j++) {
+      const uint32_t b = j & 1u, s = j & 1u;
+      ZOS_SPEC_WAIT(&bar_yuv[s], (j >> 1) & 1u)                       // geometry published, planes landed
+      if (j >= 2) ZOS_SPEC_WAIT(&bar_empty[b], ((j - 2u) >> 1) & 1u)  // the sampling warps are done with this buffer (tile j - 2)
+      const TileGeo g = geo[j & 3u];
+      const uint32_t conv_base = smem_u32(dyn + 2 * (size_t)stage_bytes + (size_t)b * conv_bytes);
+      if (g.any) {
+      if (BILINEAR && g.full && tC < 2 * TILE) {
+        // the arithmetic of the per-pixel path below, once per column (threads 0..31) and per row (32..63)
+        const bool col = tC < TILE;
+        const int q = col ? tC : tC - TILE;
+        const int kq = (col ? g.x0 - P.tgt[0] : g.y0 - P.tgt[1]) + q;
+        const float p = (float)(col ? P.sel[0] : P.sel[1]) + ((float)kq + 0.5f) * (col ? P.rx : P.ry);
+        const float f = p - 0.5f, f0 = floorf(f);
+        const int i0 = (int)f0, lim = (col ? P.sw : P.sh) - 1, org = col ? g.fx0 : g.fy0;
+        const uint32_t unit = col ? 4u : cw4;
+        const uint4 e = make_uint4((uint32_t)(min(max(i0, 0), lim) - org) * unit, (uint32_t)(min(max(i0 + 1, 0), lim) - org) * unit,
+                                   __float_as_uint(f - f0), 0u);
+        if (col) ctab[b][q] = e; else rtab[b][q] = e;
+      }
+      const uint32_t ybase = smem_u32(dyn + (size_t)s * stage_bytes);
+      const uint32_t ubase = ybase + ybox_al, vbase = P.nv12 ? ubase + 1 : ubase + cbox_al;
+      const int offx = g.fx0 - g.bx, offy = g.fy0 - g.by;  // both even
+      const int cbw = P.conv_w >> 1, cbh = P.conv_h >> 1;
+      // (2x2 blocks are numbered row-major and dealt to the threads round robin: all lanes busy)
+      for (uint32_t blk = (uint32_t)tC; blk < (uint32_t)(cbw * cbh); blk += SPEC_C) {
+        const int byi = (int)fastdiv(blk, P.div_cbw), bxi = (int)blk - byi * cbw;
+        const uint32_t ya = ybase + (uint32_t)((offy + 2 * byi) * P.box_w + offx + 2 * bxi);
+        const uint32_t ca = (uint32_t)(((offy >> 1) + byi) * P.cbox_w + (offx >> 1) + bxi) * cstep;
+        uint32_t y01, y23, u8, v8;
+        asm("ld.shared.u16 %0, [%1];" : "=r"(y01) : "r"(ya));
+        asm("ld.shared.u16 %0, [%1];" : "=r"(y23) : "r"(ya + (uint32_t)P.box_w));
+        asm("ld.shared.u8 %0, [%1];" : "=r"(u8) : "r"(ubase + ca));
+        asm("ld.shared.u8 %0, [%1];" : "=r"(v8) : "r"(vbase + ca));
+        const float cb = ((float)u8 - 128.0f) * P.csc, cr = ((float)v8 - 128.0f) * P.csc;
+        const uint32_t o = conv_base + (uint32_t)((2 * byi) * P.conv_w + 2 * bxi) * 4u;
+        F2 r0, g0, b0, r1, g1, b1;  // the block's upper and lower pair of texels
+        convert_rgb2<TRK>(P, y01, cb, cr, r0, g0, b0);
+        convert_rgb2<TRK>(P, y23, cb, cr, r1, g1, b1);
+        sts64(o, r0); sts64(o + P.plane_bytes, g0); sts64(o + 2u * P.plane_bytes, b0);
+        sts64(o + cw4, r1); sts64(o + cw4 + P.plane_bytes, g1); sts64(o + cw4 + 2u * P.plane_bytes, b1);
+      }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_full[b]);
+    }
+  } else {
+    // ================= sampling warps (+ the TMA producer): footprint buffer j & 1 -> destination tile
+    const int tS = (int)threadIdx.x - SPEC_C;
+    const int lx = tS & 31, ly = tS >> 5;
+    if (tS == 0) {
+      if (ntiles > 0) ZOS_SPEC_ISSUE(0u);
+      if (ntiles > 1) ZOS_SPEC_ISSUE(1u);
+    }
+    for (uint32_t j = 0; j < ntiles; j++) {
+      const uint32_t b = j & 1u;
+      ZOS_SPEC_WAIT(&bar_full[b], (j >> 1) & 1u)  // every conversion warp finished tile j: its footprint is complete, its YUV stage free
+      if (tS == 0 && j + 2u < ntiles) ZOS_SPEC_ISSUE(j + 2u);
+      const TileGeo g = geo[j & 3u];
+      const uint32_t conv_base = smem_u32(dyn + 2 * (size_t)stage_bytes + (size_t)b * conv_bytes);
+    const int i = g.x0 + lx;
+    if (BILINEAR && g.full) {
+      // straight path: no coverage tests, no `below`; a pixel is 12 loads at column + row offsets, 3 lerps, 3 encodes
+      const uint4 ct = ctab[b][lx];
+      const float ax = __uint_as_float(ct.z);
+      const uint32_t ca = conv_base + ct.x, cb = conv_base + ct.y;
+      uint8_t* dp = P.dst + ((uint64_t)g.frame * P.dst_bstride + (uint64_t)(g.y0 + ly) * P.dst_pitch + (uint64_t)i * 4u);
+      const uint64_t dstep = (uint64_t)SPEC_SW * P.dst_pitch;
+#pragma unroll
+      for (int k = 0; k < TILE / SPEC_SW; k += 2) {  // two of the thread's eight rows at a time: the lerps are packed
+        const uint4 rt0 = rtab[b][ly + SPEC_SW * k], rt1 = rtab[b][ly + SPEC_SW * (k + 1)];
+        const F2 ay = f2(__uint_as_float(rt0.z), __uint_as_float(rt1.z)), axx = f2(ax);
+        const uint32_t a00 = ca + rt0.x, a10 = cb + rt0.x, a01 = ca + rt0.y, a11 = cb + rt0.y;
+        const uint32_t c00 = ca + rt1.x, c10 = cb + rt1.x, c01 = ca + rt1.y, c11 = cb + rt1.y;
+        F2 r, gg, b;
+#define ZOS_TAP(dst_, off_) { const F2 p00 = f2(lds32(a00 + (off_)), lds32(c00 + (off_))), p10 = f2(lds32(a10 + (off_)), lds32(c10 + (off_))); \
+                              const F2 p01 = f2(lds32(a01 + (off_)), lds32(c01 + (off_))), p11 = f2(lds32(a11 + (off_)), lds32(c11 + (off_))); \
+                              const F2 top = f2_fma(axx, f2_sub(p10, p00), p00), bot = f2_fma(axx, f2_sub(p11, p01), p01); dst_ = f2_fma(ay, f2_sub(bot, top), top); }
+        ZOS_TAP(r, 0u) ZOS_TAP(gg, P.plane_bytes) ZOS_TAP(b, 2u * P.plane_bytes)
+#undef ZOS_TAP
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const float rr = fminf(fmaxf(h ? f2_hi(r) : f2_lo(r), 0.0f), 1.0f), g1 = fminf(fmaxf(h ? f2_hi(gg) : f2_lo(gg), 0.0f), 1.0f),
+                      bb = fminf(fmaxf(h ? f2_hi(b) : f2_lo(b), 0.0f), 1.0f);
+          uint32_t t1, t2;
+          if (SRGB_DST) {
+            t1 = __byte_perm(srgb_code_b3(rr, enc_lane), srgb_code_b3(g1, enc_lane), 0x0073);
+            t2 = __byte_perm(srgb_code_b3(bb, enc_lane), 0xffu, 0x0043);
+          } else {
+            t1 = __byte_perm(__float_as_uint(rr * 255.0f + 8388608.0f), __float_as_uint(g1 * 255.0f + 8388608.0f), 0x0040);
+            t2 = __byte_perm(__float_as_uint(bb * 255.0f + 8388608.0f), 0xffu, 0x0040);
+          }
+          __stcs(reinterpret_cast<uint32_t*>(dp + (uint64_t)(k + h) * dstep), __byte_perm(t1, t2, P.spack));
+        }
+      }
+    } else if (i < P.dw) {
+      const int kx = i - P.tgt[0];
+      const bool col_in = g.any && kx >= 0 && kx < P.tgt[2];
+      uint32_t xa4 = 0, xb4 = 0;  // byte offsets of the horizontal taps inside a footprint row
+      float ax = 0.0f;
+      if (col_in) {
+        int xa, xb;
+        if (!BILINEAR) {
+          xa = xb = min(max(P.sel[0] + rect_index(kx, P.sel[2], P.tgt[2]), 0), P.sw - 1);
+        } else {
+          const float px = (float)P.sel[0] + ((float)kx + 0.5f) * P.rx;
+          const float fx = px - 0.5f, x0f = floorf(fx);
+          ax = fx - x0f;
+          const int x0 = (int)x0f;
+          xb = min(max(x0 + 1, 0), P.sw - 1);
+          xa = min(max(x0, 0), P.sw - 1);
+        }
+        xa4 = (uint32_t)(xa - g.fx0) * 4u; xb4 = (uint32_t)(xb - g.fx0) * 4u;
+      }
+      const uint64_t off0 = (uint64_t)g.frame * P.dst_bstride + (uint64_t)(g.y0 + ly) * P.dst_pitch + (uint64_t)i * 4u;
+      const uint64_t boff0 = (uint64_t)g.frame * P.below_bstride + (uint64_t)(g.y0 + ly) * P.below_pitch + (uint64_t)i * 4u;
+#pragma unroll
+      for (int k = 0; k < TILE / SPEC_SW; k++) {
+        const int j = g.y0 + ly + SPEC_SW * k;
+        if (j < P.dh) {
+          const int ky = j - P.tgt[1];
+          const bool covered = col_in && ky >= 0 && ky < P.tgt[3];
+          uint32_t word = P.clear_word;
+          if (covered) {
+            float r, gg, b;
+            if (!BILINEAR) {
+              const int w = min(max(P.sel[1] + rect_index(ky, P.sel[3], P.tgt[3]), 0), P.sh - 1) - g.fy0;
+              const uint32_t a = conv_base + (uint32_t)w * cw4 + xa4;
+              r = lds32(a); gg = lds32(a + P.plane_bytes); b = lds32(a + 2u * P.plane_bytes);
+            } else {
+              const float py = (float)P.sel[1] + ((float)ky + 0.5f) * P.ry;
+              const float fy = py - 0.5f, y0f = floorf(fy);
+              const float ay = fy - y0f;
+              const int y0 = (int)y0f;
+              const int yb = min(max(y0 + 1, 0), P.sh - 1) - g.fy0, ya = min(max(y0, 0), P.sh - 1) - g.fy0;
+              const uint32_t ra = conv_base + (uint32_t)ya * cw4, rb = conv_base + (uint32_t)yb * cw4;
+              const uint32_t a00 = ra + xa4, a10 = ra + xb4, a01 = rb + xa4, a11 = rb + xb4;
+#define ZOS_TAP(dst_, off_) { const float p00 = lds32(a00 + (off_)), p10 = lds32(a10 + (off_)), p01 = lds32(a01 + (off_)), p11 = lds32(a11 + (off_)); \
+                              const float top = fmaf(ax, p10 - p00, p00), bot = fmaf(ax, p11 - p01, p01); dst_ = fmaf(ay, bot - top, top); }
+              ZOS_TAP(r, 0u) ZOS_TAP(gg, P.plane_bytes) ZOS_TAP(b, 2u * P.plane_bytes)
+#undef ZOS_TAP
+            }
+            // alpha of the frame is exactly 1: source-over == the frame's colour, alpha code 255
+            r = fminf(fmaxf(r, 0.0f), 1.0f); gg = fminf(fmaxf(gg, 0.0f), 1.0f); b = fminf(fmaxf(b, 0.0f), 1.0f);
+            uint32_t t1, t2;
+            if (SRGB_DST) {
+              t1 = __byte_perm(srgb_code_b3(r, enc_lane), srgb_code_b3(gg, enc_lane), 0x0073);
+              t2 = __byte_perm(srgb_code_b3(b, enc_lane), 0xffu, 0x0043);
+            } else {
+              t1 = __byte_perm(__float_as_uint(r * 255.0f + 8388608.0f), __float_as_uint(gg * 255.0f + 8388608.0f), 0x0040);
+              t2 = __byte_perm(__float_as_uint(b * 255.0f + 8388608.0f), 0xffu, 0x0040);
+            }
+            word = __byte_perm(t1, t2, P.spack);
+          } else if (P.has_below) {
+            word = __ldcs(reinterpret_cast<const uint32_t*>(P.below + boff0 + (uint64_t)(SPEC_SW * k) * P.below_pitch));
+          }
+          __stcs(reinterpret_cast<uint32_t*>(P.dst + off0 + (uint64_t)(SPEC_SW * k) * P.dst_pitch), word);
+        }
+      }
+    }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_empty[b]);
+    }
+  }
+#undef ZOS_SPEC_ISSUE
+}
+#undef ZOS_SPEC_WAIT
+
 bool native8(const DevImage& im) {
   return im.block == ZOS_BLOCK_PIXEL && im.bpp == 4 && (im.fmt.storage == ZOS_STORAGE_SRGB8 || im.fmt.storage == ZOS_STORAGE_UNORM8) &&
          ((uintptr_t)im.p0 % 4) == 0 && (im.pitch % 4) == 0 && (im.bstride % 4) == 0;
@@ -641,6 +884,23 @@ zos_status launch_frame_pipeline(zos_ctx* ctx, const DevImage* below, const DevI
     if (ok2 && !P.nv12)
       ok2 = make_map(ctx, &M.m1, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, above.p1, cw, ch, above.cpitch, batch, above.cbstride, P.cbox_w, P.cbox_h) &&
             make_map(ctx, &M.m2, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, above.p2, cw, ch, above.cpitch, batch, above.cbstride, P.cbox_w, P.cbox_h);
+    const size_t ssmem = 2 * stage + 6 * (size_t)P.plane_bytes + (srgb ? (size_t)ZOS_ENC2_N * FER * 4 : 0);  // k_frame_spec: two footprint buffers
+    if (ok2 && ssmem <= 110 * 1024 && !(ctx->flags & ZOS_CTX_FRAME_FAST_ONLY)) {
+      const uint64_t cap = (uint64_t)ctx->sm_count * SPEC_CTAS;
+      const int grid = (int)(total < cap ? total : cap);
+      const bool bil = cp.sampling != ZOS_SAMPLE_NEAREST;
+#define ZOS_FS(B, S, T)                                                                                          \
+  do {                                                                                                            \
+    ensure_dyn_smem(ctx, k_frame_spec<B, S, T>, 110 * 1024);                                                        \
+    k_frame_spec<B, S, T><<<grid, SPEC_THREADS, ssmem, ctx->stream>>>(P, M);                                       \
+  } while (0)
+      if (trk == 0) { if (bil) { if (srgb) ZOS_FS(true, true, 0); else ZOS_FS(true, false, 0); } else { if (srgb) ZOS_FS(false, true, 0); else ZOS_FS(false, false, 0); } }
+      else { if (bil) { if (srgb) ZOS_FS(true, true, 1); else ZOS_FS(true, false, 1); } else { if (srgb) ZOS_FS(false, true, 1); else ZOS_FS(false, false, 1); } }
+#undef ZOS_FS
+      ctx->launches++;
+      *handled = true;
+      return check_cuda(ctx, cudaGetLastError(), "k_frame_spec launch");
+    }
     if (ok2 && fsmem <= 160 * 1024) {
       int per_sm = (int)((226 * 1024) / (fsmem + 1024 + 256));
       per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);

@@ -300,6 +300,7 @@ zos_status zos_ctx_create(int32_t device, zos_ctx** out) {
   if (device < 0 || device >= n) return fail(nullptr, ZOS_ERR_INVALID, "device %d out of range (%d devices)", device, n);
   zos_ctx* ctx = new zos_ctx();
   ctx->device = device;
+  if (const char* f = getenv("ZOS_CTX_FLAGS")) ctx->flags = (uint32_t)strtoul(f, nullptr, 0);  // A/B of kernel variants from outside (profiles/)
   zos_status st;
   if ((st = check_cuda(ctx, cudaSetDevice(device), "cudaSetDevice")) != ZOS_OK) goto bad;
   {
