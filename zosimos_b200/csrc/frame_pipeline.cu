@@ -56,6 +56,7 @@ struct FrameParams {
   int32_t box_w, box_h, cbox_w, cbox_h, conv_w, conv_h;
   int* fault;  // mapped host word set when an mbarrier wait runs away
   // k_frame_fast
+  int32_t tile_h;       // rows of a destination tile (TILE, or SPEC_TH for k_frame_spec)
   uint32_t clear_word;  // the encoded Target::Discard clear colour (0, 0, 1, 1)
   uint32_t spack;       // byte-permute selector of the destination word (RGBA / BGRA)
   uint32_t plane_bytes; // bytes of one plane of the converted footprint
@@ -80,9 +81,9 @@ __device__ void tile_geometry(const FrameParams& P, uint32_t t, TileGeo& g) {
   uint32_t txi = t - r * P.tiles_x;
   uint32_t fr = fastdiv(r, P.div_ty);
   uint32_t tyi = r - fr * P.tiles_y;
-  g.frame = (int)fr; g.x0 = (int)txi * TILE; g.y0 = (int)tyi * TILE;
+  g.frame = (int)fr; g.x0 = (int)txi * TILE; g.y0 = (int)tyi * P.tile_h;
   g.bx = g.by = g.fx0 = g.fy0 = 0; g.any = 0; g.full = 0;
-  const int x1 = min(g.x0 + TILE, P.dw) - 1, y1 = min(g.y0 + TILE, P.dh) - 1;
+  const int x1 = min(g.x0 + TILE, P.dw) - 1, y1 = min(g.y0 + P.tile_h, P.dh) - 1;
   const int ix0 = max(g.x0, P.tgt[0]), ix1 = min(x1, P.tgt[0] + P.tgt[2] - 1);
   const int iy0 = max(g.y0, P.tgt[1]), iy1 = min(y1, P.tgt[1] + P.tgt[3] - 1);
   if (ix0 > ix1 || iy0 > iy1) return;
@@ -93,7 +94,7 @@ __device__ void tile_geometry(const FrameParams& P, uint32_t t, TileGeo& g) {
   g.bx = g.fx0 & ~31;  // 16-byte aligned TMA source address for the luma AND the (half width) chroma planes
   g.by = g.fy0;
   g.any = 1;
-  g.full = ix0 == g.x0 && iy0 == g.y0 && ix1 == g.x0 + TILE - 1 && iy1 == g.y0 + TILE - 1;
+  g.full = ix0 == g.x0 && iy0 == g.y0 && ix1 == g.x0 + TILE - 1 && iy1 == g.y0 + P.tile_h - 1;
 }
 
 // EOTF of video samples (same code as gather.cu's yuv_eotf)
@@ -563,6 +564,15 @@ __global__ void __launch_bounds__(THREADS, 4) k_frame_fast(const __grid_constant
 #endif
 constexpr int SPEC_CW = ZOS_SPEC_CW, SPEC_SW = ZOS_SPEC_SW, SPEC_CTAS = ZOS_SPEC_CTAS;  // conversion / sampling warps of a CTA, CTAs per SM
 constexpr int SPEC_C = SPEC_CW * 32, SPEC_THREADS = (SPEC_CW + SPEC_SW) * 32;
+// Tile height of this kernel.  Two footprints of a 32 x 32 tile are 85 KB of shared memory per CTA: two CTAs = 24 warps per SM.  Lower
+// tiles fit three CTAs but measured slower (config 4: 32 rows x 2 CTAs 0.131 of the HBM figure, 24 rows x 3 CTAs 0.117, 24 x 2 0.120,
+// 16 x 3 0.106): the per-tile work that does not shrink with the tile (geometry and loads by one thread, tap tables, hand-shakes)
+// and the conversions of the footprint's margin weigh more than the occupancy buys.
+#ifndef ZOS_SPEC_TH
+#define ZOS_SPEC_TH 32
+#endif
+constexpr int SPEC_TH = ZOS_SPEC_TH;
+static_assert(SPEC_TH % (2 * SPEC_SW) == 0 && SPEC_TH <= TILE, "a sampling thread owns an even number of rows");
 
 #define ZOS_SPEC_WAIT(BAR, PARITY)                                                                  \
   {                                                                                                 \
@@ -628,7 +638,7 @@ __global__ void __launch_bounds__(SPEC_THREADS, SPEC_CTAS) k_frame_spec(const __
       const TileGeo g = geo[j & 3u];
       const uint32_t conv_base = smem_u32(dyn + 2 * (size_t)stage_bytes + (size_t)b * conv_bytes);
       if (g.any) {
-      if (BILINEAR && g.full && tC < 2 * TILE) {
+      if (BILINEAR && g.full && tC < TILE + SPEC_TH) {
         // the arithmetic of the per-pixel path below, once per column (threads 0..31) and per row (32..63)
         const bool col = tC < TILE;
         const int q = col ? tC : tC - TILE;
@@ -690,7 +700,7 @@ __global__ void __launch_bounds__(SPEC_THREADS, SPEC_CTAS) k_frame_spec(const __
       uint8_t* dp = P.dst + ((uint64_t)g.frame * P.dst_bstride + (uint64_t)(g.y0 + ly) * P.dst_pitch + (uint64_t)i * 4u);
       const uint64_t dstep = (uint64_t)SPEC_SW * P.dst_pitch;
 #pragma unroll
-      for (int k = 0; k < TILE / SPEC_SW; k += 2) {  // two of the thread's eight rows at a time: the lerps are packed
+      for (int k = 0; k < SPEC_TH / SPEC_SW; k += 2) {  // two of the thread's rows at a time: the lerps are packed
         const uint4 rt0 = rtab[b][ly + SPEC_SW * k], rt1 = rtab[b][ly + SPEC_SW * (k + 1)];
         const F2 ay = f2(__uint_as_float(rt0.z), __uint_as_float(rt1.z)), axx = f2(ax);
         const uint32_t a00 = ca + rt0.x, a10 = cb + rt0.x, a01 = ca + rt0.y, a11 = cb + rt0.y;
@@ -738,7 +748,7 @@ __global__ void __launch_bounds__(SPEC_THREADS, SPEC_CTAS) k_frame_spec(const __
       const uint64_t off0 = (uint64_t)g.frame * P.dst_bstride + (uint64_t)(g.y0 + ly) * P.dst_pitch + (uint64_t)i * 4u;
       const uint64_t boff0 = (uint64_t)g.frame * P.below_bstride + (uint64_t)(g.y0 + ly) * P.below_pitch + (uint64_t)i * 4u;
 #pragma unroll
-      for (int k = 0; k < TILE / SPEC_SW; k++) {
+      for (int k = 0; k < SPEC_TH / SPEC_SW; k++) {
         const int j = g.y0 + ly + SPEC_SW * k;
         if (j < P.dh) {
           const int ky = j - P.tgt[1];
@@ -832,6 +842,7 @@ zos_status launch_frame_pipeline(zos_ctx* ctx, const DevImage* below, const DevI
   P.has_below = below != nullptr;
   if (below) { P.below = below->p0; P.below_pitch = below->pitch; P.below_bstride = below->bstride; P.below_fmt = below->fmt; }
   P.dst = dst.p0; P.dst_pitch = dst.pitch; P.dst_bstride = dst.bstride; P.dst_fmt = dst.fmt; P.dw = dst.w; P.dh = dst.h;
+  P.tile_h = TILE;
   P.tiles_x = (dst.w + TILE - 1) / TILE; P.tiles_y = (dst.h + TILE - 1) / TILE;
   uint64_t total = (uint64_t)P.tiles_x * P.tiles_y * batch;
   if (total == 0 || total >= (1ull << 31)) return ZOS_OK;
@@ -884,22 +895,47 @@ zos_status launch_frame_pipeline(zos_ctx* ctx, const DevImage* below, const DevI
     if (ok2 && !P.nv12)
       ok2 = make_map(ctx, &M.m1, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, above.p1, cw, ch, above.cpitch, batch, above.cbstride, P.cbox_w, P.cbox_h) &&
             make_map(ctx, &M.m2, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, above.p2, cw, ch, above.cpitch, batch, above.cbstride, P.cbox_w, P.cbox_h);
-    const size_t ssmem = 2 * stage + 6 * (size_t)P.plane_bytes + (srgb ? (size_t)ZOS_ENC2_N * FER * 4 : 0);  // k_frame_spec: two footprint buffers
-    if (ok2 && ssmem <= 110 * 1024 && !(ctx->flags & ZOS_CTX_FRAME_FAST_ONLY)) {
-      const uint64_t cap = (uint64_t)ctx->sm_count * SPEC_CTAS;
-      const int grid = (int)(total < cap ? total : cap);
-      const bool bil = cp.sampling != ZOS_SAMPLE_NEAREST;
-#define ZOS_FS(B, S, T)                                                                                          \
+    // ---- k_frame_spec: its own tile height, hence its own footprint, boxes and tensor maps
+    if (!(ctx->flags & ZOS_CTX_FRAME_FAST_ONLY)) {
+      FrameParams S = P;
+      TensorMaps MS;
+      memset(&MS, 0, sizeof MS);
+      S.tile_h = SPEC_TH;
+      S.tiles_y = (dst.h + SPEC_TH - 1) / SPEC_TH;
+      const uint64_t stotal = (uint64_t)S.tiles_x * S.tiles_y * batch;
+      S.div_ty = make_fastdiv(S.tiles_y);
+      S.conv_h = ((int)ceilf((SPEC_TH - 1) * P.ry) + 5) & ~1;
+      S.box_h = S.conv_h;
+      S.cbox_h = S.box_h / 2;
+      const size_t sy = ((size_t)S.box_w * S.box_h + 127) & ~(size_t)127, sc = ((size_t)S.cbox_w * S.cbox_h * cstep + 127) & ~(size_t)127;
+      const size_t sstage = sy + (P.nv12 ? 1 : 2) * sc;
+      S.plane_bytes = (uint32_t)(S.conv_w * S.conv_h * 4);
+      const size_t ssmem = 2 * sstage + 6 * (size_t)S.plane_bytes + (srgb ? (size_t)ZOS_ENC2_N * FER * 4 : 0);  // two footprint buffers
+      bool oks = stotal > 0 && stotal < (1ull << 32) && ssmem <= 110 * 1024 &&
+                 make_map(ctx, &MS.m0, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, above.p0, above.w, above.h, above.pitch, batch, above.bstride, S.box_w, S.box_h);
+      if (oks && P.nv12) oks = make_map(ctx, &MS.m1, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, above.p1, cw, ch, above.cpitch, batch, above.cbstride, S.cbox_w, S.cbox_h);
+      if (oks && !P.nv12)
+        oks = make_map(ctx, &MS.m1, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, above.p1, cw, ch, above.cpitch, batch, above.cbstride, S.cbox_w, S.cbox_h) &&
+              make_map(ctx, &MS.m2, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, above.p2, cw, ch, above.cpitch, batch, above.cbstride, S.cbox_w, S.cbox_h);
+      if (oks) {
+        S.total_tiles = (uint32_t)stotal;
+        int per_sm = (int)((227 * 1024) / (ssmem + 1024 + 2560));
+        per_sm = per_sm < 1 ? 1 : (per_sm > SPEC_CTAS ? SPEC_CTAS : per_sm);
+        const uint64_t cap = (uint64_t)ctx->sm_count * per_sm;
+        const int grid = (int)(stotal < cap ? stotal : cap);
+        const bool bil = cp.sampling != ZOS_SAMPLE_NEAREST;
+#define ZOS_FS(B, S_, T)                                                                                         \
   do {                                                                                                            \
-    ensure_dyn_smem(ctx, k_frame_spec<B, S, T>, 110 * 1024);                                                        \
-    k_frame_spec<B, S, T><<<grid, SPEC_THREADS, ssmem, ctx->stream>>>(P, M);                                       \
+    ensure_dyn_smem(ctx, k_frame_spec<B, S_, T>, 110 * 1024);                                                       \
+    k_frame_spec<B, S_, T><<<grid, SPEC_THREADS, ssmem, ctx->stream>>>(S, MS);                                      \
   } while (0)
-      if (trk == 0) { if (bil) { if (srgb) ZOS_FS(true, true, 0); else ZOS_FS(true, false, 0); } else { if (srgb) ZOS_FS(false, true, 0); else ZOS_FS(false, false, 0); } }
-      else { if (bil) { if (srgb) ZOS_FS(true, true, 1); else ZOS_FS(true, false, 1); } else { if (srgb) ZOS_FS(false, true, 1); else ZOS_FS(false, false, 1); } }
+        if (trk == 0) { if (bil) { if (srgb) ZOS_FS(true, true, 0); else ZOS_FS(true, false, 0); } else { if (srgb) ZOS_FS(false, true, 0); else ZOS_FS(false, false, 0); } }
+        else { if (bil) { if (srgb) ZOS_FS(true, true, 1); else ZOS_FS(true, false, 1); } else { if (srgb) ZOS_FS(false, true, 1); else ZOS_FS(false, false, 1); } }
 #undef ZOS_FS
-      ctx->launches++;
-      *handled = true;
-      return check_cuda(ctx, cudaGetLastError(), "k_frame_spec launch");
+        ctx->launches++;
+        *handled = true;
+        return check_cuda(ctx, cudaGetLastError(), "k_frame_spec launch");
+      }
     }
     if (ok2 && fsmem <= 160 * 1024) {
       int per_sm = (int)((226 * 1024) / (fsmem + 1024 + 256));
