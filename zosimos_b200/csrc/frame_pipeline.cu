@@ -350,10 +350,11 @@ __device__ __forceinline__ float lds32(uint32_t a) {
 }
 
 // correctly rounded sRGB8 code of x in [0, 1], in byte 3 of the result (biased-key table, texel.cuh)
+template <int R = FER>
 __device__ __forceinline__ uint32_t srgb_code_b3(float x, uint32_t enc_lane) {
   const float y = x + ZOS_ENC2_BIAS;
   const int idx = max(__float_as_int(x), ZOS_ENC2_LOW);
-  const uint32_t a = (((__float_as_uint(y) >> 16) - (uint32_t)ZOS_ENC2_K0) * (FER * 4u)) + enc_lane;
+  const uint32_t a = (((__float_as_uint(y) >> 16) - (uint32_t)ZOS_ENC2_K0) * (R * 4u)) + enc_lane;
   uint32_t e;
   asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(a));
   return e + (uint32_t)idx;
@@ -565,6 +566,10 @@ __global__ void __launch_bounds__(THREADS, 4) k_frame_fast(const __grid_constant
 #endif
 constexpr int SPEC_CW = ZOS_SPEC_CW, SPEC_SW = ZOS_SPEC_SW, SPEC_CTAS = ZOS_SPEC_CTAS;  // conversion / sampling warps of a CTA, CTAs per SM
 constexpr int SPEC_C = SPEC_CW * 32, SPEC_THREADS = (SPEC_CW + SPEC_SW) * 32;
+#ifndef ZOS_SPEC_FER
+#define ZOS_SPEC_FER 2
+#endif
+constexpr int SFER = ZOS_SPEC_FER;  // copies of the encoder bucket table (8 copies measured the same as 2: the look-ups of the sampling warps are not what binds)
 // Tile height of this kernel.  Two footprints of a 32 x 32 tile are 85 KB of shared memory per CTA: two CTAs = 24 warps per SM.  Lower
 // tiles fit three CTAs but measured slower (config 4: 32 rows x 2 CTAs 0.131 of the HBM figure, 24 rows x 3 CTAs 0.117, 24 x 2 0.120,
 // 16 x 3 0.106): the per-tile work that does not shrink with the tile (geometry and loads by one thread, tap tables, hand-shakes)
@@ -597,9 +602,9 @@ __global__ void __launch_bounds__(SPEC_THREADS, SPEC_CTAS) k_frame_spec(const __
   const uint32_t conv_bytes = 3u * P.plane_bytes;
   uint32_t* enc = reinterpret_cast<uint32_t*>(dyn + 2 * (size_t)stage_bytes + 2 * (size_t)conv_bytes);
   if (SRGB_DST) {
-    for (int i = threadIdx.x; i < ZOS_ENC2_N * FER; i += SPEC_THREADS) enc[i] = g_tables.srgb_enc2[i / FER];
+    for (int i = threadIdx.x; i < ZOS_ENC2_N * SFER; i += SPEC_THREADS) enc[i] = g_tables.srgb_enc2[i / SFER];
   }
-  const uint32_t enc_lane = smem_u32(enc) + (threadIdx.x & (FER - 1)) * 4u;
+  const uint32_t enc_lane = smem_u32(enc) + (threadIdx.x & (SFER - 1)) * 4u;
   if (threadIdx.x == 0) {
     for (int k = 0; k < 2; k++) { mbar_init(&bar_yuv[k], 1); mbar_init(&bar_full[k], SPEC_CW); mbar_init(&bar_empty[k], SPEC_SW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -718,8 +723,8 @@ __global__ void __launch_bounds__(SPEC_THREADS, SPEC_CTAS) k_frame_spec(const __
                       bb = fminf(fmaxf(h ? f2_hi(b) : f2_lo(b), 0.0f), 1.0f);
           uint32_t t1, t2;
           if (SRGB_DST) {
-            t1 = __byte_perm(srgb_code_b3(rr, enc_lane), srgb_code_b3(g1, enc_lane), 0x0073);
-            t2 = __byte_perm(srgb_code_b3(bb, enc_lane), 0xffu, 0x0043);
+            t1 = __byte_perm(srgb_code_b3<SFER>(rr, enc_lane), srgb_code_b3<SFER>(g1, enc_lane), 0x0073);
+            t2 = __byte_perm(srgb_code_b3<SFER>(bb, enc_lane), 0xffu, 0x0043);
           } else {
             t1 = __byte_perm(__float_as_uint(rr * 255.0f + 8388608.0f), __float_as_uint(g1 * 255.0f + 8388608.0f), 0x0040);
             t2 = __byte_perm(__float_as_uint(bb * 255.0f + 8388608.0f), 0xffu, 0x0040);
@@ -778,8 +783,8 @@ __global__ void __launch_bounds__(SPEC_THREADS, SPEC_CTAS) k_frame_spec(const __
             r = fminf(fmaxf(r, 0.0f), 1.0f); gg = fminf(fmaxf(gg, 0.0f), 1.0f); b = fminf(fmaxf(b, 0.0f), 1.0f);
             uint32_t t1, t2;
             if (SRGB_DST) {
-              t1 = __byte_perm(srgb_code_b3(r, enc_lane), srgb_code_b3(gg, enc_lane), 0x0073);
-              t2 = __byte_perm(srgb_code_b3(b, enc_lane), 0xffu, 0x0043);
+              t1 = __byte_perm(srgb_code_b3<SFER>(r, enc_lane), srgb_code_b3<SFER>(gg, enc_lane), 0x0073);
+              t2 = __byte_perm(srgb_code_b3<SFER>(b, enc_lane), 0xffu, 0x0043);
             } else {
               t1 = __byte_perm(__float_as_uint(r * 255.0f + 8388608.0f), __float_as_uint(gg * 255.0f + 8388608.0f), 0x0040);
               t2 = __byte_perm(__float_as_uint(b * 255.0f + 8388608.0f), 0xffu, 0x0040);
@@ -911,7 +916,7 @@ zos_status launch_frame_pipeline(zos_ctx* ctx, const DevImage* below, const DevI
       const size_t sy = ((size_t)S.box_w * S.box_h + 127) & ~(size_t)127, sc = ((size_t)S.cbox_w * S.cbox_h * cstep + 127) & ~(size_t)127;
       const size_t sstage = sy + (P.nv12 ? 1 : 2) * sc;
       S.plane_bytes = (uint32_t)(S.conv_w * S.conv_h * 4);
-      const size_t ssmem = 2 * sstage + 6 * (size_t)S.plane_bytes + (srgb ? (size_t)ZOS_ENC2_N * FER * 4 : 0);  // two footprint buffers
+      const size_t ssmem = 2 * sstage + 6 * (size_t)S.plane_bytes + (srgb ? (size_t)ZOS_ENC2_N * SFER * 4 : 0);  // two footprint buffers
       bool oks = stotal > 0 && stotal < (1ull << 32) && ssmem <= 110 * 1024 &&
                  make_map(ctx, &MS.m0, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, above.p0, above.w, above.h, above.pitch, batch, above.bstride, S.box_w, S.box_h);
       if (oks && P.nv12) oks = make_map(ctx, &MS.m1, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, above.p1, cw, ch, above.cpitch, batch, above.cbstride, S.cbox_w, S.cbox_h);
