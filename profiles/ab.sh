@@ -13,7 +13,7 @@ for round in ${ROUNDS:-1 2}; do
       python - <<PY
 import json
 d=json.loads(open("$f").read().strip().splitlines()[-1])
-rows=[(d["config"]["workload"],d)]+list(d.get("workloads",{}).items())
+rows=list({d["config"]["workload"]: d, **d.get("workloads",{})}.items())
 print("%-22s %-9s %d"%("$(basename $which .so)","$mode",$round), "  ".join("%s %.4f (%s MHz, %s W)"%(n,r["roofline"]["frac"],r["clocks"]["sm_mhz"],r["clocks"].get("power_w_max")) for n,r in rows if "roofline" in r))
 PY
     done
