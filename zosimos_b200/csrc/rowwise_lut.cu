@@ -64,6 +64,38 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   return v;
 }
 
+// Streaming 16-byte accesses of the linear path.  ZOS_LUT_LDST selects the cache operators; measured side by side on one box
+// (gpurun_out/ab8_*, c2_blend burst / sustained): 0 = .cs both ways 0.918 / 0.828, 1 = ld.global.nc.L1::no_allocate 0.921 / 0.829,
+// 2 = ld.global.L1::no_allocate 0.922 / 0.829, 3 = .cg both ways (L2 only) 0.949 / 0.831 -- the kernel's busiest unit is the L1 data
+// pipe (look-ups AND global accesses), and .cg takes the global share of it down.  (On a second box: burst 0.903 -> 0.908 for the blend,
+// 0.884 -> 0.908 for the RGBA8 conversion, sustained unchanged at 0.78: that chip is power-bound at 1.51 GHz.  The same change made
+// k_affine_f16 slower, 0.908 -> 0.878 sustained for the nearest variant, and did nothing for k_rowwise_rgb10: both keep .cs.)
+#ifndef ZOS_LUT_LDST
+#define ZOS_LUT_LDST 3
+#endif
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+#if ZOS_LUT_LDST == 0
+  return __ldcs(p);
+#elif ZOS_LUT_LDST == 1
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+#elif ZOS_LUT_LDST == 2
+  uint4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+#else
+  return __ldcg(p);
+#endif
+}
+__device__ __forceinline__ void st_stream(uint4* p, uint4 v) {
+#if ZOS_LUT_LDST == 3
+  __stcg(p, v);
+#else
+  __stcs(p, v);
+#endif
+}
+
 struct LutCtx {
   uint32_t lane4;    // (lane & 31) * 4, upper bytes zero: byte 0 of every look-up address
   uint32_t sr, sg, sb, sa;  // byte-permute selectors building (code << 8) | lane4 for R, G, B, A of a source word
@@ -242,21 +274,21 @@ __global__ void __launch_bounds__(LUT_THREADS, 1) k_rowwise_lut(const __grid_con
     for (int j = 0; j < D; j++) b[j] = a[j] = make_uint4(0, 0, 0, 0);
 #pragma unroll
     for (int j = 0; j < D - 1; j++)
-      if ((uint32_t)j < mine) { b[j] = __ldcs(pb + (size_t)j * stride); if (MODE) a[j] = __ldcs(pa + (size_t)j * stride); }
+      if ((uint32_t)j < mine) { b[j] = ld_stream(pb + (size_t)j * stride); if (MODE) a[j] = ld_stream(pa + (size_t)j * stride); }
 #define ZOS_LUT_GROUP(B, A, OUT)                                                        \
     {                                                                                   \
       uint4 o_;                                                                         \
       pixel8x2<SK, DK, MODE, NMAT>(P, B.x, B.y, A.x, A.y, c, o_.x, o_.y);               \
       pixel8x2<SK, DK, MODE, NMAT>(P, B.z, B.w, A.z, A.w, c, o_.z, o_.w);               \
-      __stcs(OUT, o_);                                                                  \
+      st_stream(OUT, o_);                                                               \
     }
     for (uint32_t k = 0;; k += D) {
 #pragma unroll
       for (int j = 0; j < D; j++) {
         if (k + j >= mine) return;
         if (k + j + (D - 1) < mine) {
-          b[(j + D - 1) % D] = __ldcs(pb + (size_t)(j + D - 1) * stride);
-          if (MODE) a[(j + D - 1) % D] = __ldcs(pa + (size_t)(j + D - 1) * stride);
+          b[(j + D - 1) % D] = ld_stream(pb + (size_t)(j + D - 1) * stride);
+          if (MODE) a[(j + D - 1) % D] = ld_stream(pa + (size_t)(j + D - 1) * stride);
         }
         ZOS_LUT_GROUP(b[j], a[j], pd + (size_t)j * stride);
       }
