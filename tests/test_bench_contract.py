@@ -62,3 +62,28 @@ def test_gpu_arm_parameters_come_from_the_product_host_layer():
     W, Hh, ang = 7680, 4320, float(np.deg2rad(30.0))
     m = (O.shift(W / 2, Hh / 2) @ O.rotate(ang) @ O.shift(-W / 2, -Hh / 2))
     assert np.abs(m - H.rotation_about(W / 2, Hh / 2, ang)).max() < 1e-3  # f32 left multiplications vs one f64 product
+
+
+def test_every_workload_has_one_config_for_both_arms_and_a_cpu_leg():
+    """`config` of the JSON line is arm independent (the driver compares the two arms' dicts), every workload of the default run has one,
+    and the CPU side (cpu_baseline leg, --impl reference) can run each of them: one bounded oracle sample per workload."""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.ALL_WORKLOADS[0] == bench.HEADLINE == "c2_blend"
+    for name in bench.ALL_WORKLOADS + ["band_affine"]:
+        cfg = bench.workload_config(name)
+        assert cfg == bench.workload_config(name) and cfg["workload"] == name and cfg["what"] and cfg["l2"] and cfg["parity"]
+        assert name in bench.DEFAULT_FRAMES
+    for name in bench.ALL_WORKLOADS:
+        r = bench.cpu_baseline_child(name, budget_s=0.01)
+        assert r["value"] > 0 and r["kind"] == "port" and r["cores"] >= 1 and r["unit"] == ("fps" if name == "loop_rs" else "MP/s"), (name, r)
+
+
+def test_reference_arm_honours_workload():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c5_rgb10a2", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json_lines(out.stdout)[0]
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["config"] == bench.workload_config("c5_rgb10a2") and line["impl"] == "reference" and line["value"] > 0
