@@ -113,6 +113,10 @@ const char* zos_last_error(const zos_ctx* ctx); /* ctx may be NULL: last error o
 int32_t zos_ctx_device(const zos_ctx* ctx);
 void* zos_ctx_stream(const zos_ctx* ctx);       /* the cudaStream_t all launches of this ctx go to */
 zos_status zos_sync(zos_ctx* ctx);             /* SyncPoint::block_on, run.rs:3019 */
+/* SyncPoint::finish (run.rs:3041-3169, tests/async.rs): the non-blocking form.  *done = 1 when everything enqueued on the context has
+ * finished (a kernel fault is reported like zos_sync does), 0 while work is still running; an asynchronous host polls this between
+ * yields instead of blocking a thread in zos_sync. */
+zos_status zos_poll(zos_ctx* ctx, int32_t* done);
 /* Verification hook, host only (no context, no GPU): the rounding thresholds of the correctly rounded sRGB8
  * encoder (thr[k] = smallest f32 whose code is >= k; [0] = -inf, [256..259] = +inf) and the two bucket tables
  * the kernels derive from them (zosimos_b200/csrc/texel.cuh).  Arrays may be NULL; buckets holds up to 2048

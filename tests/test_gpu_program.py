@@ -689,3 +689,37 @@ def test_descriptor_as_gpu_texture(pool, kind):  # tests/color_support.rs: input
     assert (out_desc.texel, out_desc.color, out_desc.size()) == (desc.texel, desc.color, desc.size())
     img, _ = run_once_with_output(c, pool, [(inp, key)], output)
     assert img.as_bytes().size == 4 * 4 * desc.layout.texel_stride and not img.as_bytes().any()
+
+
+def test_step_async(pool, images, fixtures):
+    """tests/async.rs: the affine pipeline of blend.rs driven through `SyncPoint::finish` (asyncio here, tokio there) -- 'using the
+    same as synchronous code in blend on purpose', so the same golden and the same bytes as test_run_affine."""
+    import asyncio
+    bg, fg = images
+    W, H = bg.layout().width, bg.layout().height
+    fw, fh = fg.layout().width, fg.layout().height
+    c = CommandBuffer()
+    affine = Affine.new(AffineSample.Nearest).shift(-float(fw // 2), -float(fh // 2)).rotate(np.float32(np.pi) / np.float32(4)).shift(float(W // 2), float(H // 2))
+    background, foreground = c.input(bg.descriptor()), c.input(fg.descriptor())
+    output, _ = c.output(c.affine(background, affine, foreground))
+    executable = Linker.from_included().compile(c).lower_to(Capabilities.from_device(next(pool.iter_devices())))
+    polled = []
+
+    async def run():
+        env = executable.from_pool(pool)
+        env.bind(background, bg.key()); env.bind(foreground, fg.key())
+        env.recover_buffers()
+        execution = executable.launch(env)
+        pool.clear_cache()
+        while execution.is_running():
+            await execution.step().finish(lambda gpu: polled.append(gpu) or object())
+        retire = execution.retire_gracefully(pool)
+        key = retire.output(output).key()
+        retire.retire_buffers(); retire.finish()
+        return key
+    key = asyncio.run(run())
+    img = pool.entry(key)
+    assert polled and O.blockhash256(rgba(img)) in hashes()["affine"]
+    exp = O.affine(oracle_image(bg.descriptor(), fixtures["background"]), np.array(affine.transformation, np.float32).reshape(3, 3),
+                   oracle_image(fg.descriptor(), fixtures["foreground"]), 0)
+    assert np.array_equal(img.as_bytes(), exp.data.reshape(-1))

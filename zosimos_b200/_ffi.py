@@ -129,6 +129,7 @@ SIGNATURES = {
     "zos_program_bind": (C.c_int32, [_P, C.c_int32, C.POINTER(ZosImage)]),
     "zos_program_unbind": (C.c_int32, [_P, C.c_int32]),
     "zos_program_set_knob": (C.c_int32, [_P, C.c_uint32, _P, C.c_uint64]),
+    "zos_poll": (C.c_int32, [_P, C.POINTER(C.c_int32)]),
     "zos_program_reset_knobs": (C.c_int32, [_P]),
     "zos_multi_launch": (C.c_int32, [C.POINTER(_P), C.c_uint32, C.c_uint32]),
     "zos_multi_sync": (C.c_int32, [C.POINTER(_P), C.c_uint32]),

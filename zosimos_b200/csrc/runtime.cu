@@ -398,6 +398,17 @@ zos_status zos_sync(zos_ctx* ctx) {
   return st;
 }
 
+zos_status zos_poll(zos_ctx* ctx, int32_t* done) {
+  if (!ctx || !done) return ZOS_ERR_INVALID;
+  *done = 0;
+  cudaSetDevice(ctx->device);
+  const cudaError_t e = cudaStreamQuery(ctx->stream);
+  if (e == cudaErrorNotReady) return ZOS_OK;
+  if (e != cudaSuccess) return check_cuda(ctx, e, "cudaStreamQuery");
+  *done = 1;
+  return zos_sync(ctx);  // nothing left to wait for: picks up the kernels' fault word
+}
+
 zos_status zos_buf_alloc(zos_ctx* ctx, uint64_t bytes, zos_buf** out) {
   if (!ctx || !out) return ZOS_ERR_INVALID;
   *out = nullptr;

@@ -44,6 +44,12 @@ class Context:
     def sync(self):
         self.check(self._lib.zos_sync(self.handle))
 
+    def poll(self) -> bool:
+        """zos_poll: True once everything enqueued on this context has finished; never blocks."""
+        done = C.c_int32(0)
+        self.check(self._lib.zos_poll(self.handle, C.byref(done)))
+        return bool(done.value)
+
     def arena_stats(self) -> dict:
         """zos_ctx_arena_stats: cudaMalloc calls so far, allocations served from parked blocks, bytes held / in use / parked."""
         st = _ffi.ZosArenaStats()

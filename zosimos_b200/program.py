@@ -478,6 +478,18 @@ class SyncPoint:
     def block_on(self):
         self._ctx.sync()
 
+    async def finish(self, queue_poll=None):
+        """run.rs:3041-3169 (tests/async.rs): step towards the synchronisation point without blocking the thread.  `queue_poll`, if given, is
+        called with the device context and may return a guard object that is dropped when the wait is over (the reference's callers
+        schedule their device polling there; CUDA needs none -- the stream is queried between yields to the event loop)."""
+        import asyncio
+        guard = queue_poll(self._ctx) if queue_poll is not None else None
+        try:
+            while not self._ctx.poll():
+                await asyncio.sleep(0)
+        finally:
+            del guard
+
 
 class Execution:
     """run.rs:211-260."""
