@@ -300,6 +300,37 @@ def test_affine_bilinear_f16(ctx, use_tma, angle, scale):
     assert np.array_equal(got2, tex.astype(np.float16))
 
 
+def test_affine_f16_any_rotation_equals_general_kernel(ctx):
+    """Round 2: k_affine_f16 sizes its staged box per mapping (pick_box_width: whichever of 8 widths puts the taps of a row on the
+    fewest bank conflicts), so the box geometry differs from launch to launch.  Twenty random rotations / anisotropic scales / shifts,
+    both samplings: the dedicated kernel must keep producing the general gather kernel's bytes."""
+    W, H, w, h = 400, 260, 330, 210
+    rng = np.random.default_rng(2024)
+    a16 = rng.random((h, w, 4), dtype=np.float32).astype(np.float16)
+    b16 = rng.random((H, W, 4), dtype=np.float32).astype(np.float16)
+    t = Texel.new_f16(); c = Color.Rgb(Z.Primaries.Bt709, Transfer.Linear)
+    da, dbb = zdesc(w, h, t, c), zdesc(W, H, t, c)
+    below, above, dst = ctx.upload(dbb, b16.view(np.uint8)), ctx.upload(da, a16.view(np.uint8)), ctx.image(dbb)
+    widths = set()
+    for k in range(20):
+        ang, sx, sy = rng.uniform(-np.pi, np.pi), rng.uniform(0.6, 1.8), rng.uniform(0.6, 1.8)
+        m = (O.shift(W / 2 + rng.uniform(-20, 20), H / 2 + rng.uniform(-20, 20)) @ O.rotate(ang) @ O.scale(sx, sy) @ O.shift(-w / 2, -h / 2)).astype(np.float32)
+        inv = O.inv3(m.astype(np.float64)).astype(np.float32)
+        ex = 31 * (abs(inv[0, 0]) + abs(inv[0, 1]))
+        widths.add(int(_ffi.lib().zos_affine_box_width(int(np.ceil(ex)) + 5, float(inv[0, 0]), float(inv[1, 0]))) - (int(np.ceil(ex)) + 5))
+        for sampling in (_ffi.SAMPLE_NEAREST, _ffi.SAMPLE_BILINEAR):
+            res = []
+            for flags in (0, 1):
+                ctx.set_flags(flags)
+                ops.compose(ctx, below, above, dst, ops.compose_params(map=_ffi.MAP_AFFINE, sampling=sampling, inv=inv, use_tma=True))
+                res.append(dst.download())
+            ctx.set_flags(0)
+            assert np.array_equal(res[0], res[1]), (k, ang, sx, sy, sampling)
+    assert len(widths) >= 3  # the rule really picked different paddings over the sample
+    for im in (below, above, dst):
+        im.free()
+
+
 @pytest.mark.parametrize("sampling", [_ffi.SAMPLE_NEAREST, _ffi.SAMPLE_BILINEAR])
 @pytest.mark.parametrize("with_below", [False, True])
 def test_affine_f16_special_values_equal_general_kernel(ctx, sampling, with_below):
