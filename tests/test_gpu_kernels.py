@@ -796,6 +796,45 @@ def test_frame_fast_placements_equal_general_kernels(ctx, tgt):
     assert not np.array_equal(res[0][0], bg.download())  # the frame was drawn
 
 
+def test_frame_spec_equals_fast_and_general_on_random_jobs(ctx):
+    """Round 2: k_frame_spec (conversion and sampling on different warps, two footprint buffers, mbarrier hand-over) against k_frame_fast
+    (ZOS_CTX_FRAME_FAST_ONLY) and the general kernels (ZOS_CTX_NO_FAST_PATHS) on sixteen random jobs: frame and canvas sizes, scale
+    factors on both sides of 1, placements that leave uncovered and partly covered tiles, nearest and bilinear, I420 and NV12, sRGB8
+    and unorm8 destinations, 1-5 frames (more tiles than CTAs, and fewer)."""
+    rng = np.random.default_rng(4242)
+    M = O.mul3(O.inv3(O.to_xyz("bt709", "D65")), O.to_xyz("bt2020", "D65"))
+    for job in range(16):
+        W, H = 2 * int(rng.integers(40, 260)), 2 * int(rng.integers(30, 150))
+        w, h = int(rng.integers(33, 400)), int(rng.integers(20, 250))
+        N = int(rng.integers(1, 6))
+        nv12 = bool(rng.integers(0, 2))
+        sampling = _ffi.SAMPLE_BILINEAR if rng.integers(0, 2) else _ffi.SAMPLE_NEAREST
+        srgb = bool(rng.integers(0, 2))
+        tw, th = int(rng.integers(max(8, w // 3), w + 1)), int(rng.integers(max(8, h // 3), h + 1))
+        if tw * 4 < W or th * 4 < H:  # stay out of strong minification (that is the general kernel's job anyway)
+            tw, th = max(tw, (W + 3) // 4 + 1), max(th, (H + 3) // 4 + 1)
+        tw, th = min(tw, w), min(th, h)
+        tx, ty = int(rng.integers(0, w - tw + 1)), int(rng.integers(0, h - th + 1))
+        d = Z.yuv420_descriptor(W, H, Color.Rgb(Z.Primaries.Bt2020, Transfer.Bt709), Z.YuvMatrix.Bt709, False, nv12, 0)
+        ys = rng.integers(16, 236, (N, H, W), dtype=np.uint8)
+        us = rng.integers(16, 241, (N, H // 2, W // 2), dtype=np.uint8); vs = rng.integers(16, 241, (N, H // 2, W // 2), dtype=np.uint8)
+        src = ctx.image(d, N)
+        src.upload((ys, np.stack([us, vs], -1).reshape(N, H // 2, W) if nv12 else us, None if nv12 else vs))
+        od = zdesc(w, h, Texel.new_u8(SampleParts.RgbA), Color.SRGB if srgb else Color.Rgb(Z.Primaries.Bt709, Transfer.Linear))
+        bg = ctx.upload(od, rng.integers(0, 256, (h, w * 4), dtype=np.uint8))
+        res = []
+        for flags in (0, 2, 1):
+            ctx.set_flags(flags)
+            dst = ctx.image(od, N)
+            p = ops.compose_params(map=_ffi.MAP_RECT, sampling=sampling, blend=_ffi.BLEND_SRC_OVER, sel=(0, 0, W, H), tgt=(tx, ty, tw, th), src_steps=[ops.matrix(M)])
+            ops.compose(ctx, bg, src, dst, p)
+            res.append(dst.download())
+            dst.free()
+        ctx.set_flags(0)
+        assert np.array_equal(res[0], res[1]) and np.array_equal(res[0], res[2]), (job, W, H, w, h, N, nv12, sampling, srgb, (tx, ty, tw, th))
+        src.free(); bg.free()
+
+
 @pytest.mark.parametrize("bits,parts,n", [(SampleBits.UInt16, SampleParts.Luma, 16), (SampleBits.UInt1010102, SampleParts.RgbA, 10),
                                          (SampleBits.UInt565, SampleParts.Rgb, 6), (SampleBits.UInt4x4, SampleParts.RgbA, 4)])
 def test_field_division_exact_all_codes(ctx, bits, parts, n):
