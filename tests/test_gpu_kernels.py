@@ -796,6 +796,42 @@ def test_frame_fast_placements_equal_general_kernels(ctx, tgt):
     assert not np.array_equal(res[0][0], bg.download())  # the frame was drawn
 
 
+def test_u8_compose_random_placements_equal_general_kernels(ctx):
+    """The packed pair code of k_rowwise_lut (round 2) and k_copy_linear on twenty random compositions: canvas and layer sizes (widths that
+    are and are not multiples of 4), placements at aligned and odd offsets, source-over and overwrite, sRGB8 and unorm8, 1-3 frames --
+    against the general kernels, byte for byte, and against the oracle for the blends."""
+    rng = np.random.default_rng(777)
+    for job in range(20):
+        W, H = int(rng.integers(16, 700)), int(rng.integers(8, 90))
+        aw, ah = int(rng.integers(4, W + 1)), int(rng.integers(2, H + 1))
+        tx, ty = int(rng.integers(0, W - aw + 1)), int(rng.integers(0, H - ah + 1))
+        if rng.integers(0, 2):
+            tx &= ~3
+        N = int(rng.integers(1, 4))
+        color = Color.SRGB if rng.integers(0, 2) else Color.Rgb(Z.Primaries.Bt709, Transfer.Linear)
+        blend = _ffi.BLEND_SRC_OVER if rng.integers(0, 3) else _ffi.BLEND_OVERWRITE
+        if rng.integers(0, 4) == 0:
+            aw, ah, tx, ty = W, H, 0, 0  # full cover: the linear paths
+        db, da = zdesc(W, H, Texel.new_u8(SampleParts.RgbA), color), zdesc(aw, ah, Texel.new_u8(SampleParts.RgbA), color)
+        b = rng.integers(0, 256, (N, H, W * 4), dtype=np.uint8); a = rng.integers(0, 256, (N, ah, aw * 4), dtype=np.uint8)
+        a.reshape(N, ah, aw, 4)[:, ::3, ::2, 3] = 0; a.reshape(N, ah, aw, 4)[:, 1::3, ::5, 3] = 255
+        below, above = ctx.image(db, N), ctx.image(da, N)
+        below.upload(b); above.upload(a)
+        res = []
+        for flags in (0, 1):
+            ctx.set_flags(flags)
+            dst = ctx.image(db, N)
+            ops.compose(ctx, below, above, dst, ops.compose_params(blend=blend, sel=(0, 0, aw, ah), tgt=(tx, ty, aw, ah)))
+            res.append(dst.download().reshape(N, H, W * 4))
+            dst.free()
+        ctx.set_flags(0)
+        assert np.array_equal(res[0], res[1]), (job, W, H, aw, ah, tx, ty, N, blend)
+        if blend == _ffi.BLEND_SRC_OVER:
+            exp = O.blend(oracle_image(db, b[0]), (tx, ty, tx + aw, ty + ah), oracle_image(da, a[0]), 3).data
+            assert np.array_equal(res[0][0], exp)
+        below.free(); above.free()
+
+
 def test_frame_spec_equals_fast_and_general_on_random_jobs(ctx):
     """Round 2: k_frame_spec (conversion and sampling on different warps, two footprint buffers, mbarrier hand-over) against k_frame_fast
     (ZOS_CTX_FRAME_FAST_ONLY) and the general kernels (ZOS_CTX_NO_FAST_PATHS) on sixteen random jobs: frame and canvas sizes, scale
