@@ -100,5 +100,61 @@ def main():
         dist.destroy_process_group()
 
 
+def single_process(ndev):
+    """The same traffic from ONE process that owns a context on each of `ndev` devices ('one process with 8 contexts
+    vs 8 processes'): copies are issued round robin over the devices' lanes from one host thread."""
+    import glob
+    import torch
+    cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "cuda_runtime", "lib", "libcudart.so*")) + ["libcudart.so.12"]
+    rt = C.CDLL(cands[0])
+    rt.cudaHostAlloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t, C.c_uint]
+    rt.cudaMalloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+    rt.cudaMemcpyAsync.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+    rt.cudaStreamCreate.argtypes = [C.POINTER(C.c_void_p)]
+    rt.cudaStreamSynchronize.argtypes = [C.c_void_p]
+    FB, LANES = 3840 * 2160 * 4, 3
+
+    def chk(e):
+        if e != 0:
+            raise RuntimeError("cuda error %d" % e)
+    lanes = []
+    for dev in range(ndev):
+        chk(rt.cudaSetDevice(dev))
+        for _ in range(LANES):
+            s, hin, hout, din, dout = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+            chk(rt.cudaStreamCreate(C.byref(s)))
+            chk(rt.cudaHostAlloc(C.byref(hin), 2 * FB, 1)); chk(rt.cudaHostAlloc(C.byref(hout), FB, 1))  # 1 = portable: pinned for every context
+            C.memset(hin, 1, 2 * FB); C.memset(hout, 1, FB)
+            chk(rt.cudaMalloc(C.byref(din), 2 * FB)); chk(rt.cudaMalloc(C.byref(dout), FB))
+            lanes.append((dev, s, hin, hout, din, dout))
+
+    def run(mode, n):
+        for l in lanes:
+            chk(rt.cudaSetDevice(l[0])); chk(rt.cudaStreamSynchronize(l[1]))
+        t0 = time.perf_counter()
+        for i in range(n):
+            for k in range(ndev):  # one frame on every device per round
+                dev, s, hin, hout, din, dout = lanes[k * LANES + i % LANES]
+                chk(rt.cudaSetDevice(dev))
+                if mode in ("h2d", "both"):
+                    chk(rt.cudaMemcpyAsync(din, hin, 2 * FB, 1, s))
+                if mode in ("d2h", "both"):
+                    chk(rt.cudaMemcpyAsync(hout, dout, FB, 2, s))
+        for l in lanes:
+            chk(rt.cudaSetDevice(l[0])); chk(rt.cudaStreamSynchronize(l[1]))
+        return time.perf_counter() - t0
+    out = {"n_gpus": ndev, "single_process": True, "frame_bytes": FB}
+    for mode, per in (("h2d", 2 * FB), ("d2h", FB), ("both", 3 * FB)):
+        run(mode, 12)
+        n = 240
+        dt = run(mode, n)
+        out[mode + "_gbs_aggregate"] = round(per * n * ndev / dt / 1e9, 1)
+    out["c2_blend_e2e_ceiling_mps"] = round(out["both_gbs_aggregate"] * 1e9 / 12 / 1e6, 0)
+    print(json.dumps(out), flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 2 and sys.argv[1] == "--single-process":
+        single_process(int(sys.argv[2]))
+    else:
+        main()
