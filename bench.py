@@ -15,7 +15,10 @@ samples inside the region.  Frames are independent: with N GPUs every rank owns 
 collective on the data path).
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
-  roofline     algorithmic bytes per launch / CUDA-event kernel time vs the measured HBM peak
+  roofline     algorithmic bytes per launch / CUDA-event kernel time vs the measured HBM peak; .burst = the same over the ten
+               launches of the calibration (full SM clock), .traffic / .limiter = DRAM bytes and busiest unit from the committed
+               ncu capture of this command (profiles/kernel_facts.json)
+  gather       (N > 1) the optional collective of the path, timed alone: zos_gather_nccl of one output frame per rank
   cpu_baseline the CPU oracle (restatement of the reference pipeline; kind "port") on host cores
   e2e          the same metric through host buffers: pinned H2D of the layers + kernel + D2H (C-ABI calls)
   e2e_program  the same through the reference-shaped Program API (Executable.launch -> step -> Retire.output)
